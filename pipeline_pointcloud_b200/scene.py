@@ -1,0 +1,58 @@
+"""Seeded synthetic scenes for parity tests and benchmarks.
+
+Mirrors gsplat's ``init_type="random"`` initialisation: a cube of random Gaussians
+viewed from cameras on a circle, OpenCV convention (+z forward, world->camera
+``viewmats``).  Everything is generated on the CPU from ``torch.Generator().manual_seed``
+so the CPU oracle and the GPU path see identical bits.
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict
+
+import torch
+
+SH_C0 = 0.2820947917738781
+
+
+def look_at_viewmat(eye: torch.Tensor, target: torch.Tensor, up: torch.Tensor) -> torch.Tensor:
+    """World->camera 4x4 with +z forward, +x right, +y down."""
+    fwd = target - eye
+    fwd = fwd / fwd.norm()
+    right = torch.linalg.cross(fwd, up)
+    right = right / right.norm()
+    down = torch.linalg.cross(fwd, right)
+    R = torch.stack([right, down, fwd], dim=0)          # rows = camera axes in world coords
+    V = torch.eye(4, dtype=torch.float32)
+    V[:3, :3] = R
+    V[:3, 3] = -R @ eye
+    return V
+
+
+def make_cameras(C: int, width: int, height: int, extent: float = 3.0, focal_frac: float = 0.74) -> Dict[str, torch.Tensor]:
+    viewmats = []
+    for c in range(C):
+        ang = 2.0 * math.pi * c / max(C, 1) + 0.3
+        eye = torch.tensor([2.3 * extent * math.cos(ang), 2.3 * extent * math.sin(ang), 0.5 * extent])
+        viewmats.append(look_at_viewmat(eye, torch.zeros(3), torch.tensor([0.0, 0.0, 1.0])))
+    f = focal_frac * width
+    K = torch.tensor([[f, 0.0, width / 2.0], [0.0, f, height / 2.0], [0.0, 0.0, 1.0]], dtype=torch.float32)
+    return {"viewmats": torch.stack(viewmats), "Ks": K[None].repeat(C, 1, 1).contiguous()}
+
+
+def make_scene(N: int, sh_degree: int, C: int, width: int, height: int, seed: int = 0,
+               extent: float = 3.0) -> Dict[str, torch.Tensor]:
+    """Returns post-activation tensors with the argument names of ``rasterization()``."""
+    g = torch.Generator().manual_seed(seed)
+    K = (sh_degree + 1) ** 2
+    means = extent * (2.0 * torch.rand(N, 3, generator=g) - 1.0)
+    base = math.log(0.6 * (8.0 * extent ** 3 / N) ** (1.0 / 3.0))
+    scales = torch.exp(base + 0.3 * torch.randn(N, 3, generator=g))
+    quats = torch.randn(N, 4, generator=g)
+    opacities = torch.sigmoid(1.5 * torch.randn(N, generator=g))
+    sh0 = (torch.rand(N, 1, 3, generator=g) - 0.5) / SH_C0
+    shN = 0.05 * torch.randn(N, K - 1, 3, generator=g)
+    colors = torch.cat([sh0, shN], dim=1).contiguous()
+    out = {"means": means, "quats": quats, "scales": scales, "opacities": opacities, "colors": colors}
+    out.update(make_cameras(C, width, height, extent))
+    return out
