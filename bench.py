@@ -1,0 +1,367 @@
+#!/usr/bin/env python
+"""bench.py -- fwd+bwd throughput of the rasterization() hot path (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference] [--workload config3|config2|tiny]
+
+A "step" is one `rasterization()` forward + backward (random cotangent) over one camera of the synthetic
+config-3 scene (5.8 M random Gaussians, SH degree 3, 1297x840, antialiased), inputs resident in HBM.
+N > 1 (torchrun): camera data-parallel, one camera per rank per step on replicated Gaussians followed by the
+dense-gradient all-reduce over NCCL (config 4; weak scaling: per-GPU work fixed).
+`value` = Mpix/s of the whole job (C*W*H*steps / time, max over ranks); `iters_per_s` is reported beside it.
+`e2e` = the same step driven from pinned HOST buffers: H2D of every input, the step, D2H of render, alpha and
+every gradient, all inside the timed region.
+`--impl reference` times the CPU oracle (the restated reference torch path) on a bounded sub-frustum sample
+of the same workload on the host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (N, sh_degree, W, H, rasterize_mode)
+    "config3": (5_800_000, 3, 1297, 840, "antialiased"),
+    "config2": (1_000_000, 3, 800, 800, "classic"),
+    "config1": (100_000, 0, 256, 256, "classic"),
+    "tiny": (50_000, 3, 320, 240, "antialiased"),
+}
+METRIC = "3DGS rasterization fwd+bwd throughput"
+UNIT = "Mpix/s"
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+# ----------------------------------------------------------------------------------------------------------
+# clocks sampler (nvidia-smi during the timed region)
+# ----------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 6:
+                continue
+            try:
+                sm.append(float(f[0])); mx = float(f[1])
+            except ValueError:
+                continue
+            for n, v in zip(names, f[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------------------------------------
+# algorithmic bytes per stage (DESIGN.md "Measurement")
+# ----------------------------------------------------------------------------------------------------------
+def algorithmic_bytes(N, C, V, I, P, K, n_tiles, key_bits):
+    M = C * N
+    p = math.ceil(key_bits / 8)
+    return {
+        "project_fwd": N * 44 + V * 12 * K + M * 52,               # params + SH rows of visible + all per-pair outputs
+        "isect_scan": M * 8,
+        "isect_fill": M * 20 + I * 12,
+        "isect_sort": I * 12 * 2 * p + I * 8,                        # LSD radix model; single-pass ideal = I*24
+        "isect_offsets": I * 8 + 4 * n_tiles,
+        "composite_fwd": I * 40 + P * 24,
+        "composite_bwd": I * 40 + P * 28 + I * 36,
+        "project_bwd": N * 44 + M * 4 + V * (36 + 12 * K) + N * 44 + N * 12 * K,
+    }
+
+
+# ----------------------------------------------------------------------------------------------------------
+# CPU baseline: the oracle on a bounded sub-frustum sample of the same workload
+# ----------------------------------------------------------------------------------------------------------
+def cpu_sample_inputs(scene, W, H, win_w=160, win_h=96):
+    """Central win_w x win_h window of the workload's camera 0 and the Gaussians whose 3-sigma footprint can
+    reach it (selected with a cheap bound, outside the timed region).  All stages then scale by the same
+    factor, so Mpix/s of the sample is comparable with the full frame."""
+    V, K = scene["viewmats"][0], scene["Ks"][0]
+    x0, y0 = (W - win_w) // 2 // 16 * 16, (H - win_h) // 2 // 16 * 16
+    t = scene["means"] @ V[:3, :3].T + V[:3, 3]
+    z = t[:, 2].clamp_min(1e-6)
+    px, py = K[0, 0] * t[:, 0] / z + K[0, 2], K[1, 1] * t[:, 1] / z + K[1, 2]
+    rad = 3.0 * scene["scales"].max(dim=1).values * K[0, 0] / z + 3.0
+    keep = (t[:, 2] > 0.01) & (px + rad > x0) & (px - rad < x0 + win_w) & (py + rad > y0) & (py - rad < y0 + win_h)
+    sub = {k: scene[k][keep].clone() for k in ("means", "quats", "scales", "opacities", "colors")}
+    Kc = K.clone()
+    Kc[0, 2] -= x0
+    Kc[1, 2] -= y0
+    sub["viewmats"], sub["Ks"] = V[None].clone(), Kc[None]
+    return sub, win_w, win_h, int(keep.sum())
+
+
+def cpu_oracle_step(sub, w, h, sh_degree, mode, v_r, v_a):
+    from oracle import torch_oracle as O   # the reference arm / cpu_baseline leg: the one place bench.py runs oracle/
+    leaves = [sub[k].clone().requires_grad_() for k in ("means", "quats", "scales", "opacities", "colors")]
+    r, a, m = O.rasterization(*leaves, sub["viewmats"], sub["Ks"], w, h, sh_degree=sh_degree, packed=False,
+                              rasterize_mode=mode)
+    torch.autograd.backward([r, a], [v_r, v_a])
+    return m["isect_ids"].numel()
+
+
+def run_cpu(workload, steps, warmup, seed=0):
+    from pipeline_pointcloud_b200.scene import make_scene
+    N, deg, W, H, mode = WORKLOADS[workload]
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    scene = make_scene(N, deg, 1, W, H, seed=seed)
+    sub, w, h, n_sub = cpu_sample_inputs(scene, W, H)
+    g = torch.Generator().manual_seed(seed + 1)
+    v_r, v_a = torch.rand(1, h, w, 3, generator=g), torch.rand(1, h, w, 1, generator=g)
+    for _ in range(warmup):
+        cpu_oracle_step(sub, w, h, deg, mode, v_r, v_a)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        n_is = cpu_oracle_step(sub, w, h, deg, mode, v_r, v_a)
+    dt = time.perf_counter() - t0
+    mpix = w * h * steps / dt / 1e6
+    sample = (f"{steps} fwd+bwd step(s) of the CPU oracle on a sub-frustum of {workload}: central {w}x{h} window "
+              f"({(w // 16) * (h // 16)} of {math.ceil(W / 16) * math.ceil(H / 16)} tiles) with the {n_sub} of {N} Gaussians "
+              f"that can reach it ({n_is} tile intersections); {cores} torch threads")
+    model = ""
+    try:
+        model = [l.split(":", 1)[1].strip() for l in open("/proc/cpuinfo") if l.startswith("model name")][0]
+    except Exception:
+        pass
+    return {"value": mpix, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample, "cpu_model": model,
+            "s_per_step": dt / steps, "iters_per_s_full_frame_equiv": mpix * 1e6 / (W * H)}
+
+
+# ----------------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b2s", choices=["b2s", "reference"])
+    ap.add_argument("--workload", default=os.environ.get("B2S_BENCH_WORKLOAD", "config3"), choices=sorted(WORKLOADS))
+    ap.add_argument("--packed", action="store_true", help="packed=True layout (default: dense, as ns-train splatfacto)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--e2e-steps", type=int, default=None)
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    N, deg, W, H, mode = WORKLOADS[args.workload]
+
+    # ------------------------------------------------------------------ reference arm: CPU oracle, rank 0 only
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        steps, warmup = max(1, min(args.steps, 5)), min(args.warmup, 1)
+        cb = run_cpu(args.workload, steps, warmup)
+        line = {
+            "impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus,
+            "steps": steps, "warmup": warmup, "ms_per_step": cb["s_per_step"] * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"{args.workload}: {N} Gaussians, SH deg {deg}, {W}x{H}, {mode}, fwd+bwd "
+                                   "(bounded sub-frustum sample, see cpu_baseline.sample)"},
+            "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample", "cpu_model")},
+            "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "iters_per_s": cb["iters_per_s_full_frame_equiv"],
+        }
+        print(json.dumps(line))
+        return 0
+
+    # ------------------------------------------------------------------ our arm
+    import torch.distributed as dist
+    import pipeline_pointcloud_b200 as b2s
+    from pipeline_pointcloud_b200 import ops
+    from pipeline_pointcloud_b200.distributed import allreduce_gradients
+    from pipeline_pointcloud_b200.scene import make_scene
+
+    assert torch.cuda.is_available(), "bench.py needs a GPU (there is no CPU path)"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    assert world == args.gpus or world == 1, "launch with torchrun --nproc-per-node == --gpus"
+
+    C_total = max(world, 1)
+    scene = make_scene(N, deg, C_total, W, H, seed=0)            # identical on every rank (CPU generator)
+    leaves_host = {k: scene[k].pin_memory() for k in ("means", "quats", "scales", "opacities", "colors")}
+    cam_host = {"viewmats": scene["viewmats"][rank:rank + 1].contiguous().pin_memory(),
+                "Ks": scene["Ks"][rank:rank + 1].contiguous().pin_memory()}
+    params = {k: v.to(dev).requires_grad_() for k, v in leaves_host.items()}
+    cams = {k: v.to(dev) for k, v in cam_host.items()}
+    g = torch.Generator().manual_seed(1 + rank)
+    v_r_host = torch.rand(1, H, W, 3, generator=g).pin_memory()
+    v_a_host = torch.rand(1, H, W, 1, generator=g).pin_memory()
+    v_r, v_a = v_r_host.to(dev), v_a_host.to(dev)
+    kw = dict(sh_degree=deg, packed=args.packed, rasterize_mode=mode)
+    plist = list(params.values())
+    stats = {}
+
+    def step(p=params, c=cams, vr=v_r, va=v_a):
+        for t in p.values():
+            t.grad = None
+        r, a, m = b2s.rasterization(p["means"], p["quats"], p["scales"], p["opacities"], p["colors"], c["viewmats"],
+                                    c["Ks"], W, H, **kw)
+        torch.autograd.backward([r, a], [vr, va])
+        if world > 1:
+            allreduce_gradients(p.values())
+        stats["n_isects"] = m["isect_ids"].numel()
+        stats["n_visible"] = m["n_visible"] if "n_visible" in m else None
+        return r, a, m
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    for _ in range(max(args.warmup, 3)):
+        r, a, m = step()
+    torch.cuda.synchronize()
+    n_visible = int((m["radii"] > 0).sum()) if not args.packed else int(m["means2d"].shape[0])
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ops.TIMER = ops.StageTimer()
+    ms_total = timed(step, args.steps)
+    timer, ops.TIMER = ops.TIMER, None
+    clocks = sampler.stop() if rank == 0 else None
+    stage = timer.summary()
+    ms_per_step = ms_total / args.steps
+    pix_per_step = C_total * W * H
+    value = pix_per_step / (ms_per_step * 1e-3) / 1e6
+
+    # ---- e2e: host buffers in, host buffers out -----------------------------------------------------------
+    host_out = {"render": torch.empty(1, H, W, 3).pin_memory(), "alpha": torch.empty(1, H, W, 1).pin_memory()}
+    host_grads = {k: torch.empty_like(v).pin_memory() for k, v in leaves_host.items()}
+    h2d = sum(v.numel() * 4 for v in leaves_host.values()) + sum(v.numel() * 4 for v in cam_host.values()) \
+        + v_r_host.numel() * 4 + v_a_host.numel() * 4
+    d2h = sum(v.numel() * 4 for v in host_out.values()) + sum(v.numel() * 4 for v in host_grads.values())
+
+    def e2e_step():
+        p = {k: v.to(dev, non_blocking=True).requires_grad_() for k, v in leaves_host.items()}
+        c = {k: v.to(dev, non_blocking=True) for k, v in cam_host.items()}
+        vr, va = v_r_host.to(dev, non_blocking=True), v_a_host.to(dev, non_blocking=True)
+        r, a, _ = step(p, c, vr, va)
+        host_out["render"].copy_(r.detach(), non_blocking=True)
+        host_out["alpha"].copy_(a.detach(), non_blocking=True)
+        for k in host_grads:
+            host_grads[k].copy_(p[k].grad, non_blocking=True)
+        torch.cuda.current_stream().synchronize()      # the caller reads the host buffers after every step
+
+    e2e_steps = args.e2e_steps or max(3, min(args.steps, 10))
+    for _ in range(2):
+        e2e_step()
+    e2e_ms = timed(e2e_step, e2e_steps) / e2e_steps
+    e2e_value = pix_per_step / (e2e_ms * 1e-3) / 1e6
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    # ---- roofline of the dominant kernel ------------------------------------------------------------------
+    peak, peak_src = peaks()
+    I = stats["n_isects"]
+    tiles = math.ceil(W / 16) * math.ceil(H / 16)
+    key_bits = 32 + (tiles).bit_length() + (1).bit_length()
+    K = (deg + 1) ** 2
+    ab = algorithmic_bytes(N, 1, n_visible, I, W * H, K, tiles, key_bits)
+    per_stage = {}
+    for name, s in stage.items():
+        gbs = ab.get(name, 0) / (s["ms_avg"] * 1e-3) / 1e9 if s["ms_avg"] > 0 else 0.0
+        per_stage[name] = {"ms": round(s["ms_avg"], 4), "calls_per_step": s["calls"] / args.steps,
+                           "algorithmic_bytes": ab.get(name), "GBps": round(gbs, 1), "frac_of_peak": round(gbs / peak, 4)}
+    own = {k: v for k, v in per_stage.items() if k != "isect_sort"}
+    dom = max(own, key=lambda k: own[k]["ms"])
+    roofline = {"kernel": dom, "bound": "hbm", "achieved": per_stage[dom]["GBps"], "peak": peak, "unit": "GB/s",
+                "frac": per_stage[dom]["frac_of_peak"], "traffic": None, "peak_source": peak_src,
+                "note": "compositing is FP32/SFU/shared-memory bound, its HBM fraction is low by construction; "
+                        "projection and sort are the HBM-bound stages (see stages)"}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": f"{args.workload}: {N} random Gaussians, SH deg {deg}, {W}x{H}, {mode}, fwd+bwd, "
+                               f"packed={args.packed}, 1 camera per GPU" + (", dense-gradient all-reduce" if world > 1 else ""),
+                   "n_isects": I, "n_visible": n_visible, "l2": "inputs (1.4 GB parameters + 0.3 GB keys) exceed the 126 MB L2",
+                   "parallelism": f"dp{world}"},
+        "iters_per_s": 1e3 / ms_per_step * C_total,
+        "gpu_launches": timer.launches,
+        "gpu_launches_note": "kernels of libb2s.so inside the timed region (7 per step); CUB radix-sort passes are extra",
+        "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "steps": e2e_steps},
+        "roofline": roofline, "stages": per_stage, "clocks": clocks,
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        cb = run_cpu(args.workload, 1, 0)
+        line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample", "cpu_model")}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

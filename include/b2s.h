@@ -1,0 +1,198 @@
+/* b2s -- B200-native Gaussian-splat rasterizer, C ABI.
+ *
+ * This is the drop-in boundary for the `rasterization()` hot path that the reference's
+ * Train-Stage1 component reaches through gsplat (reference call sites:
+ * source/container/src/main.py:1308-1316 `ns-train splatfacto`, and
+ * source/container/src/main.py:1339-1347 `gsplat/examples/simple_trainer.py --packed`).
+ * gsplat binds its kernels through a torch C++ extension (`gsplat/cuda/_wrapper.py` ->
+ * `gsplat.csrc`); each entry point below names the gsplat op it replaces.  gsplat itself is
+ * not in /root/reference (unpinned pip install, source/container/Dockerfile:220-229), so the
+ * cited op names are the upstream ones, see SURVEY.md section 8a.
+ *
+ * Conventions
+ *  - plain pointers and sizes only; every pointer is a DEVICE pointer unless named host_*.
+ *  - the caller owns every buffer, including scratch: query `*_workspace_bytes` first.
+ *    The library never allocates device memory, never creates streams, never calls
+ *    cudaSetDevice, and holds no global mutable state (re-entrant; forward is called on the
+ *    Python thread, backward on torch's autograd thread).
+ *  - every call takes the CUDA stream explicitly (`cudaStream_t` passed as void*) and only
+ *    enqueues work; nothing synchronises.
+ *  - return value: 0 = ok, negative = B2S_E_* argument error, positive = cudaError_t.
+ *    Never aborts, never throws.  `b2s_last_error()` gives a thread-local message.
+ *  - all floating point is fp32, ids are int32, sort keys int64 (as gsplat).
+ *  - layouts are C-contiguous; "pair" = one (camera, Gaussian) row, dense index c*N + n.
+ */
+#ifndef B2S_H
+#define B2S_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(_WIN32)
+#define B2S_API
+#else
+#define B2S_API __attribute__((visibility("default")))
+#endif
+
+#define B2S_VERSION 100
+#define B2S_E_BADARG (-1)
+#define B2S_E_UNSUPPORTED (-2)
+#define B2S_E_WORKSPACE (-3)
+#define B2S_MAX_CAMERAS_PER_CALL 64 /* project_* process cameras in chunks of this size (the host loops) */
+
+typedef void* b2s_stream_t; /* cudaStream_t */
+
+B2S_API int b2s_version(void);
+B2S_API const char* b2s_last_error(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * Stage 1 forward: fused EWA projection (+ SH colour, + tile count).
+ * Replaces gsplat `fully_fused_projection` fwd (+ `spherical_harmonics` fwd + the count half of
+ * `isect_tiles`), SURVEY.md 8a rows 1-4.  One thread per Gaussian, cameras looped inside so the
+ * 44 B of parameters and the 12*K B of SH coefficients are read once.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct {
+    int64_t N;              /* Gaussians */
+    int32_t C;              /* cameras in this call, <= B2S_MAX_CAMERAS_PER_CALL */
+    const float* means;     /* [N,3] */
+    const float* quats;     /* [N,4] (w,x,y,z), un-normalised */
+    const float* scales;    /* [N,3] post-exp */
+    const float* opacities; /* [N] post-sigmoid, or NULL */
+    const float* viewmats;  /* [C,4,4] world->camera */
+    const float* Ks;        /* [C,3,3] */
+    int32_t width, height;
+    float eps2d, near_plane, far_plane, radius_clip;
+    int32_t antialiased;    /* 1: opacities_out = opacity * compensation */
+    /* SH colour (sh_coeffs == NULL: skipped) */
+    const float* sh_coeffs; /* [N, sh_stride_k, 3] */
+    const float* campos;    /* [C,3] camera centres in world space */
+    int32_t sh_degree;      /* 0..3, uses the first (deg+1)^2 rows */
+    int32_t sh_stride_k;    /* rows per Gaussian in sh_coeffs */
+    /* tile count (tiles_per_gauss == NULL: skipped) */
+    int32_t tile_size, tile_w, tile_h;
+    /* outputs, all [C,N,...] */
+    int32_t* radii;           /* [C,N]   0 = culled */
+    float* means2d;           /* [C,N,2] */
+    float* depths;            /* [C,N] */
+    float* conics;            /* [C,N,3] */
+    float* compensations;     /* [C,N] or NULL */
+    float* opacities_out;     /* [C,N] or NULL */
+    float* colors;            /* [C,N,3] = max(SH + 0.5, 0), or NULL */
+    int32_t* tiles_per_gauss; /* [C,N] or NULL */
+} b2s_project_fwd_args;
+B2S_API int b2s_project_fwd(const b2s_project_fwd_args* a, b2s_stream_t stream);
+
+/* Stage 1 backward.  Replaces gsplat `fully_fused_projection` bwd + `spherical_harmonics` bwd
+ * (SURVEY.md 8a row 9).  Cotangent pointers may be NULL (treated as zero).  Gradients are
+ * *written* (not accumulated) unless `accumulate` is set (used by the host loop over camera chunks). */
+typedef struct {
+    int64_t N;
+    int32_t C;
+    const float* means; const float* quats; const float* scales; const float* opacities;
+    const float* viewmats; const float* Ks;
+    int32_t width, height;
+    float eps2d, near_plane, far_plane, radius_clip;
+    int32_t antialiased;
+    const float* sh_coeffs; const float* campos; int32_t sh_degree; int32_t sh_stride_k;
+    const int32_t* radii;        /* [C,N] from the forward */
+    /* cotangents [C,N,...] */
+    const float* v_means2d; const float* v_depths; const float* v_conics;
+    const float* v_compensations; /* only when the caller consumed `compensations` directly */
+    const float* v_opacities_out; const float* v_colors;
+    int32_t accumulate;
+    /* gradients */
+    float* v_means;     /* [N,3] */
+    float* v_quats;     /* [N,4] */
+    float* v_scales;    /* [N,3] */
+    float* v_opacities; /* [N] or NULL */
+    float* v_sh_coeffs; /* [N, sh_stride_k, 3] or NULL; rows >= (deg+1)^2 are not touched */
+} b2s_project_bwd_args;
+B2S_API int b2s_project_bwd(const b2s_project_bwd_args* a, b2s_stream_t stream);
+
+/* Stand-alone SH evaluation over M directions (gsplat `spherical_harmonics` fwd/bwd): the
+ * stage-level op; the training path uses the fused kernels above.  masks may be NULL. */
+B2S_API int b2s_sh_fwd(int64_t M, int32_t degree, int32_t stride_k, const float* dirs, const float* coeffs,
+                       const uint8_t* masks, float* colors, b2s_stream_t stream);
+B2S_API int b2s_sh_bwd(int64_t M, int32_t degree, int32_t stride_k, const float* dirs, const float* coeffs,
+                       const uint8_t* masks, const float* v_colors, float* v_coeffs, float* v_dirs /* or NULL */,
+                       b2s_stream_t stream);
+
+/* gsplat `quat_scale_to_covar_preci` fwd: covars/precis [N,3,3] (either may be NULL). */
+B2S_API int b2s_quat_scale_to_covar_preci(int64_t N, const float* quats, const float* scales, float* covars,
+                                          float* precis, b2s_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Stage 2: tile binning.  Replaces gsplat `isect_tiles` (count / fill), the CUB radix sort it
+ * calls, and `isect_offset_encode`.  All outputs bit-exact.
+ * Two-phase because n_isects is data dependent:
+ *   b2s_isect_count  -> tiles_per_gauss [M]                          (skipped when stage 1 made it)
+ *   b2s_isect_scan   -> cum_tiles [M] (exclusive), *total (device int64; the caller copies it to
+ *                       the host to size the next buffers -- the one host sync of a forward)
+ *   b2s_isect_fill   -> isect_ids [I] int64, flatten_ids [I] int32   (unsorted, pair-major)
+ *   b2s_isect_sort   -> sorted isect_ids / flatten_ids                (stable LSD radix)
+ *   b2s_isect_offsets-> offsets [C*tile_h*tile_w] int32
+ * M = number of rows (C*N dense, nnz packed).  camera_ids == NULL means dense rows (cam = row / N).
+ * ---------------------------------------------------------------------------------------------- */
+B2S_API int b2s_isect_count(int64_t M, const float* means2d, const int32_t* radii, int32_t tile_size,
+                            int32_t tile_w, int32_t tile_h, int32_t* tiles_per_gauss, b2s_stream_t stream);
+B2S_API int64_t b2s_isect_scan_workspace_bytes(int64_t M);
+B2S_API int b2s_isect_scan(int64_t M, const int32_t* tiles_per_gauss, int32_t* cum_tiles, int64_t* total,
+                           void* workspace, int64_t workspace_bytes, b2s_stream_t stream);
+B2S_API int b2s_isect_fill(int64_t M, int64_t N, const int64_t* camera_ids /* or NULL */, const float* means2d,
+                           const int32_t* radii, const float* depths, const int32_t* cum_tiles, int32_t tile_size,
+                           int32_t tile_w, int32_t tile_h, int64_t* isect_ids, int32_t* flatten_ids,
+                           b2s_stream_t stream);
+B2S_API int64_t b2s_isect_sort_workspace_bytes(int64_t n_isects);
+B2S_API int b2s_isect_sort(int64_t n_isects, int32_t key_bits, const int64_t* isect_ids_in, const int32_t* flatten_ids_in,
+                           int64_t* isect_ids_out, int32_t* flatten_ids_out, void* workspace, int64_t workspace_bytes,
+                           b2s_stream_t stream);
+B2S_API int b2s_isect_offsets(int64_t n_isects, const int64_t* isect_ids_sorted, int32_t C, int32_t tile_w,
+                              int32_t tile_h, int32_t* offsets, b2s_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Stage 3: per-16x16-tile front-to-back compositing.  Replaces gsplat `rasterize_to_pixels`
+ * fwd / bwd.  Rows of means2d/conics/colors/opacities are addressed by
+ * flatten_ids, so dense [C*N] and packed [nnz] layouts both work.  channels in {1,2,3,4,8,16,32}.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct {
+    int32_t C, width, height, tile_size, tile_w, tile_h, channels;
+    int64_t n_isects;
+    const float* means2d;       /* [M,2] */
+    const float* conics;        /* [M,3] */
+    const float* colors;        /* [M,channels] */
+    const float* opacities;     /* [M] */
+    const float* backgrounds;   /* [C,channels] or NULL */
+    const int32_t* isect_offsets; /* [C,tile_h,tile_w] */
+    const int32_t* flatten_ids; /* [n_isects] */
+    float* render_colors;       /* [C,H,W,channels] */
+    float* render_alphas;       /* [C,H,W,1] */
+    int32_t* last_ids;          /* [C,H,W] index into flatten_ids of the last contributor */
+    float* final_T;             /* [C,H,W] exact final transmittance for the backward, or NULL */
+} b2s_composite_fwd_args;
+B2S_API int b2s_composite_fwd(const b2s_composite_fwd_args* a, b2s_stream_t stream);
+
+typedef struct {
+    int32_t C, width, height, tile_size, tile_w, tile_h, channels;
+    int64_t n_isects;
+    const float* means2d; const float* conics; const float* colors; const float* opacities;
+    const float* backgrounds;
+    const int32_t* isect_offsets; const int32_t* flatten_ids;
+    const float* render_alphas; const int32_t* last_ids;
+    const float* final_T;         /* from the forward, or NULL (then 1 - render_alphas is used) */
+    const float* v_render_colors; /* [C,H,W,channels] */
+    const float* v_render_alphas; /* [C,H,W,1] */
+    /* gradients: ACCUMULATED with atomics, the caller zero-fills them first */
+    float* v_means2d;     /* [M,2] */
+    float* v_means2d_abs; /* [M,2] or NULL (absgrad) */
+    float* v_conics;      /* [M,3] */
+    float* v_colors;      /* [M,channels] */
+    float* v_opacities;   /* [M] */
+} b2s_composite_bwd_args;
+B2S_API int b2s_composite_bwd(const b2s_composite_bwd_args* a, b2s_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B2S_H */

@@ -1,0 +1,159 @@
+"""ctypes binding of the C-ABI library ``libb2s.so`` (``include/b2s.h``).
+
+There is no fallback: if the library is missing or a call fails this raises.  The product never
+imports ``oracle/``.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import POINTER, Structure, c_char_p, c_float, c_int32, c_int64, c_void_p
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libb2s.so")
+
+_lib = None
+
+
+class B2SError(RuntimeError):
+    pass
+
+
+class ProjectFwdArgs(Structure):
+    _fields_ = [
+        ("N", c_int64), ("C", c_int32),
+        ("means", c_void_p), ("quats", c_void_p), ("scales", c_void_p), ("opacities", c_void_p),
+        ("viewmats", c_void_p), ("Ks", c_void_p),
+        ("width", c_int32), ("height", c_int32),
+        ("eps2d", c_float), ("near_plane", c_float), ("far_plane", c_float), ("radius_clip", c_float),
+        ("antialiased", c_int32),
+        ("sh_coeffs", c_void_p), ("campos", c_void_p), ("sh_degree", c_int32), ("sh_stride_k", c_int32),
+        ("tile_size", c_int32), ("tile_w", c_int32), ("tile_h", c_int32),
+        ("radii", c_void_p), ("means2d", c_void_p), ("depths", c_void_p), ("conics", c_void_p),
+        ("compensations", c_void_p), ("opacities_out", c_void_p), ("colors", c_void_p),
+        ("tiles_per_gauss", c_void_p),
+    ]
+
+
+class ProjectBwdArgs(Structure):
+    _fields_ = [
+        ("N", c_int64), ("C", c_int32),
+        ("means", c_void_p), ("quats", c_void_p), ("scales", c_void_p), ("opacities", c_void_p),
+        ("viewmats", c_void_p), ("Ks", c_void_p),
+        ("width", c_int32), ("height", c_int32),
+        ("eps2d", c_float), ("near_plane", c_float), ("far_plane", c_float), ("radius_clip", c_float),
+        ("antialiased", c_int32),
+        ("sh_coeffs", c_void_p), ("campos", c_void_p), ("sh_degree", c_int32), ("sh_stride_k", c_int32),
+        ("radii", c_void_p),
+        ("v_means2d", c_void_p), ("v_depths", c_void_p), ("v_conics", c_void_p),
+        ("v_compensations", c_void_p), ("v_opacities_out", c_void_p), ("v_colors", c_void_p),
+        ("accumulate", c_int32),
+        ("v_means", c_void_p), ("v_quats", c_void_p), ("v_scales", c_void_p), ("v_opacities", c_void_p),
+        ("v_sh_coeffs", c_void_p),
+    ]
+
+
+class CompositeFwdArgs(Structure):
+    _fields_ = [
+        ("C", c_int32), ("width", c_int32), ("height", c_int32), ("tile_size", c_int32),
+        ("tile_w", c_int32), ("tile_h", c_int32), ("channels", c_int32),
+        ("n_isects", c_int64),
+        ("means2d", c_void_p), ("conics", c_void_p), ("colors", c_void_p), ("opacities", c_void_p),
+        ("backgrounds", c_void_p), ("isect_offsets", c_void_p), ("flatten_ids", c_void_p),
+        ("render_colors", c_void_p), ("render_alphas", c_void_p), ("last_ids", c_void_p), ("final_T", c_void_p),
+    ]
+
+
+class CompositeBwdArgs(Structure):
+    _fields_ = [
+        ("C", c_int32), ("width", c_int32), ("height", c_int32), ("tile_size", c_int32),
+        ("tile_w", c_int32), ("tile_h", c_int32), ("channels", c_int32),
+        ("n_isects", c_int64),
+        ("means2d", c_void_p), ("conics", c_void_p), ("colors", c_void_p), ("opacities", c_void_p),
+        ("backgrounds", c_void_p), ("isect_offsets", c_void_p), ("flatten_ids", c_void_p),
+        ("render_alphas", c_void_p), ("last_ids", c_void_p), ("final_T", c_void_p),
+        ("v_render_colors", c_void_p), ("v_render_alphas", c_void_p),
+        ("v_means2d", c_void_p), ("v_means2d_abs", c_void_p), ("v_conics", c_void_p), ("v_colors", c_void_p),
+        ("v_opacities", c_void_p),
+    ]
+
+
+# every symbol include/b2s.h declares: name -> (restype, argtypes)
+SYMBOLS = {
+    "b2s_version": (c_int32, []),
+    "b2s_last_error": (c_char_p, []),
+    "b2s_project_fwd": (c_int32, [POINTER(ProjectFwdArgs), c_void_p]),
+    "b2s_project_bwd": (c_int32, [POINTER(ProjectBwdArgs), c_void_p]),
+    "b2s_sh_fwd": (c_int32, [c_int64, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "b2s_sh_bwd": (c_int32, [c_int64, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "b2s_quat_scale_to_covar_preci": (c_int32, [c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "b2s_isect_count": (c_int32, [c_int64, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p]),
+    "b2s_isect_scan_workspace_bytes": (c_int64, [c_int64]),
+    "b2s_isect_scan": (c_int32, [c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
+    "b2s_isect_fill": (c_int32, [c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32,
+                                 c_int32, c_void_p, c_void_p, c_void_p]),
+    "b2s_isect_sort_workspace_bytes": (c_int64, [c_int64]),
+    "b2s_isect_sort": (c_int32, [c_int64, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
+    "b2s_isect_offsets": (c_int32, [c_int64, c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p]),
+    "b2s_composite_fwd": (c_int32, [POINTER(CompositeFwdArgs), c_void_p]),
+    "b2s_composite_bwd": (c_int32, [POINTER(CompositeBwdArgs), c_void_p]),
+}
+
+
+def lib() -> ctypes.CDLL:
+    """Loads libb2s.so once.  Raises if it is not built -- there is no other code path."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise B2SError(
+                f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(or `make -C pipeline_pointcloud_b200/csrc`).  There is no CPU or PyTorch fallback.")
+        handle = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SYMBOLS.items():
+            fn = getattr(handle, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = handle
+    return _lib
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = lib().b2s_last_error().decode("utf-8", "replace")
+        raise B2SError(f"{what} failed (code {rc}): {msg}")
+
+
+def ptr(t) -> int:
+    """Device pointer of a tensor (None -> NULL)."""
+    return None if t is None else t.data_ptr()
+
+
+def stream_ptr(device) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def require_cuda(*tensors) -> torch.device:
+    dev = None
+    for t in tensors:
+        if t is None:
+            continue
+        if not t.is_cuda:
+            raise B2SError("b2s runs on CUDA tensors only (there is no CPU path); got a tensor on " + str(t.device))
+        if dev is None:
+            dev = t.device
+        elif t.device != dev:
+            raise B2SError(f"tensors on different devices: {dev} vs {t.device}")
+    if dev is None:
+        raise B2SError("no CUDA tensor given")
+    return dev
+
+
+def f32c(t):
+    """Contiguous fp32 view/copy (None passes through)."""
+    if t is None:
+        return None
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t.contiguous()

@@ -1,0 +1,256 @@
+// Stage 2: tile binning -- count, scan, key fill, (tile, depth) radix sort, per-tile offsets.
+//
+// Replaces gsplat `isect_tiles` (two launches + cumsum), the CUB radix sort it calls, and
+// `isect_offset_encode`.  Integer work: every output is bit-exact
+// against oracle/torch_oracle.py::isect_tiles / isect_offset_encode.
+#include <cub/device/device_radix_sort.cuh>
+
+#include "b2s_math.cuh"
+#include "common.cuh"
+
+namespace b2s {
+
+// -------------------------------------------------------------------------------------------------
+// count (only used by the stage-level op; the training path gets tiles_per_gauss from stage 1)
+// -------------------------------------------------------------------------------------------------
+__global__ void isect_count_kernel(int64_t M, const float2* __restrict__ means2d, const int32_t* __restrict__ radii,
+                                   float tile_size, int tile_w, int tile_h, int32_t* __restrict__ tiles) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= M) return;
+    int r = radii[i];
+    int cnt = 0;
+    if (r > 0) {
+        float2 m = means2d[i];
+        int x0, y0, x1, y1;
+        tile_rect(m.x, m.y, r, tile_size, tile_w, tile_h, x0, y0, x1, y1);
+        cnt = (x1 - x0) * (y1 - y0);
+    }
+    tiles[i] = cnt;
+}
+
+// -------------------------------------------------------------------------------------------------
+// single-pass exclusive scan (decoupled look-back, dynamic tile ids so predecessors always run)
+// -------------------------------------------------------------------------------------------------
+constexpr int SCAN_THREADS = 256;
+constexpr int SCAN_ITEMS = 8;
+constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
+// status word: bits 63..62 = flag (0 none, 1 tile aggregate, 2 inclusive prefix), bits 61..0 = value
+constexpr unsigned long long FLAG_AGG = 1ull << 62, FLAG_INC = 2ull << 62, VAL_MASK = (1ull << 62) - 1;
+
+__global__ void __launch_bounds__(SCAN_THREADS) scan_kernel(int64_t M, const int32_t* __restrict__ in,
+                                                            int32_t* __restrict__ out, int64_t* __restrict__ total,
+                                                            unsigned long long* status, unsigned int* tile_counter) {
+    __shared__ unsigned int s_tile;
+    __shared__ unsigned long long s_warp[SCAN_THREADS / 32];
+    __shared__ unsigned long long s_prefix;
+    if (threadIdx.x == 0) s_tile = atomicAdd(tile_counter, 1u);
+    __syncthreads();
+    const unsigned int tile = s_tile;
+    const int64_t base = (int64_t)tile * SCAN_TILE + (int64_t)threadIdx.x * SCAN_ITEMS;
+    int v[SCAN_ITEMS];
+    unsigned long long tsum = 0;
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; ++k) {
+        v[k] = (base + k < M) ? in[base + k] : 0;
+        tsum += (unsigned long long)v[k];
+    }
+    // block exclusive scan of per-thread sums
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned long long inc = tsum;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        unsigned long long o = __shfl_up_sync(FULL, inc, d);
+        if (lane >= d) inc += o;
+    }
+    if (lane == 31) s_warp[warp] = inc;
+    __syncthreads();
+    unsigned long long warp_off = 0, block_sum = 0;
+#pragma unroll
+    for (int w = 0; w < SCAN_THREADS / 32; ++w) {
+        unsigned long long x = s_warp[w];
+        if (w < warp) warp_off += x;
+        block_sum += x;
+    }
+    if (threadIdx.x == 0) {
+        volatile unsigned long long* st = status;
+        unsigned long long excl = 0;
+        if (tile == 0) {
+            st[0] = FLAG_INC | block_sum;
+        } else {
+            st[tile] = FLAG_AGG | block_sum;
+            __threadfence();
+            long long j = (long long)tile - 1;
+            while (true) {
+                unsigned long long sv = st[j];
+                unsigned long long flag = sv & ~VAL_MASK;
+                if (flag == 0) continue;  // predecessor has a smaller dynamic id => it is running: spin
+                excl += sv & VAL_MASK;
+                if (flag == FLAG_INC) break;
+                --j;
+            }
+            st[tile] = FLAG_INC | (excl + block_sum);
+        }
+        s_prefix = excl;
+        if ((int64_t)(tile + 1) * SCAN_TILE >= M) *total = (int64_t)(excl + block_sum);
+    }
+    __syncthreads();
+    unsigned long long run = s_prefix + warp_off + (inc - tsum);
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; ++k) {
+        if (base + k < M) out[base + k] = (int32_t)run;
+        run += (unsigned long long)v[k];
+    }
+}
+
+// -------------------------------------------------------------------------------------------------
+// fill: one key/value per covered tile, row-major inside the rectangle (y outer, x inner)
+// key = cam << (32 + tile_bits) | tile << 32 | bits(depth)
+// -------------------------------------------------------------------------------------------------
+__global__ void isect_fill_kernel(int64_t M, int64_t N, const int64_t* __restrict__ camera_ids,
+                                  const float2* __restrict__ means2d, const int32_t* __restrict__ radii,
+                                  const float* __restrict__ depths, const int32_t* __restrict__ cum, float tile_size,
+                                  int tile_w, int tile_h, int tile_bits, int64_t* __restrict__ keys,
+                                  int32_t* __restrict__ vals) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= M) return;
+    int r = radii[i];
+    if (r <= 0) return;
+    float2 m = means2d[i];
+    int x0, y0, x1, y1;
+    tile_rect(m.x, m.y, r, tile_size, tile_w, tile_h, x0, y0, x1, y1);
+    if (x1 <= x0 || y1 <= y0) return;
+    int64_t cam = camera_ids ? camera_ids[i] : (i / N);
+    uint64_t hi = (uint64_t)cam << tile_bits;
+    uint64_t dbits = (uint64_t)__float_as_uint(depths[i]);
+    int64_t o = cum[i];
+    for (int y = y0; y < y1; ++y)
+        for (int x = x0; x < x1; ++x) {
+            uint64_t tile = (uint64_t)(y * tile_w + x);
+            keys[o] = (int64_t)(((hi | tile) << 32) | dbits);
+            vals[o] = (int32_t)i;
+            ++o;
+        }
+}
+
+// -------------------------------------------------------------------------------------------------
+// offsets: first sorted index of every (camera, tile); empty tiles take the next tile's start
+// -------------------------------------------------------------------------------------------------
+__global__ void isect_offsets_kernel(int64_t n, const int64_t* __restrict__ keys, int n_tiles, int tile_bits,
+                                     int64_t total_tiles, int32_t* __restrict__ offsets) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint64_t cur = (uint64_t)keys[i] >> 32;
+    int64_t cur_lin = (int64_t)(cur >> tile_bits) * n_tiles + (int64_t)(cur & ((1ull << tile_bits) - 1));
+    if (i == 0) {
+        for (int64_t t = 0; t <= cur_lin; ++t) offsets[t] = 0;
+    } else {
+        uint64_t prev = (uint64_t)keys[i - 1] >> 32;
+        if (prev != cur) {
+            int64_t prev_lin = (int64_t)(prev >> tile_bits) * n_tiles + (int64_t)(prev & ((1ull << tile_bits) - 1));
+            for (int64_t t = prev_lin + 1; t <= cur_lin; ++t) offsets[t] = (int32_t)i;
+        }
+    }
+    if (i == n - 1)
+        for (int64_t t = cur_lin + 1; t < total_tiles; ++t) offsets[t] = (int32_t)n;
+}
+
+static int bit_length(int64_t v) {
+    int b = 0;
+    while (v > 0) { ++b; v >>= 1; }
+    return b;
+}
+
+}  // namespace b2s
+
+using namespace b2s;
+
+extern "C" int b2s_isect_count(int64_t M, const float* means2d, const int32_t* radii, int32_t tile_size, int32_t tile_w,
+                               int32_t tile_h, int32_t* tiles_per_gauss, b2s_stream_t stream) {
+    B2S_REQUIRE(M >= 0 && tile_size > 0 && tile_w > 0 && tile_h > 0, "bad sizes");
+    if (M == 0) return 0;
+    B2S_REQUIRE(means2d && radii && tiles_per_gauss, "null pointer");
+    isect_count_kernel<<<(unsigned)cdiv(M, 256), 256, 0, (cudaStream_t)stream>>>(
+        M, reinterpret_cast<const float2*>(means2d), radii, (float)tile_size, tile_w, tile_h, tiles_per_gauss);
+    B2S_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int64_t b2s_isect_scan_workspace_bytes(int64_t M) {
+    int64_t tiles = cdiv(M > 0 ? M : 1, SCAN_TILE);
+    return 16 + tiles * 8;  // [tile counter, pad] + one status word per tile
+}
+
+extern "C" int b2s_isect_scan(int64_t M, const int32_t* tiles_per_gauss, int32_t* cum_tiles, int64_t* total,
+                              void* workspace, int64_t workspace_bytes, b2s_stream_t stream) {
+    B2S_REQUIRE(M >= 0 && total != nullptr, "bad args");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (M == 0) {
+        B2S_CUDA(cudaMemsetAsync(total, 0, sizeof(int64_t), st));
+        return 0;
+    }
+    B2S_REQUIRE(tiles_per_gauss && cum_tiles && workspace, "null pointer");
+    if (workspace_bytes < b2s_isect_scan_workspace_bytes(M)) {
+        set_error("b2s_isect_scan: workspace too small");
+        return B2S_E_WORKSPACE;
+    }
+    B2S_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 15u) == 0, "workspace must be 16-byte aligned");
+    int64_t tiles = cdiv(M, SCAN_TILE);
+    B2S_CUDA(cudaMemsetAsync(workspace, 0, (size_t)(16 + tiles * 8), st));
+    unsigned int* counter = reinterpret_cast<unsigned int*>(workspace);
+    unsigned long long* status = reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(workspace) + 16);
+    scan_kernel<<<(unsigned)tiles, SCAN_THREADS, 0, st>>>(M, tiles_per_gauss, cum_tiles, total, status, counter);
+    B2S_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int b2s_isect_fill(int64_t M, int64_t N, const int64_t* camera_ids, const float* means2d, const int32_t* radii,
+                              const float* depths, const int32_t* cum_tiles, int32_t tile_size, int32_t tile_w,
+                              int32_t tile_h, int64_t* isect_ids, int32_t* flatten_ids, b2s_stream_t stream) {
+    B2S_REQUIRE(M >= 0 && tile_size > 0 && tile_w > 0 && tile_h > 0, "bad sizes");
+    if (M == 0) return 0;
+    B2S_REQUIRE(camera_ids != nullptr || N > 0, "dense rows need N");
+    B2S_REQUIRE(means2d && radii && depths && cum_tiles, "null pointer");
+    int tile_bits = bit_length((int64_t)tile_w * tile_h);
+    isect_fill_kernel<<<(unsigned)cdiv(M, 256), 256, 0, (cudaStream_t)stream>>>(
+        M, N, camera_ids, reinterpret_cast<const float2*>(means2d), radii, depths, cum_tiles, (float)tile_size, tile_w,
+        tile_h, tile_bits, isect_ids, flatten_ids);
+    B2S_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int64_t b2s_isect_sort_workspace_bytes(int64_t n) {
+    if (n <= 0) return 16;
+    size_t bytes = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, bytes, (const uint64_t*)nullptr, (uint64_t*)nullptr, (const int32_t*)nullptr,
+                                    (int32_t*)nullptr, n, 0, 64, (cudaStream_t)0);
+    return (int64_t)bytes + 16;
+}
+
+extern "C" int b2s_isect_sort(int64_t n, int32_t key_bits, const int64_t* keys_in, const int32_t* vals_in, int64_t* keys_out,
+                              int32_t* vals_out, void* workspace, int64_t workspace_bytes, b2s_stream_t stream) {
+    B2S_REQUIRE(n >= 0 && key_bits > 0 && key_bits <= 64, "bad sizes");
+    if (n == 0) return 0;
+    B2S_REQUIRE(keys_in && vals_in && keys_out && vals_out && workspace, "null pointer");
+    size_t bytes = (size_t)workspace_bytes;
+    B2S_CUDA(cub::DeviceRadixSort::SortPairs(workspace, bytes, reinterpret_cast<const uint64_t*>(keys_in),
+                                             reinterpret_cast<uint64_t*>(keys_out), vals_in, vals_out, n, 0, key_bits,
+                                             (cudaStream_t)stream));
+    return 0;
+}
+
+extern "C" int b2s_isect_offsets(int64_t n, const int64_t* keys, int32_t C, int32_t tile_w, int32_t tile_h,
+                                 int32_t* offsets, b2s_stream_t stream) {
+    B2S_REQUIRE(n >= 0 && C >= 0 && tile_w > 0 && tile_h > 0 && offsets, "bad args");
+    int n_tiles = tile_w * tile_h;
+    int64_t total_tiles = (int64_t)C * n_tiles;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (n == 0) {
+        if (total_tiles > 0) B2S_CUDA(cudaMemsetAsync(offsets, 0, (size_t)total_tiles * 4, st));
+        return 0;
+    }
+    B2S_REQUIRE(keys != nullptr, "null keys");
+    int tile_bits = bit_length(n_tiles);
+    isect_offsets_kernel<<<(unsigned)cdiv(n, 256), 256, 0, st>>>(n, keys, n_tiles, tile_bits, total_tiles, offsets);
+    B2S_LAUNCH_CHECK();
+    return 0;
+}

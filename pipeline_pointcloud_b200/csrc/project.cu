@@ -1,0 +1,351 @@
+// Stage 1: fused EWA projection + SH colour (+ tile count), forward and backward.
+//
+// Replaces gsplat `fully_fused_projection` fwd/bwd + `spherical_harmonics` fwd/bwd + the counting
+// half of `isect_tiles`.  Reached in the reference from
+// source/container/src/main.py:1308-1316 / :1339-1347 on every training iteration.
+//
+// Design (HBM-bound streaming kernel):
+//  * one thread per Gaussian, cameras looped inside: the 44 B of parameters are read once,
+//  * SH coefficients ([N,K,3], 192 B per Gaussian at degree 3 -- the largest tensor of the path) are
+//    moved by the whole warp as one contiguous 32-row chunk with 128-bit streaming loads into a
+//    padded shared-memory tile (row stride odd => the per-thread row reads are conflict free);
+//    the backward writes v_coeffs through the same tile so the 1.1 GB gradient goes out coalesced,
+//  * rows are only fetched when some lane of the warp sees its Gaussian in some camera,
+//  * the forward also emits tiles_per_gauss so binning needs no extra pass over means2d/radii.
+#include "b2s_math.cuh"
+#include "common.cuh"
+
+namespace b2s {
+
+constexpr int FWD_THREADS = 256;
+constexpr int BWD_THREADS = 128;
+
+__host__ __device__ constexpr int sh_row_stride(int K) { return (3 * K) | 1; }  // odd => conflict-free rows
+
+// ---- warp-cooperative movement of 32 SH rows between global memory and the padded smem tile -------
+// gbase points at row 0 of the warp's chunk, `rows` valid rows, row_mask: which rows to move.
+template <int KVEC>  // 16: 3*K == 48 floats and stride_k == K -> 128-bit path; 0: generic
+__device__ __forceinline__ void sh_rows_load(float* tile, const float* gbase, int rows, unsigned row_mask, int K,
+                                             int stride_k, int lane) {
+    const int rs = sh_row_stride(K);
+    if (KVEC == 16) {
+        const float4* g4 = reinterpret_cast<const float4*>(gbase);
+        float4 v[12];
+#pragma unroll
+        for (int i = 0; i < 12; ++i) {
+            int q = lane + 32 * i;
+            int r = q / 12;
+            bool on = (r < rows) && ((row_mask >> r) & 1u);
+            v[i] = on ? ldg_stream4(g4 + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int i = 0; i < 12; ++i) {
+            int q = lane + 32 * i;
+            int r = q / 12, e = (q - r * 12) * 4;
+            float* d = tile + r * rs + e;
+            d[0] = v[i].x; d[1] = v[i].y; d[2] = v[i].z; d[3] = v[i].w;
+        }
+    } else {
+        const int per = 3 * K;
+        for (int f = lane; f < 32 * per; f += 32) {
+            int r = f / per, e = f - r * per;
+            bool on = (r < rows) && ((row_mask >> r) & 1u);
+            tile[r * rs + e] = on ? ldg_stream1(gbase + (size_t)r * stride_k * 3 + e) : 0.f;
+        }
+    }
+}
+
+template <int KVEC>
+__device__ __forceinline__ void sh_rows_store(const float* tile, float* gbase, int rows, int K, int stride_k, int lane,
+                                              bool accumulate) {
+    const int rs = sh_row_stride(K);
+    if (KVEC == 16 && !accumulate) {
+        float4* g4 = reinterpret_cast<float4*>(gbase);
+#pragma unroll
+        for (int i = 0; i < 12; ++i) {
+            int q = lane + 32 * i;
+            int r = q / 12, e = (q - r * 12) * 4;
+            if (r < rows) {
+                const float* s = tile + r * rs + e;
+                stg_stream4(g4 + q, make_float4(s[0], s[1], s[2], s[3]));
+            }
+        }
+    } else {
+        const int per = 3 * K;
+        for (int f = lane; f < 32 * per; f += 32) {
+            int r = f / per, e = f - r * per;
+            if (r < rows) {
+                float* g = gbase + (size_t)r * stride_k * 3 + e;
+                *g = accumulate ? (*g + tile[r * rs + e]) : tile[r * rs + e];
+            }
+        }
+    }
+}
+
+__device__ __forceinline__ void load_cameras(Camera* cams, int C, const float* viewmats, const float* Ks,
+                                             const float* campos, float W, float H) {
+    for (int c = threadIdx.x; c < C; c += blockDim.x)
+        camera_setup(cams[c], viewmats + 16 * c, Ks + 9 * c, campos ? campos + 3 * c : nullptr, W, H);
+    __syncthreads();
+}
+
+// =================================================================================================
+// forward
+// =================================================================================================
+template <int KVEC>
+__global__ void __launch_bounds__(FWD_THREADS) project_fwd_kernel(const b2s_project_fwd_args a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    Camera* cams = reinterpret_cast<Camera*>(smem_raw);
+    float* sh_tiles = reinterpret_cast<float*>(smem_raw + ((a.C * sizeof(Camera) + 15) / 16) * 16);
+    const float W = (float)a.width, H = (float)a.height;
+    load_cameras(cams, a.C, a.viewmats, a.Ks, a.campos, W, H);
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t n = (int64_t)blockIdx.x * FWD_THREADS + threadIdx.x;
+    const bool live = n < a.N;
+    const int64_t nc = live ? n : a.N - 1;  // clamp so every lane can run the same code
+
+    float mean[3], q[4], s[3];
+    mean[0] = __ldg(a.means + 3 * nc); mean[1] = __ldg(a.means + 3 * nc + 1); mean[2] = __ldg(a.means + 3 * nc + 2);
+    {
+        float4 qq = __ldg(reinterpret_cast<const float4*>(a.quats) + nc);
+        q[0] = qq.x; q[1] = qq.y; q[2] = qq.z; q[3] = qq.w;
+    }
+    s[0] = __ldg(a.scales + 3 * nc); s[1] = __ldg(a.scales + 3 * nc + 1); s[2] = __ldg(a.scales + 3 * nc + 2);
+    const float opac = a.opacities ? __ldg(a.opacities + nc) : 1.f;
+
+    Rot R; float qn[4], qnorm, M[9]; Sym3 S;
+    quat_to_rotmat(q, R, qn, qnorm);
+    covar_from_rot_scale(R, s, M, S);
+
+    unsigned long long vis = 0ull;
+    for (int c = 0; c < a.C; ++c) {
+        ProjOut o;
+        project_one(cams[c], mean, S, W, H, a.eps2d, a.near_plane, a.far_plane, a.radius_clip, o, nullptr);
+        if (!live) continue;
+        const int64_t i = (int64_t)c * a.N + n;
+        a.radii[i] = o.radius;
+        reinterpret_cast<float2*>(a.means2d)[i] = make_float2(o.x2d, o.y2d);
+        a.depths[i] = o.depth;
+        a.conics[3 * i] = o.conic_a; a.conics[3 * i + 1] = o.conic_b; a.conics[3 * i + 2] = o.conic_c;
+        if (a.compensations) a.compensations[i] = o.comp;
+        if (a.opacities_out) a.opacities_out[i] = o.radius > 0 ? (a.antialiased ? opac * o.comp : opac) : 0.f;
+        if (a.tiles_per_gauss) {
+            int cnt = 0;
+            if (o.radius > 0) {
+                int x0, y0, x1, y1;
+                tile_rect(o.x2d, o.y2d, o.radius, (float)a.tile_size, a.tile_w, a.tile_h, x0, y0, x1, y1);
+                cnt = (x1 - x0) * (y1 - y0);
+            }
+            a.tiles_per_gauss[i] = cnt;
+        }
+        if (o.radius > 0) vis |= 1ull << c;
+    }
+
+    if (a.sh_coeffs == nullptr || a.colors == nullptr) return;
+    const int K = (a.sh_degree + 1) * (a.sh_degree + 1);
+    const int rs = sh_row_stride(K);
+    float* tile = sh_tiles + (size_t)warp * 32 * rs;
+    const unsigned row_mask = __ballot_sync(FULL, live && vis != 0ull);
+    const int64_t row0 = (int64_t)blockIdx.x * FWD_THREADS + warp * 32;
+    if (row_mask) {
+        int rows = (int)min((int64_t)32, a.N - row0);
+        sh_rows_load<KVEC>(tile, a.sh_coeffs + (size_t)row0 * a.sh_stride_k * 3, rows, row_mask, K, a.sh_stride_k, lane);
+    }
+    __syncwarp();
+    if (!live) return;
+    const float* row = tile + lane * rs;
+    for (int c = 0; c < a.C; ++c) {
+        const int64_t i = (int64_t)c * a.N + n;
+        float r = 0.f, g = 0.f, b = 0.f;
+        if ((vis >> c) & 1ull) {
+            float dx = mean[0] - cams[c].campos[0], dy = mean[1] - cams[c].campos[1], dz = mean[2] - cams[c].campos[2];
+            float inv = 1.f / fmaxf(sqrtf(dx * dx + dy * dy + dz * dz), 1e-12f);
+            float Y[16];
+            sh_basis(a.sh_degree, dx * inv, dy * inv, dz * inv, Y);
+#pragma unroll 4
+            for (int k = 0; k < K; ++k) {
+                r += Y[k] * row[3 * k]; g += Y[k] * row[3 * k + 1]; b += Y[k] * row[3 * k + 2];
+            }
+            r = fmaxf(r + 0.5f, 0.f); g = fmaxf(g + 0.5f, 0.f); b = fmaxf(b + 0.5f, 0.f);
+        }
+        a.colors[3 * i] = r; a.colors[3 * i + 1] = g; a.colors[3 * i + 2] = b;
+    }
+}
+
+// =================================================================================================
+// backward
+// =================================================================================================
+template <int KVEC>
+__global__ void __launch_bounds__(BWD_THREADS) project_bwd_kernel(const b2s_project_bwd_args a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    Camera* cams = reinterpret_cast<Camera*>(smem_raw);
+    float* sh_tiles = reinterpret_cast<float*>(smem_raw + ((a.C * sizeof(Camera) + 15) / 16) * 16);
+    const float W = (float)a.width, H = (float)a.height;
+    load_cameras(cams, a.C, a.viewmats, a.Ks, a.campos, W, H);
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t n = (int64_t)blockIdx.x * BWD_THREADS + threadIdx.x;
+    const bool live = n < a.N;
+    const int64_t nc = live ? n : a.N - 1;
+
+    float mean[3], q[4], s[3];
+    mean[0] = __ldg(a.means + 3 * nc); mean[1] = __ldg(a.means + 3 * nc + 1); mean[2] = __ldg(a.means + 3 * nc + 2);
+    {
+        float4 qq = __ldg(reinterpret_cast<const float4*>(a.quats) + nc);
+        q[0] = qq.x; q[1] = qq.y; q[2] = qq.z; q[3] = qq.w;
+    }
+    s[0] = __ldg(a.scales + 3 * nc); s[1] = __ldg(a.scales + 3 * nc + 1); s[2] = __ldg(a.scales + 3 * nc + 2);
+    const float opac = a.opacities ? __ldg(a.opacities + nc) : 1.f;
+
+    Rot R; float qn[4], qnorm, M[9]; Sym3 S;
+    quat_to_rotmat(q, R, qn, qnorm);
+    covar_from_rot_scale(R, s, M, S);
+
+    unsigned long long vis = 0ull;
+    if (live)
+        for (int c = 0; c < a.C; ++c)
+            if (__ldg(a.radii + (int64_t)c * a.N + n) > 0) vis |= 1ull << c;
+
+    const bool with_sh = a.sh_coeffs != nullptr && a.v_sh_coeffs != nullptr;
+    const int K = (a.sh_degree + 1) * (a.sh_degree + 1);
+    const int rs = sh_row_stride(K);
+    float* tile_in = sh_tiles + (size_t)warp * 2 * 32 * rs;
+    float* tile_out = tile_in + 32 * rs;
+    const int64_t row0 = (int64_t)blockIdx.x * BWD_THREADS + warp * 32;
+    const int rows = (int)max((int64_t)0, min((int64_t)32, a.N - row0));
+    if (with_sh) {
+        const unsigned row_mask = __ballot_sync(FULL, live && vis != 0ull);
+        if (row_mask && a.v_colors)
+            sh_rows_load<KVEC>(tile_in, a.sh_coeffs + (size_t)row0 * a.sh_stride_k * 3, rows, row_mask, K, a.sh_stride_k, lane);
+        for (int f = lane; f < 32 * rs; f += 32) tile_out[f] = 0.f;
+        __syncwarp();
+    }
+
+    float v_mean[3] = {0.f, 0.f, 0.f};
+    Sym3 v_S = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    float v_opac = 0.f;
+    if (live) {
+        for (int c = 0; c < a.C; ++c) {
+            if (!((vis >> c) & 1ull)) continue;
+            ProjOut o; ProjMid mid;
+            if (!project_one(cams[c], mean, S, W, H, a.eps2d, a.near_plane, a.far_plane, a.radius_clip, o, &mid)) continue;
+            const int64_t i = (int64_t)c * a.N + n;
+            ProjGradIn g;
+            if (a.v_means2d) { float2 v = __ldg(reinterpret_cast<const float2*>(a.v_means2d) + i); g.v_x2d = v.x; g.v_y2d = v.y; }
+            else { g.v_x2d = g.v_y2d = 0.f; }
+            g.v_depth = a.v_depths ? __ldg(a.v_depths + i) : 0.f;
+            if (a.v_conics) { g.v_conic_a = __ldg(a.v_conics + 3 * i); g.v_conic_b = __ldg(a.v_conics + 3 * i + 1); g.v_conic_c = __ldg(a.v_conics + 3 * i + 2); }
+            else { g.v_conic_a = g.v_conic_b = g.v_conic_c = 0.f; }
+            g.v_comp = a.v_compensations ? __ldg(a.v_compensations + i) : 0.f;
+            if (a.v_opacities_out) {
+                float vo = __ldg(a.v_opacities_out + i);
+                if (a.antialiased) { g.v_comp += vo * opac; v_opac += vo * o.comp; }
+                else v_opac += vo;
+            }
+            if (with_sh && a.v_colors) {
+                float dx = mean[0] - cams[c].campos[0], dy = mean[1] - cams[c].campos[1], dz = mean[2] - cams[c].campos[2];
+                float inv = 1.f / fmaxf(sqrtf(dx * dx + dy * dy + dz * dz), 1e-12f);
+                float ux = dx * inv, uy = dy * inv, uz = dz * inv;
+                float Y[16], w[16];
+                sh_basis(a.sh_degree, ux, uy, uz, Y);
+                const float* rin = tile_in + lane * rs;
+                float* rout = tile_out + lane * rs;
+                float cr = 0.5f, cg = 0.5f, cb = 0.5f;
+#pragma unroll 4
+                for (int k = 0; k < K; ++k) { cr += Y[k] * rin[3 * k]; cg += Y[k] * rin[3 * k + 1]; cb += Y[k] * rin[3 * k + 2]; }
+                float vr = cr > 0.f ? __ldg(a.v_colors + 3 * i) : 0.f;        // clamp_min(.,0) gate
+                float vg = cg > 0.f ? __ldg(a.v_colors + 3 * i + 1) : 0.f;
+                float vb = cb > 0.f ? __ldg(a.v_colors + 3 * i + 2) : 0.f;
+#pragma unroll 4
+                for (int k = 0; k < K; ++k) {
+                    w[k] = rin[3 * k] * vr + rin[3 * k + 1] * vg + rin[3 * k + 2] * vb;
+                    rout[3 * k] += Y[k] * vr; rout[3 * k + 1] += Y[k] * vg; rout[3 * k + 2] += Y[k] * vb;
+                }
+                float vx, vy, vz;
+                sh_basis_vjp(a.sh_degree, ux, uy, uz, w, vx, vy, vz);
+                float dp = ux * vx + uy * vy + uz * vz;
+                v_mean[0] += (vx - ux * dp) * inv; v_mean[1] += (vy - uy * dp) * inv; v_mean[2] += (vz - uz * dp) * inv;
+            }
+            project_one_bwd(cams[c], mean, S, a.eps2d, mid, g, v_mean, v_S);
+        }
+        float v_quat[4], v_scale[3];
+        covar_bwd(q, qn, qnorm, R, s, M, v_S, v_quat, v_scale);
+        if (a.accumulate) {
+            for (int k = 0; k < 3; ++k) { a.v_means[3 * n + k] += v_mean[k]; a.v_scales[3 * n + k] += v_scale[k]; }
+            for (int k = 0; k < 4; ++k) a.v_quats[4 * n + k] += v_quat[k];
+            if (a.v_opacities) a.v_opacities[n] += v_opac;
+        } else {
+            for (int k = 0; k < 3; ++k) { a.v_means[3 * n + k] = v_mean[k]; a.v_scales[3 * n + k] = v_scale[k]; }
+            reinterpret_cast<float4*>(a.v_quats)[n] = make_float4(v_quat[0], v_quat[1], v_quat[2], v_quat[3]);
+            if (a.v_opacities) a.v_opacities[n] = v_opac;
+        }
+    }
+    if (with_sh) {
+        __syncwarp();
+        if (rows > 0)
+            sh_rows_store<KVEC>(tile_out, a.v_sh_coeffs + (size_t)row0 * a.sh_stride_k * 3, rows, K, a.sh_stride_k, lane,
+                                a.accumulate != 0);
+    }
+}
+
+static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+}  // namespace b2s
+
+using namespace b2s;
+
+extern "C" int b2s_project_fwd(const b2s_project_fwd_args* a, b2s_stream_t stream) {
+    B2S_REQUIRE(a != nullptr, "null args");
+    B2S_REQUIRE(a->N >= 0 && a->C >= 0, "negative size");
+    B2S_REQUIRE(a->C <= B2S_MAX_CAMERAS_PER_CALL, "too many cameras in one call (loop over chunks)");
+    if (a->N == 0 || a->C == 0) return 0;
+    B2S_REQUIRE(a->means && a->quats && a->scales && a->viewmats && a->Ks, "null input");
+    B2S_REQUIRE(a->radii && a->means2d && a->depths && a->conics, "null output");
+    B2S_REQUIRE(aligned16(a->quats) && (reinterpret_cast<uintptr_t>(a->means2d) & 7u) == 0, "quats/means2d misaligned");
+    const bool sh = a->sh_coeffs != nullptr && a->colors != nullptr;
+    int K = 1;
+    if (sh) {
+        B2S_REQUIRE(a->sh_degree >= 0 && a->sh_degree <= 3, "sh_degree must be 0..3");
+        K = (a->sh_degree + 1) * (a->sh_degree + 1);
+        B2S_REQUIRE(a->sh_stride_k >= K, "sh_stride_k < (deg+1)^2");
+        B2S_REQUIRE(a->campos != nullptr, "campos required for SH");
+    }
+    if (a->tiles_per_gauss) B2S_REQUIRE(a->tile_size > 0 && a->tile_w > 0 && a->tile_h > 0, "bad tile geometry");
+    const bool vec = sh && K == 16 && a->sh_stride_k == 16 && aligned16(a->sh_coeffs);
+    size_t smem = ((a->C * sizeof(Camera) + 15) / 16) * 16;
+    if (sh) smem += (size_t)(FWD_THREADS / 32) * 32 * sh_row_stride(K) * sizeof(float);
+    dim3 grid((unsigned)cdiv(a->N, FWD_THREADS));
+    auto kern = vec ? project_fwd_kernel<16> : project_fwd_kernel<0>;
+    B2S_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<grid, FWD_THREADS, smem, (cudaStream_t)stream>>>(*a);
+    B2S_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int b2s_project_bwd(const b2s_project_bwd_args* a, b2s_stream_t stream) {
+    B2S_REQUIRE(a != nullptr, "null args");
+    B2S_REQUIRE(a->N >= 0 && a->C >= 0, "negative size");
+    B2S_REQUIRE(a->C <= B2S_MAX_CAMERAS_PER_CALL, "too many cameras in one call (loop over chunks)");
+    if (a->N == 0) return 0;
+    B2S_REQUIRE(a->means && a->quats && a->scales && a->viewmats && a->Ks && a->radii, "null input");
+    B2S_REQUIRE(a->v_means && a->v_quats && a->v_scales, "null gradient output");
+    B2S_REQUIRE(aligned16(a->quats) && aligned16(a->v_quats), "quats misaligned");
+    const bool sh = a->sh_coeffs != nullptr && a->v_sh_coeffs != nullptr;
+    int K = 1;
+    if (sh) {
+        B2S_REQUIRE(a->sh_degree >= 0 && a->sh_degree <= 3, "sh_degree must be 0..3");
+        K = (a->sh_degree + 1) * (a->sh_degree + 1);
+        B2S_REQUIRE(a->sh_stride_k >= K, "sh_stride_k < (deg+1)^2");
+        B2S_REQUIRE(a->campos != nullptr, "campos required for SH");
+    }
+    const bool vec = sh && K == 16 && a->sh_stride_k == 16 && aligned16(a->sh_coeffs) && aligned16(a->v_sh_coeffs);
+    size_t smem = ((a->C * sizeof(Camera) + 15) / 16) * 16;
+    if (sh) smem += (size_t)(BWD_THREADS / 32) * 2 * 32 * sh_row_stride(K) * sizeof(float);
+    dim3 grid((unsigned)cdiv(a->N, BWD_THREADS));
+    auto kern = vec ? project_bwd_kernel<16> : project_bwd_kernel<0>;
+    B2S_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<grid, BWD_THREADS, smem, (cudaStream_t)stream>>>(*a);
+    B2S_LAUNCH_CHECK();
+    return 0;
+}

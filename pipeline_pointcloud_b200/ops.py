@@ -1,0 +1,442 @@
+"""Stage-level operators of the rasterization path, mirroring gsplat's ``gsplat/cuda/_wrapper.py``
+(same names, argument meaning and error behaviour).  Each is a thin
+``torch.autograd.Function`` around one C-ABI call of ``libb2s.so``; torch only provides device
+memory, streams and autograd bookkeeping.
+
+Reference anchors: these ops run inside the ``rasterization()`` call that the reference's
+Train-Stage1 component makes through ``ns-train splatfacto``
+(source/container/src/main.py:1308-1316) or ``simple_trainer.py --packed``
+(source/container/src/main.py:1339-1347).
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Optional, Tuple
+
+import torch
+from torch import Tensor
+
+from . import _lib as L
+from ._lib import B2SError, check, f32c, ptr
+
+MAX_CAMS = 64  # B2S_MAX_CAMERAS_PER_CALL
+
+
+class StageTimer:
+    """Optional per-stage CUDA-event timing on the launching stream (used by bench.py inside its timed
+    region; two event records per stage, no synchronisation until ``summary()``)."""
+
+    def __init__(self):
+        self.events = []      # (name, start, end)
+        self.launches = 0     # kernels of libb2s.so launched (CUB's sort passes are counted separately)
+
+    class _Range:
+        def __init__(self, timer, name, launches):
+            self.t, self.name, self.launches = timer, name, launches
+
+        def __enter__(self):
+            self.s = torch.cuda.Event(enable_timing=True)
+            self.e = torch.cuda.Event(enable_timing=True)
+            self.s.record()
+            return self
+
+        def __exit__(self, *exc):
+            self.e.record()
+            self.t.events.append((self.name, self.s, self.e))
+            self.t.launches += self.launches
+
+    def range(self, name, launches=1):
+        return StageTimer._Range(self, name, launches)
+
+    def summary(self):
+        torch.cuda.synchronize()
+        out = {}
+        for name, s, e in self.events:
+            tot, n = out.get(name, (0.0, 0))
+            out[name] = (tot + s.elapsed_time(e), n + 1)
+        return {k: {"ms_total": v[0], "calls": v[1], "ms_avg": v[0] / v[1]} for k, v in out.items()}
+
+
+class _NullRange:
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        return False
+
+
+TIMER: Optional[StageTimer] = None
+
+
+def _stage(name, launches=1):
+    return TIMER.range(name, launches) if TIMER is not None else _NullRange()
+
+
+def _bit_length(v: int) -> int:
+    return int(v).bit_length()
+
+
+# ======================================================================================
+# stage 1: fused projection (+SH colour, + tile count)
+# ======================================================================================
+class _ProjectFused(torch.autograd.Function):
+    """radii, means2d, depths, conics, compensations, opacities_out, colors, tiles_per_gauss."""
+
+    @staticmethod
+    def forward(ctx, means, quats, scales, opacities, sh_coeffs, viewmats, Ks, campos, width, height, eps2d,
+                near_plane, far_plane, radius_clip, antialiased, calc_compensations, sh_degree, tile_size):
+        dev = L.require_cuda(means, quats, scales, viewmats, Ks)
+        means, quats, scales = f32c(means), f32c(quats), f32c(scales)
+        opacities, sh_coeffs = f32c(opacities), f32c(sh_coeffs)
+        viewmats, Ks, campos = f32c(viewmats), f32c(Ks), f32c(campos)
+        N, C = means.shape[0], viewmats.shape[0]
+        if quats.shape != (N, 4) or scales.shape != (N, 3) or means.shape != (N, 3):
+            raise B2SError("means [N,3], quats [N,4], scales [N,3] expected")
+        if viewmats.shape != (C, 4, 4) or Ks.shape != (C, 3, 3):
+            raise B2SError("viewmats [C,4,4], Ks [C,3,3] expected")
+        with_sh = sh_coeffs is not None
+        if with_sh and (sh_coeffs.dim() != 3 or sh_coeffs.shape[0] != N or sh_coeffs.shape[2] != 3):
+            raise B2SError("sh coefficients must be [N,K,3]")
+        o = dict(device=dev)
+        radii = torch.empty(C, N, dtype=torch.int32, **o)
+        means2d = torch.empty(C, N, 2, dtype=torch.float32, **o)
+        depths = torch.empty(C, N, dtype=torch.float32, **o)
+        conics = torch.empty(C, N, 3, dtype=torch.float32, **o)
+        comps = torch.empty(C, N, dtype=torch.float32, **o) if (calc_compensations or antialiased) else None
+        opac_out = torch.empty(C, N, dtype=torch.float32, **o) if opacities is not None else None
+        colors = torch.empty(C, N, 3, dtype=torch.float32, **o) if with_sh else None
+        tiles = torch.empty(C, N, dtype=torch.int32, **o) if tile_size else None
+        tw = (width + tile_size - 1) // tile_size if tile_size else 0
+        th = (height + tile_size - 1) // tile_size if tile_size else 0
+        lib = L.lib()
+        st = L.stream_ptr(dev)
+        for c0 in range(0, C, MAX_CAMS):
+            c1 = min(C, c0 + MAX_CAMS)
+            a = L.ProjectFwdArgs(
+                N=N, C=c1 - c0, means=ptr(means), quats=ptr(quats), scales=ptr(scales), opacities=ptr(opacities),
+                viewmats=ptr(viewmats[c0:c1]), Ks=ptr(Ks[c0:c1]), width=width, height=height, eps2d=eps2d,
+                near_plane=near_plane, far_plane=far_plane, radius_clip=radius_clip, antialiased=int(antialiased),
+                sh_coeffs=ptr(sh_coeffs), campos=ptr(campos[c0:c1]) if campos is not None else None,
+                sh_degree=int(sh_degree) if with_sh else 0, sh_stride_k=sh_coeffs.shape[1] if with_sh else 0,
+                tile_size=int(tile_size or 0), tile_w=tw, tile_h=th,
+                radii=ptr(radii[c0:c1]), means2d=ptr(means2d[c0:c1]), depths=ptr(depths[c0:c1]),
+                conics=ptr(conics[c0:c1]), compensations=ptr(comps[c0:c1]) if comps is not None else None,
+                opacities_out=ptr(opac_out[c0:c1]) if opac_out is not None else None,
+                colors=ptr(colors[c0:c1]) if colors is not None else None,
+                tiles_per_gauss=ptr(tiles[c0:c1]) if tiles is not None else None)
+            with _stage("project_fwd"):
+                check(lib.b2s_project_fwd(ctypes.byref(a), st), "b2s_project_fwd")
+        ctx.save_for_backward(means, quats, scales, opacities, sh_coeffs, viewmats, Ks, campos, radii)
+        ctx.cfg = (width, height, eps2d, near_plane, far_plane, radius_clip, bool(antialiased), sh_degree)
+        ctx.mark_non_differentiable(radii)
+        if tiles is not None:
+            ctx.mark_non_differentiable(tiles)
+        return radii, means2d, depths, conics, comps, opac_out, colors, tiles
+
+    @staticmethod
+    def backward(ctx, _v_radii, v_means2d, v_depths, v_conics, v_comps, v_opac_out, v_colors, _v_tiles):
+        means, quats, scales, opacities, sh_coeffs, viewmats, Ks, campos, radii = ctx.saved_tensors
+        width, height, eps2d, near_plane, far_plane, radius_clip, antialiased, sh_degree = ctx.cfg
+        if ctx.needs_input_grad[5] or ctx.needs_input_grad[6]:
+            raise NotImplementedError("gradients w.r.t. viewmats / Ks are not implemented")
+        N, C = means.shape[0], viewmats.shape[0]
+        dev = means.device
+        v_means2d, v_depths, v_conics = f32c(v_means2d), f32c(v_depths), f32c(v_conics)
+        v_comps, v_opac_out, v_colors = f32c(v_comps), f32c(v_opac_out), f32c(v_colors)
+        with_sh = sh_coeffs is not None
+        v_means = torch.empty_like(means)
+        v_quats = torch.empty_like(quats)
+        v_scales = torch.empty_like(scales)
+        v_opac = torch.empty_like(opacities) if opacities is not None else None
+        v_sh = None
+        if with_sh:
+            K = (sh_degree + 1) ** 2
+            v_sh = torch.empty_like(sh_coeffs) if K == sh_coeffs.shape[1] else torch.zeros_like(sh_coeffs)
+        lib = L.lib()
+        st = L.stream_ptr(dev)
+
+        def sl(t, c0, c1):
+            return ptr(t[c0:c1]) if t is not None else None
+
+        for c0 in range(0, max(C, 1), MAX_CAMS):
+            c1 = min(C, c0 + MAX_CAMS)
+            a = L.ProjectBwdArgs(
+                N=N, C=c1 - c0, means=ptr(means), quats=ptr(quats), scales=ptr(scales), opacities=ptr(opacities),
+                viewmats=ptr(viewmats[c0:c1]), Ks=ptr(Ks[c0:c1]), width=width, height=height, eps2d=eps2d,
+                near_plane=near_plane, far_plane=far_plane, radius_clip=radius_clip, antialiased=int(antialiased),
+                sh_coeffs=ptr(sh_coeffs), campos=sl(campos, c0, c1), sh_degree=int(sh_degree) if with_sh else 0,
+                sh_stride_k=sh_coeffs.shape[1] if with_sh else 0, radii=ptr(radii[c0:c1]),
+                v_means2d=sl(v_means2d, c0, c1), v_depths=sl(v_depths, c0, c1), v_conics=sl(v_conics, c0, c1),
+                v_compensations=sl(v_comps, c0, c1), v_opacities_out=sl(v_opac_out, c0, c1),
+                v_colors=sl(v_colors, c0, c1), accumulate=int(c0 > 0),
+                v_means=ptr(v_means), v_quats=ptr(v_quats), v_scales=ptr(v_scales), v_opacities=ptr(v_opac),
+                v_sh_coeffs=ptr(v_sh))
+            with _stage("project_bwd"):
+                check(lib.b2s_project_bwd(ctypes.byref(a), st), "b2s_project_bwd")
+        return (v_means, v_quats, v_scales, v_opac, v_sh) + (None,) * 13
+
+
+def fully_fused_projection(
+    means: Tensor, covars: Optional[Tensor], quats: Optional[Tensor], scales: Optional[Tensor], viewmats: Tensor,
+    Ks: Tensor, width: int, height: int, eps2d: float = 0.3, near_plane: float = 0.01, far_plane: float = 1e10,
+    radius_clip: float = 0.0, packed: bool = False, sparse_grad: bool = False, calc_compensations: bool = False,
+    camera_model: str = "pinhole",
+):
+    """gsplat ``fully_fused_projection``: (radii, means2d, depths, conics, compensations), all ``[C,N,...]``;
+    with ``packed=True``: (camera_ids, gaussian_ids, radii, means2d, depths, conics, compensations) over the
+    ``nnz`` visible pairs, camera-major / Gaussian-ascending."""
+    if camera_model != "pinhole":
+        raise NotImplementedError("only camera_model='pinhole' is implemented")
+    if covars is not None:
+        raise NotImplementedError("pass quats and scales (precomputed covars are not implemented)")
+    if sparse_grad:
+        raise NotImplementedError("sparse_grad is not implemented")
+    if quats is None or scales is None:
+        raise ValueError("quats and scales are required")
+    radii, means2d, depths, conics, comps, _, _, _ = _ProjectFused.apply(
+        means, quats, scales, None, None, viewmats, Ks, None, int(width), int(height), float(eps2d), float(near_plane),
+        float(far_plane), float(radius_clip), False, bool(calc_compensations), 0, 0)
+    if not packed:
+        return radii, means2d, depths, conics, comps
+    N = means.shape[0]
+    sel = (radii.reshape(-1) > 0).nonzero(as_tuple=True)[0]
+    camera_ids, gaussian_ids = sel // N, sel % N
+    return (camera_ids, gaussian_ids, radii.reshape(-1)[sel], means2d.reshape(-1, 2)[sel], depths.reshape(-1)[sel],
+            conics.reshape(-1, 3)[sel], comps.reshape(-1)[sel] if comps is not None else None)
+
+
+# ======================================================================================
+# stand-alone SH / covariance ops
+# ======================================================================================
+class _SphericalHarmonics(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, degree, dirs, coeffs, masks):
+        dev = L.require_cuda(dirs, coeffs)
+        dirs, coeffs = f32c(dirs), f32c(coeffs)
+        K = coeffs.shape[-2]
+        if (degree + 1) ** 2 > K:
+            raise B2SError("coeffs has fewer than (degree+1)^2 bases")
+        if dirs.shape[:-1] != coeffs.shape[:-2] or dirs.shape[-1] != 3 or coeffs.shape[-1] != 3:
+            raise B2SError("dirs [...,3] and coeffs [...,K,3] must share their leading shape")
+        M = dirs.numel() // 3
+        m8 = masks.contiguous().to(torch.uint8) if masks is not None else None
+        colors = torch.empty(dirs.shape, dtype=torch.float32, device=dev)
+        check(L.lib().b2s_sh_fwd(M, degree, K, ptr(dirs), ptr(coeffs), ptr(m8), ptr(colors), L.stream_ptr(dev)), "b2s_sh_fwd")
+        ctx.save_for_backward(dirs, coeffs, m8)
+        ctx.degree = degree
+        return colors
+
+    @staticmethod
+    def backward(ctx, v_colors):
+        dirs, coeffs, m8 = ctx.saved_tensors
+        degree, K = ctx.degree, coeffs.shape[-2]
+        M = dirs.numel() // 3
+        v_colors = f32c(v_colors)
+        v_coeffs = torch.zeros_like(coeffs) if (degree + 1) ** 2 < K else torch.empty_like(coeffs)
+        v_dirs = torch.empty_like(dirs) if ctx.needs_input_grad[1] else None
+        check(L.lib().b2s_sh_bwd(M, degree, K, ptr(dirs), ptr(coeffs), ptr(m8), ptr(v_colors), ptr(v_coeffs), ptr(v_dirs),
+                                 L.stream_ptr(dirs.device)), "b2s_sh_bwd")
+        return None, v_dirs, v_coeffs, None
+
+
+def spherical_harmonics(degrees_to_use: int, dirs: Tensor, coeffs: Tensor, masks: Optional[Tensor] = None) -> Tensor:
+    """gsplat ``spherical_harmonics``: colours [...,3] from dirs [...,3] (normalised inside) and coeffs [...,K,3]."""
+    if not 0 <= degrees_to_use <= 3:
+        raise NotImplementedError("SH degree 0..3 (the range the training path uses)")
+    return _SphericalHarmonics.apply(int(degrees_to_use), dirs, coeffs, masks)
+
+
+def quat_scale_to_covar_preci(quats: Tensor, scales: Tensor, compute_covar: bool = True, compute_preci: bool = True,
+                              triu: bool = False):
+    """gsplat ``quat_scale_to_covar_preci`` (forward only: the fused projection never materialises covariances)."""
+    if quats.requires_grad or scales.requires_grad:
+        raise NotImplementedError("quat_scale_to_covar_preci is forward-only; the training path fuses it into projection")
+    dev = L.require_cuda(quats, scales)
+    quats, scales = f32c(quats), f32c(scales)
+    N = quats.shape[0]
+    covars = torch.empty(N, 3, 3, device=dev) if compute_covar else None
+    precis = torch.empty(N, 3, 3, device=dev) if compute_preci else None
+    check(L.lib().b2s_quat_scale_to_covar_preci(N, ptr(quats), ptr(scales), ptr(covars), ptr(precis), L.stream_ptr(dev)),
+          "b2s_quat_scale_to_covar_preci")
+    if triu:
+        idx = torch.tensor([0, 1, 2, 4, 5, 8], device=dev)
+        covars = covars.reshape(N, 9)[:, idx] if covars is not None else None
+        precis = precis.reshape(N, 9)[:, idx] if precis is not None else None
+    return covars, precis
+
+
+# ======================================================================================
+# stage 2: binning
+# ======================================================================================
+@torch.no_grad()
+def isect_tiles(means2d: Tensor, radii: Tensor, depths: Tensor, tile_size: int, tile_width: int, tile_height: int,
+                sort: bool = True, packed: bool = False, n_cameras: Optional[int] = None,
+                camera_ids: Optional[Tensor] = None, gaussian_ids: Optional[Tensor] = None,
+                tiles_per_gauss: Optional[Tensor] = None) -> Tuple[Tensor, Tensor, Tensor]:
+    """gsplat ``isect_tiles``: (tiles_per_gauss int32, isect_ids int64, flatten_ids int32), sorted by
+    (camera, tile, depth bits) when ``sort``.  ``tiles_per_gauss`` may be passed in when stage 1 already made it."""
+    dev = L.require_cuda(means2d, radii, depths)
+    if packed:
+        if camera_ids is None or n_cameras is None:
+            raise ValueError("packed=True needs n_cameras and camera_ids")
+        M, N, C = means2d.shape[0], 0, int(n_cameras)
+        cam = camera_ids.contiguous().to(torch.int64)
+        out_shape = (M,)
+    else:
+        C, N = means2d.shape[:2]
+        M, cam = C * N, None
+        out_shape = (C, N)
+    means2d, depths = f32c(means2d), f32c(depths)
+    radii = radii.contiguous().to(torch.int32)
+    lib, st = L.lib(), L.stream_ptr(dev)
+    if tiles_per_gauss is None:
+        tiles_per_gauss = torch.empty(out_shape, dtype=torch.int32, device=dev)
+        check(lib.b2s_isect_count(M, ptr(means2d), ptr(radii), tile_size, tile_width, tile_height, ptr(tiles_per_gauss), st),
+              "b2s_isect_count")
+    else:
+        tiles_per_gauss = tiles_per_gauss.contiguous()
+    cum = torch.empty(max(M, 1), dtype=torch.int32, device=dev)
+    total = torch.empty(1, dtype=torch.int64, device=dev)
+    ws = torch.empty(int(lib.b2s_isect_scan_workspace_bytes(M)), dtype=torch.uint8, device=dev)
+    with _stage("isect_scan"):
+        check(lib.b2s_isect_scan(M, ptr(tiles_per_gauss), ptr(cum), ptr(total), ptr(ws), ws.numel(), st), "b2s_isect_scan")
+    n_isects = int(total.item())          # the one host sync of a forward: sizes the key/value buffers
+    if n_isects >= 2 ** 31:
+        raise B2SError(f"n_isects = {n_isects} does not fit the int32 offsets of the API")
+    isect_ids = torch.empty(n_isects, dtype=torch.int64, device=dev)
+    flatten_ids = torch.empty(n_isects, dtype=torch.int32, device=dev)
+    with _stage("isect_fill"):
+        check(lib.b2s_isect_fill(M, N, ptr(cam), ptr(means2d), ptr(radii), ptr(depths), ptr(cum), tile_size, tile_width,
+                                 tile_height, ptr(isect_ids), ptr(flatten_ids), st), "b2s_isect_fill")
+    if sort and n_isects > 0:
+        key_bits = 32 + _bit_length(tile_width * tile_height) + _bit_length(C)
+        ids_sorted = torch.empty_like(isect_ids)
+        flat_sorted = torch.empty_like(flatten_ids)
+        ws = torch.empty(int(lib.b2s_isect_sort_workspace_bytes(n_isects)), dtype=torch.uint8, device=dev)
+        with _stage("isect_sort", launches=0):
+            check(lib.b2s_isect_sort(n_isects, min(64, key_bits), ptr(isect_ids), ptr(flatten_ids), ptr(ids_sorted),
+                                     ptr(flat_sorted), ptr(ws), ws.numel(), st), "b2s_isect_sort")
+        isect_ids, flatten_ids = ids_sorted, flat_sorted
+    return tiles_per_gauss, isect_ids, flatten_ids
+
+
+@torch.no_grad()
+def isect_offset_encode(isect_ids: Tensor, n_cameras: int, tile_width: int, tile_height: int) -> Tensor:
+    """gsplat ``isect_offset_encode``: int32 [C, tile_height, tile_width]."""
+    dev = L.require_cuda(isect_ids)
+    isect_ids = isect_ids.contiguous()
+    offsets = torch.empty(n_cameras, tile_height, tile_width, dtype=torch.int32, device=dev)
+    with _stage("isect_offsets"):
+        check(L.lib().b2s_isect_offsets(isect_ids.numel(), ptr(isect_ids), n_cameras, tile_width, tile_height, ptr(offsets),
+                                        L.stream_ptr(dev)), "b2s_isect_offsets")
+    return offsets
+
+
+# ======================================================================================
+# stage 3: compositing
+# ======================================================================================
+_CHANNELS = (1, 2, 3, 4, 8, 16, 32)
+
+
+class _RasterizeToPixels(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, means2d, conics, colors, opacities, backgrounds, width, height, tile_size, isect_offsets,
+                flatten_ids, absgrad):
+        dev = L.require_cuda(means2d, conics, colors, opacities, isect_offsets, flatten_ids)
+        means2d, conics, colors, opacities = f32c(means2d), f32c(conics), f32c(colors), f32c(opacities)
+        backgrounds = f32c(backgrounds)
+        C, th, tw = isect_offsets.shape
+        ch = colors.shape[-1]
+        render = torch.empty(C, height, width, ch, dtype=torch.float32, device=dev)
+        alphas = torch.empty(C, height, width, 1, dtype=torch.float32, device=dev)
+        last_ids = torch.empty(C, height, width, dtype=torch.int32, device=dev)
+        final_T = torch.empty(C, height, width, dtype=torch.float32, device=dev)
+        isect_offsets = isect_offsets.contiguous()
+        flatten_ids = flatten_ids.contiguous()
+        a = L.CompositeFwdArgs(
+            C=C, width=width, height=height, tile_size=tile_size, tile_w=tw, tile_h=th, channels=ch,
+            n_isects=flatten_ids.numel(), means2d=ptr(means2d), conics=ptr(conics), colors=ptr(colors),
+            opacities=ptr(opacities), backgrounds=ptr(backgrounds), isect_offsets=ptr(isect_offsets),
+            flatten_ids=ptr(flatten_ids), render_colors=ptr(render), render_alphas=ptr(alphas), last_ids=ptr(last_ids),
+            final_T=ptr(final_T))
+        with _stage("composite_fwd"):
+            check(L.lib().b2s_composite_fwd(ctypes.byref(a), L.stream_ptr(dev)), "b2s_composite_fwd")
+        ctx.save_for_backward(means2d, conics, colors, opacities, backgrounds, isect_offsets, flatten_ids, alphas,
+                              last_ids, final_T)
+        ctx.cfg = (width, height, tile_size, absgrad)
+        return render, alphas
+
+    @staticmethod
+    def backward(ctx, v_render, v_alphas):
+        (means2d, conics, colors, opacities, backgrounds, isect_offsets, flatten_ids, alphas, last_ids,
+         final_T) = ctx.saved_tensors
+        width, height, tile_size, absgrad = ctx.cfg
+        dev = means2d.device
+        C, th, tw = isect_offsets.shape
+        ch = colors.shape[-1]
+        v_render, v_alphas = f32c(v_render), f32c(v_alphas)
+        v_means2d = torch.zeros_like(means2d)
+        v_conics = torch.zeros_like(conics)
+        v_colors = torch.zeros_like(colors)
+        v_opac = torch.zeros_like(opacities)
+        v_abs = torch.zeros_like(means2d) if absgrad else None
+        a = L.CompositeBwdArgs(
+            C=C, width=width, height=height, tile_size=tile_size, tile_w=tw, tile_h=th, channels=ch,
+            n_isects=flatten_ids.numel(), means2d=ptr(means2d), conics=ptr(conics), colors=ptr(colors),
+            opacities=ptr(opacities), backgrounds=ptr(backgrounds), isect_offsets=ptr(isect_offsets),
+            flatten_ids=ptr(flatten_ids), render_alphas=ptr(alphas), last_ids=ptr(last_ids), final_T=ptr(final_T),
+            v_render_colors=ptr(v_render), v_render_alphas=ptr(v_alphas), v_means2d=ptr(v_means2d),
+            v_means2d_abs=ptr(v_abs), v_conics=ptr(v_conics), v_colors=ptr(v_colors), v_opacities=ptr(v_opac))
+        with _stage("composite_bwd"):
+            check(L.lib().b2s_composite_bwd(ctypes.byref(a), L.stream_ptr(dev)), "b2s_composite_bwd")
+        v_bg = None
+        if backgrounds is not None and ctx.needs_input_grad[4]:
+            v_bg = (v_render * final_T[..., None]).sum(dim=(1, 2))
+        if absgrad:
+            getattr(ctx, "absgrad_holder", means2d).absgrad = v_abs
+        return v_means2d, v_conics, v_colors, v_opac, v_bg, None, None, None, None, None, None
+
+
+def rasterize_to_pixels(means2d: Tensor, conics: Tensor, colors: Tensor, opacities: Tensor, image_width: int,
+                        image_height: int, tile_size: int, isect_offsets: Tensor, flatten_ids: Tensor,
+                        backgrounds: Optional[Tensor] = None, masks: Optional[Tensor] = None, packed: bool = False,
+                        absgrad: bool = False) -> Tuple[Tensor, Tensor]:
+    """gsplat ``rasterize_to_pixels``: (render_colors [C,H,W,ch], render_alphas [C,H,W,1]).  Rows of the
+    per-splat tensors are addressed through ``flatten_ids`` so dense ``[C,N,..]`` and packed ``[nnz,..]`` both work."""
+    if masks is not None:
+        raise NotImplementedError("tile masks are not implemented")
+    if tile_size != 16:
+        raise NotImplementedError("tile_size must be 16")
+    C = isect_offsets.shape[0]
+    if packed:
+        if means2d.dim() != 2:
+            raise ValueError("packed=True expects [nnz,..] tensors")
+    elif means2d.dim() != 3 or means2d.shape[0] != C:
+        raise ValueError("dense layout expects [C,N,..] tensors")
+    ch = colors.shape[-1]
+    pad = 0
+    if ch not in _CHANNELS:
+        if ch > 32:
+            raise NotImplementedError("more than 32 channels: chunk them (rasterization() does)")
+        target = next(c for c in _CHANNELS if c >= ch)
+        pad = target - ch
+        colors = torch.cat([colors, colors.new_zeros(colors.shape[:-1] + (pad,))], dim=-1)
+        if backgrounds is not None:
+            backgrounds = torch.cat([backgrounds, backgrounds.new_zeros(backgrounds.shape[:-1] + (pad,))], dim=-1)
+    holder = means2d
+    fn = _RasterizeToPixels
+    # absgrad: gsplat attaches `.absgrad` to the means2d tensor the caller passed in
+    render, alphas = _apply_with_holder(fn, holder, means2d, conics, colors, opacities, backgrounds, int(image_width),
+                                        int(image_height), int(tile_size), isect_offsets, flatten_ids, bool(absgrad))
+    if pad:
+        render = render[..., :ch]
+    return render, alphas
+
+
+def _apply_with_holder(fn, holder, *args):
+    """Runs ``fn.apply`` and lets its backward find the tensor that should receive ``.absgrad``."""
+    out = fn.apply(*args)
+    node = out[0].grad_fn
+    if node is not None:
+        node.absgrad_holder = holder
+    return out

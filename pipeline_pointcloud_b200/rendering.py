@@ -1,0 +1,169 @@
+"""``rasterization()`` -- drop-in for ``gsplat.rendering.rasterization``.
+
+This is the call the reference's splat-training stage makes on every iteration: nerfstudio
+``SplatfactoModel.get_outputs`` behind ``ns-train splatfacto`` (source/container/src/main.py:1308-1316,
+``packed=False``, ``render_mode="RGB+ED"``) and ``simple_trainer.Runner.rasterize_splats`` behind
+``simple_trainer.py --packed`` (source/container/src/main.py:1339-1347, ``packed=True``).
+
+Same argument surface and returned ``(render_colors, render_alphas, meta)``.  Every stage runs in a
+hand-written sm_100a kernel of ``libb2s.so``; there is no CPU path and no other backend, and
+options that are not implemented raise ``NotImplementedError`` instead of falling back.
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, Optional, Tuple
+
+import torch
+from torch import Tensor
+
+from . import ops
+from ._lib import require_cuda
+
+
+def rasterization(
+    means: Tensor,        # [N,3]
+    quats: Tensor,        # [N,4] wxyz, un-normalised
+    scales: Tensor,       # [N,3] post-exp
+    opacities: Tensor,    # [N] post-sigmoid
+    colors: Tensor,       # [N,D] | [C,N,D] | SH: [N,K,3] | [C,N,K,3]
+    viewmats: Tensor,     # [C,4,4] world->camera
+    Ks: Tensor,           # [C,3,3]
+    width: int,
+    height: int,
+    near_plane: float = 0.01,
+    far_plane: float = 1e10,
+    radius_clip: float = 0.0,
+    eps2d: float = 0.3,
+    sh_degree: Optional[int] = None,
+    packed: bool = True,
+    tile_size: int = 16,
+    backgrounds: Optional[Tensor] = None,
+    render_mode: str = "RGB",
+    sparse_grad: bool = False,
+    absgrad: bool = False,
+    rasterize_mode: str = "classic",
+    channel_chunk: int = 32,
+    distributed: bool = False,
+    camera_model: str = "pinhole",
+    covars: Optional[Tensor] = None,
+    **unsupported,
+) -> Tuple[Tensor, Tensor, Dict]:
+    if unsupported:
+        raise NotImplementedError(f"unsupported rasterization() options: {sorted(unsupported)}")
+    if camera_model != "pinhole":
+        raise NotImplementedError("only camera_model='pinhole' is implemented")
+    if covars is not None:
+        raise NotImplementedError("precomputed covars are not implemented (pass quats and scales)")
+    if sparse_grad:
+        raise NotImplementedError("sparse_grad is not implemented")
+    if tile_size != 16:
+        raise NotImplementedError("tile_size must be 16")
+    if render_mode not in ("RGB", "D", "ED", "RGB+D", "RGB+ED"):
+        raise ValueError(f"unknown render_mode {render_mode!r}")
+    if rasterize_mode not in ("classic", "antialiased"):
+        raise ValueError(f"unknown rasterize_mode {rasterize_mode!r}")
+    if distributed:
+        from .distributed import rasterization_distributed
+        return rasterization_distributed(
+            means, quats, scales, opacities, colors, viewmats, Ks, width, height, near_plane=near_plane,
+            far_plane=far_plane, radius_clip=radius_clip, eps2d=eps2d, sh_degree=sh_degree, packed=packed,
+            backgrounds=backgrounds, render_mode=render_mode, absgrad=absgrad, rasterize_mode=rasterize_mode)
+
+    require_cuda(means, quats, scales, opacities, colors, viewmats, Ks)
+    N, C = means.shape[0], viewmats.shape[0]
+    if means.shape != (N, 3) or quats.shape != (N, 4) or scales.shape != (N, 3) or opacities.shape != (N,):
+        raise ValueError("means [N,3], quats [N,4], scales [N,3], opacities [N] expected")
+    if viewmats.shape != (C, 4, 4) or Ks.shape != (C, 3, 3):
+        raise ValueError("viewmats [C,4,4] and Ks [C,3,3] expected")
+    if sh_degree is None:
+        if not ((colors.dim() == 2 and colors.shape[0] == N) or (colors.dim() == 3 and colors.shape[:2] == (C, N))):
+            raise ValueError("colors must be [N,D] or [C,N,D] when sh_degree is None")
+    else:
+        if not ((colors.dim() == 3 and colors.shape[0] == N and colors.shape[2] == 3)
+                or (colors.dim() == 4 and colors.shape[:2] == (C, N) and colors.shape[3] == 3)):
+            raise ValueError("colors must be [N,K,3] or [C,N,K,3] when sh_degree is set")
+        if (sh_degree + 1) ** 2 > colors.shape[-2]:
+            raise ValueError("sh_degree needs more SH bases than colors provides")
+    if backgrounds is not None and backgrounds.shape[0] != C:
+        raise ValueError("backgrounds must be [C,D]")
+
+    antialiased = rasterize_mode == "antialiased"
+    width, height = int(width), int(height)
+    tw, th = math.ceil(width / tile_size), math.ceil(height / tile_size)
+
+    # ---- stage 1: projection (+ SH colour + tile counts) in one kernel ------------------------------------
+    fused_sh = sh_degree is not None and colors.dim() == 3
+    campos = None
+    if sh_degree is not None:
+        campos = torch.linalg.inv(viewmats.detach().float())[:, :3, 3].contiguous()
+    radii, means2d, depths, conics, _comps, opac, sh_cols, tiles = ops._ProjectFused.apply(
+        means, quats, scales, opacities, colors if fused_sh else None, viewmats, Ks, campos, width, height, float(eps2d),
+        float(near_plane), float(far_plane), float(radius_clip), antialiased, False,
+        int(sh_degree) if fused_sh else 0, tile_size)
+
+    if sh_degree is None:
+        cols = colors if colors.dim() == 3 else colors[None].expand(C, N, colors.shape[-1])
+    elif fused_sh:
+        cols = sh_cols
+    else:  # per-camera coefficients [C,N,K,3]
+        dirs = means[None, :, :] - campos[:, None, :]
+        cols = ops.spherical_harmonics(sh_degree, dirs, colors, masks=radii > 0)
+        cols = torch.clamp_min(cols + 0.5, 0.0)
+
+    if render_mode in ("RGB+D", "RGB+ED"):
+        cols = torch.cat([cols, depths[..., None]], dim=-1)
+        if backgrounds is not None:
+            backgrounds = torch.cat([backgrounds, torch.zeros_like(backgrounds[:, :1])], dim=-1)
+    elif render_mode in ("D", "ED"):
+        cols = depths[..., None]
+        if backgrounds is not None:
+            backgrounds = torch.zeros_like(backgrounds[:, :1])
+
+    # ---- packed layout: compact the visible pairs (camera-major, Gaussian-ascending) ----------------------
+    camera_ids = gaussian_ids = None
+    if packed:
+        sel = (radii.reshape(-1) > 0).nonzero(as_tuple=True)[0]
+        camera_ids, gaussian_ids = sel // N, sel % N
+        radii_m = radii.reshape(-1)[sel]
+        means2d_m = means2d.reshape(-1, 2)[sel]
+        depths_m = depths.reshape(-1)[sel]
+        conics_m = conics.reshape(-1, 3)[sel]
+        opac_m = opac.reshape(-1)[sel]
+        cols_m = cols.reshape(-1, cols.shape[-1])[sel]
+        tiles_m = tiles.reshape(-1)[sel]
+    else:
+        radii_m, means2d_m, depths_m, conics_m, opac_m, cols_m, tiles_m = radii, means2d, depths, conics, opac, cols, tiles
+
+    # ---- stage 2: binning --------------------------------------------------------------------------------
+    tiles_per_gauss, isect_ids, flatten_ids = ops.isect_tiles(
+        means2d_m, radii_m, depths_m, tile_size, tw, th, sort=True, packed=packed, n_cameras=C, camera_ids=camera_ids,
+        gaussian_ids=gaussian_ids, tiles_per_gauss=tiles_m)
+    isect_offsets = ops.isect_offset_encode(isect_ids, C, tw, th)
+
+    # ---- stage 3: compositing ----------------------------------------------------------------------------
+    ch = cols_m.shape[-1]
+    if ch > channel_chunk:
+        outs = []
+        for c0 in range(0, ch, channel_chunk):
+            bg = backgrounds[..., c0:c0 + channel_chunk] if backgrounds is not None else None
+            rc, ra = ops.rasterize_to_pixels(means2d_m, conics_m, cols_m[..., c0:c0 + channel_chunk], opac_m, width, height,
+                                             tile_size, isect_offsets, flatten_ids, backgrounds=bg, packed=packed,
+                                             absgrad=absgrad)
+            outs.append(rc)
+        render_colors, render_alphas = torch.cat(outs, dim=-1), ra
+    else:
+        render_colors, render_alphas = ops.rasterize_to_pixels(
+            means2d_m, conics_m, cols_m, opac_m, width, height, tile_size, isect_offsets, flatten_ids,
+            backgrounds=backgrounds, packed=packed, absgrad=absgrad)
+    if render_mode in ("ED", "RGB+ED"):
+        render_colors = torch.cat(
+            [render_colors[..., :-1], render_colors[..., -1:] / render_alphas.clamp(min=1e-10)], dim=-1)
+
+    meta = {
+        "camera_ids": camera_ids, "gaussian_ids": gaussian_ids, "radii": radii_m, "means2d": means2d_m,
+        "depths": depths_m, "conics": conics_m, "opacities": opac_m, "tile_width": tw, "tile_height": th,
+        "tiles_per_gauss": tiles_per_gauss, "isect_ids": isect_ids, "flatten_ids": flatten_ids,
+        "isect_offsets": isect_offsets, "width": width, "height": height, "tile_size": tile_size, "n_cameras": C,
+    }
+    return render_colors, render_alphas, meta
