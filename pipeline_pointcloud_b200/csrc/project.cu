@@ -129,7 +129,7 @@ __global__ void __launch_bounds__(FWD_THREADS) project_fwd_kernel(const b2s_proj
         a.depths[i] = o.depth;
         a.conics[3 * i] = o.conic_a; a.conics[3 * i + 1] = o.conic_b; a.conics[3 * i + 2] = o.conic_c;
         if (a.compensations) a.compensations[i] = o.comp;
-        if (a.opacities_out) a.opacities_out[i] = o.radius > 0 ? (a.antialiased ? opac * o.comp : opac) : 0.f;
+        if (a.opacities_out) a.opacities_out[i] = a.antialiased ? opac * o.comp : opac;  // comp == 0 on culled rows
         if (a.tiles_per_gauss) {
             int cnt = 0;
             if (o.radius > 0) {
