@@ -189,6 +189,7 @@ def main():
     ap.add_argument("--packed", action="store_true", help="packed=True layout (default: dense, as ns-train splatfacto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=None)
+    ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (profiling runs only)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -310,10 +311,13 @@ def main():
         torch.cuda.current_stream().synchronize()      # the caller reads the host buffers after every step
 
     e2e_steps = args.e2e_steps or max(3, min(args.steps, 10))
-    for _ in range(2):
-        e2e_step()
-    e2e_ms = timed(e2e_step, e2e_steps) / e2e_steps
-    e2e_value = pix_per_step / (e2e_ms * 1e-3) / 1e6
+    if args.no_e2e:
+        e2e_ms, e2e_value = float("nan"), None
+    else:
+        for _ in range(2):
+            e2e_step()
+        e2e_ms = timed(e2e_step, e2e_steps) / e2e_steps
+        e2e_value = pix_per_step / (e2e_ms * 1e-3) / 1e6
 
     if rank != 0:
         if world > 1:

@@ -62,7 +62,19 @@ B2S_HD void camera_setup(Camera& c, const float* viewmat, const float* K, const 
     c.lim_yp = RN_ADD(RN_DIV(RN_SUB(H, c.cy), c.fy), RN_MUL(0.3f, tan_fovy));
     c.lim_yn = RN_ADD(RN_DIV(c.cy, c.fy), RN_MUL(0.3f, tan_fovy));
     if (campos) { c.campos[0] = campos[0]; c.campos[1] = campos[1]; c.campos[2] = campos[2]; }
-    else { c.campos[0] = c.campos[1] = c.campos[2] = 0.f; }
+    else {
+        // camera centre = translation column of inverse(viewmat) = -A^-1 t for the affine [A | t]
+        // (cofactor inverse, so a non-orthonormal A is handled like torch.linalg.inv does)
+        const float* R = c.R;
+        float c00 = R[4] * R[8] - R[5] * R[7], c01 = R[2] * R[7] - R[1] * R[8], c02 = R[1] * R[5] - R[2] * R[4];
+        float c10 = R[5] * R[6] - R[3] * R[8], c11 = R[0] * R[8] - R[2] * R[6], c12 = R[2] * R[3] - R[0] * R[5];
+        float c20 = R[3] * R[7] - R[4] * R[6], c21 = R[1] * R[6] - R[0] * R[7], c22 = R[0] * R[4] - R[1] * R[3];
+        float det = R[0] * c00 + R[1] * c10 + R[2] * c20;
+        float id = 1.f / det;
+        c.campos[0] = -(c00 * c.t[0] + c01 * c.t[1] + c02 * c.t[2]) * id;
+        c.campos[1] = -(c10 * c.t[0] + c11 * c.t[1] + c12 * c.t[2]) * id;
+        c.campos[2] = -(c20 * c.t[0] + c21 * c.t[1] + c22 * c.t[2]) * id;
+    }
 }
 
 // ---------------------------------------------------------------------------------------------

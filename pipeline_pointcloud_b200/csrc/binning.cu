@@ -37,7 +37,9 @@ constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
 // status word: bits 63..62 = flag (0 none, 1 tile aggregate, 2 inclusive prefix), bits 61..0 = value
 constexpr unsigned long long FLAG_AGG = 1ull << 62, FLAG_INC = 2ull << 62, VAL_MASK = (1ull << 62) - 1;
 
+template <bool GATHER>  // GATHER: scan in[idx[i]] (values taken in a permuted order)
 __global__ void __launch_bounds__(SCAN_THREADS) scan_kernel(int64_t M, const int32_t* __restrict__ in,
+                                                            const int32_t* __restrict__ idx,
                                                             int32_t* __restrict__ out, int64_t* __restrict__ total,
                                                             unsigned long long* status, unsigned int* tile_counter) {
     __shared__ unsigned int s_tile;
@@ -51,7 +53,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_kernel(int64_t M, const int
     unsigned long long tsum = 0;
 #pragma unroll
     for (int k = 0; k < SCAN_ITEMS; ++k) {
-        v[k] = (base + k < M) ? in[base + k] : 0;
+        v[k] = (base + k < M) ? (GATHER ? in[idx[base + k]] : in[base + k]) : 0;
         tsum += (unsigned long long)v[k];
     }
     // block exclusive scan of per-thread sums
@@ -154,6 +156,121 @@ __global__ void isect_offsets_kernel(int64_t n, const int64_t* __restrict__ keys
         for (int64_t t = cur_lin + 1; t < total_tiles; ++t) offsets[t] = (int32_t)n;
 }
 
+
+// =================================================================================================
+// Depth-first binning (the training path).
+//
+// The reference sorts n_isects 64-bit (camera | tile | depth) keys: 6 radix passes over 12-byte records.
+// The same order is reached with far less traffic by sorting *Gaussians* by depth once (M 32-bit keys),
+// emitting the tile intersections in that order, and stable-splitting them by (camera, tile) with two
+// 8-bit radix passes over 8-byte records:
+//     within a tile: ascending depth bits, ties by ascending flat index   == the reference's stable sort.
+// isect_ids (the 64-bit keys) are never needed by compositing and are rebuilt on demand.
+// =================================================================================================
+__global__ void depth_keys_kernel(int64_t M, const float* __restrict__ depths, const int32_t* __restrict__ radii,
+                                  uint32_t* __restrict__ keys, int32_t* __restrict__ vals) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= M) return;
+    keys[i] = radii[i] > 0 ? __float_as_uint(depths[i]) : 0xFFFFFFFFu;  // culled rows sort last
+    vals[i] = (int32_t)i;
+}
+
+// One warp expands 32 depth-ordered Gaussians; lanes stride over the warp's output range so that the
+// (tile key, flat id) stores are fully coalesced.
+constexpr int EXP_THREADS = 256;
+__global__ void __launch_bounds__(EXP_THREADS) expand_kernel(int64_t M, int64_t N, const int64_t* __restrict__ camera_ids,
+                                                             const int32_t* __restrict__ sorted_ids,
+                                                             const int32_t* __restrict__ cum_sorted,
+                                                             const float2* __restrict__ means2d,
+                                                             const int32_t* __restrict__ radii, float tile_size, int tile_w,
+                                                             int tile_h, int tile_bits, uint32_t* __restrict__ tile_keys,
+                                                             int32_t* __restrict__ vals) {
+    __shared__ int s_start[EXP_THREADS];   // output offset of each Gaussian relative to its warp's first
+    __shared__ int s_x0[EXP_THREADS], s_w[EXP_THREADS], s_id[EXP_THREADS];
+    __shared__ uint32_t s_base[EXP_THREADS];  // cam << tile_bits | (y0 * tile_w)
+    const int lane = threadIdx.x & 31, wbase = threadIdx.x & ~31;
+    const int64_t j = (int64_t)blockIdx.x * EXP_THREADS + threadIdx.x;
+    int cnt = 0, id = 0, x0 = 0, y0 = 0, x1 = 0, y1 = 0;
+    int64_t off = 0;
+    if (j < M) {
+        id = sorted_ids[j];
+        off = cum_sorted[j];
+        int r = radii[id];
+        if (r > 0) {
+            float2 m = means2d[id];
+            tile_rect(m.x, m.y, r, tile_size, tile_w, tile_h, x0, y0, x1, y1);
+            cnt = max(0, x1 - x0) * max(0, y1 - y0);
+        }
+    }
+    const int64_t warp_off = __shfl_sync(FULL, off, 0);
+    int incl = cnt;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        int o = __shfl_up_sync(FULL, incl, d);
+        if (lane >= d) incl += o;
+    }
+    const int total = __shfl_sync(FULL, incl, 31);
+    if (total == 0) return;
+    int64_t cam = 0;
+    if (cnt > 0) cam = camera_ids ? camera_ids[id] : (id / N);
+    s_start[threadIdx.x] = incl - cnt;
+    s_x0[threadIdx.x] = x0;
+    s_w[threadIdx.x] = max(1, x1 - x0);
+    s_id[threadIdx.x] = id;
+    s_base[threadIdx.x] = ((uint32_t)cam << tile_bits) + (uint32_t)(y0 * tile_w);
+    __syncwarp();
+    for (int e = lane; e < total; e += 32) {
+        // owner g = last Gaussian of the warp with start <= e (upper-bound binary search over 32 entries)
+        int lo = 0;
+#pragma unroll
+        for (int step = 16; step > 0; step >>= 1)
+            if (s_start[wbase + lo + step] <= e) lo += step;
+        const int g = wbase + lo;
+        const int k = e - s_start[g];
+        const int w = s_w[g];
+        const int dy = k / w, dx = k - dy * w;
+        tile_keys[warp_off + e] = s_base[g] + (uint32_t)(dy * tile_w + s_x0[g] + dx);
+        vals[warp_off + e] = s_id[g];
+    }
+}
+
+// offsets from the sorted 32-bit (camera << tile_bits | tile) keys
+__global__ void offsets32_kernel(int64_t n, const uint32_t* __restrict__ keys, int n_tiles, int tile_bits,
+                                 int64_t total_tiles, int32_t* __restrict__ offsets) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t mask = (1u << tile_bits) - 1u;
+    uint32_t cur = keys[i];
+    int64_t cur_lin = (int64_t)(cur >> tile_bits) * n_tiles + (int64_t)(cur & mask);
+    if (i == 0) {
+        for (int64_t t = 0; t <= cur_lin; ++t) offsets[t] = 0;
+    } else {
+        uint32_t prev = keys[i - 1];
+        if (prev != cur) {
+            int64_t prev_lin = (int64_t)(prev >> tile_bits) * n_tiles + (int64_t)(prev & mask);
+            for (int64_t t = prev_lin + 1; t <= cur_lin; ++t) offsets[t] = (int32_t)i;
+        }
+    }
+    if (i == n - 1)
+        for (int64_t t = cur_lin + 1; t < total_tiles; ++t) offsets[t] = (int32_t)n;
+}
+
+__global__ void isect_ids_kernel(int64_t n, const uint32_t* __restrict__ tile_keys, const int32_t* __restrict__ flat,
+                                 const float* __restrict__ depths, int64_t* __restrict__ isect_ids) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    isect_ids[i] = (int64_t)(((uint64_t)tile_keys[i] << 32) | (uint64_t)__float_as_uint(depths[flat[i]]));
+}
+
+static size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
+
+static size_t cub_pairs32_bytes(int64_t n) {
+    size_t bytes = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, bytes, (const uint32_t*)nullptr, (uint32_t*)nullptr, (const int32_t*)nullptr,
+                                    (int32_t*)nullptr, n > 0 ? n : 1, 0, 32, (cudaStream_t)0);
+    return bytes;
+}
+
 static int bit_length(int64_t v) {
     int b = 0;
     while (v > 0) { ++b; v >>= 1; }
@@ -198,7 +315,7 @@ extern "C" int b2s_isect_scan(int64_t M, const int32_t* tiles_per_gauss, int32_t
     B2S_CUDA(cudaMemsetAsync(workspace, 0, (size_t)(16 + tiles * 8), st));
     unsigned int* counter = reinterpret_cast<unsigned int*>(workspace);
     unsigned long long* status = reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(workspace) + 16);
-    scan_kernel<<<(unsigned)tiles, SCAN_THREADS, 0, st>>>(M, tiles_per_gauss, cum_tiles, total, status, counter);
+    scan_kernel<false><<<(unsigned)tiles, SCAN_THREADS, 0, st>>>(M, tiles_per_gauss, nullptr, cum_tiles, total, status, counter);
     B2S_LAUNCH_CHECK();
     return 0;
 }
@@ -251,6 +368,115 @@ extern "C" int b2s_isect_offsets(int64_t n, const int64_t* keys, int32_t C, int3
     B2S_REQUIRE(keys != nullptr, "null keys");
     int tile_bits = bit_length(n_tiles);
     isect_offsets_kernel<<<(unsigned)cdiv(n, 256), 256, 0, st>>>(n, keys, n_tiles, tile_bits, total_tiles, offsets);
+    B2S_LAUNCH_CHECK();
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// depth-first binning entry points
+// ---------------------------------------------------------------------------------------------------
+extern "C" int b2s_isect_depth_keys(int64_t M, const float* depths, const int32_t* radii, uint32_t* keys, int32_t* vals,
+                                    b2s_stream_t stream) {
+    B2S_REQUIRE(M >= 0, "bad size");
+    if (M == 0) return 0;
+    B2S_REQUIRE(depths && radii && keys && vals, "null pointer");
+    depth_keys_kernel<<<(unsigned)cdiv(M, 256), 256, 0, (cudaStream_t)stream>>>(M, depths, radii, keys, vals);
+    B2S_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int64_t b2s_depth_order_workspace_bytes(int64_t M) {
+    if (M <= 0) return 256;
+    // sorted keys (discarded) + CUB temp + scan status
+    return (int64_t)(align256((size_t)M * 4) + align256(cub_pairs32_bytes(M)) + align256((size_t)b2s_isect_scan_workspace_bytes(M)));
+}
+
+extern "C" int b2s_depth_order(int64_t M, const uint32_t* depth_keys, const int32_t* row_ids, const int32_t* tiles_per_gauss,
+                               int32_t* sorted_ids, int32_t* cum_sorted, int64_t* total, void* workspace,
+                               int64_t workspace_bytes, b2s_stream_t stream) {
+    B2S_REQUIRE(M >= 0 && total != nullptr, "bad args");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (M == 0) {
+        B2S_CUDA(cudaMemsetAsync(total, 0, sizeof(int64_t), st));
+        return 0;
+    }
+    B2S_REQUIRE(depth_keys && row_ids && tiles_per_gauss && sorted_ids && cum_sorted && workspace, "null pointer");
+    if (workspace_bytes < b2s_depth_order_workspace_bytes(M)) {
+        set_error("b2s_depth_order: workspace too small");
+        return B2S_E_WORKSPACE;
+    }
+    B2S_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255u) == 0, "workspace must be 256-byte aligned");
+    char* w = reinterpret_cast<char*>(workspace);
+    uint32_t* keys_sorted = reinterpret_cast<uint32_t*>(w);
+    w += align256((size_t)M * 4);
+    size_t cub_bytes = cub_pairs32_bytes(M);
+    void* cub_tmp = w;
+    w += align256(cub_bytes);
+    void* scan_ws = w;
+    B2S_CUDA(cub::DeviceRadixSort::SortPairs(cub_tmp, cub_bytes, depth_keys, keys_sorted, row_ids, sorted_ids, M, 0, 32, st));
+    int64_t tiles = cdiv(M, SCAN_TILE);
+    B2S_CUDA(cudaMemsetAsync(scan_ws, 0, (size_t)(16 + tiles * 8), st));
+    unsigned int* counter = reinterpret_cast<unsigned int*>(scan_ws);
+    unsigned long long* status = reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(scan_ws) + 16);
+    scan_kernel<true><<<(unsigned)tiles, SCAN_THREADS, 0, st>>>(M, tiles_per_gauss, sorted_ids, cum_sorted, total, status, counter);
+    B2S_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int64_t b2s_tile_bin_workspace_bytes(int64_t n_isects) {
+    if (n_isects <= 0) return 256;
+    // unsorted keys + unsorted vals + CUB temp
+    return (int64_t)(2 * align256((size_t)n_isects * 4) + align256(cub_pairs32_bytes(n_isects)));
+}
+
+extern "C" int b2s_tile_bin(int64_t M, int64_t N, const int64_t* camera_ids, int64_t n_isects, const int32_t* sorted_ids,
+                            const int32_t* cum_sorted, const float* means2d, const int32_t* radii, int32_t C,
+                            int32_t tile_size, int32_t tile_w, int32_t tile_h, uint32_t* tile_keys_sorted,
+                            int32_t* flatten_ids, int32_t* offsets, void* workspace, int64_t workspace_bytes,
+                            b2s_stream_t stream) {
+    B2S_REQUIRE(M >= 0 && n_isects >= 0 && C >= 0 && tile_size > 0 && tile_w > 0 && tile_h > 0 && offsets, "bad args");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int n_tiles = tile_w * tile_h;
+    const int64_t total_tiles = (int64_t)C * n_tiles;
+    if (n_isects == 0 || M == 0) {
+        if (total_tiles > 0) B2S_CUDA(cudaMemsetAsync(offsets, 0, (size_t)total_tiles * 4, st));
+        return 0;
+    }
+    B2S_REQUIRE(camera_ids != nullptr || N > 0, "dense rows need N");
+    B2S_REQUIRE(sorted_ids && cum_sorted && means2d && radii && tile_keys_sorted && flatten_ids && workspace, "null pointer");
+    const int tile_bits = bit_length(n_tiles);
+    const int key_bits = tile_bits + bit_length(C);
+    B2S_REQUIRE(key_bits <= 32, "camera x tile ids exceed 32 bits");
+    if (workspace_bytes < b2s_tile_bin_workspace_bytes(n_isects)) {
+        set_error("b2s_tile_bin: workspace too small");
+        return B2S_E_WORKSPACE;
+    }
+    B2S_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255u) == 0, "workspace must be 256-byte aligned");
+    char* w = reinterpret_cast<char*>(workspace);
+    uint32_t* keys_u = reinterpret_cast<uint32_t*>(w);
+    w += align256((size_t)n_isects * 4);
+    int32_t* vals_u = reinterpret_cast<int32_t*>(w);
+    w += align256((size_t)n_isects * 4);
+    size_t cub_bytes = cub_pairs32_bytes(n_isects);
+    expand_kernel<<<(unsigned)cdiv(M, EXP_THREADS), EXP_THREADS, 0, st>>>(
+        M, N, camera_ids, sorted_ids, cum_sorted, reinterpret_cast<const float2*>(means2d), radii, (float)tile_size, tile_w,
+        tile_h, tile_bits, keys_u, vals_u);
+    B2S_LAUNCH_CHECK();
+    B2S_CUDA(cub::DeviceRadixSort::SortPairs(w, cub_bytes, keys_u, tile_keys_sorted, vals_u, flatten_ids, n_isects, 0,
+                                             key_bits, st));
+    offsets32_kernel<<<(unsigned)cdiv(n_isects, 256), 256, 0, st>>>(n_isects, tile_keys_sorted, n_tiles, tile_bits,
+                                                                     total_tiles, offsets);
+    B2S_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int b2s_isect_ids_from_bins(int64_t n_isects, const uint32_t* tile_keys_sorted, const int32_t* flatten_ids,
+                                       const float* depths, int64_t* isect_ids, b2s_stream_t stream) {
+    B2S_REQUIRE(n_isects >= 0, "bad size");
+    if (n_isects == 0) return 0;
+    B2S_REQUIRE(tile_keys_sorted && flatten_ids && depths && isect_ids, "null pointer");
+    isect_ids_kernel<<<(unsigned)cdiv(n_isects, 256), 256, 0, (cudaStream_t)stream>>>(n_isects, tile_keys_sorted, flatten_ids,
+                                                                                     depths, isect_ids);
     B2S_LAUNCH_CHECK();
     return 0;
 }

@@ -139,6 +139,8 @@ __global__ void __launch_bounds__(FWD_THREADS) project_fwd_kernel(const b2s_proj
             }
             a.tiles_per_gauss[i] = cnt;
         }
+        if (a.depth_keys) a.depth_keys[i] = o.radius > 0 ? __float_as_uint(o.depth) : 0xFFFFFFFFu;
+        if (a.row_ids) a.row_ids[i] = (int32_t)i;
         if (o.radius > 0) vis |= 1ull << c;
     }
 
@@ -309,7 +311,6 @@ extern "C" int b2s_project_fwd(const b2s_project_fwd_args* a, b2s_stream_t strea
         B2S_REQUIRE(a->sh_degree >= 0 && a->sh_degree <= 3, "sh_degree must be 0..3");
         K = (a->sh_degree + 1) * (a->sh_degree + 1);
         B2S_REQUIRE(a->sh_stride_k >= K, "sh_stride_k < (deg+1)^2");
-        B2S_REQUIRE(a->campos != nullptr, "campos required for SH");
     }
     if (a->tiles_per_gauss) B2S_REQUIRE(a->tile_size > 0 && a->tile_w > 0 && a->tile_h > 0, "bad tile geometry");
     const bool vec = sh && K == 16 && a->sh_stride_k == 16 && aligned16(a->sh_coeffs);
@@ -337,7 +338,6 @@ extern "C" int b2s_project_bwd(const b2s_project_bwd_args* a, b2s_stream_t strea
         B2S_REQUIRE(a->sh_degree >= 0 && a->sh_degree <= 3, "sh_degree must be 0..3");
         K = (a->sh_degree + 1) * (a->sh_degree + 1);
         B2S_REQUIRE(a->sh_stride_k >= K, "sh_stride_k < (deg+1)^2");
-        B2S_REQUIRE(a->campos != nullptr, "campos required for SH");
     }
     const bool vec = sh && K == 16 && a->sh_stride_k == 16 && aligned16(a->sh_coeffs) && aligned16(a->v_sh_coeffs);
     size_t smem = ((a->C * sizeof(Camera) + 15) / 16) * 16;

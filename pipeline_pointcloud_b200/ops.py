@@ -80,7 +80,7 @@ def _bit_length(v: int) -> int:
 # stage 1: fused projection (+SH colour, + tile count)
 # ======================================================================================
 class _ProjectFused(torch.autograd.Function):
-    """radii, means2d, depths, conics, compensations, opacities_out, colors, tiles_per_gauss."""
+    """radii, means2d, depths, conics, compensations, opacities_out, colors, tiles_per_gauss, depth_keys, row_ids."""
 
     @staticmethod
     def forward(ctx, means, quats, scales, opacities, sh_coeffs, viewmats, Ks, campos, width, height, eps2d,
@@ -106,6 +106,8 @@ class _ProjectFused(torch.autograd.Function):
         opac_out = torch.empty(C, N, dtype=torch.float32, **o) if opacities is not None else None
         colors = torch.empty(C, N, 3, dtype=torch.float32, **o) if with_sh else None
         tiles = torch.empty(C, N, dtype=torch.int32, **o) if tile_size else None
+        dkeys = torch.empty(C, N, dtype=torch.int32, **o) if tile_size else None     # uint32 bit patterns
+        rowids = torch.empty(C, N, dtype=torch.int32, **o) if tile_size else None
         tw = (width + tile_size - 1) // tile_size if tile_size else 0
         th = (height + tile_size - 1) // tile_size if tile_size else 0
         lib = L.lib()
@@ -123,18 +125,24 @@ class _ProjectFused(torch.autograd.Function):
                 conics=ptr(conics[c0:c1]), compensations=ptr(comps[c0:c1]) if comps is not None else None,
                 opacities_out=ptr(opac_out[c0:c1]) if opac_out is not None else None,
                 colors=ptr(colors[c0:c1]) if colors is not None else None,
-                tiles_per_gauss=ptr(tiles[c0:c1]) if tiles is not None else None)
+                tiles_per_gauss=ptr(tiles[c0:c1]) if tiles is not None else None,
+                depth_keys=ptr(dkeys[c0:c1]) if dkeys is not None else None,
+                row_ids=ptr(rowids[c0:c1]) if rowids is not None else None)
+            if rowids is not None and c0 > 0:
+                raise NotImplementedError("more than 64 cameras per call with fused binning keys")
             with _stage("project_fwd"):
                 check(lib.b2s_project_fwd(ctypes.byref(a), st), "b2s_project_fwd")
         ctx.save_for_backward(means, quats, scales, opacities, sh_coeffs, viewmats, Ks, campos, radii)
         ctx.cfg = (width, height, eps2d, near_plane, far_plane, radius_clip, bool(antialiased), sh_degree)
+        ctx.set_materialize_grads(False)
         ctx.mark_non_differentiable(radii)
         if tiles is not None:
-            ctx.mark_non_differentiable(tiles)
-        return radii, means2d, depths, conics, comps, opac_out, colors, tiles
+            ctx.mark_non_differentiable(tiles, dkeys, rowids)
+        return radii, means2d, depths, conics, comps, opac_out, colors, tiles, dkeys, rowids
 
     @staticmethod
-    def backward(ctx, _v_radii, v_means2d, v_depths, v_conics, v_comps, v_opac_out, v_colors, _v_tiles):
+    def backward(ctx, _v_radii, v_means2d, v_depths, v_conics, v_comps, v_opac_out, v_colors, _v_tiles=None, _v_keys=None,
+                 _v_rows=None):
         means, quats, scales, opacities, sh_coeffs, viewmats, Ks, campos, radii = ctx.saved_tensors
         width, height, eps2d, near_plane, far_plane, radius_clip, antialiased, sh_degree = ctx.cfg
         if ctx.needs_input_grad[5] or ctx.needs_input_grad[6]:
@@ -193,9 +201,9 @@ def fully_fused_projection(
         raise NotImplementedError("sparse_grad is not implemented")
     if quats is None or scales is None:
         raise ValueError("quats and scales are required")
-    radii, means2d, depths, conics, comps, _, _, _ = _ProjectFused.apply(
+    radii, means2d, depths, conics, comps = _ProjectFused.apply(
         means, quats, scales, None, None, viewmats, Ks, None, int(width), int(height), float(eps2d), float(near_plane),
-        float(far_plane), float(radius_clip), False, bool(calc_compensations), 0, 0)
+        float(far_plane), float(radius_clip), False, bool(calc_compensations), 0, 0)[:5]
     if not packed:
         return radii, means2d, depths, conics, comps
     N = means.shape[0]
@@ -272,9 +280,13 @@ def quat_scale_to_covar_preci(quats: Tensor, scales: Tensor, compute_covar: bool
 def isect_tiles(means2d: Tensor, radii: Tensor, depths: Tensor, tile_size: int, tile_width: int, tile_height: int,
                 sort: bool = True, packed: bool = False, n_cameras: Optional[int] = None,
                 camera_ids: Optional[Tensor] = None, gaussian_ids: Optional[Tensor] = None,
-                tiles_per_gauss: Optional[Tensor] = None) -> Tuple[Tensor, Tensor, Tensor]:
+                tiles_per_gauss: Optional[Tensor] = None, method: str = "radix64") -> Tuple[Tensor, Tensor, Tensor]:
     """gsplat ``isect_tiles``: (tiles_per_gauss int32, isect_ids int64, flatten_ids int32), sorted by
-    (camera, tile, depth bits) when ``sort``.  ``tiles_per_gauss`` may be passed in when stage 1 already made it."""
+    (camera, tile, depth bits) when ``sort``.  ``tiles_per_gauss`` may be passed in when stage 1 already made it.
+    ``method="radix64"`` is the reference's algorithm (fill 64-bit keys, LSD radix sort);
+    ``method="depth_first"`` is the low-traffic path ``rasterization()`` uses -- same output bit for bit."""
+    if method not in ("radix64", "depth_first"):
+        raise ValueError("method must be 'radix64' or 'depth_first'")
     dev = L.require_cuda(means2d, radii, depths)
     if packed:
         if camera_ids is None or n_cameras is None:
@@ -295,6 +307,10 @@ def isect_tiles(means2d: Tensor, radii: Tensor, depths: Tensor, tile_size: int, 
               "b2s_isect_count")
     else:
         tiles_per_gauss = tiles_per_gauss.contiguous()
+    if method == "depth_first" and sort:
+        flat, _off, make_ids = bin_depth_first(means2d, radii, depths, tiles_per_gauss, tile_size, tile_width, tile_height,
+                                               C, camera_ids=cam)
+        return tiles_per_gauss, make_ids(), flat
     cum = torch.empty(max(M, 1), dtype=torch.int32, device=dev)
     total = torch.empty(1, dtype=torch.int64, device=dev)
     ws = torch.empty(int(lib.b2s_isect_scan_workspace_bytes(M)), dtype=torch.uint8, device=dev)
@@ -318,6 +334,107 @@ def isect_tiles(means2d: Tensor, radii: Tensor, depths: Tensor, tile_size: int, 
                                      ptr(flat_sorted), ptr(ws), ws.numel(), st), "b2s_isect_sort")
         isect_ids, flatten_ids = ids_sorted, flat_sorted
     return tiles_per_gauss, isect_ids, flatten_ids
+
+
+class LazyMeta(dict):
+    """The ``meta`` dict of ``rasterization()``.  ``isect_ids`` (the 64-bit sorted keys) is not needed by
+    compositing, so the depth-first binning path rebuilds it only when somebody looks at it."""
+
+    def __init__(self, *a, **kw):
+        super().__init__(*a, **kw)
+        self._lazy = {}
+
+    def set_lazy(self, key, fn):
+        self._lazy[key] = fn
+
+    def _force(self, key=None):
+        for k in ([key] if key is not None else list(self._lazy)):
+            if k in self._lazy:
+                super().__setitem__(k, self._lazy.pop(k)())
+
+    def __getitem__(self, key):
+        self._force(key)
+        return super().__getitem__(key)
+
+    def get(self, key, default=None):
+        self._force(key)
+        return super().get(key, default)
+
+    def __contains__(self, key):
+        return key in self._lazy or super().__contains__(key)
+
+    def keys(self):
+        self._force()
+        return super().keys()
+
+    def items(self):
+        self._force()
+        return super().items()
+
+    def values(self):
+        self._force()
+        return super().values()
+
+    def __iter__(self):
+        self._force()
+        return super().__iter__()
+
+    def __len__(self):
+        return super().__len__() + len(self._lazy)
+
+
+def _ws(nbytes: int, dev) -> Tensor:
+    return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=dev)   # torch allocations are 512-B aligned
+
+
+@torch.no_grad()
+def bin_depth_first(means2d: Tensor, radii: Tensor, depths: Tensor, tiles_per_gauss: Tensor, tile_size: int,
+                    tile_width: int, tile_height: int, n_cameras: int, camera_ids: Optional[Tensor] = None,
+                    depth_keys: Optional[Tensor] = None, row_ids: Optional[Tensor] = None):
+    """Depth-first binning (see include/b2s.h): returns (flatten_ids int32 [I], isect_offsets int32 [C,th,tw],
+    make_isect_ids) where ``make_isect_ids()`` rebuilds the 64-bit sorted keys.  Bit-identical to
+    ``isect_tiles(sort=True)`` + ``isect_offset_encode`` with ~3x less HBM traffic."""
+    dev = L.require_cuda(means2d, radii, depths)
+    packed = camera_ids is not None
+    M = radii.numel()
+    N = 0 if packed else means2d.shape[1]
+    C = int(n_cameras)
+    means2d, depths = f32c(means2d), f32c(depths)
+    radii = radii.contiguous()
+    tiles_per_gauss = tiles_per_gauss.contiguous()
+    cam = camera_ids.contiguous().to(torch.int64) if packed else None
+    lib, st = L.lib(), L.stream_ptr(dev)
+    if depth_keys is None or row_ids is None:
+        depth_keys = torch.empty(M, dtype=torch.int32, device=dev)
+        row_ids = torch.empty(M, dtype=torch.int32, device=dev)
+        with _stage("isect_depth_keys"):
+            check(lib.b2s_isect_depth_keys(M, ptr(depths), ptr(radii), ptr(depth_keys), ptr(row_ids), st), "b2s_isect_depth_keys")
+    sorted_ids = torch.empty(max(M, 1), dtype=torch.int32, device=dev)
+    cum_sorted = torch.empty(max(M, 1), dtype=torch.int32, device=dev)
+    total = torch.empty(1, dtype=torch.int64, device=dev)
+    ws = _ws(lib.b2s_depth_order_workspace_bytes(M), dev)
+    with _stage("depth_order"):
+        check(lib.b2s_depth_order(M, ptr(depth_keys), ptr(row_ids), ptr(tiles_per_gauss), ptr(sorted_ids), ptr(cum_sorted),
+                                  ptr(total), ptr(ws), ws.numel(), st), "b2s_depth_order")
+    n_isects = int(total.item())          # the one host sync of a forward: sizes the per-intersection buffers
+    if n_isects >= 2 ** 31:
+        raise B2SError(f"n_isects = {n_isects} does not fit the int32 offsets of the API")
+    tile_keys = torch.empty(n_isects, dtype=torch.int32, device=dev)
+    flatten_ids = torch.empty(n_isects, dtype=torch.int32, device=dev)
+    offsets = torch.empty(C, tile_height, tile_width, dtype=torch.int32, device=dev)
+    ws2 = _ws(lib.b2s_tile_bin_workspace_bytes(n_isects), dev)
+    with _stage("tile_bin"):
+        check(lib.b2s_tile_bin(M, N, ptr(cam), n_isects, ptr(sorted_ids), ptr(cum_sorted), ptr(means2d), ptr(radii), C,
+                               tile_size, tile_width, tile_height, ptr(tile_keys), ptr(flatten_ids), ptr(offsets), ptr(ws2),
+                               ws2.numel(), st), "b2s_tile_bin")
+
+    def make_isect_ids():
+        ids = torch.empty(n_isects, dtype=torch.int64, device=dev)
+        check(lib.b2s_isect_ids_from_bins(n_isects, ptr(tile_keys), ptr(flatten_ids), ptr(depths), ptr(ids),
+                                          L.stream_ptr(dev)), "b2s_isect_ids_from_bins")
+        return ids
+
+    return flatten_ids, offsets, make_isect_ids
 
 
 @torch.no_grad()
@@ -375,11 +492,17 @@ class _RasterizeToPixels(torch.autograd.Function):
         C, th, tw = isect_offsets.shape
         ch = colors.shape[-1]
         v_render, v_alphas = f32c(v_render), f32c(v_alphas)
-        v_means2d = torch.zeros_like(means2d)
-        v_conics = torch.zeros_like(conics)
-        v_colors = torch.zeros_like(colors)
-        v_opac = torch.zeros_like(opacities)
-        v_abs = torch.zeros_like(means2d) if absgrad else None
+        # one zero-filled slab for every atomically accumulated gradient (one fill instead of four)
+        M = opacities.numel()
+        widths = [2, 3, ch, 1] + ([2] if absgrad else [])
+        slab = torch.zeros(M * sum(widths), dtype=torch.float32, device=dev)
+        parts, o = [], 0
+        for wd in widths:
+            parts.append(slab[o:o + M * wd])
+            o += M * wd
+        v_means2d, v_conics = parts[0].view(means2d.shape), parts[1].view(conics.shape)
+        v_colors, v_opac = parts[2].view(colors.shape), parts[3].view(opacities.shape)
+        v_abs = parts[4].view(means2d.shape) if absgrad else None
         a = L.CompositeBwdArgs(
             C=C, width=width, height=height, tile_size=tile_size, tile_w=tw, tile_h=th, channels=ch,
             n_isects=flatten_ids.numel(), means2d=ptr(means2d), conics=ptr(conics), colors=ptr(colors),

@@ -94,10 +94,8 @@ def rasterization(
 
     # ---- stage 1: projection (+ SH colour + tile counts) in one kernel ------------------------------------
     fused_sh = sh_degree is not None and colors.dim() == 3
-    campos = None
-    if sh_degree is not None:
-        campos = torch.linalg.inv(viewmats.detach().float())[:, :3, 3].contiguous()
-    radii, means2d, depths, conics, _comps, opac, sh_cols, tiles = ops._ProjectFused.apply(
+    campos = None          # the kernels derive the camera centres from viewmats
+    radii, means2d, depths, conics, _comps, opac, sh_cols, tiles, dkeys, rowids = ops._ProjectFused.apply(
         means, quats, scales, opacities, colors if fused_sh else None, viewmats, Ks, campos, width, height, float(eps2d),
         float(near_plane), float(far_plane), float(radius_clip), antialiased, False,
         int(sh_degree) if fused_sh else 0, tile_size)
@@ -107,6 +105,7 @@ def rasterization(
     elif fused_sh:
         cols = sh_cols
     else:  # per-camera coefficients [C,N,K,3]
+        campos = torch.linalg.inv(viewmats.detach().float())[:, :3, 3]
         dirs = means[None, :, :] - campos[:, None, :]
         cols = ops.spherical_harmonics(sh_degree, dirs, colors, masks=radii > 0)
         cols = torch.clamp_min(cols + 0.5, 0.0)
@@ -136,10 +135,10 @@ def rasterization(
         radii_m, means2d_m, depths_m, conics_m, opac_m, cols_m, tiles_m = radii, means2d, depths, conics, opac, cols, tiles
 
     # ---- stage 2: binning --------------------------------------------------------------------------------
-    tiles_per_gauss, isect_ids, flatten_ids = ops.isect_tiles(
-        means2d_m, radii_m, depths_m, tile_size, tw, th, sort=True, packed=packed, n_cameras=C, camera_ids=camera_ids,
-        gaussian_ids=gaussian_ids, tiles_per_gauss=tiles_m)
-    isect_offsets = ops.isect_offset_encode(isect_ids, C, tw, th)
+    tiles_per_gauss = tiles_m
+    flatten_ids, isect_offsets, make_isect_ids = ops.bin_depth_first(
+        means2d_m, radii_m, depths_m, tiles_m, tile_size, tw, th, C, camera_ids=camera_ids,
+        depth_keys=None if packed else dkeys, row_ids=None if packed else rowids)
 
     # ---- stage 3: compositing ----------------------------------------------------------------------------
     ch = cols_m.shape[-1]
@@ -160,10 +159,11 @@ def rasterization(
         render_colors = torch.cat(
             [render_colors[..., :-1], render_colors[..., -1:] / render_alphas.clamp(min=1e-10)], dim=-1)
 
-    meta = {
+    meta = ops.LazyMeta({
         "camera_ids": camera_ids, "gaussian_ids": gaussian_ids, "radii": radii_m, "means2d": means2d_m,
         "depths": depths_m, "conics": conics_m, "opacities": opac_m, "tile_width": tw, "tile_height": th,
-        "tiles_per_gauss": tiles_per_gauss, "isect_ids": isect_ids, "flatten_ids": flatten_ids,
+        "tiles_per_gauss": tiles_per_gauss, "flatten_ids": flatten_ids,
         "isect_offsets": isect_offsets, "width": width, "height": height, "tile_size": tile_size, "n_cameras": C,
-    }
+    })
+    meta.set_lazy("isect_ids", make_isect_ids)     # 64-bit sorted keys, rebuilt on first access
     return render_colors, render_alphas, meta

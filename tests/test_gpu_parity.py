@@ -93,13 +93,18 @@ def test_binning_bit_exact(b2s, C, W, H, packed):
     tpg, ids, flat = O.isect_tiles(means2d, radii, depths, 16, tw, th, **kw)
     off = O.isect_offset_encode(ids, C, tw, th)
     kwg = {k: (v.cuda() if torch.is_tensor(v) else v) for k, v in kw.items()}
-    gtpg, gids, gflat = b2s.isect_tiles(means2d.cuda(), radii.cuda(), depths.cuda(), 16, tw, th, **kwg)
-    goff = b2s.isect_offset_encode(gids, C, tw, th)
     assert ids.numel() > 10000
-    assert torch.equal(gtpg.cpu(), tpg)
-    assert torch.equal(gids.cpu(), ids)          # sorted (camera, tile, depth) keys, bit for bit
-    assert torch.equal(gflat.cpu(), flat)        # and the permuted indices (stable ties)
-    assert torch.equal(goff.cpu(), off)
+    for method in ("radix64", "depth_first"):     # the reference's algorithm and the low-traffic training path
+        gtpg, gids, gflat = b2s.isect_tiles(means2d.cuda(), radii.cuda(), depths.cuda(), 16, tw, th, method=method, **kwg)
+        goff = b2s.isect_offset_encode(gids, C, tw, th)
+        assert torch.equal(gtpg.cpu(), tpg), method
+        assert torch.equal(gids.cpu(), ids), method          # sorted (camera, tile, depth) keys, bit for bit
+        assert torch.equal(gflat.cpu(), flat), method        # and the permuted indices (stable ties)
+        assert torch.equal(goff.cpu(), off), method
+    from pipeline_pointcloud_b200 import ops
+    f2, off2, mk = ops.bin_depth_first(means2d.cuda(), radii.cuda(), depths.cuda(), gtpg, 16, tw, th, C,
+                                       camera_ids=kwg.get("camera_ids"))
+    assert torch.equal(f2.cpu(), flat) and torch.equal(off2.cpu(), off) and torch.equal(mk().cpu(), ids)
     # unsorted variant
     _, uids, uflat = b2s.isect_tiles(means2d.cuda(), radii.cuda(), depths.cuda(), 16, tw, th, sort=False, **kwg)
     _, oids, oflat = O.isect_tiles(means2d, radii, depths, 16, tw, th, sort=False, **kw)
@@ -110,10 +115,24 @@ def test_binning_empty(b2s):
     means2d = torch.zeros(2, 10, 2).cuda()
     radii = torch.zeros(2, 10, dtype=torch.int32).cuda()
     depths = torch.ones(2, 10).cuda()
-    tpg, ids, flat = b2s.isect_tiles(means2d, radii, depths, 16, 4, 3)
-    assert ids.numel() == 0 and flat.numel() == 0 and tpg.sum().item() == 0
-    off = b2s.isect_offset_encode(ids, 2, 4, 3)
-    assert off.shape == (2, 3, 4) and (off == 0).all()
+    for method in ("radix64", "depth_first"):
+        tpg, ids, flat = b2s.isect_tiles(means2d, radii, depths, 16, 4, 3, method=method)
+        assert ids.numel() == 0 and flat.numel() == 0 and tpg.sum().item() == 0
+        off = b2s.isect_offset_encode(ids, 2, 4, 3)
+        assert off.shape == (2, 3, 4) and (off == 0).all()
+
+
+def test_binning_depth_ties(b2s):
+    """Equal (tile, depth) keys must keep ascending flat index (stable), in both binning methods."""
+    N = 5000
+    g = torch.Generator().manual_seed(0)
+    means2d = (torch.rand(1, N, 2, generator=g) * torch.tensor([128.0, 96.0]))
+    radii = torch.randint(0, 14, (1, N), generator=g, dtype=torch.int32)
+    depths = torch.randint(1, 6, (1, N), generator=g).float()          # only 5 distinct depths => many ties
+    tpg, ids, flat = O.isect_tiles(means2d, radii, depths, 16, 8, 6)
+    for method in ("radix64", "depth_first"):
+        _, gids, gflat = b2s.isect_tiles(means2d.cuda(), radii.cuda(), depths.cuda(), 16, 8, 6, method=method)
+        assert torch.equal(gids.cpu(), ids) and torch.equal(gflat.cpu(), flat), method
 
 
 # ----------------------------------------------------------------------------------------------------------
