@@ -113,6 +113,10 @@ def algorithmic_bytes(N, C, V, I, P, K, n_tiles, key_bits):
         "isect_fill": M * 20 + I * 12,
         "isect_sort": I * 12 * 2 * p + I * 8,                        # LSD radix model; single-pass ideal = I*24
         "isect_offsets": I * 8 + 4 * n_tiles,
+        # depth-first binning: 32-bit depth sort of M rows (histogram + 4 passes) + gather-scan;
+        # expand + 32-bit (camera,tile) sort of I records (histogram + ceil(bits/8) passes) + offsets
+        "depth_order": M * 4 + 4 * M * 16 + M * 12,
+        "tile_bin": M * 20 + I * 8 + I * 4 + math.ceil((key_bits - 32) / 8) * I * 16 + I * 4 + 4 * n_tiles,
         "composite_fwd": I * 40 + P * 24,
         "composite_bwd": I * 40 + P * 28 + I * 36,
         "project_bwd": N * 44 + M * 4 + V * (36 + 12 * K) + N * 44 + N * 12 * K,
@@ -253,7 +257,7 @@ def main():
         torch.autograd.backward([r, a], [vr, va])
         if world > 1:
             allreduce_gradients(p.values())
-        stats["n_isects"] = m["isect_ids"].numel()
+        stats["n_isects"] = m["flatten_ids"].numel()      # (not isect_ids: that would materialise the lazy 64-bit keys)
         stats["n_visible"] = m["n_visible"] if "n_visible" in m else None
         return r, a, m
 
@@ -336,7 +340,7 @@ def main():
         gbs = ab.get(name, 0) / (s["ms_avg"] * 1e-3) / 1e9 if s["ms_avg"] > 0 else 0.0
         per_stage[name] = {"ms": round(s["ms_avg"], 4), "calls_per_step": s["calls"] / args.steps,
                            "algorithmic_bytes": ab.get(name), "GBps": round(gbs, 1), "frac_of_peak": round(gbs / peak, 4)}
-    own = {k: v for k, v in per_stage.items() if k != "isect_sort"}
+    own = {k: v for k, v in per_stage.items() if k not in ("isect_sort", "depth_order", "tile_bin")}
     dom = max(own, key=lambda k: own[k]["ms"])
     roofline = {"kernel": dom, "bound": "hbm", "achieved": per_stage[dom]["GBps"], "peak": peak, "unit": "GB/s",
                 "frac": per_stage[dom]["frac_of_peak"], "traffic": None, "peak_source": peak_src,
@@ -353,7 +357,8 @@ def main():
                    "parallelism": f"dp{world}"},
         "iters_per_s": 1e3 / ms_per_step * C_total,
         "gpu_launches": timer.launches,
-        "gpu_launches_note": "kernels of libb2s.so inside the timed region (7 per step); CUB radix-sort passes are extra",
+        "gpu_launches_note": "stage calls into libb2s.so inside the timed region (6 per step: project_fwd, depth_order, "
+                             "tile_bin, composite_fwd, composite_bwd, project_bwd = 9 own kernels + CUB radix passes)",
         "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "steps": e2e_steps},
         "roofline": roofline, "stages": per_stage, "clocks": clocks,

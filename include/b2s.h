@@ -83,6 +83,7 @@ typedef struct {
     int32_t* tiles_per_gauss; /* [C,N] or NULL */
     uint32_t* depth_keys;     /* [C,N] or NULL: depth bits, 0xFFFFFFFF on culled rows (for b2s_depth_order) */
     int32_t* row_ids;         /* [C,N] or NULL: iota, c*N + n */
+    int64_t* total_isects;    /* device scalar or NULL: sum of tiles_per_gauss, ACCUMULATED (zero it first) */
 } b2s_project_fwd_args;
 B2S_API int b2s_project_fwd(const b2s_project_fwd_args* a, b2s_stream_t stream);
 
@@ -158,25 +159,30 @@ B2S_API int b2s_isect_offsets(int64_t n_isects, const int64_t* isect_ids_sorted,
  * index) with ~3x less HBM traffic: Gaussians are depth-sorted once (M 32-bit keys), expanded to tile
  * intersections in that order, then stable-split by (camera, tile) with an LSD radix over
  * tile_bits+cam_bits bits of 8-byte records.  The 64-bit isect_ids are rebuilt on demand.
- *   b2s_isect_depth_keys : depth bits (0xFFFFFFFF on culled rows) + row ids   (stage 1 can emit both)
- *   b2s_depth_order      : sorted_ids [M], cum_sorted [M] (exclusive, in depth order), *total
- *   b2s_tile_bin         : tile_keys_sorted [I] (cam << tile_bits | tile), flatten_ids [I], offsets
+ *   b2s_isect_depth_keys : depth bits (0xFFFFFFFF on culled rows) + row ids   (stage 1 can emit both,
+ *                          together with *total_isects, the data-dependent size the host must read)
+ *   b2s_depth_order      : sorted_ids [M]  (32-bit LSD radix sort of the depth keys; enqueue it BEFORE
+ *                          reading total_isects so the sort overlaps the host's wait)
+ *   b2s_tile_bin         : fused scan + expansion in depth order, (camera,tile) radix sort, offsets:
+ *                          tile_keys_sorted [I] (cam << tile_bits | tile; 16-bit when they fit, see
+ *                          b2s_tile_key_bytes), flatten_ids [I], offsets [C*tile_h*tile_w]
  *   b2s_isect_ids_from_bins : isect_ids [I] = tile_key << 32 | bits(depths[flatten_ids])
  * Workspaces must be 256-byte aligned. */
 B2S_API int b2s_isect_depth_keys(int64_t M, const float* depths, const int32_t* radii, uint32_t* keys, int32_t* vals,
                                  b2s_stream_t stream);
 B2S_API int64_t b2s_depth_order_workspace_bytes(int64_t M);
-B2S_API int b2s_depth_order(int64_t M, const uint32_t* depth_keys, const int32_t* row_ids, const int32_t* tiles_per_gauss,
-                            int32_t* sorted_ids, int32_t* cum_sorted, int64_t* total, void* workspace,
-                            int64_t workspace_bytes, b2s_stream_t stream);
-B2S_API int64_t b2s_tile_bin_workspace_bytes(int64_t n_isects);
+B2S_API int b2s_depth_order(int64_t M, const uint32_t* depth_keys, const int32_t* row_ids, int32_t* sorted_ids,
+                            void* workspace, int64_t workspace_bytes, b2s_stream_t stream);
+B2S_API int32_t b2s_tile_key_bytes(int32_t C, int32_t tile_w, int32_t tile_h);
+B2S_API int64_t b2s_tile_bin_workspace_bytes(int64_t M, int64_t n_isects);
 B2S_API int b2s_tile_bin(int64_t M, int64_t N, const int64_t* camera_ids /* or NULL */, int64_t n_isects,
-                         const int32_t* sorted_ids, const int32_t* cum_sorted, const float* means2d, const int32_t* radii,
-                         int32_t C, int32_t tile_size, int32_t tile_w, int32_t tile_h, uint32_t* tile_keys_sorted,
+                         const int32_t* sorted_ids, const float* means2d, const int32_t* radii, int32_t C,
+                         int32_t tile_size, int32_t tile_w, int32_t tile_h, void* tile_keys_sorted /* [I] x 4 bytes */,
                          int32_t* flatten_ids, int32_t* offsets, void* workspace, int64_t workspace_bytes,
                          b2s_stream_t stream);
-B2S_API int b2s_isect_ids_from_bins(int64_t n_isects, const uint32_t* tile_keys_sorted, const int32_t* flatten_ids,
-                                    const float* depths, int64_t* isect_ids, b2s_stream_t stream);
+B2S_API int b2s_isect_ids_from_bins(int64_t n_isects, int32_t key_bytes, const void* tile_keys_sorted,
+                                    const int32_t* flatten_ids, const float* depths, int64_t* isect_ids,
+                                    b2s_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Stage 3: per-16x16-tile front-to-back compositing.  Replaces gsplat `rasterize_to_pixels`

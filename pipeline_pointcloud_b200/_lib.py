@@ -34,6 +34,7 @@ class ProjectFwdArgs(Structure):
         ("radii", c_void_p), ("means2d", c_void_p), ("depths", c_void_p), ("conics", c_void_p),
         ("compensations", c_void_p), ("opacities_out", c_void_p), ("colors", c_void_p),
         ("tiles_per_gauss", c_void_p), ("depth_keys", c_void_p), ("row_ids", c_void_p),
+        ("total_isects", c_void_p),
     ]
 
 
@@ -99,12 +100,12 @@ SYMBOLS = {
     "b2s_isect_offsets": (c_int32, [c_int64, c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p]),
     "b2s_isect_depth_keys": (c_int32, [c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "b2s_depth_order_workspace_bytes": (c_int64, [c_int64]),
-    "b2s_depth_order": (c_int32, [c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64,
-                                  c_void_p]),
-    "b2s_tile_bin_workspace_bytes": (c_int64, [c_int64]),
-    "b2s_tile_bin": (c_int32, [c_int64, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32,
+    "b2s_depth_order": (c_int32, [c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
+    "b2s_tile_key_bytes": (c_int32, [c_int32, c_int32, c_int32]),
+    "b2s_tile_bin_workspace_bytes": (c_int64, [c_int64, c_int64]),
+    "b2s_tile_bin": (c_int32, [c_int64, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_int32, c_int32,
                                c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
-    "b2s_isect_ids_from_bins": (c_int32, [c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "b2s_isect_ids_from_bins": (c_int32, [c_int64, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "b2s_composite_fwd": (c_int32, [POINTER(CompositeFwdArgs), c_void_p]),
     "b2s_composite_bwd": (c_int32, [POINTER(CompositeBwdArgs), c_void_p]),
 }

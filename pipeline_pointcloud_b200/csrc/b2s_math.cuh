@@ -208,6 +208,48 @@ B2S_HD bool project_one(const Camera& cam, const float mean[3], const Sym3& S, f
     return true;
 }
 
+// The backward only needs the intermediates (never the cull decision, which it takes from the forward's
+// radii), so it recomputes them with ordinary contracted arithmetic: ~40 % fewer instructions than the
+// canonical-order forward.  Differences from project_one are at the 1e-7 level.
+B2S_HD void project_mid_fast(const Camera& cam, const float mean[3], const Sym3& S, float eps2d, ProjMid& m) {
+    const float* R = cam.R;
+    const float tx = R[0] * mean[0] + R[1] * mean[1] + R[2] * mean[2] + cam.t[0];
+    const float ty = R[3] * mean[0] + R[4] * mean[1] + R[5] * mean[2] + cam.t[1];
+    const float tz = R[6] * mean[0] + R[7] * mean[1] + R[8] * mean[2] + cam.t[2];
+    // A = R Sigma ; Sc = A R^T
+    const float a00 = R[0] * S.c00 + R[1] * S.c01 + R[2] * S.c02, a01 = R[0] * S.c01 + R[1] * S.c11 + R[2] * S.c12,
+                a02 = R[0] * S.c02 + R[1] * S.c12 + R[2] * S.c22;
+    const float a10 = R[3] * S.c00 + R[4] * S.c01 + R[5] * S.c02, a11 = R[3] * S.c01 + R[4] * S.c11 + R[5] * S.c12,
+                a12 = R[3] * S.c02 + R[4] * S.c12 + R[5] * S.c22;
+    const float a20 = R[6] * S.c00 + R[7] * S.c01 + R[8] * S.c02, a21 = R[6] * S.c01 + R[7] * S.c11 + R[8] * S.c12,
+                a22 = R[6] * S.c02 + R[7] * S.c12 + R[8] * S.c22;
+    m.s00 = a00 * R[0] + a01 * R[1] + a02 * R[2];
+    m.s01 = a00 * R[3] + a01 * R[4] + a02 * R[5];
+    m.s02 = a00 * R[6] + a01 * R[7] + a02 * R[8];
+    m.s11 = a10 * R[3] + a11 * R[4] + a12 * R[5];
+    m.s12 = a10 * R[6] + a11 * R[7] + a12 * R[8];
+    m.s22 = a20 * R[6] + a21 * R[7] + a22 * R[8];
+    const float rz = 1.f / tz;
+    const float txz = tx * rz, tyz = ty * rz;
+    const float cxr = fminf(cam.lim_xp, fmaxf(-cam.lim_xn, txz));
+    const float cyr = fminf(cam.lim_yp, fmaxf(-cam.lim_yn, tyz));
+    m.tx = tx; m.ty = ty; m.tz = tz;
+    m.txc = tz * cxr; m.tyc = tz * cyr;
+    m.clamp_x = (cxr != txz); m.clamp_y = (cyr != tyz);
+    m.limx_used = cxr; m.limy_used = cyr;
+    m.j00 = cam.fx * rz; m.j11 = cam.fy * rz;
+    m.j02 = -cam.fx * m.txc * rz * rz;
+    m.j12 = -cam.fy * m.tyc * rz * rz;
+    const float b00 = m.j00 * m.s00 + m.j02 * m.s02, b01 = m.j00 * m.s01 + m.j02 * m.s12, b02 = m.j00 * m.s02 + m.j02 * m.s22;
+    const float b11 = m.j11 * m.s11 + m.j12 * m.s12, b12 = m.j11 * m.s12 + m.j12 * m.s22;
+    m.q00 = b00 * m.j00 + b02 * m.j02;
+    m.q01 = b01 * m.j11 + b02 * m.j12;
+    m.q11 = b11 * m.j11 + b12 * m.j12;
+    m.det_orig = m.q00 * m.q11 - m.q01 * m.q01;
+    m.a = m.q00 + eps2d; m.d = m.q11 + eps2d;
+    m.det = m.a * m.d - m.q01 * m.q01;
+}
+
 B2S_HD int iclamp(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
 
 // Tile rectangle [min,max) of a projected Gaussian   

@@ -175,26 +175,33 @@ __global__ void depth_keys_kernel(int64_t M, const float* __restrict__ depths, c
     vals[i] = (int32_t)i;
 }
 
-// One warp expands 32 depth-ordered Gaussians; lanes stride over the warp's output range so that the
-// (tile key, flat id) stores are fully coalesced.
+// Expansion with a fused single-pass scan.  Every thread takes one depth-ordered Gaussian, recomputes its
+// tile rectangle, the CTA scans the counts and obtains its global base by decoupled look-back (dynamic
+// CTA ids, as scan_kernel); then each warp writes its Gaussians' (tile key, flat id) records with lanes
+// striding over the warp's output range, so the stores are fully coalesced.
 constexpr int EXP_THREADS = 256;
+template <typename KeyT>
 __global__ void __launch_bounds__(EXP_THREADS) expand_kernel(int64_t M, int64_t N, const int64_t* __restrict__ camera_ids,
                                                              const int32_t* __restrict__ sorted_ids,
-                                                             const int32_t* __restrict__ cum_sorted,
                                                              const float2* __restrict__ means2d,
                                                              const int32_t* __restrict__ radii, float tile_size, int tile_w,
-                                                             int tile_h, int tile_bits, uint32_t* __restrict__ tile_keys,
+                                                             int tile_h, int tile_bits, unsigned long long* status,
+                                                             unsigned int* cta_counter, KeyT* __restrict__ tile_keys,
                                                              int32_t* __restrict__ vals) {
     __shared__ int s_start[EXP_THREADS];   // output offset of each Gaussian relative to its warp's first
     __shared__ int s_x0[EXP_THREADS], s_w[EXP_THREADS], s_id[EXP_THREADS];
     __shared__ uint32_t s_base[EXP_THREADS];  // cam << tile_bits | (y0 * tile_w)
-    const int lane = threadIdx.x & 31, wbase = threadIdx.x & ~31;
-    const int64_t j = (int64_t)blockIdx.x * EXP_THREADS + threadIdx.x;
+    __shared__ unsigned int s_cta;
+    __shared__ int s_warp_tot[EXP_THREADS / 32];
+    __shared__ unsigned long long s_prefix;
+    if (threadIdx.x == 0) s_cta = atomicAdd(cta_counter, 1u);
+    __syncthreads();
+    const unsigned int cta = s_cta;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wbase = threadIdx.x & ~31;
+    const int64_t j = (int64_t)cta * EXP_THREADS + threadIdx.x;
     int cnt = 0, id = 0, x0 = 0, y0 = 0, x1 = 0, y1 = 0;
-    int64_t off = 0;
     if (j < M) {
         id = sorted_ids[j];
-        off = cum_sorted[j];
         int r = radii[id];
         if (r > 0) {
             float2 m = means2d[id];
@@ -202,7 +209,6 @@ __global__ void __launch_bounds__(EXP_THREADS) expand_kernel(int64_t M, int64_t 
             cnt = max(0, x1 - x0) * max(0, y1 - y0);
         }
     }
-    const int64_t warp_off = __shfl_sync(FULL, off, 0);
     int incl = cnt;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
@@ -210,7 +216,7 @@ __global__ void __launch_bounds__(EXP_THREADS) expand_kernel(int64_t M, int64_t 
         if (lane >= d) incl += o;
     }
     const int total = __shfl_sync(FULL, incl, 31);
-    if (total == 0) return;
+    if (lane == 31) s_warp_tot[warp] = total;
     int64_t cam = 0;
     if (cnt > 0) cam = camera_ids ? camera_ids[id] : (id / N);
     s_start[threadIdx.x] = incl - cnt;
@@ -218,9 +224,40 @@ __global__ void __launch_bounds__(EXP_THREADS) expand_kernel(int64_t M, int64_t 
     s_w[threadIdx.x] = max(1, x1 - x0);
     s_id[threadIdx.x] = id;
     s_base[threadIdx.x] = ((uint32_t)cam << tile_bits) + (uint32_t)(y0 * tile_w);
-    __syncwarp();
+    __syncthreads();
+    int warp_off = 0, block_sum = 0;
+#pragma unroll
+    for (int w = 0; w < EXP_THREADS / 32; ++w) {
+        int x = s_warp_tot[w];
+        if (w < warp) warp_off += x;
+        block_sum += x;
+    }
+    if (threadIdx.x == 0) {
+        volatile unsigned long long* st = status;
+        unsigned long long excl = 0;
+        if (cta == 0) {
+            st[0] = FLAG_INC | (unsigned long long)block_sum;
+        } else {
+            st[cta] = FLAG_AGG | (unsigned long long)block_sum;
+            __threadfence();
+            long long k = (long long)cta - 1;
+            while (true) {
+                unsigned long long sv = st[k];
+                unsigned long long flag = sv & ~VAL_MASK;
+                if (flag == 0) continue;
+                excl += sv & VAL_MASK;
+                if (flag == FLAG_INC) break;
+                --k;
+            }
+            st[cta] = FLAG_INC | (excl + (unsigned long long)block_sum);
+        }
+        s_prefix = excl;
+    }
+    __syncthreads();
+    if (total == 0) return;
+    const int64_t out0 = (int64_t)s_prefix + warp_off;
     for (int e = lane; e < total; e += 32) {
-        // owner g = last Gaussian of the warp with start <= e (upper-bound binary search over 32 entries)
+        // owner g = last Gaussian of the warp with start <= e (binary search over 32 entries)
         int lo = 0;
 #pragma unroll
         for (int step = 16; step > 0; step >>= 1)
@@ -229,33 +266,29 @@ __global__ void __launch_bounds__(EXP_THREADS) expand_kernel(int64_t M, int64_t 
         const int k = e - s_start[g];
         const int w = s_w[g];
         const int dy = k / w, dx = k - dy * w;
-        tile_keys[warp_off + e] = s_base[g] + (uint32_t)(dy * tile_w + s_x0[g] + dx);
-        vals[warp_off + e] = s_id[g];
+        tile_keys[out0 + e] = (KeyT)(s_base[g] + (uint32_t)(dy * tile_w + s_x0[g] + dx));
+        vals[out0 + e] = s_id[g];
     }
 }
 
-// offsets from the sorted 32-bit (camera << tile_bits | tile) keys
-__global__ void offsets32_kernel(int64_t n, const uint32_t* __restrict__ keys, int n_tiles, int tile_bits,
-                                 int64_t total_tiles, int32_t* __restrict__ offsets) {
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const uint32_t mask = (1u << tile_bits) - 1u;
-    uint32_t cur = keys[i];
-    int64_t cur_lin = (int64_t)(cur >> tile_bits) * n_tiles + (int64_t)(cur & mask);
-    if (i == 0) {
-        for (int64_t t = 0; t <= cur_lin; ++t) offsets[t] = 0;
-    } else {
-        uint32_t prev = keys[i - 1];
-        if (prev != cur) {
-            int64_t prev_lin = (int64_t)(prev >> tile_bits) * n_tiles + (int64_t)(prev & mask);
-            for (int64_t t = prev_lin + 1; t <= cur_lin; ++t) offsets[t] = (int32_t)i;
-        }
+// offsets[t] = lower bound of key(t) in the sorted (camera << tile_bits | tile) keys: one thread per tile,
+// ~log2(n) dependent loads each -- tiny next to a pass over the keys.
+template <typename KeyT>
+__global__ void offsets_search_kernel(int64_t n, const KeyT* __restrict__ keys, int n_tiles, int tile_bits,
+                                      int64_t total_tiles, int32_t* __restrict__ offsets) {
+    int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= total_tiles) return;
+    const uint32_t want = ((uint32_t)(t / n_tiles) << tile_bits) | (uint32_t)(t % n_tiles);
+    int64_t lo = 0, hi = n;
+    while (lo < hi) {
+        int64_t mid = (lo + hi) >> 1;
+        if ((uint32_t)keys[mid] < want) lo = mid + 1; else hi = mid;
     }
-    if (i == n - 1)
-        for (int64_t t = cur_lin + 1; t < total_tiles; ++t) offsets[t] = (int32_t)n;
+    offsets[t] = (int32_t)lo;
 }
 
-__global__ void isect_ids_kernel(int64_t n, const uint32_t* __restrict__ tile_keys, const int32_t* __restrict__ flat,
+template <typename KeyT>
+__global__ void isect_ids_kernel(int64_t n, const KeyT* __restrict__ tile_keys, const int32_t* __restrict__ flat,
                                  const float* __restrict__ depths, int64_t* __restrict__ isect_ids) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -264,12 +297,14 @@ __global__ void isect_ids_kernel(int64_t n, const uint32_t* __restrict__ tile_ke
 
 static size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
 
-static size_t cub_pairs32_bytes(int64_t n) {
+template <typename KeyT>
+static size_t cub_pairs_bytes(int64_t n) {
     size_t bytes = 0;
-    cub::DeviceRadixSort::SortPairs(nullptr, bytes, (const uint32_t*)nullptr, (uint32_t*)nullptr, (const int32_t*)nullptr,
-                                    (int32_t*)nullptr, n > 0 ? n : 1, 0, 32, (cudaStream_t)0);
+    cub::DeviceRadixSort::SortPairs(nullptr, bytes, (const KeyT*)nullptr, (KeyT*)nullptr, (const int32_t*)nullptr,
+                                    (int32_t*)nullptr, n > 0 ? n : 1, 0, (int)sizeof(KeyT) * 8, (cudaStream_t)0);
     return bytes;
 }
+static size_t cub_pairs32_bytes(int64_t n) { return cub_pairs_bytes<uint32_t>(n); }
 
 static int bit_length(int64_t v) {
     int b = 0;
@@ -387,20 +422,15 @@ extern "C" int b2s_isect_depth_keys(int64_t M, const float* depths, const int32_
 
 extern "C" int64_t b2s_depth_order_workspace_bytes(int64_t M) {
     if (M <= 0) return 256;
-    // sorted keys (discarded) + CUB temp + scan status
-    return (int64_t)(align256((size_t)M * 4) + align256(cub_pairs32_bytes(M)) + align256((size_t)b2s_isect_scan_workspace_bytes(M)));
+    return (int64_t)(align256((size_t)M * 4) + align256(cub_pairs32_bytes(M)));  // sorted keys (discarded) + CUB temp
 }
 
-extern "C" int b2s_depth_order(int64_t M, const uint32_t* depth_keys, const int32_t* row_ids, const int32_t* tiles_per_gauss,
-                               int32_t* sorted_ids, int32_t* cum_sorted, int64_t* total, void* workspace,
-                               int64_t workspace_bytes, b2s_stream_t stream) {
-    B2S_REQUIRE(M >= 0 && total != nullptr, "bad args");
+extern "C" int b2s_depth_order(int64_t M, const uint32_t* depth_keys, const int32_t* row_ids, int32_t* sorted_ids,
+                               void* workspace, int64_t workspace_bytes, b2s_stream_t stream) {
+    B2S_REQUIRE(M >= 0, "bad args");
     cudaStream_t st = (cudaStream_t)stream;
-    if (M == 0) {
-        B2S_CUDA(cudaMemsetAsync(total, 0, sizeof(int64_t), st));
-        return 0;
-    }
-    B2S_REQUIRE(depth_keys && row_ids && tiles_per_gauss && sorted_ids && cum_sorted && workspace, "null pointer");
+    if (M == 0) return 0;
+    B2S_REQUIRE(depth_keys && row_ids && sorted_ids && workspace, "null pointer");
     if (workspace_bytes < b2s_depth_order_workspace_bytes(M)) {
         set_error("b2s_depth_order: workspace too small");
         return B2S_E_WORKSPACE;
@@ -410,30 +440,57 @@ extern "C" int b2s_depth_order(int64_t M, const uint32_t* depth_keys, const int3
     uint32_t* keys_sorted = reinterpret_cast<uint32_t*>(w);
     w += align256((size_t)M * 4);
     size_t cub_bytes = cub_pairs32_bytes(M);
+    B2S_CUDA(cub::DeviceRadixSort::SortPairs(w, cub_bytes, depth_keys, keys_sorted, row_ids, sorted_ids, M, 0, 32, st));
+    return 0;
+}
+
+extern "C" int32_t b2s_tile_key_bytes(int32_t C, int32_t tile_w, int32_t tile_h) {
+    return (bit_length((int64_t)tile_w * tile_h) + bit_length(C) <= 16) ? 2 : 4;
+}
+
+extern "C" int64_t b2s_tile_bin_workspace_bytes(int64_t M, int64_t n_isects) {
+    if (n_isects <= 0 || M <= 0) return 256;
+    // unsorted keys + unsorted vals + CUB temp + look-back status (counter + one word per CTA)
+    size_t cub = cub_pairs32_bytes(n_isects);
+    size_t cub16 = cub_pairs_bytes<uint16_t>(n_isects);
+    return (int64_t)(2 * align256((size_t)n_isects * 4) + align256(cub > cub16 ? cub : cub16) +
+                     align256(16 + (size_t)cdiv(M, EXP_THREADS) * 8));
+}
+
+template <typename KeyT>
+static int tile_bin_impl(int64_t M, int64_t N, const int64_t* camera_ids, int64_t n_isects, const int32_t* sorted_ids,
+                         const float* means2d, const int32_t* radii, int tile_size, int tile_w, int tile_h, int tile_bits,
+                         int key_bits, int64_t total_tiles, void* tile_keys_sorted, int32_t* flatten_ids, int32_t* offsets,
+                         char* w, cudaStream_t st) {
+    const int n_tiles = tile_w * tile_h;
+    KeyT* keys_u = reinterpret_cast<KeyT*>(w);
+    w += align256((size_t)n_isects * 4);
+    int32_t* vals_u = reinterpret_cast<int32_t*>(w);
+    w += align256((size_t)n_isects * 4);
+    size_t cub_bytes = cub_pairs_bytes<KeyT>(n_isects);
     void* cub_tmp = w;
-    w += align256(cub_bytes);
-    void* scan_ws = w;
-    B2S_CUDA(cub::DeviceRadixSort::SortPairs(cub_tmp, cub_bytes, depth_keys, keys_sorted, row_ids, sorted_ids, M, 0, 32, st));
-    int64_t tiles = cdiv(M, SCAN_TILE);
-    B2S_CUDA(cudaMemsetAsync(scan_ws, 0, (size_t)(16 + tiles * 8), st));
-    unsigned int* counter = reinterpret_cast<unsigned int*>(scan_ws);
-    unsigned long long* status = reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(scan_ws) + 16);
-    scan_kernel<true><<<(unsigned)tiles, SCAN_THREADS, 0, st>>>(M, tiles_per_gauss, sorted_ids, cum_sorted, total, status, counter);
+    size_t cub32 = cub_pairs32_bytes(n_isects), cub16 = cub_pairs_bytes<uint16_t>(n_isects);
+    w += align256(cub32 > cub16 ? cub32 : cub16);
+    const int64_t ctas = cdiv(M, EXP_THREADS);
+    B2S_CUDA(cudaMemsetAsync(w, 0, (size_t)(16 + ctas * 8), st));
+    unsigned int* counter = reinterpret_cast<unsigned int*>(w);
+    unsigned long long* status = reinterpret_cast<unsigned long long*>(w + 16);
+    expand_kernel<KeyT><<<(unsigned)ctas, EXP_THREADS, 0, st>>>(
+        M, N, camera_ids, sorted_ids, reinterpret_cast<const float2*>(means2d), radii, (float)tile_size, tile_w, tile_h,
+        tile_bits, status, counter, keys_u, vals_u);
+    B2S_LAUNCH_CHECK();
+    B2S_CUDA(cub::DeviceRadixSort::SortPairs(cub_tmp, cub_bytes, keys_u, reinterpret_cast<KeyT*>(tile_keys_sorted), vals_u,
+                                             flatten_ids, n_isects, 0, key_bits, st));
+    offsets_search_kernel<KeyT><<<(unsigned)cdiv(total_tiles, 128), 128, 0, st>>>(
+        n_isects, reinterpret_cast<const KeyT*>(tile_keys_sorted), n_tiles, tile_bits, total_tiles, offsets);
     B2S_LAUNCH_CHECK();
     return 0;
 }
 
-extern "C" int64_t b2s_tile_bin_workspace_bytes(int64_t n_isects) {
-    if (n_isects <= 0) return 256;
-    // unsorted keys + unsorted vals + CUB temp
-    return (int64_t)(2 * align256((size_t)n_isects * 4) + align256(cub_pairs32_bytes(n_isects)));
-}
-
 extern "C" int b2s_tile_bin(int64_t M, int64_t N, const int64_t* camera_ids, int64_t n_isects, const int32_t* sorted_ids,
-                            const int32_t* cum_sorted, const float* means2d, const int32_t* radii, int32_t C,
-                            int32_t tile_size, int32_t tile_w, int32_t tile_h, uint32_t* tile_keys_sorted,
-                            int32_t* flatten_ids, int32_t* offsets, void* workspace, int64_t workspace_bytes,
-                            b2s_stream_t stream) {
+                            const float* means2d, const int32_t* radii, int32_t C, int32_t tile_size, int32_t tile_w,
+                            int32_t tile_h, void* tile_keys_sorted, int32_t* flatten_ids, int32_t* offsets,
+                            void* workspace, int64_t workspace_bytes, b2s_stream_t stream) {
     B2S_REQUIRE(M >= 0 && n_isects >= 0 && C >= 0 && tile_size > 0 && tile_w > 0 && tile_h > 0 && offsets, "bad args");
     cudaStream_t st = (cudaStream_t)stream;
     const int n_tiles = tile_w * tile_h;
@@ -443,40 +500,36 @@ extern "C" int b2s_tile_bin(int64_t M, int64_t N, const int64_t* camera_ids, int
         return 0;
     }
     B2S_REQUIRE(camera_ids != nullptr || N > 0, "dense rows need N");
-    B2S_REQUIRE(sorted_ids && cum_sorted && means2d && radii && tile_keys_sorted && flatten_ids && workspace, "null pointer");
+    B2S_REQUIRE(sorted_ids && means2d && radii && tile_keys_sorted && flatten_ids && workspace, "null pointer");
     const int tile_bits = bit_length(n_tiles);
     const int key_bits = tile_bits + bit_length(C);
     B2S_REQUIRE(key_bits <= 32, "camera x tile ids exceed 32 bits");
-    if (workspace_bytes < b2s_tile_bin_workspace_bytes(n_isects)) {
+    if (workspace_bytes < b2s_tile_bin_workspace_bytes(M, n_isects)) {
         set_error("b2s_tile_bin: workspace too small");
         return B2S_E_WORKSPACE;
     }
     B2S_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255u) == 0, "workspace must be 256-byte aligned");
     char* w = reinterpret_cast<char*>(workspace);
-    uint32_t* keys_u = reinterpret_cast<uint32_t*>(w);
-    w += align256((size_t)n_isects * 4);
-    int32_t* vals_u = reinterpret_cast<int32_t*>(w);
-    w += align256((size_t)n_isects * 4);
-    size_t cub_bytes = cub_pairs32_bytes(n_isects);
-    expand_kernel<<<(unsigned)cdiv(M, EXP_THREADS), EXP_THREADS, 0, st>>>(
-        M, N, camera_ids, sorted_ids, cum_sorted, reinterpret_cast<const float2*>(means2d), radii, (float)tile_size, tile_w,
-        tile_h, tile_bits, keys_u, vals_u);
-    B2S_LAUNCH_CHECK();
-    B2S_CUDA(cub::DeviceRadixSort::SortPairs(w, cub_bytes, keys_u, tile_keys_sorted, vals_u, flatten_ids, n_isects, 0,
-                                             key_bits, st));
-    offsets32_kernel<<<(unsigned)cdiv(n_isects, 256), 256, 0, st>>>(n_isects, tile_keys_sorted, n_tiles, tile_bits,
-                                                                     total_tiles, offsets);
-    B2S_LAUNCH_CHECK();
-    return 0;
+    if (key_bits <= 16)
+        return tile_bin_impl<uint16_t>(M, N, camera_ids, n_isects, sorted_ids, means2d, radii, tile_size, tile_w, tile_h,
+                                       tile_bits, key_bits, total_tiles, tile_keys_sorted, flatten_ids, offsets, w, st);
+    return tile_bin_impl<uint32_t>(M, N, camera_ids, n_isects, sorted_ids, means2d, radii, tile_size, tile_w, tile_h,
+                                   tile_bits, key_bits, total_tiles, tile_keys_sorted, flatten_ids, offsets, w, st);
 }
 
-extern "C" int b2s_isect_ids_from_bins(int64_t n_isects, const uint32_t* tile_keys_sorted, const int32_t* flatten_ids,
-                                       const float* depths, int64_t* isect_ids, b2s_stream_t stream) {
-    B2S_REQUIRE(n_isects >= 0, "bad size");
+extern "C" int b2s_isect_ids_from_bins(int64_t n_isects, int32_t key_bytes, const void* tile_keys_sorted,
+                                       const int32_t* flatten_ids, const float* depths, int64_t* isect_ids,
+                                       b2s_stream_t stream) {
+    B2S_REQUIRE(n_isects >= 0 && (key_bytes == 2 || key_bytes == 4), "bad args");
     if (n_isects == 0) return 0;
     B2S_REQUIRE(tile_keys_sorted && flatten_ids && depths && isect_ids, "null pointer");
-    isect_ids_kernel<<<(unsigned)cdiv(n_isects, 256), 256, 0, (cudaStream_t)stream>>>(n_isects, tile_keys_sorted, flatten_ids,
-                                                                                     depths, isect_ids);
+    const unsigned grid = (unsigned)cdiv(n_isects, 256);
+    if (key_bytes == 2)
+        isect_ids_kernel<uint16_t><<<grid, 256, 0, (cudaStream_t)stream>>>(
+            n_isects, reinterpret_cast<const uint16_t*>(tile_keys_sorted), flatten_ids, depths, isect_ids);
+    else
+        isect_ids_kernel<uint32_t><<<grid, 256, 0, (cudaStream_t)stream>>>(
+            n_isects, reinterpret_cast<const uint32_t*>(tile_keys_sorted), flatten_ids, depths, isect_ids);
     B2S_LAUNCH_CHECK();
     return 0;
 }

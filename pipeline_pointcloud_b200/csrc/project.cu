@@ -119,6 +119,7 @@ __global__ void __launch_bounds__(FWD_THREADS) project_fwd_kernel(const b2s_proj
     covar_from_rot_scale(R, s, M, S);
 
     unsigned long long vis = 0ull;
+    int my_tiles = 0;
     for (int c = 0; c < a.C; ++c) {
         ProjOut o;
         project_one(cams[c], mean, S, W, H, a.eps2d, a.near_plane, a.far_plane, a.radius_clip, o, nullptr);
@@ -138,10 +139,18 @@ __global__ void __launch_bounds__(FWD_THREADS) project_fwd_kernel(const b2s_proj
                 cnt = (x1 - x0) * (y1 - y0);
             }
             a.tiles_per_gauss[i] = cnt;
+            my_tiles += cnt;
         }
         if (a.depth_keys) a.depth_keys[i] = o.radius > 0 ? __float_as_uint(o.depth) : 0xFFFFFFFFu;
         if (a.row_ids) a.row_ids[i] = (int32_t)i;
         if (o.radius > 0) vis |= 1ull << c;
+    }
+
+    if (a.total_isects) {   // one atomic per warp: the data-dependent size the host reads to size the next buffers
+        int wsum = my_tiles;
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) wsum += __shfl_xor_sync(FULL, wsum, d);
+        if (lane == 0 && wsum) atomicAdd(reinterpret_cast<unsigned long long*>(a.total_isects), (unsigned long long)wsum);
     }
 
     if (a.sh_coeffs == nullptr || a.colors == nullptr) return;
@@ -176,118 +185,151 @@ __global__ void __launch_bounds__(FWD_THREADS) project_fwd_kernel(const b2s_proj
 }
 
 // =================================================================================================
-// backward
+// backward, part 1: SH colour VJP (streams 12K B/Gaussian in and out -- 85 % of the backward's bytes --
+// with few registers, so it runs at high occupancy), writes v_sh_coeffs and the view-direction part of
+// v_means.  MULTI: more than one camera => separate in/out tiles; one camera => in place.
 // =================================================================================================
-template <int KVEC>
-__global__ void __launch_bounds__(BWD_THREADS) project_bwd_kernel(const b2s_project_bwd_args a) {
+constexpr int SHB_THREADS = 256;
+
+template <int KVEC, bool MULTI>
+__global__ void __launch_bounds__(SHB_THREADS, 4) sh_bwd_fused_kernel(const b2s_project_bwd_args a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     Camera* cams = reinterpret_cast<Camera*>(smem_raw);
     float* sh_tiles = reinterpret_cast<float*>(smem_raw + ((a.C * sizeof(Camera) + 15) / 16) * 16);
-    const float W = (float)a.width, H = (float)a.height;
-    load_cameras(cams, a.C, a.viewmats, a.Ks, a.campos, W, H);
+    load_cameras(cams, a.C, a.viewmats, a.Ks, a.campos, (float)a.width, (float)a.height);
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int64_t n = (int64_t)blockIdx.x * BWD_THREADS + threadIdx.x;
+    const int64_t n = (int64_t)blockIdx.x * SHB_THREADS + threadIdx.x;
     const bool live = n < a.N;
     const int64_t nc = live ? n : a.N - 1;
-
-    float mean[3], q[4], s[3];
+    float mean[3];
     mean[0] = __ldg(a.means + 3 * nc); mean[1] = __ldg(a.means + 3 * nc + 1); mean[2] = __ldg(a.means + 3 * nc + 2);
-    {
-        float4 qq = __ldg(reinterpret_cast<const float4*>(a.quats) + nc);
-        q[0] = qq.x; q[1] = qq.y; q[2] = qq.z; q[3] = qq.w;
-    }
-    s[0] = __ldg(a.scales + 3 * nc); s[1] = __ldg(a.scales + 3 * nc + 1); s[2] = __ldg(a.scales + 3 * nc + 2);
-    const float opac = a.opacities ? __ldg(a.opacities + nc) : 1.f;
-
-    Rot R; float qn[4], qnorm, M[9]; Sym3 S;
-    quat_to_rotmat(q, R, qn, qnorm);
-    covar_from_rot_scale(R, s, M, S);
-
     unsigned long long vis = 0ull;
     if (live)
         for (int c = 0; c < a.C; ++c)
             if (__ldg(a.radii + (int64_t)c * a.N + n) > 0) vis |= 1ull << c;
 
-    const bool with_sh = a.sh_coeffs != nullptr && a.v_sh_coeffs != nullptr;
     const int K = (a.sh_degree + 1) * (a.sh_degree + 1);
     const int rs = sh_row_stride(K);
-    float* tile_in = sh_tiles + (size_t)warp * 2 * 32 * rs;
-    float* tile_out = tile_in + 32 * rs;
-    const int64_t row0 = (int64_t)blockIdx.x * BWD_THREADS + warp * 32;
+    float* tile_in = sh_tiles + (size_t)warp * (MULTI ? 2 : 1) * 32 * rs;
+    float* tile_out = MULTI ? tile_in + 32 * rs : tile_in;
+    const int64_t row0 = (int64_t)blockIdx.x * SHB_THREADS + warp * 32;
     const int rows = (int)max((int64_t)0, min((int64_t)32, a.N - row0));
-    if (with_sh) {
-        const unsigned row_mask = __ballot_sync(FULL, live && vis != 0ull);
-        if (row_mask && a.v_colors)
-            sh_rows_load<KVEC>(tile_in, a.sh_coeffs + (size_t)row0 * a.sh_stride_k * 3, rows, row_mask, K, a.sh_stride_k, lane);
+    const unsigned row_mask = a.v_colors ? __ballot_sync(FULL, live && vis != 0ull) : 0u;
+    // masked-off rows are zero-filled by the loader, so culled Gaussians get zero gradients for free
+    sh_rows_load<KVEC>(tile_in, a.sh_coeffs + (size_t)row0 * a.sh_stride_k * 3, rows, row_mask, K, a.sh_stride_k, lane);
+    if (MULTI)
         for (int f = lane; f < 32 * rs; f += 32) tile_out[f] = 0.f;
-        __syncwarp();
+    __syncwarp();
+
+    float v_mean[3] = {0.f, 0.f, 0.f};
+    if (live && vis != 0ull && a.v_colors) {
+        const float* rin = tile_in + lane * rs;
+        float* rout = tile_out + lane * rs;
+        for (int c = 0; c < a.C; ++c) {
+            if (!((vis >> c) & 1ull)) continue;
+            const int64_t i = (int64_t)c * a.N + n;
+            float dx = mean[0] - cams[c].campos[0], dy = mean[1] - cams[c].campos[1], dz = mean[2] - cams[c].campos[2];
+            float inv = 1.f / fmaxf(sqrtf(dx * dx + dy * dy + dz * dz), 1e-12f);
+            float ux = dx * inv, uy = dy * inv, uz = dz * inv;
+            float Y[16], w[16];
+            sh_basis(a.sh_degree, ux, uy, uz, Y);
+            float cr = 0.5f, cg = 0.5f, cb = 0.5f;
+#pragma unroll 4
+            for (int k = 0; k < K; ++k) { cr += Y[k] * rin[3 * k]; cg += Y[k] * rin[3 * k + 1]; cb += Y[k] * rin[3 * k + 2]; }
+            const float vr = cr > 0.f ? __ldg(a.v_colors + 3 * i) : 0.f;        // clamp_min(., 0) gate
+            const float vg = cg > 0.f ? __ldg(a.v_colors + 3 * i + 1) : 0.f;
+            const float vb = cb > 0.f ? __ldg(a.v_colors + 3 * i + 2) : 0.f;
+#pragma unroll 4
+            for (int k = 0; k < K; ++k) {
+                w[k] = rin[3 * k] * vr + rin[3 * k + 1] * vg + rin[3 * k + 2] * vb;
+                if (MULTI) { rout[3 * k] += Y[k] * vr; rout[3 * k + 1] += Y[k] * vg; rout[3 * k + 2] += Y[k] * vb; }
+                else { rout[3 * k] = Y[k] * vr; rout[3 * k + 1] = Y[k] * vg; rout[3 * k + 2] = Y[k] * vb; }
+            }
+            float vx, vy, vz;
+            sh_basis_vjp(a.sh_degree, ux, uy, uz, w, vx, vy, vz);
+            const float dp = ux * vx + uy * vy + uz * vz;
+            v_mean[0] += (vx - ux * dp) * inv; v_mean[1] += (vy - uy * dp) * inv; v_mean[2] += (vz - uz * dp) * inv;
+        }
     }
+    if (live) {
+        if (a.accumulate) { a.v_means[3 * n] += v_mean[0]; a.v_means[3 * n + 1] += v_mean[1]; a.v_means[3 * n + 2] += v_mean[2]; }
+        else { a.v_means[3 * n] = v_mean[0]; a.v_means[3 * n + 1] = v_mean[1]; a.v_means[3 * n + 2] = v_mean[2]; }
+    }
+    __syncwarp();
+    if (rows > 0)
+        sh_rows_store<KVEC>(tile_out, a.v_sh_coeffs + (size_t)row0 * a.sh_stride_k * 3, rows, K, a.sh_stride_k, lane,
+                            a.accumulate != 0);
+}
+
+// =================================================================================================
+// backward, part 2: projection VJP (little traffic, heavy arithmetic)
+// =================================================================================================
+template <bool MEANS_ACC>   // MEANS_ACC: v_means already holds the SH part (or an earlier camera chunk)
+__global__ void __launch_bounds__(BWD_THREADS) project_bwd_kernel(const b2s_project_bwd_args a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    Camera* cams = reinterpret_cast<Camera*>(smem_raw);
+    const float W = (float)a.width, H = (float)a.height;
+    load_cameras(cams, a.C, a.viewmats, a.Ks, a.campos, W, H);
+
+    const int64_t n = (int64_t)blockIdx.x * BWD_THREADS + threadIdx.x;
+    if (n >= a.N) return;
+
+    float mean[3], q[4], s[3];
+    mean[0] = __ldg(a.means + 3 * n); mean[1] = __ldg(a.means + 3 * n + 1); mean[2] = __ldg(a.means + 3 * n + 2);
+    {
+        float4 qq = __ldg(reinterpret_cast<const float4*>(a.quats) + n);
+        q[0] = qq.x; q[1] = qq.y; q[2] = qq.z; q[3] = qq.w;
+    }
+    s[0] = __ldg(a.scales + 3 * n); s[1] = __ldg(a.scales + 3 * n + 1); s[2] = __ldg(a.scales + 3 * n + 2);
+    const float opac = a.opacities ? __ldg(a.opacities + n) : 1.f;
+
+    Rot R; float qn[4], qnorm, M[9]; Sym3 S;
+    quat_to_rotmat(q, R, qn, qnorm);
+    covar_from_rot_scale(R, s, M, S);
 
     float v_mean[3] = {0.f, 0.f, 0.f};
     Sym3 v_S = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     float v_opac = 0.f;
-    if (live) {
-        for (int c = 0; c < a.C; ++c) {
-            if (!((vis >> c) & 1ull)) continue;
-            ProjOut o; ProjMid mid;
-            if (!project_one(cams[c], mean, S, W, H, a.eps2d, a.near_plane, a.far_plane, a.radius_clip, o, &mid)) continue;
-            const int64_t i = (int64_t)c * a.N + n;
-            ProjGradIn g;
-            if (a.v_means2d) { float2 v = __ldg(reinterpret_cast<const float2*>(a.v_means2d) + i); g.v_x2d = v.x; g.v_y2d = v.y; }
-            else { g.v_x2d = g.v_y2d = 0.f; }
-            g.v_depth = a.v_depths ? __ldg(a.v_depths + i) : 0.f;
-            if (a.v_conics) { g.v_conic_a = __ldg(a.v_conics + 3 * i); g.v_conic_b = __ldg(a.v_conics + 3 * i + 1); g.v_conic_c = __ldg(a.v_conics + 3 * i + 2); }
-            else { g.v_conic_a = g.v_conic_b = g.v_conic_c = 0.f; }
-            g.v_comp = a.v_compensations ? __ldg(a.v_compensations + i) : 0.f;
-            if (a.v_opacities_out) {
-                float vo = __ldg(a.v_opacities_out + i);
-                if (a.antialiased) { g.v_comp += vo * opac; v_opac += vo * o.comp; }
-                else v_opac += vo;
+    bool any = false;
+    for (int c = 0; c < a.C; ++c) {
+        const int64_t i = (int64_t)c * a.N + n;
+        if (__ldg(a.radii + i) <= 0) continue;            // the forward's cull decision is authoritative
+        ProjMid mid;
+        project_mid_fast(cams[c], mean, S, a.eps2d, mid);
+        if (!(mid.det > 0.f)) continue;
+        any = true;
+        ProjGradIn g;
+        if (a.v_means2d) { float2 v = __ldg(reinterpret_cast<const float2*>(a.v_means2d) + i); g.v_x2d = v.x; g.v_y2d = v.y; }
+        else { g.v_x2d = g.v_y2d = 0.f; }
+        g.v_depth = a.v_depths ? __ldg(a.v_depths + i) : 0.f;
+        if (a.v_conics) { g.v_conic_a = __ldg(a.v_conics + 3 * i); g.v_conic_b = __ldg(a.v_conics + 3 * i + 1); g.v_conic_c = __ldg(a.v_conics + 3 * i + 2); }
+        else { g.v_conic_a = g.v_conic_b = g.v_conic_c = 0.f; }
+        g.v_comp = a.v_compensations ? __ldg(a.v_compensations + i) : 0.f;
+        if (a.v_opacities_out) {
+            float vo = __ldg(a.v_opacities_out + i);
+            if (a.antialiased) {
+                g.v_comp += vo * opac;
+                v_opac += vo * sqrtf(fmaxf(mid.det_orig / mid.det, 0.f));
             }
-            if (with_sh && a.v_colors) {
-                float dx = mean[0] - cams[c].campos[0], dy = mean[1] - cams[c].campos[1], dz = mean[2] - cams[c].campos[2];
-                float inv = 1.f / fmaxf(sqrtf(dx * dx + dy * dy + dz * dz), 1e-12f);
-                float ux = dx * inv, uy = dy * inv, uz = dz * inv;
-                float Y[16], w[16];
-                sh_basis(a.sh_degree, ux, uy, uz, Y);
-                const float* rin = tile_in + lane * rs;
-                float* rout = tile_out + lane * rs;
-                float cr = 0.5f, cg = 0.5f, cb = 0.5f;
-#pragma unroll 4
-                for (int k = 0; k < K; ++k) { cr += Y[k] * rin[3 * k]; cg += Y[k] * rin[3 * k + 1]; cb += Y[k] * rin[3 * k + 2]; }
-                float vr = cr > 0.f ? __ldg(a.v_colors + 3 * i) : 0.f;        // clamp_min(.,0) gate
-                float vg = cg > 0.f ? __ldg(a.v_colors + 3 * i + 1) : 0.f;
-                float vb = cb > 0.f ? __ldg(a.v_colors + 3 * i + 2) : 0.f;
-#pragma unroll 4
-                for (int k = 0; k < K; ++k) {
-                    w[k] = rin[3 * k] * vr + rin[3 * k + 1] * vg + rin[3 * k + 2] * vb;
-                    rout[3 * k] += Y[k] * vr; rout[3 * k + 1] += Y[k] * vg; rout[3 * k + 2] += Y[k] * vb;
-                }
-                float vx, vy, vz;
-                sh_basis_vjp(a.sh_degree, ux, uy, uz, w, vx, vy, vz);
-                float dp = ux * vx + uy * vy + uz * vz;
-                v_mean[0] += (vx - ux * dp) * inv; v_mean[1] += (vy - uy * dp) * inv; v_mean[2] += (vz - uz * dp) * inv;
-            }
-            project_one_bwd(cams[c], mean, S, a.eps2d, mid, g, v_mean, v_S);
+            else v_opac += vo;
         }
-        float v_quat[4], v_scale[3];
-        covar_bwd(q, qn, qnorm, R, s, M, v_S, v_quat, v_scale);
-        if (a.accumulate) {
-            for (int k = 0; k < 3; ++k) { a.v_means[3 * n + k] += v_mean[k]; a.v_scales[3 * n + k] += v_scale[k]; }
-            for (int k = 0; k < 4; ++k) a.v_quats[4 * n + k] += v_quat[k];
-            if (a.v_opacities) a.v_opacities[n] += v_opac;
-        } else {
-            for (int k = 0; k < 3; ++k) { a.v_means[3 * n + k] = v_mean[k]; a.v_scales[3 * n + k] = v_scale[k]; }
-            reinterpret_cast<float4*>(a.v_quats)[n] = make_float4(v_quat[0], v_quat[1], v_quat[2], v_quat[3]);
-            if (a.v_opacities) a.v_opacities[n] = v_opac;
-        }
+        project_one_bwd(cams[c], mean, S, a.eps2d, mid, g, v_mean, v_S);
     }
-    if (with_sh) {
-        __syncwarp();
-        if (rows > 0)
-            sh_rows_store<KVEC>(tile_out, a.v_sh_coeffs + (size_t)row0 * a.sh_stride_k * 3, rows, K, a.sh_stride_k, lane,
-                                a.accumulate != 0);
+    float v_quat[4] = {0.f, 0.f, 0.f, 0.f}, v_scale[3] = {0.f, 0.f, 0.f};
+    if (any) covar_bwd(q, qn, qnorm, R, s, M, v_S, v_quat, v_scale);
+    if (a.accumulate) {
+        for (int k = 0; k < 3; ++k) { a.v_means[3 * n + k] += v_mean[k]; a.v_scales[3 * n + k] += v_scale[k]; }
+        for (int k = 0; k < 4; ++k) a.v_quats[4 * n + k] += v_quat[k];
+        if (a.v_opacities) a.v_opacities[n] += v_opac;
+    } else {
+        for (int k = 0; k < 3; ++k) {
+            if (MEANS_ACC) { if (any) a.v_means[3 * n + k] += v_mean[k]; }
+            else a.v_means[3 * n + k] = v_mean[k];
+            a.v_scales[3 * n + k] = v_scale[k];
+        }
+        reinterpret_cast<float4*>(a.v_quats)[n] = make_float4(v_quat[0], v_quat[1], v_quat[2], v_quat[3]);
+        if (a.v_opacities) a.v_opacities[n] = v_opac;
     }
 }
 
@@ -333,19 +375,23 @@ extern "C" int b2s_project_bwd(const b2s_project_bwd_args* a, b2s_stream_t strea
     B2S_REQUIRE(a->v_means && a->v_quats && a->v_scales, "null gradient output");
     B2S_REQUIRE(aligned16(a->quats) && aligned16(a->v_quats), "quats misaligned");
     const bool sh = a->sh_coeffs != nullptr && a->v_sh_coeffs != nullptr;
-    int K = 1;
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t cam_bytes = ((a->C * sizeof(Camera) + 15) / 16) * 16;
     if (sh) {
         B2S_REQUIRE(a->sh_degree >= 0 && a->sh_degree <= 3, "sh_degree must be 0..3");
-        K = (a->sh_degree + 1) * (a->sh_degree + 1);
+        const int K = (a->sh_degree + 1) * (a->sh_degree + 1);
         B2S_REQUIRE(a->sh_stride_k >= K, "sh_stride_k < (deg+1)^2");
+        const bool vec = K == 16 && a->sh_stride_k == 16 && aligned16(a->sh_coeffs) && aligned16(a->v_sh_coeffs);
+        const bool multi = a->C > 1;
+        const size_t smem = cam_bytes + (size_t)(SHB_THREADS / 32) * (multi ? 2 : 1) * 32 * sh_row_stride(K) * sizeof(float);
+        auto kern = vec ? (multi ? sh_bwd_fused_kernel<16, true> : sh_bwd_fused_kernel<16, false>)
+                        : (multi ? sh_bwd_fused_kernel<0, true> : sh_bwd_fused_kernel<0, false>);
+        B2S_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<(unsigned)cdiv(a->N, SHB_THREADS), SHB_THREADS, smem, st>>>(*a);
+        B2S_LAUNCH_CHECK();
     }
-    const bool vec = sh && K == 16 && a->sh_stride_k == 16 && aligned16(a->sh_coeffs) && aligned16(a->v_sh_coeffs);
-    size_t smem = ((a->C * sizeof(Camera) + 15) / 16) * 16;
-    if (sh) smem += (size_t)(BWD_THREADS / 32) * 2 * 32 * sh_row_stride(K) * sizeof(float);
-    dim3 grid((unsigned)cdiv(a->N, BWD_THREADS));
-    auto kern = vec ? project_bwd_kernel<16> : project_bwd_kernel<0>;
-    B2S_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<grid, BWD_THREADS, smem, (cudaStream_t)stream>>>(*a);
+    auto kern2 = sh ? project_bwd_kernel<true> : project_bwd_kernel<false>;
+    kern2<<<(unsigned)cdiv(a->N, BWD_THREADS), BWD_THREADS, cam_bytes, st>>>(*a);
     B2S_LAUNCH_CHECK();
     return 0;
 }

@@ -80,7 +80,8 @@ def _bit_length(v: int) -> int:
 # stage 1: fused projection (+SH colour, + tile count)
 # ======================================================================================
 class _ProjectFused(torch.autograd.Function):
-    """radii, means2d, depths, conics, compensations, opacities_out, colors, tiles_per_gauss, depth_keys, row_ids."""
+    """radii, means2d, depths, conics, compensations, opacities_out, colors, tiles_per_gauss, depth_keys, row_ids,
+    total_isects."""
 
     @staticmethod
     def forward(ctx, means, quats, scales, opacities, sh_coeffs, viewmats, Ks, campos, width, height, eps2d,
@@ -108,6 +109,7 @@ class _ProjectFused(torch.autograd.Function):
         tiles = torch.empty(C, N, dtype=torch.int32, **o) if tile_size else None
         dkeys = torch.empty(C, N, dtype=torch.int32, **o) if tile_size else None     # uint32 bit patterns
         rowids = torch.empty(C, N, dtype=torch.int32, **o) if tile_size else None
+        total = torch.zeros(1, dtype=torch.int64, **o) if tile_size else None
         tw = (width + tile_size - 1) // tile_size if tile_size else 0
         th = (height + tile_size - 1) // tile_size if tile_size else 0
         lib = L.lib()
@@ -127,7 +129,7 @@ class _ProjectFused(torch.autograd.Function):
                 colors=ptr(colors[c0:c1]) if colors is not None else None,
                 tiles_per_gauss=ptr(tiles[c0:c1]) if tiles is not None else None,
                 depth_keys=ptr(dkeys[c0:c1]) if dkeys is not None else None,
-                row_ids=ptr(rowids[c0:c1]) if rowids is not None else None)
+                row_ids=ptr(rowids[c0:c1]) if rowids is not None else None, total_isects=ptr(total))
             if rowids is not None and c0 > 0:
                 raise NotImplementedError("more than 64 cameras per call with fused binning keys")
             with _stage("project_fwd"):
@@ -137,12 +139,12 @@ class _ProjectFused(torch.autograd.Function):
         ctx.set_materialize_grads(False)
         ctx.mark_non_differentiable(radii)
         if tiles is not None:
-            ctx.mark_non_differentiable(tiles, dkeys, rowids)
-        return radii, means2d, depths, conics, comps, opac_out, colors, tiles, dkeys, rowids
+            ctx.mark_non_differentiable(tiles, dkeys, rowids, total)
+        return radii, means2d, depths, conics, comps, opac_out, colors, tiles, dkeys, rowids, total
 
     @staticmethod
     def backward(ctx, _v_radii, v_means2d, v_depths, v_conics, v_comps, v_opac_out, v_colors, _v_tiles=None, _v_keys=None,
-                 _v_rows=None):
+                 _v_rows=None, _v_total=None):
         means, quats, scales, opacities, sh_coeffs, viewmats, Ks, campos, radii = ctx.saved_tensors
         width, height, eps2d, near_plane, far_plane, radius_clip, antialiased, sh_degree = ctx.cfg
         if ctx.needs_input_grad[5] or ctx.needs_input_grad[6]:
@@ -390,10 +392,12 @@ def _ws(nbytes: int, dev) -> Tensor:
 @torch.no_grad()
 def bin_depth_first(means2d: Tensor, radii: Tensor, depths: Tensor, tiles_per_gauss: Tensor, tile_size: int,
                     tile_width: int, tile_height: int, n_cameras: int, camera_ids: Optional[Tensor] = None,
-                    depth_keys: Optional[Tensor] = None, row_ids: Optional[Tensor] = None):
+                    depth_keys: Optional[Tensor] = None, row_ids: Optional[Tensor] = None,
+                    total_isects: Optional[Tensor] = None):
     """Depth-first binning (see include/b2s.h): returns (flatten_ids int32 [I], isect_offsets int32 [C,th,tw],
     make_isect_ids) where ``make_isect_ids()`` rebuilds the 64-bit sorted keys.  Bit-identical to
-    ``isect_tiles(sort=True)`` + ``isect_offset_encode`` with ~3x less HBM traffic."""
+    ``isect_tiles(sort=True)`` + ``isect_offset_encode`` with ~3x less HBM traffic.
+    ``depth_keys`` / ``row_ids`` / ``total_isects`` come from stage 1 when it ran fused."""
     dev = L.require_cuda(means2d, radii, depths)
     packed = camera_ids is not None
     M = radii.numel()
@@ -401,7 +405,6 @@ def bin_depth_first(means2d: Tensor, radii: Tensor, depths: Tensor, tiles_per_ga
     C = int(n_cameras)
     means2d, depths = f32c(means2d), f32c(depths)
     radii = radii.contiguous()
-    tiles_per_gauss = tiles_per_gauss.contiguous()
     cam = camera_ids.contiguous().to(torch.int64) if packed else None
     lib, st = L.lib(), L.stream_ptr(dev)
     if depth_keys is None or row_ids is None:
@@ -409,28 +412,30 @@ def bin_depth_first(means2d: Tensor, radii: Tensor, depths: Tensor, tiles_per_ga
         row_ids = torch.empty(M, dtype=torch.int32, device=dev)
         with _stage("isect_depth_keys"):
             check(lib.b2s_isect_depth_keys(M, ptr(depths), ptr(radii), ptr(depth_keys), ptr(row_ids), st), "b2s_isect_depth_keys")
+    if total_isects is None:
+        total_isects = tiles_per_gauss.sum(dtype=torch.int64).reshape(1)
     sorted_ids = torch.empty(max(M, 1), dtype=torch.int32, device=dev)
-    cum_sorted = torch.empty(max(M, 1), dtype=torch.int32, device=dev)
-    total = torch.empty(1, dtype=torch.int64, device=dev)
     ws = _ws(lib.b2s_depth_order_workspace_bytes(M), dev)
     with _stage("depth_order"):
-        check(lib.b2s_depth_order(M, ptr(depth_keys), ptr(row_ids), ptr(tiles_per_gauss), ptr(sorted_ids), ptr(cum_sorted),
-                                  ptr(total), ptr(ws), ws.numel(), st), "b2s_depth_order")
-    n_isects = int(total.item())          # the one host sync of a forward: sizes the per-intersection buffers
+        check(lib.b2s_depth_order(M, ptr(depth_keys), ptr(row_ids), ptr(sorted_ids), ptr(ws), ws.numel(), st), "b2s_depth_order")
+    # The one host sync of a forward (sizes the per-intersection buffers).  The depth sort is already
+    # enqueued, so the GPU keeps working while the host waits for the count that stage 1 produced.
+    n_isects = int(total_isects.item())
     if n_isects >= 2 ** 31:
         raise B2SError(f"n_isects = {n_isects} does not fit the int32 offsets of the API")
-    tile_keys = torch.empty(n_isects, dtype=torch.int32, device=dev)
+    key_bytes = int(lib.b2s_tile_key_bytes(C, tile_width, tile_height))
+    tile_keys = torch.empty(n_isects, dtype=torch.int32, device=dev)      # 16- or 32-bit keys inside
     flatten_ids = torch.empty(n_isects, dtype=torch.int32, device=dev)
     offsets = torch.empty(C, tile_height, tile_width, dtype=torch.int32, device=dev)
-    ws2 = _ws(lib.b2s_tile_bin_workspace_bytes(n_isects), dev)
+    ws2 = _ws(lib.b2s_tile_bin_workspace_bytes(M, n_isects), dev)
     with _stage("tile_bin"):
-        check(lib.b2s_tile_bin(M, N, ptr(cam), n_isects, ptr(sorted_ids), ptr(cum_sorted), ptr(means2d), ptr(radii), C,
-                               tile_size, tile_width, tile_height, ptr(tile_keys), ptr(flatten_ids), ptr(offsets), ptr(ws2),
-                               ws2.numel(), st), "b2s_tile_bin")
+        check(lib.b2s_tile_bin(M, N, ptr(cam), n_isects, ptr(sorted_ids), ptr(means2d), ptr(radii), C, tile_size, tile_width,
+                               tile_height, ptr(tile_keys), ptr(flatten_ids), ptr(offsets), ptr(ws2), ws2.numel(), st),
+              "b2s_tile_bin")
 
     def make_isect_ids():
         ids = torch.empty(n_isects, dtype=torch.int64, device=dev)
-        check(lib.b2s_isect_ids_from_bins(n_isects, ptr(tile_keys), ptr(flatten_ids), ptr(depths), ptr(ids),
+        check(lib.b2s_isect_ids_from_bins(n_isects, key_bytes, ptr(tile_keys), ptr(flatten_ids), ptr(depths), ptr(ids),
                                           L.stream_ptr(dev)), "b2s_isect_ids_from_bins")
         return ids
 

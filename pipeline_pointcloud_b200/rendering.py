@@ -95,7 +95,7 @@ def rasterization(
     # ---- stage 1: projection (+ SH colour + tile counts) in one kernel ------------------------------------
     fused_sh = sh_degree is not None and colors.dim() == 3
     campos = None          # the kernels derive the camera centres from viewmats
-    radii, means2d, depths, conics, _comps, opac, sh_cols, tiles, dkeys, rowids = ops._ProjectFused.apply(
+    radii, means2d, depths, conics, _comps, opac, sh_cols, tiles, dkeys, rowids, total = ops._ProjectFused.apply(
         means, quats, scales, opacities, colors if fused_sh else None, viewmats, Ks, campos, width, height, float(eps2d),
         float(near_plane), float(far_plane), float(radius_clip), antialiased, False,
         int(sh_degree) if fused_sh else 0, tile_size)
@@ -138,7 +138,7 @@ def rasterization(
     tiles_per_gauss = tiles_m
     flatten_ids, isect_offsets, make_isect_ids = ops.bin_depth_first(
         means2d_m, radii_m, depths_m, tiles_m, tile_size, tw, th, C, camera_ids=camera_ids,
-        depth_keys=None if packed else dkeys, row_ids=None if packed else rowids)
+        depth_keys=None if packed else dkeys, row_ids=None if packed else rowids, total_isects=total)
 
     # ---- stage 3: compositing ----------------------------------------------------------------------------
     ch = cols_m.shape[-1]

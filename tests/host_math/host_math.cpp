@@ -46,7 +46,8 @@ void hm_project_bwd(long N, int C, const float* means, const float* quats, const
             Camera cam;
             camera_setup(cam, viewmats + 16 * c, Ks + 9 * c, nullptr, (float)W, (float)H);
             ProjOut o; ProjMid mid;
-            if (!project_one(cam, means + 3 * n, S, (float)W, (float)H, eps2d, near_plane, far_plane, radius_clip, o, &mid)) continue;
+            if (!project_one(cam, means + 3 * n, S, (float)W, (float)H, eps2d, near_plane, far_plane, radius_clip, o, nullptr)) continue;
+            project_mid_fast(cam, means + 3 * n, S, eps2d, mid);   // what the backward kernel uses
             long i = (long)c * N + n;
             ProjGradIn g = {v_means2d[2 * i], v_means2d[2 * i + 1], v_depths[i], v_conics[3 * i], v_conics[3 * i + 1],
                             v_conics[3 * i + 2], v_comps ? v_comps[i] : 0.f};
