@@ -37,6 +37,43 @@ constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
 // status word: bits 63..62 = flag (0 none, 1 tile aggregate, 2 inclusive prefix), bits 61..0 = value
 constexpr unsigned long long FLAG_AGG = 1ull << 62, FLAG_INC = 2ull << 62, VAL_MASK = (1ull << 62) - 1;
 
+// Decoupled look-back, executed by one full warp: lane l inspects predecessor (tile - 1 - l), so a window of
+// 32 CTAs costs one memory round trip instead of 32.  Publishes this CTA's aggregate first and its inclusive
+// prefix at the end; returns the exclusive prefix.  CTA ids must be handed out dynamically (atomic counter)
+// so that every predecessor is already running.
+__device__ __forceinline__ unsigned long long lookback_warp(volatile unsigned long long* st, unsigned tile,
+                                                            unsigned long long block_sum, int lane) {
+    if (tile == 0) {
+        if (lane == 0) st[0] = FLAG_INC | block_sum;
+        return 0ull;
+    }
+    if (lane == 0) {
+        st[tile] = FLAG_AGG | block_sum;
+        __threadfence();
+    }
+    unsigned long long excl = 0ull;
+    long long base = (long long)tile - 1;
+    while (true) {
+        const long long k = base - lane;
+        unsigned long long sv = 2ull << 62;                              // before tile 0: inclusive prefix 0
+        if (k >= 0) sv = st[k];   // before tile 0: inclusive prefix 0
+        const unsigned long long flag = sv & ~VAL_MASK;
+        const unsigned ready = __ballot_sync(FULL, flag != 0ull);
+        const unsigned inc = __ballot_sync(FULL, flag == FLAG_INC);
+        const int p = inc ? (__ffs(inc) - 1) : 31;                    // nearest predecessor with an inclusive prefix
+        const unsigned need = (p == 31) ? FULL : ((1u << (p + 1)) - 1u);
+        if ((ready & need) != need) continue;                         // someone in the window has not published yet
+        unsigned long long v = (lane <= p) ? (sv & VAL_MASK) : 0ull;
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(FULL, v, d);
+        excl += v;
+        if (inc) break;
+        base -= 32;
+    }
+    if (lane == 0) st[tile] = FLAG_INC | (excl + block_sum);
+    return excl;
+}
+
 template <bool GATHER>  // GATHER: scan in[idx[i]] (values taken in a permuted order)
 __global__ void __launch_bounds__(SCAN_THREADS) scan_kernel(int64_t M, const int32_t* __restrict__ in,
                                                             const int32_t* __restrict__ idx,
@@ -73,27 +110,12 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_kernel(int64_t M, const int
         if (w < warp) warp_off += x;
         block_sum += x;
     }
-    if (threadIdx.x == 0) {
-        volatile unsigned long long* st = status;
-        unsigned long long excl = 0;
-        if (tile == 0) {
-            st[0] = FLAG_INC | block_sum;
-        } else {
-            st[tile] = FLAG_AGG | block_sum;
-            __threadfence();
-            long long j = (long long)tile - 1;
-            while (true) {
-                unsigned long long sv = st[j];
-                unsigned long long flag = sv & ~VAL_MASK;
-                if (flag == 0) continue;  // predecessor has a smaller dynamic id => it is running: spin
-                excl += sv & VAL_MASK;
-                if (flag == FLAG_INC) break;
-                --j;
-            }
-            st[tile] = FLAG_INC | (excl + block_sum);
+    if (warp == 0) {
+        const unsigned long long excl = lookback_warp(status, tile, block_sum, lane);
+        if (lane == 0) {
+            s_prefix = excl;
+            if ((int64_t)(tile + 1) * SCAN_TILE >= M) *total = (int64_t)(excl + block_sum);
         }
-        s_prefix = excl;
-        if ((int64_t)(tile + 1) * SCAN_TILE >= M) *total = (int64_t)(excl + block_sum);
     }
     __syncthreads();
     unsigned long long run = s_prefix + warp_off + (inc - tsum);
@@ -232,26 +254,9 @@ __global__ void __launch_bounds__(EXP_THREADS) expand_kernel(int64_t M, int64_t 
         if (w < warp) warp_off += x;
         block_sum += x;
     }
-    if (threadIdx.x == 0) {
-        volatile unsigned long long* st = status;
-        unsigned long long excl = 0;
-        if (cta == 0) {
-            st[0] = FLAG_INC | (unsigned long long)block_sum;
-        } else {
-            st[cta] = FLAG_AGG | (unsigned long long)block_sum;
-            __threadfence();
-            long long k = (long long)cta - 1;
-            while (true) {
-                unsigned long long sv = st[k];
-                unsigned long long flag = sv & ~VAL_MASK;
-                if (flag == 0) continue;
-                excl += sv & VAL_MASK;
-                if (flag == FLAG_INC) break;
-                --k;
-            }
-            st[cta] = FLAG_INC | (excl + (unsigned long long)block_sum);
-        }
-        s_prefix = excl;
+    if (warp == 0) {
+        const unsigned long long excl = lookback_warp(status, cta, (unsigned long long)block_sum, lane);
+        if (lane == 0) s_prefix = excl;
     }
     __syncthreads();
     if (total == 0) return;
