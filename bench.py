@@ -194,6 +194,10 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=None)
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (profiling runs only)")
+    ap.add_argument("--multi-gpu", default="sharded", choices=["sharded", "allreduce"],
+                    help="N>1: 'sharded' = Gaussians sharded over ranks + all-to-all of projected splats to the camera "
+                         "owners (rasterization(distributed=True), what the reference's multi-GPU branch runs); "
+                         "'allreduce' = replicated Gaussians + dense-gradient all-reduce (BASELINE config 4)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -236,7 +240,9 @@ def main():
 
     C_total = max(world, 1)
     scene = make_scene(N, deg, C_total, W, H, seed=0)            # identical on every rank (CPU generator)
-    leaves_host = {k: scene[k].pin_memory() for k in ("means", "quats", "scales", "opacities", "colors")}
+    sharded = world > 1 and args.multi_gpu == "sharded"
+    lo_n, hi_n = (rank * N // world, (rank + 1) * N // world) if sharded else (0, N)
+    leaves_host = {k: scene[k][lo_n:hi_n].contiguous().pin_memory() for k in ("means", "quats", "scales", "opacities", "colors")}
     cam_host = {"viewmats": scene["viewmats"][rank:rank + 1].contiguous().pin_memory(),
                 "Ks": scene["Ks"][rank:rank + 1].contiguous().pin_memory()}
     params = {k: v.to(dev).requires_grad_() for k, v in leaves_host.items()}
@@ -245,7 +251,7 @@ def main():
     v_r_host = torch.rand(1, H, W, 3, generator=g).pin_memory()
     v_a_host = torch.rand(1, H, W, 1, generator=g).pin_memory()
     v_r, v_a = v_r_host.to(dev), v_a_host.to(dev)
-    kw = dict(sh_degree=deg, packed=args.packed, rasterize_mode=mode)
+    kw = dict(sh_degree=deg, packed=args.packed or sharded, rasterize_mode=mode, distributed=sharded)
     plist = list(params.values())
     stats = {}
 
@@ -255,7 +261,7 @@ def main():
         r, a, m = b2s.rasterization(p["means"], p["quats"], p["scales"], p["opacities"], p["colors"], c["viewmats"],
                                     c["Ks"], W, H, **kw)
         torch.autograd.backward([r, a], [vr, va])
-        if world > 1:
+        if world > 1 and not sharded:
             allreduce_gradients(p.values())
         stats["n_isects"] = m["flatten_ids"].numel()      # (not isect_ids: that would materialise the lazy 64-bit keys)
         stats["n_visible"] = m["n_visible"] if "n_visible" in m else None
@@ -282,7 +288,7 @@ def main():
     for _ in range(max(args.warmup, 3)):
         r, a, m = step()
     torch.cuda.synchronize()
-    n_visible = int((m["radii"] > 0).sum()) if not args.packed else int(m["means2d"].shape[0])
+    n_visible = int((m["radii"] > 0).sum()) if not (args.packed or sharded) else int(m["means2d"].shape[0])
 
     sampler = ClockSampler(local_rank)
     if rank == 0:
@@ -352,7 +358,10 @@ def main():
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
         "config": {"workload": f"{args.workload}: {N} random Gaussians, SH deg {deg}, {W}x{H}, {mode}, fwd+bwd, "
-                               f"packed={args.packed}, 1 camera per GPU" + (", dense-gradient all-reduce" if world > 1 else ""),
+                               f"packed={args.packed or sharded}, 1 camera per GPU" +
+                               ((", Gaussians sharded over ranks, NCCL all-to-all of projected splats to the camera owners, "
+                                 "reverse all-to-all of gradients") if sharded else
+                                (", replicated Gaussians, dense-gradient all-reduce" if world > 1 else "")),
                    "n_isects": I, "n_visible": n_visible, "l2": "inputs (1.4 GB parameters + 0.3 GB keys) exceed the 126 MB L2",
                    "parallelism": f"dp{world}"},
         "iters_per_s": 1e3 / ms_per_step * C_total,

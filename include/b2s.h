@@ -184,6 +184,51 @@ B2S_API int b2s_isect_ids_from_bins(int64_t n_isects, int32_t key_bytes, const v
                                     const int32_t* flatten_ids, const float* depths, int64_t* isect_ids,
                                     b2s_stream_t stream);
 
+/* Packed layout (gsplat `packed=True`): gather the visible rows `sel` (ascending dense indices c*N+n) of the
+ * stage-1 outputs into nnz-row tensors (+ camera_ids / gaussian_ids), and scatter gradients back into
+ * zero-filled dense tensors.  Any output pointer may be NULL (skipped). */
+B2S_API int b2s_pack_rows(int64_t nnz, int64_t N, const int64_t* sel, int32_t channels, const float* means2d,
+                          const float* depths, const float* conics, const float* opacities, const float* colors,
+                          const int32_t* radii, const int32_t* tiles, float* means2d_p, float* depths_p, float* conics_p,
+                          float* opacities_p, float* colors_p, int32_t* radii_p, int32_t* tiles_p, int64_t* camera_ids,
+                          int64_t* gaussian_ids, b2s_stream_t stream);
+B2S_API int b2s_unpack_rows(int64_t nnz, const int64_t* sel, int32_t channels, const float* g_means2d,
+                            const float* g_depths, const float* g_conics, const float* g_opacities, const float* g_colors,
+                            float* v_means2d, float* v_depths, float* v_conics, float* v_opacities, float* v_colors,
+                            b2s_stream_t stream);
+
+/* Multi-GPU routing (rasterization(distributed=True)): the visible splats of the local shard travel to the
+ * camera owners as ONE fused record each, [x, y, depth, conic(3), opacity, colour(ch), radius, tiles, local
+ * camera, global Gaussian id] = 11 + ch floats (integers bit-cast), so a single NCCL all-to-all moves them;
+ * gradients come back as [7 + ch] records by the reverse all-to-all and are scattered into dense tensors. */
+B2S_API int b2s_pack_payload(int64_t nnz, int64_t N, const int64_t* sel, int32_t channels, int32_t cams_per_rank,
+                             int64_t gid_offset, const float* means2d, const float* depths, const float* conics,
+                             const float* opacities, const float* colors, const int32_t* radii, const int32_t* tiles,
+                             float* payload, b2s_stream_t stream);
+B2S_API int b2s_split_payload(int64_t n, int32_t channels, const float* payload, float* means2d, float* depths,
+                              float* conics, float* opacities, float* colors, int32_t* radii, int32_t* tiles,
+                              int64_t* camera_ids, int64_t* gaussian_ids, b2s_stream_t stream);
+B2S_API int b2s_join_grads(int64_t n, int32_t channels, const float* g_means2d, const float* g_depths,
+                           const float* g_conics, const float* g_opacities, const float* g_colors, float* out,
+                           b2s_stream_t stream);
+B2S_API int b2s_scatter_grads(int64_t nnz, const int64_t* sel, int32_t channels, const float* in, float* v_means2d,
+                              float* v_depths, float* v_conics, float* v_opacities, float* v_colors, b2s_stream_t stream);
+
+/* Fused pack + exchange over NVLink peer memory (replaces b2s_pack_payload + NCCL all-to-all, and
+ * b2s_join_grads + the reverse all-to-all): the kernel stores every record straight into the destination
+ * rank's receive buffer.  `host_peer_buffers[d]` = this process's mapping of rank d's symmetric buffer;
+ * rows are grouped by destination (`host_*_counts[d]` rows for rank d, in order); `host_*_base[d]` = first row
+ * this rank owns inside rank d's buffer.  The three host arrays have `world` entries and are read during the
+ * call (passed to the kernel by value).  The caller provides the barriers around the exchange. */
+B2S_API int b2s_p2p_pack(int64_t nnz, int64_t N, const int64_t* sel, int32_t channels, int32_t cams_per_rank,
+                         int64_t gid_offset, const float* means2d, const float* depths, const float* conics,
+                         const float* opacities, const float* colors, const int32_t* radii, const int32_t* tiles,
+                         int32_t world, const int64_t* host_send_counts, const int64_t* host_dest_base,
+                         void* const* host_peer_buffers, b2s_stream_t stream);
+B2S_API int b2s_p2p_join(int64_t n, int32_t channels, const float* g_means2d, const float* g_depths, const float* g_conics,
+                         const float* g_opacities, const float* g_colors, int32_t world, const int64_t* host_recv_counts,
+                         const int64_t* host_src_base, void* const* host_peer_buffers, b2s_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Stage 3: per-16x16-tile front-to-back compositing.  Replaces gsplat `rasterize_to_pixels`
  * fwd / bwd.  Rows of means2d/conics/colors/opacities are addressed by

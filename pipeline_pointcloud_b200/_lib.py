@@ -106,6 +106,15 @@ SYMBOLS = {
     "b2s_tile_bin": (c_int32, [c_int64, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_int32, c_int32,
                                c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
     "b2s_isect_ids_from_bins": (c_int32, [c_int64, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "b2s_pack_rows": (c_int32, [c_int64, c_int64, c_void_p, c_int32] + [c_void_p] * 17),
+    "b2s_unpack_rows": (c_int32, [c_int64, c_void_p, c_int32] + [c_void_p] * 11),
+    "b2s_pack_payload": (c_int32, [c_int64, c_int64, c_void_p, c_int32, c_int32, c_int64] + [c_void_p] * 9),
+    "b2s_split_payload": (c_int32, [c_int64, c_int32] + [c_void_p] * 11),
+    "b2s_join_grads": (c_int32, [c_int64, c_int32] + [c_void_p] * 7),
+    "b2s_scatter_grads": (c_int32, [c_int64, c_void_p, c_int32] + [c_void_p] * 7),
+    "b2s_p2p_pack": (c_int32, [c_int64, c_int64, c_void_p, c_int32, c_int32, c_int64] + [c_void_p] * 7 +
+                     [c_int32, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "b2s_p2p_join": (c_int32, [c_int64, c_int32] + [c_void_p] * 5 + [c_int32, c_void_p, c_void_p, c_void_p, c_void_p]),
     "b2s_composite_fwd": (c_int32, [POINTER(CompositeFwdArgs), c_void_p]),
     "b2s_composite_bwd": (c_int32, [POINTER(CompositeBwdArgs), c_void_p]),
 }

@@ -1,25 +1,38 @@
 """Multi-GPU plumbing for the rasterization path: one process per GPU,
-``torch.distributed`` (NCCL over NVLink 5 / NVSwitch on the B200 box, gloo in CPU tests of the host logic).
+``torch.distributed`` (NCCL over NVLink 5 / NVSwitch on the B200 box; gloo in the CPU tests of the host logic).
 
-(i) camera data-parallel: Gaussians replicated, each rank renders its own cameras, dense-gradient all-reduce.
-(ii) Gaussian-sharded projection + tile-stripe ownership with an all-to-all of projected splats.
+Two schemes, both with exactly one exchange step:
+
+(i) camera data-parallel, replicated Gaussians (BASELINE config 4): every rank renders its own cameras and
+    the dense gradients are all-reduced -- ``allreduce_gradients``.
+(ii) Gaussian-sharded projection + all-to-all to the camera owners -- ``rasterization(distributed=True)``, the
+    scheme the reference's multi-GPU branch runs (``simple_trainer.py --packed`` under
+    ``torch.multiprocessing.spawn``, source/container/src/main.py:1317-1347; upstream
+    ``gsplat.rendering.rasterization(distributed=True)``): rank r owns N_r Gaussians and C_r cameras, projects
+    its Gaussians into *every* camera, routes the visible splats (40 B + ids each) to the rank that owns the
+    camera, and composites its own cameras from everybody's splats.  The backward returns the per-splat
+    gradients by the reverse all-to-all, so every rank ends up with the complete gradient of its own shard and
+    no all-reduce is needed.
 """
 from __future__ import annotations
 
-from typing import Iterable, List, Optional, Sequence
+from typing import Iterable, List, Optional, Sequence, Tuple
 
 import torch
 import torch.distributed as dist
 from torch import Tensor
 
 
+# ----------------------------------------------------------------------------------------------------------
+# (i) camera data-parallel
+# ----------------------------------------------------------------------------------------------------------
 def cameras_of_rank(n_cameras: int, rank: int, world_size: int) -> List[int]:
     """Camera data-parallel assignment: rank r renders cameras c with c % world_size == r."""
     return [c for c in range(n_cameras) if c % world_size == rank]
 
 
 def allreduce_gradients(params: Iterable[Tensor], group=None, average: bool = False) -> None:
-    """Sums (or averages) ``p.grad`` over ranks, one collective per parameter group so that the
+    """Sums (or averages) ``p.grad`` over ranks, one collective per parameter group, largest first, so that the
     SH-coefficient bucket (81 % of the bytes) is in flight while the small ones are issued."""
     if not dist.is_initialized() or dist.get_world_size(group) == 1:
         return
@@ -33,7 +46,339 @@ def allreduce_gradients(params: Iterable[Tensor], group=None, average: bool = Fa
             p.grad.div_(ws)
 
 
-def rasterization_distributed(*args, **kwargs):
-    raise NotImplementedError(
-        "distributed=True (Gaussian-sharded projection + all-to-all) is not implemented yet; "
-        "camera data-parallel training uses rasterization() per rank + allreduce_gradients()")
+# ----------------------------------------------------------------------------------------------------------
+# (ii) Gaussian-sharded projection + all-to-all: host-side routing (device agnostic, tested with gloo on CPU)
+# ----------------------------------------------------------------------------------------------------------
+def _exchange_rows(x: Tensor, send_counts: Sequence[int], recv_counts: Sequence[int], group=None) -> Tensor:
+    """Variable-split all-to-all over dim 0.  NCCL: one ``all_to_all_single`` (flat, topology-optimal on
+    NVSwitch); gloo has no all-to-all, so the CPU tests go through point-to-point sends."""
+    x = x.contiguous()
+    out = x.new_empty((int(sum(recv_counts)),) + tuple(x.shape[1:]))
+    if dist.get_backend(group) == "nccl":
+        dist.all_to_all_single(out, x, output_split_sizes=list(recv_counts), input_split_sizes=list(send_counts), group=group)
+        return out
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    ins = list(x.split(list(send_counts), dim=0))
+    outs = list(out.split(list(recv_counts), dim=0))
+    outs[rank].copy_(ins[rank])
+    ops = []
+    for peer in range(world):
+        if peer == rank:
+            continue
+        if send_counts[peer] > 0:
+            ops.append(dist.P2POp(dist.isend, ins[peer].contiguous(), dist.get_global_rank(group, peer) if group else peer, group))
+        if recv_counts[peer] > 0:
+            ops.append(dist.P2POp(dist.irecv, outs[peer], dist.get_global_rank(group, peer) if group else peer, group))
+    if ops:
+        for w in dist.batch_isend_irecv(ops):
+            w.wait()
+    return out
+
+
+class _AllToAllRows(torch.autograd.Function):
+    """Differentiable row exchange: the backward is the same exchange with the split lists swapped."""
+
+    @staticmethod
+    def forward(ctx, x, send_counts, recv_counts, group):
+        ctx.cfg = (list(send_counts), list(recv_counts), group)
+        return _exchange_rows(x, send_counts, recv_counts, group)
+
+    @staticmethod
+    def backward(ctx, g):
+        send_counts, recv_counts, group = ctx.cfg
+        return _exchange_rows(g, recv_counts, send_counts, group), None, None, None
+
+
+def exchange_counts(send_counts: Sequence[int], device, group=None) -> List[int]:
+    """Every rank tells every other how many rows it will send: int64[W] all-to-all (equal splits)."""
+    world = dist.get_world_size(group)
+    mine = torch.tensor(list(send_counts), dtype=torch.int64, device=device)
+    gathered = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(gathered, mine, group=group)
+    rank = dist.get_rank(group)
+    return [int(g[rank]) for g in gathered]
+
+
+def all_gather_cameras(viewmats: Tensor, Ks: Tensor, n_local_gaussians: int, group=None) -> Tuple[Tensor, Tensor, List[int]]:
+    """All ranks' cameras (every rank must hold the same number) and every rank's Gaussian count."""
+    world = dist.get_world_size(group)
+    vs = [torch.empty_like(viewmats) for _ in range(world)]
+    ks = [torch.empty_like(Ks) for _ in range(world)]
+    dist.all_gather(vs, viewmats.contiguous(), group=group)
+    dist.all_gather(ks, Ks.contiguous(), group=group)
+    n = torch.tensor([n_local_gaussians], dtype=torch.int64, device=viewmats.device)
+    ns = [torch.empty_like(n) for _ in range(world)]
+    dist.all_gather(ns, n, group=group)
+    return torch.cat(vs, 0), torch.cat(ks, 0), [int(t) for t in ns]
+
+
+def route_to_camera_owners(payload: Tensor, ids: Tensor, camera_ids: Tensor, gaussian_ids: Tensor, cams_per_rank: int,
+                           n_world: Sequence[int], group=None):
+    """Routes packed per-splat rows (camera-major: ``camera_ids`` ascending, global camera numbering) to the rank
+    that owns each camera.  ``payload`` [nnz,F] float (differentiable), ``ids`` [nnz,K] integer side data.
+    Returns (payload, ids, local camera ids, global Gaussian ids) of the rows this rank must composite."""
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    dest = torch.div(camera_ids, cams_per_rank, rounding_mode="floor")
+    send_counts = torch.bincount(dest, minlength=world).tolist()
+    recv_counts = exchange_counts(send_counts, payload.device, group)
+    offset_g = int(sum(n_world[:rank]))
+    meta = torch.stack([camera_ids - dest * cams_per_rank, gaussian_ids + offset_g], dim=1)      # local cam, global id
+    side = torch.cat([ids.to(torch.int64), meta.to(torch.int64)], dim=1)
+    payload = _AllToAllRows.apply(payload, send_counts, recv_counts, group)
+    side = _exchange_rows(side, send_counts, recv_counts, group)
+    k = ids.shape[1]
+    return payload, side[:, :k], side[:, k], side[:, k + 1], send_counts, recv_counts
+
+
+class _RouteSplatsCUDA(torch.autograd.Function):
+    """The same routing as ``route_to_camera_owners`` for CUDA tensors, fused: one pack kernel, ONE NCCL
+    all-to-all of [11+ch]-float records, one split kernel; the backward joins the gradients into [7+ch] records,
+    sends them back with the reverse all-to-all and scatters them into dense (zero-filled) gradients."""
+
+    @staticmethod
+    def forward(ctx, means2d, depths, conics, opac, cols, radii, tiles, cams_per_rank, n_world, group):
+        from . import _lib as L
+        from . import ops
+        dev = means2d.device
+        rank, world = dist.get_rank(group), dist.get_world_size(group)
+        C_all, N = radii.shape
+        ch = cols.shape[-1]
+        means2d, depths, conics, opac, cols = (L.f32c(t) for t in (means2d, depths, conics, opac, cols))
+        radii, tiles = radii.contiguous(), tiles.contiguous()
+        sel = (radii.reshape(-1) > 0).nonzero(as_tuple=True)[0]              # ascending = camera-major
+        bounds = torch.searchsorted(sel, torch.arange(world + 1, device=dev) * (cams_per_rank * N))
+        send = (bounds[1:] - bounds[:-1]).contiguous()
+        gathered = [torch.empty_like(send) for _ in range(world)]
+        dist.all_gather(gathered, send, group=group)
+        table = torch.stack(gathered).tolist()                                # one host sync: the whole W x W count table
+        send_counts, recv_counts = table[rank], [table[src][rank] for src in range(world)]
+        nnz, n_recv, F = sel.numel(), int(sum(recv_counts)), 11 + ch
+        lib, st = L.lib(), L.stream_ptr(dev)
+        payload = torch.empty(nnz, F, device=dev)
+        with ops._stage("route_pack"):
+            L.check(lib.b2s_pack_payload(nnz, N, L.ptr(sel), ch, cams_per_rank, int(sum(n_world[:rank])), L.ptr(means2d),
+                                         L.ptr(depths), L.ptr(conics), L.ptr(opac), L.ptr(cols), L.ptr(radii), L.ptr(tiles),
+                                         L.ptr(payload), st), "b2s_pack_payload")
+        recv = torch.empty(n_recv, F, device=dev)
+        with ops._stage("all_to_all_fwd", launches=0):
+            dist.all_to_all_single(recv, payload, output_split_sizes=recv_counts, input_split_sizes=send_counts, group=group)
+        o = dict(device=dev)
+        means2d_m, depths_m, conics_m = torch.empty(n_recv, 2, **o), torch.empty(n_recv, **o), torch.empty(n_recv, 3, **o)
+        opac_m, cols_m = torch.empty(n_recv, **o), torch.empty(n_recv, ch, **o)
+        radii_m, tiles_m = torch.empty(n_recv, dtype=torch.int32, **o), torch.empty(n_recv, dtype=torch.int32, **o)
+        cam_m, gid_m = torch.empty(n_recv, dtype=torch.int64, **o), torch.empty(n_recv, dtype=torch.int64, **o)
+        with ops._stage("route_split"):
+            L.check(lib.b2s_split_payload(n_recv, ch, L.ptr(recv), L.ptr(means2d_m), L.ptr(depths_m), L.ptr(conics_m),
+                                          L.ptr(opac_m), L.ptr(cols_m), L.ptr(radii_m), L.ptr(tiles_m), L.ptr(cam_m),
+                                          L.ptr(gid_m), st), "b2s_split_payload")
+        ctx.save_for_backward(sel)
+        ctx.cfg = (send_counts, recv_counts, group, ch, (means2d.shape, depths.shape, conics.shape, opac.shape, cols.shape))
+        ctx.set_materialize_grads(False)
+        ctx.mark_non_differentiable(radii_m, tiles_m, cam_m, gid_m)
+        return means2d_m, depths_m, conics_m, opac_m, cols_m, radii_m, tiles_m, cam_m, gid_m
+
+    @staticmethod
+    def backward(ctx, g_means2d, g_depths, g_conics, g_opac, g_cols, *_):
+        from . import _lib as L
+        from . import ops
+        (sel,) = ctx.saved_tensors
+        send_counts, recv_counts, group, ch, shapes = ctx.cfg
+        dev = sel.device
+        n_recv, nnz, G = int(sum(recv_counts)), sel.numel(), 7 + ch
+        lib, st = L.lib(), L.stream_ptr(dev)
+        gs = [L.f32c(g) for g in (g_means2d, g_depths, g_conics, g_opac, g_cols)]
+        joined = torch.empty(n_recv, G, device=dev)
+        with ops._stage("route_join"):
+            L.check(lib.b2s_join_grads(n_recv, ch, *[L.ptr(g) for g in gs], L.ptr(joined), st), "b2s_join_grads")
+        back = torch.empty(nnz, G, device=dev)
+        with ops._stage("all_to_all_bwd", launches=0):
+            dist.all_to_all_single(back, joined, output_split_sizes=send_counts, input_split_sizes=recv_counts, group=group)
+        outs = [torch.zeros(s, dtype=torch.float32, device=dev) for s in shapes]
+        with ops._stage("route_scatter"):
+            L.check(lib.b2s_scatter_grads(nnz, L.ptr(sel), ch, L.ptr(back), *[L.ptr(o) for o in outs], st), "b2s_scatter_grads")
+        return tuple(outs) + (None,) * 5
+
+
+class _SymmBuffers:
+    """Persistent symmetric-memory exchange buffers (one per direction), mapped into every peer.  Growing them is
+    a collective decision taken from the W x W count table, which every rank holds, so all ranks agree."""
+    _cache = {}
+
+    @classmethod
+    def get(cls, group, key, n_floats, dev):
+        import torch.distributed._symmetric_memory as symm
+        k = (id(group), key, dev.index)
+        cur = cls._cache.get(k)
+        if cur is None or cur[0].numel() < n_floats:
+            cap = int(n_floats * 1.25) + 4096
+            t = symm.empty(cap, dtype=torch.float32, device=dev)
+            h = symm.rendezvous(t, group if group is not None else dist.group.WORLD)
+            cur = (t, h)
+            cls._cache[k] = cur
+        return cur
+
+
+def _i64(vals):
+    import ctypes
+    return (ctypes.c_int64 * len(vals))(*[int(v) for v in vals])
+
+
+def _ptrs(vals):
+    import ctypes
+    return (ctypes.c_void_p * len(vals))(*[int(v) for v in vals])
+
+
+class _RouteSplatsP2P(torch.autograd.Function):
+    """Routing fused with the exchange: the pack kernel stores each [11+ch]-float record straight into the owner
+    rank's receive buffer over NVLink (symmetric memory peer mappings), the backward's join kernel stores the
+    [7+ch]-float gradient records straight back into the source rank's buffer.  No send buffers, no collective
+    call on the data path; two ~7 us symmetric-memory barriers bracket each exchange."""
+
+    @staticmethod
+    def forward(ctx, means2d, depths, conics, opac, cols, radii, tiles, cams_per_rank, n_world, group):
+        from . import _lib as L
+        from . import ops
+        dev = means2d.device
+        rank, world = dist.get_rank(group), dist.get_world_size(group)
+        C_all, N = radii.shape
+        ch = cols.shape[-1]
+        means2d, depths, conics, opac, cols = (L.f32c(t) for t in (means2d, depths, conics, opac, cols))
+        radii, tiles = radii.contiguous(), tiles.contiguous()
+        sel = (radii.reshape(-1) > 0).nonzero(as_tuple=True)[0]              # ascending = camera-major
+        bounds = torch.searchsorted(sel, torch.arange(world + 1, device=dev) * (cams_per_rank * N))
+        send = (bounds[1:] - bounds[:-1]).contiguous()
+        gathered = [torch.empty_like(send) for _ in range(world)]
+        dist.all_gather(gathered, send, group=group)
+        table = torch.stack(gathered).tolist()                                # one host sync: the W x W count table
+        send_counts, recv_counts = table[rank], [table[src][rank] for src in range(world)]
+        nnz, n_recv, F, G = sel.numel(), int(sum(recv_counts)), 11 + ch, 7 + ch
+        need_f = max(sum(table[src][d] for src in range(world)) for d in range(world)) * F
+        need_b = max(sum(table[s]) for s in range(world)) * G
+        buf_f, h_f = _SymmBuffers.get(group, "fwd", need_f, dev)
+        buf_b, h_b = _SymmBuffers.get(group, "bwd", need_b, dev)
+        dest_base = [sum(table[src][d] for src in range(rank)) for d in range(world)]
+        lib, st = L.lib(), L.stream_ptr(dev)
+        with ops._stage("route_p2p_fwd"):
+            h_f.barrier()                                                     # every peer is done with its receive buffer
+            L.check(lib.b2s_p2p_pack(nnz, N, L.ptr(sel), ch, cams_per_rank, int(sum(n_world[:rank])), L.ptr(means2d),
+                                     L.ptr(depths), L.ptr(conics), L.ptr(opac), L.ptr(cols), L.ptr(radii), L.ptr(tiles),
+                                     world, _i64(send_counts), _i64(dest_base), _ptrs(h_f.buffer_ptrs), st), "b2s_p2p_pack")
+            h_f.barrier()                                                     # every peer's stores have landed
+        recv = buf_f[: n_recv * F]
+        o = dict(device=dev)
+        means2d_m, depths_m, conics_m = torch.empty(n_recv, 2, **o), torch.empty(n_recv, **o), torch.empty(n_recv, 3, **o)
+        opac_m, cols_m = torch.empty(n_recv, **o), torch.empty(n_recv, ch, **o)
+        radii_m, tiles_m = torch.empty(n_recv, dtype=torch.int32, **o), torch.empty(n_recv, dtype=torch.int32, **o)
+        cam_m, gid_m = torch.empty(n_recv, dtype=torch.int64, **o), torch.empty(n_recv, dtype=torch.int64, **o)
+        with ops._stage("route_split"):
+            L.check(lib.b2s_split_payload(n_recv, ch, L.ptr(recv), L.ptr(means2d_m), L.ptr(depths_m), L.ptr(conics_m),
+                                          L.ptr(opac_m), L.ptr(cols_m), L.ptr(radii_m), L.ptr(tiles_m), L.ptr(cam_m),
+                                          L.ptr(gid_m), st), "b2s_split_payload")
+        ctx.save_for_backward(sel)
+        src_base = [sum(table[s][d] for d in range(rank)) for s in range(world)]   # my rows inside source s's packed list
+        ctx.cfg = (recv_counts, src_base, group, ch, (means2d.shape, depths.shape, conics.shape, opac.shape, cols.shape))
+        ctx.set_materialize_grads(False)
+        ctx.mark_non_differentiable(radii_m, tiles_m, cam_m, gid_m)
+        return means2d_m, depths_m, conics_m, opac_m, cols_m, radii_m, tiles_m, cam_m, gid_m
+
+    @staticmethod
+    def backward(ctx, g_means2d, g_depths, g_conics, g_opac, g_cols, *_):
+        from . import _lib as L
+        from . import ops
+        (sel,) = ctx.saved_tensors
+        recv_counts, src_base, group, ch, shapes = ctx.cfg
+        dev = sel.device
+        world = dist.get_world_size(group)
+        n_recv, nnz, G = int(sum(recv_counts)), sel.numel(), 7 + ch
+        buf_b, h_b = _SymmBuffers.get(group, "bwd", 0, dev)
+        lib, st = L.lib(), L.stream_ptr(dev)
+        gs = [L.f32c(g) for g in (g_means2d, g_depths, g_conics, g_opac, g_cols)]
+        with ops._stage("route_p2p_bwd"):
+            h_b.barrier()
+            L.check(lib.b2s_p2p_join(n_recv, ch, *[L.ptr(g) for g in gs], world, _i64(recv_counts), _i64(src_base),
+                                     _ptrs(h_b.buffer_ptrs), st), "b2s_p2p_join")
+            h_b.barrier()
+        outs = [torch.zeros(s, dtype=torch.float32, device=dev) for s in shapes]
+        with ops._stage("route_scatter"):
+            L.check(lib.b2s_scatter_grads(nnz, L.ptr(sel), ch, L.ptr(buf_b), *[L.ptr(o) for o in outs], st), "b2s_scatter_grads")
+        return tuple(outs) + (None,) * 5
+
+
+def _route_impl():
+    """'p2p' (default): fused pack + NVLink peer stores through symmetric memory; 'nccl': pack + all_to_all_single."""
+    import os
+    return os.environ.get("B2S_ROUTE", "p2p")
+
+
+# ----------------------------------------------------------------------------------------------------------
+# rasterization(distributed=True)
+# ----------------------------------------------------------------------------------------------------------
+def rasterization_distributed(means, quats, scales, opacities, colors, viewmats, Ks, width, height, near_plane=0.01,
+                              far_plane=1e10, radius_clip=0.0, eps2d=0.3, sh_degree=None, packed=True, backgrounds=None,
+                              render_mode="RGB", absgrad=False, rasterize_mode="classic", tile_size=16, group=None):
+    """``rasterization(..., distributed=True)``: local Gaussians [N_r,...], local cameras [C_r,...] (same C_r on
+    every rank); returns the renders of the local cameras composited from every rank's Gaussians.  ``meta`` is
+    in the packed layout (``camera_ids`` local, ``gaussian_ids`` global), as upstream."""
+    from . import ops
+    from ._lib import require_cuda
+    import math
+
+    if not dist.is_initialized():
+        raise RuntimeError("distributed=True needs an initialised torch.distributed process group")
+    if not packed:
+        raise NotImplementedError("distributed=True is implemented for packed=True (what the reference's multi-GPU branch uses)")
+    if sh_degree is not None and colors.dim() != 3:
+        raise NotImplementedError("distributed=True expects per-Gaussian SH coefficients [N,K,3]")
+    if sh_degree is None and colors.dim() != 2:
+        raise NotImplementedError("distributed=True expects per-Gaussian colours [N,D]")
+    require_cuda(means, quats, scales, opacities, colors, viewmats, Ks)
+    world = dist.get_world_size(group)
+    N, C_local = means.shape[0], viewmats.shape[0]
+    width, height = int(width), int(height)
+    tw, th = math.ceil(width / tile_size), math.ceil(height / tile_size)
+
+    viewmats_all, Ks_all, n_world = all_gather_cameras(viewmats, Ks, N, group)
+    C_all = viewmats_all.shape[0]
+    if C_all != C_local * world:
+        raise ValueError("every rank must hold the same number of cameras")
+
+    # ---- local shard projected into every camera (one kernel; SH coefficients read once) ----------------------
+    antialiased = rasterize_mode == "antialiased"
+    fused_sh = sh_degree is not None
+    radii, means2d, depths, conics, _comps, opac, sh_cols, tiles, _dk, _ri, _tot = ops._ProjectFused.apply(
+        means, quats, scales, opacities, colors if fused_sh else None, viewmats_all, Ks_all, None, width, height,
+        float(eps2d), float(near_plane), float(far_plane), float(radius_clip), antialiased, False,
+        int(sh_degree) if fused_sh else 0, tile_size)
+    cols = sh_cols if fused_sh else colors[None].expand(C_all, N, colors.shape[-1])
+    if render_mode in ("RGB+D", "RGB+ED"):
+        cols = torch.cat([cols, depths[..., None]], dim=-1)
+        if backgrounds is not None:
+            backgrounds = torch.cat([backgrounds, torch.zeros_like(backgrounds[:, :1])], dim=-1)
+    elif render_mode in ("D", "ED"):
+        cols = depths[..., None]
+        if backgrounds is not None:
+            backgrounds = torch.zeros_like(backgrounds[:, :1])
+    ch = cols.shape[-1]
+
+    # ---- route the visible pairs to the camera owners: pack -> one all-to-all -> split --------------------------
+    (means2d_m, depths_m, conics_m, opac_m, cols_m, radii_m, tiles_m, cam_local,
+     gauss_global) = (_RouteSplatsP2P if _route_impl() == "p2p" and world <= 16 else _RouteSplatsCUDA).apply(
+        means2d, depths, conics, opac, cols, radii, tiles, C_local, n_world, group)
+
+    # ---- own cameras: binning + compositing -------------------------------------------------------------------
+    flatten_ids, isect_offsets, make_isect_ids = ops.bin_depth_first(
+        means2d_m, radii_m, depths_m, tiles_m, tile_size, tw, th, C_local, camera_ids=cam_local)
+    render_colors, render_alphas = ops.rasterize_to_pixels(
+        means2d_m, conics_m, cols_m, opac_m, width, height, tile_size, isect_offsets, flatten_ids,
+        backgrounds=backgrounds, packed=True, absgrad=absgrad)
+    if render_mode in ("ED", "RGB+ED"):
+        render_colors = torch.cat(
+            [render_colors[..., :-1], render_colors[..., -1:] / render_alphas.clamp(min=1e-10)], dim=-1)
+    meta = ops.LazyMeta({
+        "camera_ids": cam_local, "gaussian_ids": gauss_global, "radii": radii_m, "means2d": means2d_m,
+        "depths": depths_m, "conics": conics_m, "opacities": opac_m, "tile_width": tw, "tile_height": th,
+        "tiles_per_gauss": tiles_m, "flatten_ids": flatten_ids, "isect_offsets": isect_offsets, "width": width,
+        "height": height, "tile_size": tile_size, "n_cameras": C_local,
+    })
+    meta.set_lazy("isect_ids", make_isect_ids)
+    return render_colors, render_alphas, meta

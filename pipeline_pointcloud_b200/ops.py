@@ -215,6 +215,62 @@ def fully_fused_projection(
             conics.reshape(-1, 3)[sel], comps.reshape(-1)[sel] if comps is not None else None)
 
 
+class _PackVisible(torch.autograd.Function):
+    """Dense stage-1 outputs -> packed rows (camera-major, Gaussian-ascending); backward scatters into zeros."""
+
+    @staticmethod
+    def forward(ctx, sel, N, means2d, depths, conics, opacities, colors, radii, tiles):
+        dev = means2d.device
+        nnz, ch = sel.numel(), colors.shape[-1]
+        means2d, depths, conics, opacities, colors = f32c(means2d), f32c(depths), f32c(conics), f32c(opacities), f32c(colors)
+        o = dict(device=dev)
+        means2d_p = torch.empty(nnz, 2, **o)
+        depths_p = torch.empty(nnz, **o)
+        conics_p = torch.empty(nnz, 3, **o)
+        opac_p = torch.empty(nnz, **o)
+        colors_p = torch.empty(nnz, ch, **o)
+        radii_p = torch.empty(nnz, dtype=torch.int32, **o)
+        tiles_p = torch.empty(nnz, dtype=torch.int32, **o) if tiles is not None else None
+        cam = torch.empty(nnz, dtype=torch.int64, **o)
+        gid = torch.empty(nnz, dtype=torch.int64, **o)
+        with _stage("pack_rows"):
+            check(L.lib().b2s_pack_rows(nnz, N, ptr(sel), ch, ptr(means2d), ptr(depths), ptr(conics), ptr(opacities),
+                                        ptr(colors), ptr(radii), ptr(tiles), ptr(means2d_p), ptr(depths_p), ptr(conics_p),
+                                        ptr(opac_p), ptr(colors_p), ptr(radii_p), ptr(tiles_p), ptr(cam), ptr(gid),
+                                        L.stream_ptr(dev)), "b2s_pack_rows")
+        ctx.save_for_backward(sel)
+        ctx.shapes = (means2d.shape, depths.shape, conics.shape, opacities.shape, colors.shape)
+        ctx.set_materialize_grads(False)
+        ctx.mark_non_differentiable(radii_p, cam, gid)
+        if tiles_p is not None:
+            ctx.mark_non_differentiable(tiles_p)
+        return means2d_p, depths_p, conics_p, opac_p, colors_p, radii_p, tiles_p, cam, gid
+
+    @staticmethod
+    def backward(ctx, g_means2d, g_depths, g_conics, g_opac, g_colors, *_):
+        (sel,) = ctx.saved_tensors
+        dev = sel.device
+        shapes = ctx.shapes
+        gs = [f32c(g) for g in (g_means2d, g_depths, g_conics, g_opac, g_colors)]
+        outs = [torch.zeros(s, dtype=torch.float32, device=dev) if g is not None else None for s, g in zip(shapes, gs)]
+        ch = shapes[4][-1]
+        with _stage("unpack_rows"):
+            check(L.lib().b2s_unpack_rows(sel.numel(), ptr(sel), ch, *[ptr(g) for g in gs], *[ptr(o) for o in outs],
+                                          L.stream_ptr(dev)), "b2s_unpack_rows")
+        return (None, None) + tuple(outs) + (None, None)
+
+
+def pack_visible(radii: Tensor, means2d: Tensor, depths: Tensor, conics: Tensor, opacities: Tensor, colors: Tensor,
+                 tiles: Optional[Tensor] = None):
+    """Packed layout of the visible (camera, Gaussian) pairs of dense ``[C,N,..]`` tensors.
+    Returns (camera_ids, gaussian_ids, radii, means2d, depths, conics, opacities, colors, tiles)."""
+    N = radii.shape[1]
+    sel = (radii.reshape(-1) > 0).nonzero(as_tuple=True)[0]
+    m2, d, c, o, col, r, t, cam, gid = _PackVisible.apply(sel, N, means2d, depths, conics, opacities, colors,
+                                                          radii.contiguous(), tiles.contiguous() if tiles is not None else None)
+    return cam, gid, r, m2, d, c, o, col, t
+
+
 # ======================================================================================
 # stand-alone SH / covariance ops
 # ======================================================================================

@@ -122,15 +122,8 @@ def rasterization(
     # ---- packed layout: compact the visible pairs (camera-major, Gaussian-ascending) ----------------------
     camera_ids = gaussian_ids = None
     if packed:
-        sel = (radii.reshape(-1) > 0).nonzero(as_tuple=True)[0]
-        camera_ids, gaussian_ids = sel // N, sel % N
-        radii_m = radii.reshape(-1)[sel]
-        means2d_m = means2d.reshape(-1, 2)[sel]
-        depths_m = depths.reshape(-1)[sel]
-        conics_m = conics.reshape(-1, 3)[sel]
-        opac_m = opac.reshape(-1)[sel]
-        cols_m = cols.reshape(-1, cols.shape[-1])[sel]
-        tiles_m = tiles.reshape(-1)[sel]
+        (camera_ids, gaussian_ids, radii_m, means2d_m, depths_m, conics_m, opac_m, cols_m,
+         tiles_m) = ops.pack_visible(radii, means2d, depths, conics, opac, cols, tiles)
     else:
         radii_m, means2d_m, depths_m, conics_m, opac_m, cols_m, tiles_m = radii, means2d, depths, conics, opac, cols, tiles
 
