@@ -3,10 +3,13 @@
 // Replaces gsplat `isect_tiles` (two launches + cumsum), the CUB radix sort it calls, and
 // `isect_offset_encode`.  Integer work: every output is bit-exact
 // against oracle/torch_oracle.py::isect_tiles / isect_offset_encode.
-#include <cub/device/device_radix_sort.cuh>
-
 #include "b2s_math.cuh"
 #include "common.cuh"
+#include "radix.cuh"
+
+#ifdef B2S_SORT_CUB   // A/B switch: build with -DB2S_SORT_CUB to route the sorts through cub::DeviceRadixSort
+#include <cub/device/device_radix_sort.cuh>
+#endif
 
 namespace b2s {
 
@@ -47,10 +50,7 @@ __device__ __forceinline__ unsigned long long lookback_warp(volatile unsigned lo
         if (lane == 0) st[0] = FLAG_INC | block_sum;
         return 0ull;
     }
-    if (lane == 0) {
-        st[tile] = FLAG_AGG | block_sum;
-        __threadfence();
-    }
+    if (lane == 0) st[tile] = FLAG_AGG | block_sum;   // flag and value travel in one word: no fence needed
     unsigned long long excl = 0ull;
     long long base = (long long)tile - 1;
     while (true) {
@@ -302,14 +302,31 @@ __global__ void isect_ids_kernel(int64_t n, const KeyT* __restrict__ tile_keys, 
 
 static size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
 
+// scratch bytes of one (key, int32) pair sort, and the sort itself: the hand-written onesweep of radix.cuh
 template <typename KeyT>
 static size_t cub_pairs_bytes(int64_t n) {
+#ifdef B2S_SORT_CUB
     size_t bytes = 0;
     cub::DeviceRadixSort::SortPairs(nullptr, bytes, (const KeyT*)nullptr, (KeyT*)nullptr, (const int32_t*)nullptr,
                                     (int32_t*)nullptr, n > 0 ? n : 1, 0, (int)sizeof(KeyT) * 8, (cudaStream_t)0);
     return bytes;
+#else
+    return radix::workspace_bytes<KeyT>(n > 0 ? n : 1);
+#endif
 }
 static size_t cub_pairs32_bytes(int64_t n) { return cub_pairs_bytes<uint32_t>(n); }
+
+template <typename KeyT>
+static int sort_pairs(void* tmp, size_t tmp_bytes, const KeyT* keys_in, KeyT* keys_out, const int32_t* vals_in,
+                      int32_t* vals_out, int64_t n, int end_bit, cudaStream_t st) {
+#ifdef B2S_SORT_CUB
+    B2S_CUDA(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, keys_in, keys_out, vals_in, vals_out, n, 0, end_bit, st));
+    return 0;
+#else
+    (void)tmp_bytes;
+    return radix::sort_pairs<KeyT>(n, end_bit, keys_in, vals_in, keys_out, vals_out, tmp, st);
+#endif
+}
 
 static int bit_length(int64_t v) {
     int b = 0;
@@ -376,11 +393,8 @@ extern "C" int b2s_isect_fill(int64_t M, int64_t N, const int64_t* camera_ids, c
 }
 
 extern "C" int64_t b2s_isect_sort_workspace_bytes(int64_t n) {
-    if (n <= 0) return 16;
-    size_t bytes = 0;
-    cub::DeviceRadixSort::SortPairs(nullptr, bytes, (const uint64_t*)nullptr, (uint64_t*)nullptr, (const int32_t*)nullptr,
-                                    (int32_t*)nullptr, n, 0, 64, (cudaStream_t)0);
-    return (int64_t)bytes + 16;
+    if (n <= 0) return 256;
+    return (int64_t)cub_pairs_bytes<uint64_t>(n) + 256;
 }
 
 extern "C" int b2s_isect_sort(int64_t n, int32_t key_bits, const int64_t* keys_in, const int32_t* vals_in, int64_t* keys_out,
@@ -388,11 +402,13 @@ extern "C" int b2s_isect_sort(int64_t n, int32_t key_bits, const int64_t* keys_i
     B2S_REQUIRE(n >= 0 && key_bits > 0 && key_bits <= 64, "bad sizes");
     if (n == 0) return 0;
     B2S_REQUIRE(keys_in && vals_in && keys_out && vals_out && workspace, "null pointer");
-    size_t bytes = (size_t)workspace_bytes;
-    B2S_CUDA(cub::DeviceRadixSort::SortPairs(workspace, bytes, reinterpret_cast<const uint64_t*>(keys_in),
-                                             reinterpret_cast<uint64_t*>(keys_out), vals_in, vals_out, n, 0, key_bits,
-                                             (cudaStream_t)stream));
-    return 0;
+    if (workspace_bytes < b2s_isect_sort_workspace_bytes(n)) {
+        set_error("b2s_isect_sort: workspace too small");
+        return B2S_E_WORKSPACE;
+    }
+    void* w = reinterpret_cast<void*>((reinterpret_cast<uintptr_t>(workspace) + 255) & ~(uintptr_t)255);
+    return sort_pairs<uint64_t>(w, (size_t)workspace_bytes - 256, reinterpret_cast<const uint64_t*>(keys_in),
+                                reinterpret_cast<uint64_t*>(keys_out), vals_in, vals_out, n, key_bits, (cudaStream_t)stream);
 }
 
 extern "C" int b2s_isect_offsets(int64_t n, const int64_t* keys, int32_t C, int32_t tile_w, int32_t tile_h,
@@ -445,8 +461,7 @@ extern "C" int b2s_depth_order(int64_t M, const uint32_t* depth_keys, const int3
     uint32_t* keys_sorted = reinterpret_cast<uint32_t*>(w);
     w += align256((size_t)M * 4);
     size_t cub_bytes = cub_pairs32_bytes(M);
-    B2S_CUDA(cub::DeviceRadixSort::SortPairs(w, cub_bytes, depth_keys, keys_sorted, row_ids, sorted_ids, M, 0, 32, st));
-    return 0;
+    return sort_pairs<uint32_t>(w, cub_bytes, depth_keys, keys_sorted, row_ids, sorted_ids, M, 32, st);
 }
 
 extern "C" int32_t b2s_tile_key_bytes(int32_t C, int32_t tile_w, int32_t tile_h) {
@@ -484,8 +499,11 @@ static int tile_bin_impl(int64_t M, int64_t N, const int64_t* camera_ids, int64_
         M, N, camera_ids, sorted_ids, reinterpret_cast<const float2*>(means2d), radii, (float)tile_size, tile_w, tile_h,
         tile_bits, status, counter, keys_u, vals_u);
     B2S_LAUNCH_CHECK();
-    B2S_CUDA(cub::DeviceRadixSort::SortPairs(cub_tmp, cub_bytes, keys_u, reinterpret_cast<KeyT*>(tile_keys_sorted), vals_u,
-                                             flatten_ids, n_isects, 0, key_bits, st));
+    {
+        int rc = sort_pairs<KeyT>(cub_tmp, cub_bytes, keys_u, reinterpret_cast<KeyT*>(tile_keys_sorted), vals_u, flatten_ids,
+                                  n_isects, key_bits, st);
+        if (rc != 0) return rc;
+    }
     offsets_search_kernel<KeyT><<<(unsigned)cdiv(total_tiles, 128), 128, 0, st>>>(
         n_isects, reinterpret_cast<const KeyT*>(tile_keys_sorted), n_tiles, tile_bits, total_tiles, offsets);
     B2S_LAUNCH_CHECK();

@@ -1,0 +1,329 @@
+// Hand-written stable LSD radix sort of (key, int32 value) pairs for sm_100a -- "onesweep" style:
+// one histogram kernel for all digits, then ONE kernel per 8-bit digit that ranks, looks back and
+// scatters in a single pass over the data (read 1x, write 1x per digit).
+//
+// Per digit pass, a CTA owns a tile of 256 threads x ITEMS consecutive elements:
+//   1. warp-striped coalesced load; each warp owns a contiguous slice, so (warp, item, lane) order is
+//      memory order and ranking in that order keeps the sort stable;
+//   2. per-warp ranking with `__match_any_sync`: lanes holding the same digit find each other, the group
+//      leader bumps the warp's digit counter in shared memory, rank = counter + popc(lower peers);
+//   3. per-digit exclusive scan across the 8 warps (thread d <-> digit d);
+//   4. decoupled look-back across tiles, one thread per digit (256 chains in parallel, coalesced status rows),
+//      tile ids handed out dynamically so predecessors are always resident;
+//   5. local reorder through shared memory so the global scatter writes runs of equal digits contiguously.
+// Replaces cub::DeviceRadixSort on the training path (depth sort of Gaussians, (camera,tile) split of the
+// intersections) and in the reference-algorithm path (64-bit isect keys).
+#pragma once
+#include "common.cuh"
+
+namespace b2s {
+namespace radix {
+
+constexpr int RADIX_BITS = 8;
+constexpr int RADIX = 1 << RADIX_BITS;
+constexpr int THREADS = 256;
+constexpr int WARPS = THREADS / 32;
+constexpr unsigned long long R_FLAG_AGG = 1ull << 62, R_FLAG_INC = 2ull << 62, R_VAL_MASK = (1ull << 62) - 1;
+
+template <typename KeyT> struct Cfg { static constexpr int ITEMS = 16; };
+template <> struct Cfg<uint64_t> { static constexpr int ITEMS = 8; };
+
+template <typename KeyT>
+__device__ __forceinline__ unsigned digit_of(KeyT k, int shift, unsigned mask = RADIX - 1) {
+    return (unsigned)(k >> shift) & mask;
+}
+
+// Digit widths: the key bits are split evenly over the passes (14 bits -> 7 + 7 rather than 8 + 6), which
+// doubles the length of the runs the 8-bit pass would scatter and keeps both passes equally cheap.
+struct Plan {
+    int passes;
+    int shift[8];
+    int bits[8];
+};
+static inline Plan make_plan(int key_bits) {
+    Plan pl;
+    pl.passes = (key_bits + RADIX_BITS - 1) / RADIX_BITS;
+    int done = 0;
+    for (int p = 0; p < pl.passes; ++p) {
+        int b = (key_bits - done + (pl.passes - p) - 1) / (pl.passes - p);
+        pl.shift[p] = done;
+        pl.bits[p] = b;
+        done += b;
+    }
+    return pl;
+}
+
+// ---- histogram of every digit position in one pass over the keys ------------------------------------------
+template <typename KeyT, int MAX_PASSES>
+__global__ void __launch_bounds__(THREADS) hist_kernel(int64_t n, const KeyT* __restrict__ keys, const Plan pl,
+                                                       unsigned long long* __restrict__ hist /* [passes][256] */) {
+    const int passes = pl.passes;
+    __shared__ unsigned s_hist[MAX_PASSES * RADIX];
+    for (int i = threadIdx.x; i < passes * RADIX; i += THREADS) s_hist[i] = 0;
+    __syncthreads();
+    for (int64_t i = (int64_t)blockIdx.x * THREADS + threadIdx.x; i < n; i += (int64_t)gridDim.x * THREADS) {
+        const KeyT k = keys[i];
+#pragma unroll
+        for (int p = 0; p < MAX_PASSES; ++p)
+            if (p < passes) atomicAdd(&s_hist[p * RADIX + digit_of(k, pl.shift[p], (1u << pl.bits[p]) - 1u)], 1u);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < passes * RADIX; i += THREADS)
+        if (s_hist[i]) atomicAdd(&hist[i], (unsigned long long)s_hist[i]);
+}
+
+// exclusive scan of each 256-bin histogram (one CTA per pass)
+__global__ void __launch_bounds__(RADIX) scan_hist_kernel(unsigned long long* __restrict__ hist) {
+    __shared__ unsigned long long s[RADIX];
+    unsigned long long* h = hist + (size_t)blockIdx.x * RADIX;
+    const unsigned long long v = h[threadIdx.x];
+    s[threadIdx.x] = v;
+    __syncthreads();
+    for (int d = 1; d < RADIX; d <<= 1) {
+        unsigned long long t = threadIdx.x >= d ? s[threadIdx.x - d] : 0ull;
+        __syncthreads();
+        s[threadIdx.x] += t;
+        __syncthreads();
+    }
+    h[threadIdx.x] = s[threadIdx.x] - v;
+}
+
+// ---- one digit pass ---------------------------------------------------------------------------------------
+// The kernel is issue-bound, so everything is kept in 32 bits: indices (n < 2^31 enforced by the host driver) and
+// the look-back status words (StatusT = uint32 with a 30-bit value when n < 2^30, else uint64).
+template <typename StatusT> struct St;
+template <> struct St<unsigned> {
+    static constexpr int SHIFT = 30;
+    static constexpr unsigned MASK = (1u << 30) - 1u;
+};
+template <> struct St<unsigned long long> {
+    static constexpr int SHIFT = 62;
+    static constexpr unsigned long long MASK = (1ull << 62) - 1ull;
+};
+
+template <typename KeyT, typename StatusT>
+__global__ void __launch_bounds__(THREADS, 3) onesweep_kernel(unsigned n, const KeyT* __restrict__ keys_in,
+                                                              const int32_t* __restrict__ vals_in, KeyT* __restrict__ keys_out,
+                                                              int32_t* __restrict__ vals_out, int shift, unsigned mask,
+                                                              const unsigned long long* __restrict__ digit_base /* [256] */,
+                                                              StatusT* status /* [tiles][256] */, unsigned int* tile_counter) {
+    constexpr int ITEMS = Cfg<KeyT>::ITEMS;
+    constexpr unsigned TILE = THREADS * ITEMS;
+    constexpr int HS = RADIX + 1;                        // +1: dump bin for the out-of-range lanes of the last tile
+    __shared__ unsigned s_warp_hist[WARPS * HS];         // per-warp digit counters -> exclusive prefix across warps
+    __shared__ unsigned s_cta_start[RADIX];              // first slot of each digit inside the locally sorted tile
+    __shared__ unsigned s_off[RADIX];                    // (global position of the digit's first element) - cta_start
+    __shared__ KeyT s_keys[TILE];
+    __shared__ int32_t s_vals[TILE];
+    __shared__ unsigned s_wsum[WARPS];
+    __shared__ unsigned int s_tile;
+
+    if (threadIdx.x == 0) s_tile = atomicAdd(tile_counter, 1u);
+    for (int i = threadIdx.x; i < WARPS * HS; i += THREADS) s_warp_hist[i] = 0;
+    __syncthreads();
+    const unsigned tile = s_tile;
+    const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned tile_base = tile * TILE;
+    const unsigned warp_base = tile_base + warp * 32 * ITEMS + lane;
+    const bool full = tile_base + TILE <= n;
+    const unsigned tile_count = full ? TILE : n - tile_base;
+
+    KeyT key[ITEMS];
+    int32_t val[ITEMS];
+    unsigned dig[ITEMS];
+    if (full) {
+#pragma unroll
+        for (int i = 0; i < ITEMS; ++i) key[i] = keys_in[warp_base + i * 32];
+#pragma unroll
+        for (int i = 0; i < ITEMS; ++i) val[i] = vals_in[warp_base + i * 32];
+#pragma unroll
+        for (int i = 0; i < ITEMS; ++i) dig[i] = digit_of(key[i], shift, mask);
+    } else {
+#pragma unroll
+        for (int i = 0; i < ITEMS; ++i) {
+            const unsigned g = warp_base + i * 32;
+            const bool ok = g < n;
+            key[i] = ok ? keys_in[g] : (KeyT)0;
+            val[i] = ok ? vals_in[g] : 0;
+            dig[i] = ok ? digit_of(key[i], shift, mask) : (unsigned)RADIX;   // out-of-range lanes share the dump bin
+        }
+    }
+    // 2. rank inside the warp, in memory order.  All MATCH instructions are issued first (independent); then, item
+    // by item, every lane reads its digit's counter (a broadcast within the group) and the group leader bumps it.
+    unsigned peers[ITEMS];
+#pragma unroll
+    for (int i = 0; i < ITEMS; ++i) peers[i] = __match_any_sync(FULL, dig[i]);
+    unsigned* my_hist = s_warp_hist + warp * HS;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    unsigned rank[ITEMS];
+#pragma unroll
+    for (int i = 0; i < ITEMS; ++i) {
+        const unsigned pre = my_hist[dig[i]];
+        __syncwarp();
+        if (lane == __ffs(peers[i]) - 1) my_hist[dig[i]] = pre + __popc(peers[i]);
+        rank[i] = pre + __popc(peers[i] & lt_mask);
+        __syncwarp();
+    }
+    __syncthreads();
+    // 3. thread d <-> digit d: exclusive prefix across warps, tile total
+    const unsigned d = threadIdx.x;
+    unsigned cnt = 0;
+#pragma unroll
+    for (int w = 0; w < WARPS; ++w) {
+        const unsigned t = s_warp_hist[w * HS + d];
+        s_warp_hist[w * HS + d] = cnt;
+        cnt += t;
+    }
+    // 4. look-back for digit d (the status word carries flag and value together: no fence needed)
+    unsigned long long excl = 0;
+    {
+        constexpr int SH = St<StatusT>::SHIFT;
+        volatile StatusT* st = status;
+        if (tile == 0) {
+            st[d] = ((StatusT)2 << SH) | (StatusT)cnt;
+        } else {
+            st[tile * RADIX + d] = ((StatusT)1 << SH) | (StatusT)cnt;
+            // Walk back LB tiles at a time: the LB status loads are independent, so a window of LB tiles costs
+            // one L2 round trip instead of LB.
+            constexpr int LB = 8;
+            int k = (int)tile - 1;
+            while (true) {
+                StatusT sv[LB];
+#pragma unroll
+                for (int u = 0; u < LB; ++u) sv[u] = (k - u >= 0) ? st[(unsigned)(k - u) * RADIX + d] : ((StatusT)2 << SH);
+                unsigned ready = 0, inc = 0;
+#pragma unroll
+                for (int u = 0; u < LB; ++u) {
+                    const unsigned f = (unsigned)(sv[u] >> SH);
+                    ready |= (f != 0u) << u;
+                    inc |= (f == 2u) << u;
+                }
+                const int first_wait = __ffs(~ready) - 1;                       // LB.. when all are published
+                const int first_inc = inc ? __ffs(inc) - 1 : LB;
+                const int usable = min(first_wait, first_inc + 1);              // tiles [k, k-usable) can be consumed
+#pragma unroll
+                for (int u = 0; u < LB; ++u)
+                    if (u < usable) excl += (unsigned long long)(sv[u] & St<StatusT>::MASK);
+                if (first_inc < usable) break;
+                k -= usable;
+            }
+            st[tile * RADIX + d] = ((StatusT)2 << SH) | (StatusT)(excl + cnt);
+        }
+    }
+    // exclusive scan of the tile's digit counts (256 values, one per thread)
+    {
+        unsigned incl = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            unsigned t = __shfl_up_sync(FULL, incl, o);
+            if (lane >= o) incl += t;
+        }
+        if (lane == 31) s_wsum[warp] = incl;
+        __syncthreads();
+        unsigned woff = 0;
+#pragma unroll
+        for (int w = 0; w < WARPS; ++w)
+            if (w < (int)warp) woff += s_wsum[w];
+        const unsigned start = woff + incl - cnt;
+        s_cta_start[d] = start;
+        s_off[d] = (unsigned)(digit_base[d] + excl) - start;
+    }
+    __syncthreads();
+    // 5. local reorder, then coalesced scatter
+#pragma unroll
+    for (int i = 0; i < ITEMS; ++i) {
+        if (full || dig[i] < RADIX) {
+            const unsigned p = s_cta_start[dig[i]] + s_warp_hist[warp * HS + dig[i]] + rank[i];
+            s_keys[p] = key[i];
+            s_vals[p] = val[i];
+        }
+    }
+    __syncthreads();
+#pragma unroll 4
+    for (unsigned p = threadIdx.x; p < tile_count; p += THREADS) {
+        const KeyT k = s_keys[p];
+        const unsigned pos = s_off[digit_of(k, shift, mask)] + p;
+        keys_out[pos] = k;
+        vals_out[pos] = s_vals[p];
+    }
+}
+
+// ---- host driver --------------------------------------------------------------------------------------------
+template <typename KeyT>
+static inline int64_t tiles_of(int64_t n) { return cdiv(n > 0 ? n : 1, (int64_t)THREADS * Cfg<KeyT>::ITEMS); }
+
+static inline size_t up256(size_t v) { return (v + 255) & ~(size_t)255; }
+
+template <typename KeyT>
+static inline int passes_of(int key_bits) { return (key_bits + RADIX_BITS - 1) / RADIX_BITS; }
+
+// workspace: 2 temp key buffers + 2 temp value buffers + histograms + status + tile counters
+template <typename KeyT>
+static inline size_t workspace_bytes(int64_t n) {
+    const int max_passes = (int)sizeof(KeyT);
+    return 2 * up256((size_t)n * sizeof(KeyT)) + 2 * up256((size_t)n * 4) + up256((size_t)max_passes * RADIX * 8) +
+           up256((size_t)tiles_of<KeyT>(n) * RADIX * 8) + up256((size_t)max_passes * 4);
+}
+
+// Sorts bits [0, key_bits) ascending, stable.  keys_in/vals_in are not modified; result in keys_out/vals_out.
+template <typename KeyT>
+static int sort_pairs(int64_t n, int key_bits, const KeyT* keys_in, const int32_t* vals_in, KeyT* keys_out, int32_t* vals_out,
+                      void* workspace, cudaStream_t st) {
+    if (n <= 0) return 0;
+    if (n >= 2147483647LL) {
+        set_error("radix::sort_pairs: n must be < 2^31");
+        return B2S_E_BADARG;
+    }
+    constexpr int MAXP = (int)sizeof(KeyT);
+    const Plan pl = make_plan(key_bits);
+    const int passes = pl.passes;
+    if (passes < 1 || passes > MAXP) {
+        set_error("radix::sort_pairs: key_bits out of range");
+        return B2S_E_BADARG;
+    }
+    char* w = reinterpret_cast<char*>(workspace);
+    KeyT* tk[2];
+    int32_t* tv[2];
+    tk[0] = reinterpret_cast<KeyT*>(w); w += up256((size_t)n * sizeof(KeyT));
+    tk[1] = reinterpret_cast<KeyT*>(w); w += up256((size_t)n * sizeof(KeyT));
+    tv[0] = reinterpret_cast<int32_t*>(w); w += up256((size_t)n * 4);
+    tv[1] = reinterpret_cast<int32_t*>(w); w += up256((size_t)n * 4);
+    unsigned long long* hist = reinterpret_cast<unsigned long long*>(w); w += up256((size_t)MAXP * RADIX * 8);
+    unsigned long long* status = reinterpret_cast<unsigned long long*>(w);
+    const int64_t tiles = tiles_of<KeyT>(n);
+    w += up256((size_t)tiles * RADIX * 8);
+    unsigned int* counters = reinterpret_cast<unsigned int*>(w);
+
+    B2S_CUDA(cudaMemsetAsync(hist, 0, (size_t)MAXP * RADIX * 8, st));
+    B2S_CUDA(cudaMemsetAsync(counters, 0, (size_t)MAXP * 4, st));
+    const int hist_grid = (int)min((int64_t)148 * 8, cdiv(n, THREADS));
+    hist_kernel<KeyT, MAXP><<<hist_grid, THREADS, 0, st>>>(n, keys_in, pl, hist);
+    B2S_LAUNCH_CHECK();
+    scan_hist_kernel<<<passes, RADIX, 0, st>>>(hist);
+    B2S_LAUNCH_CHECK();
+    const KeyT* src_k = keys_in;
+    const int32_t* src_v = vals_in;
+    for (int p = 0; p < passes; ++p) {
+        const bool last = (p == passes - 1);
+        KeyT* dst_k = last ? keys_out : tk[p & 1];
+        int32_t* dst_v = last ? vals_out : tv[p & 1];
+        if (n < (1LL << 30)) {
+            B2S_CUDA(cudaMemsetAsync(status, 0, (size_t)tiles * RADIX * 4, st));
+            onesweep_kernel<KeyT, unsigned><<<(unsigned)tiles, THREADS, 0, st>>>(
+                (unsigned)n, src_k, src_v, dst_k, dst_v, pl.shift[p], (1u << pl.bits[p]) - 1u, hist + (size_t)p * RADIX,
+                reinterpret_cast<unsigned*>(status), counters + p);
+        } else {
+            B2S_CUDA(cudaMemsetAsync(status, 0, (size_t)tiles * RADIX * 8, st));
+            onesweep_kernel<KeyT, unsigned long long><<<(unsigned)tiles, THREADS, 0, st>>>(
+                (unsigned)n, src_k, src_v, dst_k, dst_v, pl.shift[p], (1u << pl.bits[p]) - 1u, hist + (size_t)p * RADIX, status,
+                counters + p);
+        }
+        B2S_LAUNCH_CHECK();
+        src_k = dst_k;
+        src_v = dst_v;
+    }
+    return 0;
+}
+
+}  // namespace radix
+}  // namespace b2s

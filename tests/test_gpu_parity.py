@@ -79,7 +79,8 @@ def test_sh_colours(b2s, deg):
 
 
 # ----------------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("C,W,H,packed", [(1, 256, 256, False), (3, 203, 117, False), (2, 160, 96, True)])
+@pytest.mark.parametrize("C,W,H,packed", [(1, 256, 256, False), (3, 203, 117, False), (2, 160, 96, True),
+                                          (8, 1297, 840, False)])   # last: camera x tile ids need 17 bits (32-bit tile keys)
 def test_binning_bit_exact(b2s, C, W, H, packed):
     N = 20000
     a = scene_args(N, 0, C, W, H, seed=3, stress=True)
