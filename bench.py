@@ -263,8 +263,6 @@ def main():
         torch.autograd.backward([r, a], [vr, va])
         if world > 1 and not sharded:
             allreduce_gradients(p.values())
-        stats["n_isects"] = m["flatten_ids"].numel()      # (not isect_ids: that would materialise the lazy 64-bit keys)
-        stats["n_visible"] = m["n_visible"] if "n_visible" in m else None
         return r, a, m
 
     def barrier():
@@ -289,6 +287,7 @@ def main():
         r, a, m = step()
     torch.cuda.synchronize()
     n_visible = int((m["radii"] > 0).sum()) if not (args.packed or sharded) else int(m["means2d"].shape[0])
+    stats["n_isects"] = int(m["tiles_per_gauss"].sum(dtype=torch.int64))   # (the per-intersection lists of meta are lazy)
 
     sampler = ClockSampler(local_rank)
     if rank == 0:

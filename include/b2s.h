@@ -40,6 +40,7 @@ extern "C" {
 #define B2S_E_BADARG (-1)
 #define B2S_E_UNSUPPORTED (-2)
 #define B2S_E_WORKSPACE (-3)
+#define B2S_TOTAL_SLOTS 32
 #define B2S_MAX_CAMERAS_PER_CALL 64 /* project_* process cameras in chunks of this size (the host loops) */
 
 typedef void* b2s_stream_t; /* cudaStream_t */
@@ -83,7 +84,8 @@ typedef struct {
     int32_t* tiles_per_gauss; /* [C,N] or NULL */
     uint32_t* depth_keys;     /* [C,N] or NULL: depth bits, 0xFFFFFFFF on culled rows (for b2s_depth_order) */
     int32_t* row_ids;         /* [C,N] or NULL: iota, c*N + n */
-    int64_t* total_isects;    /* device scalar or NULL: sum of tiles_per_gauss, ACCUMULATED (zero it first) */
+    int64_t* total_isects;    /* device int64[B2S_TOTAL_SLOTS][2] or NULL, zero it first: slot sums give
+                                 [0] sum of tiles_per_gauss, [1] visible rows (spread to avoid same-address atomics) */
 } b2s_project_fwd_args;
 B2S_API int b2s_project_fwd(const b2s_project_fwd_args* a, b2s_stream_t stream);
 
@@ -111,6 +113,8 @@ typedef struct {
     float* v_scales;    /* [N,3] */
     float* v_opacities; /* [N] or NULL */
     float* v_sh_coeffs; /* [N, sh_stride_k, 3] or NULL; rows >= (deg+1)^2 are not touched */
+    const uint8_t* touched; /* [C,N] or NULL: rows with touched == 0 are known to have zero cotangents (occluded) */
+    int32_t stages;         /* 0 = both; 1 = SH colour VJP only (v_sh_coeffs, v_means); 2 = projection VJP only */
 } b2s_project_bwd_args;
 B2S_API int b2s_project_bwd(const b2s_project_bwd_args* a, b2s_stream_t stream);
 
@@ -184,6 +188,39 @@ B2S_API int b2s_isect_ids_from_bins(int64_t n_isects, int32_t key_bytes, const v
                                     const int32_t* flatten_ids, const float* depths, int64_t* isect_ids,
                                     b2s_stream_t stream);
 
+/* Occlusion-aware chunked binning (see csrc/chunked.cu).  The depth order is processed in a few chunks;
+ * `b2s_chunk_expand` emits the (tile key, flat id) records of the rows at depth-order positions [j0, j1) into
+ * the tiles that are still open (`tile_done[t] == 0`), evaluates the SH colour of the rows that emit (lazy
+ * shading), flags them in `touched`, and leaves the record count in *n_out (device; the host reads it to size
+ * the sort).  `b2s_tile_sort` sorts the records by (camera, tile) -- stable, so depth order is kept -- and
+ * builds the per-tile offsets of this chunk.  Compositing carries pixel state between chunks
+ * (b2s_composite_*_args.chunk_index >= 0). */
+typedef struct {
+    int64_t N;                 /* Gaussians per camera (dense rows: id = c*N + n) */
+    int32_t C;
+    int64_t j0, j1;            /* depth-order positions of this chunk */
+    const int32_t* sorted_ids; /* from b2s_depth_order */
+    const float* means2d; const int32_t* radii; const float* depths;
+    int32_t tile_size, tile_w, tile_h;
+    const uint8_t* tile_done;  /* [C*tile_h*tile_w] or NULL (first chunk) */
+    /* lazy colour: SH evaluated for emitting rows when sh_coeffs != NULL; color_channels 3, or 4 (= RGB + depth) */
+    const float* means; const float* sh_coeffs; const float* viewmats;
+    int32_t sh_degree, sh_stride_k, color_channels;
+    float* colors;             /* [C*N, color_channels] or NULL */
+    uint8_t* touched;          /* [C*N] or NULL */
+    void* tile_keys;           /* [capacity] 16- or 32-bit keys (b2s_tile_key_bytes) */
+    int32_t* vals;             /* [capacity] */
+    int64_t capacity;          /* >= number of records this chunk can emit (sum of tiles_per_gauss is always enough) */
+    int64_t* n_out;            /* device scalar */
+    void* workspace; int64_t workspace_bytes;
+} b2s_chunk_expand_args;
+B2S_API int64_t b2s_chunk_expand_workspace_bytes(int64_t n_rows);
+B2S_API int b2s_chunk_expand(const b2s_chunk_expand_args* a, b2s_stream_t stream);
+B2S_API int64_t b2s_tile_sort_workspace_bytes(int64_t n);
+B2S_API int b2s_tile_sort(int64_t n, int32_t C, int32_t tile_w, int32_t tile_h, const void* tile_keys, const int32_t* vals,
+                          void* tile_keys_sorted, int32_t* flatten_ids, int32_t* offsets, void* workspace,
+                          int64_t workspace_bytes, b2s_stream_t stream);
+
 /* Packed layout (gsplat `packed=True`): gather the visible rows `sel` (ascending dense indices c*N+n) of the
  * stage-1 outputs into nnz-row tensors (+ camera_ids / gaussian_ids), and scatter gradients back into
  * zero-filled dense tensors.  Any output pointer may be NULL (skipped). */
@@ -247,7 +284,14 @@ typedef struct {
     float* render_colors;       /* [C,H,W,channels] */
     float* render_alphas;       /* [C,H,W,1] */
     int32_t* last_ids;          /* [C,H,W] index into flatten_ids of the last contributor */
-    float* final_T;             /* [C,H,W] exact final transmittance for the backward, or NULL */
+    float* final_T;             /* [C,H,W] exact final transmittance for the backward (negated on pixels that
+                                   saturated, i.e. stopped at T_next <= 1e-4), or NULL */
+    /* chunked compositing: chunk_index < 0 = one-shot (everything above).  chunk_index >= 0: this call composites
+     * chunk `chunk_index` of the depth order; pixel state is carried in render_colors (without background),
+     * final_T (signed) and last_ids (= chunk << 28 | index into this chunk's flatten_ids); chunk 0 initialises it.
+     * tile_done[t] is set once all pixels of tile t have saturated, and such tiles are skipped afterwards. */
+    int32_t chunk_index;
+    uint8_t* tile_done;         /* [C*tile_h*tile_w], required when chunk_index >= 0 */
 } b2s_composite_fwd_args;
 B2S_API int b2s_composite_fwd(const b2s_composite_fwd_args* a, b2s_stream_t stream);
 
@@ -267,6 +311,10 @@ typedef struct {
     float* v_conics;      /* [M,3] */
     float* v_colors;      /* [M,channels] */
     float* v_opacities;   /* [M] */
+    /* chunked: call once per chunk, last chunk first.  state_T [C,H,W] (initialised by the caller to |final_T|) and
+     * state_S [C,H,W,channels] (zeros) carry the running transmittance / accumulated colour between the calls. */
+    int32_t chunk_index;  /* < 0: one-shot */
+    float* state_T; float* state_S;
 } b2s_composite_bwd_args;
 B2S_API int b2s_composite_bwd(const b2s_composite_bwd_args* a, b2s_stream_t stream);
 

@@ -49,6 +49,21 @@ struct Camera {
     float campos[3];                       // camera centre in world coords (for SH view dirs)
 };
 
+// camera centre = translation column of inverse(viewmat) = -A^-1 t for the affine [A | t]
+// (cofactor inverse, so a non-orthonormal A is handled like torch.linalg.inv does)
+B2S_HD void campos_from_viewmat(const float* V, float out[3]) {
+    const float R[9] = {V[0], V[1], V[2], V[4], V[5], V[6], V[8], V[9], V[10]};
+    const float t[3] = {V[3], V[7], V[11]};
+    float c00 = R[4] * R[8] - R[5] * R[7], c01 = R[2] * R[7] - R[1] * R[8], c02 = R[1] * R[5] - R[2] * R[4];
+    float c10 = R[5] * R[6] - R[3] * R[8], c11 = R[0] * R[8] - R[2] * R[6], c12 = R[2] * R[3] - R[0] * R[5];
+    float c20 = R[3] * R[7] - R[4] * R[6], c21 = R[1] * R[6] - R[0] * R[7], c22 = R[0] * R[4] - R[1] * R[3];
+    float det = R[0] * c00 + R[1] * c10 + R[2] * c20;
+    float id = 1.f / det;
+    out[0] = -(c00 * t[0] + c01 * t[1] + c02 * t[2]) * id;
+    out[1] = -(c10 * t[0] + c11 * t[1] + c12 * t[2]) * id;
+    out[2] = -(c20 * t[0] + c21 * t[1] + c22 * t[2]) * id;
+}
+
 // viewmat: 16 floats row-major [4,4]; K: 9 floats row-major [3,3]
 B2S_HD void camera_setup(Camera& c, const float* viewmat, const float* K, const float* campos, float W, float H) {
     c.R[0] = viewmat[0]; c.R[1] = viewmat[1]; c.R[2] = viewmat[2];  c.t[0] = viewmat[3];
@@ -62,19 +77,7 @@ B2S_HD void camera_setup(Camera& c, const float* viewmat, const float* K, const 
     c.lim_yp = RN_ADD(RN_DIV(RN_SUB(H, c.cy), c.fy), RN_MUL(0.3f, tan_fovy));
     c.lim_yn = RN_ADD(RN_DIV(c.cy, c.fy), RN_MUL(0.3f, tan_fovy));
     if (campos) { c.campos[0] = campos[0]; c.campos[1] = campos[1]; c.campos[2] = campos[2]; }
-    else {
-        // camera centre = translation column of inverse(viewmat) = -A^-1 t for the affine [A | t]
-        // (cofactor inverse, so a non-orthonormal A is handled like torch.linalg.inv does)
-        const float* R = c.R;
-        float c00 = R[4] * R[8] - R[5] * R[7], c01 = R[2] * R[7] - R[1] * R[8], c02 = R[1] * R[5] - R[2] * R[4];
-        float c10 = R[5] * R[6] - R[3] * R[8], c11 = R[0] * R[8] - R[2] * R[6], c12 = R[2] * R[3] - R[0] * R[5];
-        float c20 = R[3] * R[7] - R[4] * R[6], c21 = R[1] * R[6] - R[0] * R[7], c22 = R[0] * R[4] - R[1] * R[3];
-        float det = R[0] * c00 + R[1] * c10 + R[2] * c20;
-        float id = 1.f / det;
-        c.campos[0] = -(c00 * c.t[0] + c01 * c.t[1] + c02 * c.t[2]) * id;
-        c.campos[1] = -(c10 * c.t[0] + c11 * c.t[1] + c12 * c.t[2]) * id;
-        c.campos[2] = -(c20 * c.t[0] + c21 * c.t[1] + c22 * c.t[2]) * id;
-    }
+    else campos_from_viewmat(viewmat, c.campos);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -84,6 +84,8 @@ __global__ void __launch_bounds__(CTA) composite_fwd_kernel(const b2s_composite_
     const int lo = a.isect_offsets[tile_id];
     const int hi = (tile_id == n_tiles_total - 1) ? (int)a.n_isects : a.isect_offsets[tile_id + 1];
     const int nb = (hi - lo + CTA - 1) / CTA;
+    const bool chunked = a.chunk_index >= 0;
+    if (chunked && a.chunk_index > 0 && (hi <= lo || a.tile_done[tile_id])) return;   // state of this tile is unchanged
 
     float T = 1.f;
     float acc[CH];
@@ -91,6 +93,16 @@ __global__ void __launch_bounds__(CTA) composite_fwd_kernel(const b2s_composite_
     for (int k = 0; k < CH; ++k) acc[k] = 0.f;
     int last = 0;
     bool done = !pm.inside;
+    const int64_t pix0 = ((int64_t)cam * a.height + pm.py) * a.width + pm.px;
+    if (chunked && a.chunk_index > 0 && pm.inside) {       // resume from the state the previous chunks left
+        const float Ts = final_T[pix0];
+        done = Ts < 0.f;
+        T = fabsf(Ts);
+#pragma unroll
+        for (int k = 0; k < CH; ++k) acc[k] = a.render_colors[pix0 * CH + k];
+        last = a.last_ids[pix0];
+    }
+    const int last_tag = chunked ? (a.chunk_index << 28) : 0;
 
     for (int b = 0; b < nb; ++b) {
         if (__syncthreads_count(done) == CTA) break;  // also fences the previous batch's smem reads
@@ -123,17 +135,21 @@ __global__ void __launch_bounds__(CTA) composite_fwd_kernel(const b2s_composite_
 #pragma unroll
             for (int k = 0; k < CH; ++k) acc[k] = fmaf(w, s_col[j * CH + k], acc[k]);
             T = nT;
-            last = start + j;
+            last = last_tag | (start + j);
         }
+    }
+    if (chunked) {
+        const int n_done = __syncthreads_count(done);
+        if (threadIdx.x == 0 && n_done == CTA) a.tile_done[tile_id] = 1;
     }
     if (pm.inside) {
         const int64_t pix = ((int64_t)cam * a.height + pm.py) * a.width + pm.px;
 #pragma unroll
         for (int k = 0; k < CH; ++k)
-            a.render_colors[pix * CH + k] = a.backgrounds ? acc[k] + T * a.backgrounds[cam * CH + k] : acc[k];
+            a.render_colors[pix * CH + k] = (a.backgrounds && !chunked) ? acc[k] + T * a.backgrounds[cam * CH + k] : acc[k];
         a.render_alphas[pix] = 1.f - T;
         a.last_ids[pix] = last;
-        if (final_T) final_T[pix] = T;
+        if (final_T) final_T[pix] = done ? -T : T;    // sign bit = the pixel saturated (stopped at T_next <= 1e-4)
     }
 }
 
@@ -223,9 +239,14 @@ __global__ void __launch_bounds__(CTA) composite_bwd_kernel(const b2s_composite_
     float v_bg_dot = 0.f;  // sum_k bg_k * v_out_k
 #pragma unroll
     for (int k = 0; k < CH; ++k) { v_out[k] = 0.f; S[k] = 0.f; }
+    const bool chunked = a.chunk_index >= 0;
     if (pm.inside) {
-        T_final = final_T ? final_T[pix] : 1.f - a.render_alphas[pix];
+        T_final = final_T ? fabsf(final_T[pix]) : 1.f - a.render_alphas[pix];
         bin_final = a.last_ids[pix];
+        if (chunked) {      // last_ids = chunk << 28 | index into that chunk's list
+            const int last_chunk = bin_final >> 28;
+            bin_final = a.chunk_index > last_chunk ? -1 : (a.chunk_index == last_chunk ? (bin_final & ((1 << 28) - 1)) : hi - 1);
+        }
         v_alpha_out = a.v_render_alphas ? a.v_render_alphas[pix] : 0.f;
 #pragma unroll
         for (int k = 0; k < CH; ++k) {
@@ -236,6 +257,11 @@ __global__ void __launch_bounds__(CTA) composite_bwd_kernel(const b2s_composite_
         if (T_final == 1.f) bin_final = -1;
     }
     float T = T_final;
+    if (chunked && pm.inside) {   // running state left by the later chunks
+        T = a.state_T[pix];
+#pragma unroll
+        for (int k = 0; k < CH; ++k) S[k] = a.state_S[pix * CH + k];
+    }
     const float v_T_final = T_final * (v_alpha_out - v_bg_dot);   // d(loss)/d(alpha_i) picks up  v_T_final / (1 - alpha_i)
 
     int warp_final = bin_final;
@@ -354,6 +380,11 @@ __global__ void __launch_bounds__(CTA) composite_bwd_kernel(const b2s_composite_
             }
         }
     }
+    if (chunked && pm.inside) {
+        a.state_T[pix] = T;
+#pragma unroll
+        for (int k = 0; k < CH; ++k) a.state_S[pix * CH + k] = S[k];
+    }
 }
 
 template <int CH>
@@ -387,6 +418,10 @@ extern "C" int b2s_composite_fwd(const b2s_composite_fwd_args* a, b2s_stream_t s
     B2S_REQUIRE(a->isect_offsets && a->render_colors && a->render_alphas && a->last_ids, "null pointer");
     B2S_REQUIRE(a->n_isects == 0 || (a->means2d && a->conics && a->colors && a->opacities && a->flatten_ids), "null input");
     B2S_REQUIRE(a->n_isects < 2147483647LL, "n_isects must fit int32");
+    if (a->chunk_index >= 0) {
+        B2S_REQUIRE(a->chunk_index < 8 && a->n_isects < (1LL << 28), "chunked: at most 8 chunks of < 2^28 intersections");
+        B2S_REQUIRE(a->tile_done && a->final_T, "chunked: tile_done and final_T are required");
+    }
     cudaStream_t st = (cudaStream_t)stream;
 #define CALL_FWD(CHN) (launch_fwd<CHN>(a, a->final_T, st))
     switch (a->channels) {
@@ -410,6 +445,7 @@ extern "C" int b2s_composite_bwd(const b2s_composite_bwd_args* a, b2s_stream_t s
     B2S_REQUIRE(a->isect_offsets && a->flatten_ids && a->means2d && a->conics && a->colors && a->opacities, "null input");
     B2S_REQUIRE(a->last_ids && (a->final_T || a->render_alphas), "forward state missing");
     B2S_REQUIRE(a->v_means2d && a->v_conics && a->v_colors && a->v_opacities, "null gradient output");
+    if (a->chunk_index >= 0) B2S_REQUIRE(a->state_T && a->state_S && a->final_T, "chunked: state_T, state_S, final_T are required");
     cudaStream_t st = (cudaStream_t)stream;
 #define CALL_BWD(CHN) (launch_bwd<CHN>(a, a->final_T, st))
     switch (a->channels) {

@@ -146,11 +146,26 @@ __global__ void __launch_bounds__(FWD_THREADS) project_fwd_kernel(const b2s_proj
         if (o.radius > 0) vis |= 1ull << c;
     }
 
-    if (a.total_isects) {   // one atomic per warp: the data-dependent size the host reads to size the next buffers
-        int wsum = my_tiles;
+    if (a.total_isects) {
+        // The data-dependent sizes the host reads: sum of tile counts and number of visible rows.  One atomic per
+        // CTA, spread over B2S_TOTAL_SLOTS counter pairs (same-address atomics serialise in L2: with one per warp
+        // they cost 0.3 ms at 5.8 M Gaussians); the host sums the slots.
+        __shared__ int s_tot[2][FWD_THREADS / 32];
+        int wsum = my_tiles, vcount = __popcll(vis);
 #pragma unroll
-        for (int d = 16; d > 0; d >>= 1) wsum += __shfl_xor_sync(FULL, wsum, d);
-        if (lane == 0 && wsum) atomicAdd(reinterpret_cast<unsigned long long*>(a.total_isects), (unsigned long long)wsum);
+        for (int d = 16; d > 0; d >>= 1) {
+            wsum += __shfl_xor_sync(FULL, wsum, d);
+            vcount += __shfl_xor_sync(FULL, vcount, d);
+        }
+        if (lane == 0) { s_tot[0][warp] = wsum; s_tot[1][warp] = vcount; }
+        __syncthreads();
+        if (threadIdx.x < 2) {
+            int tsum = 0;
+#pragma unroll
+            for (int w = 0; w < FWD_THREADS / 32; ++w) tsum += s_tot[threadIdx.x][w];
+            if (tsum) atomicAdd(reinterpret_cast<unsigned long long*>(a.total_isects) + 2 * (blockIdx.x % B2S_TOTAL_SLOTS) + threadIdx.x,
+                                (unsigned long long)tsum);
+        }
     }
 
     if (a.sh_coeffs == nullptr || a.colors == nullptr) return;
@@ -206,8 +221,10 @@ __global__ void __launch_bounds__(SHB_THREADS, 4) sh_bwd_fused_kernel(const b2s_
     mean[0] = __ldg(a.means + 3 * nc); mean[1] = __ldg(a.means + 3 * nc + 1); mean[2] = __ldg(a.means + 3 * nc + 2);
     unsigned long long vis = 0ull;
     if (live)
-        for (int c = 0; c < a.C; ++c)
-            if (__ldg(a.radii + (int64_t)c * a.N + n) > 0) vis |= 1ull << c;
+        for (int c = 0; c < a.C; ++c) {
+            const int64_t i = (int64_t)c * a.N + n;
+            if (a.touched ? (a.touched[i] != 0) : (__ldg(a.radii + i) > 0)) vis |= 1ull << c;
+        }
 
     const int K = (a.sh_degree + 1) * (a.sh_degree + 1);
     const int rs = sh_row_stride(K);
@@ -216,6 +233,29 @@ __global__ void __launch_bounds__(SHB_THREADS, 4) sh_bwd_fused_kernel(const b2s_
     const int64_t row0 = (int64_t)blockIdx.x * SHB_THREADS + warp * 32;
     const int rows = (int)max((int64_t)0, min((int64_t)32, a.N - row0));
     const unsigned row_mask = a.v_colors ? __ballot_sync(FULL, live && vis != 0ull) : 0u;
+    if (row_mask == 0u && !a.accumulate) {
+        // nothing in this warp's 32 rows can have a gradient (culled / occluded): stream zeros straight out
+        if (live) { a.v_means[3 * n] = 0.f; a.v_means[3 * n + 1] = 0.f; a.v_means[3 * n + 2] = 0.f; }
+        if (rows > 0) {
+            float* g = a.v_sh_coeffs + (size_t)row0 * a.sh_stride_k * 3;
+            if (KVEC == 16) {
+                float4* g4 = reinterpret_cast<float4*>(g);
+                const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                for (int i = 0; i < 12; ++i) {
+                    const int q = lane + 32 * i;
+                    if (q < rows * 12) stg_stream4(g4 + q, z);
+                }
+            } else {
+                const int per = 3 * K;
+                for (int f = lane; f < 32 * per; f += 32) {
+                    const int r = f / per;
+                    if (r < rows) g[(size_t)r * a.sh_stride_k * 3 + (f - r * per)] = 0.f;
+                }
+            }
+        }
+        return;
+    }
     // masked-off rows are zero-filled by the loader, so culled Gaussians get zero gradients for free
     sh_rows_load<KVEC>(tile_in, a.sh_coeffs + (size_t)row0 * a.sh_stride_k * 3, rows, row_mask, K, a.sh_stride_k, lane);
     if (MULTI)
@@ -274,6 +314,16 @@ __global__ void __launch_bounds__(BWD_THREADS) project_bwd_kernel(const b2s_proj
 
     const int64_t n = (int64_t)blockIdx.x * BWD_THREADS + threadIdx.x;
     if (n >= a.N) return;
+    if (a.touched && !a.accumulate) {      // occluded in every camera: all gradients are zero, skip the parameter loads
+        bool any_t = false;
+        for (int c = 0; c < a.C; ++c) any_t |= a.touched[(int64_t)c * a.N + n] != 0;
+        if (!any_t) {
+            for (int k = 0; k < 3; ++k) { if (!MEANS_ACC) a.v_means[3 * n + k] = 0.f; a.v_scales[3 * n + k] = 0.f; }
+            reinterpret_cast<float4*>(a.v_quats)[n] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (a.v_opacities) a.v_opacities[n] = 0.f;
+            return;
+        }
+    }
 
     float mean[3], q[4], s[3];
     mean[0] = __ldg(a.means + 3 * n); mean[1] = __ldg(a.means + 3 * n + 1); mean[2] = __ldg(a.means + 3 * n + 2);
@@ -294,7 +344,7 @@ __global__ void __launch_bounds__(BWD_THREADS) project_bwd_kernel(const b2s_proj
     bool any = false;
     for (int c = 0; c < a.C; ++c) {
         const int64_t i = (int64_t)c * a.N + n;
-        if (__ldg(a.radii + i) <= 0) continue;            // the forward's cull decision is authoritative
+        if (a.touched ? (a.touched[i] == 0) : (__ldg(a.radii + i) <= 0)) continue;   // the forward's decision is authoritative
         ProjMid mid;
         project_mid_fast(cams[c], mean, S, a.eps2d, mid);
         if (!(mid.det > 0.f)) continue;
@@ -372,9 +422,11 @@ extern "C" int b2s_project_bwd(const b2s_project_bwd_args* a, b2s_stream_t strea
     B2S_REQUIRE(a->C <= B2S_MAX_CAMERAS_PER_CALL, "too many cameras in one call (loop over chunks)");
     if (a->N == 0) return 0;
     B2S_REQUIRE(a->means && a->quats && a->scales && a->viewmats && a->Ks && a->radii, "null input");
-    B2S_REQUIRE(a->v_means && a->v_quats && a->v_scales, "null gradient output");
-    B2S_REQUIRE(aligned16(a->quats) && aligned16(a->v_quats), "quats misaligned");
-    const bool sh = a->sh_coeffs != nullptr && a->v_sh_coeffs != nullptr;
+    B2S_REQUIRE(a->v_means && (a->stages == 1 || (a->v_quats && a->v_scales)), "null gradient output");
+    B2S_REQUIRE(aligned16(a->quats) && (a->stages == 1 || aligned16(a->v_quats)), "quats misaligned");
+    B2S_REQUIRE(a->stages >= 0 && a->stages <= 2, "stages must be 0, 1 or 2");
+    const bool sh = a->sh_coeffs != nullptr && a->v_sh_coeffs != nullptr && a->stages != 2;
+    const bool geom = a->stages != 1;
     cudaStream_t st = (cudaStream_t)stream;
     const size_t cam_bytes = ((a->C * sizeof(Camera) + 15) / 16) * 16;
     if (sh) {
@@ -390,8 +442,10 @@ extern "C" int b2s_project_bwd(const b2s_project_bwd_args* a, b2s_stream_t strea
         kern<<<(unsigned)cdiv(a->N, SHB_THREADS), SHB_THREADS, smem, st>>>(*a);
         B2S_LAUNCH_CHECK();
     }
-    auto kern2 = sh ? project_bwd_kernel<true> : project_bwd_kernel<false>;
-    kern2<<<(unsigned)cdiv(a->N, BWD_THREADS), BWD_THREADS, cam_bytes, st>>>(*a);
-    B2S_LAUNCH_CHECK();
+    if (geom) {
+        auto kern2 = sh ? project_bwd_kernel<true> : project_bwd_kernel<false>;
+        kern2<<<(unsigned)cdiv(a->N, BWD_THREADS), BWD_THREADS, cam_bytes, st>>>(*a);
+        B2S_LAUNCH_CHECK();
+    }
     return 0;
 }

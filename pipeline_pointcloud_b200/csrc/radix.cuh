@@ -73,7 +73,7 @@ __global__ void __launch_bounds__(THREADS) hist_kernel(int64_t n, const KeyT* __
 }
 
 // exclusive scan of each 256-bin histogram (one CTA per pass)
-__global__ void __launch_bounds__(RADIX) scan_hist_kernel(unsigned long long* __restrict__ hist) {
+static __global__ void __launch_bounds__(RADIX) scan_hist_kernel(unsigned long long* __restrict__ hist) {
     __shared__ unsigned long long s[RADIX];
     unsigned long long* h = hist + (size_t)blockIdx.x * RADIX;
     const unsigned long long v = h[threadIdx.x];

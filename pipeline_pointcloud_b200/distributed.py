@@ -345,7 +345,7 @@ def rasterization_distributed(means, quats, scales, opacities, colors, viewmats,
     # ---- local shard projected into every camera (one kernel; SH coefficients read once) ----------------------
     antialiased = rasterize_mode == "antialiased"
     fused_sh = sh_degree is not None
-    radii, means2d, depths, conics, _comps, opac, sh_cols, tiles, _dk, _ri, _tot = ops._ProjectFused.apply(
+    radii, means2d, depths, conics, _comps, opac, sh_cols, tiles, _dk, _ri, _tot, _tch = ops._ProjectFused.apply(
         means, quats, scales, opacities, colors if fused_sh else None, viewmats_all, Ks_all, None, width, height,
         float(eps2d), float(near_plane), float(far_plane), float(radius_clip), antialiased, False,
         int(sh_degree) if fused_sh else 0, tile_size)
