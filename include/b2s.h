@@ -84,8 +84,9 @@ typedef struct {
     int32_t* tiles_per_gauss; /* [C,N] or NULL */
     uint32_t* depth_keys;     /* [C,N] or NULL: depth bits, 0xFFFFFFFF on culled rows (for b2s_depth_order) */
     int32_t* row_ids;         /* [C,N] or NULL: iota, c*N + n */
-    int64_t* total_isects;    /* device int64[B2S_TOTAL_SLOTS][2] or NULL, zero it first: slot sums give
-                                 [0] sum of tiles_per_gauss, [1] visible rows (spread to avoid same-address atomics) */
+    int64_t* total_isects;    /* device int64[B2S_TOTAL_SLOTS][4] or NULL, zero it first: slot sums give
+                                 [0] sum of tiles_per_gauss, [1] visible rows, [2] coarse-bin records (b2s_coarse_bin),
+                                 [3] unused (spread over slots to avoid same-address atomics) */
 } b2s_project_fwd_args;
 B2S_API int b2s_project_fwd(const b2s_project_fwd_args* a, b2s_stream_t stream);
 
@@ -113,7 +114,6 @@ typedef struct {
     float* v_scales;    /* [N,3] */
     float* v_opacities; /* [N] or NULL */
     float* v_sh_coeffs; /* [N, sh_stride_k, 3] or NULL; rows >= (deg+1)^2 are not touched */
-    const uint8_t* touched; /* [C,N] or NULL: rows with touched == 0 are known to have zero cotangents (occluded) */
     int32_t stages;         /* 0 = both; 1 = SH colour VJP only (v_sh_coeffs, v_means); 2 = projection VJP only */
 } b2s_project_bwd_args;
 B2S_API int b2s_project_bwd(const b2s_project_bwd_args* a, b2s_stream_t stream);
@@ -188,38 +188,28 @@ B2S_API int b2s_isect_ids_from_bins(int64_t n_isects, int32_t key_bytes, const v
                                     const int32_t* flatten_ids, const float* depths, int64_t* isect_ids,
                                     b2s_stream_t stream);
 
-/* Occlusion-aware chunked binning (see csrc/chunked.cu).  The depth order is processed in a few chunks;
- * `b2s_chunk_expand` emits the (tile key, flat id) records of the rows at depth-order positions [j0, j1) into
- * the tiles that are still open (`tile_done[t] == 0`), evaluates the SH colour of the rows that emit (lazy
- * shading), flags them in `touched`, and leaves the record count in *n_out (device; the host reads it to size
- * the sort).  `b2s_tile_sort` sorts the records by (camera, tile) -- stable, so depth order is kept -- and
- * builds the per-tile offsets of this chunk.  Compositing carries pixel state between chunks
- * (b2s_composite_*_args.chunk_index >= 0). */
-typedef struct {
-    int64_t N;                 /* Gaussians per camera (dense rows: id = c*N + n) */
-    int32_t C;
-    int64_t j0, j1;            /* depth-order positions of this chunk */
-    const int32_t* sorted_ids; /* from b2s_depth_order */
-    const float* means2d; const int32_t* radii; const float* depths;
-    int32_t tile_size, tile_w, tile_h;
-    const uint8_t* tile_done;  /* [C*tile_h*tile_w] or NULL (first chunk) */
-    /* lazy colour: SH evaluated for emitting rows when sh_coeffs != NULL; color_channels 3, or 4 (= RGB + depth) */
-    const float* means; const float* sh_coeffs; const float* viewmats;
-    int32_t sh_degree, sh_stride_k, color_channels;
-    float* colors;             /* [C*N, color_channels] or NULL */
-    uint8_t* touched;          /* [C*N] or NULL */
-    void* tile_keys;           /* [capacity] 16- or 32-bit keys (b2s_tile_key_bytes) */
-    int32_t* vals;             /* [capacity] */
-    int64_t capacity;          /* >= number of records this chunk can emit (sum of tiles_per_gauss is always enough) */
-    int64_t* n_out;            /* device scalar */
-    void* workspace; int64_t workspace_bytes;
-} b2s_chunk_expand_args;
-B2S_API int64_t b2s_chunk_expand_workspace_bytes(int64_t n_rows);
-B2S_API int b2s_chunk_expand(const b2s_chunk_expand_args* a, b2s_stream_t stream);
-B2S_API int64_t b2s_tile_sort_workspace_bytes(int64_t n);
-B2S_API int b2s_tile_sort(int64_t n, int32_t C, int32_t tile_w, int32_t tile_h, const void* tile_keys, const int32_t* vals,
-                          void* tile_keys_sorted, int32_t* flatten_ids, int32_t* offsets, void* workspace,
-                          int64_t workspace_bytes, b2s_stream_t stream);
+/* Two-level binning -- what `rasterization()` runs.  Compositing stops at the first few percent of a tile's
+ * depth-sorted list once its pixels saturate, so materialising every (tile, Gaussian) intersection is mostly
+ * wasted work.  Instead the depth-ordered rows are binned into COARSE bins of B2S_COARSE x B2S_COARSE tiles
+ * (one record per (row, coarse bin) it overlaps, ~4x fewer records than tile intersections), and the compositing
+ * kernels expand a tile's list on the fly: they walk the coarse bin's list in order and keep the records whose
+ * tile mask covers the tile.  The kept records are exactly the tile's slice of the reference's sorted list
+ * (same order: depth bits, ties by flat index), so renders and gradients are unchanged.
+ *   record = mask_y(8) << 24 | mask_x(8) << 16 | coarse key(16), coarse key = (cam*bins_h + by)*bins_w + bx;
+ *   mask_x bit i set <=> the row's tile rectangle covers tile column 8*bx + i (same for y).
+ *   b2s_coarse_count : *total += number of (row, coarse bin) records        (stage 1 can emit this itself)
+ *   b2s_coarse_bin   : bin_recs [n] / bin_ids [n] sorted by coarse key (stable: depth order inside a bin),
+ *                      bin_offsets [C*bins_h*bins_w + 1].  bin_recs / bin_ids must be allocated with n rounded
+ *                      up to a multiple of 4 entries and 16-byte aligned (the kernels read them 128 bits at a time).
+ * Needs C * ceil(tile_w/8) * ceil(tile_h/8) <= 65536 (B2S_E_UNSUPPORTED otherwise). */
+#define B2S_COARSE 8
+B2S_API int b2s_coarse_count(int64_t M, const float* means2d, const int32_t* radii, int32_t tile_size, int32_t tile_w,
+                             int32_t tile_h, int64_t* total /* device, accumulated */, b2s_stream_t stream);
+B2S_API int64_t b2s_coarse_bin_workspace_bytes(int64_t M, int64_t n_records);
+B2S_API int b2s_coarse_bin(int64_t M, int64_t N, const int64_t* camera_ids /* or NULL */, int64_t n_records,
+                           const int32_t* sorted_ids, const float* means2d, const int32_t* radii, int32_t C,
+                           int32_t tile_size, int32_t tile_w, int32_t tile_h, uint32_t* bin_recs, int32_t* bin_ids,
+                           int32_t* bin_offsets, void* workspace, int64_t workspace_bytes, b2s_stream_t stream);
 
 /* Packed layout (gsplat `packed=True`): gather the visible rows `sel` (ascending dense indices c*N+n) of the
  * stage-1 outputs into nnz-row tensors (+ camera_ids / gaussian_ids), and scatter gradients back into
@@ -286,12 +276,11 @@ typedef struct {
     int32_t* last_ids;          /* [C,H,W] index into flatten_ids of the last contributor */
     float* final_T;             /* [C,H,W] exact final transmittance for the backward (negated on pixels that
                                    saturated, i.e. stopped at T_next <= 1e-4), or NULL */
-    /* chunked compositing: chunk_index < 0 = one-shot (everything above).  chunk_index >= 0: this call composites
-     * chunk `chunk_index` of the depth order; pixel state is carried in render_colors (without background),
-     * final_T (signed) and last_ids (= chunk << 28 | index into this chunk's flatten_ids); chunk 0 initialises it.
-     * tile_done[t] is set once all pixels of tile t have saturated, and such tiles are skipped afterwards. */
-    int32_t chunk_index;
-    uint8_t* tile_done;         /* [C*tile_h*tile_w], required when chunk_index >= 0 */
+    /* two-level binning (b2s_coarse_bin): when bin_offsets != NULL the tile lists are expanded from the coarse bins
+     * inside the kernel; isect_offsets / flatten_ids are not read and last_ids holds positions in bin_ids. */
+    const int32_t* bin_offsets; /* [C*bins_h*bins_w + 1] or NULL */
+    const uint32_t* bin_recs;   /* [n_isects] (n_isects = number of coarse records) */
+    const int32_t* bin_ids;     /* [n_isects] */
 } b2s_composite_fwd_args;
 B2S_API int b2s_composite_fwd(const b2s_composite_fwd_args* a, b2s_stream_t stream);
 
@@ -311,10 +300,7 @@ typedef struct {
     float* v_conics;      /* [M,3] */
     float* v_colors;      /* [M,channels] */
     float* v_opacities;   /* [M] */
-    /* chunked: call once per chunk, last chunk first.  state_T [C,H,W] (initialised by the caller to |final_T|) and
-     * state_S [C,H,W,channels] (zeros) carry the running transmittance / accumulated colour between the calls. */
-    int32_t chunk_index;  /* < 0: one-shot */
-    float* state_T; float* state_S;
+    const int32_t* bin_offsets; const uint32_t* bin_recs; const int32_t* bin_ids;   /* as in the forward */
 } b2s_composite_bwd_args;
 B2S_API int b2s_composite_bwd(const b2s_composite_bwd_args* a, b2s_stream_t stream);
 

@@ -52,7 +52,7 @@ class ProjectBwdArgs(Structure):
         ("v_compensations", c_void_p), ("v_opacities_out", c_void_p), ("v_colors", c_void_p),
         ("accumulate", c_int32),
         ("v_means", c_void_p), ("v_quats", c_void_p), ("v_scales", c_void_p), ("v_opacities", c_void_p),
-        ("v_sh_coeffs", c_void_p), ("touched", c_void_p), ("stages", c_int32),
+        ("v_sh_coeffs", c_void_p), ("stages", c_int32),
     ]
 
 
@@ -64,7 +64,7 @@ class CompositeFwdArgs(Structure):
         ("means2d", c_void_p), ("conics", c_void_p), ("colors", c_void_p), ("opacities", c_void_p),
         ("backgrounds", c_void_p), ("isect_offsets", c_void_p), ("flatten_ids", c_void_p),
         ("render_colors", c_void_p), ("render_alphas", c_void_p), ("last_ids", c_void_p), ("final_T", c_void_p),
-        ("chunk_index", c_int32), ("tile_done", c_void_p),
+        ("bin_offsets", c_void_p), ("bin_recs", c_void_p), ("bin_ids", c_void_p),
     ]
 
 
@@ -78,20 +78,7 @@ class CompositeBwdArgs(Structure):
         ("render_alphas", c_void_p), ("last_ids", c_void_p), ("final_T", c_void_p),
         ("v_render_colors", c_void_p), ("v_render_alphas", c_void_p),
         ("v_means2d", c_void_p), ("v_means2d_abs", c_void_p), ("v_conics", c_void_p), ("v_colors", c_void_p),
-        ("v_opacities", c_void_p), ("chunk_index", c_int32), ("state_T", c_void_p), ("state_S", c_void_p),
-    ]
-
-
-class ChunkExpandArgs(Structure):
-    _fields_ = [
-        ("N", c_int64), ("C", c_int32), ("j0", c_int64), ("j1", c_int64),
-        ("sorted_ids", c_void_p), ("means2d", c_void_p), ("radii", c_void_p), ("depths", c_void_p),
-        ("tile_size", c_int32), ("tile_w", c_int32), ("tile_h", c_int32),
-        ("tile_done", c_void_p),
-        ("means", c_void_p), ("sh_coeffs", c_void_p), ("viewmats", c_void_p),
-        ("sh_degree", c_int32), ("sh_stride_k", c_int32), ("color_channels", c_int32),
-        ("colors", c_void_p), ("touched", c_void_p), ("tile_keys", c_void_p), ("vals", c_void_p),
-        ("capacity", c_int64), ("n_out", c_void_p), ("workspace", c_void_p), ("workspace_bytes", c_int64),
+        ("v_opacities", c_void_p), ("bin_offsets", c_void_p), ("bin_recs", c_void_p), ("bin_ids", c_void_p),
     ]
 
 
@@ -120,11 +107,10 @@ SYMBOLS = {
     "b2s_tile_bin": (c_int32, [c_int64, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_int32, c_int32,
                                c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
     "b2s_isect_ids_from_bins": (c_int32, [c_int64, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
-    "b2s_chunk_expand_workspace_bytes": (c_int64, [c_int64]),
-    "b2s_chunk_expand": (c_int32, [POINTER(ChunkExpandArgs), c_void_p]),
-    "b2s_tile_sort_workspace_bytes": (c_int64, [c_int64]),
-    "b2s_tile_sort": (c_int32, [c_int64, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
-                                c_int64, c_void_p]),
+    "b2s_coarse_count": (c_int32, [c_int64, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p]),
+    "b2s_coarse_bin_workspace_bytes": (c_int64, [c_int64, c_int64]),
+    "b2s_coarse_bin": (c_int32, [c_int64, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_int32, c_int32,
+                                 c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
     "b2s_pack_rows": (c_int32, [c_int64, c_int64, c_void_p, c_int32] + [c_void_p] * 17),
     "b2s_unpack_rows": (c_int32, [c_int64, c_void_p, c_int32] + [c_void_p] * 11),
     "b2s_pack_payload": (c_int32, [c_int64, c_int64, c_void_p, c_int32, c_int32, c_int64] + [c_void_p] * 9),

@@ -300,6 +300,134 @@ __global__ void isect_ids_kernel(int64_t n, const KeyT* __restrict__ tile_keys, 
     isect_ids[i] = (int64_t)(((uint64_t)tile_keys[i] << 32) | (uint64_t)__float_as_uint(depths[flat[i]]));
 }
 
+
+// =================================================================================================
+// Two-level binning (the path rasterization() runs): coarse bins of B2S_COARSE x B2S_COARSE tiles.
+//
+// One record per (depth-ordered row, coarse bin it overlaps):
+//     rec = mask_y << 24 | mask_x << 16 | coarse key,   coarse key = (cam * bins_h + by) * bins_w + bx
+// mask_x bit i <=> the row's tile rectangle covers tile column 8*bx + i.  The records are stable-sorted by
+// coarse key (depth order kept inside a bin); the compositing kernels expand the per-tile lists on the fly.
+// =================================================================================================
+constexpr int CB = B2S_COARSE;
+static_assert(CB == 8, "the record format packs two 8-bit tile masks");
+
+__device__ __forceinline__ int coarse_span(int t0, int t1) { return (t1 + CB - 1) / CB - t0 / CB; }   // t1 > t0
+
+__global__ void coarse_count_kernel(int64_t M, const float2* __restrict__ means2d, const int32_t* __restrict__ radii,
+                                    float tile_size, int tile_w, int tile_h, unsigned long long* __restrict__ total) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int cnt = 0;
+    if (i < M) {
+        const int r = radii[i];
+        if (r > 0) {
+            const float2 m = means2d[i];
+            int x0, y0, x1, y1;
+            tile_rect(m.x, m.y, r, tile_size, tile_w, tile_h, x0, y0, x1, y1);
+            if (x1 > x0 && y1 > y0) cnt = coarse_span(x0, x1) * coarse_span(y0, y1);
+        }
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) cnt += __shfl_xor_sync(FULL, cnt, d);
+    if ((threadIdx.x & 31) == 0 && cnt) atomicAdd(total, (unsigned long long)cnt);
+}
+
+// Expansion in depth order with a fused single-pass scan (same structure as expand_kernel): a warp writes
+// the records of its 32 rows with lanes striding over the warp's output range (coalesced).
+__global__ void __launch_bounds__(EXP_THREADS) coarse_expand_kernel(int64_t M, int64_t N, const int64_t* __restrict__ camera_ids,
+                                                                    const int32_t* __restrict__ sorted_ids,
+                                                                    const float2* __restrict__ means2d,
+                                                                    const int32_t* __restrict__ radii, float tile_size,
+                                                                    int tile_w, int tile_h, int bins_w, int bins_h,
+                                                                    unsigned long long* status, unsigned int* cta_counter,
+                                                                    uint32_t* __restrict__ recs, int32_t* __restrict__ vals) {
+    __shared__ int s_start[EXP_THREADS];
+    __shared__ int s_id[EXP_THREADS];
+    __shared__ uint32_t s_xs[EXP_THREADS], s_ys[EXP_THREADS];   // x0 | x1 << 16, y0 | y1 << 16 (tile units)
+    __shared__ uint32_t s_cam[EXP_THREADS];                     // cam * bins_h * bins_w
+    __shared__ unsigned int s_cta;
+    __shared__ int s_warp_tot[EXP_THREADS / 32];
+    __shared__ unsigned long long s_prefix;
+    if (threadIdx.x == 0) s_cta = atomicAdd(cta_counter, 1u);
+    __syncthreads();
+    const unsigned int cta = s_cta;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wbase = threadIdx.x & ~31;
+    const int64_t j = (int64_t)cta * EXP_THREADS + threadIdx.x;
+    int cnt = 0, id = 0, x0 = 0, y0 = 0, x1 = 0, y1 = 0;
+    if (j < M) {
+        id = sorted_ids[j];
+        const int r = radii[id];
+        if (r > 0) {
+            const float2 m = means2d[id];
+            tile_rect(m.x, m.y, r, tile_size, tile_w, tile_h, x0, y0, x1, y1);
+            if (x1 > x0 && y1 > y0) cnt = coarse_span(x0, x1) * coarse_span(y0, y1);
+        }
+    }
+    int incl = cnt;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        int o = __shfl_up_sync(FULL, incl, d);
+        if (lane >= d) incl += o;
+    }
+    const int total = __shfl_sync(FULL, incl, 31);
+    if (lane == 31) s_warp_tot[warp] = total;
+    int64_t cam = 0;
+    if (cnt > 0) cam = camera_ids ? camera_ids[id] : (id / N);
+    s_start[threadIdx.x] = incl - cnt;
+    s_id[threadIdx.x] = id;
+    s_xs[threadIdx.x] = (uint32_t)x0 | ((uint32_t)x1 << 16);
+    s_ys[threadIdx.x] = (uint32_t)y0 | ((uint32_t)y1 << 16);
+    s_cam[threadIdx.x] = (uint32_t)cam * (uint32_t)(bins_w * bins_h);
+    __syncthreads();
+    int warp_off = 0, block_sum = 0;
+#pragma unroll
+    for (int w = 0; w < EXP_THREADS / 32; ++w) {
+        int x = s_warp_tot[w];
+        if (w < warp) warp_off += x;
+        block_sum += x;
+    }
+    if (warp == 0) {
+        const unsigned long long excl = lookback_warp(status, cta, (unsigned long long)block_sum, lane);
+        if (lane == 0) s_prefix = excl;
+    }
+    __syncthreads();
+    if (total == 0) return;
+    const int64_t out0 = (int64_t)s_prefix + warp_off;
+    for (int e = lane; e < total; e += 32) {
+        int lo = 0;
+#pragma unroll
+        for (int step = 16; step > 0; step >>= 1)
+            if (s_start[wbase + lo + step] <= e) lo += step;
+        const int g = wbase + lo;
+        const int k = e - s_start[g];
+        const int gx0 = (int)(s_xs[g] & 0xFFFFu), gx1 = (int)(s_xs[g] >> 16);
+        const int gy0 = (int)(s_ys[g] & 0xFFFFu), gy1 = (int)(s_ys[g] >> 16);
+        const int bx0 = gx0 / CB, by0 = gy0 / CB;
+        const int w = coarse_span(gx0, gx1);
+        const int dy = k / w, dx = k - dy * w;
+        const int bx = bx0 + dx, by = by0 + dy;
+        // tile columns / rows of this coarse bin covered by the rectangle, as bit masks
+        const int lx0 = max(gx0 - bx * CB, 0), lx1 = min(gx1 - bx * CB, CB);
+        const int ly0 = max(gy0 - by * CB, 0), ly1 = min(gy1 - by * CB, CB);
+        const uint32_t mx = ((1u << lx1) - 1u) & ~((1u << lx0) - 1u);
+        const uint32_t my = ((1u << ly1) - 1u) & ~((1u << ly0) - 1u);
+        recs[out0 + e] = (my << 24) | (mx << 16) | (s_cam[g] + (uint32_t)(by * bins_w + bx));
+        vals[out0 + e] = s_id[g];
+    }
+}
+
+// bin_offsets[k] = lower bound of coarse key k in the sorted records, k = 0 .. n_bins (inclusive: the end)
+__global__ void coarse_offsets_kernel(int64_t n, const uint32_t* __restrict__ recs, int64_t n_bins, int32_t* __restrict__ offsets) {
+    int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k > n_bins) return;
+    int64_t lo = 0, hi = n;
+    while (lo < hi) {
+        int64_t mid = (lo + hi) >> 1;
+        if ((int64_t)(recs[mid] & 0xFFFFu) < k) lo = mid + 1; else hi = mid;
+    }
+    offsets[k] = (int32_t)lo;
+}
+
 static size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
 
 // scratch bytes of one (key, int32) pair sort, and the sort itself: the hand-written onesweep of radix.cuh
@@ -553,6 +681,87 @@ extern "C" int b2s_isect_ids_from_bins(int64_t n_isects, int32_t key_bytes, cons
     else
         isect_ids_kernel<uint32_t><<<grid, 256, 0, (cudaStream_t)stream>>>(
             n_isects, reinterpret_cast<const uint32_t*>(tile_keys_sorted), flatten_ids, depths, isect_ids);
+    B2S_LAUNCH_CHECK();
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// two-level binning entry points
+// ---------------------------------------------------------------------------------------------------
+extern "C" int b2s_coarse_count(int64_t M, const float* means2d, const int32_t* radii, int32_t tile_size, int32_t tile_w,
+                                int32_t tile_h, int64_t* total, b2s_stream_t stream) {
+    B2S_REQUIRE(M >= 0 && tile_size > 0 && tile_w > 0 && tile_h > 0 && total, "bad args");
+    if (M == 0) return 0;
+    B2S_REQUIRE(means2d && radii, "null pointer");
+    coarse_count_kernel<<<(unsigned)cdiv(M, 256), 256, 0, (cudaStream_t)stream>>>(
+        M, reinterpret_cast<const float2*>(means2d), radii, (float)tile_size, tile_w, tile_h,
+        reinterpret_cast<unsigned long long*>(total));
+    B2S_LAUNCH_CHECK();
+    return 0;
+}
+
+static size_t pad4(int64_t n) { return (size_t)((n + 3) & ~(int64_t)3); }
+
+extern "C" int64_t b2s_coarse_bin_workspace_bytes(int64_t M, int64_t n_records) {
+    if (n_records <= 0 || M <= 0) return 256;
+    // unsorted records + unsorted ids + sort scratch + look-back status (counter + one word per CTA)
+    return (int64_t)(2 * align256(pad4(n_records) * 4) + align256(cub_pairs32_bytes(n_records)) +
+                     align256(16 + (size_t)cdiv(M, EXP_THREADS) * 8));
+}
+
+extern "C" int b2s_coarse_bin(int64_t M, int64_t N, const int64_t* camera_ids, int64_t n_records, const int32_t* sorted_ids,
+                              const float* means2d, const int32_t* radii, int32_t C, int32_t tile_size, int32_t tile_w,
+                              int32_t tile_h, uint32_t* bin_recs, int32_t* bin_ids, int32_t* bin_offsets, void* workspace,
+                              int64_t workspace_bytes, b2s_stream_t stream) {
+    B2S_REQUIRE(M >= 0 && n_records >= 0 && C >= 0 && tile_size > 0 && tile_w > 0 && tile_h > 0 && bin_offsets, "bad args");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int bins_w = (tile_w + CB - 1) / CB, bins_h = (tile_h + CB - 1) / CB;
+    const int64_t n_bins = (int64_t)C * bins_w * bins_h;
+    if (n_bins > 65536) {
+        set_error("b2s_coarse_bin: C * bins_w * bins_h = %lld exceeds 65536", (long long)n_bins);
+        return B2S_E_UNSUPPORTED;
+    }
+    if (n_records == 0 || M == 0) {
+        B2S_CUDA(cudaMemsetAsync(bin_offsets, 0, (size_t)(n_bins + 1) * 4, st));
+        return 0;
+    }
+    B2S_REQUIRE(camera_ids != nullptr || N > 0, "dense rows need N");
+    B2S_REQUIRE(sorted_ids && means2d && radii && bin_recs && bin_ids && workspace, "null pointer");
+    B2S_REQUIRE(n_records < 2147483647LL, "n_records must fit int32");
+    if (workspace_bytes < b2s_coarse_bin_workspace_bytes(M, n_records)) {
+        set_error("b2s_coarse_bin: workspace too small");
+        return B2S_E_WORKSPACE;
+    }
+    B2S_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255u) == 0, "workspace must be 256-byte aligned");
+    B2S_REQUIRE(((reinterpret_cast<uintptr_t>(bin_recs) | reinterpret_cast<uintptr_t>(bin_ids)) & 15u) == 0,
+                "bin_recs / bin_ids must be 16-byte aligned");
+    char* w = reinterpret_cast<char*>(workspace);
+    uint32_t* recs_u = reinterpret_cast<uint32_t*>(w);
+    w += align256(pad4(n_records) * 4);
+    int32_t* vals_u = reinterpret_cast<int32_t*>(w);
+    w += align256(pad4(n_records) * 4);
+    void* sort_tmp = w;
+    const size_t sort_bytes = cub_pairs32_bytes(n_records);
+    w += align256(sort_bytes);
+    const int64_t ctas = cdiv(M, EXP_THREADS);
+    B2S_CUDA(cudaMemsetAsync(w, 0, (size_t)(16 + ctas * 8), st));
+    unsigned int* counter = reinterpret_cast<unsigned int*>(w);
+    unsigned long long* status = reinterpret_cast<unsigned long long*>(w + 16);
+    coarse_expand_kernel<<<(unsigned)ctas, EXP_THREADS, 0, st>>>(
+        M, N, camera_ids, sorted_ids, reinterpret_cast<const float2*>(means2d), radii, (float)tile_size, tile_w, tile_h,
+        bins_w, bins_h, status, counter, recs_u, vals_u);
+    B2S_LAUNCH_CHECK();
+    const int key_bits = bit_length(n_bins > 1 ? n_bins - 1 : 1);
+    {
+        int rc = sort_pairs<uint32_t>(sort_tmp, sort_bytes, recs_u, bin_recs, vals_u, bin_ids, n_records, key_bits, st);
+        if (rc != 0) return rc;
+    }
+    // the kernels read the lists 4 entries at a time: define the (at most 3) pad entries
+    if (pad4(n_records) > (size_t)n_records) {
+        B2S_CUDA(cudaMemsetAsync(bin_recs + n_records, 0, (pad4(n_records) - (size_t)n_records) * 4, st));
+        B2S_CUDA(cudaMemsetAsync(bin_ids + n_records, 0, (pad4(n_records) - (size_t)n_records) * 4, st));
+    }
+    coarse_offsets_kernel<<<(unsigned)cdiv(n_bins + 1, 128), 128, 0, st>>>(n_records, bin_recs, n_bins, bin_offsets);
     B2S_LAUNCH_CHECK();
     return 0;
 }

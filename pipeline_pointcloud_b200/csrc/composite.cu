@@ -16,6 +16,15 @@
 // exact `alpha < 1/255` test still runs afterwards, so the reference semantics are unchanged.
 // Early termination: a warp whose 32 pixels are saturated skips the batch by vote, the CTA stops
 // when all 256 are.
+//
+// Two list sources (template parameter BINS):
+//   BINS = false  the reference's layout: the tile's Gaussians are flatten_ids[isect_offsets[t] .. isect_offsets[t+1])
+//                 (the stage-level op `rasterize_to_pixels`);
+//   BINS = true   two-level binning (binning.cu, `b2s_coarse_bin`): the CTA walks the depth-ordered list of its
+//                 8x8-tile coarse bin, 2048 records per round (each thread tests 2 x 128 bits of records against the
+//                 tile's mask bits), compacts the hits -- in order -- into a shared-memory ring and composites them
+//                 256 at a time.  The hits are exactly the tile's slice of the reference's sorted list, but only
+//                 the part in front of the saturation point is ever generated.
 #include "common.cuh"
 
 namespace b2s {
@@ -28,6 +37,72 @@ constexpr float T_STOP = 1e-4f;
 constexpr float TAU_MARGIN = 2e-3f;          // in log2 units; only widens the set that reaches the exact test
 constexpr float LOG2E = 1.4426950408889634f;
 constexpr float LN2 = 0.6931471805599453f;
+
+// ---- two-level binning: in-kernel expansion of a tile's list from its coarse bin ------------------------------
+constexpr int CB = B2S_COARSE;               // tiles per coarse-bin side
+constexpr int SCAN_PER_THREAD = 8;
+constexpr int SCAN = CTA * SCAN_PER_THREAD;  // records examined per round
+constexpr int QRING = 4096;                  // ring of pending hits (>= CTA - 1 + SCAN, power of two)
+constexpr int BINS_MAX_CH = 4;               // wider feature vectors use the classic lists (shared-memory budget)
+
+// One round: examine the records [wbase, wbase + SCAN) (wbase a multiple of 4) that also lie in [lo, hi), keep those
+// whose masks cover tile (lx, ly) of the coarse bin, and append (flat id, record position) to the ring at `qtail`
+// in list order (REVERSE: descending positions, for the backward).  Returns the number of hits (CTA-uniform).
+// s_wtot: 8 ints, alternate between two buffers on consecutive rounds (one barrier per round).
+template <bool REVERSE>
+__device__ __forceinline__ int scan_round(const uint32_t* __restrict__ recs, const int32_t* __restrict__ ids, int wbase,
+                                          int lo, int hi, unsigned lx, unsigned ly, int2* s_q, int qtail, int* s_wtot) {
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    // thread t owns 8 consecutive records (two aligned groups of 4); in REVERSE, thread 0 owns the highest 8
+    const int g0 = REVERSE ? wbase + SCAN - SCAN_PER_THREAD * (t + 1) : wbase + SCAN_PER_THREAD * t;
+    uint32_t r[SCAN_PER_THREAD];
+    int id[SCAN_PER_THREAD];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        const int g = g0 + 4 * h;
+        uint4 rv = make_uint4(0u, 0u, 0u, 0u);
+        int4 iv = make_int4(0, 0, 0, 0);
+        if (g >= 0 && g < hi && g + 4 > lo) {        // the lists are padded to a multiple of 4 entries
+            rv = __ldg(reinterpret_cast<const uint4*>(recs + g));
+            iv = __ldg(reinterpret_cast<const int4*>(ids + g));
+        }
+        r[4 * h] = rv.x; r[4 * h + 1] = rv.y; r[4 * h + 2] = rv.z; r[4 * h + 3] = rv.w;
+        id[4 * h] = iv.x; id[4 * h + 1] = iv.y; id[4 * h + 2] = iv.z; id[4 * h + 3] = iv.w;
+    }
+    unsigned hits = 0;
+#pragma unroll
+    for (int k = 0; k < SCAN_PER_THREAD; ++k) {
+        const int p = g0 + k;
+        const unsigned h = (r[k] >> (16 + lx)) & (r[k] >> (24 + ly)) & 1u;
+        hits |= ((p >= lo && p < hi) ? h : 0u) << k;
+    }
+    const int c = __popc(hits);
+    int incl = c;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const int o = __shfl_up_sync(FULL, incl, d);
+        if (lane >= d) incl += o;
+    }
+    if (lane == 31) s_wtot[warp] = incl;
+    __syncthreads();
+    int before = 0, total = 0;
+#pragma unroll
+    for (int w = 0; w < CTA / 32; ++w) {
+        const int x = s_wtot[w];
+        if (w < warp) before += x;
+        total += x;
+    }
+    int slot = qtail + before + incl - c;
+#pragma unroll
+    for (int kk = 0; kk < SCAN_PER_THREAD; ++kk) {
+        const int k = REVERSE ? SCAN_PER_THREAD - 1 - kk : kk;
+        if ((hits >> k) & 1u) {
+            s_q[slot & (QRING - 1)] = make_int2(id[k], g0 + k);
+            ++slot;
+        }
+    }
+    return total;
+}
 
 struct PixelMap {
     int px, py;
@@ -69,23 +144,30 @@ __device__ __forceinline__ void stage_splat(int g, const float* __restrict__ mea
 // =================================================================================================
 // forward
 // =================================================================================================
-template <int CH>
+template <int CH, bool BINS>
 __global__ void __launch_bounds__(CTA) composite_fwd_kernel(const b2s_composite_fwd_args a, float* __restrict__ final_T) {
     __shared__ float4 s_rec0[CTA];
     __shared__ float4 s_rec1[CTA];
     __shared__ float s_col[CTA * CH];
+    __shared__ int2 s_q[BINS ? QRING : 1];
+    __shared__ int s_wtot[2][CTA / 32];
 
     const int tile_x = blockIdx.x, tile_y = blockIdx.y, cam = blockIdx.z;
     const PixelMap pm = pixel_of_thread(tile_x, tile_y, a.width, a.height);
     float px = (float)pm.px + 0.5f, py = (float)pm.py + 0.5f;
     pin(px); pin(py);
-    const int64_t tile_id = ((int64_t)cam * a.tile_h + tile_y) * a.tile_w + tile_x;
-    const int64_t n_tiles_total = (int64_t)a.C * a.tile_h * a.tile_w;
-    const int lo = a.isect_offsets[tile_id];
-    const int hi = (tile_id == n_tiles_total - 1) ? (int)a.n_isects : a.isect_offsets[tile_id + 1];
-    const int nb = (hi - lo + CTA - 1) / CTA;
-    const bool chunked = a.chunk_index >= 0;
-    if (chunked && a.chunk_index > 0 && (hi <= lo || a.tile_done[tile_id])) return;   // state of this tile is unchanged
+    int lo, hi;
+    if (BINS) {
+        const int bins_w = (a.tile_w + CB - 1) / CB, bins_h = (a.tile_h + CB - 1) / CB;
+        const int key = (cam * bins_h + tile_y / CB) * bins_w + tile_x / CB;
+        lo = a.bin_offsets[key];
+        hi = a.bin_offsets[key + 1];
+    } else {
+        const int64_t tile_id = ((int64_t)cam * a.tile_h + tile_y) * a.tile_w + tile_x;
+        const int64_t n_tiles_total = (int64_t)a.C * a.tile_h * a.tile_w;
+        lo = a.isect_offsets[tile_id];
+        hi = (tile_id == n_tiles_total - 1) ? (int)a.n_isects : a.isect_offsets[tile_id + 1];
+    }
 
     float T = 1.f;
     float acc[CH];
@@ -93,33 +175,9 @@ __global__ void __launch_bounds__(CTA) composite_fwd_kernel(const b2s_composite_
     for (int k = 0; k < CH; ++k) acc[k] = 0.f;
     int last = 0;
     bool done = !pm.inside;
-    const int64_t pix0 = ((int64_t)cam * a.height + pm.py) * a.width + pm.px;
-    if (chunked && a.chunk_index > 0 && pm.inside) {       // resume from the state the previous chunks left
-        const float Ts = final_T[pix0];
-        done = Ts < 0.f;
-        T = fabsf(Ts);
-#pragma unroll
-        for (int k = 0; k < CH; ++k) acc[k] = a.render_colors[pix0 * CH + k];
-        last = a.last_ids[pix0];
-    }
-    const int last_tag = chunked ? (a.chunk_index << 28) : 0;
 
-    for (int b = 0; b < nb; ++b) {
-        if (__syncthreads_count(done) == CTA) break;  // also fences the previous batch's smem reads
-        const int start = lo + b * CTA;
-        const int idx = start + threadIdx.x;
-        if (idx < hi) {
-            const int g = a.flatten_ids[idx];
-            float4 r0, r1;
-            stage_splat(g, a.means2d, a.conics, a.opacities, r0, r1);
-            s_rec0[threadIdx.x] = r0;
-            s_rec1[threadIdx.x] = r1;
-#pragma unroll
-            for (int k = 0; k < CH; ++k) s_col[threadIdx.x * CH + k] = a.colors[(int64_t)g * CH + k];
-        }
-        __syncthreads();
-        if (__all_sync(FULL, done)) continue;  // early termination by warp vote
-        const int bs = min(CTA, hi - start);
+    // one batch of `bs` staged splats; `last` records s_rec1[j].w (BINS: the record position) or start + j
+    auto composite_batch = [&](int bs, int start) {
 #pragma unroll 2
         for (int j = 0; j < bs && !done; ++j) {
             const float4 r0 = s_rec0[j];
@@ -135,18 +193,67 @@ __global__ void __launch_bounds__(CTA) composite_fwd_kernel(const b2s_composite_
 #pragma unroll
             for (int k = 0; k < CH; ++k) acc[k] = fmaf(w, s_col[j * CH + k], acc[k]);
             T = nT;
-            last = last_tag | (start + j);
+            last = BINS ? __float_as_int(r1.w) : start + j;
         }
-    }
-    if (chunked) {
-        const int n_done = __syncthreads_count(done);
-        if (threadIdx.x == 0 && n_done == CTA) a.tile_done[tile_id] = 1;
+    };
+
+    if (BINS) {
+        const unsigned lx = tile_x % CB, ly = tile_y % CB;
+        int pos = lo & ~3;                       // next window of the coarse bin's list (4-aligned)
+        int qhead = 0, qcount = 0, round = 0;
+        while (true) {
+            if (__syncthreads_count(done) == CTA) break;   // also fences the previous batch's smem reads
+            bool scanned = false;
+            while (qcount < CTA && pos < hi) {
+                qcount += scan_round<false>(a.bin_recs, a.bin_ids, pos, lo, hi, lx, ly, s_q, qhead + qcount, s_wtot[round & 1]);
+                pos += SCAN;
+                ++round;
+                scanned = true;
+            }
+            if (qcount == 0) break;
+            if (scanned) __syncthreads();                  // ring writes of the last round -> staging reads
+            const int bs = min(CTA, qcount);
+            if ((int)threadIdx.x < bs) {
+                const int2 e = s_q[(qhead + threadIdx.x) & (QRING - 1)];
+                float4 r0, r1;
+                stage_splat(e.x, a.means2d, a.conics, a.opacities, r0, r1);
+                r1.w = __int_as_float(e.y);
+                s_rec0[threadIdx.x] = r0;
+                s_rec1[threadIdx.x] = r1;
+#pragma unroll
+                for (int k = 0; k < CH; ++k) s_col[threadIdx.x * CH + k] = a.colors[(int64_t)e.x * CH + k];
+            }
+            __syncthreads();
+            qhead += bs;
+            qcount -= bs;
+            if (__all_sync(FULL, done)) continue;          // early termination by warp vote
+            composite_batch(bs, 0);
+        }
+    } else {
+        const int nb = (hi - lo + CTA - 1) / CTA;
+        for (int b = 0; b < nb; ++b) {
+            if (__syncthreads_count(done) == CTA) break;  // also fences the previous batch's smem reads
+            const int start = lo + b * CTA;
+            const int idx = start + threadIdx.x;
+            if (idx < hi) {
+                const int g = a.flatten_ids[idx];
+                float4 r0, r1;
+                stage_splat(g, a.means2d, a.conics, a.opacities, r0, r1);
+                s_rec0[threadIdx.x] = r0;
+                s_rec1[threadIdx.x] = r1;
+#pragma unroll
+                for (int k = 0; k < CH; ++k) s_col[threadIdx.x * CH + k] = a.colors[(int64_t)g * CH + k];
+            }
+            __syncthreads();
+            if (__all_sync(FULL, done)) continue;  // early termination by warp vote
+            composite_batch(min(CTA, hi - start), start);
+        }
     }
     if (pm.inside) {
         const int64_t pix = ((int64_t)cam * a.height + pm.py) * a.width + pm.px;
 #pragma unroll
         for (int k = 0; k < CH; ++k)
-            a.render_colors[pix * CH + k] = (a.backgrounds && !chunked) ? acc[k] + T * a.backgrounds[cam * CH + k] : acc[k];
+            a.render_colors[pix * CH + k] = a.backgrounds ? acc[k] + T * a.backgrounds[cam * CH + k] : acc[k];
         a.render_alphas[pix] = 1.f - T;
         a.last_ids[pix] = last;
         if (final_T) final_T[pix] = done ? -T : T;    // sign bit = the pixel saturated (stopped at T_next <= 1e-4)
@@ -196,22 +303,33 @@ __device__ __forceinline__ int halving_slot(int lane, bool& owner) {
 // =================================================================================================
 // backward: replay back-to-front from the last contributor, multi-value warp reduce, one RED per warp
 // =================================================================================================
-template <int CH, bool ABS>
+template <int CH, bool ABS, bool BINS>
 __global__ void __launch_bounds__(CTA) composite_bwd_kernel(const b2s_composite_bwd_args a, const float* __restrict__ final_T) {
     constexpr int V = CH + 6 + (ABS ? 2 : 0);   // values reduced per (warp, Gaussian)
     __shared__ float4 s_rec0[CTA];
     __shared__ float4 s_rec1[CTA];
     __shared__ float s_col[CTA * CH];
+    __shared__ int s_pos[BINS ? CTA : 1];       // BINS: list position of each staged splat (descending)
+    __shared__ int2 s_q[BINS ? QRING : 1];
+    __shared__ int s_wtot[2][CTA / 32];
     __shared__ int s_max[CTA / 32];
 
     const int tile_x = blockIdx.x, tile_y = blockIdx.y, cam = blockIdx.z;
     const PixelMap pm = pixel_of_thread(tile_x, tile_y, a.width, a.height);
     float px = (float)pm.px + 0.5f, py = (float)pm.py + 0.5f;
     pin(px); pin(py);
-    const int64_t tile_id = ((int64_t)cam * a.tile_h + tile_y) * a.tile_w + tile_x;
-    const int64_t n_tiles_total = (int64_t)a.C * a.tile_h * a.tile_w;
-    const int lo = a.isect_offsets[tile_id];
-    const int hi = (tile_id == n_tiles_total - 1) ? (int)a.n_isects : a.isect_offsets[tile_id + 1];
+    int lo, hi;
+    if (BINS) {
+        const int bins_w = (a.tile_w + CB - 1) / CB, bins_h = (a.tile_h + CB - 1) / CB;
+        const int key = (cam * bins_h + tile_y / CB) * bins_w + tile_x / CB;
+        lo = a.bin_offsets[key];
+        hi = a.bin_offsets[key + 1];
+    } else {
+        const int64_t tile_id = ((int64_t)cam * a.tile_h + tile_y) * a.tile_w + tile_x;
+        const int64_t n_tiles_total = (int64_t)a.C * a.tile_h * a.tile_w;
+        lo = a.isect_offsets[tile_id];
+        hi = (tile_id == n_tiles_total - 1) ? (int)a.n_isects : a.isect_offsets[tile_id + 1];
+    }
     if (hi <= lo) return;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int64_t pix = pm.inside ? ((int64_t)cam * a.height + pm.py) * a.width + pm.px : 0;
@@ -239,14 +357,9 @@ __global__ void __launch_bounds__(CTA) composite_bwd_kernel(const b2s_composite_
     float v_bg_dot = 0.f;  // sum_k bg_k * v_out_k
 #pragma unroll
     for (int k = 0; k < CH; ++k) { v_out[k] = 0.f; S[k] = 0.f; }
-    const bool chunked = a.chunk_index >= 0;
     if (pm.inside) {
         T_final = final_T ? fabsf(final_T[pix]) : 1.f - a.render_alphas[pix];
         bin_final = a.last_ids[pix];
-        if (chunked) {      // last_ids = chunk << 28 | index into that chunk's list
-            const int last_chunk = bin_final >> 28;
-            bin_final = a.chunk_index > last_chunk ? -1 : (a.chunk_index == last_chunk ? (bin_final & ((1 << 28) - 1)) : hi - 1);
-        }
         v_alpha_out = a.v_render_alphas ? a.v_render_alphas[pix] : 0.f;
 #pragma unroll
         for (int k = 0; k < CH; ++k) {
@@ -257,11 +370,6 @@ __global__ void __launch_bounds__(CTA) composite_bwd_kernel(const b2s_composite_
         if (T_final == 1.f) bin_final = -1;
     }
     float T = T_final;
-    if (chunked && pm.inside) {   // running state left by the later chunks
-        T = a.state_T[pix];
-#pragma unroll
-        for (int k = 0; k < CH; ++k) S[k] = a.state_S[pix * CH + k];
-    }
     const float v_T_final = T_final * (v_alpha_out - v_bg_dot);   // d(loss)/d(alpha_i) picks up  v_T_final / (1 - alpha_i)
 
     int warp_final = bin_final;
@@ -274,131 +382,179 @@ __global__ void __launch_bounds__(CTA) composite_bwd_kernel(const b2s_composite_
     for (int w = 0; w < CTA / 32; ++w) cta_final = max(cta_final, s_max[w]);
     if (cta_final < lo) return;
 
-    // only [lo, cta_final] can contribute; walk it back to front in batches of 256
-    const int range_hi = min(hi, cta_final + 1);
-    const int nb = (range_hi - lo + CTA - 1) / CTA;
-    for (int b = 0; b < nb; ++b) {
-        __syncthreads();
-        const int batch_end = range_hi - 1 - b * CTA;               // highest index of this batch
-        const int bs = min(CTA, batch_end + 1 - lo);
-        const int idx = batch_end - (int)threadIdx.x;               // smem slot t holds index batch_end - t
-        if (idx >= lo) {
-            const int g = a.flatten_ids[idx];
-            float4 r0, r1;
-            stage_splat(g, a.means2d, a.conics, a.opacities, r0, r1);
-            s_rec0[threadIdx.x] = r0;
-            s_rec1[threadIdx.x] = r1;
-#pragma unroll
-            for (int k = 0; k < CH; ++k) s_col[threadIdx.x * CH + k] = a.colors[(int64_t)g * CH + k];
+    // One staged splat (smem slot t) against this thread's pixel; `mine` = the pixel takes part in it.
+    auto splat_bwd = [&](int t, bool mine) {
+        const float4 r0 = s_rec0[t];
+        const float4 r1 = s_rec1[t];
+        const float dx = r0.x - px, dy = r0.y - py;
+        const float s2 = fmaf(dx, fmaf(r1.x, dx, r1.y * dy), r1.z * dy * dy);
+        // invalid lanes run the same straight-line code with alpha = 0, vis = 0: every term vanishes
+        float vis = 0.f, alpha = 0.f;
+        if (mine && s2 >= 0.f && s2 <= r0.w) {
+            vis = ex2_approx(-s2);
+            alpha = fminf(ALPHA_MAX, r0.z * vis);
+            if (alpha < ALPHA_MIN) { alpha = 0.f; vis = 0.f; }
         }
-        __syncthreads();
-        const int t_min = pm.inside ? batch_end - bin_final : CTA;   // this pixel takes part from slot t_min on
-        for (int t = max(0, batch_end - warp_final); t < bs; ++t) {
-            const float4 r0 = s_rec0[t];
-            const float4 r1 = s_rec1[t];
-            const float dx = r0.x - px, dy = r0.y - py;
-            const float s2 = fmaf(dx, fmaf(r1.x, dx, r1.y * dy), r1.z * dy * dy);
-            // invalid lanes run the same straight-line code with alpha = 0, vis = 0: every term vanishes
-            float vis = 0.f, alpha = 0.f;
-            if (t >= t_min && s2 >= 0.f && s2 <= r0.w) {
-                vis = ex2_approx(-s2);
-                alpha = fminf(ALPHA_MAX, r0.z * vis);
-                if (alpha < ALPHA_MIN) { alpha = 0.f; vis = 0.f; }
-            }
-            if (!__any_sync(FULL, alpha > 0.f)) continue;
+        if (!__any_sync(FULL, alpha > 0.f)) return;
 
-            const float ra = rcp_approx(1.f - alpha);
-            if (alpha > 0.f) T *= ra;                               // (never trust rcp(1) == 1 over thousands of steps)
-            const float fac = alpha * T;
-            float v_alpha = v_T_final * ra;
-            float v_col[CH];
+        const float ra = rcp_approx(1.f - alpha);
+        if (alpha > 0.f) T *= ra;                               // (never trust rcp(1) == 1 over thousands of steps)
+        const float fac = alpha * T;
+        float v_alpha = v_T_final * ra;
+        float v_col[CH];
 #pragma unroll
-            for (int k = 0; k < CH; ++k) {
-                const float c = s_col[t * CH + k];
-                v_col[k] = fac * v_out[k];
-                v_alpha = fmaf(fmaf(c, T, -S[k] * ra), v_out[k], v_alpha);
-                S[k] = fmaf(c, fac, S[k]);
-            }
-            if (r0.z * vis > ALPHA_MAX) vis = 0.f;                   // clamped alpha: no gradient through sigma / opacity
-            const float v_op = vis * v_alpha;
-            const float v_s2 = -r0.z * v_op;                         // d/d(sigma)
-            // sigma = 0.5*(a dx^2 + c dy^2) + b dx dy, with (a, b, c) = (2 A, B, 2 C) / log2(e)
-            const float wx = v_s2 * dx, wy = v_s2 * dy;
-            const float v_ca = 0.5f * wx * dx, v_cb = wx * dy, v_cc = 0.5f * wy * dy;
-            const float k2 = 2.f * LN2, k1 = LN2;
-            const float v_x = v_s2 * fmaf(k2 * r1.x, dx, k1 * r1.y * dy);
-            const float v_y = v_s2 * fmaf(k1 * r1.y, dx, k2 * r1.z * dy);
+        for (int k = 0; k < CH; ++k) {
+            const float c = s_col[t * CH + k];
+            v_col[k] = fac * v_out[k];
+            v_alpha = fmaf(fmaf(c, T, -S[k] * ra), v_out[k], v_alpha);
+            S[k] = fmaf(c, fac, S[k]);
+        }
+        if (r0.z * vis > ALPHA_MAX) vis = 0.f;                   // clamped alpha: no gradient through sigma / opacity
+        const float v_op = vis * v_alpha;
+        const float v_s2 = -r0.z * v_op;                         // d/d(sigma)
+        // sigma = 0.5*(a dx^2 + c dy^2) + b dx dy, with (a, b, c) = (2 A, B, 2 C) / log2(e)
+        const float wx = v_s2 * dx, wy = v_s2 * dy;
+        const float v_ca = 0.5f * wx * dx, v_cb = wx * dy, v_cc = 0.5f * wy * dy;
+        const float k2 = 2.f * LN2, k1 = LN2;
+        const float v_x = v_s2 * fmaf(k2 * r1.x, dx, k1 * r1.y * dy);
+        const float v_y = v_s2 * fmaf(k1 * r1.y, dx, k2 * r1.z * dy);
 
-            const unsigned g = (unsigned)__float_as_int(r1.w);
-            if (V <= 9) {
-                float r8[8];
+        const unsigned g = (unsigned)__float_as_int(r1.w);
+        if (V <= 9) {
+            float r8[8];
 #pragma unroll
-                for (int k = 0; k < 8; ++k) r8[k] = 0.f;
-                r8[0] = v_x; r8[1] = v_y; r8[2] = v_ca; r8[3] = v_cb; r8[4] = v_cc;
+            for (int k = 0; k < 8; ++k) r8[k] = 0.f;
+            r8[0] = v_x; r8[1] = v_y; r8[2] = v_ca; r8[3] = v_cb; r8[4] = v_cc;
 #pragma unroll
-                for (int k = 0; k < CH && k < 3; ++k) r8[5 + k] = v_col[k];
-                if (V < 9) r8[5 + CH] = v_op;
-                float mine = halving_reduce<8>(r8, lane);
-                if (V == 9) {                      // ninth value: plain butterfly, published by lane 1
-                    const float ninth = warp_sum(v_op);
-                    if (lane == 1) mine = ninth;
-                }
-                if (slot_ptr) atomicAdd(slot_ptr + (uint64_t)g * slot_stride, mine);
-            } else if (V <= 16) {
-                float r16[16];
+            for (int k = 0; k < CH && k < 3; ++k) r8[5 + k] = v_col[k];
+            if (V < 9) r8[5 + CH] = v_op;
+            float mine_v = halving_reduce<8>(r8, lane);
+            if (V == 9) {                      // ninth value: plain butterfly, published by lane 1
+                const float ninth = warp_sum(v_op);
+                if (lane == 1) mine_v = ninth;
+            }
+            if (slot_ptr) atomicAdd(slot_ptr + (uint64_t)g * slot_stride, mine_v);
+        } else if (V <= 16) {
+            float r16[16];
 #pragma unroll
-                for (int k = 0; k < 16; ++k) r16[k] = 0.f;
-                r16[0] = v_x; r16[1] = v_y; r16[2] = v_ca; r16[3] = v_cb; r16[4] = v_cc;
+            for (int k = 0; k < 16; ++k) r16[k] = 0.f;
+            r16[0] = v_x; r16[1] = v_y; r16[2] = v_ca; r16[3] = v_cb; r16[4] = v_cc;
 #pragma unroll
-                for (int k = 0; k < CH && 5 + k < 16; ++k) r16[5 + k] = v_col[k];
-                if (5 + CH < 16) r16[5 + CH] = v_op;
-                if (ABS && 7 + CH < 16) { r16[6 + CH] = fabsf(v_x); r16[7 + CH] = fabsf(v_y); }
-                const float mine = halving_reduce<16>(r16, lane);
-                if (slot_ptr) atomicAdd(slot_ptr + (uint64_t)g * slot_stride, mine);
-            } else {                               // wide feature vectors: one butterfly per value
-                float v_ax = 0.f, v_ay = 0.f;
-                if (ABS) { v_ax = warp_sum(fabsf(v_x)); v_ay = warp_sum(fabsf(v_y)); }
+            for (int k = 0; k < CH && 5 + k < 16; ++k) r16[5 + k] = v_col[k];
+            if (5 + CH < 16) r16[5 + CH] = v_op;
+            if (ABS && 7 + CH < 16) { r16[6 + CH] = fabsf(v_x); r16[7 + CH] = fabsf(v_y); }
+            const float mine_v = halving_reduce<16>(r16, lane);
+            if (slot_ptr) atomicAdd(slot_ptr + (uint64_t)g * slot_stride, mine_v);
+        } else {                               // wide feature vectors: one butterfly per value
+            float v_ax = 0.f, v_ay = 0.f;
+            if (ABS) { v_ax = warp_sum(fabsf(v_x)); v_ay = warp_sum(fabsf(v_y)); }
 #pragma unroll
-                for (int k = 0; k < CH; ++k) v_col[k] = warp_sum(v_col[k]);
-                const float r_ca = warp_sum(v_ca), r_cb = warp_sum(v_cb), r_cc = warp_sum(v_cc);
-                const float r_x = warp_sum(v_x), r_y = warp_sum(v_y), r_op = warp_sum(v_op);
-                if (lane == 0) {
-                    const uint64_t gg = g;
+            for (int k = 0; k < CH; ++k) v_col[k] = warp_sum(v_col[k]);
+            const float r_ca = warp_sum(v_ca), r_cb = warp_sum(v_cb), r_cc = warp_sum(v_cc);
+            const float r_x = warp_sum(v_x), r_y = warp_sum(v_y), r_op = warp_sum(v_op);
+            if (lane == 0) {
+                const uint64_t gg = g;
 #pragma unroll
-                    for (int k = 0; k < CH; ++k) atomicAdd(a.v_colors + gg * CH + k, v_col[k]);
-                    atomicAdd(a.v_conics + 3 * gg, r_ca);
-                    atomicAdd(a.v_conics + 3 * gg + 1, r_cb);
-                    atomicAdd(a.v_conics + 3 * gg + 2, r_cc);
-                    atomicAdd(a.v_means2d + 2 * gg, r_x);
-                    atomicAdd(a.v_means2d + 2 * gg + 1, r_y);
-                    atomicAdd(a.v_opacities + gg, r_op);
-                    if (ABS) {
-                        atomicAdd(a.v_means2d_abs + 2 * gg, v_ax);
-                        atomicAdd(a.v_means2d_abs + 2 * gg + 1, v_ay);
-                    }
+                for (int k = 0; k < CH; ++k) atomicAdd(a.v_colors + gg * CH + k, v_col[k]);
+                atomicAdd(a.v_conics + 3 * gg, r_ca);
+                atomicAdd(a.v_conics + 3 * gg + 1, r_cb);
+                atomicAdd(a.v_conics + 3 * gg + 2, r_cc);
+                atomicAdd(a.v_means2d + 2 * gg, r_x);
+                atomicAdd(a.v_means2d + 2 * gg + 1, r_y);
+                atomicAdd(a.v_opacities + gg, r_op);
+                if (ABS) {
+                    atomicAdd(a.v_means2d_abs + 2 * gg, v_ax);
+                    atomicAdd(a.v_means2d_abs + 2 * gg + 1, v_ay);
                 }
             }
         }
-    }
-    if (chunked && pm.inside) {
-        a.state_T[pix] = T;
+    };
+
+    if (BINS) {
+        // walk the coarse bin's list back to front from the CTA's last contributor
+        const unsigned lx = tile_x % CB, ly = tile_y % CB;
+        const int range_hi = cta_final + 1;                    // records [lo, range_hi) can contribute
+        int wbase = ((range_hi + 3) & ~3) - SCAN;              // window [wbase, wbase + SCAN), walked downwards
+        int qhead = 0, qcount = 0, round = 0;
+        while (true) {
+            __syncthreads();                                   // fences the previous batch's smem reads
+            bool scanned = false;
+            while (qcount < CTA && wbase + SCAN > lo) {
+                qcount += scan_round<true>(a.bin_recs, a.bin_ids, wbase, lo, range_hi, lx, ly, s_q, qhead + qcount,
+                                           s_wtot[round & 1]);
+                wbase -= SCAN;
+                ++round;
+                scanned = true;
+            }
+            if (qcount == 0) break;
+            if (scanned) __syncthreads();
+            const int bs = min(CTA, qcount);
+            if ((int)threadIdx.x < bs) {
+                const int2 e = s_q[(qhead + threadIdx.x) & (QRING - 1)];
+                float4 r0, r1;
+                stage_splat(e.x, a.means2d, a.conics, a.opacities, r0, r1);
+                s_rec0[threadIdx.x] = r0;
+                s_rec1[threadIdx.x] = r1;
+                s_pos[threadIdx.x] = e.y;
 #pragma unroll
-        for (int k = 0; k < CH; ++k) a.state_S[pix * CH + k] = S[k];
+                for (int k = 0; k < CH; ++k) s_col[threadIdx.x * CH + k] = a.colors[(int64_t)e.x * CH + k];
+            }
+            __syncthreads();
+            qhead += bs;
+            qcount -= bs;
+            for (int t = 0; t < bs; ++t) {
+                const int p = s_pos[t];
+                if (p > warp_final) continue;                  // behind every pixel of this warp
+                splat_bwd(t, p <= bin_final);
+            }
+        }
+    } else {
+        // only [lo, cta_final] can contribute; walk it back to front in batches of 256
+        const int range_hi = min(hi, cta_final + 1);
+        const int nb = (range_hi - lo + CTA - 1) / CTA;
+        for (int b = 0; b < nb; ++b) {
+            __syncthreads();
+            const int batch_end = range_hi - 1 - b * CTA;               // highest index of this batch
+            const int bs = min(CTA, batch_end + 1 - lo);
+            const int idx = batch_end - (int)threadIdx.x;               // smem slot t holds index batch_end - t
+            if (idx >= lo) {
+                const int g = a.flatten_ids[idx];
+                float4 r0, r1;
+                stage_splat(g, a.means2d, a.conics, a.opacities, r0, r1);
+                s_rec0[threadIdx.x] = r0;
+                s_rec1[threadIdx.x] = r1;
+#pragma unroll
+                for (int k = 0; k < CH; ++k) s_col[threadIdx.x * CH + k] = a.colors[(int64_t)g * CH + k];
+            }
+            __syncthreads();
+            const int t_min = pm.inside ? batch_end - bin_final : CTA;   // this pixel takes part from slot t_min on
+            for (int t = max(0, batch_end - warp_final); t < bs; ++t) splat_bwd(t, t >= t_min);
+        }
     }
 }
 
 template <int CH>
 static int launch_fwd(const b2s_composite_fwd_args* a, float* final_T, cudaStream_t st) {
     dim3 grid(a->tile_w, a->tile_h, a->C);
-    composite_fwd_kernel<CH><<<grid, CTA, 0, st>>>(*a, final_T);
+    if (a->bin_offsets) {
+        if constexpr (CH <= BINS_MAX_CH) composite_fwd_kernel<CH, true><<<grid, CTA, 0, st>>>(*a, final_T);
+        else { set_error("composite: two-level binning supports up to %d channels", BINS_MAX_CH); return B2S_E_UNSUPPORTED; }
+    } else composite_fwd_kernel<CH, false><<<grid, CTA, 0, st>>>(*a, final_T);
     B2S_LAUNCH_CHECK();
     return 0;
 }
 template <int CH>
 static int launch_bwd(const b2s_composite_bwd_args* a, const float* final_T, cudaStream_t st) {
     dim3 grid(a->tile_w, a->tile_h, a->C);
-    if (a->v_means2d_abs) composite_bwd_kernel<CH, true><<<grid, CTA, 0, st>>>(*a, final_T);
-    else composite_bwd_kernel<CH, false><<<grid, CTA, 0, st>>>(*a, final_T);
+    if (a->bin_offsets) {
+        if constexpr (CH <= BINS_MAX_CH) {
+            if (a->v_means2d_abs) composite_bwd_kernel<CH, true, true><<<grid, CTA, 0, st>>>(*a, final_T);
+            else composite_bwd_kernel<CH, false, true><<<grid, CTA, 0, st>>>(*a, final_T);
+        } else { set_error("composite: two-level binning supports up to %d channels", BINS_MAX_CH); return B2S_E_UNSUPPORTED; }
+    } else {
+        if (a->v_means2d_abs) composite_bwd_kernel<CH, true, false><<<grid, CTA, 0, st>>>(*a, final_T);
+        else composite_bwd_kernel<CH, false, false><<<grid, CTA, 0, st>>>(*a, final_T);
+    }
     B2S_LAUNCH_CHECK();
     return 0;
 }
@@ -415,13 +571,13 @@ extern "C" int b2s_composite_fwd(const b2s_composite_fwd_args* a, b2s_stream_t s
     B2S_REQUIRE(a->C >= 0 && a->width > 0 && a->height > 0, "bad sizes");
     B2S_REQUIRE(a->tile_w == (a->width + TILE - 1) / TILE && a->tile_h == (a->height + TILE - 1) / TILE, "tile grid mismatch");
     if (a->C == 0) return 0;
-    B2S_REQUIRE(a->isect_offsets && a->render_colors && a->render_alphas && a->last_ids, "null pointer");
-    B2S_REQUIRE(a->n_isects == 0 || (a->means2d && a->conics && a->colors && a->opacities && a->flatten_ids), "null input");
+    B2S_REQUIRE((a->isect_offsets || a->bin_offsets) && a->render_colors && a->render_alphas && a->last_ids, "null pointer");
+    B2S_REQUIRE(a->n_isects == 0 || (a->means2d && a->conics && a->colors && a->opacities), "null input");
+    B2S_REQUIRE(a->n_isects == 0 || (a->bin_offsets ? (a->bin_recs && a->bin_ids) : a->flatten_ids != nullptr), "null list");
     B2S_REQUIRE(a->n_isects < 2147483647LL, "n_isects must fit int32");
-    if (a->chunk_index >= 0) {
-        B2S_REQUIRE(a->chunk_index < 8 && a->n_isects < (1LL << 28), "chunked: at most 8 chunks of < 2^28 intersections");
-        B2S_REQUIRE(a->tile_done && a->final_T, "chunked: tile_done and final_T are required");
-    }
+    if (a->bin_offsets)
+        B2S_REQUIRE(((reinterpret_cast<uintptr_t>(a->bin_recs) | reinterpret_cast<uintptr_t>(a->bin_ids)) & 15u) == 0,
+                    "bin_recs / bin_ids must be 16-byte aligned");
     cudaStream_t st = (cudaStream_t)stream;
 #define CALL_FWD(CHN) (launch_fwd<CHN>(a, a->final_T, st))
     switch (a->channels) {
@@ -442,10 +598,10 @@ extern "C" int b2s_composite_bwd(const b2s_composite_bwd_args* a, b2s_stream_t s
     B2S_REQUIRE(a->tile_size == TILE, "tile_size must be 16");
     B2S_REQUIRE(a->C >= 0 && a->width > 0 && a->height > 0, "bad sizes");
     if (a->C == 0 || a->n_isects == 0) return 0;
-    B2S_REQUIRE(a->isect_offsets && a->flatten_ids && a->means2d && a->conics && a->colors && a->opacities, "null input");
+    B2S_REQUIRE(a->means2d && a->conics && a->colors && a->opacities, "null input");
+    B2S_REQUIRE(a->bin_offsets ? (a->bin_recs && a->bin_ids) : (a->isect_offsets && a->flatten_ids), "null list");
     B2S_REQUIRE(a->last_ids && (a->final_T || a->render_alphas), "forward state missing");
     B2S_REQUIRE(a->v_means2d && a->v_conics && a->v_colors && a->v_opacities, "null gradient output");
-    if (a->chunk_index >= 0) B2S_REQUIRE(a->state_T && a->state_S && a->final_T, "chunked: state_T, state_S, final_T are required");
     cudaStream_t st = (cudaStream_t)stream;
 #define CALL_BWD(CHN) (launch_bwd<CHN>(a, a->final_T, st))
     switch (a->channels) {

@@ -119,7 +119,7 @@ __global__ void __launch_bounds__(FWD_THREADS) project_fwd_kernel(const b2s_proj
     covar_from_rot_scale(R, s, M, S);
 
     unsigned long long vis = 0ull;
-    int my_tiles = 0;
+    int my_tiles = 0, my_coarse = 0;
     for (int c = 0; c < a.C; ++c) {
         ProjOut o;
         project_one(cams[c], mean, S, W, H, a.eps2d, a.near_plane, a.far_plane, a.radius_clip, o, nullptr);
@@ -137,6 +137,9 @@ __global__ void __launch_bounds__(FWD_THREADS) project_fwd_kernel(const b2s_proj
                 int x0, y0, x1, y1;
                 tile_rect(o.x2d, o.y2d, o.radius, (float)a.tile_size, a.tile_w, a.tile_h, x0, y0, x1, y1);
                 cnt = (x1 - x0) * (y1 - y0);
+                if (cnt > 0)
+                    my_coarse += (((x1 + B2S_COARSE - 1) / B2S_COARSE) - x0 / B2S_COARSE) *
+                                 (((y1 + B2S_COARSE - 1) / B2S_COARSE) - y0 / B2S_COARSE);
             }
             a.tiles_per_gauss[i] = cnt;
             my_tiles += cnt;
@@ -147,23 +150,24 @@ __global__ void __launch_bounds__(FWD_THREADS) project_fwd_kernel(const b2s_proj
     }
 
     if (a.total_isects) {
-        // The data-dependent sizes the host reads: sum of tile counts and number of visible rows.  One atomic per
-        // CTA, spread over B2S_TOTAL_SLOTS counter pairs (same-address atomics serialise in L2: with one per warp
-        // they cost 0.3 ms at 5.8 M Gaussians); the host sums the slots.
-        __shared__ int s_tot[2][FWD_THREADS / 32];
-        int wsum = my_tiles, vcount = __popcll(vis);
+        // The data-dependent sizes the host reads: sum of tile counts, number of visible rows, number of coarse-bin
+        // records.  One atomic per CTA and counter, spread over B2S_TOTAL_SLOTS counter rows (same-address atomics
+        // serialise in L2: with one per warp they cost 0.3 ms at 5.8 M Gaussians); the host sums the slots.
+        __shared__ int s_tot[3][FWD_THREADS / 32];
+        int wsum = my_tiles, vcount = __popcll(vis), csum = my_coarse;
 #pragma unroll
         for (int d = 16; d > 0; d >>= 1) {
             wsum += __shfl_xor_sync(FULL, wsum, d);
             vcount += __shfl_xor_sync(FULL, vcount, d);
+            csum += __shfl_xor_sync(FULL, csum, d);
         }
-        if (lane == 0) { s_tot[0][warp] = wsum; s_tot[1][warp] = vcount; }
+        if (lane == 0) { s_tot[0][warp] = wsum; s_tot[1][warp] = vcount; s_tot[2][warp] = csum; }
         __syncthreads();
-        if (threadIdx.x < 2) {
+        if (threadIdx.x < 3) {
             int tsum = 0;
 #pragma unroll
             for (int w = 0; w < FWD_THREADS / 32; ++w) tsum += s_tot[threadIdx.x][w];
-            if (tsum) atomicAdd(reinterpret_cast<unsigned long long*>(a.total_isects) + 2 * (blockIdx.x % B2S_TOTAL_SLOTS) + threadIdx.x,
+            if (tsum) atomicAdd(reinterpret_cast<unsigned long long*>(a.total_isects) + 4 * (blockIdx.x % B2S_TOTAL_SLOTS) + threadIdx.x,
                                 (unsigned long long)tsum);
         }
     }
@@ -223,7 +227,12 @@ __global__ void __launch_bounds__(SHB_THREADS, 4) sh_bwd_fused_kernel(const b2s_
     if (live)
         for (int c = 0; c < a.C; ++c) {
             const int64_t i = (int64_t)c * a.N + n;
-            if (a.touched ? (a.touched[i] != 0) : (__ldg(a.radii + i) > 0)) vis |= 1ull << c;
+            if (__ldg(a.radii + i) <= 0) continue;
+            if (a.v_colors) {   // a zero colour cotangent (occluded row) contributes exactly nothing: skip its 12K bytes
+                const float v0 = __ldg(a.v_colors + 3 * i), v1 = __ldg(a.v_colors + 3 * i + 1), v2 = __ldg(a.v_colors + 3 * i + 2);
+                if (v0 == 0.f && v1 == 0.f && v2 == 0.f) continue;
+            }
+            vis |= 1ull << c;
         }
 
     const int K = (a.sh_degree + 1) * (a.sh_degree + 1);
@@ -314,17 +323,26 @@ __global__ void __launch_bounds__(BWD_THREADS) project_bwd_kernel(const b2s_proj
 
     const int64_t n = (int64_t)blockIdx.x * BWD_THREADS + threadIdx.x;
     if (n >= a.N) return;
-    if (a.touched && !a.accumulate) {      // occluded in every camera: all gradients are zero, skip the parameter loads
-        bool any_t = false;
-        for (int c = 0; c < a.C; ++c) any_t |= a.touched[(int64_t)c * a.N + n] != 0;
-        if (!any_t) {
+    if (!a.accumulate) {
+        // Rows that are culled, or whose cotangents are all exactly zero (occluded: compositing never reached them),
+        // have zero gradients: write the zeros and skip the parameter loads and the arithmetic.
+        bool live = false;
+        for (int c = 0; c < a.C && !live; ++c) {
+            const int64_t i = (int64_t)c * a.N + n;
+            if (__ldg(a.radii + i) <= 0) continue;
+            if (a.v_means2d) { const float2 v = __ldg(reinterpret_cast<const float2*>(a.v_means2d) + i); live |= (v.x != 0.f) | (v.y != 0.f); }
+            if (a.v_conics) live |= (__ldg(a.v_conics + 3 * i) != 0.f) | (__ldg(a.v_conics + 3 * i + 1) != 0.f) | (__ldg(a.v_conics + 3 * i + 2) != 0.f);
+            if (a.v_opacities_out) live |= __ldg(a.v_opacities_out + i) != 0.f;
+            if (a.v_depths) live |= __ldg(a.v_depths + i) != 0.f;
+            if (a.v_compensations) live |= __ldg(a.v_compensations + i) != 0.f;
+        }
+        if (!live) {
             for (int k = 0; k < 3; ++k) { if (!MEANS_ACC) a.v_means[3 * n + k] = 0.f; a.v_scales[3 * n + k] = 0.f; }
             reinterpret_cast<float4*>(a.v_quats)[n] = make_float4(0.f, 0.f, 0.f, 0.f);
             if (a.v_opacities) a.v_opacities[n] = 0.f;
             return;
         }
     }
-
     float mean[3], q[4], s[3];
     mean[0] = __ldg(a.means + 3 * n); mean[1] = __ldg(a.means + 3 * n + 1); mean[2] = __ldg(a.means + 3 * n + 2);
     {
@@ -344,7 +362,7 @@ __global__ void __launch_bounds__(BWD_THREADS) project_bwd_kernel(const b2s_proj
     bool any = false;
     for (int c = 0; c < a.C; ++c) {
         const int64_t i = (int64_t)c * a.N + n;
-        if (a.touched ? (a.touched[i] == 0) : (__ldg(a.radii + i) <= 0)) continue;   // the forward's decision is authoritative
+        if (__ldg(a.radii + i) <= 0) continue;   // the forward's decision is authoritative
         ProjMid mid;
         project_mid_fast(cams[c], mean, S, a.eps2d, mid);
         if (!(mid.det > 0.f)) continue;

@@ -345,7 +345,7 @@ def rasterization_distributed(means, quats, scales, opacities, colors, viewmats,
     # ---- local shard projected into every camera (one kernel; SH coefficients read once) ----------------------
     antialiased = rasterize_mode == "antialiased"
     fused_sh = sh_degree is not None
-    radii, means2d, depths, conics, _comps, opac, sh_cols, tiles, _dk, _ri, _tot, _tch = ops._ProjectFused.apply(
+    radii, means2d, depths, conics, _comps, opac, sh_cols, tiles, _dk, _ri, _tot = ops._ProjectFused.apply(
         means, quats, scales, opacities, colors if fused_sh else None, viewmats_all, Ks_all, None, width, height,
         float(eps2d), float(near_plane), float(far_plane), float(radius_clip), antialiased, False,
         int(sh_degree) if fused_sh else 0, tile_size)
@@ -366,19 +366,38 @@ def rasterization_distributed(means, quats, scales, opacities, colors, viewmats,
         means2d, depths, conics, opac, cols, radii, tiles, C_local, n_world, group)
 
     # ---- own cameras: binning + compositing -------------------------------------------------------------------
-    flatten_ids, isect_offsets, make_isect_ids = ops.bin_depth_first(
-        means2d_m, radii_m, depths_m, tiles_m, tile_size, tw, th, C_local, camera_ids=cam_local)
-    render_colors, render_alphas = ops.rasterize_to_pixels(
-        means2d_m, conics_m, cols_m, opac_m, width, height, tile_size, isect_offsets, flatten_ids,
-        backgrounds=backgrounds, packed=True, absgrad=absgrad)
-    if render_mode in ("ED", "RGB+ED"):
-        render_colors = torch.cat(
-            [render_colors[..., :-1], render_colors[..., -1:] / render_alphas.clamp(min=1e-10)], dim=-1)
+    from .rendering import _use_coarse_bins
     meta = ops.LazyMeta({
         "camera_ids": cam_local, "gaussian_ids": gauss_global, "radii": radii_m, "means2d": means2d_m,
         "depths": depths_m, "conics": conics_m, "opacities": opac_m, "tile_width": tw, "tile_height": th,
-        "tiles_per_gauss": tiles_m, "flatten_ids": flatten_ids, "isect_offsets": isect_offsets, "width": width,
-        "height": height, "tile_size": tile_size, "n_cameras": C_local,
+        "tiles_per_gauss": tiles_m, "width": width, "height": height, "tile_size": tile_size, "n_cameras": C_local,
     })
-    meta.set_lazy("isect_ids", make_isect_ids)
+    if _use_coarse_bins() and ops.coarse_bins_supported(C_local, tw, th, ch):
+        bins = ops.bin_coarse(means2d_m, radii_m, depths_m, tile_size, tw, th, C_local, camera_ids=cam_local)
+        render_colors, render_alphas = ops.rasterize_to_pixels(
+            means2d_m, conics_m, cols_m, opac_m, width, height, tile_size, None, None,
+            backgrounds=backgrounds, packed=True, absgrad=absgrad, bins=bins, n_cameras=C_local)
+        cache = {}
+
+        def lists():
+            if not cache:
+                flat, off, mk = ops.bin_depth_first(means2d_m.detach(), radii_m, depths_m.detach(), tiles_m, tile_size, tw, th,
+                                                    C_local, camera_ids=cam_local, sorted_ids=bins.sorted_ids)
+                cache.update(flat=flat, off=off, mk=mk)
+            return cache
+
+        meta.set_lazy("flatten_ids", lambda: lists()["flat"])
+        meta.set_lazy("isect_offsets", lambda: lists()["off"])
+        meta.set_lazy("isect_ids", lambda: lists()["mk"]())
+    else:
+        flatten_ids, isect_offsets, make_isect_ids = ops.bin_depth_first(
+            means2d_m, radii_m, depths_m, tiles_m, tile_size, tw, th, C_local, camera_ids=cam_local)
+        render_colors, render_alphas = ops.rasterize_to_pixels(
+            means2d_m, conics_m, cols_m, opac_m, width, height, tile_size, isect_offsets, flatten_ids,
+            backgrounds=backgrounds, packed=True, absgrad=absgrad)
+        meta["flatten_ids"], meta["isect_offsets"] = flatten_ids, isect_offsets
+        meta.set_lazy("isect_ids", make_isect_ids)
+    if render_mode in ("ED", "RGB+ED"):
+        render_colors = torch.cat(
+            [render_colors[..., :-1], render_colors[..., -1:] / render_alphas.clamp(min=1e-10)], dim=-1)
     return render_colors, render_alphas, meta

@@ -85,8 +85,7 @@ class _ProjectFused(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, means, quats, scales, opacities, sh_coeffs, viewmats, Ks, campos, width, height, eps2d,
-                near_plane, far_plane, radius_clip, antialiased, calc_compensations, sh_degree, tile_size,
-                with_touched=False):
+                near_plane, far_plane, radius_clip, antialiased, calc_compensations, sh_degree, tile_size):
         dev = L.require_cuda(means, quats, scales, viewmats, Ks)
         means, quats, scales = f32c(means), f32c(quats), f32c(scales)
         opacities, sh_coeffs = f32c(opacities), f32c(sh_coeffs)
@@ -110,7 +109,7 @@ class _ProjectFused(torch.autograd.Function):
         tiles = torch.empty(C, N, dtype=torch.int32, **o) if tile_size else None
         dkeys = torch.empty(C, N, dtype=torch.int32, **o) if tile_size else None     # uint32 bit patterns
         rowids = torch.empty(C, N, dtype=torch.int32, **o) if tile_size else None
-        total = torch.zeros(32, 2, dtype=torch.int64, **o) if tile_size else None   # B2S_TOTAL_SLOTS x [sum of tiles, visible rows]
+        total = torch.zeros(32, 4, dtype=torch.int64, **o) if tile_size else None   # B2S_TOTAL_SLOTS x [tiles, visible rows, coarse records, -]
         tw = (width + tile_size - 1) // tile_size if tile_size else 0
         th = (height + tile_size - 1) // tile_size if tile_size else 0
         lib = L.lib()
@@ -135,23 +134,18 @@ class _ProjectFused(torch.autograd.Function):
                 raise NotImplementedError("more than 64 cameras per call with fused binning keys")
             with _stage("project_fwd"):
                 check(lib.b2s_project_fwd(ctypes.byref(a), st), "b2s_project_fwd")
-        # `touched` (rows that emit an intersection) is filled in by the occlusion-aware renderer downstream; the
-        # backward then skips every other row, whose cotangents are known to be zero
-        touched = torch.zeros(C, N, dtype=torch.uint8, **o) if with_touched else None
-        ctx.save_for_backward(means, quats, scales, opacities, sh_coeffs, viewmats, Ks, campos, radii, touched)
+        ctx.save_for_backward(means, quats, scales, opacities, sh_coeffs, viewmats, Ks, campos, radii)
         ctx.cfg = (width, height, eps2d, near_plane, far_plane, radius_clip, bool(antialiased), sh_degree)
         ctx.set_materialize_grads(False)
         ctx.mark_non_differentiable(radii)
         if tiles is not None:
             ctx.mark_non_differentiable(tiles, dkeys, rowids, total)
-        if touched is not None:
-            ctx.mark_non_differentiable(touched)
-        return radii, means2d, depths, conics, comps, opac_out, colors, tiles, dkeys, rowids, total, touched
+        return radii, means2d, depths, conics, comps, opac_out, colors, tiles, dkeys, rowids, total
 
     @staticmethod
     def backward(ctx, _v_radii, v_means2d, v_depths, v_conics, v_comps, v_opac_out, v_colors, _v_tiles=None, _v_keys=None,
-                 _v_rows=None, _v_total=None, _v_touched=None):
-        means, quats, scales, opacities, sh_coeffs, viewmats, Ks, campos, radii, touched = ctx.saved_tensors
+                 _v_rows=None, _v_total=None):
+        means, quats, scales, opacities, sh_coeffs, viewmats, Ks, campos, radii = ctx.saved_tensors
         width, height, eps2d, near_plane, far_plane, radius_clip, antialiased, sh_degree = ctx.cfg
         if ctx.needs_input_grad[5] or ctx.needs_input_grad[6]:
             raise NotImplementedError("gradients w.r.t. viewmats / Ks are not implemented")
@@ -186,10 +180,10 @@ class _ProjectFused(torch.autograd.Function):
                 v_compensations=sl(v_comps, c0, c1), v_opacities_out=sl(v_opac_out, c0, c1),
                 v_colors=sl(v_colors, c0, c1), accumulate=int(c0 > 0),
                 v_means=ptr(v_means), v_quats=ptr(v_quats), v_scales=ptr(v_scales), v_opacities=ptr(v_opac),
-                v_sh_coeffs=ptr(v_sh), touched=ptr(touched[c0:c1]) if touched is not None else None, stages=0)
+                v_sh_coeffs=ptr(v_sh), stages=0)
             with _stage("project_bwd"):
                 check(lib.b2s_project_bwd(ctypes.byref(a), st), "b2s_project_bwd")
-        return (v_means, v_quats, v_scales, v_opac, v_sh) + (None,) * 14
+        return (v_means, v_quats, v_scales, v_opac, v_sh) + (None,) * 13
 
 
 def fully_fused_projection(
@@ -483,7 +477,7 @@ def bin_depth_first(means2d: Tensor, radii: Tensor, depths: Tensor, tiles_per_ga
             check(lib.b2s_depth_order(M, ptr(depth_keys), ptr(row_ids), ptr(sorted_ids), ptr(ws), ws.numel(), st), "b2s_depth_order")
     # The one host sync of a forward (sizes the per-intersection buffers).  The depth sort is already
     # enqueued, so the GPU keeps working while the host waits for the count that stage 1 produced.
-    n_isects = int(total_isects.reshape(-1, 2)[:, 0].sum().item()) if total_isects.numel() > 1 else int(total_isects.item())
+    n_isects = int(total_isects.reshape(-1, 4)[:, 0].sum().item()) if total_isects.numel() > 1 else int(total_isects.item())
     if n_isects >= 2 ** 31:
         raise B2SError(f"n_isects = {n_isects} does not fit the int32 offsets of the API")
     key_bytes = int(lib.b2s_tile_key_bytes(C, tile_width, tile_height))
@@ -518,161 +512,73 @@ def isect_offset_encode(isect_ids: Tensor, n_cameras: int, tile_width: int, tile
 
 
 # ======================================================================================
-# occlusion-aware chunked binning + compositing (csrc/chunked.cu)
+# two-level binning (what rasterization() runs; include/b2s.h "Two-level binning")
 # ======================================================================================
-CHUNK_FRACTIONS = (0.03, 0.10, 0.30, 1.0)   # cumulative fractions of the visible rows, in depth order
+COARSE = 8   # B2S_COARSE: tiles per coarse-bin side
 
 
-class _RenderChunked(torch.autograd.Function):
-    """Depth order -> [expand into open tiles -> tile sort -> composite, carrying pixel state] per chunk.
-    Same result as binning everything and compositing once; intersections behind saturated tiles are never
-    generated, SH colour is evaluated only for rows that emit, and ``touched`` bounds the backward."""
+def coarse_bins_supported(n_cameras: int, tile_width: int, tile_height: int, channels: int) -> bool:
+    bw, bh = (tile_width + COARSE - 1) // COARSE, (tile_height + COARSE - 1) // COARSE
+    return n_cameras * bw * bh <= 65536 and channels in (1, 2, 3, 4)
 
-    @staticmethod
-    def forward(ctx, means2d, conics, opac, depths, means, sh_coeffs, colors_in, viewmats, backgrounds, radii, tiles,
-                depth_keys, row_ids, totals, touched, width, height, tile_size, sh_degree, with_depth, absgrad):
-        dev = L.require_cuda(means2d, conics, opac, radii)
-        lib, st = L.lib(), L.stream_ptr(dev)
-        C, N = radii.shape
-        M = C * N
-        tw, th = (width + tile_size - 1) // tile_size, (height + tile_size - 1) // tile_size
-        means2d, conics, opac, depths = f32c(means2d), f32c(conics), f32c(opac), f32c(depths)
-        means, sh_coeffs, viewmats, backgrounds = f32c(means), f32c(sh_coeffs), f32c(viewmats), f32c(backgrounds)
-        radii = radii.contiguous()
-        lazy_sh = sh_coeffs is not None
-        ch = (4 if with_depth else 3) if lazy_sh else colors_in.shape[-1]
-        if ch not in _CHANNELS:
-            raise B2SError("chunked rendering: channel count must be one of " + str(_CHANNELS))
-        colors = torch.empty(M, ch, device=dev) if lazy_sh else f32c(colors_in).reshape(M, ch)
 
-        sorted_ids = torch.empty(max(M, 1), dtype=torch.int32, device=dev)
-        ws = _ws(lib.b2s_depth_order_workspace_bytes(M), dev)
-        with _stage("depth_order"):
-            check(lib.b2s_depth_order(M, ptr(depth_keys), ptr(row_ids), ptr(sorted_ids), ptr(ws), ws.numel(), st), "b2s_depth_order")
-        n_total, n_vis = (int(v) for v in totals.sum(dim=0).tolist())     # host sync #1 (the depth sort is already enqueued)
-        if n_total >= 2 ** 28:
-            raise B2SError("chunked rendering handles < 2^28 intersections per frame")
+class CoarseBins:
+    """Depth-ordered rows binned into 8x8-tile coarse bins; the compositing kernels expand per-tile lists from it."""
+    __slots__ = ("recs", "ids", "offsets", "sorted_ids", "n_records", "n_isects")
 
-        tile_done = torch.zeros(C * th * tw, dtype=torch.uint8, device=dev)
-        render = torch.empty(C, height, width, ch, device=dev)
-        alphas = torch.empty(C, height, width, 1, device=dev)
-        last_ids = torch.empty(C, height, width, dtype=torch.int32, device=dev)
-        final_T = torch.empty(C, height, width, device=dev)
-        keys_u = torch.empty(max(n_total, 1), dtype=torch.int32, device=dev)
-        vals_u = torch.empty(max(n_total, 1), dtype=torch.int32, device=dev)
-        n_dev = torch.empty(1, dtype=torch.int64, device=dev)
+    def __init__(self, recs, ids, offsets, sorted_ids, n_records, n_isects):
+        self.recs, self.ids, self.offsets, self.sorted_ids = recs, ids, offsets, sorted_ids
+        self.n_records, self.n_isects = n_records, n_isects
 
-        bounds = [0] + [min(n_vis, int(round(f * n_vis))) for f in CHUNK_FRACTIONS]
-        chunks = []
-        for ci in range(len(CHUNK_FRACTIONS)):
-            j0, j1 = bounds[ci], bounds[ci + 1]
-            k = len(chunks)
-            if j1 <= j0 and not (ci == len(CHUNK_FRACTIONS) - 1 and k == 0):
-                continue
-            wse = _ws(lib.b2s_chunk_expand_workspace_bytes(max(j1 - j0, 1)), dev)
-            a = L.ChunkExpandArgs(
-                N=N, C=C, j0=j0, j1=j1, sorted_ids=ptr(sorted_ids), means2d=ptr(means2d), radii=ptr(radii), depths=ptr(depths),
-                tile_size=tile_size, tile_w=tw, tile_h=th, tile_done=ptr(tile_done) if k > 0 else None, means=ptr(means),
-                sh_coeffs=ptr(sh_coeffs), viewmats=ptr(viewmats), sh_degree=int(sh_degree) if lazy_sh else 0,
-                sh_stride_k=sh_coeffs.shape[1] if lazy_sh else 0, color_channels=ch, colors=ptr(colors) if lazy_sh else None,
-                touched=ptr(touched), tile_keys=ptr(keys_u), vals=ptr(vals_u), capacity=max(n_total, 1), n_out=ptr(n_dev),
-                workspace=ptr(wse), workspace_bytes=wse.numel())
-            with _stage("chunk_expand"):
-                check(lib.b2s_chunk_expand(ctypes.byref(a), st), "b2s_chunk_expand")
-            n_c = int(n_dev.item())                             # host sync per chunk: sizes the sort
-            if n_c == 0 and k > 0:
-                continue
-            keys_s = torch.empty(max(n_c, 1), dtype=torch.int32, device=dev)
-            flat_c = torch.empty(max(n_c, 1), dtype=torch.int32, device=dev)
-            off_c = torch.empty(C, th, tw, dtype=torch.int32, device=dev)
-            wss = _ws(lib.b2s_tile_sort_workspace_bytes(n_c), dev)
-            with _stage("tile_sort"):
-                check(lib.b2s_tile_sort(n_c, C, tw, th, ptr(keys_u), ptr(vals_u), ptr(keys_s), ptr(flat_c), ptr(off_c), ptr(wss),
-                                        wss.numel(), st), "b2s_tile_sort")
-            fa = L.CompositeFwdArgs(
-                C=C, width=width, height=height, tile_size=tile_size, tile_w=tw, tile_h=th, channels=ch, n_isects=n_c,
-                means2d=ptr(means2d), conics=ptr(conics), colors=ptr(colors), opacities=ptr(opac), backgrounds=None,
-                isect_offsets=ptr(off_c), flatten_ids=ptr(flat_c), render_colors=ptr(render), render_alphas=ptr(alphas),
-                last_ids=ptr(last_ids), final_T=ptr(final_T), chunk_index=k, tile_done=ptr(tile_done))
-            with _stage("composite_fwd"):
-                check(lib.b2s_composite_fwd(ctypes.byref(fa), st), "b2s_composite_fwd")
-            chunks.append((flat_c, off_c, n_c))
 
-        out = render
-        if backgrounds is not None:
-            out = render + final_T.abs()[..., None] * backgrounds[:, None, None, :]
-        ctx.save_for_backward(means2d, conics, colors, opac, backgrounds, alphas, last_ids, final_T, means, sh_coeffs,
-                              viewmats, radii, touched, *[t for c in chunks for t in c[:2]])
-        ctx.cfg = (width, height, tile_size, sh_degree, with_depth, absgrad, lazy_sh, ch, [c[2] for c in chunks], C, N)
-        ctx.set_materialize_grads(False)
-        ctx.mark_non_differentiable(sorted_ids)
-        return out, alphas, sorted_ids
-
-    @staticmethod
-    def backward(ctx, v_render, v_alphas, _v_sorted=None):
-        saved = ctx.saved_tensors
-        (means2d, conics, colors, opac, backgrounds, alphas, last_ids, final_T, means, sh_coeffs, viewmats, radii,
-         touched) = saved[:13]
-        chunk_t = saved[13:]
-        width, height, tile_size, sh_degree, with_depth, absgrad, lazy_sh, ch, n_cs, C, N = ctx.cfg
-        dev = means2d.device
-        lib, st = L.lib(), L.stream_ptr(dev)
-        M = C * N
-        tw, th = (width + tile_size - 1) // tile_size, (height + tile_size - 1) // tile_size
-        v_render = f32c(v_render) if v_render is not None else torch.zeros(C, height, width, ch, device=dev)
-        v_alphas = f32c(v_alphas)
-        widths = [2, 3, ch, 1] + ([2] if absgrad else [])
-        slab = torch.zeros(M * sum(widths), dtype=torch.float32, device=dev)
-        parts, o = [], 0
-        for wd in widths:
-            parts.append(slab[o:o + M * wd])
-            o += M * wd
-        v_means2d, v_conics = parts[0].view(means2d.shape), parts[1].view(conics.shape)
-        v_colors, v_opac = parts[2].view(M, ch), parts[3].view(opac.shape)
-        v_abs = parts[4].view(means2d.shape) if absgrad else None
-        state_T = final_T.abs()
-        state_S = torch.zeros(C, height, width, ch, device=dev)
-        for k in reversed(range(len(n_cs))):
-            flat_c, off_c = chunk_t[2 * k], chunk_t[2 * k + 1]
-            if n_cs[k] == 0:
-                continue
-            a = L.CompositeBwdArgs(
-                C=C, width=width, height=height, tile_size=tile_size, tile_w=tw, tile_h=th, channels=ch, n_isects=n_cs[k],
-                means2d=ptr(means2d), conics=ptr(conics), colors=ptr(colors), opacities=ptr(opac), backgrounds=ptr(backgrounds),
-                isect_offsets=ptr(off_c), flatten_ids=ptr(flat_c), render_alphas=ptr(alphas), last_ids=ptr(last_ids),
-                final_T=ptr(final_T), v_render_colors=ptr(v_render), v_render_alphas=ptr(v_alphas), v_means2d=ptr(v_means2d),
-                v_means2d_abs=ptr(v_abs), v_conics=ptr(v_conics), v_colors=ptr(v_colors), v_opacities=ptr(v_opac),
-                chunk_index=k, state_T=ptr(state_T), state_S=ptr(state_S))
-            with _stage("composite_bwd"):
-                check(lib.b2s_composite_bwd(ctypes.byref(a), st), "b2s_composite_bwd")
-        if absgrad:
-            means2d.absgrad = v_abs
-        v_bg = None
-        if backgrounds is not None and ctx.needs_input_grad[8]:
-            v_bg = (v_render * final_T.abs()[..., None]).sum(dim=(1, 2))
-        v_depths = v_means = v_sh = v_colors_in = None
-        if lazy_sh:
-            v_rgb = v_colors if ch == 3 else v_colors[:, :3].contiguous()
-            if with_depth:
-                v_depths = v_colors[:, 3].reshape(C, N)
-            K = (sh_degree + 1) ** 2
-            v_sh = torch.empty_like(sh_coeffs) if K == sh_coeffs.shape[1] else torch.zeros_like(sh_coeffs)
-            v_means = torch.empty_like(means)
-            tch = touched.view(C, N)
-            for c0 in range(0, C, MAX_CAMS):
-                c1 = min(C, c0 + MAX_CAMS)
-                pa = L.ProjectBwdArgs(
-                    N=N, C=c1 - c0, means=ptr(means), quats=ptr(means), scales=ptr(means), opacities=None,
-                    viewmats=ptr(viewmats[c0:c1]), Ks=ptr(viewmats[c0:c1]), width=width, height=height, eps2d=0.3, near_plane=0.01,
-                    far_plane=1e10, radius_clip=0.0, antialiased=0, sh_coeffs=ptr(sh_coeffs), campos=None,
-                    sh_degree=int(sh_degree), sh_stride_k=sh_coeffs.shape[1], radii=ptr(radii[c0:c1]),
-                    v_colors=ptr(v_rgb.view(C, N, 3)[c0:c1]), accumulate=int(c0 > 0), v_means=ptr(v_means), v_sh_coeffs=ptr(v_sh),
-                    touched=ptr(tch[c0:c1]), stages=1)
-                with _stage("sh_bwd"):
-                    check(lib.b2s_project_bwd(ctypes.byref(pa), st), "b2s_project_bwd(sh)")
-        else:
-            v_colors_in = v_colors.view(C, N, ch)
-        return (v_means2d, v_conics, v_opac, v_depths, v_means, v_sh, v_colors_in, None, v_bg) + (None,) * 12
+@torch.no_grad()
+def bin_coarse(means2d: Tensor, radii: Tensor, depths: Tensor, tile_size: int, tile_width: int, tile_height: int,
+               n_cameras: int, camera_ids: Optional[Tensor] = None, depth_keys: Optional[Tensor] = None,
+               row_ids: Optional[Tensor] = None, totals: Optional[Tensor] = None) -> CoarseBins:
+    """Depth sort of the rows + coarse binning (b2s_depth_order, b2s_coarse_bin).  ``depth_keys`` / ``row_ids`` /
+    ``totals`` ([B2S_TOTAL_SLOTS,4] counters) come from stage 1 when it ran fused with the same rows."""
+    dev = L.require_cuda(means2d, radii, depths)
+    packed = camera_ids is not None
+    M = radii.numel()
+    N = 0 if packed else means2d.shape[1]
+    C = int(n_cameras)
+    means2d, depths = f32c(means2d), f32c(depths)
+    radii = radii.contiguous()
+    cam = camera_ids.contiguous().to(torch.int64) if packed else None
+    lib, st = L.lib(), L.stream_ptr(dev)
+    if depth_keys is None or row_ids is None:
+        depth_keys = torch.empty(max(M, 1), dtype=torch.int32, device=dev)
+        row_ids = torch.empty(max(M, 1), dtype=torch.int32, device=dev)
+        with _stage("isect_depth_keys"):
+            check(lib.b2s_isect_depth_keys(M, ptr(depths), ptr(radii), ptr(depth_keys), ptr(row_ids), st), "b2s_isect_depth_keys")
+    if totals is None:
+        tot = torch.zeros(1, dtype=torch.int64, device=dev)
+        with _stage("coarse_count"):
+            check(lib.b2s_coarse_count(M, ptr(means2d), ptr(radii), tile_size, tile_width, tile_height, ptr(tot), st),
+                  "b2s_coarse_count")
+    sorted_ids = torch.empty(max(M, 1), dtype=torch.int32, device=dev)
+    ws = _ws(lib.b2s_depth_order_workspace_bytes(M), dev)
+    with _stage("depth_order"):
+        check(lib.b2s_depth_order(M, ptr(depth_keys), ptr(row_ids), ptr(sorted_ids), ptr(ws), ws.numel(), st), "b2s_depth_order")
+    # The one host sync of a forward (sizes the record buffers).  The depth sort is already enqueued, so the GPU
+    # keeps working while the host waits for the counts that stage 1 produced.
+    if totals is not None:
+        sums = totals.sum(dim=0).tolist()
+        n_isects, n_records = int(sums[0]), int(sums[2])
+    else:
+        n_isects, n_records = None, int(tot.item())
+    if n_records >= 2 ** 31:
+        raise B2SError(f"{n_records} coarse-bin records do not fit the int32 offsets of the API")
+    bw, bh = (tile_width + COARSE - 1) // COARSE, (tile_height + COARSE - 1) // COARSE
+    n_alloc = (n_records + 3) // 4 * 4 + 4
+    recs = torch.empty(n_alloc, dtype=torch.int32, device=dev)
+    ids = torch.empty(n_alloc, dtype=torch.int32, device=dev)
+    offsets = torch.empty(C * bw * bh + 1, dtype=torch.int32, device=dev)
+    ws2 = _ws(lib.b2s_coarse_bin_workspace_bytes(M, n_records), dev)
+    with _stage("coarse_bin"):
+        check(lib.b2s_coarse_bin(M, N, ptr(cam), n_records, ptr(sorted_ids), ptr(means2d), ptr(radii), C, tile_size, tile_width,
+                                 tile_height, ptr(recs), ptr(ids), ptr(offsets), ptr(ws2), ws2.numel(), st), "b2s_coarse_bin")
+    return CoarseBins(recs, ids, offsets, sorted_ids, n_records, n_isects)
 
 
 # ======================================================================================
@@ -684,38 +590,52 @@ _CHANNELS = (1, 2, 3, 4, 8, 16, 32)
 class _RasterizeToPixels(torch.autograd.Function):
     @staticmethod
     def forward(ctx, means2d, conics, colors, opacities, backgrounds, width, height, tile_size, isect_offsets,
-                flatten_ids, absgrad):
-        dev = L.require_cuda(means2d, conics, colors, opacities, isect_offsets, flatten_ids)
+                flatten_ids, absgrad, bins=None, n_cameras=None):
+        """Either the reference's lists (isect_offsets [C,th,tw], flatten_ids [I]) or ``bins`` (CoarseBins, with
+        ``n_cameras``): then the kernels expand the per-tile lists from the coarse bins themselves."""
+        dev = L.require_cuda(means2d, conics, colors, opacities)
         means2d, conics, colors, opacities = f32c(means2d), f32c(conics), f32c(colors), f32c(opacities)
         backgrounds = f32c(backgrounds)
-        C, th, tw = isect_offsets.shape
+        if bins is not None:
+            C, tw, th = int(n_cameras), (width + tile_size - 1) // tile_size, (height + tile_size - 1) // tile_size
+            isect_offsets = bins.offsets            # (saved in the slots of the classic lists)
+            flatten_ids = bins.ids
+            recs = bins.recs
+            n_list = bins.n_records
+        else:
+            C, th, tw = isect_offsets.shape
+            recs = None
+            isect_offsets = isect_offsets.contiguous()
+            flatten_ids = flatten_ids.contiguous()
+            n_list = flatten_ids.numel()
         ch = colors.shape[-1]
         render = torch.empty(C, height, width, ch, dtype=torch.float32, device=dev)
         alphas = torch.empty(C, height, width, 1, dtype=torch.float32, device=dev)
         last_ids = torch.empty(C, height, width, dtype=torch.int32, device=dev)
         final_T = torch.empty(C, height, width, dtype=torch.float32, device=dev)
-        isect_offsets = isect_offsets.contiguous()
-        flatten_ids = flatten_ids.contiguous()
         a = L.CompositeFwdArgs(
             C=C, width=width, height=height, tile_size=tile_size, tile_w=tw, tile_h=th, channels=ch,
-            n_isects=flatten_ids.numel(), means2d=ptr(means2d), conics=ptr(conics), colors=ptr(colors),
-            opacities=ptr(opacities), backgrounds=ptr(backgrounds), isect_offsets=ptr(isect_offsets),
-            flatten_ids=ptr(flatten_ids), render_colors=ptr(render), render_alphas=ptr(alphas), last_ids=ptr(last_ids),
-            final_T=ptr(final_T), chunk_index=-1, tile_done=None)
+            n_isects=n_list, means2d=ptr(means2d), conics=ptr(conics), colors=ptr(colors),
+            opacities=ptr(opacities), backgrounds=ptr(backgrounds),
+            isect_offsets=None if bins is not None else ptr(isect_offsets),
+            flatten_ids=None if bins is not None else ptr(flatten_ids),
+            render_colors=ptr(render), render_alphas=ptr(alphas), last_ids=ptr(last_ids), final_T=ptr(final_T),
+            bin_offsets=ptr(isect_offsets) if bins is not None else None, bin_recs=ptr(recs),
+            bin_ids=ptr(flatten_ids) if bins is not None else None)
         with _stage("composite_fwd"):
             check(L.lib().b2s_composite_fwd(ctypes.byref(a), L.stream_ptr(dev)), "b2s_composite_fwd")
         ctx.save_for_backward(means2d, conics, colors, opacities, backgrounds, isect_offsets, flatten_ids, alphas,
-                              last_ids, final_T)
-        ctx.cfg = (width, height, tile_size, absgrad)
+                              last_ids, final_T, recs)
+        ctx.cfg = (width, height, tile_size, absgrad, C, tw, th, n_list)
         return render, alphas
 
     @staticmethod
     def backward(ctx, v_render, v_alphas):
         (means2d, conics, colors, opacities, backgrounds, isect_offsets, flatten_ids, alphas, last_ids,
-         final_T) = ctx.saved_tensors
-        width, height, tile_size, absgrad = ctx.cfg
+         final_T, recs) = ctx.saved_tensors
+        width, height, tile_size, absgrad, C, tw, th, n_list = ctx.cfg
         dev = means2d.device
-        C, th, tw = isect_offsets.shape
+        use_bins = recs is not None
         ch = colors.shape[-1]
         v_render, v_alphas = f32c(v_render), f32c(v_alphas)
         # one zero-filled slab for every atomically accumulated gradient (one fill instead of four)
@@ -731,12 +651,14 @@ class _RasterizeToPixels(torch.autograd.Function):
         v_abs = parts[4].view(means2d.shape) if absgrad else None
         a = L.CompositeBwdArgs(
             C=C, width=width, height=height, tile_size=tile_size, tile_w=tw, tile_h=th, channels=ch,
-            n_isects=flatten_ids.numel(), means2d=ptr(means2d), conics=ptr(conics), colors=ptr(colors),
-            opacities=ptr(opacities), backgrounds=ptr(backgrounds), isect_offsets=ptr(isect_offsets),
-            flatten_ids=ptr(flatten_ids), render_alphas=ptr(alphas), last_ids=ptr(last_ids), final_T=ptr(final_T),
+            n_isects=n_list, means2d=ptr(means2d), conics=ptr(conics), colors=ptr(colors),
+            opacities=ptr(opacities), backgrounds=ptr(backgrounds),
+            isect_offsets=None if use_bins else ptr(isect_offsets), flatten_ids=None if use_bins else ptr(flatten_ids),
+            render_alphas=ptr(alphas), last_ids=ptr(last_ids), final_T=ptr(final_T),
             v_render_colors=ptr(v_render), v_render_alphas=ptr(v_alphas), v_means2d=ptr(v_means2d),
             v_means2d_abs=ptr(v_abs), v_conics=ptr(v_conics), v_colors=ptr(v_colors), v_opacities=ptr(v_opac),
-            chunk_index=-1, state_T=None, state_S=None)
+            bin_offsets=ptr(isect_offsets) if use_bins else None, bin_recs=ptr(recs),
+            bin_ids=ptr(flatten_ids) if use_bins else None)
         with _stage("composite_bwd"):
             check(L.lib().b2s_composite_bwd(ctypes.byref(a), L.stream_ptr(dev)), "b2s_composite_bwd")
         v_bg = None
@@ -744,20 +666,21 @@ class _RasterizeToPixels(torch.autograd.Function):
             v_bg = (v_render * final_T.abs()[..., None]).sum(dim=(1, 2))
         if absgrad:
             getattr(ctx, "absgrad_holder", means2d).absgrad = v_abs
-        return v_means2d, v_conics, v_colors, v_opac, v_bg, None, None, None, None, None, None
+        return v_means2d, v_conics, v_colors, v_opac, v_bg, None, None, None, None, None, None, None, None
 
 
 def rasterize_to_pixels(means2d: Tensor, conics: Tensor, colors: Tensor, opacities: Tensor, image_width: int,
                         image_height: int, tile_size: int, isect_offsets: Tensor, flatten_ids: Tensor,
                         backgrounds: Optional[Tensor] = None, masks: Optional[Tensor] = None, packed: bool = False,
-                        absgrad: bool = False) -> Tuple[Tensor, Tensor]:
+                        absgrad: bool = False, bins: Optional["CoarseBins"] = None,
+                        n_cameras: Optional[int] = None) -> Tuple[Tensor, Tensor]:
     """gsplat ``rasterize_to_pixels``: (render_colors [C,H,W,ch], render_alphas [C,H,W,1]).  Rows of the
     per-splat tensors are addressed through ``flatten_ids`` so dense ``[C,N,..]`` and packed ``[nnz,..]`` both work."""
     if masks is not None:
         raise NotImplementedError("tile masks are not implemented")
     if tile_size != 16:
         raise NotImplementedError("tile_size must be 16")
-    C = isect_offsets.shape[0]
+    C = int(n_cameras) if bins is not None else isect_offsets.shape[0]
     if packed:
         if means2d.dim() != 2:
             raise ValueError("packed=True expects [nnz,..] tensors")
@@ -777,7 +700,7 @@ def rasterize_to_pixels(means2d: Tensor, conics: Tensor, colors: Tensor, opaciti
     fn = _RasterizeToPixels
     # absgrad: gsplat attaches `.absgrad` to the means2d tensor the caller passed in
     render, alphas = _apply_with_holder(fn, holder, means2d, conics, colors, opacities, backgrounds, int(image_width),
-                                        int(image_height), int(tile_size), isect_offsets, flatten_ids, bool(absgrad))
+                                        int(image_height), int(tile_size), isect_offsets, flatten_ids, bool(absgrad), bins, C)
     if pad:
         render = render[..., :ch]
     return render, alphas

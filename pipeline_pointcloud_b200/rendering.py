@@ -23,11 +23,10 @@ from . import ops
 from ._lib import require_cuda
 
 
-def _use_chunked() -> bool:
-    """Occlusion-aware chunked binning (csrc/chunked.cu) is an opt-in experiment (B2S_CHUNKED=1) for the dense
-    layout: on the config-3 scene it measured 3.91 ms/step against 3.68 ms for the one-shot pipeline (bin everything,
-    composite once), which therefore stays the default."""
-    return os.environ.get("B2S_CHUNKED", "0") == "1"
+def _use_coarse_bins() -> bool:
+    """Two-level binning (coarse bins expanded inside the compositing kernels) is the default;
+    B2S_BINNING=tiles selects the reference-shaped pipeline (materialise every tile intersection) for A/B runs."""
+    return os.environ.get("B2S_BINNING", "coarse") != "tiles"
 
 
 def rasterization(
@@ -104,28 +103,10 @@ def rasterization(
     # ---- stage 1: projection (+ SH colour + tile counts) in one kernel ------------------------------------
     fused_sh = sh_degree is not None and colors.dim() == 3
     campos = None          # the kernels derive the camera centres from viewmats
-    chunked = (not packed) and _use_chunked() and C <= ops.MAX_CAMS
-    lazy_sh = chunked and fused_sh and render_mode in ("RGB", "RGB+D", "RGB+ED")
-    if chunked and not lazy_sh:
-        d = 3 if sh_degree is not None else colors.shape[-1]
-        ch_needed = 1 if render_mode in ("D", "ED") else d + (1 if render_mode in ("RGB+D", "RGB+ED") else 0)
-        chunked = ch_needed in ops._CHANNELS
-    radii, means2d, depths, conics, _comps, opac, sh_cols, tiles, dkeys, rowids, total, touched = ops._ProjectFused.apply(
-        means, quats, scales, opacities, colors if (fused_sh and not lazy_sh) else None, viewmats, Ks, campos, width, height,
+    radii, means2d, depths, conics, _comps, opac, sh_cols, tiles, dkeys, rowids, total = ops._ProjectFused.apply(
+        means, quats, scales, opacities, colors if fused_sh else None, viewmats, Ks, campos, width, height,
         float(eps2d), float(near_plane), float(far_plane), float(radius_clip), antialiased, False,
-        int(sh_degree) if fused_sh else 0, tile_size, chunked)
-
-    if lazy_sh:
-        # occlusion-aware path with lazy shading: SH colour is evaluated inside the chunk loop, only for rows that emit
-        with_depth = render_mode in ("RGB+D", "RGB+ED")
-        bg = backgrounds
-        if with_depth and bg is not None:
-            bg = torch.cat([bg, torch.zeros_like(bg[:, :1])], dim=-1)
-        render_colors, render_alphas, sorted_ids = ops._RenderChunked.apply(
-            means2d, conics, opac, depths, means, colors, None, viewmats, bg, radii, tiles, dkeys, rowids, total, touched, width,
-            height, tile_size, int(sh_degree), with_depth, absgrad)
-        return _finish(render_colors, render_alphas, render_mode, None, None, radii, means2d, depths, conics, opac, tiles,
-                       tw, th, width, height, tile_size, C, total, sorted_ids)
+        int(sh_degree) if fused_sh else 0, tile_size)
 
     if sh_degree is None:
         cols = colors if colors.dim() == 3 else colors[None].expand(C, N, colors.shape[-1])
@@ -154,34 +135,44 @@ def rasterization(
     else:
         radii_m, means2d_m, depths_m, conics_m, opac_m, cols_m, tiles_m = radii, means2d, depths, conics, opac, cols, tiles
 
-    if chunked:
-        render_colors, render_alphas, sorted_ids = ops._RenderChunked.apply(
-            means2d, conics, opac, depths, means, None, cols_m, viewmats, backgrounds, radii, tiles, dkeys, rowids, total, touched,
-            width, height, tile_size, 0, False, absgrad)
-        return _finish(render_colors, render_alphas, render_mode, None, None, radii, means2d, depths, conics, opac, tiles,
-                       tw, th, width, height, tile_size, C, total, sorted_ids)
-
     # ---- stage 2: binning --------------------------------------------------------------------------------
     tiles_per_gauss = tiles_m
-    flatten_ids, isect_offsets, make_isect_ids = ops.bin_depth_first(
-        means2d_m, radii_m, depths_m, tiles_m, tile_size, tw, th, C, camera_ids=camera_ids,
-        depth_keys=None if packed else dkeys, row_ids=None if packed else rowids, total_isects=total)
+    ch = cols_m.shape[-1]
+    fused_keys = (not packed) and C <= ops.MAX_CAMS
+    if _use_coarse_bins() and ops.coarse_bins_supported(C, tw, th, ch):
+        # two-level binning: coarse bins now, per-tile lists expanded inside the compositing kernels; the reference's
+        # per-intersection lists (flatten_ids, isect_offsets, isect_ids) are built only if somebody reads them
+        bins = ops.bin_coarse(means2d_m, radii_m, depths_m, tile_size, tw, th, C, camera_ids=camera_ids,
+                              depth_keys=dkeys if fused_keys else None, row_ids=rowids if fused_keys else None, totals=total)
+        flatten_ids = isect_offsets = None
+        cache = {}
+
+        def lists():
+            if not cache:
+                flat, off, mk = ops.bin_depth_first(means2d_m.detach(), radii_m, depths_m.detach(), tiles_m, tile_size, tw, th,
+                                                    C, camera_ids=camera_ids, total_isects=total, sorted_ids=bins.sorted_ids)
+                cache.update(flat=flat, off=off, mk=mk)
+            return cache
+    else:
+        bins = None
+        flatten_ids, isect_offsets, make_isect_ids = ops.bin_depth_first(
+            means2d_m, radii_m, depths_m, tiles_m, tile_size, tw, th, C, camera_ids=camera_ids,
+            depth_keys=dkeys if fused_keys else None, row_ids=rowids if fused_keys else None, total_isects=total)
 
     # ---- stage 3: compositing ----------------------------------------------------------------------------
-    ch = cols_m.shape[-1]
     if ch > channel_chunk:
         outs = []
         for c0 in range(0, ch, channel_chunk):
             bg = backgrounds[..., c0:c0 + channel_chunk] if backgrounds is not None else None
             rc, ra = ops.rasterize_to_pixels(means2d_m, conics_m, cols_m[..., c0:c0 + channel_chunk], opac_m, width, height,
                                              tile_size, isect_offsets, flatten_ids, backgrounds=bg, packed=packed,
-                                             absgrad=absgrad)
+                                             absgrad=absgrad, bins=bins, n_cameras=C)
             outs.append(rc)
         render_colors, render_alphas = torch.cat(outs, dim=-1), ra
     else:
         render_colors, render_alphas = ops.rasterize_to_pixels(
             means2d_m, conics_m, cols_m, opac_m, width, height, tile_size, isect_offsets, flatten_ids,
-            backgrounds=backgrounds, packed=packed, absgrad=absgrad)
+            backgrounds=backgrounds, packed=packed, absgrad=absgrad, bins=bins, n_cameras=C)
     if render_mode in ("ED", "RGB+ED"):
         render_colors = torch.cat(
             [render_colors[..., :-1], render_colors[..., -1:] / render_alphas.clamp(min=1e-10)], dim=-1)
@@ -189,36 +180,14 @@ def rasterization(
     meta = ops.LazyMeta({
         "camera_ids": camera_ids, "gaussian_ids": gaussian_ids, "radii": radii_m, "means2d": means2d_m,
         "depths": depths_m, "conics": conics_m, "opacities": opac_m, "tile_width": tw, "tile_height": th,
-        "tiles_per_gauss": tiles_per_gauss, "flatten_ids": flatten_ids,
-        "isect_offsets": isect_offsets, "width": width, "height": height, "tile_size": tile_size, "n_cameras": C,
+        "tiles_per_gauss": tiles_per_gauss, "width": width, "height": height, "tile_size": tile_size, "n_cameras": C,
     })
-    meta.set_lazy("isect_ids", make_isect_ids)     # 64-bit sorted keys, rebuilt on first access
-    return render_colors, render_alphas, meta
-
-
-def _finish(render_colors, render_alphas, render_mode, camera_ids, gaussian_ids, radii, means2d, depths, conics, opac, tiles,
-            tw, th, width, height, tile_size, C, total, sorted_ids):
-    """Common tail of the chunked path: expected-depth normalisation and the meta dict.  The per-intersection lists
-    (flatten_ids, isect_offsets, isect_ids) of the *whole* frame are not needed by chunked compositing; they are
-    produced on first access by the one-shot binning, from the depth order that already exists."""
-    if render_mode in ("ED", "RGB+ED"):
-        render_colors = torch.cat(
-            [render_colors[..., :-1], render_colors[..., -1:] / render_alphas.clamp(min=1e-10)], dim=-1)
-    meta = ops.LazyMeta({
-        "camera_ids": camera_ids, "gaussian_ids": gaussian_ids, "radii": radii, "means2d": means2d, "depths": depths,
-        "conics": conics, "opacities": opac, "tile_width": tw, "tile_height": th, "tiles_per_gauss": tiles, "width": width,
-        "height": height, "tile_size": tile_size, "n_cameras": C,
-    })
-    cache = {}
-
-    def bins():
-        if not cache:
-            flat, off, mk = ops.bin_depth_first(means2d.detach(), radii, depths.detach(), tiles, tile_size, tw, th, C,
-                                                total_isects=total, sorted_ids=sorted_ids)
-            cache.update(flat=flat, off=off, mk=mk)
-        return cache
-
-    meta.set_lazy("flatten_ids", lambda: bins()["flat"])
-    meta.set_lazy("isect_offsets", lambda: bins()["off"])
-    meta.set_lazy("isect_ids", lambda: bins()["mk"]())
+    if bins is not None:
+        meta["n_isects"] = bins.n_isects
+        meta.set_lazy("flatten_ids", lambda: lists()["flat"])
+        meta.set_lazy("isect_offsets", lambda: lists()["off"])
+        meta.set_lazy("isect_ids", lambda: lists()["mk"]())
+    else:
+        meta["flatten_ids"], meta["isect_offsets"] = flatten_ids, isect_offsets
+        meta.set_lazy("isect_ids", make_isect_ids)     # 64-bit sorted keys, rebuilt on first access
     return render_colors, render_alphas, meta

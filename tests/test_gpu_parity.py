@@ -168,18 +168,20 @@ def test_rasterize_to_pixels_forward(b2s, ch, bg):
 
 
 @pytest.mark.parametrize("cfg", [
-    dict(N=3000, deg=3, C=2, W=96, H=64, packed=False, mode="antialiased"),                       # chunked, lazy SH
-    dict(N=3000, deg=3, C=2, W=96, H=64, packed=False, mode="antialiased", chunked="0"),          # one-shot pipeline
+    dict(N=3000, deg=3, C=2, W=96, H=64, packed=False, mode="antialiased"),                       # two-level binning (default)
+    dict(N=3000, deg=3, C=2, W=96, H=64, packed=False, mode="antialiased", binning="tiles"),      # reference-shaped lists
     dict(N=3000, deg=3, C=1, W=111, H=70, packed=True, mode="classic"),
     dict(N=2500, deg=1, C=3, W=80, H=48, packed=True, mode="antialiased", render_mode="RGB+ED", bg=True),
-    dict(N=2500, deg=2, C=2, W=80, H=48, packed=False, mode="antialiased", render_mode="RGB+ED", bg=True),  # chunked, depth channel
-    dict(N=2000, deg=None, C=2, W=64, H=64, packed=False, mode="classic", render_mode="RGB+D"),   # chunked, given colours
-    dict(N=2000, deg=None, C=2, W=64, H=64, packed=False, mode="classic", render_mode="RGB+D", chunked="0"),
-    dict(N=20000, deg=3, C=1, W=64, H=48, packed=False, mode="classic", dense=True),              # deep overdraw: tiles finish early
+    dict(N=2500, deg=2, C=2, W=80, H=48, packed=False, mode="antialiased", render_mode="RGB+ED", bg=True),
+    dict(N=2000, deg=None, C=2, W=64, H=64, packed=False, mode="classic", render_mode="RGB+D"),
+    dict(N=2000, deg=None, C=2, W=64, H=64, packed=False, mode="classic", render_mode="RGB+D", binning="tiles"),
+    dict(N=3000, deg=3, C=1, W=111, H=70, packed=True, mode="classic", binning="tiles"),
+    dict(N=20000, deg=3, C=1, W=64, H=48, packed=False, mode="classic", dense=True),              # deep overdraw: tiles saturate early
+    dict(N=6000, deg=1, C=2, W=300, H=200, packed=False, mode="classic", big=True),               # several coarse bins per camera
 ])
 def test_rasterization_forward_backward(b2s, cfg, monkeypatch):
     """The whole drop-in call, forward and backward, against the oracle's autograd."""
-    monkeypatch.setenv("B2S_CHUNKED", cfg.get("chunked", "1"))   # (the product default is "0")
+    monkeypatch.setenv("B2S_BINNING", cfg.get("binning", "coarse"))
     N, deg, C, W, H = cfg["N"], cfg["deg"], cfg["C"], cfg["W"], cfg["H"]
     a = scene_args(N, deg if deg is not None else 0, C, W, H, seed=6, requires_grad=True, stress=not cfg.get("dense"))
     if cfg.get("dense"):     # opaque, large splats: most tiles saturate inside the first chunk
@@ -291,20 +293,18 @@ def test_edge_cases(b2s):
         call(b2s.rasterization, {k: v.cpu() for k, v in g.items()}, W, H)   # no CPU path
 
 
-def test_full_size_chunked_matches_one_shot(b2s, monkeypatch):
-    """The opt-in occlusion-aware chunked pipeline renders the same image as the one-shot pipeline at config-3 size, up to
-    the rounding of two different SH evaluation kernels (and ex2.approx knife edges, rare at this tolerance)."""
+def test_full_size_coarse_bins_match_tile_lists(b2s, monkeypatch):
+    """Config-3 size: two-level binning (lists expanded inside the compositing kernels) renders bit for bit what the
+    reference-shaped pipeline (every tile intersection materialised and sorted) renders."""
     N, W, H = 5_800_000, 1297, 840
     a = scene_args(N, 3, 1, W, H, seed=0)
     g = {k: v.cuda() for k, v in a.items()}
     with torch.no_grad():
-        monkeypatch.setenv("B2S_CHUNKED", "0")
+        monkeypatch.setenv("B2S_BINNING", "tiles")
         r, al, _ = call(b2s.rasterization, g, W, H, sh_degree=3, packed=False, rasterize_mode="antialiased")
-        monkeypatch.setenv("B2S_CHUNKED", "1")
+        monkeypatch.setenv("B2S_BINNING", "coarse")
         rc, alc, _ = call(b2s.rasterization, g, W, H, sh_degree=3, packed=False, rasterize_mode="antialiased")
-    dr, da = (r - rc).abs(), (al - alc).abs()
-    assert float(da.max()) < 2e-2 and float((da > 1e-5).float().mean()) < 1e-3, (float(da.max()), float((da > 1e-5).float().mean()))
-    assert float(dr.max()) < 2e-2 and float((dr > 1e-5).float().mean()) < 1e-3, (float(dr.max()), float((dr > 1e-5).float().mean()))
+    assert torch.equal(r, rc) and torch.equal(al, alc)
 
 
 def test_full_size_properties(b2s):
