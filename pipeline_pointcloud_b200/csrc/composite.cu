@@ -21,7 +21,7 @@
 //   BINS = false  the reference's layout: the tile's Gaussians are flatten_ids[isect_offsets[t] .. isect_offsets[t+1])
 //                 (the stage-level op `rasterize_to_pixels`);
 //   BINS = true   two-level binning (binning.cu, `b2s_coarse_bin`): the CTA walks the depth-ordered list of its
-//                 8x8-tile coarse bin, 2048 records per round (each thread tests 2 x 128 bits of records against the
+//                 8x8-tile coarse bin, 1024 records per round (each thread tests 128 bits of records against the
 //                 tile's mask bits), compacts the hits -- in order -- into a shared-memory ring and composites them
 //                 256 at a time.  The hits are exactly the tile's slice of the reference's sorted list, but only
 //                 the part in front of the saturation point is ever generated.
@@ -40,9 +40,9 @@ constexpr float LN2 = 0.6931471805599453f;
 
 // ---- two-level binning: in-kernel expansion of a tile's list from its coarse bin ------------------------------
 constexpr int CB = B2S_COARSE;               // tiles per coarse-bin side
-constexpr int SCAN_PER_THREAD = 8;
+constexpr int SCAN_PER_THREAD = 4;
 constexpr int SCAN = CTA * SCAN_PER_THREAD;  // records examined per round
-constexpr int QRING = 4096;                  // ring of pending hits (>= CTA - 1 + SCAN, power of two)
+constexpr int QRING = 2048;                  // ring of pending hits (>= CTA - 1 + SCAN, power of two)
 constexpr int BINS_MAX_CH = 4;               // wider feature vectors use the classic lists (shared-memory budget)
 
 // One round: examine the records [wbase, wbase + SCAN) (wbase a multiple of 4) that also lie in [lo, hi), keep those
@@ -53,21 +53,20 @@ template <bool REVERSE>
 __device__ __forceinline__ int scan_round(const uint32_t* __restrict__ recs, const int32_t* __restrict__ ids, int wbase,
                                           int lo, int hi, unsigned lx, unsigned ly, int2* s_q, int qtail, int* s_wtot) {
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
-    // thread t owns 8 consecutive records (two aligned groups of 4); in REVERSE, thread 0 owns the highest 8
+    // thread t owns 4 consecutive records (one aligned 128-bit group); in REVERSE, thread 0 owns the highest 4
+    static_assert(SCAN_PER_THREAD == 4, "one 128-bit load per thread");
     const int g0 = REVERSE ? wbase + SCAN - SCAN_PER_THREAD * (t + 1) : wbase + SCAN_PER_THREAD * t;
     uint32_t r[SCAN_PER_THREAD];
     int id[SCAN_PER_THREAD];
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-        const int g = g0 + 4 * h;
+    {
         uint4 rv = make_uint4(0u, 0u, 0u, 0u);
         int4 iv = make_int4(0, 0, 0, 0);
-        if (g >= 0 && g < hi && g + 4 > lo) {        // the lists are padded to a multiple of 4 entries
-            rv = __ldg(reinterpret_cast<const uint4*>(recs + g));
-            iv = __ldg(reinterpret_cast<const int4*>(ids + g));
+        if (g0 >= 0 && g0 < hi && g0 + 4 > lo) {     // the lists are padded to a multiple of 4 entries
+            rv = __ldg(reinterpret_cast<const uint4*>(recs + g0));
+            iv = __ldg(reinterpret_cast<const int4*>(ids + g0));
         }
-        r[4 * h] = rv.x; r[4 * h + 1] = rv.y; r[4 * h + 2] = rv.z; r[4 * h + 3] = rv.w;
-        id[4 * h] = iv.x; id[4 * h + 1] = iv.y; id[4 * h + 2] = iv.z; id[4 * h + 3] = iv.w;
+        r[0] = rv.x; r[1] = rv.y; r[2] = rv.z; r[3] = rv.w;
+        id[0] = iv.x; id[1] = iv.y; id[2] = iv.z; id[3] = iv.w;
     }
     unsigned hits = 0;
 #pragma unroll
@@ -117,6 +116,23 @@ __device__ __forceinline__ PixelMap pixel_of_thread(int tile_x, int tile_y, int 
     return p;
 }
 
+// pixel-centre bounds of the 8x4 block a warp owns
+struct WarpBlock {
+    float xmin, xmax, ymin, ymax;
+};
+__device__ __forceinline__ WarpBlock warp_block(int tile_x, int tile_y) {
+    const int warp = threadIdx.x >> 5;
+    WarpBlock b;
+    b.xmin = (float)(tile_x * TILE + (warp & 1) * 8) + 0.5f;
+    b.xmax = b.xmin + 7.f;
+    b.ymin = (float)(tile_y * TILE + (warp >> 1) * 4) + 0.5f;
+    b.ymax = b.ymin + 3.f;
+    return b;
+}
+__device__ __forceinline__ bool box_hits(const float4& box, const WarpBlock& b) {
+    return box.x <= b.xmax && box.y >= b.xmin && box.z <= b.ymax && box.w >= b.ymin;
+}
+
 // keeps a value in a register: without it ptxas rematerialises the pixel centre from %ctaid/%tid
 // inside the hot loop (14 extra instructions per Gaussian)
 __device__ __forceinline__ void pin(float& v) { asm volatile("" : "+f"(v)); }
@@ -131,14 +147,27 @@ __device__ __forceinline__ float rcp_approx(float x) {
     return r;
 }
 
-// gathers one splat into the staged record format
+// gathers one splat into the staged record format; `box` = (xmin, xmax, ymin, ymax) of the region where the splat
+// can pass the `sigma2 <= tau2` test (the axis-aligned bounding box of that ellipse, padded), used to skip the splat
+// for a whole warp when it cannot reach the warp's 8x4 pixel block
 __device__ __forceinline__ void stage_splat(int g, const float* __restrict__ means2d, const float* __restrict__ conics,
-                                            const float* __restrict__ opacities, float4& rec0, float4& rec1) {
+                                            const float* __restrict__ opacities, float4& rec0, float4& rec1, float4& box) {
     const float2 xy = reinterpret_cast<const float2*>(means2d)[g];
     const float op = opacities[g];
-    rec0 = make_float4(xy.x, xy.y, op, __log2f(255.f * op) + TAU_MARGIN);
-    rec1 = make_float4(0.5f * LOG2E * conics[3 * g], LOG2E * conics[3 * g + 1], 0.5f * LOG2E * conics[3 * g + 2],
-                       __int_as_float(g));
+    const float tau = __log2f(255.f * op) + TAU_MARGIN;
+    const float A = 0.5f * LOG2E * conics[3 * g], B = LOG2E * conics[3 * g + 1], C = 0.5f * LOG2E * conics[3 * g + 2];
+    rec0 = make_float4(xy.x, xy.y, op, tau);
+    rec1 = make_float4(A, B, C, __int_as_float(g));
+    // { A dx^2 + B dx dy + C dy^2 <= tau }: |dx| <= sqrt(4 C tau / (4AC - B^2)), |dy| <= sqrt(4 A tau / (4AC - B^2))
+    const float det4 = 4.f * A * C - B * B;
+    float ex = 3.0e38f, ey = 3.0e38f;              // degenerate conic: never culled here (the exact test decides)
+    if (!(tau >= 0.f)) { ex = -1.f; ey = -1.f; }   // alpha < 1/255 everywhere (also NaN opacity): empty region
+    else if (det4 > 0.f && A > 0.f && C > 0.f) {
+        const float k = 4.f * tau / det4;
+        ex = sqrtf(k * C) * 1.0001f + 1e-3f;
+        ey = sqrtf(k * A) * 1.0001f + 1e-3f;
+    }
+    box = make_float4(xy.x - ex, xy.x + ex, xy.y - ey, xy.y + ey);
 }
 
 // =================================================================================================
@@ -148,6 +177,7 @@ template <int CH, bool BINS>
 __global__ void __launch_bounds__(CTA) composite_fwd_kernel(const b2s_composite_fwd_args a, float* __restrict__ final_T) {
     __shared__ float4 s_rec0[CTA];
     __shared__ float4 s_rec1[CTA];
+    __shared__ float4 s_box[CTA];
     __shared__ float s_col[CTA * CH];
     __shared__ int2 s_q[BINS ? QRING : 1];
     __shared__ int s_wtot[2][CTA / 32];
@@ -156,6 +186,8 @@ __global__ void __launch_bounds__(CTA) composite_fwd_kernel(const b2s_composite_
     const PixelMap pm = pixel_of_thread(tile_x, tile_y, a.width, a.height);
     float px = (float)pm.px + 0.5f, py = (float)pm.py + 0.5f;
     pin(px); pin(py);
+    const int lane = threadIdx.x & 31;
+    const WarpBlock wb = warp_block(tile_x, tile_y);
     int lo, hi;
     if (BINS) {
         const int bins_w = (a.tile_w + CB - 1) / CB, bins_h = (a.tile_h + CB - 1) / CB;
@@ -176,24 +208,33 @@ __global__ void __launch_bounds__(CTA) composite_fwd_kernel(const b2s_composite_
     int last = 0;
     bool done = !pm.inside;
 
-    // one batch of `bs` staged splats; `last` records s_rec1[j].w (BINS: the record position) or start + j
+    // One batch of `bs` staged splats.  32 splats at a time, each lane tests one splat's box against the warp's pixel
+    // block; only the survivors are evaluated per pixel.  `last` records s_rec1[j].w (BINS: the record position) or
+    // start + j.
     auto composite_batch = [&](int bs, int start) {
-#pragma unroll 2
-        for (int j = 0; j < bs && !done; ++j) {
-            const float4 r0 = s_rec0[j];
-            const float4 r1 = s_rec1[j];
-            const float dx = r0.x - px, dy = r0.y - py;
-            const float s2 = fmaf(dx, fmaf(r1.x, dx, r1.y * dy), r1.z * dy * dy);
-            if (s2 < 0.f || s2 > r0.w) continue;
-            const float alpha = fminf(ALPHA_MAX, r0.z * ex2_approx(-s2));
-            if (alpha < ALPHA_MIN) continue;
-            const float nT = T * (1.f - alpha);
-            if (nT <= T_STOP) { done = true; break; }
-            const float w = alpha * T;
+        for (int j0 = 0; j0 < bs; j0 += 32) {
+            const int jl = j0 + lane;
+            unsigned m = __ballot_sync(FULL, jl < bs && box_hits(s_box[jl], wb));
+            while (m) {
+                const int j = j0 + __ffs(m) - 1;
+                m &= m - 1;
+                if (done) continue;
+                const float4 r0 = s_rec0[j];
+                const float4 r1 = s_rec1[j];
+                const float dx = r0.x - px, dy = r0.y - py;
+                const float s2 = fmaf(dx, fmaf(r1.x, dx, r1.y * dy), r1.z * dy * dy);
+                if (s2 < 0.f || s2 > r0.w) continue;
+                const float alpha = fminf(ALPHA_MAX, r0.z * ex2_approx(-s2));
+                if (alpha < ALPHA_MIN) continue;
+                const float nT = T * (1.f - alpha);
+                if (nT <= T_STOP) { done = true; continue; }
+                const float w = alpha * T;
 #pragma unroll
-            for (int k = 0; k < CH; ++k) acc[k] = fmaf(w, s_col[j * CH + k], acc[k]);
-            T = nT;
-            last = BINS ? __float_as_int(r1.w) : start + j;
+                for (int k = 0; k < CH; ++k) acc[k] = fmaf(w, s_col[j * CH + k], acc[k]);
+                T = nT;
+                last = BINS ? __float_as_int(r1.w) : start + j;
+            }
+            if (__all_sync(FULL, done)) break;
         }
     };
 
@@ -215,11 +256,12 @@ __global__ void __launch_bounds__(CTA) composite_fwd_kernel(const b2s_composite_
             const int bs = min(CTA, qcount);
             if ((int)threadIdx.x < bs) {
                 const int2 e = s_q[(qhead + threadIdx.x) & (QRING - 1)];
-                float4 r0, r1;
-                stage_splat(e.x, a.means2d, a.conics, a.opacities, r0, r1);
+                float4 r0, r1, bx;
+                stage_splat(e.x, a.means2d, a.conics, a.opacities, r0, r1, bx);
                 r1.w = __int_as_float(e.y);
                 s_rec0[threadIdx.x] = r0;
                 s_rec1[threadIdx.x] = r1;
+                s_box[threadIdx.x] = bx;
 #pragma unroll
                 for (int k = 0; k < CH; ++k) s_col[threadIdx.x * CH + k] = a.colors[(int64_t)e.x * CH + k];
             }
@@ -237,10 +279,11 @@ __global__ void __launch_bounds__(CTA) composite_fwd_kernel(const b2s_composite_
             const int idx = start + threadIdx.x;
             if (idx < hi) {
                 const int g = a.flatten_ids[idx];
-                float4 r0, r1;
-                stage_splat(g, a.means2d, a.conics, a.opacities, r0, r1);
+                float4 r0, r1, bx;
+                stage_splat(g, a.means2d, a.conics, a.opacities, r0, r1, bx);
                 s_rec0[threadIdx.x] = r0;
                 s_rec1[threadIdx.x] = r1;
+                s_box[threadIdx.x] = bx;
 #pragma unroll
                 for (int k = 0; k < CH; ++k) s_col[threadIdx.x * CH + k] = a.colors[(int64_t)g * CH + k];
             }
@@ -308,6 +351,7 @@ __global__ void __launch_bounds__(CTA) composite_bwd_kernel(const b2s_composite_
     constexpr int V = CH + 6 + (ABS ? 2 : 0);   // values reduced per (warp, Gaussian)
     __shared__ float4 s_rec0[CTA];
     __shared__ float4 s_rec1[CTA];
+    __shared__ float4 s_box[CTA];
     __shared__ float s_col[CTA * CH];
     __shared__ int s_pos[BINS ? CTA : 1];       // BINS: list position of each staged splat (descending)
     __shared__ int2 s_q[BINS ? QRING : 1];
@@ -332,6 +376,7 @@ __global__ void __launch_bounds__(CTA) composite_bwd_kernel(const b2s_composite_
     }
     if (hi <= lo) return;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const WarpBlock wb = warp_block(tile_x, tile_y);
     const int64_t pix = pm.inside ? ((int64_t)cam * a.height + pm.py) * a.width + pm.px : 0;
 
     // which gradient slot this lane publishes after the multi-value reduction (lane-constant)
@@ -491,10 +536,11 @@ __global__ void __launch_bounds__(CTA) composite_bwd_kernel(const b2s_composite_
             const int bs = min(CTA, qcount);
             if ((int)threadIdx.x < bs) {
                 const int2 e = s_q[(qhead + threadIdx.x) & (QRING - 1)];
-                float4 r0, r1;
-                stage_splat(e.x, a.means2d, a.conics, a.opacities, r0, r1);
+                float4 r0, r1, bx;
+                stage_splat(e.x, a.means2d, a.conics, a.opacities, r0, r1, bx);
                 s_rec0[threadIdx.x] = r0;
                 s_rec1[threadIdx.x] = r1;
+                s_box[threadIdx.x] = bx;
                 s_pos[threadIdx.x] = e.y;
 #pragma unroll
                 for (int k = 0; k < CH; ++k) s_col[threadIdx.x * CH + k] = a.colors[(int64_t)e.x * CH + k];
@@ -502,10 +548,15 @@ __global__ void __launch_bounds__(CTA) composite_bwd_kernel(const b2s_composite_
             __syncthreads();
             qhead += bs;
             qcount -= bs;
-            for (int t = 0; t < bs; ++t) {
-                const int p = s_pos[t];
-                if (p > warp_final) continue;                  // behind every pixel of this warp
-                splat_bwd(t, p <= bin_final);
+            for (int t0 = 0; t0 < bs; t0 += 32) {
+                const int tl = t0 + lane;
+                // skip what lies behind every pixel of this warp, and what cannot reach its pixel block
+                unsigned m = __ballot_sync(FULL, tl < bs && s_pos[tl] <= warp_final && box_hits(s_box[tl], wb));
+                while (m) {
+                    const int t = t0 + __ffs(m) - 1;
+                    m &= m - 1;
+                    splat_bwd(t, s_pos[t] <= bin_final);
+                }
             }
         }
     } else {
@@ -519,16 +570,26 @@ __global__ void __launch_bounds__(CTA) composite_bwd_kernel(const b2s_composite_
             const int idx = batch_end - (int)threadIdx.x;               // smem slot t holds index batch_end - t
             if (idx >= lo) {
                 const int g = a.flatten_ids[idx];
-                float4 r0, r1;
-                stage_splat(g, a.means2d, a.conics, a.opacities, r0, r1);
+                float4 r0, r1, bx;
+                stage_splat(g, a.means2d, a.conics, a.opacities, r0, r1, bx);
                 s_rec0[threadIdx.x] = r0;
                 s_rec1[threadIdx.x] = r1;
+                s_box[threadIdx.x] = bx;
 #pragma unroll
                 for (int k = 0; k < CH; ++k) s_col[threadIdx.x * CH + k] = a.colors[(int64_t)g * CH + k];
             }
             __syncthreads();
             const int t_min = pm.inside ? batch_end - bin_final : CTA;   // this pixel takes part from slot t_min on
-            for (int t = max(0, batch_end - warp_final); t < bs; ++t) splat_bwd(t, t >= t_min);
+            const int t_first = batch_end - warp_final;                  // slots before it lie behind every pixel of this warp
+            for (int t0 = max(0, t_first) & ~31; t0 < bs; t0 += 32) {
+                const int tl = t0 + lane;
+                unsigned m = __ballot_sync(FULL, tl < bs && tl >= t_first && box_hits(s_box[tl], wb));
+                while (m) {
+                    const int t = t0 + __ffs(m) - 1;
+                    m &= m - 1;
+                    splat_bwd(t, t >= t_min);
+                }
+            }
         }
     }
 }
