@@ -38,6 +38,8 @@ WORKLOADS = {
     "tiny": (50_000, 3, 320, 240, "antialiased"),
 }
 METRIC = "3DGS rasterization fwd+bwd throughput"
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture (profiles/), config 3
+NCU_TRAFFIC = {}
 UNIT = "Mpix/s"
 
 
@@ -104,22 +106,30 @@ class ClockSampler:
 # ----------------------------------------------------------------------------------------------------------
 # algorithmic bytes per stage (DESIGN.md "Measurement")
 # ----------------------------------------------------------------------------------------------------------
-def algorithmic_bytes(N, C, V, I, P, K, n_tiles, key_bits):
+def algorithmic_bytes(N, C, V, Vt, I, R, P, K, n_tiles, key_bits):
+    """Compulsory HBM traffic per stage (every input read once, every output written once).
+    V = visible rows, Vt = rows compositing actually reached (non-zero cotangent), I = tile intersections,
+    R = coarse-bin records.  The compositing stages are instruction-issue bound, not HBM bound: no figure."""
     M = C * N
     p = math.ceil(key_bits / 8)
     return {
-        "project_fwd": N * 44 + V * 12 * K + M * 52,               # params + SH rows of visible + all per-pair outputs
+        "project_fwd": N * 44 + V * 12 * K + M * 60,               # params + SH rows of visible + per-pair outputs (incl. keys)
+        # reference-shaped lists (B2S_BINNING=tiles)
         "isect_scan": M * 8,
         "isect_fill": M * 20 + I * 12,
         "isect_sort": I * 12 * 2 * p + I * 8,                        # LSD radix model; single-pass ideal = I*24
         "isect_offsets": I * 8 + 4 * n_tiles,
-        # depth-first binning: 32-bit depth sort of M rows (histogram + 4 passes) + gather-scan;
-        # expand + 32-bit (camera,tile) sort of I records (histogram + ceil(bits/8) passes) + offsets
-        "depth_order": M * 4 + 4 * M * 16 + M * 12,
         "tile_bin": M * 20 + I * 8 + I * 4 + math.ceil((key_bits - 32) / 8) * I * 16 + I * 4 + 4 * n_tiles,
-        "composite_fwd": I * 40 + P * 24,
-        "composite_bwd": I * 40 + P * 28 + I * 36,
-        "project_bwd": N * 44 + M * 4 + V * (36 + 12 * K) + N * 44 + N * 12 * K,
+        # depth sort of the rows: histogram read + 4 digit passes over (key, id) pairs, read + write each
+        "depth_order": M * 4 + 4 * M * 16,
+        # coarse binning: sorted ids + gathered (means2d, radius) in, records out; histogram; one digit pass; offsets
+        "coarse_bin": M * 4 + V * 12 + R * 8 + R * 4 + R * 16 + 4 * (n_tiles // 64 + 1),
+        "composite_fwd": None,
+        "composite_bwd": None,
+        # SH colour VJP: means + radii + colour cotangents in, coefficient rows of the reached rows in, all gradients out
+        "sh_bwd": N * 12 + M * 4 + V * 12 + Vt * 12 * K + N * 12 * K + N * 12,
+        # projection VJP: radii + cotangents of the visible rows, parameters of the reached rows, gradients out
+        "project_bwd": M * 4 + V * 36 + Vt * 44 + N * 44,
     }
 
 
@@ -209,7 +219,7 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return 0
-        steps, warmup = max(1, min(args.steps, 5)), min(args.warmup, 1)
+        steps, warmup = max(1, min(args.steps, 30)), min(args.warmup, 2)
         cb = run_cpu(args.workload, steps, warmup)
         line = {
             "impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus,
@@ -286,8 +296,18 @@ def main():
     for _ in range(max(args.warmup, 3)):
         r, a, m = step()
     torch.cuda.synchronize()
+    m_last = m
     n_visible = int((m["radii"] > 0).sum()) if not (args.packed or sharded) else int(m["means2d"].shape[0])
     stats["n_isects"] = int(m["tiles_per_gauss"].sum(dtype=torch.int64))   # (the per-intersection lists of meta are lazy)
+    # rows compositing reached before saturation (outside the timed region): non-zero opacity cotangent
+    for t in params.values():
+        t.grad = None
+    r, a, m = b2s.rasterization(params["means"], params["quats"], params["scales"], params["opacities"], params["colors"],
+                                cams["viewmats"], cams["Ks"], W, H, **kw)
+    m["opacities"].retain_grad()
+    torch.autograd.backward([r, a], [v_r, v_a])
+    stats["n_reached"] = int((m["opacities"].grad != 0).sum())
+    del r, a, m
 
     sampler = ClockSampler(local_rank)
     if rank == 0:
@@ -302,30 +322,74 @@ def main():
     value = pix_per_step / (ms_per_step * 1e-3) / 1e6
 
     # ---- e2e: host buffers in, host buffers out -----------------------------------------------------------
-    host_out = {"render": torch.empty(1, H, W, 3).pin_memory(), "alpha": torch.empty(1, H, W, 1).pin_memory()}
-    host_grads = {k: torch.empty_like(v).pin_memory() for k, v in leaves_host.items()}
     h2d = sum(v.numel() * 4 for v in leaves_host.values()) + sum(v.numel() * 4 for v in cam_host.values()) \
         + v_r_host.numel() * 4 + v_a_host.numel() * 4
-    d2h = sum(v.numel() * 4 for v in host_out.values()) + sum(v.numel() * 4 for v in host_grads.values())
+    d2h = (H * W * 3 + H * W) * 4 + sum(v.numel() * 4 for v in leaves_host.values())
+
+    # Two slots, three streams: the H2D of step i+1 runs while step i computes and while its results go back (PCIe is
+    # full duplex), so a step costs max(H2D, D2H, compute) instead of their sum.  Every step still moves all of its
+    # inputs in and all of its results out.
+    s_in, s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+    main = torch.cuda.current_stream(dev)
+    slots = []
+    for _ in range(2):
+        slots.append({
+            "p": {k: torch.empty_like(v, device=dev).requires_grad_() for k, v in leaves_host.items()},
+            "c": {k: torch.empty_like(v, device=dev) for k, v in cam_host.items()},
+            "vr": torch.empty_like(v_r), "va": torch.empty_like(v_a),
+            "out": {"render": torch.empty(1, H, W, 3).pin_memory(), "alpha": torch.empty(1, H, W, 1).pin_memory()},
+            "grads": {k: torch.empty_like(v).pin_memory() for k, v in leaves_host.items()},
+            "ev_in": torch.cuda.Event(), "ev_done": torch.cuda.Event(), "ev_out": None, "keep": None,
+        })
+    state = {"i": 0}
 
     def e2e_step():
-        p = {k: v.to(dev, non_blocking=True).requires_grad_() for k, v in leaves_host.items()}
-        c = {k: v.to(dev, non_blocking=True) for k, v in cam_host.items()}
-        vr, va = v_r_host.to(dev, non_blocking=True), v_a_host.to(dev, non_blocking=True)
-        r, a, _ = step(p, c, vr, va)
-        host_out["render"].copy_(r.detach(), non_blocking=True)
-        host_out["alpha"].copy_(a.detach(), non_blocking=True)
-        for k in host_grads:
-            host_grads[k].copy_(p[k].grad, non_blocking=True)
-        torch.cuda.current_stream().synchronize()      # the caller reads the host buffers after every step
+        sl = slots[state["i"] % 2]
+        state["i"] += 1
+        if sl["ev_out"] is not None:
+            sl["ev_out"].synchronize()          # the caller has read this slot's host buffers; its device buffers are free
+        with torch.cuda.stream(s_in), torch.no_grad():
+            for k, v in leaves_host.items():
+                sl["p"][k].copy_(v, non_blocking=True)
+            for k, v in cam_host.items():
+                sl["c"][k].copy_(v, non_blocking=True)
+            sl["vr"].copy_(v_r_host, non_blocking=True)
+            sl["va"].copy_(v_a_host, non_blocking=True)
+            sl["ev_in"].record(s_in)
+        main.wait_event(sl["ev_in"])
+        r, a, _ = step(sl["p"], sl["c"], sl["vr"], sl["va"])
+        sl["ev_done"].record(main)
+        sl["keep"] = (r, a)                      # keep the results alive until their copy has run
+        with torch.cuda.stream(s_out), torch.no_grad():
+            s_out.wait_event(sl["ev_done"])
+            sl["out"]["render"].copy_(r.detach(), non_blocking=True)
+            sl["out"]["alpha"].copy_(a.detach(), non_blocking=True)
+            for k in sl["grads"]:
+                sl["grads"][k].copy_(sl["p"][k].grad, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(s_out)
+            sl["ev_out"] = ev
 
-    e2e_steps = args.e2e_steps or max(3, min(args.steps, 10))
-    if args.no_e2e:
-        e2e_ms, e2e_value = float("nan"), None
-    else:
-        for _ in range(2):
+    def e2e_run(steps):
+        for _ in range(steps):
             e2e_step()
-        e2e_ms = timed(e2e_step, e2e_steps) / e2e_steps
+        for sl in slots:                         # the last results are on the host when the timed region ends
+            if sl["ev_out"] is not None:
+                sl["ev_out"].synchronize()
+
+    e2e_steps = args.e2e_steps or max(4, min(args.steps, 10))
+    if args.no_e2e:
+        e2e_ms, e2e_value = None, None
+    else:
+        e2e_run(2)
+        barrier()
+        t0 = time.perf_counter()                 # three streams: wall clock between device-wide synchronisations
+        e2e_run(e2e_steps)
+        barrier()
+        ms = torch.tensor([(time.perf_counter() - t0) * 1e3], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        e2e_ms = float(ms.item()) / e2e_steps
         e2e_value = pix_per_step / (e2e_ms * 1e-3) / 1e6
 
     if rank != 0:
@@ -333,24 +397,29 @@ def main():
             dist.destroy_process_group()
         return 0
 
-    # ---- roofline of the dominant kernel ------------------------------------------------------------------
+    # ---- roofline of the dominant HBM-bound kernel ----------------------------------------------------------
     peak, peak_src = peaks()
     I = stats["n_isects"]
     tiles = math.ceil(W / 16) * math.ceil(H / 16)
     key_bits = 32 + (tiles).bit_length() + (1).bit_length()
     K = (deg + 1) ** 2
-    ab = algorithmic_bytes(N, 1, n_visible, I, W * H, K, tiles, key_bits)
+    n_cam_local = C_total if (world > 1 and sharded) else 1
+    R = int(m_last.get("n_coarse_records") or 0) if m_last is not None else 0
+    ab = algorithmic_bytes(hi_n - lo_n, n_cam_local, n_visible, stats["n_reached"], I, R, W * H, K, tiles, key_bits)
     per_stage = {}
-    for name, s in stage.items():
-        gbs = ab.get(name, 0) / (s["ms_avg"] * 1e-3) / 1e9 if s["ms_avg"] > 0 else 0.0
-        per_stage[name] = {"ms": round(s["ms_avg"], 4), "calls_per_step": s["calls"] / args.steps,
-                           "algorithmic_bytes": ab.get(name), "GBps": round(gbs, 1), "frac_of_peak": round(gbs / peak, 4)}
-    own = {k: v for k, v in per_stage.items() if k not in ("isect_sort", "depth_order", "tile_bin")}
-    dom = max(own, key=lambda k: own[k]["ms"])
-    roofline = {"kernel": dom, "bound": "hbm", "achieved": per_stage[dom]["GBps"], "peak": peak, "unit": "GB/s",
-                "frac": per_stage[dom]["frac_of_peak"], "traffic": None, "peak_source": peak_src,
-                "note": "compositing is FP32/SFU/shared-memory bound, its HBM fraction is low by construction; "
-                        "projection and sort are the HBM-bound stages (see stages)"}
+    for name, st_ in stage.items():
+        b = ab.get(name)
+        gbs = b / (st_["ms_avg"] * 1e-3) / 1e9 if (b and st_["ms_avg"] > 0) else None
+        per_stage[name] = {"ms": round(st_["ms_avg"], 4), "calls_per_step": st_["calls"] / args.steps, "algorithmic_bytes": b,
+                           "GBps": round(gbs, 1) if gbs else None, "frac_of_peak": round(gbs / peak, 4) if gbs else None}
+    hbm_stages = {k: v for k, v in per_stage.items() if v["GBps"] and k in ("project_fwd", "sh_bwd", "project_bwd")}
+    dom = max(hbm_stages, key=lambda k: hbm_stages[k]["ms"])
+    kernel_of = {"project_fwd": "project_fwd_kernel", "sh_bwd": "sh_bwd_fused_kernel", "project_bwd": "project_bwd_kernel"}
+    roofline = {"kernel": kernel_of[dom], "stage": dom, "bound": "hbm", "achieved": per_stage[dom]["GBps"], "peak": peak,
+                "unit": "GB/s", "frac": per_stage[dom]["frac_of_peak"], "traffic": NCU_TRAFFIC.get(dom), "peak_source": peak_src,
+                "note": "largest HBM-bound kernel of the step (one launch per step; CUDA events around the launch, inside the "
+                        "timed region); the compositing kernels are instruction-issue bound (see profiles/), the sorts are "
+                        "L2-resident at this size; per-stage figures under 'stages'"}
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
@@ -361,14 +430,17 @@ def main():
                                ((", Gaussians sharded over ranks, NCCL all-to-all of projected splats to the camera owners, "
                                  "reverse all-to-all of gradients") if sharded else
                                 (", replicated Gaussians, dense-gradient all-reduce" if world > 1 else "")),
-                   "n_isects": I, "n_visible": n_visible, "l2": "inputs (1.4 GB parameters + 0.3 GB keys) exceed the 126 MB L2",
+                   "n_isects": I, "n_visible": n_visible, "n_reached": stats["n_reached"], "n_coarse_records": R,
+                   "l2": "inputs (1.4 GB parameters + 0.3 GB keys) exceed the 126 MB L2",
                    "parallelism": f"dp{world}"},
         "iters_per_s": 1e3 / ms_per_step * C_total,
         "gpu_launches": timer.launches,
-        "gpu_launches_note": "stage calls into libb2s.so inside the timed region (6 per step: project_fwd, depth_order, "
-                             "tile_bin, composite_fwd, composite_bwd, project_bwd = 9 own kernels + CUB radix passes)",
+        "gpu_launches_note": "kernels of libb2s.so launched inside the timed region (per step: project_fwd 1, depth sort 6, "
+                             "coarse binning 5, composite_fwd 1, composite_bwd 1, sh_bwd 1, project_bwd 1; all hand-written, "
+                             "no library kernels)",
         "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "steps": e2e_steps},
+                "steps": e2e_steps, "note": "rasterization() + backward driven from pinned host buffers: every step copies all "
+                "inputs in and render, alpha and all gradients out; copies of neighbouring steps overlap (2 slots, 3 streams)"},
         "roofline": roofline, "stages": per_stage, "clocks": clocks,
     }
     if world == 1 and not args.no_cpu_baseline:

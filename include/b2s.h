@@ -114,7 +114,8 @@ typedef struct {
     float* v_scales;    /* [N,3] */
     float* v_opacities; /* [N] or NULL */
     float* v_sh_coeffs; /* [N, sh_stride_k, 3] or NULL; rows >= (deg+1)^2 are not touched */
-    int32_t stages;         /* 0 = both; 1 = SH colour VJP only (v_sh_coeffs, v_means); 2 = projection VJP only */
+    int32_t stages;         /* 0 = both; 1 = SH colour VJP only (v_sh_coeffs, v_means); 2 = projection VJP only (when
+                               sh_coeffs and v_sh_coeffs are set it ADDS to the v_means a stages == 1 call left) */
 } b2s_project_bwd_args;
 B2S_API int b2s_project_bwd(const b2s_project_bwd_args* a, b2s_stream_t stream);
 

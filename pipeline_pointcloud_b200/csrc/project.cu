@@ -461,7 +461,9 @@ extern "C" int b2s_project_bwd(const b2s_project_bwd_args* a, b2s_stream_t strea
         B2S_LAUNCH_CHECK();
     }
     if (geom) {
-        auto kern2 = sh ? project_bwd_kernel<true> : project_bwd_kernel<false>;
+        // stages == 2 with the SH pointers set: the SH part is already in v_means (an earlier stages == 1 call)
+        const bool means_acc = a->sh_coeffs != nullptr && a->v_sh_coeffs != nullptr;
+        auto kern2 = means_acc ? project_bwd_kernel<true> : project_bwd_kernel<false>;
         kern2<<<(unsigned)cdiv(a->N, BWD_THREADS), BWD_THREADS, cam_bytes, st>>>(*a);
         B2S_LAUNCH_CHECK();
     }

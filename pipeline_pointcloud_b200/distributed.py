@@ -377,6 +377,7 @@ def rasterization_distributed(means, quats, scales, opacities, colors, viewmats,
         render_colors, render_alphas = ops.rasterize_to_pixels(
             means2d_m, conics_m, cols_m, opac_m, width, height, tile_size, None, None,
             backgrounds=backgrounds, packed=True, absgrad=absgrad, bins=bins, n_cameras=C_local)
+        meta["n_coarse_records"] = bins.n_records
         cache = {}
 
         def lists():

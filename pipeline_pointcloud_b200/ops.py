@@ -170,19 +170,28 @@ class _ProjectFused(torch.autograd.Function):
 
         for c0 in range(0, max(C, 1), MAX_CAMS):
             c1 = min(C, c0 + MAX_CAMS)
-            a = L.ProjectBwdArgs(
-                N=N, C=c1 - c0, means=ptr(means), quats=ptr(quats), scales=ptr(scales), opacities=ptr(opacities),
-                viewmats=ptr(viewmats[c0:c1]), Ks=ptr(Ks[c0:c1]), width=width, height=height, eps2d=eps2d,
-                near_plane=near_plane, far_plane=far_plane, radius_clip=radius_clip, antialiased=int(antialiased),
-                sh_coeffs=ptr(sh_coeffs), campos=sl(campos, c0, c1), sh_degree=int(sh_degree) if with_sh else 0,
-                sh_stride_k=sh_coeffs.shape[1] if with_sh else 0, radii=ptr(radii[c0:c1]),
-                v_means2d=sl(v_means2d, c0, c1), v_depths=sl(v_depths, c0, c1), v_conics=sl(v_conics, c0, c1),
-                v_compensations=sl(v_comps, c0, c1), v_opacities_out=sl(v_opac_out, c0, c1),
-                v_colors=sl(v_colors, c0, c1), accumulate=int(c0 > 0),
-                v_means=ptr(v_means), v_quats=ptr(v_quats), v_scales=ptr(v_scales), v_opacities=ptr(v_opac),
-                v_sh_coeffs=ptr(v_sh), stages=0)
-            with _stage("project_bwd"):
-                check(lib.b2s_project_bwd(ctypes.byref(a), st), "b2s_project_bwd")
+
+            def args(stages):
+                return L.ProjectBwdArgs(
+                    N=N, C=c1 - c0, means=ptr(means), quats=ptr(quats), scales=ptr(scales), opacities=ptr(opacities),
+                    viewmats=ptr(viewmats[c0:c1]), Ks=ptr(Ks[c0:c1]), width=width, height=height, eps2d=eps2d,
+                    near_plane=near_plane, far_plane=far_plane, radius_clip=radius_clip, antialiased=int(antialiased),
+                    sh_coeffs=ptr(sh_coeffs), campos=sl(campos, c0, c1), sh_degree=int(sh_degree) if with_sh else 0,
+                    sh_stride_k=sh_coeffs.shape[1] if with_sh else 0, radii=ptr(radii[c0:c1]),
+                    v_means2d=sl(v_means2d, c0, c1), v_depths=sl(v_depths, c0, c1), v_conics=sl(v_conics, c0, c1),
+                    v_compensations=sl(v_comps, c0, c1), v_opacities_out=sl(v_opac_out, c0, c1),
+                    v_colors=sl(v_colors, c0, c1), accumulate=int(c0 > 0),
+                    v_means=ptr(v_means), v_quats=ptr(v_quats), v_scales=ptr(v_scales), v_opacities=ptr(v_opac),
+                    v_sh_coeffs=ptr(v_sh), stages=stages)
+
+            if with_sh and TIMER is not None:     # time the two kernels of the call separately (bench.py)
+                with _stage("sh_bwd"):
+                    check(lib.b2s_project_bwd(ctypes.byref(args(1)), st), "b2s_project_bwd")
+                with _stage("project_bwd"):
+                    check(lib.b2s_project_bwd(ctypes.byref(args(2)), st), "b2s_project_bwd")
+            else:
+                with _stage("project_bwd", launches=2 if with_sh else 1):
+                    check(lib.b2s_project_bwd(ctypes.byref(args(0)), st), "b2s_project_bwd")
         return (v_means, v_quats, v_scales, v_opac, v_sh) + (None,) * 13
 
 
@@ -558,7 +567,7 @@ def bin_coarse(means2d: Tensor, radii: Tensor, depths: Tensor, tile_size: int, t
                   "b2s_coarse_count")
     sorted_ids = torch.empty(max(M, 1), dtype=torch.int32, device=dev)
     ws = _ws(lib.b2s_depth_order_workspace_bytes(M), dev)
-    with _stage("depth_order"):
+    with _stage("depth_order", launches=6):      # histogram, scan, 4 digit passes
         check(lib.b2s_depth_order(M, ptr(depth_keys), ptr(row_ids), ptr(sorted_ids), ptr(ws), ws.numel(), st), "b2s_depth_order")
     # The one host sync of a forward (sizes the record buffers).  The depth sort is already enqueued, so the GPU
     # keeps working while the host waits for the counts that stage 1 produced.
@@ -575,7 +584,7 @@ def bin_coarse(means2d: Tensor, radii: Tensor, depths: Tensor, tile_size: int, t
     ids = torch.empty(n_alloc, dtype=torch.int32, device=dev)
     offsets = torch.empty(C * bw * bh + 1, dtype=torch.int32, device=dev)
     ws2 = _ws(lib.b2s_coarse_bin_workspace_bytes(M, n_records), dev)
-    with _stage("coarse_bin"):
+    with _stage("coarse_bin", launches=5 + ((C * bw * bh - 1).bit_length() > 8)):   # expand, histogram, scan, passes, offsets
         check(lib.b2s_coarse_bin(M, N, ptr(cam), n_records, ptr(sorted_ids), ptr(means2d), ptr(radii), C, tile_size, tile_width,
                                  tile_height, ptr(recs), ptr(ids), ptr(offsets), ptr(ws2), ws2.numel(), st), "b2s_coarse_bin")
     return CoarseBins(recs, ids, offsets, sorted_ids, n_records, n_isects)

@@ -183,7 +183,7 @@ def rasterization(
         "tiles_per_gauss": tiles_per_gauss, "width": width, "height": height, "tile_size": tile_size, "n_cameras": C,
     })
     if bins is not None:
-        meta["n_isects"] = bins.n_isects
+        meta["n_isects"], meta["n_coarse_records"] = bins.n_isects, bins.n_records
         meta.set_lazy("flatten_ids", lambda: lists()["flat"])
         meta.set_lazy("isect_offsets", lambda: lists()["off"])
         meta.set_lazy("isect_ids", lambda: lists()["mk"]())
