@@ -39,7 +39,11 @@ WORKLOADS = {
 }
 METRIC = "3DGS rasterization fwd+bwd throughput"
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture (profiles/), config 3
-NCU_TRAFFIC = {}
+NCU_TRAFFIC = {   # profiles/r01_ncu_full_v6_summary.md
+    "project_fwd": 1_628_177_000,   # 1.313962 GB read + 0.314215 GB written
+    "sh_bwd": 1_382_513_000,        # 0.226162 GB read + 1.156351 GB written
+    "project_bwd": 397_205_000,     # 0.244680 GB read + 0.152525 GB written
+}
 UNIT = "Mpix/s"
 
 
@@ -416,7 +420,7 @@ def main():
     dom = max(hbm_stages, key=lambda k: hbm_stages[k]["ms"])
     kernel_of = {"project_fwd": "project_fwd_kernel", "sh_bwd": "sh_bwd_fused_kernel", "project_bwd": "project_bwd_kernel"}
     roofline = {"kernel": kernel_of[dom], "stage": dom, "bound": "hbm", "achieved": per_stage[dom]["GBps"], "peak": peak,
-                "unit": "GB/s", "frac": per_stage[dom]["frac_of_peak"], "traffic": NCU_TRAFFIC.get(dom), "peak_source": peak_src,
+                "unit": "GB/s", "frac": per_stage[dom]["frac_of_peak"], "traffic": NCU_TRAFFIC.get(dom) if args.workload == "config3" and world == 1 else None, "peak_source": peak_src,
                 "note": "largest HBM-bound kernel of the step (one launch per step; CUDA events around the launch, inside the "
                         "timed region); the compositing kernels are instruction-issue bound (see profiles/), the sorts are "
                         "L2-resident at this size; per-stage figures under 'stages'"}
