@@ -142,16 +142,23 @@ B2S_API int b2s_quat_scale_to_covar_preci(int64_t N, const float* quats, const f
  *   b2s_isect_sort   -> sorted isect_ids / flatten_ids                (stable LSD radix)
  *   b2s_isect_offsets-> offsets [C*tile_h*tile_w] int32
  * M = number of rows (C*N dense, nnz packed).  camera_ids == NULL means dense rows (cam = row / N).
+ *
+ * Tile-row window (`rows`, a HOST struct read during the call; NULL = the whole grid): restricts every
+ * tile rectangle to tile rows [row_lo, row_hi) of the image's tile grid.  This is how a rank of a multi-GPU
+ * job bins only the tile stripe it owns: tile ids, keys and offsets stay those of the whole
+ * image, so a stripe's sorted list is exactly the single-GPU list filtered by tile row.
  * ---------------------------------------------------------------------------------------------- */
+typedef struct { int32_t row_lo, row_hi; } b2s_tile_rows;
 B2S_API int b2s_isect_count(int64_t M, const float* means2d, const int32_t* radii, int32_t tile_size,
-                            int32_t tile_w, int32_t tile_h, int32_t* tiles_per_gauss, b2s_stream_t stream);
+                            int32_t tile_w, int32_t tile_h, int32_t* tiles_per_gauss, const b2s_tile_rows* rows,
+                            b2s_stream_t stream);
 B2S_API int64_t b2s_isect_scan_workspace_bytes(int64_t M);
 B2S_API int b2s_isect_scan(int64_t M, const int32_t* tiles_per_gauss, int32_t* cum_tiles, int64_t* total,
                            void* workspace, int64_t workspace_bytes, b2s_stream_t stream);
 B2S_API int b2s_isect_fill(int64_t M, int64_t N, const int64_t* camera_ids /* or NULL */, const float* means2d,
                            const int32_t* radii, const float* depths, const int32_t* cum_tiles, int32_t tile_size,
                            int32_t tile_w, int32_t tile_h, int64_t* isect_ids, int32_t* flatten_ids,
-                           b2s_stream_t stream);
+                           const b2s_tile_rows* rows, b2s_stream_t stream);
 B2S_API int64_t b2s_isect_sort_workspace_bytes(int64_t n_isects);
 B2S_API int b2s_isect_sort(int64_t n_isects, int32_t key_bits, const int64_t* isect_ids_in, const int32_t* flatten_ids_in,
                            int64_t* isect_ids_out, int32_t* flatten_ids_out, void* workspace, int64_t workspace_bytes,
@@ -184,7 +191,7 @@ B2S_API int b2s_tile_bin(int64_t M, int64_t N, const int64_t* camera_ids /* or N
                          const int32_t* sorted_ids, const float* means2d, const int32_t* radii, int32_t C,
                          int32_t tile_size, int32_t tile_w, int32_t tile_h, void* tile_keys_sorted /* [I] x 4 bytes */,
                          int32_t* flatten_ids, int32_t* offsets, void* workspace, int64_t workspace_bytes,
-                         b2s_stream_t stream);
+                         const b2s_tile_rows* rows, b2s_stream_t stream);
 B2S_API int b2s_isect_ids_from_bins(int64_t n_isects, int32_t key_bytes, const void* tile_keys_sorted,
                                     const int32_t* flatten_ids, const float* depths, int64_t* isect_ids,
                                     b2s_stream_t stream);
@@ -205,12 +212,14 @@ B2S_API int b2s_isect_ids_from_bins(int64_t n_isects, int32_t key_bytes, const v
  * Needs C * ceil(tile_w/8) * ceil(tile_h/8) <= 65536 (B2S_E_UNSUPPORTED otherwise). */
 #define B2S_COARSE 8
 B2S_API int b2s_coarse_count(int64_t M, const float* means2d, const int32_t* radii, int32_t tile_size, int32_t tile_w,
-                             int32_t tile_h, int64_t* total /* device, accumulated */, b2s_stream_t stream);
+                             int32_t tile_h, int64_t* total /* device, accumulated */, const b2s_tile_rows* rows,
+                             b2s_stream_t stream);
 B2S_API int64_t b2s_coarse_bin_workspace_bytes(int64_t M, int64_t n_records);
 B2S_API int b2s_coarse_bin(int64_t M, int64_t N, const int64_t* camera_ids /* or NULL */, int64_t n_records,
                            const int32_t* sorted_ids, const float* means2d, const int32_t* radii, int32_t C,
                            int32_t tile_size, int32_t tile_w, int32_t tile_h, uint32_t* bin_recs, int32_t* bin_ids,
-                           int32_t* bin_offsets, void* workspace, int64_t workspace_bytes, b2s_stream_t stream);
+                           int32_t* bin_offsets, void* workspace, int64_t workspace_bytes, const b2s_tile_rows* rows,
+                           b2s_stream_t stream);
 
 /* Packed layout (gsplat `packed=True`): gather the visible rows `sel` (ascending dense indices c*N+n) of the
  * stage-1 outputs into nnz-row tensors (+ camera_ids / gaussian_ids), and scatter gradients back into
@@ -240,7 +249,9 @@ B2S_API int b2s_join_grads(int64_t n, int32_t channels, const float* g_means2d, 
                            const float* g_conics, const float* g_opacities, const float* g_colors, float* out,
                            b2s_stream_t stream);
 B2S_API int b2s_scatter_grads(int64_t nnz, const int64_t* sel, int32_t channels, const float* in, float* v_means2d,
-                              float* v_depths, float* v_conics, float* v_opacities, float* v_colors, b2s_stream_t stream);
+                              float* v_depths, float* v_conics, float* v_opacities, float* v_colors,
+                              int32_t accumulate /* 1: rows may repeat in sel (tile stripes), records are summed */,
+                              b2s_stream_t stream);
 
 /* Fused pack + exchange over NVLink peer memory (replaces b2s_pack_payload + NCCL all-to-all, and
  * b2s_join_grads + the reverse all-to-all): the kernel stores every record straight into the destination
@@ -282,6 +293,10 @@ typedef struct {
     const int32_t* bin_offsets; /* [C*bins_h*bins_w + 1] or NULL */
     const uint32_t* bin_recs;   /* [n_isects] (n_isects = number of coarse records) */
     const int32_t* bin_ids;     /* [n_isects] */
+    /* tile-row window (multi-GPU tile stripes): only tile rows [tile_row_lo, tile_row_hi) of the grid are composited
+     * and the per-pixel tensors (render_colors, render_alphas, last_ids, final_T) hold just those rows:
+     * [C, min(height, 16*tile_row_hi) - 16*tile_row_lo, W, ..].  0, 0 = the whole grid. */
+    int32_t tile_row_lo, tile_row_hi;
 } b2s_composite_fwd_args;
 B2S_API int b2s_composite_fwd(const b2s_composite_fwd_args* a, b2s_stream_t stream);
 
@@ -302,6 +317,7 @@ typedef struct {
     float* v_colors;      /* [M,channels] */
     float* v_opacities;   /* [M] */
     const int32_t* bin_offsets; const uint32_t* bin_recs; const int32_t* bin_ids;   /* as in the forward */
+    int32_t tile_row_lo, tile_row_hi; /* as in the forward: the per-pixel tensors hold the window's rows only */
 } b2s_composite_bwd_args;
 B2S_API int b2s_composite_bwd(const b2s_composite_bwd_args* a, b2s_stream_t stream);
 

@@ -21,6 +21,16 @@ class B2SError(RuntimeError):
     pass
 
 
+class TileRows(Structure):
+    """b2s_tile_rows: tile-row window [row_lo, row_hi) of the tile grid (None / NULL = the whole grid)."""
+    _fields_ = [("row_lo", c_int32), ("row_hi", c_int32)]
+
+
+def tile_rows(rows):
+    """ctypes argument for an optional (row_lo, row_hi) window."""
+    return None if rows is None else ctypes.byref(TileRows(int(rows[0]), int(rows[1])))
+
+
 class ProjectFwdArgs(Structure):
     _fields_ = [
         ("N", c_int64), ("C", c_int32),
@@ -65,6 +75,7 @@ class CompositeFwdArgs(Structure):
         ("backgrounds", c_void_p), ("isect_offsets", c_void_p), ("flatten_ids", c_void_p),
         ("render_colors", c_void_p), ("render_alphas", c_void_p), ("last_ids", c_void_p), ("final_T", c_void_p),
         ("bin_offsets", c_void_p), ("bin_recs", c_void_p), ("bin_ids", c_void_p),
+        ("tile_row_lo", c_int32), ("tile_row_hi", c_int32),
     ]
 
 
@@ -79,6 +90,7 @@ class CompositeBwdArgs(Structure):
         ("v_render_colors", c_void_p), ("v_render_alphas", c_void_p),
         ("v_means2d", c_void_p), ("v_means2d_abs", c_void_p), ("v_conics", c_void_p), ("v_colors", c_void_p),
         ("v_opacities", c_void_p), ("bin_offsets", c_void_p), ("bin_recs", c_void_p), ("bin_ids", c_void_p),
+        ("tile_row_lo", c_int32), ("tile_row_hi", c_int32),
     ]
 
 
@@ -91,11 +103,11 @@ SYMBOLS = {
     "b2s_sh_fwd": (c_int32, [c_int64, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "b2s_sh_bwd": (c_int32, [c_int64, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "b2s_quat_scale_to_covar_preci": (c_int32, [c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
-    "b2s_isect_count": (c_int32, [c_int64, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p]),
+    "b2s_isect_count": (c_int32, [c_int64, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p, POINTER(TileRows), c_void_p]),
     "b2s_isect_scan_workspace_bytes": (c_int64, [c_int64]),
     "b2s_isect_scan": (c_int32, [c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
     "b2s_isect_fill": (c_int32, [c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32,
-                                 c_int32, c_void_p, c_void_p, c_void_p]),
+                                 c_int32, c_void_p, c_void_p, POINTER(TileRows), c_void_p]),
     "b2s_isect_sort_workspace_bytes": (c_int64, [c_int64]),
     "b2s_isect_sort": (c_int32, [c_int64, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
     "b2s_isect_offsets": (c_int32, [c_int64, c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p]),
@@ -105,18 +117,18 @@ SYMBOLS = {
     "b2s_tile_key_bytes": (c_int32, [c_int32, c_int32, c_int32]),
     "b2s_tile_bin_workspace_bytes": (c_int64, [c_int64, c_int64]),
     "b2s_tile_bin": (c_int32, [c_int64, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_int32, c_int32,
-                               c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
+                               c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, POINTER(TileRows), c_void_p]),
     "b2s_isect_ids_from_bins": (c_int32, [c_int64, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
-    "b2s_coarse_count": (c_int32, [c_int64, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p]),
+    "b2s_coarse_count": (c_int32, [c_int64, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p, POINTER(TileRows), c_void_p]),
     "b2s_coarse_bin_workspace_bytes": (c_int64, [c_int64, c_int64]),
     "b2s_coarse_bin": (c_int32, [c_int64, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_int32, c_int32,
-                                 c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
+                                 c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, POINTER(TileRows), c_void_p]),
     "b2s_pack_rows": (c_int32, [c_int64, c_int64, c_void_p, c_int32] + [c_void_p] * 17),
     "b2s_unpack_rows": (c_int32, [c_int64, c_void_p, c_int32] + [c_void_p] * 11),
     "b2s_pack_payload": (c_int32, [c_int64, c_int64, c_void_p, c_int32, c_int32, c_int64] + [c_void_p] * 9),
     "b2s_split_payload": (c_int32, [c_int64, c_int32] + [c_void_p] * 11),
     "b2s_join_grads": (c_int32, [c_int64, c_int32] + [c_void_p] * 7),
-    "b2s_scatter_grads": (c_int32, [c_int64, c_void_p, c_int32] + [c_void_p] * 7),
+    "b2s_scatter_grads": (c_int32, [c_int64, c_void_p, c_int32] + [c_void_p] * 6 + [c_int32, c_void_p]),
     "b2s_p2p_pack": (c_int32, [c_int64, c_int64, c_void_p, c_int32, c_int32, c_int64] + [c_void_p] * 7 +
                      [c_int32, c_void_p, c_void_p, c_void_p, c_void_p]),
     "b2s_p2p_join": (c_int32, [c_int64, c_int32] + [c_void_p] * 5 + [c_int32, c_void_p, c_void_p, c_void_p, c_void_p]),

@@ -255,14 +255,19 @@ B2S_HD void project_mid_fast(const Camera& cam, const float mean[3], const Sym3&
 
 B2S_HD int iclamp(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
 
-// Tile rectangle [min,max) of a projected Gaussian   
-B2S_HD void tile_rect(float x2d, float y2d, int radius, float tile_size, int tile_w, int tile_h, int& x0, int& y0, int& x1,
-                      int& y1) {
+// Tile rectangle [min,max) of a projected Gaussian   (SURVEY 8a row 4), rows clipped to the window
+// [row_lo, row_hi) of the tile grid (the whole grid: 0, tile_h; a tile stripe of a multi-GPU job otherwise)
+B2S_HD void tile_rect(float x2d, float y2d, int radius, float tile_size, int tile_w, int row_lo, int row_hi, int& x0, int& y0,
+                      int& x1, int& y1) {
     float mx = RN_DIV(x2d, tile_size), my = RN_DIV(y2d, tile_size), r = RN_DIV((float)radius, tile_size);
     int ax = (int)floorf(RN_SUB(mx, r)), ay = (int)floorf(RN_SUB(my, r));
     int bx = (int)ceilf(RN_ADD(mx, r)), by = (int)ceilf(RN_ADD(my, r));
-    x0 = iclamp(ax, 0, tile_w); y0 = iclamp(ay, 0, tile_h);
-    x1 = iclamp(bx, 0, tile_w); y1 = iclamp(by, 0, tile_h);
+    x0 = iclamp(ax, 0, tile_w); y0 = iclamp(ay, row_lo, row_hi);
+    x1 = iclamp(bx, 0, tile_w); y1 = iclamp(by, row_lo, row_hi);
+}
+B2S_HD void tile_rect(float x2d, float y2d, int radius, float tile_size, int tile_w, int tile_h, int& x0, int& y0, int& x1,
+                      int& y1) {
+    tile_rect(x2d, y2d, radius, tile_size, tile_w, 0, tile_h, x0, y0, x1, y1);
 }
 
 // ---------------------------------------------------------------------------------------------

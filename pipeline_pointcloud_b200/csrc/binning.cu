@@ -17,7 +17,7 @@ namespace b2s {
 // count (only used by the stage-level op; the training path gets tiles_per_gauss from stage 1)
 // -------------------------------------------------------------------------------------------------
 __global__ void isect_count_kernel(int64_t M, const float2* __restrict__ means2d, const int32_t* __restrict__ radii,
-                                   float tile_size, int tile_w, int tile_h, int32_t* __restrict__ tiles) {
+                                   float tile_size, int tile_w, int row_lo, int row_hi, int32_t* __restrict__ tiles) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= M) return;
     int r = radii[i];
@@ -25,7 +25,7 @@ __global__ void isect_count_kernel(int64_t M, const float2* __restrict__ means2d
     if (r > 0) {
         float2 m = means2d[i];
         int x0, y0, x1, y1;
-        tile_rect(m.x, m.y, r, tile_size, tile_w, tile_h, x0, y0, x1, y1);
+        tile_rect(m.x, m.y, r, tile_size, tile_w, row_lo, row_hi, x0, y0, x1, y1);
         cnt = (x1 - x0) * (y1 - y0);
     }
     tiles[i] = cnt;
@@ -133,7 +133,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_kernel(int64_t M, const int
 __global__ void isect_fill_kernel(int64_t M, int64_t N, const int64_t* __restrict__ camera_ids,
                                   const float2* __restrict__ means2d, const int32_t* __restrict__ radii,
                                   const float* __restrict__ depths, const int32_t* __restrict__ cum, float tile_size,
-                                  int tile_w, int tile_h, int tile_bits, int64_t* __restrict__ keys,
+                                  int tile_w, int row_lo, int row_hi, int tile_bits, int64_t* __restrict__ keys,
                                   int32_t* __restrict__ vals) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= M) return;
@@ -141,7 +141,7 @@ __global__ void isect_fill_kernel(int64_t M, int64_t N, const int64_t* __restric
     if (r <= 0) return;
     float2 m = means2d[i];
     int x0, y0, x1, y1;
-    tile_rect(m.x, m.y, r, tile_size, tile_w, tile_h, x0, y0, x1, y1);
+    tile_rect(m.x, m.y, r, tile_size, tile_w, row_lo, row_hi, x0, y0, x1, y1);
     if (x1 <= x0 || y1 <= y0) return;
     int64_t cam = camera_ids ? camera_ids[i] : (i / N);
     uint64_t hi = (uint64_t)cam << tile_bits;
@@ -207,7 +207,7 @@ __global__ void __launch_bounds__(EXP_THREADS) expand_kernel(int64_t M, int64_t 
                                                              const int32_t* __restrict__ sorted_ids,
                                                              const float2* __restrict__ means2d,
                                                              const int32_t* __restrict__ radii, float tile_size, int tile_w,
-                                                             int tile_h, int tile_bits, unsigned long long* status,
+                                                             int row_lo, int row_hi, int tile_bits, unsigned long long* status,
                                                              unsigned int* cta_counter, KeyT* __restrict__ tile_keys,
                                                              int32_t* __restrict__ vals) {
     __shared__ int s_start[EXP_THREADS];   // output offset of each Gaussian relative to its warp's first
@@ -227,7 +227,7 @@ __global__ void __launch_bounds__(EXP_THREADS) expand_kernel(int64_t M, int64_t 
         int r = radii[id];
         if (r > 0) {
             float2 m = means2d[id];
-            tile_rect(m.x, m.y, r, tile_size, tile_w, tile_h, x0, y0, x1, y1);
+            tile_rect(m.x, m.y, r, tile_size, tile_w, row_lo, row_hi, x0, y0, x1, y1);
             cnt = max(0, x1 - x0) * max(0, y1 - y0);
         }
     }
@@ -315,7 +315,7 @@ static_assert(CB == 8, "the record format packs two 8-bit tile masks");
 __device__ __forceinline__ int coarse_span(int t0, int t1) { return (t1 + CB - 1) / CB - t0 / CB; }   // t1 > t0
 
 __global__ void coarse_count_kernel(int64_t M, const float2* __restrict__ means2d, const int32_t* __restrict__ radii,
-                                    float tile_size, int tile_w, int tile_h, unsigned long long* __restrict__ total) {
+                                    float tile_size, int tile_w, int row_lo, int row_hi, unsigned long long* __restrict__ total) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     int cnt = 0;
     if (i < M) {
@@ -323,7 +323,7 @@ __global__ void coarse_count_kernel(int64_t M, const float2* __restrict__ means2
         if (r > 0) {
             const float2 m = means2d[i];
             int x0, y0, x1, y1;
-            tile_rect(m.x, m.y, r, tile_size, tile_w, tile_h, x0, y0, x1, y1);
+            tile_rect(m.x, m.y, r, tile_size, tile_w, row_lo, row_hi, x0, y0, x1, y1);
             if (x1 > x0 && y1 > y0) cnt = coarse_span(x0, x1) * coarse_span(y0, y1);
         }
     }
@@ -338,7 +338,7 @@ __global__ void __launch_bounds__(EXP_THREADS) coarse_expand_kernel(int64_t M, i
                                                                     const int32_t* __restrict__ sorted_ids,
                                                                     const float2* __restrict__ means2d,
                                                                     const int32_t* __restrict__ radii, float tile_size,
-                                                                    int tile_w, int tile_h, int bins_w, int bins_h,
+                                                                    int tile_w, int row_lo, int row_hi, int bins_w, int bins_h,
                                                                     unsigned long long* status, unsigned int* cta_counter,
                                                                     uint32_t* __restrict__ recs, int32_t* __restrict__ vals) {
     __shared__ int s_start[EXP_THREADS];
@@ -359,7 +359,7 @@ __global__ void __launch_bounds__(EXP_THREADS) coarse_expand_kernel(int64_t M, i
         const int r = radii[id];
         if (r > 0) {
             const float2 m = means2d[id];
-            tile_rect(m.x, m.y, r, tile_size, tile_w, tile_h, x0, y0, x1, y1);
+            tile_rect(m.x, m.y, r, tile_size, tile_w, row_lo, row_hi, x0, y0, x1, y1);
             if (x1 > x0 && y1 > y0) cnt = coarse_span(x0, x1) * coarse_span(y0, y1);
         }
     }
@@ -466,13 +466,22 @@ static int bit_length(int64_t v) {
 
 using namespace b2s;
 
+// tile-row window of a call: NULL = the whole grid
+static inline bool row_window(const b2s_tile_rows* rows, int tile_h, int& lo, int& hi) {
+    lo = 0; hi = tile_h;
+    if (rows) { lo = rows->row_lo; hi = rows->row_hi; }
+    return lo >= 0 && hi >= lo && hi <= tile_h;
+}
+
 extern "C" int b2s_isect_count(int64_t M, const float* means2d, const int32_t* radii, int32_t tile_size, int32_t tile_w,
-                               int32_t tile_h, int32_t* tiles_per_gauss, b2s_stream_t stream) {
+                               int32_t tile_h, int32_t* tiles_per_gauss, const b2s_tile_rows* rows, b2s_stream_t stream) {
     B2S_REQUIRE(M >= 0 && tile_size > 0 && tile_w > 0 && tile_h > 0, "bad sizes");
+    int row_lo, row_hi;
+    B2S_REQUIRE(row_window(rows, tile_h, row_lo, row_hi), "bad tile-row window");
     if (M == 0) return 0;
     B2S_REQUIRE(means2d && radii && tiles_per_gauss, "null pointer");
     isect_count_kernel<<<(unsigned)cdiv(M, 256), 256, 0, (cudaStream_t)stream>>>(
-        M, reinterpret_cast<const float2*>(means2d), radii, (float)tile_size, tile_w, tile_h, tiles_per_gauss);
+        M, reinterpret_cast<const float2*>(means2d), radii, (float)tile_size, tile_w, row_lo, row_hi, tiles_per_gauss);
     B2S_LAUNCH_CHECK();
     return 0;
 }
@@ -507,15 +516,18 @@ extern "C" int b2s_isect_scan(int64_t M, const int32_t* tiles_per_gauss, int32_t
 
 extern "C" int b2s_isect_fill(int64_t M, int64_t N, const int64_t* camera_ids, const float* means2d, const int32_t* radii,
                               const float* depths, const int32_t* cum_tiles, int32_t tile_size, int32_t tile_w,
-                              int32_t tile_h, int64_t* isect_ids, int32_t* flatten_ids, b2s_stream_t stream) {
+                              int32_t tile_h, int64_t* isect_ids, int32_t* flatten_ids, const b2s_tile_rows* rows,
+                              b2s_stream_t stream) {
     B2S_REQUIRE(M >= 0 && tile_size > 0 && tile_w > 0 && tile_h > 0, "bad sizes");
+    int row_lo, row_hi;
+    B2S_REQUIRE(row_window(rows, tile_h, row_lo, row_hi), "bad tile-row window");
     if (M == 0) return 0;
     B2S_REQUIRE(camera_ids != nullptr || N > 0, "dense rows need N");
     B2S_REQUIRE(means2d && radii && depths && cum_tiles, "null pointer");
     int tile_bits = bit_length((int64_t)tile_w * tile_h);
     isect_fill_kernel<<<(unsigned)cdiv(M, 256), 256, 0, (cudaStream_t)stream>>>(
         M, N, camera_ids, reinterpret_cast<const float2*>(means2d), radii, depths, cum_tiles, (float)tile_size, tile_w,
-        tile_h, tile_bits, isect_ids, flatten_ids);
+        row_lo, row_hi, tile_bits, isect_ids, flatten_ids);
     B2S_LAUNCH_CHECK();
     return 0;
 }
@@ -607,7 +619,7 @@ extern "C" int64_t b2s_tile_bin_workspace_bytes(int64_t M, int64_t n_isects) {
 
 template <typename KeyT>
 static int tile_bin_impl(int64_t M, int64_t N, const int64_t* camera_ids, int64_t n_isects, const int32_t* sorted_ids,
-                         const float* means2d, const int32_t* radii, int tile_size, int tile_w, int tile_h, int tile_bits,
+                         const float* means2d, const int32_t* radii, int tile_size, int tile_w, int tile_h, int row_lo, int row_hi, int tile_bits,
                          int key_bits, int64_t total_tiles, void* tile_keys_sorted, int32_t* flatten_ids, int32_t* offsets,
                          char* w, cudaStream_t st) {
     const int n_tiles = tile_w * tile_h;
@@ -624,7 +636,7 @@ static int tile_bin_impl(int64_t M, int64_t N, const int64_t* camera_ids, int64_
     unsigned int* counter = reinterpret_cast<unsigned int*>(w);
     unsigned long long* status = reinterpret_cast<unsigned long long*>(w + 16);
     expand_kernel<KeyT><<<(unsigned)ctas, EXP_THREADS, 0, st>>>(
-        M, N, camera_ids, sorted_ids, reinterpret_cast<const float2*>(means2d), radii, (float)tile_size, tile_w, tile_h,
+        M, N, camera_ids, sorted_ids, reinterpret_cast<const float2*>(means2d), radii, (float)tile_size, tile_w, row_lo, row_hi,
         tile_bits, status, counter, keys_u, vals_u);
     B2S_LAUNCH_CHECK();
     {
@@ -641,8 +653,10 @@ static int tile_bin_impl(int64_t M, int64_t N, const int64_t* camera_ids, int64_
 extern "C" int b2s_tile_bin(int64_t M, int64_t N, const int64_t* camera_ids, int64_t n_isects, const int32_t* sorted_ids,
                             const float* means2d, const int32_t* radii, int32_t C, int32_t tile_size, int32_t tile_w,
                             int32_t tile_h, void* tile_keys_sorted, int32_t* flatten_ids, int32_t* offsets,
-                            void* workspace, int64_t workspace_bytes, b2s_stream_t stream) {
+                            void* workspace, int64_t workspace_bytes, const b2s_tile_rows* rows, b2s_stream_t stream) {
     B2S_REQUIRE(M >= 0 && n_isects >= 0 && C >= 0 && tile_size > 0 && tile_w > 0 && tile_h > 0 && offsets, "bad args");
+    int row_lo, row_hi;
+    B2S_REQUIRE(row_window(rows, tile_h, row_lo, row_hi), "bad tile-row window");
     cudaStream_t st = (cudaStream_t)stream;
     const int n_tiles = tile_w * tile_h;
     const int64_t total_tiles = (int64_t)C * n_tiles;
@@ -663,9 +677,9 @@ extern "C" int b2s_tile_bin(int64_t M, int64_t N, const int64_t* camera_ids, int
     char* w = reinterpret_cast<char*>(workspace);
     if (key_bits <= 16)
         return tile_bin_impl<uint16_t>(M, N, camera_ids, n_isects, sorted_ids, means2d, radii, tile_size, tile_w, tile_h,
-                                       tile_bits, key_bits, total_tiles, tile_keys_sorted, flatten_ids, offsets, w, st);
+                                       row_lo, row_hi, tile_bits, key_bits, total_tiles, tile_keys_sorted, flatten_ids, offsets, w, st);
     return tile_bin_impl<uint32_t>(M, N, camera_ids, n_isects, sorted_ids, means2d, radii, tile_size, tile_w, tile_h,
-                                   tile_bits, key_bits, total_tiles, tile_keys_sorted, flatten_ids, offsets, w, st);
+                                   row_lo, row_hi, tile_bits, key_bits, total_tiles, tile_keys_sorted, flatten_ids, offsets, w, st);
 }
 
 extern "C" int b2s_isect_ids_from_bins(int64_t n_isects, int32_t key_bytes, const void* tile_keys_sorted,
@@ -689,12 +703,14 @@ extern "C" int b2s_isect_ids_from_bins(int64_t n_isects, int32_t key_bytes, cons
 // two-level binning entry points
 // ---------------------------------------------------------------------------------------------------
 extern "C" int b2s_coarse_count(int64_t M, const float* means2d, const int32_t* radii, int32_t tile_size, int32_t tile_w,
-                                int32_t tile_h, int64_t* total, b2s_stream_t stream) {
+                                int32_t tile_h, int64_t* total, const b2s_tile_rows* rows, b2s_stream_t stream) {
     B2S_REQUIRE(M >= 0 && tile_size > 0 && tile_w > 0 && tile_h > 0 && total, "bad args");
+    int row_lo, row_hi;
+    B2S_REQUIRE(row_window(rows, tile_h, row_lo, row_hi), "bad tile-row window");
     if (M == 0) return 0;
     B2S_REQUIRE(means2d && radii, "null pointer");
     coarse_count_kernel<<<(unsigned)cdiv(M, 256), 256, 0, (cudaStream_t)stream>>>(
-        M, reinterpret_cast<const float2*>(means2d), radii, (float)tile_size, tile_w, tile_h,
+        M, reinterpret_cast<const float2*>(means2d), radii, (float)tile_size, tile_w, row_lo, row_hi,
         reinterpret_cast<unsigned long long*>(total));
     B2S_LAUNCH_CHECK();
     return 0;
@@ -712,8 +728,10 @@ extern "C" int64_t b2s_coarse_bin_workspace_bytes(int64_t M, int64_t n_records) 
 extern "C" int b2s_coarse_bin(int64_t M, int64_t N, const int64_t* camera_ids, int64_t n_records, const int32_t* sorted_ids,
                               const float* means2d, const int32_t* radii, int32_t C, int32_t tile_size, int32_t tile_w,
                               int32_t tile_h, uint32_t* bin_recs, int32_t* bin_ids, int32_t* bin_offsets, void* workspace,
-                              int64_t workspace_bytes, b2s_stream_t stream) {
+                              int64_t workspace_bytes, const b2s_tile_rows* rows, b2s_stream_t stream) {
     B2S_REQUIRE(M >= 0 && n_records >= 0 && C >= 0 && tile_size > 0 && tile_w > 0 && tile_h > 0 && bin_offsets, "bad args");
+    int row_lo, row_hi;
+    B2S_REQUIRE(row_window(rows, tile_h, row_lo, row_hi), "bad tile-row window");
     cudaStream_t st = (cudaStream_t)stream;
     const int bins_w = (tile_w + CB - 1) / CB, bins_h = (tile_h + CB - 1) / CB;
     const int64_t n_bins = (int64_t)C * bins_w * bins_h;
@@ -748,7 +766,7 @@ extern "C" int b2s_coarse_bin(int64_t M, int64_t N, const int64_t* camera_ids, i
     unsigned int* counter = reinterpret_cast<unsigned int*>(w);
     unsigned long long* status = reinterpret_cast<unsigned long long*>(w + 16);
     coarse_expand_kernel<<<(unsigned)ctas, EXP_THREADS, 0, st>>>(
-        M, N, camera_ids, sorted_ids, reinterpret_cast<const float2*>(means2d), radii, (float)tile_size, tile_w, tile_h,
+        M, N, camera_ids, sorted_ids, reinterpret_cast<const float2*>(means2d), radii, (float)tile_size, tile_w, row_lo, row_hi,
         bins_w, bins_h, status, counter, recs_u, vals_u);
     B2S_LAUNCH_CHECK();
     const int key_bits = bit_length(n_bins > 1 ? n_bins - 1 : 1);

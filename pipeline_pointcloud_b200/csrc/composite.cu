@@ -182,8 +182,11 @@ __global__ void __launch_bounds__(CTA) composite_fwd_kernel(const b2s_composite_
     __shared__ int2 s_q[BINS ? QRING : 1];
     __shared__ int s_wtot[2][CTA / 32];
 
-    const int tile_x = blockIdx.x, tile_y = blockIdx.y, cam = blockIdx.z;
+    // blockIdx.y counts from the first tile row of the launch's window (a tile stripe of a multi-GPU job, or the whole grid);
+    // tile ids, bin keys and pixel centres are those of the whole image, the output tensors hold the window's rows only
+    const int tile_x = blockIdx.x, tile_y = blockIdx.y + a.tile_row_lo, cam = blockIdx.z;
     const PixelMap pm = pixel_of_thread(tile_x, tile_y, a.width, a.height);
+    const int out_y0 = a.tile_row_lo * TILE, out_h = min(a.height, a.tile_row_hi * TILE) - out_y0;
     float px = (float)pm.px + 0.5f, py = (float)pm.py + 0.5f;
     pin(px); pin(py);
     const int lane = threadIdx.x & 31;
@@ -293,7 +296,7 @@ __global__ void __launch_bounds__(CTA) composite_fwd_kernel(const b2s_composite_
         }
     }
     if (pm.inside) {
-        const int64_t pix = ((int64_t)cam * a.height + pm.py) * a.width + pm.px;
+        const int64_t pix = ((int64_t)cam * out_h + (pm.py - out_y0)) * a.width + pm.px;
 #pragma unroll
         for (int k = 0; k < CH; ++k)
             a.render_colors[pix * CH + k] = a.backgrounds ? acc[k] + T * a.backgrounds[cam * CH + k] : acc[k];
@@ -358,8 +361,11 @@ __global__ void __launch_bounds__(CTA) composite_bwd_kernel(const b2s_composite_
     __shared__ int s_wtot[2][CTA / 32];
     __shared__ int s_max[CTA / 32];
 
-    const int tile_x = blockIdx.x, tile_y = blockIdx.y, cam = blockIdx.z;
+    // blockIdx.y counts from the first tile row of the launch's window (a tile stripe of a multi-GPU job, or the whole grid);
+    // tile ids, bin keys and pixel centres are those of the whole image, the output tensors hold the window's rows only
+    const int tile_x = blockIdx.x, tile_y = blockIdx.y + a.tile_row_lo, cam = blockIdx.z;
     const PixelMap pm = pixel_of_thread(tile_x, tile_y, a.width, a.height);
+    const int out_y0 = a.tile_row_lo * TILE, out_h = min(a.height, a.tile_row_hi * TILE) - out_y0;
     float px = (float)pm.px + 0.5f, py = (float)pm.py + 0.5f;
     pin(px); pin(py);
     int lo, hi;
@@ -377,7 +383,7 @@ __global__ void __launch_bounds__(CTA) composite_bwd_kernel(const b2s_composite_
     if (hi <= lo) return;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const WarpBlock wb = warp_block(tile_x, tile_y);
-    const int64_t pix = pm.inside ? ((int64_t)cam * a.height + pm.py) * a.width + pm.px : 0;
+    const int64_t pix = pm.inside ? ((int64_t)cam * out_h + (pm.py - out_y0)) * a.width + pm.px : 0;
 
     // which gradient slot this lane publishes after the multi-value reduction (lane-constant)
     // slots: 0-1 v_xy | 2-4 v_conic | 5..5+CH v_colour | 5+CH v_opacity | then |v_xy| (absgrad)
@@ -596,7 +602,7 @@ __global__ void __launch_bounds__(CTA) composite_bwd_kernel(const b2s_composite_
 
 template <int CH>
 static int launch_fwd(const b2s_composite_fwd_args* a, float* final_T, cudaStream_t st) {
-    dim3 grid(a->tile_w, a->tile_h, a->C);
+    dim3 grid(a->tile_w, a->tile_row_hi - a->tile_row_lo, a->C);
     if (a->bin_offsets) {
         if constexpr (CH <= BINS_MAX_CH) composite_fwd_kernel<CH, true><<<grid, CTA, 0, st>>>(*a, final_T);
         else { set_error("composite: two-level binning supports up to %d channels", BINS_MAX_CH); return B2S_E_UNSUPPORTED; }
@@ -606,7 +612,7 @@ static int launch_fwd(const b2s_composite_fwd_args* a, float* final_T, cudaStrea
 }
 template <int CH>
 static int launch_bwd(const b2s_composite_bwd_args* a, const float* final_T, cudaStream_t st) {
-    dim3 grid(a->tile_w, a->tile_h, a->C);
+    dim3 grid(a->tile_w, a->tile_row_hi - a->tile_row_lo, a->C);
     if (a->bin_offsets) {
         if constexpr (CH <= BINS_MAX_CH) {
             if (a->v_means2d_abs) composite_bwd_kernel<CH, true, true><<<grid, CTA, 0, st>>>(*a, final_T);
@@ -626,12 +632,16 @@ using namespace b2s;
 
 // The exact final transmittance is carried in an optional side buffer (args.final_T):
 // 1 - alpha loses up to 6e-4 relative on nearly opaque pixels, which the backward would inherit.
-extern "C" int b2s_composite_fwd(const b2s_composite_fwd_args* a, b2s_stream_t stream) {
-    B2S_REQUIRE(a != nullptr, "null args");
+extern "C" int b2s_composite_fwd(const b2s_composite_fwd_args* a_in, b2s_stream_t stream) {
+    B2S_REQUIRE(a_in != nullptr, "null args");
+    b2s_composite_fwd_args args = *a_in;
+    const b2s_composite_fwd_args* a = &args;
+    if (args.tile_row_hi == 0 && args.tile_row_lo == 0) args.tile_row_hi = args.tile_h;   // no window: the whole grid
+    B2S_REQUIRE(args.tile_row_lo >= 0 && args.tile_row_lo <= args.tile_row_hi && args.tile_row_hi <= args.tile_h, "bad tile-row window");
     B2S_REQUIRE(a->tile_size == TILE, "tile_size must be 16");
     B2S_REQUIRE(a->C >= 0 && a->width > 0 && a->height > 0, "bad sizes");
     B2S_REQUIRE(a->tile_w == (a->width + TILE - 1) / TILE && a->tile_h == (a->height + TILE - 1) / TILE, "tile grid mismatch");
-    if (a->C == 0) return 0;
+    if (a->C == 0 || a->tile_row_hi == a->tile_row_lo) return 0;
     B2S_REQUIRE((a->isect_offsets || a->bin_offsets) && a->render_colors && a->render_alphas && a->last_ids, "null pointer");
     B2S_REQUIRE(a->n_isects == 0 || (a->means2d && a->conics && a->colors && a->opacities), "null input");
     B2S_REQUIRE(a->n_isects == 0 || (a->bin_offsets ? (a->bin_recs && a->bin_ids) : a->flatten_ids != nullptr), "null list");
@@ -654,11 +664,15 @@ extern "C" int b2s_composite_fwd(const b2s_composite_fwd_args* a, b2s_stream_t s
 #undef CALL_FWD
 }
 
-extern "C" int b2s_composite_bwd(const b2s_composite_bwd_args* a, b2s_stream_t stream) {
-    B2S_REQUIRE(a != nullptr, "null args");
+extern "C" int b2s_composite_bwd(const b2s_composite_bwd_args* a_in, b2s_stream_t stream) {
+    B2S_REQUIRE(a_in != nullptr, "null args");
+    b2s_composite_bwd_args args = *a_in;
+    const b2s_composite_bwd_args* a = &args;
+    if (args.tile_row_hi == 0 && args.tile_row_lo == 0) args.tile_row_hi = args.tile_h;
+    B2S_REQUIRE(args.tile_row_lo >= 0 && args.tile_row_lo <= args.tile_row_hi && args.tile_row_hi <= args.tile_h, "bad tile-row window");
     B2S_REQUIRE(a->tile_size == TILE, "tile_size must be 16");
     B2S_REQUIRE(a->C >= 0 && a->width > 0 && a->height > 0, "bad sizes");
-    if (a->C == 0 || a->n_isects == 0) return 0;
+    if (a->C == 0 || a->n_isects == 0 || a->tile_row_hi == a->tile_row_lo) return 0;
     B2S_REQUIRE(a->means2d && a->conics && a->colors && a->opacities, "null input");
     B2S_REQUIRE(a->bin_offsets ? (a->bin_recs && a->bin_ids) : (a->isect_offsets && a->flatten_ids), "null list");
     B2S_REQUIRE(a->last_ids && (a->final_T || a->render_alphas), "forward state missing");

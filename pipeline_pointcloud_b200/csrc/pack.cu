@@ -102,20 +102,27 @@ __global__ void join_grads_kernel(int64_t n, int ch, const float2* __restrict__ 
     for (int k = 0; k < ch; ++k) o[7 + k] = g_colors ? g_colors[i * ch + k] : 0.f;
 }
 
-// returned gradient records -> dense (zero-filled) gradients of the stage-1 outputs
+// returned gradient records -> dense (zero-filled) gradients of the stage-1 outputs.  ADD: a row may occur several
+// times in `sel` (tile stripes: a splat that straddles a stripe boundary was sent to every stripe it touches), so the
+// records are summed with red.global.add instead of stored.
+template <bool ADD>
 __global__ void scatter_grads_kernel(int64_t nnz, const int64_t* __restrict__ sel, int ch, const float* __restrict__ in,
-                                     float2* __restrict__ v_means2d, float* __restrict__ v_depths, float* __restrict__ v_conics,
+                                     float* __restrict__ v_means2d, float* __restrict__ v_depths, float* __restrict__ v_conics,
                                      float* __restrict__ v_opac, float* __restrict__ v_colors) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nnz) return;
     const int G = 7 + ch;
     const float* p = in + i * G;
     const int64_t r = sel[i];
-    v_means2d[r] = make_float2(p[0], p[1]);
-    v_depths[r] = p[2];
-    v_conics[3 * r] = p[3]; v_conics[3 * r + 1] = p[4]; v_conics[3 * r + 2] = p[5];
-    v_opac[r] = p[6];
-    for (int k = 0; k < ch; ++k) v_colors[r * ch + k] = p[7 + k];
+    auto put = [](float* dst, float v) {
+        if (ADD) atomicAdd(dst, v);
+        else *dst = v;
+    };
+    put(v_means2d + 2 * r, p[0]); put(v_means2d + 2 * r + 1, p[1]);
+    put(v_depths + r, p[2]);
+    put(v_conics + 3 * r, p[3]); put(v_conics + 3 * r + 1, p[4]); put(v_conics + 3 * r + 2, p[5]);
+    put(v_opac + r, p[6]);
+    for (int k = 0; k < ch; ++k) put(v_colors + r * ch + k, p[7 + k]);
 }
 
 // ---- fused pack + exchange over NVLink peer memory --------------------------------------------------------
@@ -303,12 +310,17 @@ extern "C" int b2s_join_grads(int64_t n, int32_t channels, const float* g_means2
 }
 
 extern "C" int b2s_scatter_grads(int64_t nnz, const int64_t* sel, int32_t channels, const float* in, float* v_means2d,
-                                 float* v_depths, float* v_conics, float* v_opacities, float* v_colors, b2s_stream_t stream) {
+                                 float* v_depths, float* v_conics, float* v_opacities, float* v_colors, int32_t accumulate,
+                                 b2s_stream_t stream) {
     B2S_REQUIRE(nnz >= 0 && channels >= 0, "bad sizes");
     if (nnz == 0) return 0;
     B2S_REQUIRE(sel && in && v_means2d && v_depths && v_conics && v_opacities && v_colors, "null pointer");
-    scatter_grads_kernel<<<(unsigned)cdiv(nnz, 256), 256, 0, (cudaStream_t)stream>>>(
-        nnz, sel, channels, in, reinterpret_cast<float2*>(v_means2d), v_depths, v_conics, v_opacities, v_colors);
+    if (accumulate)
+        scatter_grads_kernel<true><<<(unsigned)cdiv(nnz, 256), 256, 0, (cudaStream_t)stream>>>(
+            nnz, sel, channels, in, v_means2d, v_depths, v_conics, v_opacities, v_colors);
+    else
+        scatter_grads_kernel<false><<<(unsigned)cdiv(nnz, 256), 256, 0, (cudaStream_t)stream>>>(
+            nnz, sel, channels, in, v_means2d, v_depths, v_conics, v_opacities, v_colors);
     B2S_LAUNCH_CHECK();
     return 0;
 }

@@ -130,13 +130,92 @@ def route_to_camera_owners(payload: Tensor, ids: Tensor, camera_ids: Tensor, gau
     return payload, side[:, :k], side[:, k], side[:, k + 1], send_counts, recv_counts
 
 
+# ----------------------------------------------------------------------------------------------------------
+# destination lists: which dense rows (c*N + n) go to which rank, grouped by destination
+# ----------------------------------------------------------------------------------------------------------
+def camera_owner_selection(radii: Tensor, cams_per_rank: int, world: int) -> Tuple[Tensor, Tensor]:
+    """Visible rows of dense ``radii`` [C_all,N], ascending (= camera-major, hence grouped by the rank that owns
+    the camera) and the number of rows per destination rank (int64 [world])."""
+    N = radii.shape[1]
+    sel = (radii.reshape(-1) > 0).nonzero(as_tuple=True)[0]
+    bounds = torch.searchsorted(sel, torch.arange(world + 1, device=radii.device) * (cams_per_rank * N))
+    return sel, (bounds[1:] - bounds[:-1]).contiguous()
+
+
+def stripe_bounds(tile_height: int, world: int) -> List[int]:
+    """Default tile-row stripes: rank r owns tile rows [r*th//W, (r+1)*th//W)."""
+    return [r * tile_height // world for r in range(world + 1)]
+
+
+def balanced_stripe_bounds(tiles_per_row: Tensor, world: int) -> List[int]:
+    """Stripe boundaries that equalise a per-tile-row cost (e.g. last iteration's intersections per tile row,
+    int64 [tile_height]): boundary r is the first row at which the running cost reaches r/W of the total."""
+    th = tiles_per_row.numel()
+    cum = torch.cumsum(tiles_per_row.to(torch.float64).reshape(-1).cpu(), 0)
+    total = float(cum[-1]) if th else 0.0
+    if total <= 0:
+        return stripe_bounds(th, world)
+    targets = torch.arange(1, world, dtype=torch.float64) * (total / world)
+    inner = (torch.searchsorted(cum, targets) + 1).clamp(max=th).tolist()
+    bounds = [0] + [int(b) for b in inner] + [th]
+    for i in range(1, len(bounds)):               # monotone
+        bounds[i] = max(bounds[i], bounds[i - 1])
+    return bounds
+
+
+def stripe_selection(means2d: Tensor, radii: Tensor, tile_size: int, tile_height: int,
+                     bounds: Sequence[int]) -> Tuple[Tensor, Tensor]:
+    """Tile-stripe routing: rows of dense ``means2d`` [C,N,2] / ``radii`` [C,N] whose tile rectangle
+    intersects stripe d = tile rows [bounds[d], bounds[d+1]), for d = 0..W-1, concatenated by destination and
+    ascending inside each destination; a splat that straddles a boundary appears once per stripe it touches.
+    The row range is computed with the same single-rounding fp32 operations as the binning kernels
+    (``tile_rect`` in csrc/b2s_math.cuh; oracle ``tile_rects``), so the decision is bit-identical to theirs.
+    Device agnostic.  Returns (sel int64 [n], counts int64 [W])."""
+    th = int(tile_height)
+    my = means2d[..., 1].reshape(-1).float() / float(tile_size)
+    rr = radii.reshape(-1).to(torch.float32) / float(tile_size)
+    y0 = torch.floor(my - rr).clamp_(0, th)
+    y1 = torch.ceil(my + rr).clamp_(0, th)
+    vis = (radii.reshape(-1) > 0) & (y1 > y0)
+    sels = []
+    for d in range(len(bounds) - 1):
+        lo, hi = float(bounds[d]), float(bounds[d + 1])
+        if hi <= lo:
+            sels.append(my.new_empty(0, dtype=torch.int64))
+            continue
+        sels.append((vis & (y0 < hi) & (y1 > lo)).nonzero(as_tuple=True)[0])
+    counts = torch.tensor([t.numel() for t in sels], dtype=torch.int64, device=means2d.device)
+    return torch.cat(sels), counts
+
+
+def route_to_stripe_owners(payload: Tensor, ids: Tensor, means2d: Tensor, radii: Tensor, tile_size: int, tile_height: int,
+                           bounds: Sequence[int], n_world: Sequence[int], group=None):
+    """Device-agnostic tile-stripe routing of dense per-pair rows (tested with gloo on CPU): ``payload`` [C*N,F]
+    float (differentiable), ``ids`` [C*N,K] integers.  Returns (payload, ids, camera ids, global Gaussian ids) of the
+    rows whose tile rectangle touches this rank's stripe, source-rank-major and ascending inside a source, i.e. in
+    ascending global flat index per camera (the order the reference's stable sort breaks ties by).  The backward
+    returns every copy's gradient to its source row and sums the copies of a straddling splat."""
+    rank = dist.get_rank(group)
+    C, N = radii.shape
+    sel, counts = stripe_selection(means2d, radii, tile_size, tile_height, bounds)
+    send_counts = counts.tolist()
+    recv_counts = exchange_counts(send_counts, payload.device, group)
+    offset_g = int(sum(n_world[:rank]))
+    cam, gid = torch.div(sel, N, rounding_mode="floor"), sel % N + offset_g
+    side = torch.cat([ids.reshape(C * N, -1)[sel].to(torch.int64), torch.stack([cam, gid], dim=1)], dim=1)
+    out = _AllToAllRows.apply(payload.reshape(C * N, -1)[sel], send_counts, recv_counts, group)   # indexing backward = index_add
+    side = _exchange_rows(side, send_counts, recv_counts, group)
+    k = side.shape[1] - 2
+    return out, side[:, :k], side[:, k], side[:, k + 1], send_counts, recv_counts
+
+
 class _RouteSplatsCUDA(torch.autograd.Function):
     """The same routing as ``route_to_camera_owners`` for CUDA tensors, fused: one pack kernel, ONE NCCL
     all-to-all of [11+ch]-float records, one split kernel; the backward joins the gradients into [7+ch] records,
     sends them back with the reverse all-to-all and scatters them into dense (zero-filled) gradients."""
 
     @staticmethod
-    def forward(ctx, means2d, depths, conics, opac, cols, radii, tiles, cams_per_rank, n_world, group):
+    def forward(ctx, means2d, depths, conics, opac, cols, radii, tiles, cams_per_rank, n_world, group, sel, send, dup):
         from . import _lib as L
         from . import ops
         dev = means2d.device
@@ -145,9 +224,7 @@ class _RouteSplatsCUDA(torch.autograd.Function):
         ch = cols.shape[-1]
         means2d, depths, conics, opac, cols = (L.f32c(t) for t in (means2d, depths, conics, opac, cols))
         radii, tiles = radii.contiguous(), tiles.contiguous()
-        sel = (radii.reshape(-1) > 0).nonzero(as_tuple=True)[0]              # ascending = camera-major
-        bounds = torch.searchsorted(sel, torch.arange(world + 1, device=dev) * (cams_per_rank * N))
-        send = (bounds[1:] - bounds[:-1]).contiguous()
+        # sel: dense rows grouped by destination rank, send: rows per destination (camera_owner_selection / stripe_selection)
         gathered = [torch.empty_like(send) for _ in range(world)]
         dist.all_gather(gathered, send, group=group)
         table = torch.stack(gathered).tolist()                                # one host sync: the whole W x W count table
@@ -172,7 +249,7 @@ class _RouteSplatsCUDA(torch.autograd.Function):
                                           L.ptr(opac_m), L.ptr(cols_m), L.ptr(radii_m), L.ptr(tiles_m), L.ptr(cam_m),
                                           L.ptr(gid_m), st), "b2s_split_payload")
         ctx.save_for_backward(sel)
-        ctx.cfg = (send_counts, recv_counts, group, ch, (means2d.shape, depths.shape, conics.shape, opac.shape, cols.shape))
+        ctx.cfg = (send_counts, recv_counts, group, ch, (means2d.shape, depths.shape, conics.shape, opac.shape, cols.shape), dup)
         ctx.set_materialize_grads(False)
         ctx.mark_non_differentiable(radii_m, tiles_m, cam_m, gid_m)
         return means2d_m, depths_m, conics_m, opac_m, cols_m, radii_m, tiles_m, cam_m, gid_m
@@ -182,7 +259,7 @@ class _RouteSplatsCUDA(torch.autograd.Function):
         from . import _lib as L
         from . import ops
         (sel,) = ctx.saved_tensors
-        send_counts, recv_counts, group, ch, shapes = ctx.cfg
+        send_counts, recv_counts, group, ch, shapes, dup = ctx.cfg
         dev = sel.device
         n_recv, nnz, G = int(sum(recv_counts)), sel.numel(), 7 + ch
         lib, st = L.lib(), L.stream_ptr(dev)
@@ -195,8 +272,9 @@ class _RouteSplatsCUDA(torch.autograd.Function):
             dist.all_to_all_single(back, joined, output_split_sizes=send_counts, input_split_sizes=recv_counts, group=group)
         outs = [torch.zeros(s, dtype=torch.float32, device=dev) for s in shapes]
         with ops._stage("route_scatter"):
-            L.check(lib.b2s_scatter_grads(nnz, L.ptr(sel), ch, L.ptr(back), *[L.ptr(o) for o in outs], st), "b2s_scatter_grads")
-        return tuple(outs) + (None,) * 5
+            L.check(lib.b2s_scatter_grads(nnz, L.ptr(sel), ch, L.ptr(back), *[L.ptr(o) for o in outs], int(dup), st),
+                    "b2s_scatter_grads")
+        return tuple(outs) + (None,) * 8
 
 
 class _SymmBuffers:
@@ -235,7 +313,7 @@ class _RouteSplatsP2P(torch.autograd.Function):
     call on the data path; two ~7 us symmetric-memory barriers bracket each exchange."""
 
     @staticmethod
-    def forward(ctx, means2d, depths, conics, opac, cols, radii, tiles, cams_per_rank, n_world, group):
+    def forward(ctx, means2d, depths, conics, opac, cols, radii, tiles, cams_per_rank, n_world, group, sel, send, dup):
         from . import _lib as L
         from . import ops
         dev = means2d.device
@@ -244,9 +322,7 @@ class _RouteSplatsP2P(torch.autograd.Function):
         ch = cols.shape[-1]
         means2d, depths, conics, opac, cols = (L.f32c(t) for t in (means2d, depths, conics, opac, cols))
         radii, tiles = radii.contiguous(), tiles.contiguous()
-        sel = (radii.reshape(-1) > 0).nonzero(as_tuple=True)[0]              # ascending = camera-major
-        bounds = torch.searchsorted(sel, torch.arange(world + 1, device=dev) * (cams_per_rank * N))
-        send = (bounds[1:] - bounds[:-1]).contiguous()
+        # sel: dense rows grouped by destination rank, send: rows per destination (camera_owner_selection / stripe_selection)
         gathered = [torch.empty_like(send) for _ in range(world)]
         dist.all_gather(gathered, send, group=group)
         table = torch.stack(gathered).tolist()                                # one host sync: the W x W count table
@@ -276,7 +352,7 @@ class _RouteSplatsP2P(torch.autograd.Function):
                                           L.ptr(gid_m), st), "b2s_split_payload")
         ctx.save_for_backward(sel)
         src_base = [sum(table[s][d] for d in range(rank)) for s in range(world)]   # my rows inside source s's packed list
-        ctx.cfg = (recv_counts, src_base, group, ch, (means2d.shape, depths.shape, conics.shape, opac.shape, cols.shape))
+        ctx.cfg = (recv_counts, src_base, group, ch, (means2d.shape, depths.shape, conics.shape, opac.shape, cols.shape), dup)
         ctx.set_materialize_grads(False)
         ctx.mark_non_differentiable(radii_m, tiles_m, cam_m, gid_m)
         return means2d_m, depths_m, conics_m, opac_m, cols_m, radii_m, tiles_m, cam_m, gid_m
@@ -286,7 +362,7 @@ class _RouteSplatsP2P(torch.autograd.Function):
         from . import _lib as L
         from . import ops
         (sel,) = ctx.saved_tensors
-        recv_counts, src_base, group, ch, shapes = ctx.cfg
+        recv_counts, src_base, group, ch, shapes, dup = ctx.cfg
         dev = sel.device
         world = dist.get_world_size(group)
         n_recv, nnz, G = int(sum(recv_counts)), sel.numel(), 7 + ch
@@ -300,8 +376,9 @@ class _RouteSplatsP2P(torch.autograd.Function):
             h_b.barrier()
         outs = [torch.zeros(s, dtype=torch.float32, device=dev) for s in shapes]
         with ops._stage("route_scatter"):
-            L.check(lib.b2s_scatter_grads(nnz, L.ptr(sel), ch, L.ptr(buf_b), *[L.ptr(o) for o in outs], st), "b2s_scatter_grads")
-        return tuple(outs) + (None,) * 5
+            L.check(lib.b2s_scatter_grads(nnz, L.ptr(sel), ch, L.ptr(buf_b), *[L.ptr(o) for o in outs], int(dup), st),
+                    "b2s_scatter_grads")
+        return tuple(outs) + (None,) * 8
 
 
 def _route_impl():
@@ -315,10 +392,20 @@ def _route_impl():
 # ----------------------------------------------------------------------------------------------------------
 def rasterization_distributed(means, quats, scales, opacities, colors, viewmats, Ks, width, height, near_plane=0.01,
                               far_plane=1e10, radius_clip=0.0, eps2d=0.3, sh_degree=None, packed=True, backgrounds=None,
-                              render_mode="RGB", absgrad=False, rasterize_mode="classic", tile_size=16, group=None):
-    """``rasterization(..., distributed=True)``: local Gaussians [N_r,...], local cameras [C_r,...] (same C_r on
-    every rank); returns the renders of the local cameras composited from every rank's Gaussians.  ``meta`` is
-    in the packed layout (``camera_ids`` local, ``gaussian_ids`` global), as upstream."""
+                              render_mode="RGB", absgrad=False, rasterize_mode="classic", tile_size=16, group=None,
+                              tile_stripes=False, stripe_rows=None):
+    """``rasterization(..., distributed=True)``: local Gaussians [N_r,...] on every rank.
+
+    Camera owners (default; upstream's scheme): local cameras [C_r,...] (same C_r on every rank); returns the
+    renders of the local cameras composited from every rank's Gaussians.
+
+    ``tile_stripes=True`` (BASELINE config 5): every rank passes the SAME cameras [C,...]; rank r owns
+    tile rows [stripe_rows[r], stripe_rows[r+1]) of every camera (default: an even split of the tile grid; see
+    ``balanced_stripe_bounds``) and returns only those pixel rows: ``render_colors`` [C, rows, W, ch]
+    (``meta["stripe_pixel_rows"]`` = (y0, y1); ``gather_stripes`` assembles the full image).  A splat whose tile
+    rectangle straddles a boundary is sent to every stripe it touches; its gradients are summed at the owner.
+
+    ``meta`` is in the packed layout (``camera_ids`` local, ``gaussian_ids`` global), as upstream."""
     from . import ops
     from ._lib import require_cuda
     import math
@@ -332,15 +419,27 @@ def rasterization_distributed(means, quats, scales, opacities, colors, viewmats,
     if sh_degree is None and colors.dim() != 2:
         raise NotImplementedError("distributed=True expects per-Gaussian colours [N,D]")
     require_cuda(means, quats, scales, opacities, colors, viewmats, Ks)
-    world = dist.get_world_size(group)
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
     N, C_local = means.shape[0], viewmats.shape[0]
     width, height = int(width), int(height)
     tw, th = math.ceil(width / tile_size), math.ceil(height / tile_size)
 
-    viewmats_all, Ks_all, n_world = all_gather_cameras(viewmats, Ks, N, group)
-    C_all = viewmats_all.shape[0]
-    if C_all != C_local * world:
-        raise ValueError("every rank must hold the same number of cameras")
+    if tile_stripes:
+        n = torch.tensor([N], dtype=torch.int64, device=means.device)
+        ns = [torch.empty_like(n) for _ in range(world)]
+        dist.all_gather(ns, n, group=group)
+        n_world = [int(t) for t in ns]
+        viewmats_all, Ks_all, C_all = viewmats, Ks, C_local          # the same cameras on every rank
+        bounds = [int(b) for b in (stripe_rows if stripe_rows is not None else stripe_bounds(th, world))]
+        if len(bounds) != world + 1 or bounds[0] != 0 or bounds[-1] != th or any(b1 < b0 for b0, b1 in zip(bounds, bounds[1:])):
+            raise ValueError(f"stripe_rows must be {world + 1} ascending tile rows from 0 to {th}")
+        rows = (bounds[rank], bounds[rank + 1])
+    else:
+        viewmats_all, Ks_all, n_world = all_gather_cameras(viewmats, Ks, N, group)
+        C_all = viewmats_all.shape[0]
+        if C_all != C_local * world:
+            raise ValueError("every rank must hold the same number of cameras")
+        rows = None
 
     # ---- local shard projected into every camera (one kernel; SH coefficients read once) ----------------------
     antialiased = rasterize_mode == "antialiased"
@@ -360,30 +459,45 @@ def rasterization_distributed(means, quats, scales, opacities, colors, viewmats,
             backgrounds = torch.zeros_like(backgrounds[:, :1])
     ch = cols.shape[-1]
 
-    # ---- route the visible pairs to the camera owners: pack -> one all-to-all -> split --------------------------
+    # ---- route the visible pairs to their owners: (fused) pack -> exchange -> split -------------------------------
+    with torch.no_grad():
+        if tile_stripes:
+            with ops._stage("stripe_select", launches=0):
+                sel, send = stripe_selection(means2d, radii, tile_size, th, bounds)
+        else:
+            sel, send = camera_owner_selection(radii, C_local, world)
     (means2d_m, depths_m, conics_m, opac_m, cols_m, radii_m, tiles_m, cam_local,
      gauss_global) = (_RouteSplatsP2P if _route_impl() == "p2p" and world <= 16 else _RouteSplatsCUDA).apply(
-        means2d, depths, conics, opac, cols, radii, tiles, C_local, n_world, group)
+        means2d, depths, conics, opac, cols, radii, tiles, C_all if tile_stripes else C_local, n_world, group, sel, send,
+        bool(tile_stripes))
+    if tile_stripes:
+        # the record carries the whole-image tile count: recount inside the stripe
+        tiles_m = ops.isect_tiles(means2d_m.detach(), radii_m, depths_m.detach(), tile_size, tw, th, sort=False, packed=True,
+                                  n_cameras=C_local, camera_ids=cam_local, tile_rows=rows, count_only=True)
 
-    # ---- own cameras: binning + compositing -------------------------------------------------------------------
+    # ---- own cameras / own stripe: binning + compositing ---------------------------------------------------------
     from .rendering import _use_coarse_bins
     meta = ops.LazyMeta({
         "camera_ids": cam_local, "gaussian_ids": gauss_global, "radii": radii_m, "means2d": means2d_m,
         "depths": depths_m, "conics": conics_m, "opacities": opac_m, "tile_width": tw, "tile_height": th,
         "tiles_per_gauss": tiles_m, "width": width, "height": height, "tile_size": tile_size, "n_cameras": C_local,
     })
+    if tile_stripes:
+        meta["stripe_tile_rows"] = rows
+        meta["stripe_pixel_rows"] = (rows[0] * tile_size, max(rows[0] * tile_size, min(height, rows[1] * tile_size)))
+        meta["stripe_bounds"] = bounds
     if _use_coarse_bins() and ops.coarse_bins_supported(C_local, tw, th, ch):
-        bins = ops.bin_coarse(means2d_m, radii_m, depths_m, tile_size, tw, th, C_local, camera_ids=cam_local)
+        bins = ops.bin_coarse(means2d_m, radii_m, depths_m, tile_size, tw, th, C_local, camera_ids=cam_local, tile_rows=rows)
         render_colors, render_alphas = ops.rasterize_to_pixels(
             means2d_m, conics_m, cols_m, opac_m, width, height, tile_size, None, None,
-            backgrounds=backgrounds, packed=True, absgrad=absgrad, bins=bins, n_cameras=C_local)
+            backgrounds=backgrounds, packed=True, absgrad=absgrad, bins=bins, n_cameras=C_local, tile_rows=rows)
         meta["n_coarse_records"] = bins.n_records
         cache = {}
 
         def lists():
             if not cache:
                 flat, off, mk = ops.bin_depth_first(means2d_m.detach(), radii_m, depths_m.detach(), tiles_m, tile_size, tw, th,
-                                                    C_local, camera_ids=cam_local, sorted_ids=bins.sorted_ids)
+                                                    C_local, camera_ids=cam_local, sorted_ids=bins.sorted_ids, tile_rows=rows)
                 cache.update(flat=flat, off=off, mk=mk)
             return cache
 
@@ -392,13 +506,39 @@ def rasterization_distributed(means, quats, scales, opacities, colors, viewmats,
         meta.set_lazy("isect_ids", lambda: lists()["mk"]())
     else:
         flatten_ids, isect_offsets, make_isect_ids = ops.bin_depth_first(
-            means2d_m, radii_m, depths_m, tiles_m, tile_size, tw, th, C_local, camera_ids=cam_local)
+            means2d_m, radii_m, depths_m, tiles_m, tile_size, tw, th, C_local, camera_ids=cam_local, tile_rows=rows)
         render_colors, render_alphas = ops.rasterize_to_pixels(
             means2d_m, conics_m, cols_m, opac_m, width, height, tile_size, isect_offsets, flatten_ids,
-            backgrounds=backgrounds, packed=True, absgrad=absgrad)
+            backgrounds=backgrounds, packed=True, absgrad=absgrad, tile_rows=rows)
         meta["flatten_ids"], meta["isect_offsets"] = flatten_ids, isect_offsets
         meta.set_lazy("isect_ids", make_isect_ids)
     if render_mode in ("ED", "RGB+ED"):
         render_colors = torch.cat(
             [render_colors[..., :-1], render_colors[..., -1:] / render_alphas.clamp(min=1e-10)], dim=-1)
     return render_colors, render_alphas, meta
+
+
+class _GatherStripes(torch.autograd.Function):
+    """all-gather of per-rank pixel-row stripes [C, rows_r, W, ch] into the full image; the backward hands every rank
+    the slice of the image cotangent that belongs to its stripe (each rank is expected to evaluate the same loss on
+    the full image, as data-parallel trainers do, so no reduction is needed)."""
+
+    @staticmethod
+    def forward(ctx, x, pixel_bounds, group):
+        rank, world = dist.get_rank(group), dist.get_world_size(group)
+        C, _, W, ch = x.shape
+        parts = [x.new_empty(C, pixel_bounds[r + 1] - pixel_bounds[r], W, ch) for r in range(world)]
+        dist.all_gather(parts, x.contiguous(), group=group)
+        ctx.rows = (pixel_bounds[rank], pixel_bounds[rank + 1])
+        return torch.cat(parts, dim=1)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g[:, ctx.rows[0]:ctx.rows[1]].contiguous(), None, None
+
+
+def gather_stripes(x: Tensor, meta, group=None) -> Tensor:
+    """Full image [C,H,W,ch] from the stripes ``rasterization(distributed=True, tile_stripes=True)`` returned."""
+    ts, H = meta["tile_size"], meta["height"]
+    pixel_bounds = [min(H, b * ts) for b in meta["stripe_bounds"]]
+    return _GatherStripes.apply(x, pixel_bounds, group)

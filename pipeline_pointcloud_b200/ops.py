@@ -347,11 +347,14 @@ def quat_scale_to_covar_preci(quats: Tensor, scales: Tensor, compute_covar: bool
 def isect_tiles(means2d: Tensor, radii: Tensor, depths: Tensor, tile_size: int, tile_width: int, tile_height: int,
                 sort: bool = True, packed: bool = False, n_cameras: Optional[int] = None,
                 camera_ids: Optional[Tensor] = None, gaussian_ids: Optional[Tensor] = None,
-                tiles_per_gauss: Optional[Tensor] = None, method: str = "radix64") -> Tuple[Tensor, Tensor, Tensor]:
+                tiles_per_gauss: Optional[Tensor] = None, method: str = "radix64",
+                tile_rows: Optional[Tuple[int, int]] = None, count_only: bool = False) -> Tuple[Tensor, Tensor, Tensor]:
     """gsplat ``isect_tiles``: (tiles_per_gauss int32, isect_ids int64, flatten_ids int32), sorted by
     (camera, tile, depth bits) when ``sort``.  ``tiles_per_gauss`` may be passed in when stage 1 already made it.
     ``method="radix64"`` is the reference's algorithm (fill 64-bit keys, LSD radix sort);
-    ``method="depth_first"`` is the low-traffic path ``rasterization()`` uses -- same output bit for bit."""
+    ``method="depth_first"`` is the low-traffic path ``rasterization()`` uses -- same output bit for bit.
+    ``tile_rows=(lo, hi)`` restricts the intersections to tile rows [lo, hi) of the grid (a multi-GPU tile stripe):
+    the result is the whole-image list filtered by tile row (``tiles_per_gauss`` must then be None or clipped alike)."""
     if method not in ("radix64", "depth_first"):
         raise ValueError("method must be 'radix64' or 'depth_first'")
     dev = L.require_cuda(means2d, radii, depths)
@@ -370,13 +373,15 @@ def isect_tiles(means2d: Tensor, radii: Tensor, depths: Tensor, tile_size: int, 
     lib, st = L.lib(), L.stream_ptr(dev)
     if tiles_per_gauss is None:
         tiles_per_gauss = torch.empty(out_shape, dtype=torch.int32, device=dev)
-        check(lib.b2s_isect_count(M, ptr(means2d), ptr(radii), tile_size, tile_width, tile_height, ptr(tiles_per_gauss), st),
-              "b2s_isect_count")
+        check(lib.b2s_isect_count(M, ptr(means2d), ptr(radii), tile_size, tile_width, tile_height, ptr(tiles_per_gauss),
+                                  L.tile_rows(tile_rows), st), "b2s_isect_count")
     else:
         tiles_per_gauss = tiles_per_gauss.contiguous()
+    if count_only:
+        return tiles_per_gauss
     if method == "depth_first" and sort:
         flat, _off, make_ids = bin_depth_first(means2d, radii, depths, tiles_per_gauss, tile_size, tile_width, tile_height,
-                                               C, camera_ids=cam)
+                                               C, camera_ids=cam, tile_rows=tile_rows)
         return tiles_per_gauss, make_ids(), flat
     cum = torch.empty(max(M, 1), dtype=torch.int32, device=dev)
     total = torch.empty(1, dtype=torch.int64, device=dev)
@@ -390,7 +395,7 @@ def isect_tiles(means2d: Tensor, radii: Tensor, depths: Tensor, tile_size: int, 
     flatten_ids = torch.empty(n_isects, dtype=torch.int32, device=dev)
     with _stage("isect_fill"):
         check(lib.b2s_isect_fill(M, N, ptr(cam), ptr(means2d), ptr(radii), ptr(depths), ptr(cum), tile_size, tile_width,
-                                 tile_height, ptr(isect_ids), ptr(flatten_ids), st), "b2s_isect_fill")
+                                 tile_height, ptr(isect_ids), ptr(flatten_ids), L.tile_rows(tile_rows), st), "b2s_isect_fill")
     if sort and n_isects > 0:
         key_bits = 32 + _bit_length(tile_width * tile_height) + _bit_length(C)
         ids_sorted = torch.empty_like(isect_ids)
@@ -458,7 +463,8 @@ def _ws(nbytes: int, dev) -> Tensor:
 def bin_depth_first(means2d: Tensor, radii: Tensor, depths: Tensor, tiles_per_gauss: Tensor, tile_size: int,
                     tile_width: int, tile_height: int, n_cameras: int, camera_ids: Optional[Tensor] = None,
                     depth_keys: Optional[Tensor] = None, row_ids: Optional[Tensor] = None,
-                    total_isects: Optional[Tensor] = None, sorted_ids: Optional[Tensor] = None):
+                    total_isects: Optional[Tensor] = None, sorted_ids: Optional[Tensor] = None,
+                    tile_rows: Optional[Tuple[int, int]] = None):
     """Depth-first binning (see include/b2s.h): returns (flatten_ids int32 [I], isect_offsets int32 [C,th,tw],
     make_isect_ids) where ``make_isect_ids()`` rebuilds the 64-bit sorted keys.  Bit-identical to
     ``isect_tiles(sort=True)`` + ``isect_offset_encode`` with ~3x less HBM traffic.
@@ -496,8 +502,8 @@ def bin_depth_first(means2d: Tensor, radii: Tensor, depths: Tensor, tiles_per_ga
     ws2 = _ws(lib.b2s_tile_bin_workspace_bytes(M, n_isects), dev)
     with _stage("tile_bin"):
         check(lib.b2s_tile_bin(M, N, ptr(cam), n_isects, ptr(sorted_ids), ptr(means2d), ptr(radii), C, tile_size, tile_width,
-                               tile_height, ptr(tile_keys), ptr(flatten_ids), ptr(offsets), ptr(ws2), ws2.numel(), st),
-              "b2s_tile_bin")
+                               tile_height, ptr(tile_keys), ptr(flatten_ids), ptr(offsets), ptr(ws2), ws2.numel(),
+                               L.tile_rows(tile_rows), st), "b2s_tile_bin")
 
     def make_isect_ids():
         ids = torch.empty(n_isects, dtype=torch.int64, device=dev)
@@ -543,7 +549,8 @@ class CoarseBins:
 @torch.no_grad()
 def bin_coarse(means2d: Tensor, radii: Tensor, depths: Tensor, tile_size: int, tile_width: int, tile_height: int,
                n_cameras: int, camera_ids: Optional[Tensor] = None, depth_keys: Optional[Tensor] = None,
-               row_ids: Optional[Tensor] = None, totals: Optional[Tensor] = None) -> CoarseBins:
+               row_ids: Optional[Tensor] = None, totals: Optional[Tensor] = None,
+               tile_rows: Optional[Tuple[int, int]] = None) -> CoarseBins:
     """Depth sort of the rows + coarse binning (b2s_depth_order, b2s_coarse_bin).  ``depth_keys`` / ``row_ids`` /
     ``totals`` ([B2S_TOTAL_SLOTS,4] counters) come from stage 1 when it ran fused with the same rows."""
     dev = L.require_cuda(means2d, radii, depths)
@@ -560,11 +567,13 @@ def bin_coarse(means2d: Tensor, radii: Tensor, depths: Tensor, tile_size: int, t
         row_ids = torch.empty(max(M, 1), dtype=torch.int32, device=dev)
         with _stage("isect_depth_keys"):
             check(lib.b2s_isect_depth_keys(M, ptr(depths), ptr(radii), ptr(depth_keys), ptr(row_ids), st), "b2s_isect_depth_keys")
+    if totals is not None and tile_rows is not None:
+        raise B2SError("stage-1 totals count the whole grid: pass totals=None with a tile-row window")
     if totals is None:
         tot = torch.zeros(1, dtype=torch.int64, device=dev)
         with _stage("coarse_count"):
-            check(lib.b2s_coarse_count(M, ptr(means2d), ptr(radii), tile_size, tile_width, tile_height, ptr(tot), st),
-                  "b2s_coarse_count")
+            check(lib.b2s_coarse_count(M, ptr(means2d), ptr(radii), tile_size, tile_width, tile_height, ptr(tot),
+                                       L.tile_rows(tile_rows), st), "b2s_coarse_count")
     sorted_ids = torch.empty(max(M, 1), dtype=torch.int32, device=dev)
     ws = _ws(lib.b2s_depth_order_workspace_bytes(M), dev)
     with _stage("depth_order", launches=6):      # histogram, scan, 4 digit passes
@@ -586,7 +595,8 @@ def bin_coarse(means2d: Tensor, radii: Tensor, depths: Tensor, tile_size: int, t
     ws2 = _ws(lib.b2s_coarse_bin_workspace_bytes(M, n_records), dev)
     with _stage("coarse_bin", launches=5 + ((C * bw * bh - 1).bit_length() > 8)):   # expand, histogram, scan, passes, offsets
         check(lib.b2s_coarse_bin(M, N, ptr(cam), n_records, ptr(sorted_ids), ptr(means2d), ptr(radii), C, tile_size, tile_width,
-                                 tile_height, ptr(recs), ptr(ids), ptr(offsets), ptr(ws2), ws2.numel(), st), "b2s_coarse_bin")
+                                 tile_height, ptr(recs), ptr(ids), ptr(offsets), ptr(ws2), ws2.numel(), L.tile_rows(tile_rows),
+                                 st), "b2s_coarse_bin")
     return CoarseBins(recs, ids, offsets, sorted_ids, n_records, n_isects)
 
 
@@ -599,9 +609,10 @@ _CHANNELS = (1, 2, 3, 4, 8, 16, 32)
 class _RasterizeToPixels(torch.autograd.Function):
     @staticmethod
     def forward(ctx, means2d, conics, colors, opacities, backgrounds, width, height, tile_size, isect_offsets,
-                flatten_ids, absgrad, bins=None, n_cameras=None):
+                flatten_ids, absgrad, bins=None, n_cameras=None, tile_rows=None):
         """Either the reference's lists (isect_offsets [C,th,tw], flatten_ids [I]) or ``bins`` (CoarseBins, with
-        ``n_cameras``): then the kernels expand the per-tile lists from the coarse bins themselves."""
+        ``n_cameras``): then the kernels expand the per-tile lists from the coarse bins themselves.
+        ``tile_rows=(lo, hi)``: composite only tile rows [lo, hi); the outputs hold just those pixel rows."""
         dev = L.require_cuda(means2d, conics, colors, opacities)
         means2d, conics, colors, opacities = f32c(means2d), f32c(conics), f32c(colors), f32c(opacities)
         backgrounds = f32c(backgrounds)
@@ -618,10 +629,14 @@ class _RasterizeToPixels(torch.autograd.Function):
             flatten_ids = flatten_ids.contiguous()
             n_list = flatten_ids.numel()
         ch = colors.shape[-1]
-        render = torch.empty(C, height, width, ch, dtype=torch.float32, device=dev)
-        alphas = torch.empty(C, height, width, 1, dtype=torch.float32, device=dev)
-        last_ids = torch.empty(C, height, width, dtype=torch.int32, device=dev)
-        final_T = torch.empty(C, height, width, dtype=torch.float32, device=dev)
+        row_lo, row_hi = (0, th) if tile_rows is None else (int(tile_rows[0]), int(tile_rows[1]))
+        if not 0 <= row_lo <= row_hi <= th:
+            raise B2SError(f"tile_rows {tile_rows} outside the {th}-row tile grid")
+        out_h = max(0, min(height, row_hi * tile_size) - row_lo * tile_size)
+        render = torch.empty(C, out_h, width, ch, dtype=torch.float32, device=dev)
+        alphas = torch.empty(C, out_h, width, 1, dtype=torch.float32, device=dev)
+        last_ids = torch.empty(C, out_h, width, dtype=torch.int32, device=dev)
+        final_T = torch.empty(C, out_h, width, dtype=torch.float32, device=dev)
         a = L.CompositeFwdArgs(
             C=C, width=width, height=height, tile_size=tile_size, tile_w=tw, tile_h=th, channels=ch,
             n_isects=n_list, means2d=ptr(means2d), conics=ptr(conics), colors=ptr(colors),
@@ -630,19 +645,21 @@ class _RasterizeToPixels(torch.autograd.Function):
             flatten_ids=None if bins is not None else ptr(flatten_ids),
             render_colors=ptr(render), render_alphas=ptr(alphas), last_ids=ptr(last_ids), final_T=ptr(final_T),
             bin_offsets=ptr(isect_offsets) if bins is not None else None, bin_recs=ptr(recs),
-            bin_ids=ptr(flatten_ids) if bins is not None else None)
+            bin_ids=ptr(flatten_ids) if bins is not None else None, tile_row_lo=row_lo, tile_row_hi=row_hi)
+        if row_lo == row_hi == 0 and th > 0:        # an empty window at row 0 would read as "no window"
+            return render, alphas
         with _stage("composite_fwd"):
             check(L.lib().b2s_composite_fwd(ctypes.byref(a), L.stream_ptr(dev)), "b2s_composite_fwd")
         ctx.save_for_backward(means2d, conics, colors, opacities, backgrounds, isect_offsets, flatten_ids, alphas,
                               last_ids, final_T, recs)
-        ctx.cfg = (width, height, tile_size, absgrad, C, tw, th, n_list)
+        ctx.cfg = (width, height, tile_size, absgrad, C, tw, th, n_list, row_lo, row_hi)
         return render, alphas
 
     @staticmethod
     def backward(ctx, v_render, v_alphas):
         (means2d, conics, colors, opacities, backgrounds, isect_offsets, flatten_ids, alphas, last_ids,
          final_T, recs) = ctx.saved_tensors
-        width, height, tile_size, absgrad, C, tw, th, n_list = ctx.cfg
+        width, height, tile_size, absgrad, C, tw, th, n_list, row_lo, row_hi = ctx.cfg
         dev = means2d.device
         use_bins = recs is not None
         ch = colors.shape[-1]
@@ -667,7 +684,7 @@ class _RasterizeToPixels(torch.autograd.Function):
             v_render_colors=ptr(v_render), v_render_alphas=ptr(v_alphas), v_means2d=ptr(v_means2d),
             v_means2d_abs=ptr(v_abs), v_conics=ptr(v_conics), v_colors=ptr(v_colors), v_opacities=ptr(v_opac),
             bin_offsets=ptr(isect_offsets) if use_bins else None, bin_recs=ptr(recs),
-            bin_ids=ptr(flatten_ids) if use_bins else None)
+            bin_ids=ptr(flatten_ids) if use_bins else None, tile_row_lo=row_lo, tile_row_hi=row_hi)
         with _stage("composite_bwd"):
             check(L.lib().b2s_composite_bwd(ctypes.byref(a), L.stream_ptr(dev)), "b2s_composite_bwd")
         v_bg = None
@@ -675,14 +692,14 @@ class _RasterizeToPixels(torch.autograd.Function):
             v_bg = (v_render * final_T.abs()[..., None]).sum(dim=(1, 2))
         if absgrad:
             getattr(ctx, "absgrad_holder", means2d).absgrad = v_abs
-        return v_means2d, v_conics, v_colors, v_opac, v_bg, None, None, None, None, None, None, None, None
+        return v_means2d, v_conics, v_colors, v_opac, v_bg, None, None, None, None, None, None, None, None, None
 
 
 def rasterize_to_pixels(means2d: Tensor, conics: Tensor, colors: Tensor, opacities: Tensor, image_width: int,
                         image_height: int, tile_size: int, isect_offsets: Tensor, flatten_ids: Tensor,
                         backgrounds: Optional[Tensor] = None, masks: Optional[Tensor] = None, packed: bool = False,
                         absgrad: bool = False, bins: Optional["CoarseBins"] = None,
-                        n_cameras: Optional[int] = None) -> Tuple[Tensor, Tensor]:
+                        n_cameras: Optional[int] = None, tile_rows: Optional[Tuple[int, int]] = None) -> Tuple[Tensor, Tensor]:
     """gsplat ``rasterize_to_pixels``: (render_colors [C,H,W,ch], render_alphas [C,H,W,1]).  Rows of the
     per-splat tensors are addressed through ``flatten_ids`` so dense ``[C,N,..]`` and packed ``[nnz,..]`` both work."""
     if masks is not None:
@@ -709,7 +726,8 @@ def rasterize_to_pixels(means2d: Tensor, conics: Tensor, colors: Tensor, opaciti
     fn = _RasterizeToPixels
     # absgrad: gsplat attaches `.absgrad` to the means2d tensor the caller passed in
     render, alphas = _apply_with_holder(fn, holder, means2d, conics, colors, opacities, backgrounds, int(image_width),
-                                        int(image_height), int(tile_size), isect_offsets, flatten_ids, bool(absgrad), bins, C)
+                                        int(image_height), int(tile_size), isect_offsets, flatten_ids, bool(absgrad), bins, C,
+                                        tile_rows)
     if pad:
         render = render[..., :ch]
     return render, alphas

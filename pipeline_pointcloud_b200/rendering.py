@@ -55,6 +55,8 @@ def rasterization(
     distributed: bool = False,
     camera_model: str = "pinhole",
     covars: Optional[Tensor] = None,
+    tile_stripes: bool = False,
+    stripe_rows=None,
     **unsupported,
 ) -> Tuple[Tensor, Tensor, Dict]:
     if unsupported:
@@ -76,7 +78,10 @@ def rasterization(
         return rasterization_distributed(
             means, quats, scales, opacities, colors, viewmats, Ks, width, height, near_plane=near_plane,
             far_plane=far_plane, radius_clip=radius_clip, eps2d=eps2d, sh_degree=sh_degree, packed=packed,
-            backgrounds=backgrounds, render_mode=render_mode, absgrad=absgrad, rasterize_mode=rasterize_mode)
+            backgrounds=backgrounds, render_mode=render_mode, absgrad=absgrad, rasterize_mode=rasterize_mode,
+            tile_stripes=tile_stripes, stripe_rows=stripe_rows)
+    if tile_stripes:
+        raise ValueError("tile_stripes=True needs distributed=True")
 
     require_cuda(means, quats, scales, opacities, colors, viewmats, Ks)
     N, C = means.shape[0], viewmats.shape[0]

@@ -83,3 +83,93 @@ def _allreduce_worker(rank, port):
 
 def test_allreduce_and_camera_gather():
     mp.spawn(_allreduce_worker, args=(29650,), nprocs=WORLD, join=True)
+
+
+# ----------------------------------------------------------------------------------------------------------
+# tile stripes: Gaussian-sharded projection, rows routed to the owners of tile-row stripes
+# ----------------------------------------------------------------------------------------------------------
+S_N, S_C, S_W, S_H = 900, 2, 200, 150          # th = 10 tile rows
+
+
+def _stripe_scene():
+    from oracle import torch_oracle as O           # the checker of the routing decision
+    from pipeline_pointcloud_b200.scene import make_scene
+    s = make_scene(S_N, 0, S_C, S_W, S_H, seed=11)
+    s["scales"][:60] *= 6.0                        # some splats that straddle stripe boundaries
+    radii, means2d, depths, conics, _ = O.fully_fused_projection(s["means"], s["quats"], s["scales"], s["viewmats"], s["Ks"],
+                                                                 S_W, S_H)
+    return O, radii, means2d, depths
+
+
+def test_stripe_selection_matches_oracle_tile_rects():
+    O, radii, means2d, depths = _stripe_scene()
+    th = (S_H + 15) // 16
+    tmin, tmax = O.tile_rects(means2d.reshape(-1, 2), radii.reshape(-1), 16, (S_W + 15) // 16, th)
+    for bounds in ([0, 5, 10], [0, 3, 3, 7, 10], [0, 10]):
+        sel, counts = D.stripe_selection(means2d, radii, 16, th, bounds)
+        start = 0
+        for d in range(len(bounds) - 1):
+            lo, hi = bounds[d], bounds[d + 1]
+            y0, y1 = tmin[:, 1].clamp(lo, hi), tmax[:, 1].clamp(lo, hi)
+            exp = ((radii.reshape(-1) > 0) & (y1 > y0)).nonzero()[:, 0]
+            got = sel[start:start + int(counts[d])]
+            start += int(counts[d])
+            assert torch.equal(got, exp), (bounds, d)
+        assert start == sel.numel()
+    assert D.stripe_bounds(135, 8) == [0, 16, 33, 50, 67, 84, 101, 118, 135]
+    assert D.balanced_stripe_bounds(torch.tensor([1, 1, 1, 1, 10, 10, 1, 1]), 2) == [0, 5, 8]
+    b = D.balanced_stripe_bounds(torch.zeros(9), 3)
+    assert b == D.stripe_bounds(9, 3)
+
+
+def _stripe_worker(rank, port):
+    _init(rank, port)
+    try:
+        O, radii, means2d, depths = _stripe_scene()
+        th = (S_H + 15) // 16
+        bounds = [0, 4, th]
+        n_locals = [S_N // 3, S_N - S_N // 3]
+        lo_n = sum(n_locals[:rank])
+        sl = slice(lo_n, lo_n + n_locals[rank])
+        r_l, m_l = radii[:, sl].contiguous(), means2d[:, sl].contiguous()
+        Nl = n_locals[rank]
+        cam = torch.arange(S_C)[:, None].expand(S_C, Nl)
+        gid = torch.arange(Nl)[None, :].expand(S_C, Nl) + lo_n
+        payload = torch.stack([cam, gid], -1).reshape(-1, 2).double().requires_grad_()
+        ids = (cam * 10000 + gid).reshape(-1, 1)
+        out, oids, cams, gids, sc, rc = D.route_to_stripe_owners(payload, ids, m_l, r_l, 16, th, bounds, n_locals)
+        # expected: every (camera, Gaussian) of the whole scene whose tile rows touch my stripe, source-rank-major,
+        # camera-major inside a source, Gaussian-ascending inside a camera
+        tmin, tmax = O.tile_rects(means2d.reshape(-1, 2), radii.reshape(-1), 16, (S_W + 15) // 16, th)
+        lo, hi = bounds[rank], bounds[rank + 1]
+        hit = ((radii.reshape(-1) > 0) & (tmax[:, 1].clamp(lo, hi) > tmin[:, 1].clamp(lo, hi))).reshape(S_C, S_N)
+        exp_c, exp_g = [], []
+        for src in range(WORLD):
+            s0 = sum(n_locals[:src])
+            h = hit[:, s0:s0 + n_locals[src]]
+            c, g = h.nonzero(as_tuple=True)
+            exp_c.append(c); exp_g.append(g + s0)
+        exp_c, exp_g = torch.cat(exp_c), torch.cat(exp_g)
+        assert torch.equal(cams, exp_c) and torch.equal(gids, exp_g)
+        assert torch.equal(out.detach()[:, 0].long(), exp_c) and torch.equal(out.detach()[:, 1].long(), exp_g)
+        assert torch.equal(oids[:, 0], exp_c * 10000 + exp_g)
+        # per camera, the received rows are in ascending global Gaussian id (the tie-break order of the stable sort)
+        for c in range(S_C):
+            g = gids[cams == c]
+            assert (g[1:] > g[:-1]).all()
+        # backward: a row sent to both stripes receives the sum of both owners' cotangents
+        (out[:, 0] * (rank + 1)).sum().backward()
+        tmin_l, tmax_l = tmin[:, 1].reshape(S_C, S_N)[:, sl].reshape(-1), tmax[:, 1].reshape(S_C, S_N)[:, sl].reshape(-1)
+        vis = r_l.reshape(-1) > 0
+        exp_grad = torch.zeros(S_C * Nl, dtype=torch.float64)
+        for d in range(WORLD):
+            dl, dh = bounds[d], bounds[d + 1]
+            exp_grad += (vis & (tmax_l.clamp(dl, dh) > tmin_l.clamp(dl, dh))).double() * (d + 1)
+        assert torch.equal(payload.grad[:, 0], exp_grad)
+        assert (exp_grad == 3).sum() > 0, "the scene must contain splats that straddle the stripe boundary"
+    finally:
+        dist.destroy_process_group()
+
+
+def test_route_to_stripe_owners():
+    mp.spawn(_stripe_worker, args=(29670,), nprocs=WORLD, join=True)
