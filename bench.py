@@ -35,6 +35,7 @@ WORKLOADS = {
     "config3": (5_800_000, 3, 1297, 840, "antialiased"),
     "config2": (1_000_000, 3, 800, 800, "classic"),
     "config1": (100_000, 0, 256, 256, "classic"),
+    "config5": (30_000_000, 3, 3840, 2160, "antialiased"),     # with --multi-gpu stripes: one 4K camera, strong scaling
     "tiny": (50_000, 3, 320, 240, "antialiased"),
 }
 METRIC = "3DGS rasterization fwd+bwd throughput"
@@ -173,7 +174,11 @@ def run_cpu(workload, steps, warmup, seed=0):
     N, deg, W, H, mode = WORKLOADS[workload]
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    scene = make_scene(N, deg, 1, W, H, seed=seed)
+    if N > 10_000_000:
+        from pipeline_pointcloud_b200.scene import make_scene_blocked
+        scene = make_scene_blocked(N, deg, 1, W, H, seed=seed)
+    else:
+        scene = make_scene(N, deg, 1, W, H, seed=seed)
     sub, w, h, n_sub = cpu_sample_inputs(scene, W, H)
     g = torch.Generator().manual_seed(seed + 1)
     v_r, v_a = torch.rand(1, h, w, 3, generator=g), torch.rand(1, h, w, 1, generator=g)
@@ -208,10 +213,12 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=None)
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (profiling runs only)")
-    ap.add_argument("--multi-gpu", default="sharded", choices=["sharded", "allreduce"],
+    ap.add_argument("--multi-gpu", default="sharded", choices=["sharded", "allreduce", "stripes"],
                     help="N>1: 'sharded' = Gaussians sharded over ranks + all-to-all of projected splats to the camera "
                          "owners (rasterization(distributed=True), what the reference's multi-GPU branch runs); "
-                         "'allreduce' = replicated Gaussians + dense-gradient all-reduce (BASELINE config 4)")
+                         "'allreduce' = replicated Gaussians + dense-gradient all-reduce (BASELINE config 4); "
+                         "'stripes' = ONE camera, Gaussians sharded over ranks, every rank composites a stripe of tile rows "
+                         "(rasterization(distributed=True, tile_stripes=True), BASELINE config 5; strong scaling)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -252,20 +259,35 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     assert world == args.gpus or world == 1, "launch with torchrun --nproc-per-node == --gpus"
 
-    C_total = max(world, 1)
-    scene = make_scene(N, deg, C_total, W, H, seed=0)            # identical on every rank (CPU generator)
-    sharded = world > 1 and args.multi_gpu == "sharded"
+    stripes = world > 1 and args.multi_gpu == "stripes"
+    sharded = world > 1 and args.multi_gpu in ("sharded", "stripes")
+    C_total = 1 if (stripes or args.multi_gpu == "stripes") else max(world, 1)
     lo_n, hi_n = (rank * N // world, (rank + 1) * N // world) if sharded else (0, N)
-    leaves_host = {k: scene[k][lo_n:hi_n].contiguous().pin_memory() for k in ("means", "quats", "scales", "opacities", "colors")}
-    cam_host = {"viewmats": scene["viewmats"][rank:rank + 1].contiguous().pin_memory(),
-                "Ks": scene["Ks"][rank:rank + 1].contiguous().pin_memory()}
+    if N > 10_000_000:      # too large to generate once per rank: block-seeded scene, only this rank's shard
+        from pipeline_pointcloud_b200.scene import make_scene_blocked
+        scene = make_scene_blocked(N, deg, C_total, W, H, seed=0, lo=lo_n, hi=hi_n)
+        leaves_host = {k: scene[k].pin_memory() for k in ("means", "quats", "scales", "opacities", "colors")}
+    else:
+        scene = make_scene(N, deg, C_total, W, H, seed=0)            # identical on every rank (CPU generator)
+        leaves_host = {k: scene[k][lo_n:hi_n].contiguous().pin_memory() for k in ("means", "quats", "scales", "opacities", "colors")}
+    cam_i = 0 if C_total == 1 else rank
+    cam_host = {"viewmats": scene["viewmats"][cam_i:cam_i + 1].contiguous().pin_memory(),
+                "Ks": scene["Ks"][cam_i:cam_i + 1].contiguous().pin_memory()}
     params = {k: v.to(dev).requires_grad_() for k, v in leaves_host.items()}
     cams = {k: v.to(dev) for k, v in cam_host.items()}
-    g = torch.Generator().manual_seed(1 + rank)
-    v_r_host = torch.rand(1, H, W, 3, generator=g).pin_memory()
-    v_a_host = torch.rand(1, H, W, 1, generator=g).pin_memory()
+    g = torch.Generator().manual_seed(1 + (0 if stripes else rank))
+    v_r_host = torch.rand(1, H, W, 3, generator=g)
+    v_a_host = torch.rand(1, H, W, 1, generator=g)
+    if stripes:             # every rank differentiates its own pixel rows of the same image cotangent
+        from pipeline_pointcloud_b200.distributed import stripe_bounds
+        sb = stripe_bounds(math.ceil(H / 16), world)
+        y0, y1 = min(H, sb[rank] * 16), min(H, sb[rank + 1] * 16)
+        v_r_host, v_a_host = v_r_host[:, y0:y1].contiguous(), v_a_host[:, y0:y1].contiguous()
+    v_r_host, v_a_host = v_r_host.pin_memory(), v_a_host.pin_memory()
     v_r, v_a = v_r_host.to(dev), v_a_host.to(dev)
     kw = dict(sh_degree=deg, packed=args.packed or sharded, rasterize_mode=mode, distributed=sharded)
+    if stripes:
+        kw["tile_stripes"] = True
     plist = list(params.values())
     stats = {}
 
@@ -328,7 +350,7 @@ def main():
     # ---- e2e: host buffers in, host buffers out -----------------------------------------------------------
     h2d = sum(v.numel() * 4 for v in leaves_host.values()) + sum(v.numel() * 4 for v in cam_host.values()) \
         + v_r_host.numel() * 4 + v_a_host.numel() * 4
-    d2h = (H * W * 3 + H * W) * 4 + sum(v.numel() * 4 for v in leaves_host.values())
+    d2h = (v_r_host.numel() + v_a_host.numel()) * 4 + sum(v.numel() * 4 for v in leaves_host.values())
 
     # Two slots, three streams: the H2D of step i+1 runs while step i computes and while its results go back (PCIe is
     # full duplex), so a step costs max(H2D, D2H, compute) instead of their sum.  Every step still moves all of its
@@ -341,7 +363,7 @@ def main():
             "p": {k: torch.empty_like(v, device=dev).requires_grad_() for k, v in leaves_host.items()},
             "c": {k: torch.empty_like(v, device=dev) for k, v in cam_host.items()},
             "vr": torch.empty_like(v_r), "va": torch.empty_like(v_a),
-            "out": {"render": torch.empty(1, H, W, 3).pin_memory(), "alpha": torch.empty(1, H, W, 1).pin_memory()},
+            "out": {"render": torch.empty(v_r_host.shape).pin_memory(), "alpha": torch.empty(v_a_host.shape).pin_memory()},
             "grads": {k: torch.empty_like(v).pin_memory() for k, v in leaves_host.items()},
             "ev_in": torch.cuda.Event(), "ev_done": torch.cuda.Event(), "ev_out": None, "keep": None,
         })
@@ -408,6 +430,8 @@ def main():
     key_bits = 32 + (tiles).bit_length() + (1).bit_length()
     K = (deg + 1) ** 2
     n_cam_local = C_total if (world > 1 and sharded) else 1
+    if stripes:      # per-rank counters -> whole-job totals are not gathered; report rank 0's
+        pass
     R = int(m_last.get("n_coarse_records") or 0) if m_last is not None else 0
     ab = algorithmic_bytes(hi_n - lo_n, n_cam_local, n_visible, stats["n_reached"], I, R, W * H, K, tiles, key_bits)
     per_stage = {}
@@ -427,11 +451,15 @@ def main():
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong" if args.multi_gpu == "stripes" else "weak",
+        "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
         "config": {"workload": f"{args.workload}: {N} random Gaussians, SH deg {deg}, {W}x{H}, {mode}, fwd+bwd, "
-                               f"packed={args.packed or sharded}, 1 camera per GPU" +
-                               ((", Gaussians sharded over ranks, NCCL all-to-all of projected splats to the camera owners, "
+                               f"packed={args.packed or sharded}, " + ("1 camera" if C_total == 1 else "1 camera per GPU") +
+                               ((", Gaussians sharded over ranks, every rank composites a stripe of tile rows of the one camera: "
+                                 "fused pack + NVLink peer-store exchange of projected splats to the stripe owners, gradients "
+                                 "returned by the reverse exchange and summed at the owner") if stripes else
+                                (", Gaussians sharded over ranks, NCCL all-to-all of projected splats to the camera owners, "
                                  "reverse all-to-all of gradients") if sharded else
                                 (", replicated Gaussians, dense-gradient all-reduce" if world > 1 else "")),
                    "n_isects": I, "n_visible": n_visible, "n_reached": stats["n_reached"], "n_coarse_records": R,

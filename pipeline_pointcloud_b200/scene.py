@@ -56,3 +56,33 @@ def make_scene(N: int, sh_degree: int, C: int, width: int, height: int, seed: in
     out = {"means": means, "quats": quats, "scales": scales, "opacities": opacities, "colors": colors}
     out.update(make_cameras(C, width, height, extent))
     return out
+
+
+def make_scene_blocked(N: int, sh_degree: int, C: int, width: int, height: int, seed: int = 0, extent: float = 3.0,
+                       lo: int = 0, hi: int = None, block: int = 1 << 20) -> Dict[str, torch.Tensor]:
+    """The same distribution as ``make_scene``, generated in independent blocks of ``block`` Gaussians (block b is
+    seeded by (seed, b)), so a rank of a Gaussian-sharded job can build just its shard [lo, hi) of a scene too large
+    to generate N times over (30 M Gaussians = 7 GB).  Any [lo, hi) is a slice of the same N-Gaussian scene."""
+    hi = N if hi is None else hi
+    K = (sh_degree + 1) ** 2
+    base = math.log(0.6 * (8.0 * extent ** 3 / N) ** (1.0 / 3.0))
+    parts = {k: [] for k in ("means", "quats", "scales", "opacities", "colors")}
+    for b in range(lo // block, (max(hi, lo + 1) - 1) // block + 1):
+        b0, b1 = b * block, min(N, (b + 1) * block)
+        n = b1 - b0
+        if n <= 0:
+            break
+        g = torch.Generator().manual_seed(seed * 1_000_003 + b + 1)
+        means = extent * (2.0 * torch.rand(n, 3, generator=g) - 1.0)
+        scales = torch.exp(base + 0.3 * torch.randn(n, 3, generator=g))
+        quats = torch.randn(n, 4, generator=g)
+        opacities = torch.sigmoid(1.5 * torch.randn(n, generator=g))
+        sh0 = (torch.rand(n, 1, 3, generator=g) - 0.5) / SH_C0
+        shN = 0.05 * torch.randn(n, K - 1, 3, generator=g)
+        colors = torch.cat([sh0, shN], dim=1)
+        s0, s1 = max(lo, b0) - b0, min(hi, b1) - b0
+        for k, v in (("means", means), ("quats", quats), ("scales", scales), ("opacities", opacities), ("colors", colors)):
+            parts[k].append(v[s0:s1])
+    out = {k: (torch.cat(v).contiguous() if v else torch.empty(0)) for k, v in parts.items()}
+    out.update(make_cameras(C, width, height, extent))
+    return out
