@@ -269,6 +269,62 @@ B2S_API int b2s_p2p_join(int64_t n, int32_t channels, const float* g_means2d, co
                          const int64_t* host_src_base, void* const* host_peer_buffers, b2s_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Multi-GPU tile stripes (rasterization(distributed=True, tile_stripes=True); SURVEY.md 8e-ii, BASELINE config 5):
+ * every rank owns a shard of the Gaussians and the tile rows [bounds[r], bounds[r+1]) of the shared camera(s).
+ * The exchange is fused into the producing kernels over NVLink peer mappings of symmetric memory; the caller
+ * provides the barriers.  No counterpart in the reference (its multi-GPU branch routes to camera owners, above).
+ *
+ *   b2s_stripe_count : dest_mask [M] (bit d: the row's tile rectangle touches stripe d), per-CTA row counts per
+ *                      destination cta_counts [world][b2s_stripe_ctas(M)], totals [world][4] int64 =
+ *                      (rows, tile intersections, coarse-bin records, tag) per destination (zeroed by the call)
+ *   b2s_stripe_scan  : cta_counts -> exclusive prefix along the CTAs, per destination (in place)
+ *   b2s_p2p_put      : words_per_peer 64-bit words from src + d*src_stride to host_peer_dst[d] (NULL: skipped)
+ *   b2s_stripe_pack  : stores every row's record into each destination's receive buffer at
+ *                      host_dest_base[d] + its rank among this rank's rows for d (ascending row order).
+ *                      Receive buffer (capacity cap_rows, 32-bit words, SoA): [means2d 2cap][depths cap][conics 3cap]
+ *                      [opacities cap][colours ch*cap][radii cap][camera cap][global Gaussian id cap]
+ *   b2s_stripe_unpack: receiver, rows [0,n) of its buffer -> tensors (+ int64 camera_ids / gaussian_ids), and the
+ *                      inputs of binning: tiles_per_gauss inside the window `rows`, depth_keys, row_ids
+ *   b2s_stripe_return: backward; rows with a non-zero gradient are appended as [source row, v_xy, v_depth, v_conic,
+ *                      v_opacity, v_colour] = 8+ch words to this rank's region (first slot host_region_base[s]) of
+ *                      source rank s's return buffer; counters [world] (zeroed by the call) = records per source
+ *   b2s_stripe_scatter_add : source; adds the ret_counts[d] records of every region into the dense zero-filled gradients
+ * ---------------------------------------------------------------------------------------------- */
+#define B2S_MAX_RANKS 16
+typedef struct {
+    int32_t world;                      /* stripes = ranks, 1..B2S_MAX_RANKS */
+    int32_t bounds[B2S_MAX_RANKS + 1];  /* ascending tile rows, bounds[0] = 0, bounds[world] = tile_h */
+} b2s_stripes;
+B2S_API int64_t b2s_stripe_ctas(int64_t M);
+B2S_API int b2s_stripe_count(int64_t M, const float* means2d, const int32_t* radii, int32_t tile_size, int32_t tile_w,
+                             int32_t tile_h, const b2s_stripes* stripes /* host */, uint16_t* dest_mask, uint32_t* cta_counts,
+                             int64_t* totals, int64_t tag /* stored in totals[d][3], e.g. this rank's Gaussian count */,
+                             b2s_stream_t stream);
+B2S_API int b2s_stripe_scan(int64_t M, int32_t world, uint32_t* cta_counts, b2s_stream_t stream);
+B2S_API int b2s_p2p_put(int32_t world, const int64_t* src, int32_t words_per_peer, int32_t src_stride,
+                        void* const* host_peer_dst, b2s_stream_t stream);
+B2S_API int b2s_stripe_pack(int64_t M, int64_t N, int32_t channels, int64_t gid_offset, const float* means2d,
+                            const float* depths, const float* conics, const float* opacities, const float* colors,
+                            const int32_t* radii, const uint16_t* dest_mask, const uint32_t* cta_prefix, int32_t world,
+                            const int64_t* host_dest_base, int64_t cap_rows, void* const* host_peer_buffers,
+                            b2s_stream_t stream);
+B2S_API int b2s_stripe_unpack(int64_t n, int64_t cap_rows, int32_t channels, const float* recv_buffer, int32_t tile_size,
+                              int32_t tile_w, int32_t tile_h, const b2s_tile_rows* rows, float* means2d, float* depths,
+                              float* conics, float* opacities, float* colors, int32_t* radii, int64_t* camera_ids,
+                              int64_t* gaussian_ids, int32_t* tiles_per_gauss, uint32_t* depth_keys, int32_t* row_ids,
+                              b2s_stream_t stream);
+B2S_API int b2s_stripe_return(int64_t n, int32_t channels, const float* g_means2d, const float* g_depths,
+                              const float* g_conics, const float* g_opacities, const float* g_colors,
+                              const int64_t* camera_ids, const int64_t* gaussian_ids, int32_t world,
+                              const int64_t* host_recv_prefix /* [world+1] */, const int64_t* host_gid_offset,
+                              const int64_t* host_n_src, const int64_t* host_region_base, int64_t* counters,
+                              void* const* host_peer_buffers, b2s_stream_t stream);
+B2S_API int b2s_stripe_scatter_add(int32_t world, int32_t channels, const float* ret_buffer, const int64_t* host_region_base,
+                                   const int64_t* host_region_cap, const int64_t* ret_counts /* device [world] */,
+                                   float* v_means2d, float* v_depths, float* v_conics, float* v_opacities, float* v_colors,
+                                   b2s_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Stage 3: per-16x16-tile front-to-back compositing.  Replaces gsplat `rasterize_to_pixels`
  * fwd / bwd.  Rows of means2d/conics/colors/opacities are addressed by
  * flatten_ids, so dense [C*N] and packed [nnz] layouts both work.  channels in {1,2,3,4,8,16,32}.

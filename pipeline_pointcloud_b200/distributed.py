@@ -283,13 +283,13 @@ class _SymmBuffers:
     _cache = {}
 
     @classmethod
-    def get(cls, group, key, n_floats, dev):
+    def get(cls, group, key, n_floats, dev, dtype=torch.float32):
         import torch.distributed._symmetric_memory as symm
         k = (id(group), key, dev.index)
         cur = cls._cache.get(k)
         if cur is None or cur[0].numel() < n_floats:
             cap = int(n_floats * 1.25) + 4096
-            t = symm.empty(cap, dtype=torch.float32, device=dev)
+            t = symm.empty(cap, dtype=dtype, device=dev)
             h = symm.rendezvous(t, group if group is not None else dist.group.WORLD)
             cur = (t, h)
             cls._cache[k] = cur
@@ -381,6 +381,126 @@ class _RouteSplatsP2P(torch.autograd.Function):
         return tuple(outs) + (None,) * 8
 
 
+class _RouteStripes(torch.autograd.Function):
+    """Tile-stripe routing fused with the exchange (csrc/stripes.cu).  Forward: count -> scan -> W x W table through
+    peer stores (ONE host sync: it sizes every buffer of the receiver, binning included) -> pack kernel storing SoA
+    records straight into the stripe owners' buffers -> unpack (+ tile counts / depth keys of the stripe).
+    Backward: only rows compositing reached are returned, as sparse records appended to the source's buffer, and
+    added into its dense gradients.  Four ~7 us symmetric-memory barriers forward, two backward; no NCCL call."""
+
+    @staticmethod
+    def forward(ctx, means2d, depths, conics, opac, cols, radii, group, bounds, tile_geom):
+        import ctypes
+        from . import _lib as L
+        from . import ops
+        dev = means2d.device
+        rank, world = dist.get_rank(group), dist.get_world_size(group)
+        tile_size, tw, th = tile_geom
+        C, N = radii.shape
+        M, ch = C * N, cols.shape[-1]
+        means2d, depths, conics, opac, cols = (L.f32c(t) for t in (means2d, depths, conics, opac, cols))
+        radii = radii.contiguous()
+        lib, st = L.lib(), L.stream_ptr(dev)
+        n_ctas = int(lib.b2s_stripe_ctas(M))
+        mask = torch.empty(max(M, 1), dtype=torch.int16, device=dev)
+        cta_counts = torch.empty(world * n_ctas, dtype=torch.int32, device=dev)
+        totals = torch.empty(world * 4, dtype=torch.int64, device=dev)
+        sb = L.Stripes(world=world)
+        for d, b in enumerate(bounds):
+            sb.bounds[d] = int(b)
+        W4 = world * 4
+        tab, h_tab = _SymmBuffers.get(group, "s_tab", world * W4 + world, dev, dtype=torch.int64)
+        with ops._stage("stripe_count", launches=3):
+            L.check(lib.b2s_stripe_count(M, L.ptr(means2d), L.ptr(radii), tile_size, tw, th, ctypes.byref(sb), L.ptr(mask),
+                                         L.ptr(cta_counts), L.ptr(totals), N, st), "b2s_stripe_count")
+            L.check(lib.b2s_stripe_scan(M, world, L.ptr(cta_counts), st), "b2s_stripe_scan")
+            h_tab.barrier()            # every rank has finished with last iteration's table and exchange buffers
+            L.check(lib.b2s_p2p_put(world, L.ptr(totals), W4, 0, _ptrs([p + rank * W4 * 8 for p in h_tab.buffer_ptrs]), st),
+                    "b2s_p2p_put")
+            h_tab.barrier()
+        table = tab[: world * W4].view(world, world, 4).tolist()       # the one host sync: [src][dst] -> rows, isects, records
+        send_counts = [table[rank][d][0] for d in range(world)]
+        recv_counts = [table[s][rank][0] for s in range(world)]
+        n_recv = int(sum(recv_counts))
+        n_isects = int(sum(table[s][rank][1] for s in range(world)))
+        n_records = int(sum(table[s][rank][2] for s in range(world)))
+        n_world = [int(table[s][0][3]) for s in range(world)]           # every rank's Gaussian count rode along as the tag
+        F, G = 10 + ch, 8 + ch
+        need_rows = max(sum(table[s][d][0] for s in range(world)) for d in range(world))
+        need_ret = max(sum(table[s][d][0] for d in range(world)) for s in range(world))
+        buf_f, h_f = _SymmBuffers.get(group, "s_fwd", (need_rows + 2) * F, dev)
+        buf_r, h_r = _SymmBuffers.get(group, "s_ret", need_ret * G, dev)
+        cap = (buf_f.numel() // F) & ~1
+        dest_base = [sum(table[s][d][0] for s in range(rank)) for d in range(world)]
+        with ops._stage("stripe_pack"):
+            L.check(lib.b2s_stripe_pack(M, N, ch, int(sum(n_world[:rank])), L.ptr(means2d), L.ptr(depths), L.ptr(conics),
+                                        L.ptr(opac), L.ptr(cols), L.ptr(radii), L.ptr(mask), L.ptr(cta_counts), world,
+                                        _i64(dest_base), cap, _ptrs(h_f.buffer_ptrs), st), "b2s_stripe_pack")
+            h_f.barrier()              # every peer's stores have landed
+        o = dict(device=dev)
+        means2d_m, depths_m, conics_m = torch.empty(n_recv, 2, **o), torch.empty(n_recv, **o), torch.empty(n_recv, 3, **o)
+        opac_m, cols_m = torch.empty(n_recv, **o), torch.empty(n_recv, ch, **o)
+        radii_m, tiles_m = torch.empty(n_recv, dtype=torch.int32, **o), torch.empty(n_recv, dtype=torch.int32, **o)
+        dkeys, rowids = torch.empty(max(n_recv, 1), dtype=torch.int32, **o), torch.empty(max(n_recv, 1), dtype=torch.int32, **o)
+        cam_m, gid_m = torch.empty(n_recv, dtype=torch.int64, **o), torch.empty(n_recv, dtype=torch.int64, **o)
+        rows = L.TileRows(int(bounds[rank]), int(bounds[rank + 1]))
+        with ops._stage("stripe_unpack"):
+            L.check(lib.b2s_stripe_unpack(n_recv, cap, ch, L.ptr(buf_f), tile_size, tw, th, ctypes.byref(rows), L.ptr(means2d_m),
+                                          L.ptr(depths_m), L.ptr(conics_m), L.ptr(opac_m), L.ptr(cols_m), L.ptr(radii_m),
+                                          L.ptr(cam_m), L.ptr(gid_m), L.ptr(tiles_m), L.ptr(dkeys), L.ptr(rowids), st),
+                    "b2s_stripe_unpack")
+        ctx.save_for_backward(cam_m, gid_m)
+        ctx.cfg = (send_counts, recv_counts, [table[s][:] for s in range(world)], list(n_world), group, ch,
+                   (means2d.shape, depths.shape, conics.shape, opac.shape, cols.shape))
+        ctx.set_materialize_grads(False)
+        ctx.mark_non_differentiable(radii_m, tiles_m, dkeys, rowids, cam_m, gid_m)
+        ctx.counts = (n_isects, n_records)
+        _RouteStripes.last_counts = (n_isects, n_records)
+        return means2d_m, depths_m, conics_m, opac_m, cols_m, radii_m, tiles_m, dkeys, rowids, cam_m, gid_m
+
+    @staticmethod
+    def backward(ctx, g_means2d, g_depths, g_conics, g_opac, g_cols, *_):
+        from . import _lib as L
+        from . import ops
+        cam_m, gid_m = ctx.saved_tensors
+        send_counts, recv_counts, table, n_world, group, ch, shapes = ctx.cfg
+        dev = cam_m.device
+        rank, world = dist.get_rank(group), dist.get_world_size(group)
+        n_recv, G, W4 = int(sum(recv_counts)), 8 + ch, world * 4
+        lib, st = L.lib(), L.stream_ptr(dev)
+        tab, h_tab = _SymmBuffers.get(group, "s_tab", 0, dev, dtype=torch.int64)
+        buf_r, h_r = _SymmBuffers.get(group, "s_ret", 0, dev)
+        gs = [L.f32c(g) for g in (g_means2d, g_depths, g_conics, g_opac, g_cols)]
+        counters = torch.empty(world, dtype=torch.int64, device=dev)
+        recv_prefix = [0]
+        for c in recv_counts:
+            recv_prefix.append(recv_prefix[-1] + int(c))
+        gid_offset = [int(sum(n_world[:s])) for s in range(world)]
+        region_base = [sum(table[s][d][0] for d in range(rank)) for s in range(world)]     # my region inside s's buffer
+        with ops._stage("stripe_return", launches=2):
+            h_r.barrier()              # every source has consumed what the previous backward left in its buffer
+            L.check(lib.b2s_stripe_return(n_recv, ch, *[L.ptr(g) for g in gs], L.ptr(cam_m), L.ptr(gid_m), world,
+                                          _i64(recv_prefix), _i64(gid_offset), _i64(n_world), _i64(region_base), L.ptr(counters),
+                                          _ptrs(h_r.buffer_ptrs), st), "b2s_stripe_return")
+            L.check(lib.b2s_p2p_put(world, L.ptr(counters), 1, 1,
+                                    _ptrs([p + (world * W4 + rank) * 8 for p in h_tab.buffer_ptrs]), st), "b2s_p2p_put")
+            h_r.barrier()
+        # one zero-filled slab for the dense gradients of the projected rows
+        sizes = [int(torch.Size(s).numel()) for s in shapes]
+        slab = torch.zeros(sum(sizes), dtype=torch.float32, device=dev)
+        outs, o = [], 0
+        for sz, shp in zip(sizes, shapes):
+            outs.append(slab[o:o + sz].view(shp))
+            o += sz
+        my_base = [0]
+        for c in send_counts:
+            my_base.append(my_base[-1] + int(c))
+        with ops._stage("stripe_scatter"):
+            L.check(lib.b2s_stripe_scatter_add(world, ch, L.ptr(buf_r), _i64(my_base[:-1]), _i64(send_counts),
+                                               tab[world * W4:].data_ptr(), *[L.ptr(t) for t in outs], st), "b2s_stripe_scatter_add")
+        return tuple(outs) + (None,) * 4
+
+
 def _route_impl():
     """'p2p' (default): fused pack + NVLink peer stores through symmetric memory; 'nccl': pack + all_to_all_single."""
     import os
@@ -425,10 +545,12 @@ def rasterization_distributed(means, quats, scales, opacities, colors, viewmats,
     tw, th = math.ceil(width / tile_size), math.ceil(height / tile_size)
 
     if tile_stripes:
-        n = torch.tensor([N], dtype=torch.int64, device=means.device)
-        ns = [torch.empty_like(n) for _ in range(world)]
-        dist.all_gather(ns, n, group=group)
-        n_world = [int(t) for t in ns]
+        n_world = None
+        if not (_route_impl() == "p2p" and world <= 16):      # (the fused path carries the shard sizes in its count table)
+            n = torch.tensor([N], dtype=torch.int64, device=means.device)
+            ns = [torch.empty_like(n) for _ in range(world)]
+            dist.all_gather(ns, n, group=group)
+            n_world = [int(t) for t in ns]
         viewmats_all, Ks_all, C_all = viewmats, Ks, C_local          # the same cameras on every rank
         bounds = [int(b) for b in (stripe_rows if stripe_rows is not None else stripe_bounds(th, world))]
         if len(bounds) != world + 1 or bounds[0] != 0 or bounds[-1] != th or any(b1 < b0 for b0, b1 in zip(bounds, bounds[1:])):
@@ -460,20 +582,27 @@ def rasterization_distributed(means, quats, scales, opacities, colors, viewmats,
     ch = cols.shape[-1]
 
     # ---- route the visible pairs to their owners: (fused) pack -> exchange -> split -------------------------------
-    with torch.no_grad():
+    fused_stripes = tile_stripes and _route_impl() == "p2p" and world <= 16
+    dkeys = rowids = counts = None
+    if fused_stripes:
+        (means2d_m, depths_m, conics_m, opac_m, cols_m, radii_m, tiles_m, dkeys, rowids, cam_local,
+         gauss_global) = _RouteStripes.apply(means2d, depths, conics, opac, cols, radii, group, bounds, (tile_size, tw, th))
+        counts = _RouteStripes.last_counts
+    else:
+        with torch.no_grad():
+            if tile_stripes:
+                with ops._stage("stripe_select", launches=0):
+                    sel, send = stripe_selection(means2d, radii, tile_size, th, bounds)
+            else:
+                sel, send = camera_owner_selection(radii, C_local, world)
+        (means2d_m, depths_m, conics_m, opac_m, cols_m, radii_m, tiles_m, cam_local,
+         gauss_global) = (_RouteSplatsP2P if _route_impl() == "p2p" and world <= 16 else _RouteSplatsCUDA).apply(
+            means2d, depths, conics, opac, cols, radii, tiles, C_all if tile_stripes else C_local, n_world, group, sel, send,
+            bool(tile_stripes))
         if tile_stripes:
-            with ops._stage("stripe_select", launches=0):
-                sel, send = stripe_selection(means2d, radii, tile_size, th, bounds)
-        else:
-            sel, send = camera_owner_selection(radii, C_local, world)
-    (means2d_m, depths_m, conics_m, opac_m, cols_m, radii_m, tiles_m, cam_local,
-     gauss_global) = (_RouteSplatsP2P if _route_impl() == "p2p" and world <= 16 else _RouteSplatsCUDA).apply(
-        means2d, depths, conics, opac, cols, radii, tiles, C_all if tile_stripes else C_local, n_world, group, sel, send,
-        bool(tile_stripes))
-    if tile_stripes:
-        # the record carries the whole-image tile count: recount inside the stripe
-        tiles_m = ops.isect_tiles(means2d_m.detach(), radii_m, depths_m.detach(), tile_size, tw, th, sort=False, packed=True,
-                                  n_cameras=C_local, camera_ids=cam_local, tile_rows=rows, count_only=True)
+            # the record carries the whole-image tile count: recount inside the stripe
+            tiles_m = ops.isect_tiles(means2d_m.detach(), radii_m, depths_m.detach(), tile_size, tw, th, sort=False, packed=True,
+                                      n_cameras=C_local, camera_ids=cam_local, tile_rows=rows, count_only=True)
 
     # ---- own cameras / own stripe: binning + compositing ---------------------------------------------------------
     from .rendering import _use_coarse_bins
@@ -487,7 +616,8 @@ def rasterization_distributed(means, quats, scales, opacities, colors, viewmats,
         meta["stripe_pixel_rows"] = (rows[0] * tile_size, max(rows[0] * tile_size, min(height, rows[1] * tile_size)))
         meta["stripe_bounds"] = bounds
     if _use_coarse_bins() and ops.coarse_bins_supported(C_local, tw, th, ch):
-        bins = ops.bin_coarse(means2d_m, radii_m, depths_m, tile_size, tw, th, C_local, camera_ids=cam_local, tile_rows=rows)
+        bins = ops.bin_coarse(means2d_m, radii_m, depths_m, tile_size, tw, th, C_local, camera_ids=cam_local, tile_rows=rows,
+                              depth_keys=dkeys, row_ids=rowids, counts=counts)
         render_colors, render_alphas = ops.rasterize_to_pixels(
             means2d_m, conics_m, cols_m, opac_m, width, height, tile_size, None, None,
             backgrounds=backgrounds, packed=True, absgrad=absgrad, bins=bins, n_cameras=C_local, tile_rows=rows)

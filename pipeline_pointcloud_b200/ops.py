@@ -550,7 +550,7 @@ class CoarseBins:
 def bin_coarse(means2d: Tensor, radii: Tensor, depths: Tensor, tile_size: int, tile_width: int, tile_height: int,
                n_cameras: int, camera_ids: Optional[Tensor] = None, depth_keys: Optional[Tensor] = None,
                row_ids: Optional[Tensor] = None, totals: Optional[Tensor] = None,
-               tile_rows: Optional[Tuple[int, int]] = None) -> CoarseBins:
+               tile_rows: Optional[Tuple[int, int]] = None, counts: Optional[Tuple[int, int]] = None) -> CoarseBins:
     """Depth sort of the rows + coarse binning (b2s_depth_order, b2s_coarse_bin).  ``depth_keys`` / ``row_ids`` /
     ``totals`` ([B2S_TOTAL_SLOTS,4] counters) come from stage 1 when it ran fused with the same rows."""
     dev = L.require_cuda(means2d, radii, depths)
@@ -569,7 +569,7 @@ def bin_coarse(means2d: Tensor, radii: Tensor, depths: Tensor, tile_size: int, t
             check(lib.b2s_isect_depth_keys(M, ptr(depths), ptr(radii), ptr(depth_keys), ptr(row_ids), st), "b2s_isect_depth_keys")
     if totals is not None and tile_rows is not None:
         raise B2SError("stage-1 totals count the whole grid: pass totals=None with a tile-row window")
-    if totals is None:
+    if totals is None and counts is None:
         tot = torch.zeros(1, dtype=torch.int64, device=dev)
         with _stage("coarse_count"):
             check(lib.b2s_coarse_count(M, ptr(means2d), ptr(radii), tile_size, tile_width, tile_height, ptr(tot),
@@ -580,7 +580,9 @@ def bin_coarse(means2d: Tensor, radii: Tensor, depths: Tensor, tile_size: int, t
         check(lib.b2s_depth_order(M, ptr(depth_keys), ptr(row_ids), ptr(sorted_ids), ptr(ws), ws.numel(), st), "b2s_depth_order")
     # The one host sync of a forward (sizes the record buffers).  The depth sort is already enqueued, so the GPU
     # keeps working while the host waits for the counts that stage 1 produced.
-    if totals is not None:
+    if counts is not None:             # (n_isects, n_records) already on the host (the multi-GPU stripe table)
+        n_isects, n_records = int(counts[0]), int(counts[1])
+    elif totals is not None:
         sums = totals.sum(dim=0).tolist()
         n_isects, n_records = int(sums[0]), int(sums[2])
     else:
