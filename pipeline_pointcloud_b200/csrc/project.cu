@@ -23,9 +23,7 @@ constexpr int BWD_THREADS = 128;
 __host__ __device__ constexpr int sh_row_stride(int K) { return (3 * K) | 1; }  // odd => conflict-free rows
 
 // ---- warp-cooperative movement of 32 SH rows between global memory and the padded smem tile -------
-// gbase points at row 0 of the warp's chunk, `rows` valid rows, row_mask: which rows to move.  Rows outside the
-// mask never touch shared memory: the loader leaves their tile rows undefined (nobody reads them) and the store
-// writes zeros for them straight from registers, so a warp with few live rows is a pure streaming write.
+// gbase points at row 0 of the warp's chunk, `rows` valid rows, row_mask: which rows to move.
 template <int KVEC>  // 16: 3*K == 48 floats and stride_k == K -> 128-bit path; 0: generic
 __device__ __forceinline__ void sh_rows_load(float* tile, const float* gbase, int rows, unsigned row_mask, int K,
                                              int stride_k, int lane) {
@@ -44,23 +42,22 @@ __device__ __forceinline__ void sh_rows_load(float* tile, const float* gbase, in
         for (int i = 0; i < 12; ++i) {
             int q = lane + 32 * i;
             int r = q / 12, e = (q - r * 12) * 4;
-            if ((row_mask >> r) & 1u) {
-                float* d = tile + r * rs + e;
-                d[0] = v[i].x; d[1] = v[i].y; d[2] = v[i].z; d[3] = v[i].w;
-            }
+            float* d = tile + r * rs + e;
+            d[0] = v[i].x; d[1] = v[i].y; d[2] = v[i].z; d[3] = v[i].w;
         }
     } else {
         const int per = 3 * K;
         for (int f = lane; f < 32 * per; f += 32) {
             int r = f / per, e = f - r * per;
-            if ((r < rows) && ((row_mask >> r) & 1u)) tile[r * rs + e] = ldg_stream1(gbase + (size_t)r * stride_k * 3 + e);
+            bool on = (r < rows) && ((row_mask >> r) & 1u);
+            tile[r * rs + e] = on ? ldg_stream1(gbase + (size_t)r * stride_k * 3 + e) : 0.f;
         }
     }
 }
 
 template <int KVEC>
-__device__ __forceinline__ void sh_rows_store(const float* tile, float* gbase, int rows, unsigned row_mask, int K, int stride_k,
-                                              int lane, bool accumulate) {
+__device__ __forceinline__ void sh_rows_store(const float* tile, float* gbase, int rows, int K, int stride_k, int lane,
+                                              bool accumulate) {
     const int rs = sh_row_stride(K);
     if (KVEC == 16 && !accumulate) {
         float4* g4 = reinterpret_cast<float4*>(gbase);
@@ -69,12 +66,8 @@ __device__ __forceinline__ void sh_rows_store(const float* tile, float* gbase, i
             int q = lane + 32 * i;
             int r = q / 12, e = (q - r * 12) * 4;
             if (r < rows) {
-                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                if ((row_mask >> r) & 1u) {
-                    const float* s = tile + r * rs + e;
-                    v = make_float4(s[0], s[1], s[2], s[3]);
-                }
-                stg_stream4(g4 + q, v);
+                const float* s = tile + r * rs + e;
+                stg_stream4(g4 + q, make_float4(s[0], s[1], s[2], s[3]));
             }
         }
     } else {
@@ -82,10 +75,8 @@ __device__ __forceinline__ void sh_rows_store(const float* tile, float* gbase, i
         for (int f = lane; f < 32 * per; f += 32) {
             int r = f / per, e = f - r * per;
             if (r < rows) {
-                const bool on = (row_mask >> r) & 1u;
                 float* g = gbase + (size_t)r * stride_k * 3 + e;
-                if (accumulate) { if (on) *g += tile[r * rs + e]; }
-                else *g = on ? tile[r * rs + e] : 0.f;
+                *g = accumulate ? (*g + tile[r * rs + e]) : tile[r * rs + e];
             }
         }
     }
@@ -274,7 +265,7 @@ __global__ void __launch_bounds__(SHB_THREADS, 4) sh_bwd_fused_kernel(const b2s_
         }
         return;
     }
-    // rows outside row_mask (culled / occluded in every camera) stay out of shared memory; the store writes their zeros
+    // masked-off rows are zero-filled by the loader, so culled Gaussians get zero gradients for free
     sh_rows_load<KVEC>(tile_in, a.sh_coeffs + (size_t)row0 * a.sh_stride_k * 3, rows, row_mask, K, a.sh_stride_k, lane);
     if (MULTI)
         for (int f = lane; f < 32 * rs; f += 32) tile_out[f] = 0.f;
@@ -316,7 +307,7 @@ __global__ void __launch_bounds__(SHB_THREADS, 4) sh_bwd_fused_kernel(const b2s_
     }
     __syncwarp();
     if (rows > 0)
-        sh_rows_store<KVEC>(tile_out, a.v_sh_coeffs + (size_t)row0 * a.sh_stride_k * 3, rows, row_mask, K, a.sh_stride_k, lane,
+        sh_rows_store<KVEC>(tile_out, a.v_sh_coeffs + (size_t)row0 * a.sh_stride_k * 3, rows, K, a.sh_stride_k, lane,
                             a.accumulate != 0);
 }
 
