@@ -293,11 +293,14 @@ B2S_API int b2s_p2p_join(int64_t n, int32_t channels, const float* g_means2d, co
 #define B2S_MAX_RANKS 16
 typedef struct {
     int32_t world;                      /* stripes = ranks, 1..B2S_MAX_RANKS */
-    int32_t bounds[B2S_MAX_RANKS + 1];  /* ascending tile rows, bounds[0] = 0, bounds[world] = tile_h */
+    int32_t cams_per_rank;              /* 0: tile stripes.  > 0: CAMERA OWNERS instead (upstream's scheme): rank d owns
+                                           cameras [d*cams_per_rank, (d+1)*cams_per_rank) and their whole tile grid;
+                                           the same kernels then route every visible row to its camera's owner */
+    int32_t bounds[B2S_MAX_RANKS + 1];  /* tile stripes: ascending tile rows, bounds[0] = 0, bounds[world] = tile_h */
 } b2s_stripes;
 B2S_API int64_t b2s_stripe_ctas(int64_t M);
-B2S_API int b2s_stripe_count(int64_t M, const float* means2d, const int32_t* radii, int32_t tile_size, int32_t tile_w,
-                             int32_t tile_h, const b2s_stripes* stripes /* host */, uint16_t* dest_mask, uint32_t* cta_counts,
+B2S_API int b2s_stripe_count(int64_t M, int64_t N /* rows per camera */, const float* means2d, const int32_t* radii,
+                             int32_t tile_size, int32_t tile_w, int32_t tile_h, const b2s_stripes* stripes /* host */, uint16_t* dest_mask, uint32_t* cta_counts,
                              int64_t* totals, int64_t tag /* stored in totals[d][3], e.g. this rank's Gaussian count */,
                              b2s_stream_t stream);
 B2S_API int b2s_stripe_scan(int64_t M, int32_t world, uint32_t* cta_counts, b2s_stream_t stream);
@@ -306,8 +309,8 @@ B2S_API int b2s_p2p_put(int32_t world, const int64_t* src, int32_t words_per_pee
 B2S_API int b2s_stripe_pack(int64_t M, int64_t N, int32_t channels, int64_t gid_offset, const float* means2d,
                             const float* depths, const float* conics, const float* opacities, const float* colors,
                             const int32_t* radii, const uint16_t* dest_mask, const uint32_t* cta_prefix, int32_t world,
-                            const int64_t* host_dest_base, int64_t cap_rows, void* const* host_peer_buffers,
-                            b2s_stream_t stream);
+                            int32_t cams_per_rank, const int64_t* host_dest_base, int64_t cap_rows,
+                            void* const* host_peer_buffers, b2s_stream_t stream);
 B2S_API int b2s_stripe_unpack(int64_t n, int64_t cap_rows, int32_t channels, const float* recv_buffer, int32_t tile_size,
                               int32_t tile_w, int32_t tile_h, const b2s_tile_rows* rows, float* means2d, float* depths,
                               float* conics, float* opacities, float* colors, int32_t* radii, int64_t* camera_ids,
@@ -315,8 +318,9 @@ B2S_API int b2s_stripe_unpack(int64_t n, int64_t cap_rows, int32_t channels, con
                               b2s_stream_t stream);
 B2S_API int b2s_stripe_return(int64_t n, int32_t channels, const float* g_means2d, const float* g_depths,
                               const float* g_conics, const float* g_opacities, const float* g_colors,
-                              const int64_t* camera_ids, const int64_t* gaussian_ids, int32_t world,
-                              const int64_t* host_recv_prefix /* [world+1] */, const int64_t* host_gid_offset,
+                              const int64_t* camera_ids, const int64_t* gaussian_ids,
+                              int64_t cam_offset /* camera owners: this rank's first global camera; stripes: 0 */,
+                              int32_t world, const int64_t* host_recv_prefix /* [world+1] */, const int64_t* host_gid_offset,
                               const int64_t* host_n_src, const int64_t* host_region_base, int64_t* counters,
                               void* const* host_peer_buffers, b2s_stream_t stream);
 B2S_API int b2s_stripe_scatter_add(int32_t world, int32_t channels, const float* ret_buffer, const int64_t* host_region_base,

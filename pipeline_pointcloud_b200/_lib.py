@@ -33,7 +33,7 @@ def tile_rows(rows):
 
 class Stripes(Structure):
     """b2s_stripes: tile-row bounds of the ranks' stripes."""
-    _fields_ = [("world", c_int32), ("bounds", c_int32 * 17)]
+    _fields_ = [("world", c_int32), ("cams_per_rank", c_int32), ("bounds", c_int32 * 17)]
 
 
 class ProjectFwdArgs(Structure):
@@ -138,15 +138,15 @@ SYMBOLS = {
                      [c_int32, c_void_p, c_void_p, c_void_p, c_void_p]),
     "b2s_p2p_join": (c_int32, [c_int64, c_int32] + [c_void_p] * 5 + [c_int32, c_void_p, c_void_p, c_void_p, c_void_p]),
     "b2s_stripe_ctas": (c_int64, [c_int64]),
-    "b2s_stripe_count": (c_int32, [c_int64, c_void_p, c_void_p, c_int32, c_int32, c_int32, POINTER(Stripes), c_void_p, c_void_p,
-                                   c_void_p, c_int64, c_void_p]),
+    "b2s_stripe_count": (c_int32, [c_int64, c_int64, c_void_p, c_void_p, c_int32, c_int32, c_int32, POINTER(Stripes), c_void_p,
+                                   c_void_p, c_void_p, c_int64, c_void_p]),
     "b2s_stripe_scan": (c_int32, [c_int64, c_int32, c_void_p, c_void_p]),
     "b2s_p2p_put": (c_int32, [c_int32, c_void_p, c_int32, c_int32, c_void_p, c_void_p]),
-    "b2s_stripe_pack": (c_int32, [c_int64, c_int64, c_int32, c_int64] + [c_void_p] * 8 + [c_int32, c_void_p, c_int64, c_void_p,
-                                                                                           c_void_p]),
+    "b2s_stripe_pack": (c_int32, [c_int64, c_int64, c_int32, c_int64] + [c_void_p] * 8 + [c_int32, c_int32, c_void_p, c_int64,
+                                                                                           c_void_p, c_void_p]),
     "b2s_stripe_unpack": (c_int32, [c_int64, c_int64, c_int32, c_void_p, c_int32, c_int32, c_int32, POINTER(TileRows)] +
                           [c_void_p] * 11 + [c_void_p]),
-    "b2s_stripe_return": (c_int32, [c_int64, c_int32] + [c_void_p] * 7 + [c_int32] + [c_void_p] * 6 + [c_void_p]),
+    "b2s_stripe_return": (c_int32, [c_int64, c_int32] + [c_void_p] * 7 + [c_int64, c_int32] + [c_void_p] * 6 + [c_void_p]),
     "b2s_stripe_scatter_add": (c_int32, [c_int32, c_int32] + [c_void_p] * 9 + [c_void_p]),
     "b2s_composite_fwd": (c_int32, [POINTER(CompositeFwdArgs), c_void_p]),
     "b2s_composite_bwd": (c_int32, [POINTER(CompositeBwdArgs), c_void_p]),

@@ -33,7 +33,8 @@ constexpr int CB_ = B2S_COARSE;
 
 struct StripeTable {
     int world;
-    int bounds[B2S_MAX_RANKS + 1];
+    int cams_per_rank;                 // > 0: camera owners (rank d owns cameras [d*cpr, (d+1)*cpr), whole tile grid)
+    int bounds[B2S_MAX_RANKS + 1];     // cams_per_rank == 0: tile rows of the stripes
 };
 struct PeerPtrs {
     void* p[B2S_MAX_RANKS];
@@ -48,8 +49,9 @@ __device__ __forceinline__ int coarse_span_(int t0, int t1) { return (t1 + CB_ -
 // count
 // -------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(ST_THREADS) stripe_count_kernel(int64_t M, const float2* __restrict__ means2d,
-                                                                  const int32_t* __restrict__ radii, float tile_size, int tile_w,
-                                                                  int tile_h, const StripeTable sb, uint16_t* __restrict__ dest_mask,
+                                                                  const int32_t* __restrict__ radii, int64_t N, float tile_size,
+                                                                  int tile_w, int tile_h, const StripeTable sb,
+                                                                  uint16_t* __restrict__ dest_mask,
                                                                   uint32_t* __restrict__ cta_counts, int64_t n_ctas,
                                                                   unsigned long long* __restrict__ totals, long long tag) {
     __shared__ unsigned s_acc[B2S_MAX_RANKS * 3];
@@ -68,10 +70,11 @@ __global__ void __launch_bounds__(ST_THREADS) stripe_count_kernel(int64_t M, con
         }
     }
     unsigned mask = 0;
+    const int owner = sb.cams_per_rank > 0 ? (int)((i < M ? i : 0) / N) / sb.cams_per_rank : -1;
     for (int d = 0; d < sb.world; ++d) {
-        const int lo = sb.bounds[d], hi = sb.bounds[d + 1];
+        const int lo = sb.cams_per_rank > 0 ? 0 : sb.bounds[d], hi = sb.cams_per_rank > 0 ? tile_h : sb.bounds[d + 1];
         const int cy0 = min(max(y0, lo), hi), cy1 = min(max(y1, lo), hi);
-        const bool hit = vis && cy1 > cy0;
+        const bool hit = vis && cy1 > cy0 && (owner < 0 || owner == d);
         const unsigned b = __ballot_sync(FULL, hit);
         if (b == 0u) continue;                                      // warp-uniform
         unsigned tiles = hit ? (unsigned)((x1 - x0) * (cy1 - cy0)) : 0u;
@@ -141,7 +144,7 @@ __global__ void p2p_put_kernel(int world, const unsigned long long* __restrict__
 // -------------------------------------------------------------------------------------------------------------
 struct PackArgs {
     int64_t M, N, n_ctas, cap, gid_offset;
-    int ch, world;
+    int ch, world, cams_per_rank;
     const float2* means2d; const float* depths; const float* conics; const float* opac; const float* colors;
     const int32_t* radii; const uint16_t* dest_mask; const uint32_t* cta_prefix;
     int64_t base[B2S_MAX_RANKS];     // first row this rank owns in each destination's buffer
@@ -172,6 +175,7 @@ __global__ void __launch_bounds__(ST_THREADS) stripe_pack_kernel(const PackArgs 
         radius = a.radii[i];
         cam = (int)(i / a.N);
         gid = (int)(i - (int64_t)cam * a.N + a.gid_offset);
+        if (a.cams_per_rank > 0) cam %= a.cams_per_rank;      // camera owners: the receiver numbers its own cameras from 0
         if (a.ch <= 4)
             for (int k = 0; k < a.ch; ++k) col[k] = a.colors[i * a.ch + k];
     }
@@ -236,7 +240,7 @@ __global__ void __launch_bounds__(ST_THREADS) stripe_unpack_kernel(int64_t n, in
 // v_opacity, v_colour(ch)] = 8 + ch words, appended to the region this rank owns in the source rank's buffer.
 // -------------------------------------------------------------------------------------------------------------
 struct ReturnArgs {
-    int64_t n;
+    int64_t n, cam_offset;                    // cam_offset: first global camera of this rank (camera owners), else 0
     int ch, world;
     const float2* g_means2d; const float* g_depths; const float* g_conics; const float* g_opac; const float* g_colors;
     const int64_t* camera_ids; const int64_t* gaussian_ids;
@@ -279,7 +283,7 @@ __global__ void __launch_bounds__(ST_THREADS) stripe_return_kernel(const ReturnA
         if (nz && src == s) {
             const int64_t slot = a.region_base[s] + (int64_t)base + __popc(grp & lt);
             float* o = a.peer[s] + slot * G;
-            const int64_t row = a.camera_ids[j] * a.n_src[s] + (a.gaussian_ids[j] - a.gid_offset[s]);
+            const int64_t row = (a.camera_ids[j] + a.cam_offset) * a.n_src[s] + (a.gaussian_ids[j] - a.gid_offset[s]);
             o[0] = __int_as_float((int)row);
 #pragma unroll
             for (int k = 0; k < 7; ++k) o[1 + k] = g[k];
@@ -318,8 +322,13 @@ __global__ void __launch_bounds__(ST_THREADS) stripe_scatter_add_kernel(const Sc
 }
 
 static bool fill_stripes(StripeTable& sb, const b2s_stripes* s, int tile_h) {
-    if (!s || s->world < 1 || s->world > B2S_MAX_RANKS) return false;
+    if (!s || s->world < 1 || s->world > B2S_MAX_RANKS || s->cams_per_rank < 0) return false;
     sb.world = s->world;
+    sb.cams_per_rank = s->cams_per_rank;
+    if (s->cams_per_rank > 0) {
+        for (int d = 0; d <= B2S_MAX_RANKS; ++d) sb.bounds[d] = 0;
+        return true;
+    }
     for (int d = 0; d <= s->world; ++d) {
         sb.bounds[d] = s->bounds[d];
         if (d > 0 && sb.bounds[d] < sb.bounds[d - 1]) return false;
@@ -333,17 +342,18 @@ using namespace b2s;
 
 extern "C" int64_t b2s_stripe_ctas(int64_t M) { return cdiv(M > 0 ? M : 1, ST_THREADS); }
 
-extern "C" int b2s_stripe_count(int64_t M, const float* means2d, const int32_t* radii, int32_t tile_size, int32_t tile_w,
-                                int32_t tile_h, const b2s_stripes* stripes, uint16_t* dest_mask, uint32_t* cta_counts,
+extern "C" int b2s_stripe_count(int64_t M, int64_t N, const float* means2d, const int32_t* radii, int32_t tile_size,
+                                int32_t tile_w, int32_t tile_h, const b2s_stripes* stripes, uint16_t* dest_mask, uint32_t* cta_counts,
                                 int64_t* totals, int64_t tag, b2s_stream_t stream) {
-    B2S_REQUIRE(M >= 0 && tile_size > 0 && tile_w > 0 && tile_h > 0 && totals && cta_counts, "bad args");
+    B2S_REQUIRE(M >= 0 && N > 0 && tile_size > 0 && tile_w > 0 && tile_h > 0 && totals && cta_counts, "bad args");
     StripeTable sb;
     B2S_REQUIRE(fill_stripes(sb, stripes, tile_h), "stripes: 1..16 ranks, ascending tile rows from 0 to tile_h");
+    B2S_REQUIRE(sb.cams_per_rank == 0 || M <= N * sb.cams_per_rank * sb.world, "more cameras than cams_per_rank * world");
     cudaStream_t st = (cudaStream_t)stream;
     B2S_CUDA(cudaMemsetAsync(totals, 0, (size_t)sb.world * 4 * sizeof(int64_t), st));
     const int64_t n_ctas = b2s_stripe_ctas(M);
     B2S_REQUIRE(M == 0 || (means2d && radii && dest_mask), "null pointer");
-    stripe_count_kernel<<<(unsigned)n_ctas, ST_THREADS, 0, st>>>(M, reinterpret_cast<const float2*>(means2d), radii,
+    stripe_count_kernel<<<(unsigned)n_ctas, ST_THREADS, 0, st>>>(M, reinterpret_cast<const float2*>(means2d), radii, N,
                                                                 (float)tile_size, tile_w, tile_h, sb, dest_mask, cta_counts, n_ctas,
                                                                 reinterpret_cast<unsigned long long*>(totals), (long long)tag);
     B2S_LAUNCH_CHECK();
@@ -371,8 +381,8 @@ extern "C" int b2s_p2p_put(int32_t world, const int64_t* src, int32_t words_per_
 extern "C" int b2s_stripe_pack(int64_t M, int64_t N, int32_t channels, int64_t gid_offset, const float* means2d,
                                const float* depths, const float* conics, const float* opacities, const float* colors,
                                const int32_t* radii, const uint16_t* dest_mask, const uint32_t* cta_prefix, int32_t world,
-                               const int64_t* host_dest_base, int64_t cap_rows, void* const* host_peer_buffers,
-                               b2s_stream_t stream) {
+                               int32_t cams_per_rank, const int64_t* host_dest_base, int64_t cap_rows,
+                               void* const* host_peer_buffers, b2s_stream_t stream) {
     B2S_REQUIRE(M >= 0 && N > 0 && channels >= 0 && world >= 1 && world <= B2S_MAX_RANKS && cap_rows >= 0, "bad sizes");
     if (M == 0) return 0;
     B2S_REQUIRE(means2d && depths && conics && opacities && colors && radii && dest_mask && cta_prefix, "null pointer");
@@ -380,7 +390,7 @@ extern "C" int b2s_stripe_pack(int64_t M, int64_t N, int32_t channels, int64_t g
     B2S_REQUIRE(cap_rows % 2 == 0, "cap_rows must be even (8-byte alignment of the field blocks)");
     PackArgs a;
     a.M = M; a.N = N; a.n_ctas = b2s_stripe_ctas(M); a.cap = cap_rows; a.gid_offset = gid_offset;
-    a.ch = channels; a.world = world;
+    a.ch = channels; a.world = world; a.cams_per_rank = cams_per_rank;
     a.means2d = reinterpret_cast<const float2*>(means2d); a.depths = depths; a.conics = conics; a.opac = opacities;
     a.colors = colors; a.radii = radii; a.dest_mask = dest_mask; a.cta_prefix = cta_prefix;
     for (int d = 0; d < B2S_MAX_RANKS; ++d) {
@@ -413,7 +423,7 @@ extern "C" int b2s_stripe_unpack(int64_t n, int64_t cap_rows, int32_t channels, 
 
 extern "C" int b2s_stripe_return(int64_t n, int32_t channels, const float* g_means2d, const float* g_depths,
                                  const float* g_conics, const float* g_opacities, const float* g_colors,
-                                 const int64_t* camera_ids, const int64_t* gaussian_ids, int32_t world,
+                                 const int64_t* camera_ids, const int64_t* gaussian_ids, int64_t cam_offset, int32_t world,
                                  const int64_t* host_recv_prefix, const int64_t* host_gid_offset, const int64_t* host_n_src,
                                  const int64_t* host_region_base, int64_t* counters, void* const* host_peer_buffers,
                                  b2s_stream_t stream) {
@@ -424,7 +434,7 @@ extern "C" int b2s_stripe_return(int64_t n, int32_t channels, const float* g_mea
     B2S_REQUIRE(camera_ids && gaussian_ids && host_recv_prefix && host_gid_offset && host_n_src && host_region_base &&
                 host_peer_buffers, "null pointer");
     ReturnArgs a;
-    a.n = n; a.ch = channels; a.world = world;
+    a.n = n; a.cam_offset = cam_offset; a.ch = channels; a.world = world;
     a.g_means2d = reinterpret_cast<const float2*>(g_means2d); a.g_depths = g_depths; a.g_conics = g_conics;
     a.g_opac = g_opacities; a.g_colors = g_colors; a.camera_ids = camera_ids; a.gaussian_ids = gaussian_ids;
     a.counters = reinterpret_cast<unsigned long long*>(counters);

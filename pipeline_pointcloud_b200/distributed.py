@@ -99,17 +99,22 @@ def exchange_counts(send_counts: Sequence[int], device, group=None) -> List[int]
     return [int(g[rank]) for g in gathered]
 
 
-def all_gather_cameras(viewmats: Tensor, Ks: Tensor, n_local_gaussians: int, group=None) -> Tuple[Tensor, Tensor, List[int]]:
-    """All ranks' cameras (every rank must hold the same number) and every rank's Gaussian count."""
+def all_gather_cameras(viewmats: Tensor, Ks: Tensor, n_local_gaussians: int, group=None,
+                       with_sizes: bool = True) -> Tuple[Tensor, Tensor, Optional[List[int]]]:
+    """All ranks' cameras (every rank must hold the same number; one collective for viewmats and Ks together) and,
+    ``with_sizes``, every rank's Gaussian count (a second collective and a host sync)."""
     world = dist.get_world_size(group)
-    vs = [torch.empty_like(viewmats) for _ in range(world)]
-    ks = [torch.empty_like(Ks) for _ in range(world)]
-    dist.all_gather(vs, viewmats.contiguous(), group=group)
-    dist.all_gather(ks, Ks.contiguous(), group=group)
+    C = viewmats.shape[0]
+    mine = torch.cat([viewmats.reshape(C, 16), Ks.reshape(C, 9)], dim=1).contiguous()
+    allc = mine.new_empty(world * C, 25)
+    dist.all_gather_into_tensor(allc, mine, group=group)
+    vs, ks = allc[:, :16].reshape(world * C, 4, 4).contiguous(), allc[:, 16:].reshape(world * C, 3, 3).contiguous()
+    if not with_sizes:
+        return vs, ks, None
     n = torch.tensor([n_local_gaussians], dtype=torch.int64, device=viewmats.device)
     ns = [torch.empty_like(n) for _ in range(world)]
     dist.all_gather(ns, n, group=group)
-    return torch.cat(vs, 0), torch.cat(ks, 0), [int(t) for t in ns]
+    return vs, ks, [int(t) for t in ns]
 
 
 def route_to_camera_owners(payload: Tensor, ids: Tensor, camera_ids: Tensor, gaussian_ids: Tensor, cams_per_rank: int,
@@ -389,7 +394,7 @@ class _RouteStripes(torch.autograd.Function):
     added into its dense gradients.  Four ~7 us symmetric-memory barriers forward, two backward; no NCCL call."""
 
     @staticmethod
-    def forward(ctx, means2d, depths, conics, opac, cols, radii, group, bounds, tile_geom):
+    def forward(ctx, means2d, depths, conics, opac, cols, radii, group, bounds, tile_geom, cams_per_rank=0):
         import ctypes
         from . import _lib as L
         from . import ops
@@ -405,13 +410,13 @@ class _RouteStripes(torch.autograd.Function):
         mask = torch.empty(max(M, 1), dtype=torch.int16, device=dev)
         cta_counts = torch.empty(world * n_ctas, dtype=torch.int32, device=dev)
         totals = torch.empty(world * 4, dtype=torch.int64, device=dev)
-        sb = L.Stripes(world=world)
-        for d, b in enumerate(bounds):
+        sb = L.Stripes(world=world, cams_per_rank=int(cams_per_rank))     # cams_per_rank > 0: camera owners, else stripes
+        for d, b in enumerate(bounds if not cams_per_rank else []):
             sb.bounds[d] = int(b)
         W4 = world * 4
         tab, h_tab = _SymmBuffers.get(group, "s_tab", world * W4 + world, dev, dtype=torch.int64)
         with ops._stage("stripe_count", launches=3):
-            L.check(lib.b2s_stripe_count(M, L.ptr(means2d), L.ptr(radii), tile_size, tw, th, ctypes.byref(sb), L.ptr(mask),
+            L.check(lib.b2s_stripe_count(M, N, L.ptr(means2d), L.ptr(radii), tile_size, tw, th, ctypes.byref(sb), L.ptr(mask),
                                          L.ptr(cta_counts), L.ptr(totals), N, st), "b2s_stripe_count")
             L.check(lib.b2s_stripe_scan(M, world, L.ptr(cta_counts), st), "b2s_stripe_scan")
             h_tab.barrier()            # every rank has finished with last iteration's table and exchange buffers
@@ -435,7 +440,7 @@ class _RouteStripes(torch.autograd.Function):
         with ops._stage("stripe_pack"):
             L.check(lib.b2s_stripe_pack(M, N, ch, int(sum(n_world[:rank])), L.ptr(means2d), L.ptr(depths), L.ptr(conics),
                                         L.ptr(opac), L.ptr(cols), L.ptr(radii), L.ptr(mask), L.ptr(cta_counts), world,
-                                        _i64(dest_base), cap, _ptrs(h_f.buffer_ptrs), st), "b2s_stripe_pack")
+                                        int(cams_per_rank), _i64(dest_base), cap, _ptrs(h_f.buffer_ptrs), st), "b2s_stripe_pack")
             h_f.barrier()              # every peer's stores have landed
         o = dict(device=dev)
         means2d_m, depths_m, conics_m = torch.empty(n_recv, 2, **o), torch.empty(n_recv, **o), torch.empty(n_recv, 3, **o)
@@ -443,7 +448,7 @@ class _RouteStripes(torch.autograd.Function):
         radii_m, tiles_m = torch.empty(n_recv, dtype=torch.int32, **o), torch.empty(n_recv, dtype=torch.int32, **o)
         dkeys, rowids = torch.empty(max(n_recv, 1), dtype=torch.int32, **o), torch.empty(max(n_recv, 1), dtype=torch.int32, **o)
         cam_m, gid_m = torch.empty(n_recv, dtype=torch.int64, **o), torch.empty(n_recv, dtype=torch.int64, **o)
-        rows = L.TileRows(int(bounds[rank]), int(bounds[rank + 1]))
+        rows = L.TileRows(0, th) if cams_per_rank else L.TileRows(int(bounds[rank]), int(bounds[rank + 1]))
         with ops._stage("stripe_unpack"):
             L.check(lib.b2s_stripe_unpack(n_recv, cap, ch, L.ptr(buf_f), tile_size, tw, th, ctypes.byref(rows), L.ptr(means2d_m),
                                           L.ptr(depths_m), L.ptr(conics_m), L.ptr(opac_m), L.ptr(cols_m), L.ptr(radii_m),
@@ -451,7 +456,7 @@ class _RouteStripes(torch.autograd.Function):
                     "b2s_stripe_unpack")
         ctx.save_for_backward(cam_m, gid_m)
         ctx.cfg = (send_counts, recv_counts, [table[s][:] for s in range(world)], list(n_world), group, ch,
-                   (means2d.shape, depths.shape, conics.shape, opac.shape, cols.shape))
+                   (means2d.shape, depths.shape, conics.shape, opac.shape, cols.shape), rank * int(cams_per_rank))
         ctx.set_materialize_grads(False)
         ctx.mark_non_differentiable(radii_m, tiles_m, dkeys, rowids, cam_m, gid_m)
         ctx.counts = (n_isects, n_records)
@@ -463,7 +468,7 @@ class _RouteStripes(torch.autograd.Function):
         from . import _lib as L
         from . import ops
         cam_m, gid_m = ctx.saved_tensors
-        send_counts, recv_counts, table, n_world, group, ch, shapes = ctx.cfg
+        send_counts, recv_counts, table, n_world, group, ch, shapes, cam_offset = ctx.cfg
         dev = cam_m.device
         rank, world = dist.get_rank(group), dist.get_world_size(group)
         n_recv, G, W4 = int(sum(recv_counts)), 8 + ch, world * 4
@@ -479,7 +484,7 @@ class _RouteStripes(torch.autograd.Function):
         region_base = [sum(table[s][d][0] for d in range(rank)) for s in range(world)]     # my region inside s's buffer
         with ops._stage("stripe_return", launches=2):
             h_r.barrier()              # every source has consumed what the previous backward left in its buffer
-            L.check(lib.b2s_stripe_return(n_recv, ch, *[L.ptr(g) for g in gs], L.ptr(cam_m), L.ptr(gid_m), world,
+            L.check(lib.b2s_stripe_return(n_recv, ch, *[L.ptr(g) for g in gs], L.ptr(cam_m), L.ptr(gid_m), cam_offset, world,
                                           _i64(recv_prefix), _i64(gid_offset), _i64(n_world), _i64(region_base), L.ptr(counters),
                                           _ptrs(h_r.buffer_ptrs), st), "b2s_stripe_return")
             L.check(lib.b2s_p2p_put(world, L.ptr(counters), 1, 1,
@@ -498,7 +503,7 @@ class _RouteStripes(torch.autograd.Function):
         with ops._stage("stripe_scatter"):
             L.check(lib.b2s_stripe_scatter_add(world, ch, L.ptr(buf_r), _i64(my_base[:-1]), _i64(send_counts),
                                                tab[world * W4:].data_ptr(), *[L.ptr(t) for t in outs], st), "b2s_stripe_scatter_add")
-        return tuple(outs) + (None,) * 4
+        return tuple(outs) + (None,) * 5
 
 
 def _route_impl():
@@ -557,7 +562,9 @@ def rasterization_distributed(means, quats, scales, opacities, colors, viewmats,
             raise ValueError(f"stripe_rows must be {world + 1} ascending tile rows from 0 to {th}")
         rows = (bounds[rank], bounds[rank + 1])
     else:
-        viewmats_all, Ks_all, n_world = all_gather_cameras(viewmats, Ks, N, group)
+        # (the fused route carries the shard sizes in its count table)
+        viewmats_all, Ks_all, n_world = all_gather_cameras(viewmats.detach(), Ks.detach(), N, group,
+                                                           with_sizes=not (_route_impl() == "p2p" and world <= 16))
         C_all = viewmats_all.shape[0]
         if C_all != C_local * world:
             raise ValueError("every rank must hold the same number of cameras")
@@ -582,11 +589,12 @@ def rasterization_distributed(means, quats, scales, opacities, colors, viewmats,
     ch = cols.shape[-1]
 
     # ---- route the visible pairs to their owners: (fused) pack -> exchange -> split -------------------------------
-    fused_stripes = tile_stripes and _route_impl() == "p2p" and world <= 16
+    fused_route = _route_impl() == "p2p" and world <= 16
     dkeys = rowids = counts = None
-    if fused_stripes:
+    if fused_route:
         (means2d_m, depths_m, conics_m, opac_m, cols_m, radii_m, tiles_m, dkeys, rowids, cam_local,
-         gauss_global) = _RouteStripes.apply(means2d, depths, conics, opac, cols, radii, group, bounds, (tile_size, tw, th))
+         gauss_global) = _RouteStripes.apply(means2d, depths, conics, opac, cols, radii, group, bounds if tile_stripes else None,
+                                             (tile_size, tw, th), 0 if tile_stripes else C_local)
         counts = _RouteStripes.last_counts
     else:
         with torch.no_grad():
