@@ -213,6 +213,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=None)
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (profiling runs only)")
+    ap.add_argument("--no-balance", action="store_true", help="stripes: keep the even split of the tile rows")
     ap.add_argument("--multi-gpu", default="sharded", choices=["sharded", "allreduce", "stripes"],
                     help="N>1: 'sharded' = Gaussians sharded over ranks + all-to-all of projected splats to the camera "
                          "owners (rasterization(distributed=True), what the reference's multi-GPU branch runs); "
@@ -276,22 +277,34 @@ def main():
     params = {k: v.to(dev).requires_grad_() for k, v in leaves_host.items()}
     cams = {k: v.to(dev) for k, v in cam_host.items()}
     g = torch.Generator().manual_seed(1 + (0 if stripes else rank))
-    v_r_host = torch.rand(1, H, W, 3, generator=g)
-    v_a_host = torch.rand(1, H, W, 1, generator=g)
-    if stripes:             # every rank differentiates its own pixel rows of the same image cotangent
-        from pipeline_pointcloud_b200.distributed import stripe_bounds
-        sb = stripe_bounds(math.ceil(H / 16), world)
-        y0, y1 = min(H, sb[rank] * 16), min(H, sb[rank + 1] * 16)
-        v_r_host, v_a_host = v_r_host[:, y0:y1].contiguous(), v_a_host[:, y0:y1].contiguous()
-    v_r_host, v_a_host = v_r_host.pin_memory(), v_a_host.pin_memory()
-    v_r, v_a = v_r_host.to(dev), v_a_host.to(dev)
+    v_r_full = torch.rand(1, H, W, 3, generator=g)
+    v_a_full = torch.rand(1, H, W, 1, generator=g)
     kw = dict(sh_degree=deg, packed=args.packed or sharded, rasterize_mode=mode, distributed=sharded)
+    cot = {}
+
+    def set_cotangents(bounds=None):
+        """Every rank differentiates its own pixel rows (its stripe) of the same image cotangent."""
+        vr, va = v_r_full, v_a_full
+        if bounds is not None:
+            y0, y1 = min(H, bounds[rank] * 16), min(H, bounds[rank + 1] * 16)
+            vr, va = vr[:, y0:y1].contiguous(), va[:, y0:y1].contiguous()
+            kw["stripe_rows"] = list(bounds)
+        cot["v_r_host"], cot["v_a_host"] = vr.pin_memory(), va.pin_memory()
+        cot["v_r"], cot["v_a"] = cot["v_r_host"].to(dev), cot["v_a_host"].to(dev)
+
+    stripe_rows = None
     if stripes:
+        from pipeline_pointcloud_b200.distributed import rebalance_stripe_bounds, stripe_bounds
         kw["tile_stripes"] = True
+        stripe_rows = stripe_bounds(math.ceil(H / 16), world)
+    set_cotangents(stripe_rows)
+    v_r_host, v_a_host, v_r, v_a = cot["v_r_host"], cot["v_a_host"], cot["v_r"], cot["v_a"]
     plist = list(params.values())
     stats = {}
 
-    def step(p=params, c=cams, vr=v_r, va=v_a):
+    def step(p=params, c=cams, vr=None, va=None):
+        vr = cot["v_r"] if vr is None else vr
+        va = cot["v_a"] if va is None else va
         for t in p.values():
             t.grad = None
         r, a, m = b2s.rasterization(p["means"], p["quats"], p["scales"], p["opacities"], p["colors"], c["viewmats"],
@@ -319,6 +332,24 @@ def main():
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item())
 
+    balance_log = []
+    if stripes and not args.no_balance:
+        # feedback load balancing of the stripes (untimed, part of the warm-up): every rank measures its stripe-dependent
+        # stages, the bounds are cut again at equal-cost quantiles; three rounds
+        STRIPE_STAGES = ("stripe_unpack", "depth_order", "coarse_bin", "composite_fwd", "composite_bwd", "stripe_return")
+        step(); step()
+        for _ in range(3):
+            ops.TIMER = ops.StageTimer()
+            step(); step()
+            tm, ops.TIMER = ops.TIMER, None
+            mine = sum(v["ms_avg"] for k, v in tm.summary().items() if k in STRIPE_STAGES)
+            allt = torch.zeros(world, device=dev)
+            dist.all_gather_into_tensor(allt, torch.tensor([mine], device=dev))
+            costs = allt.tolist()
+            balance_log.append({"bounds": list(stripe_rows), "ms": [round(c, 3) for c in costs]})
+            stripe_rows = rebalance_stripe_bounds(stripe_rows, costs)
+            set_cotangents(stripe_rows)
+        v_r_host, v_a_host, v_r, v_a = cot["v_r_host"], cot["v_a_host"], cot["v_r"], cot["v_a"]
     for _ in range(max(args.warmup, 3)):
         r, a, m = step()
     torch.cuda.synchronize()
@@ -464,7 +495,7 @@ def main():
                                 (", replicated Gaussians, dense-gradient all-reduce" if world > 1 else "")),
                    "n_isects": I, "n_visible": n_visible, "n_reached": stats["n_reached"], "n_coarse_records": R,
                    "l2": "inputs (1.4 GB parameters + 0.3 GB keys) exceed the 126 MB L2",
-                   "parallelism": f"dp{world}"},
+                   "parallelism": f"dp{world}", "stripe_rows": stripe_rows, "stripe_balance_rounds": balance_log},
         "iters_per_s": 1e3 / ms_per_step * C_total,
         "gpu_launches": timer.launches,
         "gpu_launches_note": "kernels of libb2s.so launched inside the timed region (per step: project_fwd 1, depth sort 6, "

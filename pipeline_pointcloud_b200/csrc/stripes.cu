@@ -151,8 +151,19 @@ struct PackArgs {
     float* peer[B2S_MAX_RANKS];
 };
 
+// Rows of a CTA are first grouped by destination in shared memory (slot order kept), then every destination's group
+// leaves as contiguous runs per field: a CTA's ~256/W rows for one peer become 128 B+ NVLink stores instead of the
+// 4 B-per-lane scatter a direct store would produce (Gaussians of a warp land in unrelated stripes).
+constexpr int PACK_STAGE = ST_THREADS + ST_THREADS / 2;    // staged records per CTA (straddlers are staged once per stripe)
+constexpr int PACK_MAXCH = 4;                              // wider colour vectors take the direct path
+
 __global__ void __launch_bounds__(ST_THREADS) stripe_pack_kernel(const PackArgs a) {
     __shared__ unsigned s_wtot[B2S_MAX_RANKS][ST_WARPS];
+    __shared__ int s_seg[B2S_MAX_RANKS + 1];               // first staged slot of each destination's group
+    __shared__ float2 s_xy[PACK_STAGE];
+    __shared__ float s_f[5][PACK_STAGE];                   // depth, conic a b c, opacity
+    __shared__ float s_col[PACK_STAGE * PACK_MAXCH];
+    __shared__ int s_i[3][PACK_STAGE];                     // radius, camera, global id
     const int64_t i = (int64_t)blockIdx.x * ST_THREADS + threadIdx.x;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const unsigned mask = i < a.M ? (unsigned)a.dest_mask[i] : 0u;
@@ -162,11 +173,22 @@ __global__ void __launch_bounds__(ST_THREADS) stripe_pack_kernel(const PackArgs 
         if (lane == 0) s_wtot[d][warp] = __popc(b);
     }
     __syncthreads();
+    if (threadIdx.x == 0) {
+        int run = 0;
+        for (int d = 0; d < a.world; ++d) {
+            s_seg[d] = run;
+            for (int w = 0; w < ST_WARPS; ++w) run += (int)s_wtot[d][w];
+        }
+        s_seg[a.world] = run;
+    }
+    __syncthreads();
+    const int staged = s_seg[a.world];
+    const bool stage = staged <= PACK_STAGE && a.ch <= PACK_MAXCH;   // CTA-uniform
     // the row's record, loaded once (a straddling splat is stored several times)
     float2 m = make_float2(0.f, 0.f);
     float depth = 0.f, ca = 0.f, cb = 0.f, cc = 0.f, op = 0.f;
     int radius = 0, cam = 0, gid = 0;
-    float col[4] = {0.f, 0.f, 0.f, 0.f};
+    float col[PACK_MAXCH] = {0.f, 0.f, 0.f, 0.f};
     if (mask) {
         m = a.means2d[i];
         depth = a.depths[i];
@@ -176,7 +198,7 @@ __global__ void __launch_bounds__(ST_THREADS) stripe_pack_kernel(const PackArgs 
         cam = (int)(i / a.N);
         gid = (int)(i - (int64_t)cam * a.N + a.gid_offset);
         if (a.cams_per_rank > 0) cam %= a.cams_per_rank;      // camera owners: the receiver numbers its own cameras from 0
-        if (a.ch <= 4)
+        if (a.ch <= PACK_MAXCH)
             for (int k = 0; k < a.ch; ++k) col[k] = a.colors[i * a.ch + k];
     }
     const int64_t cap = a.cap;
@@ -186,22 +208,50 @@ __global__ void __launch_bounds__(ST_THREADS) stripe_pack_kernel(const PackArgs 
         if (!mine) continue;
         unsigned before = 0;
         for (int w = 0; w < warp; ++w) before += s_wtot[d][w];
-        const int64_t s = a.base[d] + a.cta_prefix[(int64_t)d * a.n_ctas + blockIdx.x] + before + __popc(b & lt);
-        float* o = a.peer[d];
-        reinterpret_cast<float2*>(o)[s] = m;
-        o[2 * cap + s] = depth;
-        o[3 * cap + 3 * s] = ca; o[3 * cap + 3 * s + 1] = cb; o[3 * cap + 3 * s + 2] = cc;
-        o[6 * cap + s] = op;
-        float* oc = o + 7 * cap + s * a.ch;
-        if (a.ch <= 4) {
-            for (int k = 0; k < a.ch; ++k) oc[k] = col[k];
+        const int local = (int)before + __popc(b & lt);              // rank among this CTA's rows for d
+        if (stage) {
+            const int r = s_seg[d] + local;
+            s_xy[r] = m;
+            s_f[0][r] = depth; s_f[1][r] = ca; s_f[2][r] = cb; s_f[3][r] = cc; s_f[4][r] = op;
+            for (int k = 0; k < a.ch; ++k) s_col[r * a.ch + k] = col[k];
+            s_i[0][r] = radius; s_i[1][r] = cam; s_i[2][r] = gid;
         } else {
-            for (int k = 0; k < a.ch; ++k) oc[k] = a.colors[i * a.ch + k];
+            const int64_t s = a.base[d] + a.cta_prefix[(int64_t)d * a.n_ctas + blockIdx.x] + local;
+            float* o = a.peer[d];
+            reinterpret_cast<float2*>(o)[s] = m;
+            o[2 * cap + s] = depth;
+            o[3 * cap + 3 * s] = ca; o[3 * cap + 3 * s + 1] = cb; o[3 * cap + 3 * s + 2] = cc;
+            o[6 * cap + s] = op;
+            float* oc = o + 7 * cap + s * a.ch;
+            for (int k = 0; k < a.ch; ++k) oc[k] = a.ch <= PACK_MAXCH ? col[k] : a.colors[i * a.ch + k];
+            int32_t* oi = reinterpret_cast<int32_t*>(o + (7 + (int64_t)a.ch) * cap);
+            oi[s] = radius;
+            oi[cap + s] = cam;
+            oi[2 * cap + s] = gid;
         }
+    }
+    if (!stage) return;
+    __syncthreads();
+    // group by group, field by field: consecutive threads write consecutive slots of one peer
+    for (int d = 0; d < a.world; ++d) {
+        const int g0 = s_seg[d], cnt = s_seg[d + 1] - g0;
+        if (cnt == 0) continue;
+        const int64_t s0 = a.base[d] + a.cta_prefix[(int64_t)d * a.n_ctas + blockIdx.x];
+        float* o = a.peer[d];
         int32_t* oi = reinterpret_cast<int32_t*>(o + (7 + (int64_t)a.ch) * cap);
-        oi[s] = radius;
-        oi[cap + s] = cam;
-        oi[2 * cap + s] = gid;
+        for (int t = threadIdx.x; t < cnt; t += ST_THREADS) {
+            reinterpret_cast<float2*>(o)[s0 + t] = s_xy[g0 + t];
+            o[2 * cap + s0 + t] = s_f[0][g0 + t];
+            o[6 * cap + s0 + t] = s_f[4][g0 + t];
+            oi[s0 + t] = s_i[0][g0 + t];
+            oi[cap + s0 + t] = s_i[1][g0 + t];
+            oi[2 * cap + s0 + t] = s_i[2][g0 + t];
+        }
+        for (int t = threadIdx.x; t < 3 * cnt; t += ST_THREADS) {       // conics: 3 words per row, contiguous in the buffer
+            const int r = t / 3, e = t - 3 * r;
+            o[3 * cap + 3 * s0 + t] = s_f[1 + e][g0 + r];
+        }
+        for (int t = threadIdx.x; t < a.ch * cnt; t += ST_THREADS) o[7 * cap + s0 * a.ch + t] = s_col[g0 * a.ch + t];
     }
 }
 

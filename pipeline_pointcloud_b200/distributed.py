@@ -168,6 +168,38 @@ def balanced_stripe_bounds(tiles_per_row: Tensor, world: int) -> List[int]:
     return bounds
 
 
+def rebalance_stripe_bounds(bounds: Sequence[int], cost_per_rank: Sequence[float], min_rows: int = 1) -> List[int]:
+    """Feedback load balancing of the tile stripes: given the stripe-dependent time (or any cost) every rank measured
+    with the current ``bounds``, returns bounds that would equalise it if the cost were spread evenly over the tile
+    rows of each current stripe (piecewise-linear cumulative cost, cut at equal quantiles).  Deterministic, so every
+    rank computes the same answer from the all-gathered costs; a few rounds converge."""
+    W = len(bounds) - 1
+    th = int(bounds[-1])
+    cost = [max(float(c), 0.0) for c in cost_per_rank]
+    total = sum(cost)
+    if W <= 1 or total <= 0.0 or th < W * min_rows:
+        return [int(b) for b in bounds]
+    cum = [0.0]
+    for c in cost:
+        cum.append(cum[-1] + c)
+    new = [0]
+    r = 0
+    for k in range(1, W):
+        target = total * k / W
+        while r < W - 1 and cum[r + 1] < target:
+            r += 1
+        span = cum[r + 1] - cum[r]
+        frac = (target - cum[r]) / span if span > 0 else 0.0
+        row = bounds[r] + frac * (bounds[r + 1] - bounds[r])
+        new.append(int(round(row)))
+    new.append(th)
+    for k in range(1, W):                                   # at least min_rows per stripe, ascending
+        new[k] = max(new[k], new[k - 1] + min_rows)
+    for k in range(W - 1, 0, -1):
+        new[k] = min(new[k], new[k + 1] - min_rows)
+    return new
+
+
 def stripe_selection(means2d: Tensor, radii: Tensor, tile_size: int, tile_height: int,
                      bounds: Sequence[int]) -> Tuple[Tensor, Tensor]:
     """Tile-stripe routing: rows of dense ``means2d`` [C,N,2] / ``radii`` [C,N] whose tile rectangle
@@ -415,10 +447,11 @@ class _RouteStripes(torch.autograd.Function):
             sb.bounds[d] = int(b)
         W4 = world * 4
         tab, h_tab = _SymmBuffers.get(group, "s_tab", world * W4 + world, dev, dtype=torch.int64)
-        with ops._stage("stripe_count", launches=3):
+        with ops._stage("stripe_count", launches=2):
             L.check(lib.b2s_stripe_count(M, N, L.ptr(means2d), L.ptr(radii), tile_size, tw, th, ctypes.byref(sb), L.ptr(mask),
                                          L.ptr(cta_counts), L.ptr(totals), N, st), "b2s_stripe_count")
             L.check(lib.b2s_stripe_scan(M, world, L.ptr(cta_counts), st), "b2s_stripe_scan")
+        with ops._stage("stripe_table", launches=1):     # (barrier time = waiting for the slowest rank to get here)
             h_tab.barrier()            # every rank has finished with last iteration's table and exchange buffers
             L.check(lib.b2s_p2p_put(world, L.ptr(totals), W4, 0, _ptrs([p + rank * W4 * 8 for p in h_tab.buffer_ptrs]), st),
                     "b2s_p2p_put")
@@ -441,6 +474,7 @@ class _RouteStripes(torch.autograd.Function):
             L.check(lib.b2s_stripe_pack(M, N, ch, int(sum(n_world[:rank])), L.ptr(means2d), L.ptr(depths), L.ptr(conics),
                                         L.ptr(opac), L.ptr(cols), L.ptr(radii), L.ptr(mask), L.ptr(cta_counts), world,
                                         int(cams_per_rank), _i64(dest_base), cap, _ptrs(h_f.buffer_ptrs), st), "b2s_stripe_pack")
+        with ops._stage("stripe_pack_barrier", launches=0):
             h_f.barrier()              # every peer's stores have landed
         o = dict(device=dev)
         means2d_m, depths_m, conics_m = torch.empty(n_recv, 2, **o), torch.empty(n_recv, **o), torch.empty(n_recv, 3, **o)
@@ -482,13 +516,15 @@ class _RouteStripes(torch.autograd.Function):
             recv_prefix.append(recv_prefix[-1] + int(c))
         gid_offset = [int(sum(n_world[:s])) for s in range(world)]
         region_base = [sum(table[s][d][0] for d in range(rank)) for s in range(world)]     # my region inside s's buffer
-        with ops._stage("stripe_return", launches=2):
+        with ops._stage("stripe_return_barrier0", launches=0):
             h_r.barrier()              # every source has consumed what the previous backward left in its buffer
+        with ops._stage("stripe_return", launches=2):
             L.check(lib.b2s_stripe_return(n_recv, ch, *[L.ptr(g) for g in gs], L.ptr(cam_m), L.ptr(gid_m), cam_offset, world,
                                           _i64(recv_prefix), _i64(gid_offset), _i64(n_world), _i64(region_base), L.ptr(counters),
                                           _ptrs(h_r.buffer_ptrs), st), "b2s_stripe_return")
             L.check(lib.b2s_p2p_put(world, L.ptr(counters), 1, 1,
                                     _ptrs([p + (world * W4 + rank) * 8 for p in h_tab.buffer_ptrs]), st), "b2s_p2p_put")
+        with ops._stage("stripe_return_barrier1", launches=0):
             h_r.barrier()
         # one zero-filled slab for the dense gradients of the projected rows
         sizes = [int(torch.Size(s).numel()) for s in shapes]

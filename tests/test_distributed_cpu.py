@@ -120,6 +120,12 @@ def test_stripe_selection_matches_oracle_tile_rects():
     assert D.balanced_stripe_bounds(torch.tensor([1, 1, 1, 1, 10, 10, 1, 1]), 2) == [0, 5, 8]
     b = D.balanced_stripe_bounds(torch.zeros(9), 3)
     assert b == D.stripe_bounds(9, 3)
+    # feedback balancing: cost concentrated in the middle stripe -> the middle stripe shrinks, the cut points stay ordered
+    nb = D.rebalance_stripe_bounds([0, 40, 80, 120], [1.0, 4.0, 1.0])
+    assert nb[0] == 0 and nb[-1] == 120 and nb == sorted(nb) and nb[2] - nb[1] < 40 and nb[1] > 40 and nb[2] < 80
+    assert D.rebalance_stripe_bounds([0, 40, 80, 120], [1.0, 1.0, 1.0]) == [0, 40, 80, 120]
+    assert D.rebalance_stripe_bounds([0, 1, 2, 3], [5.0, 0.0, 0.0]) == [0, 1, 2, 3]          # nothing left to move
+    assert D.rebalance_stripe_bounds([0, 10], [3.0]) == [0, 10]
 
 
 def _stripe_worker(rank, port):
