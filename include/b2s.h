@@ -274,15 +274,17 @@ B2S_API int b2s_p2p_join(int64_t n, int32_t channels, const float* g_means2d, co
  * The exchange is fused into the producing kernels over NVLink peer mappings of symmetric memory; the caller
  * provides the barriers.  No counterpart in the reference (its multi-GPU branch routes to camera owners, above).
  *
- *   b2s_stripe_count : dest_mask [M] (bit d: the row's tile rectangle touches stripe d), per-CTA row counts per
- *                      destination cta_counts [world][b2s_stripe_ctas(M)], totals [world][4] int64 =
- *                      (rows, tile intersections, coarse-bin records, tag) per destination (zeroed by the call)
- *   b2s_stripe_scan  : cta_counts -> exclusive prefix along the CTAs, per destination (in place)
+ *   b2s_stripe_count : dest_mask [M] (bit d: the row's tile rectangle touches stripe d) and per-CTA partial sums per
+ *                      destination, cta_counts [3][world][b2s_stripe_ctas(M)] = rows, tile intersections, coarse-bin
+ *                      records; totals [world][4] int64: slot 3 = tag (the other slots are written by the scan)
+ *   b2s_stripe_scan  : cta_counts[0] -> exclusive prefix along the CTAs, per destination (in place);
+ *                      totals [world][4] = (rows, tile intersections, coarse-bin records, tag) per destination
  *   b2s_p2p_put      : words_per_peer 64-bit words from src + d*src_stride to host_peer_dst[d] (NULL: skipped)
  *   b2s_stripe_pack  : stores every row's record into each destination's receive buffer at
  *                      host_dest_base[d] + its rank among this rank's rows for d (ascending row order).
- *                      Receive buffer (capacity cap_rows, 32-bit words, SoA): [means2d 2cap][depths cap][conics 3cap]
- *                      [opacities cap][colours ch*cap][radii cap][camera cap][global Gaussian id cap]
+ *                      Receive buffer: one record of 10+ch 32-bit words per row = [x, y, depth, conic(3), opacity,
+ *                      colour(ch), radius, camera, global Gaussian id]; a CTA's rows for one peer leave as one
+ *                      contiguous, coalesced run
  *   b2s_stripe_unpack: receiver, rows [0,n) of its buffer -> tensors (+ int64 camera_ids / gaussian_ids), and the
  *                      inputs of binning: tiles_per_gauss inside the window `rows`, depth_keys, row_ids
  *   b2s_stripe_return: backward; rows with a non-zero gradient are appended as [source row, v_xy, v_depth, v_conic,
@@ -303,15 +305,15 @@ B2S_API int b2s_stripe_count(int64_t M, int64_t N /* rows per camera */, const f
                              int32_t tile_size, int32_t tile_w, int32_t tile_h, const b2s_stripes* stripes /* host */, uint16_t* dest_mask, uint32_t* cta_counts,
                              int64_t* totals, int64_t tag /* stored in totals[d][3], e.g. this rank's Gaussian count */,
                              b2s_stream_t stream);
-B2S_API int b2s_stripe_scan(int64_t M, int32_t world, uint32_t* cta_counts, b2s_stream_t stream);
+B2S_API int b2s_stripe_scan(int64_t M, int32_t world, uint32_t* cta_counts, int64_t* totals, b2s_stream_t stream);
 B2S_API int b2s_p2p_put(int32_t world, const int64_t* src, int32_t words_per_peer, int32_t src_stride,
                         void* const* host_peer_dst, b2s_stream_t stream);
 B2S_API int b2s_stripe_pack(int64_t M, int64_t N, int32_t channels, int64_t gid_offset, const float* means2d,
                             const float* depths, const float* conics, const float* opacities, const float* colors,
                             const int32_t* radii, const uint16_t* dest_mask, const uint32_t* cta_prefix, int32_t world,
-                            int32_t cams_per_rank, const int64_t* host_dest_base, int64_t cap_rows,
-                            void* const* host_peer_buffers, b2s_stream_t stream);
-B2S_API int b2s_stripe_unpack(int64_t n, int64_t cap_rows, int32_t channels, const float* recv_buffer, int32_t tile_size,
+                            int32_t cams_per_rank, const int64_t* host_dest_base, void* const* host_peer_buffers,
+                            b2s_stream_t stream);
+B2S_API int b2s_stripe_unpack(int64_t n, int32_t channels, const float* recv_buffer, int32_t tile_size,
                               int32_t tile_w, int32_t tile_h, const b2s_tile_rows* rows, float* means2d, float* depths,
                               float* conics, float* opacities, float* colors, int32_t* radii, int64_t* camera_ids,
                               int64_t* gaussian_ids, int32_t* tiles_per_gauss, uint32_t* depth_keys, int32_t* row_ids,

@@ -140,11 +140,11 @@ SYMBOLS = {
     "b2s_stripe_ctas": (c_int64, [c_int64]),
     "b2s_stripe_count": (c_int32, [c_int64, c_int64, c_void_p, c_void_p, c_int32, c_int32, c_int32, POINTER(Stripes), c_void_p,
                                    c_void_p, c_void_p, c_int64, c_void_p]),
-    "b2s_stripe_scan": (c_int32, [c_int64, c_int32, c_void_p, c_void_p]),
+    "b2s_stripe_scan": (c_int32, [c_int64, c_int32, c_void_p, c_void_p, c_void_p]),
     "b2s_p2p_put": (c_int32, [c_int32, c_void_p, c_int32, c_int32, c_void_p, c_void_p]),
-    "b2s_stripe_pack": (c_int32, [c_int64, c_int64, c_int32, c_int64] + [c_void_p] * 8 + [c_int32, c_int32, c_void_p, c_int64,
-                                                                                           c_void_p, c_void_p]),
-    "b2s_stripe_unpack": (c_int32, [c_int64, c_int64, c_int32, c_void_p, c_int32, c_int32, c_int32, POINTER(TileRows)] +
+    "b2s_stripe_pack": (c_int32, [c_int64, c_int64, c_int32, c_int64] + [c_void_p] * 8 + [c_int32, c_int32, c_void_p, c_void_p,
+                                                                                           c_void_p]),
+    "b2s_stripe_unpack": (c_int32, [c_int64, c_int32, c_void_p, c_int32, c_int32, c_int32, POINTER(TileRows)] +
                           [c_void_p] * 11 + [c_void_p]),
     "b2s_stripe_return": (c_int32, [c_int64, c_int32] + [c_void_p] * 7 + [c_int64, c_int32] + [c_void_p] * 6 + [c_void_p]),
     "b2s_stripe_scatter_add": (c_int32, [c_int32, c_int32] + [c_void_p] * 9 + [c_void_p]),

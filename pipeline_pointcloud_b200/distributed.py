@@ -440,7 +440,7 @@ class _RouteStripes(torch.autograd.Function):
         lib, st = L.lib(), L.stream_ptr(dev)
         n_ctas = int(lib.b2s_stripe_ctas(M))
         mask = torch.empty(max(M, 1), dtype=torch.int16, device=dev)
-        cta_counts = torch.empty(world * n_ctas, dtype=torch.int32, device=dev)
+        cta_counts = torch.empty(3 * world * n_ctas, dtype=torch.int32, device=dev)   # rows | tile isects | coarse records
         totals = torch.empty(world * 4, dtype=torch.int64, device=dev)
         sb = L.Stripes(world=world, cams_per_rank=int(cams_per_rank))     # cams_per_rank > 0: camera owners, else stripes
         for d, b in enumerate(bounds if not cams_per_rank else []):
@@ -450,7 +450,7 @@ class _RouteStripes(torch.autograd.Function):
         with ops._stage("stripe_count", launches=2):
             L.check(lib.b2s_stripe_count(M, N, L.ptr(means2d), L.ptr(radii), tile_size, tw, th, ctypes.byref(sb), L.ptr(mask),
                                          L.ptr(cta_counts), L.ptr(totals), N, st), "b2s_stripe_count")
-            L.check(lib.b2s_stripe_scan(M, world, L.ptr(cta_counts), st), "b2s_stripe_scan")
+            L.check(lib.b2s_stripe_scan(M, world, L.ptr(cta_counts), L.ptr(totals), st), "b2s_stripe_scan")
         with ops._stage("stripe_table", launches=1):     # (barrier time = waiting for the slowest rank to get here)
             h_tab.barrier()            # every rank has finished with last iteration's table and exchange buffers
             L.check(lib.b2s_p2p_put(world, L.ptr(totals), W4, 0, _ptrs([p + rank * W4 * 8 for p in h_tab.buffer_ptrs]), st),
@@ -468,12 +468,11 @@ class _RouteStripes(torch.autograd.Function):
         need_ret = max(sum(table[s][d][0] for d in range(world)) for s in range(world))
         buf_f, h_f = _SymmBuffers.get(group, "s_fwd", (need_rows + 2) * F, dev)
         buf_r, h_r = _SymmBuffers.get(group, "s_ret", need_ret * G, dev)
-        cap = (buf_f.numel() // F) & ~1
         dest_base = [sum(table[s][d][0] for s in range(rank)) for d in range(world)]
         with ops._stage("stripe_pack"):
             L.check(lib.b2s_stripe_pack(M, N, ch, int(sum(n_world[:rank])), L.ptr(means2d), L.ptr(depths), L.ptr(conics),
                                         L.ptr(opac), L.ptr(cols), L.ptr(radii), L.ptr(mask), L.ptr(cta_counts), world,
-                                        int(cams_per_rank), _i64(dest_base), cap, _ptrs(h_f.buffer_ptrs), st), "b2s_stripe_pack")
+                                        int(cams_per_rank), _i64(dest_base), _ptrs(h_f.buffer_ptrs), st), "b2s_stripe_pack")
         with ops._stage("stripe_pack_barrier", launches=0):
             h_f.barrier()              # every peer's stores have landed
         o = dict(device=dev)
@@ -484,7 +483,7 @@ class _RouteStripes(torch.autograd.Function):
         cam_m, gid_m = torch.empty(n_recv, dtype=torch.int64, **o), torch.empty(n_recv, dtype=torch.int64, **o)
         rows = L.TileRows(0, th) if cams_per_rank else L.TileRows(int(bounds[rank]), int(bounds[rank + 1]))
         with ops._stage("stripe_unpack"):
-            L.check(lib.b2s_stripe_unpack(n_recv, cap, ch, L.ptr(buf_f), tile_size, tw, th, ctypes.byref(rows), L.ptr(means2d_m),
+            L.check(lib.b2s_stripe_unpack(n_recv, ch, L.ptr(buf_f), tile_size, tw, th, ctypes.byref(rows), L.ptr(means2d_m),
                                           L.ptr(depths_m), L.ptr(conics_m), L.ptr(opac_m), L.ptr(cols_m), L.ptr(radii_m),
                                           L.ptr(cam_m), L.ptr(gid_m), L.ptr(tiles_m), L.ptr(dkeys), L.ptr(rowids), st),
                     "b2s_stripe_unpack")
