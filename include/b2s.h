@@ -383,6 +383,27 @@ typedef struct {
 } b2s_composite_bwd_args;
 B2S_API int b2s_composite_bwd(const b2s_composite_bwd_args* a, b2s_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * The step either side of rasterization() in the training loop.  The reference's
+ * Train-Stage1 component runs gsplat's examples/simple_trainer.py (source/container/src/main.py:1328-1347):
+ * loss = (1-lambda) * L1 + lambda * (1 - SSIM) (fused_ssim: 11x11 Gaussian window, sigma 1.5, "valid" padding,
+ * C1 = 0.01^2, C2 = 0.03^2), optimizers = torch.optim.Adam per parameter group.
+ *   b2s_l1_ssim_fwd : render / target [C,H,W,ch]; partial [b2s_l1_ssim_ctas(C,H,W)][2] = per-CTA sums of |x-y| and of
+ *                     the SSIM map (the caller adds them up: deterministic); dmaps [C,H-10,W-10,ch,3] = partial
+ *                     derivatives of the SSIM map w.r.t. the render's window moments (NULL: forward only)
+ *   b2s_l1_ssim_bwd : v_render [C,H,W,ch] = w_l1 * sign(x-y) + w_ssim * correlate(dmaps, window)
+ *   b2s_adam_step   : p, g, exp_avg, exp_avg_sq [rows, width]; row_mask (1 byte per row, NULL = all rows) skips rows
+ *                     entirely (SelectiveAdam: rows invisible this step keep parameters AND moments); step counts from 1
+ * ---------------------------------------------------------------------------------------------- */
+B2S_API int64_t b2s_l1_ssim_ctas(int32_t C, int32_t H, int32_t W);
+B2S_API int b2s_l1_ssim_fwd(int32_t C, int32_t H, int32_t W, int32_t channels, const float* render, const float* target,
+                            float* dmaps, float* partial, b2s_stream_t stream);
+B2S_API int b2s_l1_ssim_bwd(int32_t C, int32_t H, int32_t W, int32_t channels, const float* render, const float* target,
+                            const float* dmaps, float w_l1, float w_ssim, float* v_render, b2s_stream_t stream);
+B2S_API int b2s_adam_step(int64_t rows, int32_t width, float* param, const float* grad, float* exp_avg, float* exp_avg_sq,
+                          const uint8_t* row_mask, float lr, float beta1, float beta2, float eps, int64_t step,
+                          b2s_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

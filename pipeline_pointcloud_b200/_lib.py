@@ -148,6 +148,12 @@ SYMBOLS = {
                           [c_void_p] * 11 + [c_void_p]),
     "b2s_stripe_return": (c_int32, [c_int64, c_int32] + [c_void_p] * 7 + [c_int64, c_int32] + [c_void_p] * 6 + [c_void_p]),
     "b2s_stripe_scatter_add": (c_int32, [c_int32, c_int32] + [c_void_p] * 9 + [c_void_p]),
+    "b2s_l1_ssim_ctas": (c_int64, [c_int32, c_int32, c_int32]),
+    "b2s_l1_ssim_fwd": (c_int32, [c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "b2s_l1_ssim_bwd": (c_int32, [c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_float, c_float, c_void_p,
+                                  c_void_p]),
+    "b2s_adam_step": (c_int32, [c_int64, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_float, c_float,
+                                c_float, c_int64, c_void_p]),
     "b2s_composite_fwd": (c_int32, [POINTER(CompositeFwdArgs), c_void_p]),
     "b2s_composite_bwd": (c_int32, [POINTER(CompositeBwdArgs), c_void_p]),
 }
