@@ -1,0 +1,353 @@
+"""Trainer shell around the rasterization path: a drop-in for the command line the reference's
+Train-Stage1 component runs,
+
+    python gsplat/examples/simple_trainer.py {default|mcmc} --max_steps N --result-dir DIR --data_factor 1
+        --steps_scaler S --disable_viewer --packed --batch-size 1 --data-dir DATASET
+
+(source/container/src/main.py:1328-1347), producing the checkpoint the export stage reads:
+``DIR/ckpts/ckpt_{step}_rank{r}.pt`` = ``{"step", "splats": {means [N,3], scales [N,3] (log), quats [N,4] (wxyz),
+opacities [N] (logit), sh0 [N,1,3], shN [N,K-1,3]}}`` (source/container/src/pipeline/post_processing/gsplat_pt_to_ply.py:38-73).
+
+Every iteration runs on this package's kernels: ``rasterization()`` forward + backward, the fused L1+SSIM loss and the
+fused (Selective)Adam update.  Densification follows gsplat's ``DefaultStrategy`` (clone / split / prune / opacity
+reset) with torch tensor ops -- it runs every 100th step and is not on the per-iteration hot path.  ``mcmc`` is not
+implemented (raises).  Multi-GPU: launch under torchrun; Gaussians are sharded over the ranks and every rank renders its
+own camera (``rasterization(distributed=True)``), one checkpoint per rank as upstream.
+"""
+from __future__ import annotations
+
+import argparse
+import math
+import os
+import sys
+import time
+from typing import Dict, List, Optional
+
+import numpy as np
+import torch
+from torch import Tensor
+
+SH_C0 = 0.2820947917738781
+
+
+# ----------------------------------------------------------------------------------------------------------
+# command line (the argument surface of gsplat's simple_trainer that the reference uses; dashes and underscores both work)
+# ----------------------------------------------------------------------------------------------------------
+def parse_args(argv: Optional[List[str]] = None) -> argparse.Namespace:
+    argv = list(sys.argv[1:] if argv is None else argv)
+    argv = [("--" + a[2:].replace("_", "-")) if a.startswith("--") else a for a in argv]
+    ap = argparse.ArgumentParser(prog="simple_trainer.py", description=__doc__.split("\n\n")[0])
+    ap.add_argument("strategy", choices=["default", "mcmc"])
+    ap.add_argument("--data-dir", required=True)
+    ap.add_argument("--result-dir", default="results")
+    ap.add_argument("--data-factor", type=int, default=1)
+    ap.add_argument("--max-steps", type=int, default=30_000)
+    ap.add_argument("--steps-scaler", type=float, default=1.0)
+    ap.add_argument("--batch-size", type=int, default=1)
+    ap.add_argument("--packed", action="store_true")
+    ap.add_argument("--disable-viewer", action="store_true")
+    ap.add_argument("--sh-degree", type=int, default=3)
+    ap.add_argument("--sh-degree-interval", type=int, default=1000)
+    ap.add_argument("--ssim-lambda", type=float, default=0.2)
+    ap.add_argument("--init-opa", type=float, default=0.1)
+    ap.add_argument("--init-scale", type=float, default=1.0)
+    ap.add_argument("--antialiased", action="store_true")
+    ap.add_argument("--visible-adam", action="store_true")
+    ap.add_argument("--save-steps", type=int, nargs="*", default=[7_000, 30_000])
+    ap.add_argument("--seed", type=int, default=42)
+    ap.add_argument("--log-every", type=int, default=100)
+    a = ap.parse_args(argv)
+    if a.strategy == "mcmc":
+        raise NotImplementedError("the mcmc strategy is not implemented; use `default`")
+    if a.batch_size != 1:
+        raise NotImplementedError("--batch-size 1 is what the reference passes; larger batches are not implemented")
+    # gsplat scales every step-count option by steps_scaler (the reference passes 1 / n_gpus)
+    s = a.steps_scaler
+    a.max_steps = int(a.max_steps * s)
+    a.save_steps = [int(x * s) for x in a.save_steps]
+    a.sh_degree_interval = max(1, int(a.sh_degree_interval * s))
+    return a
+
+
+# ----------------------------------------------------------------------------------------------------------
+# dataset
+# ----------------------------------------------------------------------------------------------------------
+class ColmapDataset:
+    """images/ + sparse/0 of a COLMAP project; pinhole intrinsics (undistorted input, as the reference's SfM stage writes)."""
+
+    def __init__(self, data_dir: str, factor: int = 1):
+        import cv2
+        from . import colmap
+        sparse = colmap.find_sparse_dir(data_dir)
+        cams = colmap.read_cameras(os.path.join(sparse, "cameras.bin"))
+        imgs = colmap.read_images(os.path.join(sparse, "images.bin"))
+        self.points, self.points_rgb = colmap.read_points3d(os.path.join(sparse, "points3D.bin"))
+        img_dir = os.path.join(data_dir, "images" if factor == 1 else f"images_{factor}")
+        if not os.path.isdir(img_dir):
+            raise FileNotFoundError(img_dir)
+        self._cv2 = cv2
+        self.items = []
+        for im in sorted(imgs.values(), key=lambda t: t.name):
+            cam = cams[im.camera_id]
+            if np.any(np.abs(cam.distortion()) > 1e-8):
+                raise NotImplementedError(f"camera {cam.id} ({cam.model}) has lens distortion: undistort the images first")
+            K = cam.K().copy()
+            K[:2] /= factor
+            self.items.append({"path": os.path.join(img_dir, im.name), "K": K.astype(np.float32),
+                               "viewmat": im.world_to_cam().astype(np.float32),
+                               "size": (cam.width // factor, cam.height // factor)})
+        if not self.items:
+            raise ValueError("the COLMAP model registers no image")
+        centres = np.stack([np.linalg.inv(it["viewmat"])[:3, 3] for it in self.items])
+        self.scene_scale = float(np.linalg.norm(centres - centres.mean(0), axis=1).max()) * 1.1 or 1.0
+        self._cache: Dict[int, Tensor] = {}
+
+    def __len__(self):
+        return len(self.items)
+
+    def image(self, i: int) -> Tensor:
+        t = self._cache.get(i)
+        if t is None:
+            bgr = self._cv2.imread(self.items[i]["path"], self._cv2.IMREAD_COLOR)
+            if bgr is None:
+                raise FileNotFoundError(self.items[i]["path"])
+            t = torch.from_numpy(np.ascontiguousarray(bgr[..., ::-1])).float().div_(255.0).pin_memory() \
+                if torch.cuda.is_available() else torch.from_numpy(np.ascontiguousarray(bgr[..., ::-1])).float().div_(255.0)
+            self._cache[i] = t
+        return t
+
+
+# ----------------------------------------------------------------------------------------------------------
+# splats
+# ----------------------------------------------------------------------------------------------------------
+def knn_mean_dist(points: Tensor, k: int = 3, chunk: int = 4096) -> Tensor:
+    """Mean distance to the k nearest neighbours (chunked brute force on the device; initialisation only)."""
+    out = torch.empty(points.shape[0], device=points.device)
+    for s in range(0, points.shape[0], chunk):
+        d = torch.cdist(points[s:s + chunk], points)
+        out[s:s + chunk] = d.topk(min(k + 1, points.shape[0]), largest=False).values[:, 1:].mean(dim=1)
+    return out
+
+
+def create_splats(points: np.ndarray, rgb: np.ndarray, sh_degree: int, init_opa: float, init_scale: float, device,
+                  rank: int = 0, world: int = 1) -> Dict[str, Tensor]:
+    pts = torch.from_numpy(points).float().to(device)
+    col = torch.from_numpy(rgb).float().to(device) / 255.0
+    n_all = pts.shape[0]
+    dist = knn_mean_dist(pts[: min(n_all, 200_000)]) if n_all > 1 else torch.ones(1, device=device)
+    if n_all > dist.shape[0]:
+        dist = torch.cat([dist, dist.median().expand(n_all - dist.shape[0])])
+    pts, col, dist = pts[rank::world], col[rank::world], dist[rank::world]          # Gaussian sharding, as upstream
+    N, K = pts.shape[0], (sh_degree + 1) ** 2
+    g = torch.Generator(device="cpu").manual_seed(1234 + rank)
+    splats = {
+        "means": pts.clone(),
+        "scales": torch.log(dist.clamp_min(1e-7) * init_scale)[:, None].repeat(1, 3),
+        "quats": torch.rand(N, 4, generator=g).to(device),
+        "opacities": torch.logit(torch.full((N,), init_opa, device=device)),
+        "sh0": ((col - 0.5) / SH_C0)[:, None, :].contiguous(),
+        "shN": torch.zeros(N, K - 1, 3, device=device),
+    }
+    return {k: v.contiguous().requires_grad_() for k, v in splats.items()}
+
+
+LRS = {"means": 1.6e-4, "scales": 5e-3, "quats": 1e-3, "opacities": 5e-2, "sh0": 2.5e-3, "shN": 2.5e-3 / 20}
+
+
+# ----------------------------------------------------------------------------------------------------------
+# densification: gsplat DefaultStrategy (clone / split / prune / opacity reset)
+# ----------------------------------------------------------------------------------------------------------
+class DefaultStrategy:
+    def __init__(self, scene_scale: float, s: float = 1.0, prune_opa=0.005, grow_grad2d=0.0002, grow_scale3d=0.01,
+                 prune_scale3d=0.1, refine_start=500, refine_stop=15_000, reset_every=3000, refine_every=100):
+        self.scene_scale = scene_scale
+        self.prune_opa, self.grow_grad2d, self.grow_scale3d, self.prune_scale3d = prune_opa, grow_grad2d, grow_scale3d, prune_scale3d
+        self.refine_start, self.refine_stop = int(refine_start * s), int(refine_stop * s)
+        self.reset_every, self.refine_every = max(1, int(reset_every * s)), max(1, int(refine_every * s))
+        self.grad2d = self.count = None
+
+    def _replace(self, splats, opt, fn_param, fn_state):
+        for name in list(splats):
+            old = splats[name]
+            new = fn_param(name, old.detach()).contiguous().requires_grad_()
+            for grp in opt.param_groups:
+                for i, p in enumerate(grp["params"]):
+                    if p is old:
+                        st = opt.state.pop(old, None)
+                        grp["params"][i] = new
+                        if st is not None:
+                            opt.state[new] = {"step": st["step"], "exp_avg": fn_state(st["exp_avg"]).contiguous(),
+                                              "exp_avg_sq": fn_state(st["exp_avg_sq"]).contiguous()}
+            splats[name] = new
+
+    @torch.no_grad()
+    def accumulate(self, splats, meta, step):
+        if step >= self.refine_stop:
+            return
+        g = meta["means2d"].grad
+        if g is None:
+            return
+        N = splats["means"].shape[0]
+        if self.grad2d is None or self.grad2d.shape[0] != N:
+            self.grad2d = torch.zeros(N, device=g.device)
+            self.count = torch.zeros(N, device=g.device)
+        g = g.clone()
+        g[..., 0] *= meta["width"] / 2.0 * meta["n_cameras"]
+        g[..., 1] *= meta["height"] / 2.0 * meta["n_cameras"]
+        if meta.get("gaussian_ids") is not None:            # packed rows
+            ids = meta["gaussian_ids"]
+            off = getattr(self, "gid_offset", 0)
+            ids = ids - off
+            ok = (ids >= 0) & (ids < N)
+            self.grad2d.index_add_(0, ids[ok], g.norm(dim=-1)[ok])
+            self.count.index_add_(0, ids[ok], torch.ones_like(ids[ok], dtype=torch.float32))
+        else:
+            sel = meta["radii"] > 0                          # [C,N]
+            self.grad2d += (g.norm(dim=-1) * sel).sum(0)
+            self.count += sel.sum(0).float()
+
+    @torch.no_grad()
+    def refine(self, splats, opt, step) -> Dict[str, int]:
+        stats = {}
+        if step >= self.refine_stop or self.grad2d is None:
+            return stats
+        if step > self.refine_start and step % self.refine_every == 0:
+            grads = self.grad2d / self.count.clamp_min(1)
+            scales = torch.exp(splats["scales"].detach())
+            high = grads > self.grow_grad2d
+            small = scales.max(dim=-1).values <= self.grow_scale3d * self.scene_scale
+            dup, split = high & small, high & ~small
+            n_dup, n_split = int(dup.sum()), int(split.sum())
+            if n_dup or n_split:
+                quats = torch.nn.functional.normalize(splats["quats"].detach()[split], dim=-1)
+                w, x, y, z = quats.unbind(-1)
+                R = torch.stack([1 - 2 * (y * y + z * z), 2 * (x * y - w * z), 2 * (x * z + w * y),
+                                 2 * (x * y + w * z), 1 - 2 * (x * x + z * z), 2 * (y * z - w * x),
+                                 2 * (x * z - w * y), 2 * (y * z + w * x), 1 - 2 * (x * x + y * y)], -1).reshape(-1, 3, 3)
+                noise = torch.einsum("nij,nj,bnj->bni", R, scales[split], torch.randn(2, n_split, 3, device=scales.device))
+                keep = ~split
+
+                def fn_param(name, p):
+                    parts = [p[keep], p[dup]]
+                    if name == "means":
+                        parts.append((p[split][None] + noise).reshape(-1, 3))
+                    elif name == "scales":
+                        parts.append(torch.log(torch.exp(p[split]) / 1.6).repeat(2, 1))
+                    else:
+                        parts.append(p[split].repeat(2, *([1] * (p.dim() - 1))))
+                    return torch.cat(parts)
+
+                def fn_state(v):
+                    z = torch.zeros((n_dup + 2 * n_split,) + v.shape[1:], device=v.device)
+                    return torch.cat([v[keep], z])
+
+                self._replace(splats, opt, fn_param, fn_state)
+            # prune
+            opa = torch.sigmoid(splats["opacities"].detach())
+            prune = opa < self.prune_opa
+            if step > self.reset_every:
+                prune |= torch.exp(splats["scales"].detach()).max(dim=-1).values > self.prune_scale3d * self.scene_scale
+            n_prune = int(prune.sum())
+            if n_prune:
+                keep2 = ~prune
+                self._replace(splats, opt, lambda name, p: p[keep2], lambda v: v[keep2])
+            stats = {"duplicated": n_dup, "split": n_split, "pruned": n_prune, "n": splats["means"].shape[0]}
+            self.grad2d = self.count = None
+        if step % self.reset_every == 0 and step > 0:
+            cap = math.log(2 * self.prune_opa / (1 - 2 * self.prune_opa))
+
+            def fn_param(name, p):
+                return p.clamp(max=cap) if name == "opacities" else p
+
+            old_opa = splats["opacities"]
+            self._replace(splats, opt, fn_param, lambda v: v)
+            st = opt.state.get(splats["opacities"])
+            if st is not None:
+                st["exp_avg"].zero_(); st["exp_avg_sq"].zero_()
+            del old_opa
+            stats["opacity_reset"] = 1
+        return stats
+
+
+# ----------------------------------------------------------------------------------------------------------
+def train(a: argparse.Namespace) -> str:
+    import torch.distributed as dist
+    import pipeline_pointcloud_b200 as b2s
+    from .training import FusedAdam, l1_ssim_loss
+
+    if not torch.cuda.is_available():
+        raise RuntimeError("simple_trainer needs a CUDA device (there is no CPU path)")
+    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1 and not dist.is_initialized():
+        dist.init_process_group("nccl", device_id=dev)
+    torch.manual_seed(a.seed + rank)
+    np.random.seed(a.seed + rank)
+
+    data = ColmapDataset(a.data_dir, a.data_factor)
+    splats = create_splats(data.points, data.points_rgb, a.sh_degree, a.init_opa, a.init_scale, dev, rank, world)
+    opt = FusedAdam([{"params": [splats[k]], "lr": LRS[k] * (data.scene_scale if k == "means" else 1.0), "name": k} for k in LRS],
+                    eps=1e-15)
+    means_lr0 = opt.param_groups[0]["lr"]
+    gamma = 0.01 ** (1.0 / max(a.max_steps, 1))
+    strategy = DefaultStrategy(data.scene_scale, a.steps_scaler)
+    ckpt_dir = os.path.join(a.result_dir, "ckpts")
+    os.makedirs(ckpt_dir, exist_ok=True)
+    save_at = {s - 1 for s in a.save_steps} | {a.max_steps - 1}
+    order = np.random.permutation(len(data))
+    last_ckpt, t0, stats = "", time.time(), {}
+    strategy.gid_offset = 0
+    for step in range(a.max_steps):
+        i = int(order[(step * world + rank) % len(order)])
+        if (step * world + rank) % len(order) == 0 and step > 0:
+            order = np.random.permutation(len(data))
+        item = data.items[i]
+        W, H = item["size"]
+        target = data.image(i).to(dev, non_blocking=True)[None]
+        deg = min(step // a.sh_degree_interval, a.sh_degree)
+        colors = torch.cat([splats["sh0"], splats["shN"]], dim=1)
+        render, alpha, meta = b2s.rasterization(
+            splats["means"], splats["quats"], torch.exp(splats["scales"]), torch.sigmoid(splats["opacities"]), colors,
+            torch.from_numpy(item["viewmat"])[None].to(dev), torch.from_numpy(item["K"])[None].to(dev), W, H, sh_degree=deg,
+            packed=a.packed or world > 1, rasterize_mode="antialiased" if a.antialiased else "classic", distributed=world > 1)
+        meta["means2d"].retain_grad()
+        loss = l1_ssim_loss(render, target, a.ssim_lambda)
+        opt.zero_grad()
+        loss.backward()
+        if world > 1 and (step == 0 or stats):       # shard sizes change only when densification ran (same step on every rank)
+            n = torch.tensor([splats["means"].shape[0]], dtype=torch.int64, device=dev)
+            ns = [torch.empty_like(n) for _ in range(world)]
+            dist.all_gather(ns, n)
+            strategy.gid_offset = int(sum(int(t) for t in ns[:rank]))
+        # multi-GPU: this rank sees every rank's Gaussians through its own camera only; the statistics of its own
+        # Gaussians therefore come from 1/world of the views (rows of other ranks' Gaussians are ignored)
+        strategy.accumulate(splats, meta, step)
+        vis = None
+        if a.visible_adam and world == 1:
+            vis = (meta["radii"] > 0).any(0) if meta.get("gaussian_ids") is None else \
+                torch.zeros(splats["means"].shape[0], dtype=torch.bool, device=dev).index_fill_(0, meta["gaussian_ids"], True)
+        opt.step(visibility=vis)
+        opt.param_groups[0]["lr"] = means_lr0 * gamma ** (step + 1)
+        stats = strategy.refine(splats, opt, step)
+        if rank == 0 and (step % a.log_every == 0 or step == a.max_steps - 1 or stats):
+            print(f"step {step:6d}  loss {loss.item():.5f}  N {splats['means'].shape[0]}  sh {deg}  "
+                  f"{(time.time() - t0) / (step + 1) * 1e3:.1f} ms/it  {stats if stats else ''}", flush=True)
+        if step in save_at:
+            last_ckpt = os.path.join(ckpt_dir, f"ckpt_{step}_rank{rank}.pt")
+            torch.save({"step": step, "splats": {k: v.detach().cpu() for k, v in splats.items()}}, last_ckpt)
+    if world > 1:
+        dist.barrier()
+    return last_ckpt
+
+
+def main(argv: Optional[List[str]] = None) -> int:
+    a = parse_args(argv)
+    ckpt = train(a)
+    print(f"checkpoint: {ckpt}")
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

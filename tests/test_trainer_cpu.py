@@ -1,0 +1,101 @@
+"""CPU tests of the trainer shell's host logic: command line of the reference's Train-Stage1
+component, COLMAP model I/O, and the checkpoint -> PLY export against a numpy restatement of the reference's
+gsplat_pt_to_ply.py (source/container/src/pipeline/post_processing/gsplat_pt_to_ply.py:52-75)."""
+import os
+import struct
+
+import numpy as np
+import pytest
+import torch
+
+from pipeline_pointcloud_b200 import colmap, export
+from pipeline_pointcloud_b200.simple_trainer import parse_args
+
+
+def test_reference_command_line_is_accepted():
+    # the exact argument list source/container/src/main.py:1328-1338 builds (4 GPUs, MAX_STEPS 30000)
+    a = parse_args(["default", "--max_steps", "30000", "--result-dir", "/tmp/out", "--data_factor", "1", "--steps_scaler", "0.25",
+                    "--disable_viewer", "--packed", "--batch-size", "1", "--data-dir", "/data/set"])
+    assert a.strategy == "default" and a.packed and a.disable_viewer and a.batch_size == 1 and a.data_factor == 1
+    assert a.max_steps == 7500 and a.save_steps == [1750, 7500] and a.sh_degree_interval == 250
+    assert a.result_dir == "/tmp/out" and a.data_dir == "/data/set"
+    with pytest.raises(NotImplementedError):
+        parse_args(["mcmc", "--data-dir", "x"])
+    with pytest.raises(NotImplementedError):
+        parse_args(["default", "--data-dir", "x", "--batch-size", "2"])
+    with pytest.raises(SystemExit):
+        parse_args(["default"])                      # --data-dir is required
+
+
+def test_colmap_model_roundtrip(tmp_path):
+    rng = np.random.default_rng(0)
+    n_img = 5
+    Ks = np.stack([np.array([[500.0 + i, 0, 160], [0, 510.0 + i, 120], [0, 0, 1]]) for i in range(n_img)])
+    views = []
+    for i in range(n_img):
+        A = rng.normal(size=(3, 3))
+        Q, _ = np.linalg.qr(A)
+        if np.linalg.det(Q) < 0:
+            Q[:, 0] *= -1
+        V = np.eye(4)
+        V[:3, :3], V[:3, 3] = Q, rng.normal(size=3)
+        views.append(V)
+    names = [f"img_{i:03d}.png" for i in range(n_img)]
+    xyz, rgb = rng.normal(size=(40, 3)), rng.integers(0, 256, size=(40, 3), dtype=np.uint8)
+    sparse = str(tmp_path / "sparse" / "0")
+    colmap.write_model(sparse, Ks, np.stack(views), names, 320, 240, xyz, rgb)
+    assert colmap.find_sparse_dir(str(tmp_path)) == sparse
+    cams, imgs = colmap.read_cameras(sparse + "/cameras.bin"), colmap.read_images(sparse + "/images.bin")
+    p, c = colmap.read_points3d(sparse + "/points3D.bin")
+    assert np.allclose(p, xyz) and np.array_equal(c, rgb)
+    assert len(cams) == n_img and len(imgs) == n_img
+    for i in range(n_img):
+        im = imgs[i + 1]
+        assert im.name == names[i] and cams[im.camera_id].model == "PINHOLE"
+        assert np.allclose(im.world_to_cam(), views[i], atol=1e-9)
+        assert np.allclose(cams[im.camera_id].K(), Ks[i]) and cams[im.camera_id].distortion().size == 0
+    # a camera model with distortion parameters is parsed (the trainer then refuses it)
+    with open(sparse + "/cameras.bin", "wb") as f:
+        f.write(struct.pack("<Q", 1) + struct.pack("<iiQQ", 1, 2, 320, 240) + struct.pack("<dddd", 400.0, 160.0, 120.0, 0.05))
+    cam = colmap.read_cameras(sparse + "/cameras.bin")[1]
+    assert cam.model == "SIMPLE_RADIAL" and np.allclose(cam.distortion(), [0.05]) and cam.K()[0, 0] == 400.0
+
+
+def reference_ply_channels(splats):
+    """numpy restatement of gsplat_pt_to_ply.py:52-73 (column order and SH transposition)."""
+    pos = splats["means"].numpy()
+    cols = [("x", pos[:, 0]), ("y", pos[:, 1]), ("z", pos[:, 2])] + [(k, np.zeros(len(pos), np.float32)) for k in ("nx", "ny", "nz")]
+    f_dc = np.transpose(splats["sh0"].numpy(), (0, 2, 1)).reshape(len(pos), -1)
+    cols += [(f"f_dc_{i}", f_dc[:, i]) for i in range(f_dc.shape[1])]
+    f_rest = np.transpose(splats["shN"].numpy(), (0, 2, 1)).reshape(len(pos), -1)
+    cols += [(f"f_rest_{i}", f_rest[:, i]) for i in range(f_rest.shape[1])]
+    cols.append(("opacity", splats["opacities"].numpy()))
+    cols += [(f"scale_{i}", splats["scales"].numpy()[:, i]) for i in range(3)]
+    cols += [(f"rot_{i}", splats["quats"].numpy()[:, i]) for i in range(4)]
+    return cols
+
+
+def test_export_ply_matches_reference_layout(tmp_path):
+    g = torch.Generator().manual_seed(0)
+    N = 37
+    splats = {"means": torch.randn(N, 3, generator=g), "scales": torch.randn(N, 3, generator=g), "quats": torch.randn(N, 4, generator=g),
+              "opacities": torch.randn(N, generator=g), "sh0": torch.randn(N, 1, 3, generator=g), "shN": torch.randn(N, 15, 3, generator=g)}
+    ck = tmp_path / "ckpts"
+    ck.mkdir()
+    torch.save({"step": 9, "splats": {k: torch.zeros_like(v) for k, v in splats.items()}}, ck / "ckpt_1749_rank0.pt")
+    torch.save({"step": 99, "splats": splats}, ck / "ckpt_7499_rank0.pt")        # lexicographically last -> the one exported
+    out = str(tmp_path / "splat.ply")
+    assert export.main([str(ck), out]) == 0
+    raw = open(out, "rb").read()
+    head, body = raw.split(b"end_header\n", 1)
+    ref = reference_ply_channels(splats)
+    lines = head.decode().strip().split("\n")
+    assert lines[:3] == ["ply", "format binary_little_endian 1.0", f"element vertex {N}"]
+    assert lines[3:] == [f"property float {k}" for k, _ in ref]
+    assert len(ref) == 3 + 3 + 3 + 45 + 1 + 3 + 4
+    table = np.stack([np.asarray(v, np.float32).reshape(-1) for _, v in ref], axis=1)      # one interleaved row per Gaussian
+    assert body == table.astype("<f4").tobytes()
+    back = export.read_ply(out)
+    assert list(back) == [k for k, _ in ref] and np.array_equal(back["f_rest_17"], table[:, 9 + 17])
+    # f_rest is channel-major: f_rest_0..14 = red coefficients 1..15
+    assert np.array_equal(back["f_rest_3"], splats["shN"][:, 3, 0].numpy()) and np.array_equal(back["f_rest_15"], splats["shN"][:, 0, 1].numpy())
