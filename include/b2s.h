@@ -404,6 +404,19 @@ B2S_API int b2s_adam_step(int64_t rows, int32_t width, float* param, const float
                           const uint8_t* row_mask, float lr, float beta1, float beta2, float eps, int64_t step,
                           b2s_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * SPZ packing: packGaussians() of the reference's vendored Niantic codec
+ * (source/container/src/pipeline/post_processing/spz/src/cc/load-spz.cc:213-289), the quantisation behind the Spz-Export
+ * component (`splat_converter splat.ply`, source/container/src/main.py:1532-1545).  Inputs are the checkpoint tensors
+ * (log-scales, wxyz quaternions, opacity logits, sh0 [N,1,3], shN [N,shN_rows,3] of which the first sh_dim rows are
+ * used); outputs are the codec's byte arrays: positions [9N], alphas [N], colors [3N], scales [3N], rotations [3N],
+ * sh [3*sh_dim*N].  Byte-exact against the reference's converter (oracle/_ref/splat_converter).
+ * ---------------------------------------------------------------------------------------------- */
+B2S_API int b2s_spz_pack(int64_t N, int32_t sh_dim, const float* means, const float* log_scales, const float* quats_wxyz,
+                         const float* opacity_logits, const float* sh0, const float* shN, int32_t shN_rows,
+                         uint8_t* positions, uint8_t* alphas, uint8_t* colors, uint8_t* scales, uint8_t* rotations,
+                         uint8_t* sh, b2s_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -92,10 +92,72 @@ def export_ply(ckpt_dir: str, out_ply: str) -> int:
     return write_ply(out_ply, ply_channels(ckpt["splats"]))
 
 
+# ----------------------------------------------------------------------------------------------------------
+# .spz (second half): the reference's Spz-Export component runs `splat_converter splat.ply`
+# (source/container/src/main.py:1532-1545) = loadSplatFromPly + saveSpz of the vendored Niantic codec
+# (source/container/src/pipeline/post_processing/spz/src/cc/load-spz.cc:492-500): pack, serialise, gzip.
+# ----------------------------------------------------------------------------------------------------------
+def spz_payload(splats: Dict[str, torch.Tensor], antialiased: bool = False) -> bytes:
+    """Header + packed arrays (the bytes inside the gzip container).  Packing runs on the GPU (csrc/spz.cu)."""
+    import struct
+    from . import _lib as L
+    dev = L.require_cuda(splats["means"])
+    t = {k: L.f32c(v.detach()) for k, v in splats.items()}
+    n = t["means"].shape[0]
+    rows = t["shN"].shape[1] if t["shN"].dim() == 3 else 0
+    sh_dim = 15 if rows >= 15 else 8 if rows >= 8 else 3 if rows >= 3 else 0       # load-spz.cc:47-55 degreeForDim
+    sh_degree = {0: 0, 3: 1, 8: 2, 15: 3}[sh_dim]
+    if n > 10 * 1024 * 1024:
+        raise ValueError("the SPZ loader of the reference refuses more than 10 Mi points (load-spz.cc:611)")
+    u8 = lambda m: torch.empty(m, dtype=torch.uint8, device=dev)
+    pos, alp, col, sca, rot, sh = u8(9 * n), u8(n), u8(3 * n), u8(3 * n), u8(3 * n), u8(3 * sh_dim * n)
+    L.check(L.lib().b2s_spz_pack(n, sh_dim, L.ptr(t["means"]), L.ptr(t["scales"]), L.ptr(t["quats"]), L.ptr(t["opacities"]),
+                                 L.ptr(t["sh0"]), L.ptr(t["shN"]) if sh_dim else None, rows, L.ptr(pos), L.ptr(alp), L.ptr(col),
+                                 L.ptr(sca), L.ptr(rot), L.ptr(sh) if sh_dim else None, L.stream_ptr(dev)), "b2s_spz_pack")
+    head = struct.pack("<IIIBBBB", 0x5053474E, 2, n, sh_degree, 12, 1 if antialiased else 0, 0)
+    return head + b"".join(x.cpu().numpy().tobytes() for x in (pos, alp, col, sca, rot, sh))
+
+
+def write_spz(path: str, splats: Dict[str, torch.Tensor], antialiased: bool = False) -> int:
+    import zlib
+    data = spz_payload(splats, antialiased)
+    # deflateInit2(Z_DEFAULT_COMPRESSION, Z_DEFLATED, 16 + MAX_WBITS, memLevel 9, Z_DEFAULT_STRATEGY)   (load-spz.cc:189-191)
+    c = zlib.compressobj(zlib.Z_DEFAULT_COMPRESSION, zlib.DEFLATED, 16 + zlib.MAX_WBITS, 9, zlib.Z_DEFAULT_STRATEGY)
+    blob = c.compress(data) + c.flush()
+    os.makedirs(os.path.dirname(os.path.abspath(path)), exist_ok=True)
+    with open(path, "wb") as f:
+        f.write(blob)
+    return len(blob)
+
+
+def splats_from_ply(path: str, device="cuda") -> Dict[str, torch.Tensor]:
+    """Checkpoint-shaped tensors from a 3DGS PLY (the inverse of ``ply_channels``)."""
+    cols = read_ply(path)
+    n = len(cols["x"])
+    f = lambda names: torch.from_numpy(np.stack([cols[k] for k in names], axis=1)).to(device)
+    rest = [k for k in cols if k.startswith("f_rest_")]
+    S = len(rest) // 3
+    shN = torch.from_numpy(np.stack([cols[f"f_rest_{i}"] for i in range(3 * S)], axis=1).reshape(n, 3, S).transpose(0, 2, 1).copy()
+                           if S else np.zeros((n, 0, 3), np.float32)).to(device)
+    return {"means": f(["x", "y", "z"]), "scales": f(["scale_0", "scale_1", "scale_2"]), "quats": f(["rot_0", "rot_1", "rot_2", "rot_3"]),
+            "opacities": torch.from_numpy(cols["opacity"].copy()).to(device), "sh0": f(["f_dc_0", "f_dc_1", "f_dc_2"])[:, None, :].contiguous(),
+            "shN": shN.contiguous()}
+
+
+def convert_ply_to_spz(ply_path: str) -> str:
+    """`splat_converter splat.ply`: writes splat.spz next to it."""
+    out = os.path.splitext(ply_path)[0] + ".spz"
+    write_spz(out, splats_from_ply(ply_path))
+    return out
+
+
 def main(argv=None) -> int:
     argv = list(sys.argv[1:] if argv is None else argv)
+    if len(argv) == 1 and argv[0].endswith(".ply"):          # the Spz-Export component's command line
+        print(f"Converted {argv[0]} to {convert_ply_to_spz(argv[0])}")
+        return 0
     if len(argv) != 2:
-        print("usage: python -m pipeline_pointcloud_b200.export CKPT_DIR OUTPUT.ply", file=sys.stderr)
+        print("usage: python -m pipeline_pointcloud_b200.export CKPT_DIR OUTPUT.ply | INPUT.ply", file=sys.stderr)
         return 2
     n = export_ply(argv[0], argv[1])
     print(f"wrote {n} Gaussians to {argv[1]}")
