@@ -499,8 +499,8 @@ def main():
         "iters_per_s": 1e3 / ms_per_step * C_total,
         "gpu_launches": timer.launches,
         "gpu_launches_note": "kernels of libb2s.so launched inside the timed region (per step: project_fwd 1, depth sort 6, "
-                             "coarse binning 5, composite_fwd 1, composite_bwd 1, sh_bwd 1, project_bwd 1; all hand-written, "
-                             "no library kernels)",
+                             "coarse binning 5, composite_fwd 1, composite_bwd 1, sh_bwd 4 (classify, dense [returns at once in "
+                             "sparse mode], zero fill, list-driven), project_bwd 2; all hand-written, no library kernels)",
         "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "steps": e2e_steps, "note": "rasterization() + backward driven from pinned host buffers: every step copies all "
                 "inputs in and render, alpha and all gradients out; copies of neighbouring steps overlap (2 slots, 3 streams)"},

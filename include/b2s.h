@@ -116,7 +116,14 @@ typedef struct {
     float* v_sh_coeffs; /* [N, sh_stride_k, 3] or NULL; rows >= (deg+1)^2 are not touched */
     int32_t stages;         /* 0 = both; 1 = SH colour VJP only (v_sh_coeffs, v_means); 2 = projection VJP only (when
                                sh_coeffs and v_sh_coeffs are set it ADDS to the v_means a stages == 1 call left) */
+    /* optional scratch of b2s_project_bwd_workspace_bytes(N) bytes, 256-byte aligned (NULL: dense kernels only).
+     * With it, rows whose cotangents are all zero (occluded: compositing never reached them) are filtered out once:
+     * when at most a quarter of the rows is live the gradients are produced by a zero fill plus list-driven kernels.
+     * A stages == 2 call must be given the workspace its stages == 1 call used. */
+    void* workspace;
+    int64_t workspace_bytes;
 } b2s_project_bwd_args;
+B2S_API int64_t b2s_project_bwd_workspace_bytes(int64_t N);
 B2S_API int b2s_project_bwd(const b2s_project_bwd_args* a, b2s_stream_t stream);
 
 /* Stand-alone SH evaluation over M directions (gsplat `spherical_harmonics` fwd/bwd): the

@@ -20,7 +20,10 @@ namespace b2s {
 constexpr int FWD_THREADS = 256;
 constexpr int BWD_THREADS = 128;
 
-__host__ __device__ constexpr int sh_row_stride(int K) { return (3 * K) | 1; }  // odd => conflict-free rows
+// Row stride of the smem SH tile (floats).  Degree 3 (48 floats per row): 52, i.e. 16-byte aligned rows whose per-thread
+// 128-bit reads are conflict free (8 consecutive rows start in banks 0,20,8,28,16,4,24,12: disjoint 4-bank groups), so the
+// tile is filled, read and drained with LDS.128 / STS.128.  Other degrees: odd stride, conflict-free scalar rows.
+__host__ __device__ constexpr int sh_row_stride(int K) { return K == 16 ? 52 : ((3 * K) | 1); }
 
 // ---- warp-cooperative movement of 32 SH rows between global memory and the padded smem tile -------
 // gbase points at row 0 of the warp's chunk, `rows` valid rows, row_mask: which rows to move.
@@ -42,8 +45,7 @@ __device__ __forceinline__ void sh_rows_load(float* tile, const float* gbase, in
         for (int i = 0; i < 12; ++i) {
             int q = lane + 32 * i;
             int r = q / 12, e = (q - r * 12) * 4;
-            float* d = tile + r * rs + e;
-            d[0] = v[i].x; d[1] = v[i].y; d[2] = v[i].z; d[3] = v[i].w;
+            *reinterpret_cast<float4*>(tile + r * rs + e) = v[i];
         }
     } else {
         const int per = 3 * K;
@@ -65,10 +67,7 @@ __device__ __forceinline__ void sh_rows_store(const float* tile, float* gbase, i
         for (int i = 0; i < 12; ++i) {
             int q = lane + 32 * i;
             int r = q / 12, e = (q - r * 12) * 4;
-            if (r < rows) {
-                const float* s = tile + r * rs + e;
-                stg_stream4(g4 + q, make_float4(s[0], s[1], s[2], s[3]));
-            }
+            if (r < rows) stg_stream4(g4 + q, *reinterpret_cast<const float4*>(tile + r * rs + e));
         }
     } else {
         const int per = 3 * K;
@@ -193,9 +192,21 @@ __global__ void __launch_bounds__(FWD_THREADS) project_fwd_kernel(const b2s_proj
             float inv = 1.f / fmaxf(sqrtf(dx * dx + dy * dy + dz * dz), 1e-12f);
             float Y[16];
             sh_basis(a.sh_degree, dx * inv, dy * inv, dz * inv, Y);
+            if (KVEC == 16) {                      // 4 bases = 12 floats = three 128-bit shared loads
+                const float4* row4 = reinterpret_cast<const float4*>(row);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const float4 c0 = row4[3 * q], c1 = row4[3 * q + 1], c2 = row4[3 * q + 2];
+                    r += Y[4 * q] * c0.x; g += Y[4 * q] * c0.y; b += Y[4 * q] * c0.z;
+                    r += Y[4 * q + 1] * c0.w; g += Y[4 * q + 1] * c1.x; b += Y[4 * q + 1] * c1.y;
+                    r += Y[4 * q + 2] * c1.z; g += Y[4 * q + 2] * c1.w; b += Y[4 * q + 2] * c2.x;
+                    r += Y[4 * q + 3] * c2.y; g += Y[4 * q + 3] * c2.z; b += Y[4 * q + 3] * c2.w;
+                }
+            } else {
 #pragma unroll 4
-            for (int k = 0; k < K; ++k) {
-                r += Y[k] * row[3 * k]; g += Y[k] * row[3 * k + 1]; b += Y[k] * row[3 * k + 2];
+                for (int k = 0; k < K; ++k) {
+                    r += Y[k] * row[3 * k]; g += Y[k] * row[3 * k + 1]; b += Y[k] * row[3 * k + 2];
+                }
             }
             r = fmaxf(r + 0.5f, 0.f); g = fmaxf(g + 0.5f, 0.f); b = fmaxf(b + 0.5f, 0.f);
         }
@@ -210,10 +221,18 @@ __global__ void __launch_bounds__(FWD_THREADS) project_fwd_kernel(const b2s_proj
 // =================================================================================================
 constexpr int SHB_THREADS = 256;
 
+// sparse backward mode (see bwd_classify_kernel below): list lengths, written by the classify pass of the same call
+struct BwdCounts {
+    unsigned n_geom, n_sh;
+    unsigned pad[62];
+};
+__device__ __forceinline__ bool bwd_sparse(unsigned n_live, int64_t N) { return (int64_t)n_live * 4 <= N; }
+
 template <int KVEC, bool MULTI>
-__global__ void __launch_bounds__(SHB_THREADS, 4) sh_bwd_fused_kernel(const b2s_project_bwd_args a) {
+__global__ void __launch_bounds__(SHB_THREADS, 4) sh_bwd_fused_kernel(const b2s_project_bwd_args a, const BwdCounts* cnt) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     Camera* cams = reinterpret_cast<Camera*>(smem_raw);
+    if (cnt && bwd_sparse(cnt->n_sh, a.N)) return;          // sh_zero_kernel + sh_sparse_kernel do this call's work
     float* sh_tiles = reinterpret_cast<float*>(smem_raw + ((a.C * sizeof(Camera) + 15) / 16) * 16);
     load_cameras(cams, a.C, a.viewmats, a.Ks, a.campos, (float)a.width, (float)a.height);
 
@@ -284,16 +303,51 @@ __global__ void __launch_bounds__(SHB_THREADS, 4) sh_bwd_fused_kernel(const b2s_
             float Y[16], w[16];
             sh_basis(a.sh_degree, ux, uy, uz, Y);
             float cr = 0.5f, cg = 0.5f, cb = 0.5f;
+            if (KVEC == 16) {
+                const float4* rin4 = reinterpret_cast<const float4*>(rin);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const float4 c0 = rin4[3 * q], c1 = rin4[3 * q + 1], c2 = rin4[3 * q + 2];
+                    cr += Y[4 * q] * c0.x; cg += Y[4 * q] * c0.y; cb += Y[4 * q] * c0.z;
+                    cr += Y[4 * q + 1] * c0.w; cg += Y[4 * q + 1] * c1.x; cb += Y[4 * q + 1] * c1.y;
+                    cr += Y[4 * q + 2] * c1.z; cg += Y[4 * q + 2] * c1.w; cb += Y[4 * q + 2] * c2.x;
+                    cr += Y[4 * q + 3] * c2.y; cg += Y[4 * q + 3] * c2.z; cb += Y[4 * q + 3] * c2.w;
+                }
+            } else {
 #pragma unroll 4
-            for (int k = 0; k < K; ++k) { cr += Y[k] * rin[3 * k]; cg += Y[k] * rin[3 * k + 1]; cb += Y[k] * rin[3 * k + 2]; }
+                for (int k = 0; k < K; ++k) { cr += Y[k] * rin[3 * k]; cg += Y[k] * rin[3 * k + 1]; cb += Y[k] * rin[3 * k + 2]; }
+            }
             const float vr = cr > 0.f ? __ldg(a.v_colors + 3 * i) : 0.f;        // clamp_min(., 0) gate
             const float vg = cg > 0.f ? __ldg(a.v_colors + 3 * i + 1) : 0.f;
             const float vb = cb > 0.f ? __ldg(a.v_colors + 3 * i + 2) : 0.f;
+            if (KVEC == 16) {
+                const float4* rin4 = reinterpret_cast<const float4*>(rin);
+                float4* rout4 = reinterpret_cast<float4*>(rout);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const float4 c0 = rin4[3 * q], c1 = rin4[3 * q + 1], c2 = rin4[3 * q + 2];
+                    w[4 * q] = c0.x * vr + c0.y * vg + c0.z * vb;
+                    w[4 * q + 1] = c0.w * vr + c1.x * vg + c1.y * vb;
+                    w[4 * q + 2] = c1.z * vr + c1.w * vg + c2.x * vb;
+                    w[4 * q + 3] = c2.y * vr + c2.z * vg + c2.w * vb;
+                    float4 o0 = make_float4(Y[4 * q] * vr, Y[4 * q] * vg, Y[4 * q] * vb, Y[4 * q + 1] * vr);
+                    float4 o1 = make_float4(Y[4 * q + 1] * vg, Y[4 * q + 1] * vb, Y[4 * q + 2] * vr, Y[4 * q + 2] * vg);
+                    float4 o2 = make_float4(Y[4 * q + 2] * vb, Y[4 * q + 3] * vr, Y[4 * q + 3] * vg, Y[4 * q + 3] * vb);
+                    if (MULTI) {
+                        const float4 p0 = rout4[3 * q], p1 = rout4[3 * q + 1], p2 = rout4[3 * q + 2];
+                        o0.x += p0.x; o0.y += p0.y; o0.z += p0.z; o0.w += p0.w;
+                        o1.x += p1.x; o1.y += p1.y; o1.z += p1.z; o1.w += p1.w;
+                        o2.x += p2.x; o2.y += p2.y; o2.z += p2.z; o2.w += p2.w;
+                    }
+                    rout4[3 * q] = o0; rout4[3 * q + 1] = o1; rout4[3 * q + 2] = o2;
+                }
+            } else {
 #pragma unroll 4
-            for (int k = 0; k < K; ++k) {
-                w[k] = rin[3 * k] * vr + rin[3 * k + 1] * vg + rin[3 * k + 2] * vb;
-                if (MULTI) { rout[3 * k] += Y[k] * vr; rout[3 * k + 1] += Y[k] * vg; rout[3 * k + 2] += Y[k] * vb; }
-                else { rout[3 * k] = Y[k] * vr; rout[3 * k + 1] = Y[k] * vg; rout[3 * k + 2] = Y[k] * vb; }
+                for (int k = 0; k < K; ++k) {
+                    w[k] = rin[3 * k] * vr + rin[3 * k + 1] * vg + rin[3 * k + 2] * vb;
+                    if (MULTI) { rout[3 * k] += Y[k] * vr; rout[3 * k + 1] += Y[k] * vg; rout[3 * k + 2] += Y[k] * vb; }
+                    else { rout[3 * k] = Y[k] * vr; rout[3 * k + 1] = Y[k] * vg; rout[3 * k + 2] = Y[k] * vb; }
+                }
             }
             float vx, vy, vz;
             sh_basis_vjp(a.sh_degree, ux, uy, uz, w, vx, vy, vz);
@@ -312,37 +366,104 @@ __global__ void __launch_bounds__(SHB_THREADS, 4) sh_bwd_fused_kernel(const b2s_
 }
 
 // =================================================================================================
-// backward, part 2: projection VJP (little traffic, heavy arithmetic)
+// backward, sparse mode.  In a dense scene compositing saturates after the first few layers, so most visible rows
+// come back with an all-zero cotangent (2.7 % are reached in the 5.8 M benchmark scene).  `bwd_classify_kernel`
+// zero-fills the small gradients, tests every row once and appends the live ones to two lists (geometry, SH colour);
+// when a list holds at most a quarter of the rows the dense kernel of that stage returns immediately and a
+// list-driven kernel does the work instead (for SH: a streaming zero fill of v_sh plus one thread per live row).
+// The choice is made on the device from the list lengths: no host round trip.
 // =================================================================================================
-template <bool MEANS_ACC>   // MEANS_ACC: v_means already holds the SH part (or an earlier camera chunk)
-__global__ void __launch_bounds__(BWD_THREADS) project_bwd_kernel(const b2s_project_bwd_args a) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    Camera* cams = reinterpret_cast<Camera*>(smem_raw);
-    const float W = (float)a.width, H = (float)a.height;
-    load_cameras(cams, a.C, a.viewmats, a.Ks, a.campos, W, H);
 
-    const int64_t n = (int64_t)blockIdx.x * BWD_THREADS + threadIdx.x;
-    if (n >= a.N) return;
-    if (!a.accumulate) {
-        // Rows that are culled, or whose cotangents are all exactly zero (occluded: compositing never reached them),
-        // have zero gradients: write the zeros and skip the parameter loads and the arithmetic.
-        bool live = false;
-        for (int c = 0; c < a.C && !live; ++c) {
+__global__ void __launch_bounds__(256) bwd_classify_kernel(const b2s_project_bwd_args a, bool with_sh, BwdCounts* cnt,
+                                                           int32_t* __restrict__ list_geom, int32_t* __restrict__ list_sh) {
+    const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    bool live_g = false, live_s = false;
+    if (n < a.N) {
+        for (int c = 0; c < a.C; ++c) {
             const int64_t i = (int64_t)c * a.N + n;
             if (__ldg(a.radii + i) <= 0) continue;
-            if (a.v_means2d) { const float2 v = __ldg(reinterpret_cast<const float2*>(a.v_means2d) + i); live |= (v.x != 0.f) | (v.y != 0.f); }
-            if (a.v_conics) live |= (__ldg(a.v_conics + 3 * i) != 0.f) | (__ldg(a.v_conics + 3 * i + 1) != 0.f) | (__ldg(a.v_conics + 3 * i + 2) != 0.f);
-            if (a.v_opacities_out) live |= __ldg(a.v_opacities_out + i) != 0.f;
-            if (a.v_depths) live |= __ldg(a.v_depths + i) != 0.f;
-            if (a.v_compensations) live |= __ldg(a.v_compensations + i) != 0.f;
+            if (a.v_means2d) { const float2 v = __ldg(reinterpret_cast<const float2*>(a.v_means2d) + i); live_g |= (v.x != 0.f) | (v.y != 0.f); }
+            if (a.v_conics) live_g |= (__ldg(a.v_conics + 3 * i) != 0.f) | (__ldg(a.v_conics + 3 * i + 1) != 0.f) | (__ldg(a.v_conics + 3 * i + 2) != 0.f);
+            if (a.v_opacities_out) live_g |= __ldg(a.v_opacities_out + i) != 0.f;
+            if (a.v_depths) live_g |= __ldg(a.v_depths + i) != 0.f;
+            if (a.v_compensations) live_g |= __ldg(a.v_compensations + i) != 0.f;
+            if (with_sh && a.v_colors)
+                live_s |= (__ldg(a.v_colors + 3 * i) != 0.f) | (__ldg(a.v_colors + 3 * i + 1) != 0.f) | (__ldg(a.v_colors + 3 * i + 2) != 0.f);
         }
-        if (!live) {
-            for (int k = 0; k < 3; ++k) { if (!MEANS_ACC) a.v_means[3 * n + k] = 0.f; a.v_scales[3 * n + k] = 0.f; }
-            reinterpret_cast<float4*>(a.v_quats)[n] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (a.v_opacities) a.v_opacities[n] = 0.f;
-            return;
-        }
+        a.v_means[3 * n] = 0.f; a.v_means[3 * n + 1] = 0.f; a.v_means[3 * n + 2] = 0.f;
+        if (a.v_scales) { a.v_scales[3 * n] = 0.f; a.v_scales[3 * n + 1] = 0.f; a.v_scales[3 * n + 2] = 0.f; }
+        if (a.v_quats) reinterpret_cast<float4*>(a.v_quats)[n] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (a.v_opacities) a.v_opacities[n] = 0.f;
     }
+    const unsigned lt = (1u << lane) - 1u;
+    const unsigned bg = __ballot_sync(FULL, live_g), bs = __ballot_sync(FULL, live_s);
+    unsigned base_g = 0, base_s = 0;
+    if (lane == 0) {
+        if (bg) base_g = atomicAdd(&cnt->n_geom, (unsigned)__popc(bg));
+        if (bs) base_s = atomicAdd(&cnt->n_sh, (unsigned)__popc(bs));
+    }
+    base_g = __shfl_sync(FULL, base_g, 0); base_s = __shfl_sync(FULL, base_s, 0);
+    if (live_g) list_geom[base_g + __popc(bg & lt)] = (int32_t)n;
+    if (live_s) list_sh[base_s + __popc(bs & lt)] = (int32_t)n;
+}
+
+__global__ void __launch_bounds__(256) sh_zero_kernel(const b2s_project_bwd_args a, const BwdCounts* cnt) {
+    if (!bwd_sparse(cnt->n_sh, a.N)) return;
+    const int64_t total = a.N * a.sh_stride_k * 3;            // floats; the tensor is 16-byte aligned and a multiple of 4 here
+    float4* o = reinterpret_cast<float4*>(a.v_sh_coeffs);
+    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total / 4; i += (int64_t)gridDim.x * blockDim.x)
+        stg_stream4(o + i, z);
+    if (blockIdx.x == 0 && threadIdx.x < (total & 3)) a.v_sh_coeffs[(total & ~(int64_t)3) + threadIdx.x] = 0.f;
+}
+
+// one thread per live row: SH colour VJP straight from / to global memory (few rows: no staging needed)
+__global__ void __launch_bounds__(128) sh_sparse_kernel(const b2s_project_bwd_args a, const BwdCounts* cnt,
+                                                        const int32_t* __restrict__ list_sh) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    Camera* cams = reinterpret_cast<Camera*>(smem_raw);
+    if (!bwd_sparse(cnt->n_sh, a.N)) return;
+    load_cameras(cams, a.C, a.viewmats, a.Ks, a.campos, (float)a.width, (float)a.height);
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (int64_t)cnt->n_sh) return;
+    const int64_t n = list_sh[idx];
+    const int K = (a.sh_degree + 1) * (a.sh_degree + 1);
+    const float* cf = a.sh_coeffs + n * a.sh_stride_k * 3;
+    float* out = a.v_sh_coeffs + n * a.sh_stride_k * 3;
+    const float mx = __ldg(a.means + 3 * n), my = __ldg(a.means + 3 * n + 1), mz = __ldg(a.means + 3 * n + 2);
+    float v_mean[3] = {0.f, 0.f, 0.f};
+    bool first = true;
+    for (int c = 0; c < a.C; ++c) {
+        const int64_t i = (int64_t)c * a.N + n;
+        if (__ldg(a.radii + i) <= 0) continue;
+        const float g0 = __ldg(a.v_colors + 3 * i), g1 = __ldg(a.v_colors + 3 * i + 1), g2 = __ldg(a.v_colors + 3 * i + 2);
+        if (g0 == 0.f && g1 == 0.f && g2 == 0.f) continue;
+        const float dx = mx - cams[c].campos[0], dy = my - cams[c].campos[1], dz = mz - cams[c].campos[2];
+        const float inv = 1.f / fmaxf(sqrtf(dx * dx + dy * dy + dz * dz), 1e-12f);
+        const float ux = dx * inv, uy = dy * inv, uz = dz * inv;
+        float Y[16], w[16];
+        sh_basis(a.sh_degree, ux, uy, uz, Y);
+        float cr = 0.5f, cg = 0.5f, cb = 0.5f;
+        for (int k = 0; k < K; ++k) { cr += Y[k] * __ldg(cf + 3 * k); cg += Y[k] * __ldg(cf + 3 * k + 1); cb += Y[k] * __ldg(cf + 3 * k + 2); }
+        const float vr = cr > 0.f ? g0 : 0.f, vg = cg > 0.f ? g1 : 0.f, vb = cb > 0.f ? g2 : 0.f;   // clamp_min(., 0) gate
+        for (int k = 0; k < K; ++k) {
+            w[k] = __ldg(cf + 3 * k) * vr + __ldg(cf + 3 * k + 1) * vg + __ldg(cf + 3 * k + 2) * vb;
+            if (first) { out[3 * k] = Y[k] * vr; out[3 * k + 1] = Y[k] * vg; out[3 * k + 2] = Y[k] * vb; }
+            else { out[3 * k] += Y[k] * vr; out[3 * k + 1] += Y[k] * vg; out[3 * k + 2] += Y[k] * vb; }
+        }
+        first = false;
+        float vx, vy, vz;
+        sh_basis_vjp(a.sh_degree, ux, uy, uz, w, vx, vy, vz);
+        const float dp = ux * vx + uy * vy + uz * vz;
+        v_mean[0] += (vx - ux * dp) * inv; v_mean[1] += (vy - uy * dp) * inv; v_mean[2] += (vz - uz * dp) * inv;
+    }
+    a.v_means[3 * n] += v_mean[0]; a.v_means[3 * n + 1] += v_mean[1]; a.v_means[3 * n + 2] += v_mean[2];   // zero-filled by classify
+}
+
+// projection VJP of one Gaussian over the call's cameras (shared by the dense and the list-driven kernel)
+__device__ __forceinline__ bool project_bwd_row(const b2s_project_bwd_args& a, const Camera* cams, int64_t n, float (&v_mean)[3],
+                                                float (&v_quat)[4], float (&v_scale)[3], float& v_opac) {
     float mean[3], q[4], s[3];
     mean[0] = __ldg(a.means + 3 * n); mean[1] = __ldg(a.means + 3 * n + 1); mean[2] = __ldg(a.means + 3 * n + 2);
     {
@@ -356,9 +477,9 @@ __global__ void __launch_bounds__(BWD_THREADS) project_bwd_kernel(const b2s_proj
     quat_to_rotmat(q, R, qn, qnorm);
     covar_from_rot_scale(R, s, M, S);
 
-    float v_mean[3] = {0.f, 0.f, 0.f};
+    v_mean[0] = v_mean[1] = v_mean[2] = 0.f;
     Sym3 v_S = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    float v_opac = 0.f;
+    v_opac = 0.f;
     bool any = false;
     for (int c = 0; c < a.C; ++c) {
         const int64_t i = (int64_t)c * a.N + n;
@@ -384,8 +505,47 @@ __global__ void __launch_bounds__(BWD_THREADS) project_bwd_kernel(const b2s_proj
         }
         project_one_bwd(cams[c], mean, S, a.eps2d, mid, g, v_mean, v_S);
     }
-    float v_quat[4] = {0.f, 0.f, 0.f, 0.f}, v_scale[3] = {0.f, 0.f, 0.f};
+    v_quat[0] = v_quat[1] = v_quat[2] = v_quat[3] = 0.f;
+    v_scale[0] = v_scale[1] = v_scale[2] = 0.f;
     if (any) covar_bwd(q, qn, qnorm, R, s, M, v_S, v_quat, v_scale);
+    return any;
+}
+
+// =================================================================================================
+// backward, part 2: projection VJP (little traffic, heavy arithmetic)
+// =================================================================================================
+template <bool MEANS_ACC>   // MEANS_ACC: v_means already holds the SH part (or an earlier camera chunk)
+__global__ void __launch_bounds__(BWD_THREADS) project_bwd_kernel(const b2s_project_bwd_args a, const BwdCounts* cnt) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    Camera* cams = reinterpret_cast<Camera*>(smem_raw);
+    if (cnt && bwd_sparse(cnt->n_geom, a.N)) return;        // the list-driven kernel does this call's work
+    const float W = (float)a.width, H = (float)a.height;
+    load_cameras(cams, a.C, a.viewmats, a.Ks, a.campos, W, H);
+
+    const int64_t n = (int64_t)blockIdx.x * BWD_THREADS + threadIdx.x;
+    if (n >= a.N) return;
+    if (!a.accumulate) {
+        // Rows that are culled, or whose cotangents are all exactly zero (occluded: compositing never reached them),
+        // have zero gradients: write the zeros and skip the parameter loads and the arithmetic.
+        bool live = false;
+        for (int c = 0; c < a.C && !live; ++c) {
+            const int64_t i = (int64_t)c * a.N + n;
+            if (__ldg(a.radii + i) <= 0) continue;
+            if (a.v_means2d) { const float2 v = __ldg(reinterpret_cast<const float2*>(a.v_means2d) + i); live |= (v.x != 0.f) | (v.y != 0.f); }
+            if (a.v_conics) live |= (__ldg(a.v_conics + 3 * i) != 0.f) | (__ldg(a.v_conics + 3 * i + 1) != 0.f) | (__ldg(a.v_conics + 3 * i + 2) != 0.f);
+            if (a.v_opacities_out) live |= __ldg(a.v_opacities_out + i) != 0.f;
+            if (a.v_depths) live |= __ldg(a.v_depths + i) != 0.f;
+            if (a.v_compensations) live |= __ldg(a.v_compensations + i) != 0.f;
+        }
+        if (!live) {
+            for (int k = 0; k < 3; ++k) { if (!MEANS_ACC) a.v_means[3 * n + k] = 0.f; a.v_scales[3 * n + k] = 0.f; }
+            reinterpret_cast<float4*>(a.v_quats)[n] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (a.v_opacities) a.v_opacities[n] = 0.f;
+            return;
+        }
+    }
+    float v_mean[3], v_quat[4], v_scale[3], v_opac;
+    const bool any = project_bwd_row(a, cams, n, v_mean, v_quat, v_scale, v_opac);
     if (a.accumulate) {
         for (int k = 0; k < 3; ++k) { a.v_means[3 * n + k] += v_mean[k]; a.v_scales[3 * n + k] += v_scale[k]; }
         for (int k = 0; k < 4; ++k) a.v_quats[4 * n + k] += v_quat[k];
@@ -399,6 +559,25 @@ __global__ void __launch_bounds__(BWD_THREADS) project_bwd_kernel(const b2s_proj
         reinterpret_cast<float4*>(a.v_quats)[n] = make_float4(v_quat[0], v_quat[1], v_quat[2], v_quat[3]);
         if (a.v_opacities) a.v_opacities[n] = v_opac;
     }
+}
+
+
+// list-driven projection VJP: one thread per live row (the rest was zero-filled by bwd_classify_kernel)
+__global__ void __launch_bounds__(BWD_THREADS) project_bwd_sparse_kernel(const b2s_project_bwd_args a, const BwdCounts* cnt,
+                                                                        const int32_t* __restrict__ list_geom) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    Camera* cams = reinterpret_cast<Camera*>(smem_raw);
+    if (!bwd_sparse(cnt->n_geom, a.N)) return;
+    load_cameras(cams, a.C, a.viewmats, a.Ks, a.campos, (float)a.width, (float)a.height);
+    const int64_t idx = (int64_t)blockIdx.x * BWD_THREADS + threadIdx.x;
+    if (idx >= (int64_t)cnt->n_geom) return;
+    const int64_t n = list_geom[idx];
+    float v_mean[3], v_quat[4], v_scale[3], v_opac;
+    const bool any = project_bwd_row(a, cams, n, v_mean, v_quat, v_scale, v_opac);
+    if (any) { a.v_means[3 * n] += v_mean[0]; a.v_means[3 * n + 1] += v_mean[1]; a.v_means[3 * n + 2] += v_mean[2]; }
+    a.v_scales[3 * n] = v_scale[0]; a.v_scales[3 * n + 1] = v_scale[1]; a.v_scales[3 * n + 2] = v_scale[2];
+    reinterpret_cast<float4*>(a.v_quats)[n] = make_float4(v_quat[0], v_quat[1], v_quat[2], v_quat[3]);
+    if (a.v_opacities) a.v_opacities[n] = v_opac;
 }
 
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
@@ -434,6 +613,10 @@ extern "C" int b2s_project_fwd(const b2s_project_fwd_args* a, b2s_stream_t strea
     return 0;
 }
 
+extern "C" int64_t b2s_project_bwd_workspace_bytes(int64_t N) {
+    return 256 + 2 * ((N + 63) / 64) * 64 * (int64_t)sizeof(int32_t);
+}
+
 extern "C" int b2s_project_bwd(const b2s_project_bwd_args* a, b2s_stream_t stream) {
     B2S_REQUIRE(a != nullptr, "null args");
     B2S_REQUIRE(a->N >= 0 && a->C >= 0, "negative size");
@@ -445,8 +628,30 @@ extern "C" int b2s_project_bwd(const b2s_project_bwd_args* a, b2s_stream_t strea
     B2S_REQUIRE(a->stages >= 0 && a->stages <= 2, "stages must be 0, 1 or 2");
     const bool sh = a->sh_coeffs != nullptr && a->v_sh_coeffs != nullptr && a->stages != 2;
     const bool geom = a->stages != 1;
+    const bool has_sh = a->sh_coeffs != nullptr && a->v_sh_coeffs != nullptr;
     cudaStream_t st = (cudaStream_t)stream;
     const size_t cam_bytes = ((a->C * sizeof(Camera) + 15) / 16) * 16;
+    // sparse mode: needs the caller's workspace, a single camera chunk, and (for the streaming zero fill) an aligned v_sh
+    BwdCounts* cnt = nullptr;
+    int32_t *list_geom = nullptr, *list_sh = nullptr;
+    if (a->workspace && !a->accumulate && a->N < 2147483647LL && a->v_quats && a->v_scales) {
+        if (a->workspace_bytes < b2s_project_bwd_workspace_bytes(a->N)) {
+            set_error("b2s_project_bwd: workspace too small");
+            return B2S_E_WORKSPACE;
+        }
+        B2S_REQUIRE((reinterpret_cast<uintptr_t>(a->workspace) & 255u) == 0, "workspace must be 256-byte aligned");
+        if (!has_sh || aligned16(a->v_sh_coeffs)) {
+            cnt = reinterpret_cast<BwdCounts*>(a->workspace);
+            list_geom = reinterpret_cast<int32_t*>(reinterpret_cast<char*>(a->workspace) + 256);
+            list_sh = list_geom + ((a->N + 63) / 64) * 64;
+        }
+    }
+    if (cnt && (a->stages != 2 || !has_sh)) {
+        // first (or only) call of this backward: zero the small gradients, build the two lists
+        B2S_CUDA(cudaMemsetAsync(cnt, 0, sizeof(BwdCounts), st));
+        bwd_classify_kernel<<<(unsigned)cdiv(a->N, 256), 256, 0, st>>>(*a, has_sh, cnt, list_geom, list_sh);
+        B2S_LAUNCH_CHECK();
+    }
     if (sh) {
         B2S_REQUIRE(a->sh_degree >= 0 && a->sh_degree <= 3, "sh_degree must be 0..3");
         const int K = (a->sh_degree + 1) * (a->sh_degree + 1);
@@ -457,15 +662,25 @@ extern "C" int b2s_project_bwd(const b2s_project_bwd_args* a, b2s_stream_t strea
         auto kern = vec ? (multi ? sh_bwd_fused_kernel<16, true> : sh_bwd_fused_kernel<16, false>)
                         : (multi ? sh_bwd_fused_kernel<0, true> : sh_bwd_fused_kernel<0, false>);
         B2S_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kern<<<(unsigned)cdiv(a->N, SHB_THREADS), SHB_THREADS, smem, st>>>(*a);
+        kern<<<(unsigned)cdiv(a->N, SHB_THREADS), SHB_THREADS, smem, st>>>(*a, cnt);
         B2S_LAUNCH_CHECK();
+        if (cnt) {
+            sh_zero_kernel<<<148 * 8, 256, 0, st>>>(*a, cnt);
+            B2S_LAUNCH_CHECK();
+            sh_sparse_kernel<<<(unsigned)cdiv(cdiv(a->N, 4), 128), 128, cam_bytes, st>>>(*a, cnt, list_sh);
+            B2S_LAUNCH_CHECK();
+        }
     }
     if (geom) {
         // stages == 2 with the SH pointers set: the SH part is already in v_means (an earlier stages == 1 call)
-        const bool means_acc = a->sh_coeffs != nullptr && a->v_sh_coeffs != nullptr;
+        const bool means_acc = has_sh;
         auto kern2 = means_acc ? project_bwd_kernel<true> : project_bwd_kernel<false>;
-        kern2<<<(unsigned)cdiv(a->N, BWD_THREADS), BWD_THREADS, cam_bytes, st>>>(*a);
+        kern2<<<(unsigned)cdiv(a->N, BWD_THREADS), BWD_THREADS, cam_bytes, st>>>(*a, cnt);
         B2S_LAUNCH_CHECK();
+        if (cnt) {
+            project_bwd_sparse_kernel<<<(unsigned)cdiv(cdiv(a->N, 4), BWD_THREADS), BWD_THREADS, cam_bytes, st>>>(*a, cnt, list_geom);
+            B2S_LAUNCH_CHECK();
+        }
     }
     return 0;
 }

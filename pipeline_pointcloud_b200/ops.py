@@ -11,6 +11,7 @@ Train-Stage1 component makes through ``ns-train splatfacto``
 from __future__ import annotations
 
 import ctypes
+import os
 from typing import Optional, Tuple
 
 import torch
@@ -164,6 +165,10 @@ class _ProjectFused(torch.autograd.Function):
             v_sh = torch.empty_like(sh_coeffs) if K == sh_coeffs.shape[1] else torch.zeros_like(sh_coeffs)
         lib = L.lib()
         st = L.stream_ptr(dev)
+        # scratch for the sparse backward (rows with all-zero cotangents are filtered once; include/b2s.h)
+        ws = None
+        if C <= MAX_CAMS and os.environ.get("B2S_SPARSE_BWD", "1") != "0":
+            ws = torch.empty(int(lib.b2s_project_bwd_workspace_bytes(N)), dtype=torch.uint8, device=dev)
 
         def sl(t, c0, c1):
             return ptr(t[c0:c1]) if t is not None else None
@@ -182,15 +187,16 @@ class _ProjectFused(torch.autograd.Function):
                     v_compensations=sl(v_comps, c0, c1), v_opacities_out=sl(v_opac_out, c0, c1),
                     v_colors=sl(v_colors, c0, c1), accumulate=int(c0 > 0),
                     v_means=ptr(v_means), v_quats=ptr(v_quats), v_scales=ptr(v_scales), v_opacities=ptr(v_opac),
-                    v_sh_coeffs=ptr(v_sh), stages=stages)
+                    v_sh_coeffs=ptr(v_sh), stages=stages, workspace=ptr(ws), workspace_bytes=ws.numel() if ws is not None else 0)
 
-            if with_sh and TIMER is not None:     # time the two kernels of the call separately (bench.py)
-                with _stage("sh_bwd"):
+            sparse = ws is not None and c0 == 0      # kernels launched: + classify, zero fill and the two list-driven ones
+            if with_sh and TIMER is not None:     # time the two stages of the call separately (bench.py)
+                with _stage("sh_bwd", launches=4 if sparse else 1):
                     check(lib.b2s_project_bwd(ctypes.byref(args(1)), st), "b2s_project_bwd")
-                with _stage("project_bwd"):
+                with _stage("project_bwd", launches=2 if sparse else 1):
                     check(lib.b2s_project_bwd(ctypes.byref(args(2)), st), "b2s_project_bwd")
             else:
-                with _stage("project_bwd", launches=2 if with_sh else 1):
+                with _stage("project_bwd", launches=(6 if with_sh else 3) if sparse else (2 if with_sh else 1)):
                     check(lib.b2s_project_bwd(ctypes.byref(args(0)), st), "b2s_project_bwd")
         return (v_means, v_quats, v_scales, v_opac, v_sh) + (None,) * 13
 
