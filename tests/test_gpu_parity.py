@@ -328,3 +328,32 @@ def test_full_size_properties(b2s):
         rp, alp, mp = call(b2s.rasterization, g, W, H, sh_degree=3, packed=True, rasterize_mode="antialiased")
         assert torch.equal(r, rp) and torch.equal(al, alp)                        # packed == dense, bit for bit
         assert mp["means2d"].shape[0] == int((m["radii"] > 0).sum())
+
+
+# ----------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("C,deg", [(1, 3), (2, 3), (1, 1), (1, None)])
+def test_sparse_backward_equals_dense_backward(b2s, monkeypatch, C, deg):
+    """A saturated scene: most visible rows come back with all-zero cotangents, so the backward of stage 1 switches (on
+    the device) to the zero fill + list-driven kernels; the gradients must equal the dense kernels' (B2S_SPARSE_BWD=0)."""
+    N, W, H = 60000, 96, 64
+    a = scene_args(N, 3, C, W, H, seed=17)
+    a["scales"] *= 3.0
+    a["opacities"] = a["opacities"].clamp_min(0.6)
+    gen = torch.Generator().manual_seed(2)
+    v_r, v_a = torch.rand(C, H, W, 3, generator=gen).cuda(), torch.rand(C, H, W, 1, generator=gen).cuda()
+    out = {}
+    for mode in ("1", "0"):
+        monkeypatch.setenv("B2S_SPARSE_BWD", mode)
+        g = {k: (v.cuda().requires_grad_() if k in LEAVES else v.cuda()) for k, v in a.items()}
+        cols = g["colors"] if deg is not None else g["colors"][:, 0, :].detach().clone().requires_grad_()
+        r, al, m = b2s.rasterization(g["means"], g["quats"], g["scales"], g["opacities"], cols, g["viewmats"], g["Ks"], W, H,
+                                     sh_degree=deg, packed=False, rasterize_mode="antialiased")
+        m["opacities"].retain_grad()
+        torch.autograd.backward([r, al], [v_r, v_a])
+        live = (m["opacities"].grad != 0).float().sum().item() / N
+        assert live < 0.25, live                                  # the sparse mode really is the one taken
+        out[mode] = [g[k].grad for k in ("means", "quats", "scales", "opacities")] + [cols.grad]
+    for name, x, y in zip(("means", "quats", "scales", "opacities", "colors"), out["1"], out["0"]):
+        assert x.shape == y.shape
+        assert ((x == 0) == (y == 0)).all(), name                 # the same rows are touched
+        assert grad_report(x, y)[0] < 1e-5, name
