@@ -374,38 +374,55 @@ __global__ void __launch_bounds__(SHB_THREADS, 4) sh_bwd_fused_kernel(const b2s_
 // The choice is made on the device from the list lengths: no host round trip.
 // =================================================================================================
 
+constexpr int CLS_ROWS = 4;      // rows per thread: 1024 rows per CTA, ONE global atomic per CTA and list (same-address
+                                 // atomics serialise in L2: one per warp cost 0.18 ms at 5.8 M rows)
 __global__ void __launch_bounds__(256) bwd_classify_kernel(const b2s_project_bwd_args a, bool with_sh, BwdCounts* cnt,
                                                            int32_t* __restrict__ list_geom, int32_t* __restrict__ list_sh) {
-    const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int lane = threadIdx.x & 31;
-    bool live_g = false, live_s = false;
-    if (n < a.N) {
-        for (int c = 0; c < a.C; ++c) {
-            const int64_t i = (int64_t)c * a.N + n;
-            if (__ldg(a.radii + i) <= 0) continue;
-            if (a.v_means2d) { const float2 v = __ldg(reinterpret_cast<const float2*>(a.v_means2d) + i); live_g |= (v.x != 0.f) | (v.y != 0.f); }
-            if (a.v_conics) live_g |= (__ldg(a.v_conics + 3 * i) != 0.f) | (__ldg(a.v_conics + 3 * i + 1) != 0.f) | (__ldg(a.v_conics + 3 * i + 2) != 0.f);
-            if (a.v_opacities_out) live_g |= __ldg(a.v_opacities_out + i) != 0.f;
-            if (a.v_depths) live_g |= __ldg(a.v_depths + i) != 0.f;
-            if (a.v_compensations) live_g |= __ldg(a.v_compensations + i) != 0.f;
-            if (with_sh && a.v_colors)
-                live_s |= (__ldg(a.v_colors + 3 * i) != 0.f) | (__ldg(a.v_colors + 3 * i + 1) != 0.f) | (__ldg(a.v_colors + 3 * i + 2) != 0.f);
+    __shared__ unsigned s_g[CLS_ROWS * 8 + 1], s_s[CLS_ROWS * 8 + 1];      // per (k, warp) counts -> exclusive prefix
+    __shared__ unsigned s_base[2];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned bg[CLS_ROWS], bs[CLS_ROWS];
+    bool lg[CLS_ROWS], ls[CLS_ROWS];
+#pragma unroll
+    for (int k = 0; k < CLS_ROWS; ++k) {
+        const int64_t n = ((int64_t)blockIdx.x * CLS_ROWS + k) * 256 + threadIdx.x;
+        bool live_g = false, live_s = false;
+        if (n < a.N) {
+            for (int c = 0; c < a.C; ++c) {
+                const int64_t i = (int64_t)c * a.N + n;
+                if (__ldg(a.radii + i) <= 0) continue;
+                if (a.v_means2d) { const float2 v = __ldg(reinterpret_cast<const float2*>(a.v_means2d) + i); live_g |= (v.x != 0.f) | (v.y != 0.f); }
+                if (a.v_conics) live_g |= (__ldg(a.v_conics + 3 * i) != 0.f) | (__ldg(a.v_conics + 3 * i + 1) != 0.f) | (__ldg(a.v_conics + 3 * i + 2) != 0.f);
+                if (a.v_opacities_out) live_g |= __ldg(a.v_opacities_out + i) != 0.f;
+                if (a.v_depths) live_g |= __ldg(a.v_depths + i) != 0.f;
+                if (a.v_compensations) live_g |= __ldg(a.v_compensations + i) != 0.f;
+                if (with_sh && a.v_colors)
+                    live_s |= (__ldg(a.v_colors + 3 * i) != 0.f) | (__ldg(a.v_colors + 3 * i + 1) != 0.f) | (__ldg(a.v_colors + 3 * i + 2) != 0.f);
+            }
+            a.v_means[3 * n] = 0.f; a.v_means[3 * n + 1] = 0.f; a.v_means[3 * n + 2] = 0.f;
+            if (a.v_scales) { a.v_scales[3 * n] = 0.f; a.v_scales[3 * n + 1] = 0.f; a.v_scales[3 * n + 2] = 0.f; }
+            if (a.v_quats) reinterpret_cast<float4*>(a.v_quats)[n] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (a.v_opacities) a.v_opacities[n] = 0.f;
         }
-        a.v_means[3 * n] = 0.f; a.v_means[3 * n + 1] = 0.f; a.v_means[3 * n + 2] = 0.f;
-        if (a.v_scales) { a.v_scales[3 * n] = 0.f; a.v_scales[3 * n + 1] = 0.f; a.v_scales[3 * n + 2] = 0.f; }
-        if (a.v_quats) reinterpret_cast<float4*>(a.v_quats)[n] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (a.v_opacities) a.v_opacities[n] = 0.f;
+        lg[k] = live_g; ls[k] = live_s;
+        bg[k] = __ballot_sync(FULL, live_g); bs[k] = __ballot_sync(FULL, live_s);
+        if (lane == 0) { s_g[k * 8 + warp] = __popc(bg[k]); s_s[k * 8 + warp] = __popc(bs[k]); }
     }
+    __syncthreads();
+    if (threadIdx.x < 2) {
+        unsigned* c = threadIdx.x == 0 ? s_g : s_s;
+        unsigned run = 0;
+        for (int j = 0; j < CLS_ROWS * 8; ++j) { const unsigned v = c[j]; c[j] = run; run += v; }
+        s_base[threadIdx.x] = run ? atomicAdd(threadIdx.x == 0 ? &cnt->n_geom : &cnt->n_sh, run) : 0u;
+    }
+    __syncthreads();
     const unsigned lt = (1u << lane) - 1u;
-    const unsigned bg = __ballot_sync(FULL, live_g), bs = __ballot_sync(FULL, live_s);
-    unsigned base_g = 0, base_s = 0;
-    if (lane == 0) {
-        if (bg) base_g = atomicAdd(&cnt->n_geom, (unsigned)__popc(bg));
-        if (bs) base_s = atomicAdd(&cnt->n_sh, (unsigned)__popc(bs));
+#pragma unroll
+    for (int k = 0; k < CLS_ROWS; ++k) {
+        const int64_t n = ((int64_t)blockIdx.x * CLS_ROWS + k) * 256 + threadIdx.x;
+        if (lg[k]) list_geom[s_base[0] + s_g[k * 8 + warp] + __popc(bg[k] & lt)] = (int32_t)n;
+        if (ls[k]) list_sh[s_base[1] + s_s[k * 8 + warp] + __popc(bs[k] & lt)] = (int32_t)n;
     }
-    base_g = __shfl_sync(FULL, base_g, 0); base_s = __shfl_sync(FULL, base_s, 0);
-    if (live_g) list_geom[base_g + __popc(bg & lt)] = (int32_t)n;
-    if (live_s) list_sh[base_s + __popc(bs & lt)] = (int32_t)n;
 }
 
 __global__ void __launch_bounds__(256) sh_zero_kernel(const b2s_project_bwd_args a, const BwdCounts* cnt) {
@@ -418,47 +435,78 @@ __global__ void __launch_bounds__(256) sh_zero_kernel(const b2s_project_bwd_args
     if (blockIdx.x == 0 && threadIdx.x < (total & 3)) a.v_sh_coeffs[(total & ~(int64_t)3) + threadIdx.x] = 0.f;
 }
 
-// one thread per live row: SH colour VJP straight from / to global memory (few rows: no staging needed)
+// one thread per live row: SH colour VJP straight from / to global memory (few rows: no staging needed).
+// VEC: degree 3, 16-byte aligned rows of 48 floats -> twelve 128-bit loads and stores per row.
+template <bool VEC>
 __global__ void __launch_bounds__(128) sh_sparse_kernel(const b2s_project_bwd_args a, const BwdCounts* cnt,
                                                         const int32_t* __restrict__ list_sh) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     Camera* cams = reinterpret_cast<Camera*>(smem_raw);
     if (!bwd_sparse(cnt->n_sh, a.N)) return;
     load_cameras(cams, a.C, a.viewmats, a.Ks, a.campos, (float)a.width, (float)a.height);
-    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= (int64_t)cnt->n_sh) return;
-    const int64_t n = list_sh[idx];
     const int K = (a.sh_degree + 1) * (a.sh_degree + 1);
-    const float* cf = a.sh_coeffs + n * a.sh_stride_k * 3;
-    float* out = a.v_sh_coeffs + n * a.sh_stride_k * 3;
-    const float mx = __ldg(a.means + 3 * n), my = __ldg(a.means + 3 * n + 1), mz = __ldg(a.means + 3 * n + 2);
-    float v_mean[3] = {0.f, 0.f, 0.f};
-    bool first = true;
-    for (int c = 0; c < a.C; ++c) {
-        const int64_t i = (int64_t)c * a.N + n;
-        if (__ldg(a.radii + i) <= 0) continue;
-        const float g0 = __ldg(a.v_colors + 3 * i), g1 = __ldg(a.v_colors + 3 * i + 1), g2 = __ldg(a.v_colors + 3 * i + 2);
-        if (g0 == 0.f && g1 == 0.f && g2 == 0.f) continue;
-        const float dx = mx - cams[c].campos[0], dy = my - cams[c].campos[1], dz = mz - cams[c].campos[2];
-        const float inv = 1.f / fmaxf(sqrtf(dx * dx + dy * dy + dz * dz), 1e-12f);
-        const float ux = dx * inv, uy = dy * inv, uz = dz * inv;
-        float Y[16], w[16];
-        sh_basis(a.sh_degree, ux, uy, uz, Y);
-        float cr = 0.5f, cg = 0.5f, cb = 0.5f;
-        for (int k = 0; k < K; ++k) { cr += Y[k] * __ldg(cf + 3 * k); cg += Y[k] * __ldg(cf + 3 * k + 1); cb += Y[k] * __ldg(cf + 3 * k + 2); }
-        const float vr = cr > 0.f ? g0 : 0.f, vg = cg > 0.f ? g1 : 0.f, vb = cb > 0.f ? g2 : 0.f;   // clamp_min(., 0) gate
-        for (int k = 0; k < K; ++k) {
-            w[k] = __ldg(cf + 3 * k) * vr + __ldg(cf + 3 * k + 1) * vg + __ldg(cf + 3 * k + 2) * vb;
-            if (first) { out[3 * k] = Y[k] * vr; out[3 * k + 1] = Y[k] * vg; out[3 * k + 2] = Y[k] * vb; }
-            else { out[3 * k] += Y[k] * vr; out[3 * k + 1] += Y[k] * vg; out[3 * k + 2] += Y[k] * vb; }
+    const int64_t total = cnt->n_sh;
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t n = list_sh[idx];
+        const float* cf = a.sh_coeffs + n * a.sh_stride_k * 3;
+        float* out = a.v_sh_coeffs + n * a.sh_stride_k * 3;
+        float co[48], acc[48];
+        if (VEC) {
+#pragma unroll
+            for (int q = 0; q < 12; ++q) {
+                const float4 v = ldg_stream4(reinterpret_cast<const float4*>(cf) + q);
+                co[4 * q] = v.x; co[4 * q + 1] = v.y; co[4 * q + 2] = v.z; co[4 * q + 3] = v.w;
+            }
+#pragma unroll
+            for (int e = 0; e < 48; ++e) acc[e] = 0.f;
         }
-        first = false;
-        float vx, vy, vz;
-        sh_basis_vjp(a.sh_degree, ux, uy, uz, w, vx, vy, vz);
-        const float dp = ux * vx + uy * vy + uz * vz;
-        v_mean[0] += (vx - ux * dp) * inv; v_mean[1] += (vy - uy * dp) * inv; v_mean[2] += (vz - uz * dp) * inv;
+        const float mx = __ldg(a.means + 3 * n), my = __ldg(a.means + 3 * n + 1), mz = __ldg(a.means + 3 * n + 2);
+        float v_mean[3] = {0.f, 0.f, 0.f};
+        bool first = true;
+        for (int c = 0; c < a.C; ++c) {
+            const int64_t i = (int64_t)c * a.N + n;
+            if (__ldg(a.radii + i) <= 0) continue;
+            const float g0 = __ldg(a.v_colors + 3 * i), g1 = __ldg(a.v_colors + 3 * i + 1), g2 = __ldg(a.v_colors + 3 * i + 2);
+            if (g0 == 0.f && g1 == 0.f && g2 == 0.f) continue;
+            const float dx = mx - cams[c].campos[0], dy = my - cams[c].campos[1], dz = mz - cams[c].campos[2];
+            const float inv = 1.f / fmaxf(sqrtf(dx * dx + dy * dy + dz * dz), 1e-12f);
+            const float ux = dx * inv, uy = dy * inv, uz = dz * inv;
+            float Y[16], w[16];
+            sh_basis(a.sh_degree, ux, uy, uz, Y);
+            float cr = 0.5f, cg = 0.5f, cb = 0.5f;
+            if (VEC) {
+#pragma unroll
+                for (int k = 0; k < 16; ++k) { cr += Y[k] * co[3 * k]; cg += Y[k] * co[3 * k + 1]; cb += Y[k] * co[3 * k + 2]; }
+            } else {
+                for (int k = 0; k < K; ++k) { cr += Y[k] * __ldg(cf + 3 * k); cg += Y[k] * __ldg(cf + 3 * k + 1); cb += Y[k] * __ldg(cf + 3 * k + 2); }
+            }
+            const float vr = cr > 0.f ? g0 : 0.f, vg = cg > 0.f ? g1 : 0.f, vb = cb > 0.f ? g2 : 0.f;   // clamp_min(., 0) gate
+            if (VEC) {
+#pragma unroll
+                for (int k = 0; k < 16; ++k) {
+                    w[k] = co[3 * k] * vr + co[3 * k + 1] * vg + co[3 * k + 2] * vb;
+                    acc[3 * k] += Y[k] * vr; acc[3 * k + 1] += Y[k] * vg; acc[3 * k + 2] += Y[k] * vb;
+                }
+            } else {
+                for (int k = 0; k < K; ++k) {
+                    w[k] = __ldg(cf + 3 * k) * vr + __ldg(cf + 3 * k + 1) * vg + __ldg(cf + 3 * k + 2) * vb;
+                    if (first) { out[3 * k] = Y[k] * vr; out[3 * k + 1] = Y[k] * vg; out[3 * k + 2] = Y[k] * vb; }
+                    else { out[3 * k] += Y[k] * vr; out[3 * k + 1] += Y[k] * vg; out[3 * k + 2] += Y[k] * vb; }
+                }
+            }
+            first = false;
+            float vx, vy, vz;
+            sh_basis_vjp(a.sh_degree, ux, uy, uz, w, vx, vy, vz);
+            const float dp = ux * vx + uy * vy + uz * vz;
+            v_mean[0] += (vx - ux * dp) * inv; v_mean[1] += (vy - uy * dp) * inv; v_mean[2] += (vz - uz * dp) * inv;
+        }
+        if (VEC) {
+#pragma unroll
+            for (int q = 0; q < 12; ++q)
+                stg_stream4(reinterpret_cast<float4*>(out) + q, make_float4(acc[4 * q], acc[4 * q + 1], acc[4 * q + 2], acc[4 * q + 3]));
+        }
+        a.v_means[3 * n] += v_mean[0]; a.v_means[3 * n + 1] += v_mean[1]; a.v_means[3 * n + 2] += v_mean[2];   // zero-filled by classify
     }
-    a.v_means[3 * n] += v_mean[0]; a.v_means[3 * n + 1] += v_mean[1]; a.v_means[3 * n + 2] += v_mean[2];   // zero-filled by classify
 }
 
 // projection VJP of one Gaussian over the call's cameras (shared by the dense and the list-driven kernel)
@@ -562,22 +610,24 @@ __global__ void __launch_bounds__(BWD_THREADS) project_bwd_kernel(const b2s_proj
 }
 
 
-// list-driven projection VJP: one thread per live row (the rest was zero-filled by bwd_classify_kernel)
+// list-driven projection VJP: one thread per live row (the rest was zero-filled by bwd_classify_kernel).  Used whenever
+// the workspace is present, sparse or not: the list keeps 1024-row blocks in ascending order, so loads stay coalesced.
 __global__ void __launch_bounds__(BWD_THREADS) project_bwd_sparse_kernel(const b2s_project_bwd_args a, const BwdCounts* cnt,
                                                                         const int32_t* __restrict__ list_geom) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     Camera* cams = reinterpret_cast<Camera*>(smem_raw);
-    if (!bwd_sparse(cnt->n_geom, a.N)) return;
+    const int64_t total = cnt->n_geom;
+    if ((int64_t)blockIdx.x * BWD_THREADS >= total) return;
     load_cameras(cams, a.C, a.viewmats, a.Ks, a.campos, (float)a.width, (float)a.height);
-    const int64_t idx = (int64_t)blockIdx.x * BWD_THREADS + threadIdx.x;
-    if (idx >= (int64_t)cnt->n_geom) return;
-    const int64_t n = list_geom[idx];
-    float v_mean[3], v_quat[4], v_scale[3], v_opac;
-    const bool any = project_bwd_row(a, cams, n, v_mean, v_quat, v_scale, v_opac);
-    if (any) { a.v_means[3 * n] += v_mean[0]; a.v_means[3 * n + 1] += v_mean[1]; a.v_means[3 * n + 2] += v_mean[2]; }
-    a.v_scales[3 * n] = v_scale[0]; a.v_scales[3 * n + 1] = v_scale[1]; a.v_scales[3 * n + 2] = v_scale[2];
-    reinterpret_cast<float4*>(a.v_quats)[n] = make_float4(v_quat[0], v_quat[1], v_quat[2], v_quat[3]);
-    if (a.v_opacities) a.v_opacities[n] = v_opac;
+    for (int64_t idx = (int64_t)blockIdx.x * BWD_THREADS + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * BWD_THREADS) {
+        const int64_t n = list_geom[idx];
+        float v_mean[3], v_quat[4], v_scale[3], v_opac;
+        const bool any = project_bwd_row(a, cams, n, v_mean, v_quat, v_scale, v_opac);
+        if (any) { a.v_means[3 * n] += v_mean[0]; a.v_means[3 * n + 1] += v_mean[1]; a.v_means[3 * n + 2] += v_mean[2]; }
+        a.v_scales[3 * n] = v_scale[0]; a.v_scales[3 * n + 1] = v_scale[1]; a.v_scales[3 * n + 2] = v_scale[2];
+        reinterpret_cast<float4*>(a.v_quats)[n] = make_float4(v_quat[0], v_quat[1], v_quat[2], v_quat[3]);
+        if (a.v_opacities) a.v_opacities[n] = v_opac;
+    }
 }
 
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
@@ -649,7 +699,7 @@ extern "C" int b2s_project_bwd(const b2s_project_bwd_args* a, b2s_stream_t strea
     if (cnt && (a->stages != 2 || !has_sh)) {
         // first (or only) call of this backward: zero the small gradients, build the two lists
         B2S_CUDA(cudaMemsetAsync(cnt, 0, sizeof(BwdCounts), st));
-        bwd_classify_kernel<<<(unsigned)cdiv(a->N, 256), 256, 0, st>>>(*a, has_sh, cnt, list_geom, list_sh);
+        bwd_classify_kernel<<<(unsigned)cdiv(a->N, 256 * CLS_ROWS), 256, 0, st>>>(*a, has_sh, cnt, list_geom, list_sh);
         B2S_LAUNCH_CHECK();
     }
     if (sh) {
@@ -665,22 +715,25 @@ extern "C" int b2s_project_bwd(const b2s_project_bwd_args* a, b2s_stream_t strea
         kern<<<(unsigned)cdiv(a->N, SHB_THREADS), SHB_THREADS, smem, st>>>(*a, cnt);
         B2S_LAUNCH_CHECK();
         if (cnt) {
-            sh_zero_kernel<<<148 * 8, 256, 0, st>>>(*a, cnt);
+            sh_zero_kernel<<<148 * 32, 256, 0, st>>>(*a, cnt);
             B2S_LAUNCH_CHECK();
-            sh_sparse_kernel<<<(unsigned)cdiv(cdiv(a->N, 4), 128), 128, cam_bytes, st>>>(*a, cnt, list_sh);
+            const unsigned grid = (unsigned)min((int64_t)148 * 16, cdiv(cdiv(a->N, 4), 128));
+            if (vec) sh_sparse_kernel<true><<<grid, 128, cam_bytes, st>>>(*a, cnt, list_sh);
+            else sh_sparse_kernel<false><<<grid, 128, cam_bytes, st>>>(*a, cnt, list_sh);
             B2S_LAUNCH_CHECK();
         }
     }
     if (geom) {
         // stages == 2 with the SH pointers set: the SH part is already in v_means (an earlier stages == 1 call)
         const bool means_acc = has_sh;
-        auto kern2 = means_acc ? project_bwd_kernel<true> : project_bwd_kernel<false>;
-        kern2<<<(unsigned)cdiv(a->N, BWD_THREADS), BWD_THREADS, cam_bytes, st>>>(*a, cnt);
-        B2S_LAUNCH_CHECK();
-        if (cnt) {
-            project_bwd_sparse_kernel<<<(unsigned)cdiv(cdiv(a->N, 4), BWD_THREADS), BWD_THREADS, cam_bytes, st>>>(*a, cnt, list_geom);
-            B2S_LAUNCH_CHECK();
+        if (cnt) {      // the small gradients are zero-filled and the live rows listed: one list-driven kernel, whatever the density
+            project_bwd_sparse_kernel<<<(unsigned)min((int64_t)148 * 16, cdiv(a->N, BWD_THREADS)), BWD_THREADS, cam_bytes, st>>>(
+                *a, cnt, list_geom);
+        } else {
+            auto kern2 = means_acc ? project_bwd_kernel<true> : project_bwd_kernel<false>;
+            kern2<<<(unsigned)cdiv(a->N, BWD_THREADS), BWD_THREADS, cam_bytes, st>>>(*a, nullptr);
         }
+        B2S_LAUNCH_CHECK();
     }
     return 0;
 }

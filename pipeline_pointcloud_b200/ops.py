@@ -193,10 +193,10 @@ class _ProjectFused(torch.autograd.Function):
             if with_sh and TIMER is not None:     # time the two stages of the call separately (bench.py)
                 with _stage("sh_bwd", launches=4 if sparse else 1):
                     check(lib.b2s_project_bwd(ctypes.byref(args(1)), st), "b2s_project_bwd")
-                with _stage("project_bwd", launches=2 if sparse else 1):
+                with _stage("project_bwd", launches=1):
                     check(lib.b2s_project_bwd(ctypes.byref(args(2)), st), "b2s_project_bwd")
             else:
-                with _stage("project_bwd", launches=(6 if with_sh else 3) if sparse else (2 if with_sh else 1)):
+                with _stage("project_bwd", launches=(5 if with_sh else 2) if sparse else (2 if with_sh else 1)):
                     check(lib.b2s_project_bwd(ctypes.byref(args(0)), st), "b2s_project_bwd")
         return (v_means, v_quats, v_scales, v_opac, v_sh) + (None,) * 13
 
