@@ -40,10 +40,8 @@ WORKLOADS = {
 }
 METRIC = "3DGS rasterization fwd+bwd throughput"
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture (profiles/), config 3
-NCU_TRAFFIC = {   # profiles/r01_ncu_full_v6_summary.md
-    "project_fwd": 1_628_177_000,   # 1.313962 GB read + 0.314215 GB written
-    "sh_bwd": 1_382_513_000,        # 0.226162 GB read + 1.156351 GB written
-    "project_bwd": 397_205_000,     # 0.244680 GB read + 0.152525 GB written
+NCU_TRAFFIC = {   # profiles/r01_ncu_full_v6_summary.md; launch list with DRAM bytes: profiles/r01_launches_v12.csv
+    "project_fwd": 1_628_177_000,   # 1.313962 GB read + 0.314215 GB written (v12 launch list: 1.310 + 0.300)
 }
 UNIT = "Mpix/s"
 
