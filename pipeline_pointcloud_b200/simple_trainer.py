@@ -10,8 +10,8 @@ opacities [N] (logit), sh0 [N,1,3], shN [N,K-1,3]}}`` (source/container/src/pipe
 
 Every iteration runs on this package's kernels: ``rasterization()`` forward + backward, the fused L1+SSIM loss and the
 fused (Selective)Adam update.  Densification follows gsplat's ``DefaultStrategy`` (clone / split / prune / opacity
-reset) with torch tensor ops -- it runs every 100th step and is not on the per-iteration hot path.  ``mcmc`` is not
-implemented (raises).  Multi-GPU: launch under torchrun; Gaussians are sharded over the ranks and every rank renders its
+reset) and ``MCMCStrategy`` (relocation, 5 % growth, position noise) with torch tensor ops -- they run every 100th step
+and are not on the per-iteration hot path.  Multi-GPU: launch under torchrun; Gaussians are sharded over the ranks and every rank renders its
 own camera (``rasterization(distributed=True)``), one checkpoint per rank as upstream.
 """
 from __future__ import annotations
@@ -49,16 +49,23 @@ def parse_args(argv: Optional[List[str]] = None) -> argparse.Namespace:
     ap.add_argument("--sh-degree", type=int, default=3)
     ap.add_argument("--sh-degree-interval", type=int, default=1000)
     ap.add_argument("--ssim-lambda", type=float, default=0.2)
-    ap.add_argument("--init-opa", type=float, default=0.1)
-    ap.add_argument("--init-scale", type=float, default=1.0)
+    ap.add_argument("--init-opa", type=float, default=None, help="default 0.1 (default strategy) / 0.5 (mcmc)")
+    ap.add_argument("--init-scale", type=float, default=None, help="default 1.0 (default strategy) / 0.1 (mcmc)")
+    ap.add_argument("--cap-max", type=int, default=1_000_000, help="mcmc: maximum number of Gaussians")
+    ap.add_argument("--opacity-reg", type=float, default=None, help="default 0 / 0.01 (mcmc)")
+    ap.add_argument("--scale-reg", type=float, default=None, help="default 0 / 0.01 (mcmc)")
     ap.add_argument("--antialiased", action="store_true")
     ap.add_argument("--visible-adam", action="store_true")
     ap.add_argument("--save-steps", type=int, nargs="*", default=[7_000, 30_000])
     ap.add_argument("--seed", type=int, default=42)
     ap.add_argument("--log-every", type=int, default=100)
     a = ap.parse_args(argv)
-    if a.strategy == "mcmc":
-        raise NotImplementedError("the mcmc strategy is not implemented; use `default`")
+    # gsplat's two presets (examples/simple_trainer.py: `default` and `mcmc` sub-commands)
+    mcmc = a.strategy == "mcmc"
+    a.init_opa = (0.5 if mcmc else 0.1) if a.init_opa is None else a.init_opa
+    a.init_scale = (0.1 if mcmc else 1.0) if a.init_scale is None else a.init_scale
+    a.opacity_reg = (0.01 if mcmc else 0.0) if a.opacity_reg is None else a.opacity_reg
+    a.scale_reg = (0.01 if mcmc else 0.0) if a.scale_reg is None else a.scale_reg
     if a.batch_size != 1:
         raise NotImplementedError("--batch-size 1 is what the reference passes; larger batches are not implemented")
     # gsplat scales every step-count option by steps_scaler (the reference passes 1 / n_gpus)
@@ -270,6 +277,107 @@ class DefaultStrategy:
 
 
 # ----------------------------------------------------------------------------------------------------------
+# densification: gsplat MCMCStrategy ("3D Gaussian Splatting as Markov Chain Monte Carlo"): dead Gaussians are relocated
+# onto live ones sampled by opacity, the population grows 5 % per refinement up to cap_max, and every step perturbs the
+# means with covariance-shaped noise scaled by the means' learning rate
+# ----------------------------------------------------------------------------------------------------------
+def compute_relocation(opacities: Tensor, scales: Tensor, ratios: Tensor, n_max: int = 51):
+    """Opacity and scale of the N copies that replace one Gaussian so that the rendered contribution is preserved
+    (gsplat `compute_relocation`, eq. 9 of the paper): new_opacity = 1 - (1 - o)^(1/N);
+    new_scale = scale * o / sum_{i=1..N} sum_{k=0..i-1} C(i-1, k) (-1)^k new_opacity^(k+1) / sqrt(k+1)."""
+    N = ratios.clamp(1, n_max).to(torch.int64)
+    o64 = opacities.double()
+    new_o = 1.0 - torch.pow(1.0 - o64, 1.0 / N.double())
+    denom = torch.zeros_like(o64)
+    for i in range(1, int(N.max().item()) + 1 if N.numel() else 1):
+        inner = torch.zeros_like(o64)
+        for k in range(i):
+            inner += math.comb(i - 1, k) * ((-1.0) ** k) * torch.pow(new_o, k + 1) / math.sqrt(k + 1)
+        denom += torch.where(N >= i, inner, torch.zeros_like(inner))
+    coeff = (o64 / denom.clamp_min(1e-300)).to(scales.dtype)
+    return new_o.to(opacities.dtype), scales * coeff[:, None]
+
+
+class MCMCStrategy(DefaultStrategy):
+    def __init__(self, scene_scale: float, s: float = 1.0, cap_max=1_000_000, noise_lr=5e5, refine_start=500, refine_stop=25_000,
+                 refine_every=100, min_opacity=0.005):
+        self.scene_scale, self.cap_max, self.noise_lr, self.min_opacity = scene_scale, cap_max, noise_lr, min_opacity
+        self.refine_start, self.refine_stop, self.refine_every = int(refine_start * s), int(refine_stop * s), max(1, int(refine_every * s))
+        self.grad2d = self.count = None
+
+    def accumulate(self, splats, meta, step):         # no gradient statistics in this strategy
+        return
+
+    def _resample(self, splats, idx, eps=torch.finfo(torch.float32).eps):
+        """New opacity / scale of the sampled sources (each shared with its new copies)."""
+        opa = torch.sigmoid(splats["opacities"].detach())
+        ratios = torch.bincount(idx, minlength=opa.shape[0])[idx] + 1
+        new_o, new_s = compute_relocation(opa[idx], torch.exp(splats["scales"].detach()[idx]), ratios)
+        new_o = new_o.clamp(min=self.min_opacity, max=1.0 - eps)
+        return torch.logit(new_o), torch.log(new_s)
+
+    @torch.no_grad()
+    def refine(self, splats, opt, step, lr: float = 0.0) -> Dict[str, int]:
+        stats = {}
+        if self.refine_start < step < self.refine_stop and step % self.refine_every == 0:
+            opa = torch.sigmoid(splats["opacities"].detach())
+            dead = opa <= self.min_opacity
+            n_dead = int(dead.sum())
+            if 0 < n_dead < opa.shape[0]:
+                dead_idx, alive_idx = dead.nonzero(as_tuple=True)[0], (~dead).nonzero(as_tuple=True)[0]
+                src = alive_idx[torch.multinomial(opa[alive_idx], n_dead, replacement=True)]
+                new_logit, new_logs = self._resample(splats, src)
+
+                def fn_param(name, p):
+                    p = p.clone()
+                    if name == "opacities":
+                        p[src] = new_logit
+                    elif name == "scales":
+                        p[src] = new_logs
+                    p[dead_idx] = p[src]
+                    return p
+
+                def fn_state(v):
+                    v = v.clone()
+                    v[src] = 0
+                    v[dead_idx] = 0
+                    return v
+
+                self._replace(splats, opt, fn_param, fn_state)
+            n = splats["means"].shape[0]
+            n_new = max(0, min(self.cap_max, int(1.05 * n)) - n)
+            if n_new > 0:
+                opa = torch.sigmoid(splats["opacities"].detach())
+                src = torch.multinomial(opa, n_new, replacement=True)
+                new_logit, new_logs = self._resample(splats, src)
+
+                def fn_param(name, p):
+                    p = p.clone()
+                    if name == "opacities":
+                        p[src] = new_logit
+                    elif name == "scales":
+                        p[src] = new_logs
+                    return torch.cat([p, p[src]])
+
+                def fn_state(v):
+                    v = v.clone()
+                    v[src] = 0
+                    return torch.cat([v, torch.zeros((n_new,) + v.shape[1:], device=v.device)])
+
+                self._replace(splats, opt, fn_param, fn_state)
+            stats = {"relocated": n_dead, "added": n_new, "n": splats["means"].shape[0]}
+        # every step: covariance-shaped noise on the means, faded out on opaque Gaussians
+        from .ops import quat_scale_to_covar_preci
+        opa = torch.sigmoid(splats["opacities"].detach())
+        covars, _ = quat_scale_to_covar_preci(splats["quats"].detach(), torch.exp(splats["scales"].detach()), compute_covar=True,
+                                              compute_preci=False)
+        gate = 1.0 / (1.0 + torch.exp(-100.0 * ((1.0 - opa) - 0.995)))
+        noise = torch.randn_like(splats["means"]) * gate[:, None] * (lr * self.noise_lr)
+        splats["means"].data.add_(torch.einsum("bij,bj->bi", covars, noise))
+        return stats
+
+
+# ----------------------------------------------------------------------------------------------------------
 def train(a: argparse.Namespace) -> str:
     import torch.distributed as dist
     import pipeline_pointcloud_b200 as b2s
@@ -292,7 +400,8 @@ def train(a: argparse.Namespace) -> str:
                     eps=1e-15)
     means_lr0 = opt.param_groups[0]["lr"]
     gamma = 0.01 ** (1.0 / max(a.max_steps, 1))
-    strategy = DefaultStrategy(data.scene_scale, a.steps_scaler)
+    strategy = (MCMCStrategy(data.scene_scale, a.steps_scaler, cap_max=a.cap_max) if a.strategy == "mcmc"
+                else DefaultStrategy(data.scene_scale, a.steps_scaler))
     ckpt_dir = os.path.join(a.result_dir, "ckpts")
     os.makedirs(ckpt_dir, exist_ok=True)
     save_at = {s - 1 for s in a.save_steps} | {a.max_steps - 1}
@@ -314,6 +423,10 @@ def train(a: argparse.Namespace) -> str:
             packed=a.packed or world > 1, rasterize_mode="antialiased" if a.antialiased else "classic", distributed=world > 1)
         meta["means2d"].retain_grad()
         loss = l1_ssim_loss(render, target, a.ssim_lambda)
+        if a.opacity_reg > 0.0:                         # mcmc preset: sparsity pressure on opacities and scales
+            loss = loss + a.opacity_reg * torch.sigmoid(splats["opacities"]).abs().mean()
+        if a.scale_reg > 0.0:
+            loss = loss + a.scale_reg * torch.exp(splats["scales"]).abs().mean()
         opt.zero_grad()
         loss.backward()
         if world > 1 and (step == 0 or stats):       # shard sizes change only when densification ran (same step on every rank)
@@ -330,7 +443,8 @@ def train(a: argparse.Namespace) -> str:
                 torch.zeros(splats["means"].shape[0], dtype=torch.bool, device=dev).index_fill_(0, meta["gaussian_ids"], True)
         opt.step(visibility=vis)
         opt.param_groups[0]["lr"] = means_lr0 * gamma ** (step + 1)
-        stats = strategy.refine(splats, opt, step)
+        stats = (strategy.refine(splats, opt, step, lr=opt.param_groups[0]["lr"]) if a.strategy == "mcmc"
+                 else strategy.refine(splats, opt, step))
         if rank == 0 and (step % a.log_every == 0 or step == a.max_steps - 1 or stats):
             print(f"step {step:6d}  loss {loss.item():.5f}  N {splats['means'].shape[0]}  sh {deg}  "
                   f"{(time.time() - t0) / (step + 1) * 1e3:.1f} ms/it  {stats if stats else ''}", flush=True)

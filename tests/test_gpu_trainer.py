@@ -56,3 +56,19 @@ def test_train_on_synthetic_colmap_dataset(tmp_path, capsys):
     assert all(torch.isfinite(v).all() for v in sp.values())
     ply = os.path.join(out, "splat.ply")
     assert export.export_ply(ck, ply) == N and len(export.read_ply(ply)) == 62
+
+
+def test_mcmc_strategy_trains_and_grows(tmp_path, capsys):
+    from pipeline_pointcloud_b200.simple_trainer import main
+    data, out = str(tmp_path / "data"), str(tmp_path / "out")
+    make_dataset(data)
+    rc = main(["mcmc", "--max_steps", "720", "--result-dir", out, "--data_factor", "1", "--steps_scaler", "1.0", "--disable_viewer",
+               "--packed", "--batch-size", "1", "--data-dir", data, "--log-every", "60", "--save-steps", "720", "--cap-max", "700"])
+    assert rc == 0
+    log = capsys.readouterr().out
+    losses = [float(l.split("loss")[1].split()[0]) for l in log.splitlines() if l.startswith("step")]
+    assert np.mean(losses[-3:]) < 0.7 * np.mean(losses[:2]), losses
+    assert "added" in log
+    sp = torch.load(os.path.join(out, "ckpts", "ckpt_719_rank0.pt"), map_location="cpu", weights_only=True)["splats"]
+    assert 600 < sp["means"].shape[0] <= 700                          # 600 SfM points, +5 % per refinement, capped
+    assert all(torch.isfinite(v).all() for v in sp.values())

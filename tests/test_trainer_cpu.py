@@ -19,8 +19,9 @@ def test_reference_command_line_is_accepted():
     assert a.strategy == "default" and a.packed and a.disable_viewer and a.batch_size == 1 and a.data_factor == 1
     assert a.max_steps == 7500 and a.save_steps == [1750, 7500] and a.sh_degree_interval == 250
     assert a.result_dir == "/tmp/out" and a.data_dir == "/data/set"
-    with pytest.raises(NotImplementedError):
-        parse_args(["mcmc", "--data-dir", "x"])
+    m = parse_args(["mcmc", "--data-dir", "x"])              # gsplat's mcmc preset
+    assert (m.init_opa, m.init_scale, m.opacity_reg, m.scale_reg, m.cap_max) == (0.5, 0.1, 0.01, 0.01, 1_000_000)
+    assert (a.init_opa, a.init_scale, a.opacity_reg, a.scale_reg) == (0.1, 1.0, 0.0, 0.0)
     with pytest.raises(NotImplementedError):
         parse_args(["default", "--data-dir", "x", "--batch-size", "2"])
     with pytest.raises(SystemExit):
@@ -99,3 +100,18 @@ def test_export_ply_matches_reference_layout(tmp_path):
     assert list(back) == [k for k, _ in ref] and np.array_equal(back["f_rest_17"], table[:, 9 + 17])
     # f_rest is channel-major: f_rest_0..14 = red coefficients 1..15
     assert np.array_equal(back["f_rest_3"], splats["shN"][:, 3, 0].numpy()) and np.array_equal(back["f_rest_15"], splats["shN"][:, 0, 1].numpy())
+
+
+def test_mcmc_relocation_preserves_opacity_and_closed_form():
+    import math
+    from pipeline_pointcloud_b200.simple_trainer import compute_relocation
+    o = torch.tensor([0.9, 0.5, 0.2, 0.7])
+    sc = torch.tensor([[1.0, 2.0, 3.0]] * 4)
+    N = torch.tensor([1, 2, 3, 80])                                   # 80 is capped at 51
+    new_o, new_s = compute_relocation(o, sc, N)
+    n_eff = torch.tensor([1.0, 2.0, 3.0, 51.0])
+    assert torch.allclose(1 - (1 - new_o) ** n_eff, o, atol=1e-6)   # N copies composite to the original opacity
+    assert torch.allclose(new_o[0], o[0]) and torch.allclose(new_s[0], sc[0])          # N = 1: unchanged
+    x = new_o[1].item()                                               # N = 2: denominator x + (x - x^2 / sqrt 2)
+    assert abs(new_s[1, 0].item() - 0.5 / (x + x - x * x / math.sqrt(2))) < 1e-6
+    assert (new_s[1:] < sc[1:]).all() and torch.isfinite(new_s).all()
