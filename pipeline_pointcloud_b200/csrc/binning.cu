@@ -416,6 +416,130 @@ __global__ void __launch_bounds__(EXP_THREADS) coarse_expand_kernel(int64_t M, i
     }
 }
 
+// ---- two-kernel expansion (no chained scan) -------------------------------------------------------------------------
+// coarse_expand_kernel above spends half its time at the barrier behind the decoupled look-back (ncu: 53 % stall_barrier).
+// Here the per-row work is split so that no CTA waits on another:
+//   coarse_rects_kernel : gathers each depth-ordered row once, stores its tile rectangle (x0|x1<<16, y0|y1<<16) in depth
+//                         order and the CTA's record count;
+//   coarse_scan_kernel  : exclusive scan of the CTA counts (one CTA);
+//   coarse_emit_kernel  : streams the rectangles (coalesced, no gather), scans inside the CTA and writes the records.
+__global__ void __launch_bounds__(EXP_THREADS) coarse_rects_kernel(int64_t M, const int32_t* __restrict__ sorted_ids,
+                                                                   const float2* __restrict__ means2d,
+                                                                   const int32_t* __restrict__ radii, float tile_size, int tile_w,
+                                                                   int row_lo, int row_hi, uint32_t* __restrict__ xs,
+                                                                   uint32_t* __restrict__ ys, uint32_t* __restrict__ cta_tot) {
+    __shared__ int s_w[EXP_THREADS / 32];
+    const int64_t j = (int64_t)blockIdx.x * EXP_THREADS + threadIdx.x;
+    int cnt = 0, x0 = 0, y0 = 0, x1 = 0, y1 = 0;
+    if (j < M) {
+        const int id = sorted_ids[j];
+        const int r = radii[id];
+        if (r > 0) {
+            const float2 m = means2d[id];
+            tile_rect(m.x, m.y, r, tile_size, tile_w, row_lo, row_hi, x0, y0, x1, y1);
+            if (x1 > x0 && y1 > y0) cnt = coarse_span(x0, x1) * coarse_span(y0, y1);
+            else x0 = x1 = y0 = y1 = 0;
+        }
+        xs[j] = (uint32_t)x0 | ((uint32_t)x1 << 16);
+        ys[j] = (uint32_t)y0 | ((uint32_t)y1 << 16);
+    }
+    cnt = __reduce_add_sync(FULL, cnt);
+    if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = cnt;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int t = 0;
+#pragma unroll
+        for (int w = 0; w < EXP_THREADS / 32; ++w) t += s_w[w];
+        cta_tot[blockIdx.x] = (uint32_t)t;
+    }
+}
+
+__global__ void __launch_bounds__(1024) coarse_scan_kernel(uint32_t* __restrict__ cta_tot, int64_t n) {
+    __shared__ unsigned s_tot[1024];
+    const int64_t per = (n + 1023) / 1024;
+    const int64_t b = min(n, (int64_t)threadIdx.x * per), e = min(n, b + per);
+    unsigned sum = 0;
+    for (int64_t k = b; k < e; ++k) sum += cta_tot[k];
+    s_tot[threadIdx.x] = sum;
+    __syncthreads();
+    for (int d = 1; d < 1024; d <<= 1) {
+        const unsigned t = (int)threadIdx.x >= d ? s_tot[threadIdx.x - d] : 0u;
+        __syncthreads();
+        s_tot[threadIdx.x] += t;
+        __syncthreads();
+    }
+    unsigned run = s_tot[threadIdx.x] - sum;
+    for (int64_t k = b; k < e; ++k) {
+        const unsigned v = cta_tot[k];
+        cta_tot[k] = run;
+        run += v;
+    }
+}
+
+__global__ void __launch_bounds__(EXP_THREADS) coarse_emit_kernel(int64_t M, int64_t N, const int64_t* __restrict__ camera_ids,
+                                                                  const int32_t* __restrict__ sorted_ids,
+                                                                  const uint32_t* __restrict__ xs, const uint32_t* __restrict__ ys,
+                                                                  const uint32_t* __restrict__ cta_base, int bins_w, int bins_h,
+                                                                  uint32_t* __restrict__ recs, int32_t* __restrict__ vals) {
+    __shared__ int s_start[EXP_THREADS];
+    __shared__ int s_id[EXP_THREADS];
+    __shared__ uint32_t s_xs[EXP_THREADS], s_ys[EXP_THREADS];
+    __shared__ uint32_t s_cam[EXP_THREADS];
+    __shared__ int s_warp_tot[EXP_THREADS / 32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wbase = threadIdx.x & ~31;
+    const int64_t j = (int64_t)blockIdx.x * EXP_THREADS + threadIdx.x;
+    uint32_t px = 0, py = 0;
+    int id = 0, cnt = 0;
+    if (j < M) {
+        px = xs[j]; py = ys[j];
+        id = sorted_ids[j];
+        const int x0 = (int)(px & 0xFFFFu), x1 = (int)(px >> 16), y0 = (int)(py & 0xFFFFu), y1 = (int)(py >> 16);
+        if (x1 > x0 && y1 > y0) cnt = coarse_span(x0, x1) * coarse_span(y0, y1);
+    }
+    int incl = cnt;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        int o = __shfl_up_sync(FULL, incl, d);
+        if (lane >= d) incl += o;
+    }
+    const int total = __shfl_sync(FULL, incl, 31);
+    if (lane == 31) s_warp_tot[warp] = total;
+    int64_t cam = 0;
+    if (cnt > 0) cam = camera_ids ? camera_ids[id] : (id / N);
+    s_start[threadIdx.x] = incl - cnt;
+    s_id[threadIdx.x] = id;
+    s_xs[threadIdx.x] = px;
+    s_ys[threadIdx.x] = py;
+    s_cam[threadIdx.x] = (uint32_t)cam * (uint32_t)(bins_w * bins_h);
+    __syncthreads();
+    if (total == 0) return;
+    int warp_off = 0;
+#pragma unroll
+    for (int w = 0; w < EXP_THREADS / 32; ++w)
+        if (w < warp) warp_off += s_warp_tot[w];
+    const int64_t out0 = (int64_t)cta_base[blockIdx.x] + warp_off;
+    for (int e = lane; e < total; e += 32) {
+        int lo = 0;
+#pragma unroll
+        for (int step = 16; step > 0; step >>= 1)
+            if (s_start[wbase + lo + step] <= e) lo += step;
+        const int g = wbase + lo;
+        const int k = e - s_start[g];
+        const int gx0 = (int)(s_xs[g] & 0xFFFFu), gx1 = (int)(s_xs[g] >> 16);
+        const int gy0 = (int)(s_ys[g] & 0xFFFFu), gy1 = (int)(s_ys[g] >> 16);
+        const int bx0 = gx0 / CB, by0 = gy0 / CB;
+        const int w = coarse_span(gx0, gx1);
+        const int dy = k / w, dx = k - dy * w;
+        const int bx = bx0 + dx, by = by0 + dy;
+        const int lx0 = max(gx0 - bx * CB, 0), lx1 = min(gx1 - bx * CB, CB);
+        const int ly0 = max(gy0 - by * CB, 0), ly1 = min(gy1 - by * CB, CB);
+        const uint32_t mx = ((1u << lx1) - 1u) & ~((1u << lx0) - 1u);
+        const uint32_t my = ((1u << ly1) - 1u) & ~((1u << ly0) - 1u);
+        recs[out0 + e] = (my << 24) | (mx << 16) | (s_cam[g] + (uint32_t)(by * bins_w + bx));
+        vals[out0 + e] = s_id[g];
+    }
+}
+
 // bin_offsets[k] = lower bound of coarse key k in the sorted records, k = 0 .. n_bins (inclusive: the end)
 __global__ void coarse_offsets_kernel(int64_t n, const uint32_t* __restrict__ recs, int64_t n_bins, int32_t* __restrict__ offsets) {
     int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -722,7 +846,7 @@ extern "C" int64_t b2s_coarse_bin_workspace_bytes(int64_t M, int64_t n_records) 
     if (n_records <= 0 || M <= 0) return 256;
     // unsorted records + unsorted ids + sort scratch + look-back status (counter + one word per CTA)
     return (int64_t)(2 * align256(pad4(n_records) * 4) + align256(cub_pairs32_bytes(n_records)) +
-                     align256(16 + (size_t)cdiv(M, EXP_THREADS) * 8));
+                     align256(16 + (size_t)cdiv(M, EXP_THREADS) * 8) + 2 * align256((size_t)M * 4));
 }
 
 extern "C" int b2s_coarse_bin(int64_t M, int64_t N, const int64_t* camera_ids, int64_t n_records, const int32_t* sorted_ids,
@@ -762,13 +886,29 @@ extern "C" int b2s_coarse_bin(int64_t M, int64_t N, const int64_t* camera_ids, i
     const size_t sort_bytes = cub_pairs32_bytes(n_records);
     w += align256(sort_bytes);
     const int64_t ctas = cdiv(M, EXP_THREADS);
-    B2S_CUDA(cudaMemsetAsync(w, 0, (size_t)(16 + ctas * 8), st));
-    unsigned int* counter = reinterpret_cast<unsigned int*>(w);
-    unsigned long long* status = reinterpret_cast<unsigned long long*>(w + 16);
-    coarse_expand_kernel<<<(unsigned)ctas, EXP_THREADS, 0, st>>>(
-        M, N, camera_ids, sorted_ids, reinterpret_cast<const float2*>(means2d), radii, (float)tile_size, tile_w, row_lo, row_hi,
-        bins_w, bins_h, status, counter, recs_u, vals_u);
-    B2S_LAUNCH_CHECK();
+    uint32_t* cta_tot = reinterpret_cast<uint32_t*>(w);                 // (the look-back status area of the fused variant)
+    w += align256(16 + (size_t)ctas * 8);
+    uint32_t* xs = reinterpret_cast<uint32_t*>(w);
+    w += align256((size_t)M * 4);
+    uint32_t* ys = reinterpret_cast<uint32_t*>(w);
+    if (tile_w < 65536 && tile_h < 65536 && n_records < 4294967295LL) {
+        coarse_rects_kernel<<<(unsigned)ctas, EXP_THREADS, 0, st>>>(M, sorted_ids, reinterpret_cast<const float2*>(means2d), radii,
+                                                                    (float)tile_size, tile_w, row_lo, row_hi, xs, ys, cta_tot);
+        B2S_LAUNCH_CHECK();
+        coarse_scan_kernel<<<1, 1024, 0, st>>>(cta_tot, ctas);
+        B2S_LAUNCH_CHECK();
+        coarse_emit_kernel<<<(unsigned)ctas, EXP_THREADS, 0, st>>>(M, N, camera_ids, sorted_ids, xs, ys, cta_tot, bins_w, bins_h,
+                                                                   recs_u, vals_u);
+        B2S_LAUNCH_CHECK();
+    } else {
+        B2S_CUDA(cudaMemsetAsync(cta_tot, 0, (size_t)(16 + ctas * 8), st));
+        unsigned int* counter = reinterpret_cast<unsigned int*>(cta_tot);
+        unsigned long long* status = reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(cta_tot) + 16);
+        coarse_expand_kernel<<<(unsigned)ctas, EXP_THREADS, 0, st>>>(
+            M, N, camera_ids, sorted_ids, reinterpret_cast<const float2*>(means2d), radii, (float)tile_size, tile_w, row_lo, row_hi,
+            bins_w, bins_h, status, counter, recs_u, vals_u);
+        B2S_LAUNCH_CHECK();
+    }
     const int key_bits = bit_length(n_bins > 1 ? n_bins - 1 : 1);
     {
         int rc = sort_pairs<uint32_t>(sort_tmp, sort_bytes, recs_u, bin_recs, vals_u, bin_ids, n_records, key_bits, st);

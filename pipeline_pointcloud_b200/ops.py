@@ -601,7 +601,7 @@ def bin_coarse(means2d: Tensor, radii: Tensor, depths: Tensor, tile_size: int, t
     ids = torch.empty(n_alloc, dtype=torch.int32, device=dev)
     offsets = torch.empty(C * bw * bh + 1, dtype=torch.int32, device=dev)
     ws2 = _ws(lib.b2s_coarse_bin_workspace_bytes(M, n_records), dev)
-    with _stage("coarse_bin", launches=5 + ((C * bw * bh - 1).bit_length() > 8)):   # expand, histogram, scan, passes, offsets
+    with _stage("coarse_bin", launches=7 + ((C * bw * bh - 1).bit_length() > 8)):   # rects, scan, emit, histogram, scan, passes, offsets
         check(lib.b2s_coarse_bin(M, N, ptr(cam), n_records, ptr(sorted_ids), ptr(means2d), ptr(radii), C, tile_size, tile_width,
                                  tile_height, ptr(recs), ptr(ids), ptr(offsets), ptr(ws2), ws2.numel(), L.tile_rows(tile_rows),
                                  st), "b2s_coarse_bin")
