@@ -725,10 +725,6 @@ extern "C" int b2s_depth_order(int64_t M, const uint32_t* depth_keys, const int3
     uint32_t* keys_sorted = reinterpret_cast<uint32_t*>(w);
     w += align256((size_t)M * 4);
     size_t cub_bytes = cub_pairs32_bytes(M);
-#ifndef B2S_SORT_CUB
-    if (M < (1LL << 30))      // range-compressed digits: 4 passes over (key - kmin), widths chosen on the device
-        return radix::sort_pairs_range(M, 4, depth_keys, row_ids, keys_sorted, sorted_ids, w, st);
-#endif
     return sort_pairs<uint32_t>(w, cub_bytes, depth_keys, keys_sorted, row_ids, sorted_ids, M, 32, st);
 }
 

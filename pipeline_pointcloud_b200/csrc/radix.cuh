@@ -53,52 +53,6 @@ static inline Plan make_plan(int key_bits) {
     return pl;
 }
 
-// ---- range-compressed keys (the depth sort) ------------------------------------------------------------------
-// Depth keys are fp32 bit patterns of z in (near, far): in a real scene they span one or two binades, so of the 32 key
-// bits only ~25 vary.  `range_kernel` finds [kmin, kmax] of the keys that are not the sentinel 0xFFFFFFFF (culled rows),
-// `plan_kernel` splits bit_length(kmax - kmin + 1) evenly over the FIXED number of passes the host enqueued, and every
-// pass sorts by digits of (key - kmin) (sentinel -> span, i.e. last).  Narrower digits mean fewer, longer runs per tile
-// in the scatter and fewer distinct values per MATCH.  Everything stays on the device: no host round trip.
-struct DevPlan {
-    unsigned kmin, kmax, span;      // span = kmax - kmin + 1 = the normalised value of the sentinel
-    int shift[4], bits[4];
-};
-constexpr unsigned SENTINEL = 0xFFFFFFFFu;
-__device__ __forceinline__ unsigned norm_key(unsigned k, const unsigned kmin, const unsigned span) {
-    return k == SENTINEL ? span : k - kmin;
-}
-
-static __global__ void __launch_bounds__(THREADS) range_kernel(int64_t n, const unsigned* __restrict__ keys, DevPlan* plan) {
-    __shared__ unsigned s_lo[WARPS], s_hi[WARPS];
-    unsigned lo = 0xFFFFFFFEu, hi = 0u;
-    for (int64_t i = (int64_t)blockIdx.x * THREADS + threadIdx.x; i < n; i += (int64_t)gridDim.x * THREADS) {
-        const unsigned k = keys[i];
-        if (k != SENTINEL) { lo = min(lo, k); hi = max(hi, k); }
-    }
-    lo = __reduce_min_sync(FULL, lo); hi = __reduce_max_sync(FULL, hi);
-    if ((threadIdx.x & 31) == 0) { s_lo[threadIdx.x >> 5] = lo; s_hi[threadIdx.x >> 5] = hi; }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        for (int w = 1; w < WARPS; ++w) { lo = min(lo, s_lo[w]); hi = max(hi, s_hi[w]); }
-        atomicMin(&plan->kmin, lo);
-        atomicMax(&plan->kmax, hi);
-    }
-}
-
-static __global__ void plan_kernel(DevPlan* plan, int passes) {
-    unsigned lo = plan->kmin, hi = plan->kmax;
-    if (hi < lo) { lo = 0u; hi = 0u; }                       // no visible row at all
-    const unsigned span = hi - lo + 1u;                       // <= 0xFFFFFFFF because the sentinel never enters the range
-    int key_bits = 32 - __clz(span);                          // values 0 .. span
-    plan->kmin = lo; plan->span = span;
-    int done = 0;
-    for (int p = 0; p < 4; ++p) {
-        int b = p < passes ? (key_bits - done + (passes - p) - 1) / (passes - p) : 0;
-        plan->shift[p] = done; plan->bits[p] = b;
-        done += b;
-    }
-}
-
 // ---- histogram of every digit position in one pass over the keys ------------------------------------------
 template <typename KeyT, int MAX_PASSES>
 __global__ void __launch_bounds__(THREADS) hist_kernel(int64_t n, const KeyT* __restrict__ keys, const Plan pl,
@@ -112,27 +66,6 @@ __global__ void __launch_bounds__(THREADS) hist_kernel(int64_t n, const KeyT* __
 #pragma unroll
         for (int p = 0; p < MAX_PASSES; ++p)
             if (p < passes) atomicAdd(&s_hist[p * RADIX + digit_of(k, pl.shift[p], (1u << pl.bits[p]) - 1u)], 1u);
-    }
-    __syncthreads();
-    for (int i = threadIdx.x; i < passes * RADIX; i += THREADS)
-        if (s_hist[i]) atomicAdd(&hist[i], (unsigned long long)s_hist[i]);
-}
-
-static __global__ void __launch_bounds__(THREADS) hist_range_kernel(int64_t n, const unsigned* __restrict__ keys,
-                                                                    const DevPlan* __restrict__ plan, int passes,
-                                                                    unsigned long long* __restrict__ hist /* [passes][256] */) {
-    __shared__ unsigned s_hist[4 * RADIX];
-    for (int i = threadIdx.x; i < passes * RADIX; i += THREADS) s_hist[i] = 0;
-    __syncthreads();
-    const unsigned kmin = plan->kmin, span = plan->span;
-    int sh[4]; unsigned mk[4];
-#pragma unroll
-    for (int p = 0; p < 4; ++p) { sh[p] = plan->shift[p]; mk[p] = (1u << plan->bits[p]) - 1u; }
-    for (int64_t i = (int64_t)blockIdx.x * THREADS + threadIdx.x; i < n; i += (int64_t)gridDim.x * THREADS) {
-        const unsigned k = norm_key(keys[i], kmin, span);
-#pragma unroll
-        for (int p = 0; p < 4; ++p)
-            if (p < passes) atomicAdd(&s_hist[p * RADIX + ((k >> sh[p]) & mk[p])], 1u);
     }
     __syncthreads();
     for (int i = threadIdx.x; i < passes * RADIX; i += THREADS)
@@ -168,22 +101,12 @@ template <> struct St<unsigned long long> {
     static constexpr unsigned long long MASK = (1ull << 62) - 1ull;
 };
 
-template <typename KeyT, typename StatusT, bool RANGE = false>
+template <typename KeyT, typename StatusT>
 __global__ void __launch_bounds__(THREADS, 3) onesweep_kernel(unsigned n, const KeyT* __restrict__ keys_in,
                                                               const int32_t* __restrict__ vals_in, KeyT* __restrict__ keys_out,
                                                               int32_t* __restrict__ vals_out, int shift, unsigned mask,
                                                               const unsigned long long* __restrict__ digit_base /* [256] */,
-                                                              StatusT* status /* [tiles][256] */, unsigned int* tile_counter,
-                                                              const DevPlan* __restrict__ plan = nullptr, int pass = 0) {
-    unsigned kmin = 0u, span = 0u;
-    if (RANGE) {      // digits of (key - kmin), widths from the device-side plan
-        kmin = plan->kmin; span = plan->span;
-        shift = plan->shift[pass]; mask = (1u << plan->bits[pass]) - 1u;
-    }
-    auto dig_of = [&](KeyT k) -> unsigned {
-        if (RANGE) return (norm_key((unsigned)k, kmin, span) >> shift) & mask;
-        return digit_of(k, shift, mask);
-    };
+                                                              StatusT* status /* [tiles][256] */, unsigned int* tile_counter) {
     constexpr int ITEMS = Cfg<KeyT>::ITEMS;
     constexpr unsigned TILE = THREADS * ITEMS;
     constexpr int HS = RADIX + 1;                        // +1: dump bin for the out-of-range lanes of the last tile
@@ -214,7 +137,7 @@ __global__ void __launch_bounds__(THREADS, 3) onesweep_kernel(unsigned n, const 
 #pragma unroll
         for (int i = 0; i < ITEMS; ++i) val[i] = vals_in[warp_base + i * 32];
 #pragma unroll
-        for (int i = 0; i < ITEMS; ++i) dig[i] = dig_of(key[i]);
+        for (int i = 0; i < ITEMS; ++i) dig[i] = digit_of(key[i], shift, mask);
     } else {
 #pragma unroll
         for (int i = 0; i < ITEMS; ++i) {
@@ -222,7 +145,7 @@ __global__ void __launch_bounds__(THREADS, 3) onesweep_kernel(unsigned n, const 
             const bool ok = g < n;
             key[i] = ok ? keys_in[g] : (KeyT)0;
             val[i] = ok ? vals_in[g] : 0;
-            dig[i] = ok ? dig_of(key[i]) : (unsigned)RADIX;   // out-of-range lanes share the dump bin
+            dig[i] = ok ? digit_of(key[i], shift, mask) : (unsigned)RADIX;   // out-of-range lanes share the dump bin
         }
     }
     // 2. rank inside the warp, in memory order.  All MATCH instructions are issued first (independent); then, item
@@ -319,7 +242,7 @@ __global__ void __launch_bounds__(THREADS, 3) onesweep_kernel(unsigned n, const 
 #pragma unroll 4
     for (unsigned p = threadIdx.x; p < tile_count; p += THREADS) {
         const KeyT k = s_keys[p];
-        const unsigned pos = s_off[dig_of(k)] + p;
+        const unsigned pos = s_off[digit_of(k, shift, mask)] + p;
         keys_out[pos] = k;
         vals_out[pos] = s_vals[p];
     }
@@ -395,56 +318,6 @@ static int sort_pairs(int64_t n, int key_bits, const KeyT* keys_in, const int32_
                 (unsigned)n, src_k, src_v, dst_k, dst_v, pl.shift[p], (1u << pl.bits[p]) - 1u, hist + (size_t)p * RADIX, status,
                 counters + p);
         }
-        B2S_LAUNCH_CHECK();
-        src_k = dst_k;
-        src_v = dst_v;
-    }
-    return 0;
-}
-
-// Sort of 32-bit keys whose non-sentinel values occupy a narrow range (depth keys): `passes` digit passes over
-// (key - kmin), digit widths chosen on the device.  Workspace as sort_pairs<uint32_t> (+ the plan in the counters slot).
-static int sort_pairs_range(int64_t n, int passes, const unsigned* keys_in, const int32_t* vals_in, unsigned* keys_out,
-                            int32_t* vals_out, void* workspace, cudaStream_t st) {
-    if (n <= 0) return 0;
-    if (n >= (1LL << 30) || passes < 1 || passes > 4) {
-        set_error("radix::sort_pairs_range: n must be < 2^30 and passes 1..4");
-        return B2S_E_BADARG;
-    }
-    constexpr int MAXP = 4;
-    char* w = reinterpret_cast<char*>(workspace);
-    unsigned* tk[2];
-    int32_t* tv[2];
-    tk[0] = reinterpret_cast<unsigned*>(w); w += up256((size_t)n * 4);
-    tk[1] = reinterpret_cast<unsigned*>(w); w += up256((size_t)n * 4);
-    tv[0] = reinterpret_cast<int32_t*>(w); w += up256((size_t)n * 4);
-    tv[1] = reinterpret_cast<int32_t*>(w); w += up256((size_t)n * 4);
-    unsigned long long* hist = reinterpret_cast<unsigned long long*>(w); w += up256((size_t)MAXP * RADIX * 8);
-    unsigned* status = reinterpret_cast<unsigned*>(w);
-    const int64_t tiles = tiles_of<unsigned>(n);
-    w += up256((size_t)tiles * RADIX * 8);
-    unsigned int* counters = reinterpret_cast<unsigned int*>(w);          // [4] tile counters, then the plan
-    DevPlan* plan = reinterpret_cast<DevPlan*>(w + 64);
-    static_assert(sizeof(DevPlan) <= 64, "plan must fit the tail of the counters slot");
-    B2S_CUDA(cudaMemsetAsync(hist, 0, (size_t)MAXP * RADIX * 8, st));
-    B2S_CUDA(cudaMemsetAsync(counters, 0, 128, st));
-    B2S_CUDA(cudaMemsetAsync(&plan->kmin, 0xFF, 4, st));                  // kmin = 0xFFFFFFFF, kmax = 0 (memset above)
-    const int grid = (int)min((int64_t)148 * 8, cdiv(n, THREADS));
-    range_kernel<<<grid, THREADS, 0, st>>>(n, keys_in, plan);
-    plan_kernel<<<1, 1, 0, st>>>(plan, passes);
-    hist_range_kernel<<<grid, THREADS, 0, st>>>(n, keys_in, plan, passes, hist);
-    B2S_LAUNCH_CHECK();
-    scan_hist_kernel<<<passes, RADIX, 0, st>>>(hist);
-    B2S_LAUNCH_CHECK();
-    const unsigned* src_k = keys_in;
-    const int32_t* src_v = vals_in;
-    for (int p = 0; p < passes; ++p) {
-        const bool last = (p == passes - 1);
-        unsigned* dst_k = last ? keys_out : tk[p & 1];
-        int32_t* dst_v = last ? vals_out : tv[p & 1];
-        B2S_CUDA(cudaMemsetAsync(status, 0, (size_t)tiles * RADIX * 4, st));
-        onesweep_kernel<unsigned, unsigned, true><<<(unsigned)tiles, THREADS, 0, st>>>(
-            (unsigned)n, src_k, src_v, dst_k, dst_v, 0, 0u, hist + (size_t)p * RADIX, status, counters + p, plan, p);
         B2S_LAUNCH_CHECK();
         src_k = dst_k;
         src_v = dst_v;
