@@ -12,7 +12,7 @@ from ctypes import POINTER, Structure, c_char_p, c_float, c_int32, c_int64, c_vo
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libb2s.so")
+LIB_PATH = os.environ.get("B2S_LIB") or os.path.join(_HERE, "libb2s.so")     # B2S_LIB: an A/B build of the same ABI
 
 _lib = None
 
