@@ -237,7 +237,11 @@ __global__ void __launch_bounds__(SHB_THREADS, 4) sh_bwd_fused_kernel(const b2s_
     load_cameras(cams, a.C, a.viewmats, a.Ks, a.campos, (float)a.width, (float)a.height);
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int64_t n = (int64_t)blockIdx.x * SHB_THREADS + threadIdx.x;
+    // persistent: a fixed grid walks the 256-row blocks (in sparse mode the whole grid returns above after a handful of
+    // CTA launches instead of N / 256 of them)
+    const int64_t n_blocks = (a.N + SHB_THREADS - 1) / SHB_THREADS;
+    for (int64_t blk = blockIdx.x; blk < n_blocks; blk += gridDim.x) {
+    const int64_t n = blk * SHB_THREADS + threadIdx.x;
     const bool live = n < a.N;
     const int64_t nc = live ? n : a.N - 1;
     float mean[3];
@@ -258,7 +262,7 @@ __global__ void __launch_bounds__(SHB_THREADS, 4) sh_bwd_fused_kernel(const b2s_
     const int rs = sh_row_stride(K);
     float* tile_in = sh_tiles + (size_t)warp * (MULTI ? 2 : 1) * 32 * rs;
     float* tile_out = MULTI ? tile_in + 32 * rs : tile_in;
-    const int64_t row0 = (int64_t)blockIdx.x * SHB_THREADS + warp * 32;
+    const int64_t row0 = blk * SHB_THREADS + warp * 32;
     const int rows = (int)max((int64_t)0, min((int64_t)32, a.N - row0));
     const unsigned row_mask = a.v_colors ? __ballot_sync(FULL, live && vis != 0ull) : 0u;
     if (row_mask == 0u && !a.accumulate) {
@@ -282,7 +286,7 @@ __global__ void __launch_bounds__(SHB_THREADS, 4) sh_bwd_fused_kernel(const b2s_
                 }
             }
         }
-        return;
+        continue;
     }
     // masked-off rows are zero-filled by the loader, so culled Gaussians get zero gradients for free
     sh_rows_load<KVEC>(tile_in, a.sh_coeffs + (size_t)row0 * a.sh_stride_k * 3, rows, row_mask, K, a.sh_stride_k, lane);
@@ -363,6 +367,8 @@ __global__ void __launch_bounds__(SHB_THREADS, 4) sh_bwd_fused_kernel(const b2s_
     if (rows > 0)
         sh_rows_store<KVEC>(tile_out, a.v_sh_coeffs + (size_t)row0 * a.sh_stride_k * 3, rows, K, a.sh_stride_k, lane,
                             a.accumulate != 0);
+    __syncwarp();      // the next block reuses this warp's tile
+    }
 }
 
 // =================================================================================================
@@ -712,7 +718,7 @@ extern "C" int b2s_project_bwd(const b2s_project_bwd_args* a, b2s_stream_t strea
         auto kern = vec ? (multi ? sh_bwd_fused_kernel<16, true> : sh_bwd_fused_kernel<16, false>)
                         : (multi ? sh_bwd_fused_kernel<0, true> : sh_bwd_fused_kernel<0, false>);
         B2S_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kern<<<(unsigned)cdiv(a->N, SHB_THREADS), SHB_THREADS, smem, st>>>(*a, cnt);
+        kern<<<(unsigned)min((int64_t)148 * 4, cdiv(a->N, SHB_THREADS)), SHB_THREADS, smem, st>>>(*a, cnt);
         B2S_LAUNCH_CHECK();
         if (cnt) {
             sh_zero_kernel<<<148 * 32, 256, 0, st>>>(*a, cnt);
