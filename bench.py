@@ -40,7 +40,7 @@ WORKLOADS = {
 }
 METRIC = "3DGS rasterization fwd+bwd throughput"
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture (profiles/), config 3
-NCU_TRAFFIC = {   # profiles/r01_ncu_full_v6_summary.md; launch list with DRAM bytes: profiles/r01_launches_v12.csv
+NCU_TRAFFIC = {   # profiles/r01_ncu_full_v14_summary.md; launch list with DRAM bytes: profiles/r01_launches_v14.csv
     "project_fwd": 1_628_177_000,   # 1.313962 GB read + 0.314215 GB written (v12 launch list: 1.310 + 0.300)
 }
 UNIT = "Mpix/s"
