@@ -5,8 +5,10 @@
 
 A "step" is one `rasterization()` forward + backward (random cotangent) over one camera of the synthetic
 config-3 scene (5.8 M random Gaussians, SH degree 3, 1297x840, antialiased), inputs resident in HBM.
-N > 1 (torchrun): camera data-parallel, one camera per rank per step on replicated Gaussians followed by the
-dense-gradient all-reduce over NCCL (config 4; weak scaling: per-GPU work fixed).
+N > 1 (torchrun): Gaussians sharded over the ranks, one camera per rank per step, projected splats routed to the camera
+owners by the fused NVLink exchange (rasterization(distributed=True); weak scaling: per-GPU work fixed).
+`--multi-gpu stripes --workload config5`: ONE 4K camera over N GPUs, tile-row stripes (strong scaling);
+`--multi-gpu allreduce`: replicated Gaussians + dense-gradient all-reduce (BASELINE config 4).
 `value` = Mpix/s of the whole job (C*W*H*steps / time, max over ranks); `iters_per_s` is reported beside it.
 `e2e` = the same step driven from pinned HOST buffers: H2D of every input, the step, D2H of render, alpha and
 every gradient, all inside the timed region.

@@ -241,8 +241,8 @@ B2S_API int b2s_unpack_rows(int64_t nnz, const int64_t* sel, int32_t channels, c
                             float* v_means2d, float* v_depths, float* v_conics, float* v_opacities, float* v_colors,
                             b2s_stream_t stream);
 
-/* Multi-GPU routing (rasterization(distributed=True)): the visible splats of the local shard travel to the
- * camera owners as ONE fused record each, [x, y, depth, conic(3), opacity, colour(ch), radius, tiles, local
+/* Multi-GPU routing, UNFUSED reference implementation (B2S_ROUTE=nccl; the default path is the fused stripe / camera-owner
+ * exchange further down): the visible splats of the local shard travel to their owners as ONE fused record each, [x, y, depth, conic(3), opacity, colour(ch), radius, tiles, local
  * camera, global Gaussian id] = 11 + ch floats (integers bit-cast), so a single NCCL all-to-all moves them;
  * gradients come back as [7 + ch] records by the reverse all-to-all and are scattered into dense tensors. */
 B2S_API int b2s_pack_payload(int64_t nnz, int64_t N, const int64_t* sel, int32_t channels, int32_t cams_per_rank,
@@ -259,21 +259,6 @@ B2S_API int b2s_scatter_grads(int64_t nnz, const int64_t* sel, int32_t channels,
                               float* v_depths, float* v_conics, float* v_opacities, float* v_colors,
                               int32_t accumulate /* 1: rows may repeat in sel (tile stripes), records are summed */,
                               b2s_stream_t stream);
-
-/* Fused pack + exchange over NVLink peer memory (replaces b2s_pack_payload + NCCL all-to-all, and
- * b2s_join_grads + the reverse all-to-all): the kernel stores every record straight into the destination
- * rank's receive buffer.  `host_peer_buffers[d]` = this process's mapping of rank d's symmetric buffer;
- * rows are grouped by destination (`host_*_counts[d]` rows for rank d, in order); `host_*_base[d]` = first row
- * this rank owns inside rank d's buffer.  The three host arrays have `world` entries and are read during the
- * call (passed to the kernel by value).  The caller provides the barriers around the exchange. */
-B2S_API int b2s_p2p_pack(int64_t nnz, int64_t N, const int64_t* sel, int32_t channels, int32_t cams_per_rank,
-                         int64_t gid_offset, const float* means2d, const float* depths, const float* conics,
-                         const float* opacities, const float* colors, const int32_t* radii, const int32_t* tiles,
-                         int32_t world, const int64_t* host_send_counts, const int64_t* host_dest_base,
-                         void* const* host_peer_buffers, b2s_stream_t stream);
-B2S_API int b2s_p2p_join(int64_t n, int32_t channels, const float* g_means2d, const float* g_depths, const float* g_conics,
-                         const float* g_opacities, const float* g_colors, int32_t world, const int64_t* host_recv_counts,
-                         const int64_t* host_src_base, void* const* host_peer_buffers, b2s_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Multi-GPU tile stripes (rasterization(distributed=True, tile_stripes=True); SURVEY.md 8e-ii, BASELINE config 5):

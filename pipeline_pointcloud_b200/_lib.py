@@ -136,9 +136,6 @@ SYMBOLS = {
     "b2s_split_payload": (c_int32, [c_int64, c_int32] + [c_void_p] * 11),
     "b2s_join_grads": (c_int32, [c_int64, c_int32] + [c_void_p] * 7),
     "b2s_scatter_grads": (c_int32, [c_int64, c_void_p, c_int32] + [c_void_p] * 6 + [c_int32, c_void_p]),
-    "b2s_p2p_pack": (c_int32, [c_int64, c_int64, c_void_p, c_int32, c_int32, c_int64] + [c_void_p] * 7 +
-                     [c_int32, c_void_p, c_void_p, c_void_p, c_void_p]),
-    "b2s_p2p_join": (c_int32, [c_int64, c_int32] + [c_void_p] * 5 + [c_int32, c_void_p, c_void_p, c_void_p, c_void_p]),
     "b2s_stripe_ctas": (c_int64, [c_int64]),
     "b2s_stripe_count": (c_int32, [c_int64, c_int64, c_void_p, c_void_p, c_int32, c_int32, c_int32, POINTER(Stripes), c_void_p,
                                    c_void_p, c_void_p, c_int64, c_void_p]),

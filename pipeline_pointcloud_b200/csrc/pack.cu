@@ -125,149 +125,9 @@ __global__ void scatter_grads_kernel(int64_t nnz, const int64_t* __restrict__ se
     for (int k = 0; k < ch; ++k) put(v_colors + r * ch + k, p[7 + k]);
 }
 
-// ---- fused pack + exchange over NVLink peer memory --------------------------------------------------------
-// The all-to-all is folded into the producing kernel: every warp stages its 32 records in shared memory and
-// streams them with coalesced stores straight into the *destination rank's* receive buffer (a peer mapping of
-// symmetric memory), at the row that the W x W count table assigns to (source rank, row).  No intermediate
-// send buffer, no separate collective; NVSwitch carries the stores while later warps are still packing.
-constexpr int P2P_MAX_RANKS = 16;
-struct P2PRoute {
-    int world;
-    int64_t start[P2P_MAX_RANKS + 1];   // prefix of this rank's row counts per peer (rows are grouped by peer)
-    int64_t base[P2P_MAX_RANKS];        // first row this rank owns in each peer's buffer
-    float* peer[P2P_MAX_RANKS];         // peer buffer base pointers
-};
-
-__device__ __forceinline__ float* p2p_row_ptr(const P2PRoute& rt, int64_t row, int F) {
-    int d = 0;
-#pragma unroll 1
-    while (d + 1 < rt.world && row >= rt.start[d + 1]) ++d;
-    return rt.peer[d] + (rt.base[d] + (row - rt.start[d])) * F;
-}
-
-template <int THREADS>
-__device__ __forceinline__ void p2p_flush_tile(const float* tile, int64_t row0, int64_t n_rows, int F, const P2PRoute& rt) {
-    // tile: [32 rows][F] of this warp; copy out element-wise coalesced, each row to its own destination
-    const int lane = threadIdx.x & 31;
-    const int rows = (int)min((int64_t)32, n_rows - row0);
-    if (rows <= 0) return;
-    float* first = p2p_row_ptr(rt, row0, F);
-    float* last = p2p_row_ptr(rt, row0 + rows - 1, F);
-    if (last == first + (int64_t)(rows - 1) * F) {          // whole tile goes to one contiguous range (the common case)
-        for (int e = lane; e < rows * F; e += 32) first[e] = tile[e];
-    } else {
-        for (int e = lane; e < rows * F; e += 32) {
-            const int r = e / F;
-            p2p_row_ptr(rt, row0 + r, F)[e - r * F] = tile[e];
-        }
-    }
-}
-
-constexpr int P2P_THREADS = 256;
-__global__ void __launch_bounds__(P2P_THREADS) p2p_pack_kernel(int64_t nnz, int64_t N, const int64_t* __restrict__ sel, int ch,
-                                                               int cams_per_rank, int64_t gid_offset,
-                                                               const float2* __restrict__ means2d, const float* __restrict__ depths,
-                                                               const float* __restrict__ conics, const float* __restrict__ opac,
-                                                               const float* __restrict__ colors, const int32_t* __restrict__ radii,
-                                                               const int32_t* __restrict__ tiles, const P2PRoute rt) {
-    extern __shared__ float s_tiles[];
-    const int F = 11 + ch;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    float* tile = s_tiles + (size_t)warp * 32 * F;
-    const int64_t i = (int64_t)blockIdx.x * P2P_THREADS + threadIdx.x;
-    if (i < nnz) {
-        const int64_t r = sel[i];
-        float* o = tile + lane * F;
-        const float2 m = means2d[r];
-        o[0] = m.x; o[1] = m.y; o[2] = depths[r];
-        o[3] = conics[3 * r]; o[4] = conics[3 * r + 1]; o[5] = conics[3 * r + 2];
-        o[6] = opac[r];
-        for (int k = 0; k < ch; ++k) o[7 + k] = colors[r * ch + k];
-        const int64_t cam = r / N, gid = r % N;
-        o[7 + ch] = __int_as_float(radii[r]);
-        o[8 + ch] = __int_as_float(tiles[r]);
-        o[9 + ch] = __int_as_float((int)(cam % cams_per_rank));
-        o[10 + ch] = __int_as_float((int)(gid + gid_offset));
-    }
-    __syncwarp();
-    p2p_flush_tile<P2P_THREADS>(tile, (int64_t)blockIdx.x * P2P_THREADS + warp * 32, nnz, F, rt);
-}
-
-__global__ void __launch_bounds__(P2P_THREADS) p2p_join_kernel(int64_t n, int ch, const float2* __restrict__ g_means2d,
-                                                               const float* __restrict__ g_depths, const float* __restrict__ g_conics,
-                                                               const float* __restrict__ g_opac, const float* __restrict__ g_colors,
-                                                               const P2PRoute rt) {
-    extern __shared__ float s_tiles[];
-    const int G = 7 + ch;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    float* tile = s_tiles + (size_t)warp * 32 * G;
-    const int64_t i = (int64_t)blockIdx.x * P2P_THREADS + threadIdx.x;
-    if (i < n) {
-        float* o = tile + lane * G;
-        const float2 m = g_means2d ? g_means2d[i] : make_float2(0.f, 0.f);
-        o[0] = m.x; o[1] = m.y;
-        o[2] = g_depths ? g_depths[i] : 0.f;
-        o[3] = g_conics ? g_conics[3 * i] : 0.f; o[4] = g_conics ? g_conics[3 * i + 1] : 0.f; o[5] = g_conics ? g_conics[3 * i + 2] : 0.f;
-        o[6] = g_opac ? g_opac[i] : 0.f;
-        for (int k = 0; k < ch; ++k) o[7 + k] = g_colors ? g_colors[i * ch + k] : 0.f;
-    }
-    __syncwarp();
-    p2p_flush_tile<P2P_THREADS>(tile, (int64_t)blockIdx.x * P2P_THREADS + warp * 32, n, G, rt);
-}
-
-static int fill_route(P2PRoute& rt, int32_t world, const int64_t* counts, const int64_t* base, void* const* peers) {
-    if (world < 1 || world > P2P_MAX_RANKS) return -1;
-    rt.world = world;
-    rt.start[0] = 0;
-    for (int d = 0; d < world; ++d) {
-        rt.start[d + 1] = rt.start[d] + counts[d];
-        rt.base[d] = base[d];
-        rt.peer[d] = reinterpret_cast<float*>(peers[d]);
-    }
-    return 0;
-}
-
 }  // namespace b2s
 
 using namespace b2s;
-
-extern "C" int b2s_p2p_pack(int64_t nnz, int64_t N, const int64_t* sel, int32_t channels, int32_t cams_per_rank,
-                            int64_t gid_offset, const float* means2d, const float* depths, const float* conics,
-                            const float* opacities, const float* colors, const int32_t* radii, const int32_t* tiles,
-                            int32_t world, const int64_t* host_send_counts, const int64_t* host_dest_base,
-                            void* const* host_peer_buffers, b2s_stream_t stream) {
-    B2S_REQUIRE(nnz >= 0 && N > 0 && channels >= 0 && cams_per_rank > 0, "bad sizes");
-    if (nnz == 0) return 0;
-    B2S_REQUIRE(sel && means2d && depths && conics && opacities && colors && radii && tiles, "null pointer");
-    B2S_REQUIRE(host_send_counts && host_dest_base && host_peer_buffers, "null routing table");
-    P2PRoute rt;
-    B2S_REQUIRE(fill_route(rt, world, host_send_counts, host_dest_base, host_peer_buffers) == 0, "world size must be 1..16");
-    B2S_REQUIRE(rt.start[world] == nnz, "send counts do not add up to nnz");
-    const size_t smem = (size_t)(P2P_THREADS / 32) * 32 * (11 + channels) * sizeof(float);
-    B2S_CUDA(cudaFuncSetAttribute(p2p_pack_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    p2p_pack_kernel<<<(unsigned)cdiv(nnz, P2P_THREADS), P2P_THREADS, smem, (cudaStream_t)stream>>>(
-        nnz, N, sel, channels, cams_per_rank, gid_offset, reinterpret_cast<const float2*>(means2d), depths, conics, opacities,
-        colors, radii, tiles, rt);
-    B2S_LAUNCH_CHECK();
-    return 0;
-}
-
-extern "C" int b2s_p2p_join(int64_t n, int32_t channels, const float* g_means2d, const float* g_depths, const float* g_conics,
-                            const float* g_opacities, const float* g_colors, int32_t world, const int64_t* host_recv_counts,
-                            const int64_t* host_src_base, void* const* host_peer_buffers, b2s_stream_t stream) {
-    B2S_REQUIRE(n >= 0 && channels >= 0, "bad sizes");
-    if (n == 0) return 0;
-    B2S_REQUIRE(host_recv_counts && host_src_base && host_peer_buffers, "null routing table");
-    P2PRoute rt;
-    B2S_REQUIRE(fill_route(rt, world, host_recv_counts, host_src_base, host_peer_buffers) == 0, "world size must be 1..16");
-    B2S_REQUIRE(rt.start[world] == n, "receive counts do not add up to n");
-    const size_t smem = (size_t)(P2P_THREADS / 32) * 32 * (7 + channels) * sizeof(float);
-    B2S_CUDA(cudaFuncSetAttribute(p2p_join_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    p2p_join_kernel<<<(unsigned)cdiv(n, P2P_THREADS), P2P_THREADS, smem, (cudaStream_t)stream>>>(
-        n, channels, reinterpret_cast<const float2*>(g_means2d), g_depths, g_conics, g_opacities, g_colors, rt);
-    B2S_LAUNCH_CHECK();
-    return 0;
-}
 
 extern "C" int b2s_pack_payload(int64_t nnz, int64_t N, const int64_t* sel, int32_t channels, int32_t cams_per_rank,
                                 int64_t gid_offset, const float* means2d, const float* depths, const float* conics,

@@ -343,81 +343,6 @@ def _ptrs(vals):
     return (ctypes.c_void_p * len(vals))(*[int(v) for v in vals])
 
 
-class _RouteSplatsP2P(torch.autograd.Function):
-    """Routing fused with the exchange: the pack kernel stores each [11+ch]-float record straight into the owner
-    rank's receive buffer over NVLink (symmetric memory peer mappings), the backward's join kernel stores the
-    [7+ch]-float gradient records straight back into the source rank's buffer.  No send buffers, no collective
-    call on the data path; two ~7 us symmetric-memory barriers bracket each exchange."""
-
-    @staticmethod
-    def forward(ctx, means2d, depths, conics, opac, cols, radii, tiles, cams_per_rank, n_world, group, sel, send, dup):
-        from . import _lib as L
-        from . import ops
-        dev = means2d.device
-        rank, world = dist.get_rank(group), dist.get_world_size(group)
-        C_all, N = radii.shape
-        ch = cols.shape[-1]
-        means2d, depths, conics, opac, cols = (L.f32c(t) for t in (means2d, depths, conics, opac, cols))
-        radii, tiles = radii.contiguous(), tiles.contiguous()
-        # sel: dense rows grouped by destination rank, send: rows per destination (camera_owner_selection / stripe_selection)
-        gathered = [torch.empty_like(send) for _ in range(world)]
-        dist.all_gather(gathered, send, group=group)
-        table = torch.stack(gathered).tolist()                                # one host sync: the W x W count table
-        send_counts, recv_counts = table[rank], [table[src][rank] for src in range(world)]
-        nnz, n_recv, F, G = sel.numel(), int(sum(recv_counts)), 11 + ch, 7 + ch
-        need_f = max(sum(table[src][d] for src in range(world)) for d in range(world)) * F
-        need_b = max(sum(table[s]) for s in range(world)) * G
-        buf_f, h_f = _SymmBuffers.get(group, "fwd", need_f, dev)
-        buf_b, h_b = _SymmBuffers.get(group, "bwd", need_b, dev)
-        dest_base = [sum(table[src][d] for src in range(rank)) for d in range(world)]
-        lib, st = L.lib(), L.stream_ptr(dev)
-        with ops._stage("route_p2p_fwd"):
-            h_f.barrier()                                                     # every peer is done with its receive buffer
-            L.check(lib.b2s_p2p_pack(nnz, N, L.ptr(sel), ch, cams_per_rank, int(sum(n_world[:rank])), L.ptr(means2d),
-                                     L.ptr(depths), L.ptr(conics), L.ptr(opac), L.ptr(cols), L.ptr(radii), L.ptr(tiles),
-                                     world, _i64(send_counts), _i64(dest_base), _ptrs(h_f.buffer_ptrs), st), "b2s_p2p_pack")
-            h_f.barrier()                                                     # every peer's stores have landed
-        recv = buf_f[: n_recv * F]
-        o = dict(device=dev)
-        means2d_m, depths_m, conics_m = torch.empty(n_recv, 2, **o), torch.empty(n_recv, **o), torch.empty(n_recv, 3, **o)
-        opac_m, cols_m = torch.empty(n_recv, **o), torch.empty(n_recv, ch, **o)
-        radii_m, tiles_m = torch.empty(n_recv, dtype=torch.int32, **o), torch.empty(n_recv, dtype=torch.int32, **o)
-        cam_m, gid_m = torch.empty(n_recv, dtype=torch.int64, **o), torch.empty(n_recv, dtype=torch.int64, **o)
-        with ops._stage("route_split"):
-            L.check(lib.b2s_split_payload(n_recv, ch, L.ptr(recv), L.ptr(means2d_m), L.ptr(depths_m), L.ptr(conics_m),
-                                          L.ptr(opac_m), L.ptr(cols_m), L.ptr(radii_m), L.ptr(tiles_m), L.ptr(cam_m),
-                                          L.ptr(gid_m), st), "b2s_split_payload")
-        ctx.save_for_backward(sel)
-        src_base = [sum(table[s][d] for d in range(rank)) for s in range(world)]   # my rows inside source s's packed list
-        ctx.cfg = (recv_counts, src_base, group, ch, (means2d.shape, depths.shape, conics.shape, opac.shape, cols.shape), dup)
-        ctx.set_materialize_grads(False)
-        ctx.mark_non_differentiable(radii_m, tiles_m, cam_m, gid_m)
-        return means2d_m, depths_m, conics_m, opac_m, cols_m, radii_m, tiles_m, cam_m, gid_m
-
-    @staticmethod
-    def backward(ctx, g_means2d, g_depths, g_conics, g_opac, g_cols, *_):
-        from . import _lib as L
-        from . import ops
-        (sel,) = ctx.saved_tensors
-        recv_counts, src_base, group, ch, shapes, dup = ctx.cfg
-        dev = sel.device
-        world = dist.get_world_size(group)
-        n_recv, nnz, G = int(sum(recv_counts)), sel.numel(), 7 + ch
-        buf_b, h_b = _SymmBuffers.get(group, "bwd", 0, dev)
-        lib, st = L.lib(), L.stream_ptr(dev)
-        gs = [L.f32c(g) for g in (g_means2d, g_depths, g_conics, g_opac, g_cols)]
-        with ops._stage("route_p2p_bwd"):
-            h_b.barrier()
-            L.check(lib.b2s_p2p_join(n_recv, ch, *[L.ptr(g) for g in gs], world, _i64(recv_counts), _i64(src_base),
-                                     _ptrs(h_b.buffer_ptrs), st), "b2s_p2p_join")
-            h_b.barrier()
-        outs = [torch.zeros(s, dtype=torch.float32, device=dev) for s in shapes]
-        with ops._stage("route_scatter"):
-            L.check(lib.b2s_scatter_grads(nnz, L.ptr(sel), ch, L.ptr(buf_b), *[L.ptr(o) for o in outs], int(dup), st),
-                    "b2s_scatter_grads")
-        return tuple(outs) + (None,) * 8
-
-
 class _RouteStripes(torch.autograd.Function):
     """Tile-stripe routing fused with the exchange (csrc/stripes.cu).  Forward: count -> scan -> W x W table through
     peer stores (ONE host sync: it sizes every buffer of the receiver, binning included) -> pack kernel storing SoA
@@ -542,7 +467,8 @@ class _RouteStripes(torch.autograd.Function):
 
 
 def _route_impl():
-    """'p2p' (default): fused pack + NVLink peer stores through symmetric memory; 'nccl': pack + all_to_all_single."""
+    """'p2p' (default): the exchange fused into the count / pack / return kernels over NVLink peer stores (symmetric
+    memory, `_RouteStripes`); 'nccl': the unfused reference implementation (torch selection + pack + all_to_all_single)."""
     import os
     return os.environ.get("B2S_ROUTE", "p2p")
 
@@ -639,7 +565,7 @@ def rasterization_distributed(means, quats, scales, opacities, colors, viewmats,
             else:
                 sel, send = camera_owner_selection(radii, C_local, world)
         (means2d_m, depths_m, conics_m, opac_m, cols_m, radii_m, tiles_m, cam_local,
-         gauss_global) = (_RouteSplatsP2P if _route_impl() == "p2p" and world <= 16 else _RouteSplatsCUDA).apply(
+         gauss_global) = _RouteSplatsCUDA.apply(
             means2d, depths, conics, opac, cols, radii, tiles, C_all if tile_stripes else C_local, n_world, group, sel, send,
             bool(tile_stripes))
         if tile_stripes:
