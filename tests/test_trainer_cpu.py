@@ -115,3 +115,58 @@ def test_mcmc_relocation_preserves_opacity_and_closed_form():
     x = new_o[1].item()                                               # N = 2: denominator x + (x - x^2 / sqrt 2)
     assert abs(new_s[1, 0].item() - 0.5 / (x + x - x * x / math.sqrt(2))) < 1e-6
     assert (new_s[1:] < sc[1:]).all() and torch.isfinite(new_s).all()
+
+
+def _toy_splats(n, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    return {"means": torch.randn(n, 3, generator=g).requires_grad_(), "scales": (torch.randn(n, 3, generator=g) * 0.3 - 6.0).requires_grad_(),
+            "quats": torch.randn(n, 4, generator=g).requires_grad_(), "opacities": torch.randn(n, generator=g).requires_grad_(),
+            "sh0": torch.randn(n, 1, 3, generator=g).requires_grad_(), "shN": torch.zeros(n, 15, 3).requires_grad_()}
+
+
+def test_default_strategy_clone_split_prune_and_optimizer_state():
+    """Densification bookkeeping on CPU tensors (the strategy is plain torch): clones keep their parameters, splits
+    produce two shrunken children, pruned rows vanish, and the Adam moments follow the rows (zeros for the new ones)."""
+    from pipeline_pointcloud_b200.simple_trainer import DefaultStrategy
+    from pipeline_pointcloud_b200.training import FusedAdam
+    n = 50
+    sp = _toy_splats(n)
+    with torch.no_grad():
+        sp["scales"][10:20] = -2.0                     # exp(-2) = 0.14 > 0.01 * scene_scale -> split candidates
+        sp["opacities"][40:45] = -9.0                  # sigmoid < 0.005 -> pruned
+    opt = FusedAdam([{"params": [sp[k]], "lr": 1e-3, "name": k} for k in sp])
+    for k, p in sp.items():                            # pretend some steps happened: recognisable moments
+        opt.state[p] = {"step": 7, "exp_avg": torch.arange(p.numel(), dtype=torch.float32).reshape(p.shape) + 1,
+                        "exp_avg_sq": torch.ones_like(p) * 2}
+    st = DefaultStrategy(scene_scale=1.0, refine_start=0, refine_every=1)
+    st.grad2d, st.count = torch.zeros(n), torch.ones(n)
+    st.grad2d[0:5] = 1.0                               # small + high gradient -> duplicated
+    st.grad2d[10:20] = 1.0                             # large + high gradient -> split
+    old = {k: v.detach().clone() for k, v in sp.items()}
+    stats = st.refine(sp, opt, step=1)
+    assert stats["duplicated"] == 5 and stats["split"] == 10 and stats["pruned"] == 5
+    N = sp["means"].shape[0]
+    assert N == stats["n"] == n - 10 + 5 + 20 - 5
+    for k, p in sp.items():
+        assert p.shape[0] == N and p.requires_grad and p.is_leaf
+        s_ = opt.state[p]
+        assert s_["step"] == 7 and s_["exp_avg"].shape == p.shape and s_["exp_avg_sq"].shape == p.shape
+        assert any(q is p for g_ in opt.param_groups for q in g_["params"])
+    # survivors first (rows 0..9, 20..39, 45..49), then the 5 clones, then 2 x 10 children
+    keep = [i for i in range(n) if not (10 <= i < 20 or 40 <= i < 45)]
+    assert torch.equal(sp["quats"][: len(keep)], old["quats"][keep])
+    assert torch.equal(sp["means"][len(keep): len(keep) + 5], old["means"][0:5])
+    kids = sp["scales"][len(keep) + 5:]
+    assert kids.shape[0] == 20 and torch.allclose(torch.exp(kids[:10]), torch.exp(old["scales"][10:20]) / 1.6)
+    assert opt.state[sp["means"]]["exp_avg"][len(keep):].abs().sum() == 0          # new rows start with zero moments
+    assert opt.state[sp["opacities"]]["exp_avg"][: len(keep)].min() > 0          # survivors keep theirs
+    # opacity reset: capped at logit(2 * prune_opa), moments zeroed
+    with torch.no_grad():
+        sp["opacities"].fill_(3.0)
+    st2 = DefaultStrategy(scene_scale=1.0, reset_every=4)
+    st2.grad2d = torch.zeros(N)
+    st2.count = torch.zeros(N)
+    stats = st2.refine(sp, opt, step=8)
+    assert stats.get("opacity_reset") == 1
+    assert torch.allclose(torch.sigmoid(sp["opacities"]), torch.full((N,), 0.01), atol=1e-6)
+    assert opt.state[sp["opacities"]]["exp_avg"].abs().sum() == 0
