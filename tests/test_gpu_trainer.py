@@ -72,3 +72,31 @@ def test_mcmc_strategy_trains_and_grows(tmp_path, capsys):
     sp = torch.load(os.path.join(out, "ckpts", "ckpt_719_rank0.pt"), map_location="cpu", weights_only=True)["splats"]
     assert 600 < sp["means"].shape[0] <= 700                          # 600 SfM points, +5 % per refinement, capped
     assert all(torch.isfinite(v).all() for v in sp.values())
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_trainer_under_torchrun_two_gpus(tmp_path):
+    """The reference's multi-GPU command line (source/container/src/main.py:1321-1338: steps_scaler = 1 / n_gpus) under
+    torchrun: Gaussians sharded over the ranks, rasterization(distributed=True), densification changing the shard sizes,
+    one checkpoint per rank."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    data, out = str(tmp_path / "data"), str(tmp_path / "out")
+    make_dataset(data)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29841", "-m", "pipeline_pointcloud_b200.simple_trainer", "default", "--max_steps", "1400", "--result-dir", out,
+           "--data_factor", "1", "--steps_scaler", "0.5", "--disable_viewer", "--packed", "--batch-size", "1", "--data-dir", data,
+           "--save-steps", "1400", "--log-every", "100"]
+    res = subprocess.run(cmd, cwd=root, capture_output=True, text=True, timeout=300)
+    assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
+    assert sorted(os.listdir(os.path.join(out, "ckpts"))) == ["ckpt_699_rank0.pt", "ckpt_699_rank1.pt"]
+    losses = [float(l.split("loss")[1].split()[0]) for l in res.stdout.splitlines() if l.startswith("step")]
+    assert np.mean(losses[-3:]) < 0.6 * np.mean(losses[:2]), losses
+    assert "split" in res.stdout
+    n = 0
+    for r in range(2):
+        sp = torch.load(os.path.join(out, "ckpts", f"ckpt_699_rank{r}.pt"), map_location="cpu", weights_only=True)["splats"]
+        assert all(torch.isfinite(v).all() for v in sp.values())
+        n += sp["means"].shape[0]
+    assert n > 600                                             # the two shards grew beyond the 600 SfM points
