@@ -11,8 +11,13 @@ opacities [N] (logit), sh0 [N,1,3], shN [N,K-1,3]}}`` (source/container/src/pipe
 Every iteration runs on this package's kernels: ``rasterization()`` forward + backward, the fused L1+SSIM loss and the
 fused (Selective)Adam update.  Densification follows gsplat's ``DefaultStrategy`` (clone / split / prune / opacity
 reset) and ``MCMCStrategy`` (relocation, 5 % growth, position noise) with torch tensor ops -- they run every 100th step
-and are not on the per-iteration hot path.  Multi-GPU: launch under torchrun; Gaussians are sharded over the ranks and every rank renders its
-own camera (``rasterization(distributed=True)``), one checkpoint per rank as upstream.
+and are not on the per-iteration hot path.
+
+Multi-GPU follows upstream's ``gsplat.distributed.cli``: the reference launches plain ``python simple_trainer.py`` with
+``CUDA_VISIBLE_DEVICES=0..n-1``, ``WORLD_SIZE=1`` (the number of *nodes*), ``RANK=0`` (the node rank) and
+``--steps_scaler 1/n`` (source/container/src/main.py:620-655, :1321-1347), so ``main()`` itself spawns one worker per
+visible GPU (``launch``); under torchrun the ranks torchrun made are used as they are.  Gaussians are sharded over the ranks
+and every rank renders its own camera (``rasterization(distributed=True)``), one checkpoint per rank as upstream.
 """
 from __future__ import annotations
 
@@ -59,6 +64,8 @@ def parse_args(argv: Optional[List[str]] = None) -> argparse.Namespace:
     ap.add_argument("--save-steps", type=int, nargs="*", default=[7_000, 30_000])
     ap.add_argument("--seed", type=int, default=42)
     ap.add_argument("--log-every", type=int, default=100)
+    ap.add_argument("--dry-run", action="store_true",
+                    help="parse the command line, read the COLMAP model, print the launch plan and exit 0 (no GPU needed)")
     a = ap.parse_args(argv)
     # gsplat's two presets (examples/simple_trainer.py: `default` and `mcmc` sub-commands)
     mcmc = a.strategy == "mcmc"
@@ -108,31 +115,46 @@ class ColmapDataset:
         centres = np.stack([np.linalg.inv(it["viewmat"])[:3, 3] for it in self.items])
         self.scene_scale = float(np.linalg.norm(centres - centres.mean(0), axis=1).max()) * 1.1 or 1.0
         self._cache: Dict[int, Tensor] = {}
+        self._cache_bytes, self.cache_limit = 0, int(float(os.environ.get("B2S_IMAGE_CACHE_GB", "8")) * (1 << 30))
 
     def __len__(self):
         return len(self.items)
 
-    def image(self, i: int) -> Tensor:
+    def image_u8(self, i: int) -> Tensor:
+        """RGB uint8 [H,W,3] on the host (pinned when a GPU is present).  The cache holds uint8 -- 12x smaller than the
+        float image the loss consumes -- and is bounded (B2S_IMAGE_CACHE_GB per rank, default 8): beyond the bound
+        images are decoded again on demand instead of page-locking tens of GB."""
         t = self._cache.get(i)
         if t is None:
             bgr = self._cv2.imread(self.items[i]["path"], self._cv2.IMREAD_COLOR)
             if bgr is None:
                 raise FileNotFoundError(self.items[i]["path"])
-            t = torch.from_numpy(np.ascontiguousarray(bgr[..., ::-1])).float().div_(255.0).pin_memory() \
-                if torch.cuda.is_available() else torch.from_numpy(np.ascontiguousarray(bgr[..., ::-1])).float().div_(255.0)
-            self._cache[i] = t
+            t = torch.from_numpy(np.ascontiguousarray(bgr[..., ::-1]))
+            if self._cache_bytes + t.numel() <= self.cache_limit:
+                if torch.cuda.is_available():
+                    t = t.pin_memory()
+                self._cache[i] = t
+                self._cache_bytes += t.numel()
         return t
+
+    def image(self, i: int, device=None) -> Tensor:
+        """float32 [H,W,3] in [0,1]; converted on ``device`` when given (the uint8 bytes are what crosses PCIe)."""
+        u8 = self.image_u8(i)
+        if device is not None:
+            return u8.to(device, non_blocking=True).float().div_(255.0)
+        return u8.float().div_(255.0)
 
 
 # ----------------------------------------------------------------------------------------------------------
 # splats
 # ----------------------------------------------------------------------------------------------------------
-def knn_mean_dist(points: Tensor, k: int = 3, chunk: int = 4096) -> Tensor:
-    """Mean distance to the k nearest neighbours (chunked brute force on the device; initialisation only)."""
+def knn_rms_dist(points: Tensor, k: int = 3, chunk: int = 4096) -> Tensor:
+    """RMS distance to the k nearest neighbours, sqrt(mean(d^2)) -- upstream's initial scale (chunked brute force on the
+    device; initialisation only)."""
     out = torch.empty(points.shape[0], device=points.device)
     for s in range(0, points.shape[0], chunk):
         d = torch.cdist(points[s:s + chunk], points)
-        out[s:s + chunk] = d.topk(min(k + 1, points.shape[0]), largest=False).values[:, 1:].mean(dim=1)
+        out[s:s + chunk] = d.topk(min(k + 1, points.shape[0]), largest=False).values[:, 1:].square().mean(dim=1).sqrt()
     return out
 
 
@@ -141,7 +163,7 @@ def create_splats(points: np.ndarray, rgb: np.ndarray, sh_degree: int, init_opa:
     pts = torch.from_numpy(points).float().to(device)
     col = torch.from_numpy(rgb).float().to(device) / 255.0
     n_all = pts.shape[0]
-    dist = knn_mean_dist(pts[: min(n_all, 200_000)]) if n_all > 1 else torch.ones(1, device=device)
+    dist = knn_rms_dist(pts[: min(n_all, 200_000)]) if n_all > 1 else torch.ones(1, device=device)
     if n_all > dist.shape[0]:
         dist = torch.cat([dist, dist.median().expand(n_all - dist.shape[0])])
     pts, col, dist = pts[rank::world], col[rank::world], dist[rank::world]          # Gaussian sharding, as upstream
@@ -378,26 +400,40 @@ class MCMCStrategy(DefaultStrategy):
 
 
 # ----------------------------------------------------------------------------------------------------------
-def train(a: argparse.Namespace) -> str:
+def optimizer_hparams(world: int, batch_size: int = 1):
+    """Upstream's batch/world scaling (gsplat ``create_splats_with_optimizers``): with BS = batch_size * world views per
+    optimizer step, lr * sqrt(BS), eps / sqrt(BS), betas = (1 - BS (1 - 0.9), 1 - BS (1 - 0.999)) -- this is what makes
+    ``--steps_scaler 1/n`` on n GPUs (source/container/src/main.py:1321-1322) equivalent to the single-GPU schedule."""
+    BS = max(1, int(batch_size) * int(world))
+    return {"lr_scale": math.sqrt(BS), "eps": 1e-15 / math.sqrt(BS), "betas": (1.0 - BS * (1.0 - 0.9), 1.0 - BS * (1.0 - 0.999))}
+
+
+def view_of_step(order: np.ndarray, step: int, rank: int, world: int) -> int:
+    """One permutation shared by every rank (same seed), strided by rank as ``DistributedSampler`` does: in one step
+    the ranks render ``world`` different views."""
+    return int(order[(step * world + rank) % len(order)])
+
+
+def train(a: argparse.Namespace, rank: int = 0, world: int = 1, local_rank: int = 0) -> str:
     import torch.distributed as dist
     import pipeline_pointcloud_b200 as b2s
     from .training import FusedAdam, l1_ssim_loss
 
     if not torch.cuda.is_available():
         raise RuntimeError("simple_trainer needs a CUDA device (there is no CPU path)")
-    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1 and not dist.is_initialized():
         dist.init_process_group("nccl", device_id=dev)
     torch.manual_seed(a.seed + rank)
     np.random.seed(a.seed + rank)
+    order_rng = np.random.default_rng(a.seed)                 # the SAME view order on every rank
 
     data = ColmapDataset(a.data_dir, a.data_factor)
     splats = create_splats(data.points, data.points_rgb, a.sh_degree, a.init_opa, a.init_scale, dev, rank, world)
-    opt = FusedAdam([{"params": [splats[k]], "lr": LRS[k] * (data.scene_scale if k == "means" else 1.0), "name": k} for k in LRS],
-                    eps=1e-15)
+    hp = optimizer_hparams(world, a.batch_size)
+    opt = FusedAdam([{"params": [splats[k]], "lr": LRS[k] * (data.scene_scale if k == "means" else 1.0) * hp["lr_scale"], "name": k}
+                     for k in LRS], eps=hp["eps"], betas=hp["betas"])
     means_lr0 = opt.param_groups[0]["lr"]
     gamma = 0.01 ** (1.0 / max(a.max_steps, 1))
     strategy = (MCMCStrategy(data.scene_scale, a.steps_scaler, cap_max=a.cap_max) if a.strategy == "mcmc"
@@ -405,16 +441,18 @@ def train(a: argparse.Namespace) -> str:
     ckpt_dir = os.path.join(a.result_dir, "ckpts")
     os.makedirs(ckpt_dir, exist_ok=True)
     save_at = {s - 1 for s in a.save_steps} | {a.max_steps - 1}
-    order = np.random.permutation(len(data))
+    order = order_rng.permutation(len(data))
+    epoch = 0
     last_ckpt, t0, stats = "", time.time(), {}
     strategy.gid_offset = 0
     for step in range(a.max_steps):
-        i = int(order[(step * world + rank) % len(order)])
-        if (step * world + rank) % len(order) == 0 and step > 0:
-            order = np.random.permutation(len(data))
+        e = (step * world) // len(order)                     # every rank crosses the epoch boundary at the same step
+        if e != epoch:
+            epoch, order = e, order_rng.permutation(len(data))
+        i = view_of_step(order, step, rank, world)
         item = data.items[i]
         W, H = item["size"]
-        target = data.image(i).to(dev, non_blocking=True)[None]
+        target = data.image(i, dev)[None]
         deg = min(step // a.sh_degree_interval, a.sh_degree)
         colors = torch.cat([splats["sh0"], splats["shN"]], dim=1)
         render, alpha, meta = b2s.rasterization(
@@ -456,11 +494,80 @@ def train(a: argparse.Namespace) -> str:
     return last_ckpt
 
 
-def main(argv: Optional[List[str]] = None) -> int:
-    a = parse_args(argv)
-    ckpt = train(a)
-    print(f"checkpoint: {ckpt}")
+# ----------------------------------------------------------------------------------------------------------
+# launch: upstream's gsplat.distributed.cli, restated
+# ----------------------------------------------------------------------------------------------------------
+def launch_plan(env=None, n_local_gpus: Optional[int] = None) -> Dict[str, object]:
+    """How this process must start the workers, from the environment the reference's runner leaves behind.
+
+    * under torchrun (``TORCHELASTIC_RUN_ID`` / ``LOCAL_WORLD_SIZE`` set): the process IS a worker -- RANK / WORLD_SIZE /
+      LOCAL_RANK are per-process and are used as they are;
+    * otherwise (the reference's launch, source/container/src/main.py:620-655 and :1339-1347: plain ``python
+      simple_trainer.py`` with ``CUDA_VISIBLE_DEVICES=0..n-1``): WORLD_SIZE counts *nodes* and RANK is the node rank, as in
+      upstream's ``cli()``; one worker per visible GPU is spawned, world = nodes * local GPUs, rank = node * local + i.
+    """
+    env = os.environ if env is None else env
+    if n_local_gpus is None:
+        n_local_gpus = torch.cuda.device_count()
+    if "TORCHELASTIC_RUN_ID" in env or "LOCAL_WORLD_SIZE" in env:
+        return {"mode": "worker", "rank": int(env.get("RANK", "0")), "world": int(env.get("WORLD_SIZE", "1")),
+                "local_rank": int(env.get("LOCAL_RANK", "0"))}
+    nodes, node_rank = int(env.get("WORLD_SIZE", "1") or 1), int(env.get("RANK", "0") or 0)
+    n_local = max(int(n_local_gpus), 1)
+    world = nodes * n_local
+    if world == 1:
+        return {"mode": "single", "rank": 0, "world": 1, "local_rank": 0}
+    addr = env.get("MASTER_ADDR", "127.0.0.1") or "127.0.0.1"
+    if nodes == 1 and addr == "localhost":         # (main.py:648; a container's resolver may not know "localhost")
+        addr = "127.0.0.1"
+    return {"mode": "spawn", "nodes": nodes, "node_rank": node_rank, "n_local": n_local, "world": world,
+            "master_addr": addr, "master_port": int(env.get("MASTER_PORT", "29500") or 29500)}
+
+
+def _spawned_worker(local_rank: int, a: argparse.Namespace, plan: Dict[str, object]) -> None:
+    import torch.distributed as dist
+    rank = int(plan["node_rank"]) * int(plan["n_local"]) + local_rank
+    world = int(plan["world"])
+    os.environ.update({"RANK": str(rank), "WORLD_SIZE": str(world), "LOCAL_RANK": str(local_rank),
+                       "LOCAL_WORLD_SIZE": str(plan["n_local"]), "MASTER_ADDR": str(plan["master_addr"]),
+                       "MASTER_PORT": str(plan["master_port"])})
+    torch.cuda.set_device(local_rank)
+    dist.init_process_group("nccl", init_method=f"tcp://{plan['master_addr']}:{plan['master_port']}", rank=rank,
+                            world_size=world, device_id=torch.device("cuda", local_rank))
+    try:
+        ckpt = train(a, rank, world, local_rank)
+        if rank == 0:
+            print(f"checkpoint: {ckpt}", flush=True)
+    finally:
+        if dist.is_initialized():
+            dist.destroy_process_group()
+
+
+def launch(a: argparse.Namespace) -> int:
+    plan = launch_plan()
+    if a.dry_run or os.environ.get("B2S_TRAINER_DRY_RUN", "0") == "1":
+        data = ColmapDataset(a.data_dir, a.data_factor)
+        print(f"dry run: CUDA_VISIBLE_DEVICES={os.environ.get('CUDA_VISIBLE_DEVICES', '')} {plan}; {len(data)} views, {data.points.shape[0]} SfM points, max_steps {a.max_steps}, "
+              f"save_steps {a.save_steps}, result_dir {a.result_dir}", flush=True)
+        return 0
+    if plan["mode"] == "spawn":
+        if a.steps_scaler * plan["world"] > 1.0 + 1e-6 and plan["node_rank"] == 0:
+            print(f"note: --steps_scaler {a.steps_scaler} with {plan['world']} ranks", flush=True)
+        import torch.multiprocessing as mp
+        # a worker that fails makes spawn raise -> non-zero exit code -> pipeline.py:226-235 stops the pipeline
+        mp.spawn(_spawned_worker, args=(a, plan), nprocs=int(plan["n_local"]), join=True)
+        return 0
+    if plan["world"] == 1 and a.steps_scaler < 1.0:
+        print(f"warning: --steps_scaler {a.steps_scaler} but only one GPU is visible: training {a.max_steps} steps on one rank",
+              flush=True)
+    ckpt = train(a, int(plan["rank"]), int(plan["world"]), int(plan["local_rank"]))
+    if plan["rank"] == 0:
+        print(f"checkpoint: {ckpt}")
     return 0
+
+
+def main(argv: Optional[List[str]] = None) -> int:
+    return launch(parse_args(argv))
 
 
 if __name__ == "__main__":

@@ -100,3 +100,46 @@ def test_trainer_under_torchrun_two_gpus(tmp_path):
         assert all(torch.isfinite(v).all() for v in sp.values())
         n += sp["means"].shape[0]
     assert n > 600                                             # the two shards grew beyond the 600 SfM points
+
+
+def _reference_launch(tmp_path, n_gpus, max_steps=600):
+    """What source/container/src/pipeline/pipeline.py:175-222 executes for the Train-Stage1 component of the multi-GPU branch
+    (main.py:1321-1347) after main.py:620-655 prepared the environment: plain `python gsplat/examples/simple_trainer.py`,
+    cwd = the directory holding gsplat/ (shim/), CUDA_VISIBLE_DEVICES=0..n-1, WORLD_SIZE=1 (nodes), RANK=0, no torchrun."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    data, out = str(tmp_path / "data"), str(tmp_path / "out")
+    make_dataset(data)
+    env = {k: v for k, v in os.environ.items() if k not in ("TORCHELASTIC_RUN_ID", "LOCAL_WORLD_SIZE")}
+    env.update({"CUDA_VISIBLE_DEVICES": ",".join(str(i) for i in range(n_gpus)), "MASTER_ADDR": "localhost",
+                "MASTER_PORT": "29853", "WORLD_SIZE": "1", "RANK": "0", "LOCAL_RANK": "0"})
+    args = ["default", "--max_steps", str(max_steps * n_gpus), "--result-dir", out, "--data_factor", "1", "--steps_scaler",
+            str(float(1 / n_gpus)), "--disable_viewer", "--packed", "--batch-size", "1", "--data-dir", data]
+    res = subprocess.run([sys.executable, "gsplat/examples/simple_trainer.py"] + args, cwd=os.path.join(root, "shim"), env=env,
+                         capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-3000:]
+    return out, res.stdout
+
+
+def test_reference_launch_single_gpu(tmp_path):
+    out, log = _reference_launch(tmp_path, 1)
+    assert sorted(os.listdir(os.path.join(out, "ckpts"))) == ["ckpt_599_rank0.pt"]
+    losses = [float(l.split("loss")[1].split()[0]) for l in log.splitlines() if l.startswith("step")]
+    assert np.mean(losses[-2:]) < 0.7 * losses[0], losses
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_reference_launch_spawns_one_worker_per_gpu(tmp_path):
+    """The drop-in must not silently train on one GPU for 1/n of the steps: one worker per visible GPU, one checkpoint
+    per rank, steps scaled by 1/n (upstream gsplat.distributed.cli behaviour)."""
+    out, log = _reference_launch(tmp_path, 2)
+    assert sorted(os.listdir(os.path.join(out, "ckpts"))) == ["ckpt_599_rank0.pt", "ckpt_599_rank1.pt"]
+    n = 0
+    for r in range(2):
+        sp = torch.load(os.path.join(out, "ckpts", f"ckpt_599_rank{r}.pt"), map_location="cpu", weights_only=True)["splats"]
+        assert all(torch.isfinite(v).all() for v in sp.values())
+        n += sp["means"].shape[0]
+    assert n >= 600                       # the 600 SfM points were sharded over the two ranks (and densified)
+    losses = [float(l.split("loss")[1].split()[0]) for l in log.splitlines() if l.startswith("step")]
+    assert np.mean(losses[-2:]) < 0.7 * losses[0], losses
