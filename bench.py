@@ -1,19 +1,24 @@
 #!/usr/bin/env python
 """bench.py -- fwd+bwd throughput of the rasterization() hot path (BASELINE.json metric).
 
-    python bench.py --gpus N --steps K --warmup W [--impl reference] [--workload config3|config2|tiny]
+    python bench.py --gpus N --steps K --warmup W [--impl reference] [--workload config3|config2|config1|config5|...]
 
-A "step" is one `rasterization()` forward + backward (random cotangent) over one camera of the synthetic
+A "step" is one `rasterization()` forward + backward (seeded random cotangent) over one camera of the synthetic
 config-3 scene (5.8 M random Gaussians, SH degree 3, 1297x840, antialiased), inputs resident in HBM.
 N > 1 (torchrun): Gaussians sharded over the ranks, one camera per rank per step, projected splats routed to the camera
-owners by the fused NVLink exchange (rasterization(distributed=True); weak scaling: per-GPU work fixed).
+owners by the fused NVLink peer-store exchange (rasterization(distributed=True); weak scaling: per-GPU work fixed).
 `--multi-gpu stripes --workload config5`: ONE 4K camera over N GPUs, tile-row stripes (strong scaling);
 `--multi-gpu allreduce`: replicated Gaussians + dense-gradient all-reduce (BASELINE config 4).
-`value` = Mpix/s of the whole job (C*W*H*steps / time, max over ranks); `iters_per_s` is reported beside it.
+`value` = Mpix/s of the whole job (C*W*H*steps / time, max over ranks); `iters_per_s` is reported beside it, and the
+median / p10 / p90 of the per-step device times.
 `e2e` = the same step driven from pinned HOST buffers: H2D of every input, the step, D2H of render, alpha and
 every gradient, all inside the timed region.
-`--impl reference` times the CPU oracle (the restated reference torch path) on a bounded sub-frustum sample
-of the same workload on the host cores.
+`cpu_baseline` / `--impl reference`: the CPU oracle (the restated reference torch path) on a bounded sub-frustum sample of
+the same workload on the host cores; at N = 1 the same oracle run is then used as the checker of the CUDA path on that
+sub-frustum (`parity_check`: bit-equal keys, render / alpha error, gradient error).
+`extras` (default on; --no-extras): short side measurements kept in the same JSON line -- packed=True, a scene in
+gsplat's initial state (opacity 0.1: nothing saturates, the dense backward runs), BASELINE configs 1 and 2 at N = 1,
+and at any N the config-5 tile-stripe step and the config-4 all-reduce step, so that the 1/2/4/8 records hold them.
 """
 from __future__ import annotations
 
@@ -33,19 +38,21 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 WORKLOADS = {
-    # name: (N, sh_degree, W, H, rasterize_mode)
-    "config3": (5_800_000, 3, 1297, 840, "antialiased"),
-    "config2": (1_000_000, 3, 800, 800, "classic"),
-    "config1": (100_000, 0, 256, 256, "classic"),
-    "config5": (30_000_000, 3, 3840, 2160, "antialiased"),     # with --multi-gpu stripes: one 4K camera, strong scaling
-    "tiny": (50_000, 3, 320, 240, "antialiased"),
+    # name: (N, sh_degree, W, H, rasterize_mode, fwd_only, init)
+    "config3": (5_800_000, 3, 1297, 840, "antialiased", False, "random"),
+    "config3_init": (5_800_000, 3, 1297, 840, "antialiased", False, "gsplat_init"),
+    "config2": (1_000_000, 3, 800, 800, "classic", False, "random"),
+    "config1": (100_000, 0, 256, 256, "classic", True, "random"),
+    "config5": (30_000_000, 3, 3840, 2160, "antialiased", False, "random"),     # with --multi-gpu stripes: strong scaling
+    "tiny": (50_000, 3, 320, 240, "antialiased", False, "random"),
 }
 METRIC = "3DGS rasterization fwd+bwd throughput"
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture (profiles/), config 3
-NCU_TRAFFIC = {   # profiles/r01_ncu_full_v14_summary.md; launch list with DRAM bytes: profiles/r01_launches_v14.csv
-    "project_fwd": 1_628_177_000,   # 1.313962 GB read + 0.314215 GB written (v12 launch list: 1.310 + 0.300)
+NCU_TRAFFIC = {
+    "project_fwd": 1_628_177_000,   # profiles/r01_ncu_full_v14_summary.md: 1.314 GB read + 0.314 GB written
 }
 UNIT = "Mpix/s"
+LEAVES = ("means", "quats", "scales", "opacities", "colors")
 
 
 def peaks():
@@ -56,6 +63,27 @@ def peaks():
         except Exception:
             pass
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def workload_config(workload, packed, world, multi_gpu):
+    """The `config` object of the JSON line: the same for the CUDA arm and the reference arm of one invocation."""
+    N, deg, W, H, mode, fwd_only, init = WORKLOADS[workload]
+    stripes = multi_gpu == "stripes"
+    sharded = world > 1 and multi_gpu in ("sharded", "stripes")
+    s = (f"{workload}: {N} random Gaussians" + (" in gsplat's initial state (opacity 0.1, isotropic NN-distance scales)"
+                                                 if init == "gsplat_init" else "") +
+         f", SH deg {deg}, {W}x{H}, {mode}, " + ("forward only" if fwd_only else "fwd+bwd") +
+         f", packed={bool(packed or sharded)}, " + ("1 camera" if (world == 1 or stripes) else "1 camera per GPU"))
+    if world > 1 and stripes:
+        s += (", Gaussians sharded over ranks, every rank composites a stripe of tile rows of the one camera: fused pack + NVLink "
+              "peer-store exchange of projected splats to the stripe owners, gradients returned by the reverse exchange")
+    elif world > 1 and sharded:
+        s += (", Gaussians sharded over ranks, fused pack + NVLink peer-store exchange of projected splats to the camera owners "
+              "(NCCL all-to-all when peer access is unavailable), gradients returned by the reverse exchange")
+    elif world > 1:
+        s += ", replicated Gaussians, dense-gradient all-reduce"
+    return {"workload": s, "l2": "inputs (1.4 GB parameters + 0.3 GB keys at config 3) exceed the 126 MB L2",
+            "parallelism": f"dp{world}"}
 
 
 # ----------------------------------------------------------------------------------------------------------
@@ -111,13 +139,14 @@ class ClockSampler:
 # ----------------------------------------------------------------------------------------------------------
 # algorithmic bytes per stage (DESIGN.md "Measurement")
 # ----------------------------------------------------------------------------------------------------------
-def algorithmic_bytes(N, C, V, Vt, I, R, P, K, n_tiles, key_bits):
-    """Compulsory HBM traffic per stage (every input read once, every output written once).
-    V = visible rows, Vt = rows compositing actually reached (non-zero cotangent), I = tile intersections,
-    R = coarse-bin records.  The compositing stages are instruction-issue bound, not HBM bound: no figure."""
+def algorithmic_bytes(N, C, V, Vt, I, R, K, n_tiles, key_bits, sparse_bwd):
+    """Compulsory HBM traffic per stage of ONE rank's launch (every input read once, every output written once; DESIGN.md
+    section 4).  N = Gaussians the rank projects, C = cameras it projects them into, V = visible (camera, Gaussian)
+    rows of THAT projection, Vt = rows compositing reached (non-zero cotangent), I = tile intersections, R = coarse-bin
+    records.  The compositing stages are instruction-issue bound, not HBM bound: no figure."""
     M = C * N
     p = math.ceil(key_bits / 8)
-    return {
+    b = {
         "project_fwd": N * 44 + V * 12 * K + M * 60,               # params + SH rows of visible + per-pair outputs (incl. keys)
         # reference-shaped lists (B2S_BINNING=tiles)
         "isect_scan": M * 8,
@@ -131,155 +160,173 @@ def algorithmic_bytes(N, C, V, Vt, I, R, P, K, n_tiles, key_bits):
         "coarse_bin": M * 4 + V * 12 + R * 8 + R * 4 + R * 16 + 4 * (n_tiles // 64 + 1),
         "composite_fwd": None,
         "composite_bwd": None,
-        # SH colour VJP: means + radii + colour cotangents in, coefficient rows of the reached rows in, all gradients out
-        "sh_bwd": N * 12 + M * 4 + V * 12 + Vt * 12 * K + N * 12 * K + N * 12,
-        # projection VJP: radii + cotangents of the visible rows, parameters of the reached rows, gradients out
-        "project_bwd": M * 4 + V * 36 + Vt * 44 + N * 44,
     }
+    if sparse_bwd:
+        # classify: radii of every row, the cotangents (means2d 8, conics 12, opacity 4, colour 12) of the visible rows in;
+        # zero-filled small gradients (44 B/Gaussian) and the two live-row lists out
+        b["bwd_classify"] = M * 4 + V * 36 + N * 44 + Vt * 8
+        # SH VJP, sparse mode: streaming zero fill of v_sh + per live row: list entry, coefficients in, gradients out,
+        # colour cotangent, mean in, v_mean read-modify-write
+        b["sh_bwd"] = N * 12 * K + Vt * (4 + 24 * K + 12 + 12 + 24)
+        # projection VJP, list-driven: list entry, parameters, cotangents in, gradients out (v_mean read-modify-write)
+        b["project_bwd"] = Vt * (4 + 44 + 36 + 44 + 12)
+    else:
+        b["sh_bwd"] = N * 12 + M * 4 + V * 12 + Vt * 12 * K + N * 12 * K + N * 12
+        b["project_bwd"] = M * 4 + V * 36 + Vt * 44 + N * 44
+    return b
+
+
+# ----------------------------------------------------------------------------------------------------------
+# scenes
+# ----------------------------------------------------------------------------------------------------------
+def build_scene(workload, C_total, lo=None, hi=None, seed=0):
+    from pipeline_pointcloud_b200.scene import make_scene, make_scene_blocked
+    N, deg, W, H, mode, fwd_only, init = WORKLOADS[workload]
+    lo = 0 if lo is None else lo
+    hi = N if hi is None else hi
+    if N > 10_000_000:      # too large to generate once per rank: block-seeded scene, only this rank's shard
+        scene = make_scene_blocked(N, deg, C_total, W, H, seed=seed, lo=lo, hi=hi)
+    else:
+        scene = make_scene(N, deg, C_total, W, H, seed=seed)            # identical on every rank (CPU generator)
+        for k in LEAVES:
+            scene[k] = scene[k][lo:hi].contiguous()
+    if init == "gsplat_init":
+        # gsplat's simple_trainer initial state on these positions: opacity 0.1, isotropic scale = RMS distance to the 3
+        # nearest neighbours (uniform points of density rho: ~0.75 rho^(-1/3); a log-normal jitter stands in for its spread)
+        g = torch.Generator().manual_seed(seed + 77)
+        d = 0.75 * (8.0 * 3.0 ** 3 / N) ** (1.0 / 3.0)
+        n = scene["means"].shape[0]
+        scene["opacities"] = torch.full((n,), 0.1)
+        scene["scales"] = (d * torch.exp(0.25 * torch.randn(n, 1, generator=g))).repeat(1, 3).contiguous()
+    return scene
 
 
 # ----------------------------------------------------------------------------------------------------------
 # CPU baseline: the oracle on a bounded sub-frustum sample of the same workload
 # ----------------------------------------------------------------------------------------------------------
-def cpu_sample_inputs(scene, W, H, win_w=160, win_h=96):
-    """Central win_w x win_h window of the workload's camera 0 and the Gaussians whose 3-sigma footprint can
-    reach it (selected with a cheap bound, outside the timed region).  All stages then scale by the same
-    factor, so Mpix/s of the sample is comparable with the full frame."""
-    V, K = scene["viewmats"][0], scene["Ks"][0]
-    x0, y0 = (W - win_w) // 2 // 16 * 16, (H - win_h) // 2 // 16 * 16
-    t = scene["means"] @ V[:3, :3].T + V[:3, 3]
-    z = t[:, 2].clamp_min(1e-6)
-    px, py = K[0, 0] * t[:, 0] / z + K[0, 2], K[1, 1] * t[:, 1] / z + K[1, 2]
-    rad = 3.0 * scene["scales"].max(dim=1).values * K[0, 0] / z + 3.0
-    keep = (t[:, 2] > 0.01) & (px + rad > x0) & (px - rad < x0 + win_w) & (py + rad > y0) & (py - rad < y0 + win_h)
-    sub = {k: scene[k][keep].clone() for k in ("means", "quats", "scales", "opacities", "colors")}
-    Kc = K.clone()
-    Kc[0, 2] -= x0
-    Kc[1, 2] -= y0
-    sub["viewmats"], sub["Ks"] = V[None].clone(), Kc[None]
-    return sub, win_w, win_h, int(keep.sum())
-
-
-def cpu_oracle_step(sub, w, h, sh_degree, mode, v_r, v_a):
+def run_cpu(workload, steps, warmup, seed=0, keep_ref=False):
+    """The oracle on the host cores: the central ~160x96 window of the workload's camera 0, whole-frame geometry, the
+    Gaussians that can reach the window (oracle/window_check.py).  Forward-only workloads that are small enough
+    (BASELINE config 1) run the whole frame instead."""
     from oracle import torch_oracle as O   # the reference arm / cpu_baseline leg: the one place bench.py runs oracle/
-    leaves = [sub[k].clone().requires_grad_() for k in ("means", "quats", "scales", "opacities", "colors")]
-    r, a, m = O.rasterization(*leaves, sub["viewmats"], sub["Ks"], w, h, sh_degree=sh_degree, packed=False,
-                              rasterize_mode=mode)
-    torch.autograd.backward([r, a], [v_r, v_a])
-    return m["isect_ids"].numel()
-
-
-def run_cpu(workload, steps, warmup, seed=0):
-    from pipeline_pointcloud_b200.scene import make_scene
-    N, deg, W, H, mode = WORKLOADS[workload]
+    from oracle import window_check as WC
+    N, deg, W, H, mode, fwd_only, init = WORKLOADS[workload]
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    if N > 10_000_000:
-        from pipeline_pointcloud_b200.scene import make_scene_blocked
-        scene = make_scene_blocked(N, deg, 1, W, H, seed=seed)
+    scene = build_scene(workload, 1, seed=seed)
+    whole = fwd_only and N <= 200_000
+    tw, th = math.ceil(W / 16), math.ceil(H / 16)
+    if whole:
+        window, (sub, idx) = (0, 0, tw, th), ({k: scene[k] for k in LEAVES + ("viewmats", "Ks")}, torch.arange(N))
     else:
-        scene = make_scene(N, deg, 1, W, H, seed=seed)
-    sub, w, h, n_sub = cpu_sample_inputs(scene, W, H)
-    g = torch.Generator().manual_seed(seed + 1)
-    v_r, v_a = torch.rand(1, h, w, 3, generator=g), torch.rand(1, h, w, 1, generator=g)
+        window = WC.central_window(W, H)
+        sub, idx = WC.select_window_inputs(scene, W, H, window)
+    v_r, v_a = WC.window_cotangents(W, H, window, seed=seed + 1)
+    ref = None
+
+    def one():
+        if fwd_only:
+            with torch.no_grad():
+                r, a, m = O.rasterization(sub["means"], sub["quats"], sub["scales"], sub["opacities"], sub["colors"],
+                                          sub["viewmats"], sub["Ks"], W, H, sh_degree=deg, packed=False, rasterize_mode=mode,
+                                          return_fragile=True, tile_window=None if whole else window)
+            return {"render": r, "alpha": a, "fragile": m["fragile"], "isect_ids": m["isect_ids"],
+                    "flatten_ids": m["flatten_ids"], "n_isects": int(m["isect_ids"].numel()), "grads": None}
+        return WC.oracle_window_step(sub, W, H, deg, mode, window, v_r, v_a, zero_fragile=True)
+
     for _ in range(warmup):
-        cpu_oracle_step(sub, w, h, deg, mode, v_r, v_a)
+        one()
     t0 = time.perf_counter()
     for _ in range(steps):
-        n_is = cpu_oracle_step(sub, w, h, deg, mode, v_r, v_a)
+        ref = one()
     dt = time.perf_counter() - t0
-    mpix = w * h * steps / dt / 1e6
-    sample = (f"{steps} fwd+bwd step(s) of the CPU oracle on a sub-frustum of {workload}: central {w}x{h} window "
-              f"({(w // 16) * (h // 16)} of {math.ceil(W / 16) * math.ceil(H / 16)} tiles) with the {n_sub} of {N} Gaussians "
-              f"that can reach it ({n_is} tile intersections); {cores} torch threads")
+    wpx = (window[2] - window[0]) * 16 * (window[3] - window[1]) * 16 if not whole else W * H
+    mpix = wpx * steps / dt / 1e6
+    sample = (f"{steps} {'forward' if fwd_only else 'fwd+bwd'} step(s) of the CPU oracle on " +
+              (f"the whole frame of {workload}" if whole else
+               f"a sub-frustum of {workload}: tiles x [{window[0]},{window[2]}) y [{window[1]},{window[3]}) of the {tw}x{th} grid "
+               f"({wpx} pixels), whole-frame geometry, the {idx.numel()} of {N} Gaussians that can reach them") +
+              f" ({ref['n_isects']} tile intersections composited); {cores} torch threads")
     model = ""
     try:
         model = [l.split(":", 1)[1].strip() for l in open("/proc/cpuinfo") if l.startswith("model name")][0]
     except Exception:
         pass
-    return {"value": mpix, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample, "cpu_model": model,
-            "s_per_step": dt / steps, "iters_per_s_full_frame_equiv": mpix * 1e6 / (W * H)}
+    out = {"value": mpix, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample, "cpu_model": model,
+           "s_per_step": dt / steps, "iters_per_s_full_frame_equiv": mpix * 1e6 / (W * H)}
+    if keep_ref:
+        out["_ref"] = (ref, idx, window, scene)
+    return out
+
+
+def parity_against_oracle(workload, cb, dev, packed):
+    """The oracle run of the cpu_baseline leg, reused as the checker of the CUDA path on the same sub-frustum: the full
+    frame is rendered and differentiated on the GPU with the cotangent the oracle used (zero outside the window and on
+    the knife-edge pixels it reported)."""
+    import pipeline_pointcloud_b200 as b2s
+    from oracle import window_check as WC
+    N, deg, W, H, mode, fwd_only, init = WORKLOADS[workload]
+    ref, idx, window, scene = cb["_ref"]
+    p = {k: scene[k].to(dev).requires_grad_(not fwd_only) for k in LEAVES}
+    r, a, m = b2s.rasterization(p["means"], p["quats"], p["scales"], p["opacities"], p["colors"], scene["viewmats"][:1].to(dev),
+                                scene["Ks"][:1].to(dev), W, H, sh_degree=deg, packed=packed, rasterize_mode=mode)
+    flat = m["flatten_ids"]
+    if packed:
+        flat = m["gaussian_ids"][flat.long()]
+    grads = None
+    if not fwd_only:
+        torch.autograd.backward([r, a], [ref["v_render"].to(dev), ref["v_alpha"].to(dev)])
+        grads = {k: p[k].grad.cpu() for k in LEAVES}
+    else:
+        ref = dict(ref)
+        ref["grads"] = {k: torch.zeros_like(scene[k][idx]) for k in LEAVES}
+        grads = {k: torch.zeros_like(scene[k]) for k in LEAVES}
+    rep = WC.compare_window(ref, idx, r.detach().cpu(), a.detach().cpu(), m["isect_ids"].cpu(), flat.cpu(), grads, W, H, window)
+    if fwd_only:
+        rep.pop("grad_rel_err"); rep.pop("grad_outside_selection_max")
+        rep["pass"] = bool(rep["keys_bit_equal"] and rep["ids_bit_equal"] and rep["render_max_err"] <= 1e-4 and rep["alpha_max_err"] <= 1e-4)
+    rep["checker"] = "oracle/torch_oracle.py on the cpu_baseline sample (parity unpinned: no gsplat in the container)"
+    return rep
 
 
 # ----------------------------------------------------------------------------------------------------------
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--impl", default="b2s", choices=["b2s", "reference"])
-    ap.add_argument("--workload", default=os.environ.get("B2S_BENCH_WORKLOAD", "config3"), choices=sorted(WORKLOADS))
-    ap.add_argument("--packed", action="store_true", help="packed=True layout (default: dense, as ns-train splatfacto)")
-    ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--e2e-steps", type=int, default=None)
-    ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (profiling runs only)")
-    ap.add_argument("--no-balance", action="store_true", help="stripes: keep the even split of the tile rows")
-    ap.add_argument("--multi-gpu", default="sharded", choices=["sharded", "allreduce", "stripes"],
-                    help="N>1: 'sharded' = Gaussians sharded over ranks + all-to-all of projected splats to the camera "
-                         "owners (rasterization(distributed=True), what the reference's multi-GPU branch runs); "
-                         "'allreduce' = replicated Gaussians + dense-gradient all-reduce (BASELINE config 4); "
-                         "'stripes' = ONE camera, Gaussians sharded over ranks, every rank composites a stripe of tile rows "
-                         "(rasterization(distributed=True, tile_stripes=True), BASELINE config 5; strong scaling)")
-    args = ap.parse_args()
+# one measurement of the CUDA path
+# ----------------------------------------------------------------------------------------------------------
+def pctl(xs, q):
+    xs = sorted(xs)
+    if not xs:
+        return None
+    i = q * (len(xs) - 1)
+    lo, hi = int(math.floor(i)), int(math.ceil(i))
+    return xs[lo] + (xs[hi] - xs[lo]) * (i - lo)
 
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    N, deg, W, H, mode = WORKLOADS[args.workload]
 
-    # ------------------------------------------------------------------ reference arm: CPU oracle, rank 0 only
-    if args.impl == "reference":
-        if rank != 0:
-            return 0
-        steps, warmup = max(1, min(args.steps, 30)), min(args.warmup, 2)
-        cb = run_cpu(args.workload, steps, warmup)
-        line = {
-            "impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus,
-            "steps": steps, "warmup": warmup, "ms_per_step": cb["s_per_step"] * 1e3, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"{args.workload}: {N} Gaussians, SH deg {deg}, {W}x{H}, {mode}, fwd+bwd "
-                                   "(bounded sub-frustum sample, see cpu_baseline.sample)"},
-            "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample", "cpu_model")},
-            "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "iters_per_s": cb["iters_per_s_full_frame_equiv"],
-        }
-        print(json.dumps(line))
-        return 0
-
-    # ------------------------------------------------------------------ our arm
+def run_gpu(workload, multi_gpu, steps, warmup, packed=False, e2e_steps=0, stages=True, balance=True, clocks=False):
+    """Times `steps` steps of `workload` on the current process group.  Returns the result dict on every rank."""
     import torch.distributed as dist
     import pipeline_pointcloud_b200 as b2s
     from pipeline_pointcloud_b200 import ops
     from pipeline_pointcloud_b200.distributed import allreduce_gradients
-    from pipeline_pointcloud_b200.scene import make_scene
 
-    assert torch.cuda.is_available(), "bench.py needs a GPU (there is no CPU path)"
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-    assert world == args.gpus or world == 1, "launch with torchrun --nproc-per-node == --gpus"
-
-    stripes = world > 1 and args.multi_gpu == "stripes"
-    sharded = world > 1 and args.multi_gpu in ("sharded", "stripes")
-    C_total = 1 if (stripes or args.multi_gpu == "stripes") else max(world, 1)
+    rank = dist.get_rank() if dist.is_initialized() else 0
+    world = dist.get_world_size() if dist.is_initialized() else 1
+    dev = torch.device("cuda", torch.cuda.current_device())
+    N, deg, W, H, mode, fwd_only, init = WORKLOADS[workload]
+    stripes = world > 1 and multi_gpu == "stripes"
+    sharded = world > 1 and multi_gpu in ("sharded", "stripes")
+    C_total = 1 if (world == 1 or multi_gpu == "stripes") else world
     lo_n, hi_n = (rank * N // world, (rank + 1) * N // world) if sharded else (0, N)
-    if N > 10_000_000:      # too large to generate once per rank: block-seeded scene, only this rank's shard
-        from pipeline_pointcloud_b200.scene import make_scene_blocked
-        scene = make_scene_blocked(N, deg, C_total, W, H, seed=0, lo=lo_n, hi=hi_n)
-        leaves_host = {k: scene[k].pin_memory() for k in ("means", "quats", "scales", "opacities", "colors")}
-    else:
-        scene = make_scene(N, deg, C_total, W, H, seed=0)            # identical on every rank (CPU generator)
-        leaves_host = {k: scene[k][lo_n:hi_n].contiguous().pin_memory() for k in ("means", "quats", "scales", "opacities", "colors")}
+    scene = build_scene(workload, C_total, lo_n, hi_n)
+    leaves_host = {k: scene[k].pin_memory() for k in LEAVES}
     cam_i = 0 if C_total == 1 else rank
     cam_host = {"viewmats": scene["viewmats"][cam_i:cam_i + 1].contiguous().pin_memory(),
                 "Ks": scene["Ks"][cam_i:cam_i + 1].contiguous().pin_memory()}
-    params = {k: v.to(dev).requires_grad_() for k, v in leaves_host.items()}
+    params = {k: v.to(dev).requires_grad_(not fwd_only) for k, v in leaves_host.items()}
     cams = {k: v.to(dev) for k, v in cam_host.items()}
-    g = torch.Generator().manual_seed(1 + (0 if stripes else rank))
+    g = torch.Generator().manual_seed(1 + (0 if (stripes or world == 1) else rank))
     v_r_full = torch.rand(1, H, W, 3, generator=g)
     v_a_full = torch.rand(1, H, W, 1, generator=g)
-    kw = dict(sh_degree=deg, packed=args.packed or sharded, rasterize_mode=mode, distributed=sharded)
+    kw = dict(sh_degree=deg, packed=packed or sharded, rasterize_mode=mode, distributed=sharded)
     cot = {}
 
     def set_cotangents(bounds=None):
@@ -298,20 +345,22 @@ def main():
         kw["tile_stripes"] = True
         stripe_rows = stripe_bounds(math.ceil(H / 16), world)
     set_cotangents(stripe_rows)
-    v_r_host, v_a_host, v_r, v_a = cot["v_r_host"], cot["v_a_host"], cot["v_r"], cot["v_a"]
-    plist = list(params.values())
-    stats = {}
 
     def step(p=params, c=cams, vr=None, va=None):
         vr = cot["v_r"] if vr is None else vr
         va = cot["v_a"] if va is None else va
+        if fwd_only:
+            with torch.no_grad():
+                return b2s.rasterization(p["means"], p["quats"], p["scales"], p["opacities"], p["colors"], c["viewmats"],
+                                         c["Ks"], W, H, **kw)
         for t in p.values():
             t.grad = None
         r, a, m = b2s.rasterization(p["means"], p["quats"], p["scales"], p["opacities"], p["colors"], c["viewmats"],
                                     c["Ks"], W, H, **kw)
         torch.autograd.backward([r, a], [vr, va])
         if world > 1 and not sharded:
-            allreduce_gradients(p.values())
+            with ops._stage("grad_allreduce", launches=0):
+                allreduce_gradients(p.values())
         return r, a, m
 
     def barrier():
@@ -319,21 +368,8 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, steps):
-        barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(steps):
-            fn()
-        e1.record()
-        barrier()
-        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
-        if world > 1:
-            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        return float(ms.item())
-
     balance_log = []
-    if stripes and not args.no_balance:
+    if stripes and balance:
         # feedback load balancing of the stripes (untimed, part of the warm-up): every rank measures its stripe-dependent
         # stages, the bounds are cut again at equal-cost quantiles; three rounds
         STRIPE_STAGES = ("stripe_unpack", "depth_order", "coarse_bin", "composite_fwd", "composite_bwd", "stripe_return")
@@ -349,95 +385,123 @@ def main():
             balance_log.append({"bounds": list(stripe_rows), "ms": [round(c, 3) for c in costs]})
             stripe_rows = rebalance_stripe_bounds(stripe_rows, costs)
             set_cotangents(stripe_rows)
-        v_r_host, v_a_host, v_r, v_a = cot["v_r_host"], cot["v_a_host"], cot["v_r"], cot["v_a"]
-    for _ in range(max(args.warmup, 3)):
+    warm = max(warmup, 3)
+    for _ in range(warm):
         r, a, m = step()
     torch.cuda.synchronize()
     m_last = m
-    n_visible = int((m["radii"] > 0).sum()) if not (args.packed or sharded) else int(m["means2d"].shape[0])
-    stats["n_isects"] = int(m["tiles_per_gauss"].sum(dtype=torch.int64))   # (the per-intersection lists of meta are lazy)
+    stats = {"n_isects": int(m["tiles_per_gauss"].sum(dtype=torch.int64)),      # (the per-intersection lists of meta are lazy)
+             "n_rows_composited": int(m["means2d"].shape[0]) if (packed or sharded) else int((m["radii"] > 0).sum()),
+             "n_coarse_records": int(m_last.get("n_coarse_records") or 0)}
+    # what THIS rank's projection launch sees: its Gaussians into every camera of the job (untimed)
+    with torch.no_grad():
+        all_v, all_k = scene["viewmats"].to(dev), scene["Ks"].to(dev)
+        rad = b2s.fully_fused_projection(params["means"], None, params["quats"], params["scales"],
+                                         all_v if sharded and not stripes else cams["viewmats"],
+                                         all_k if sharded and not stripes else cams["Ks"], W, H)[0]
+        stats["n_visible_projected"] = int((rad > 0).sum())
+        stats["n_cameras_projected"] = int(rad.shape[0])
+        del rad
     # rows compositing reached before saturation (outside the timed region): non-zero opacity cotangent
-    for t in params.values():
-        t.grad = None
-    r, a, m = b2s.rasterization(params["means"], params["quats"], params["scales"], params["opacities"], params["colors"],
-                                cams["viewmats"], cams["Ks"], W, H, **kw)
-    m["opacities"].retain_grad()
-    torch.autograd.backward([r, a], [v_r, v_a])
-    stats["n_reached"] = int((m["opacities"].grad != 0).sum())
+    stats["n_reached"] = None
+    if not fwd_only:
+        for t in params.values():
+            t.grad = None
+        r, a, m = b2s.rasterization(params["means"], params["quats"], params["scales"], params["opacities"], params["colors"],
+                                    cams["viewmats"], cams["Ks"], W, H, **kw)
+        m["opacities"].retain_grad()
+        torch.autograd.backward([r, a], [cot["v_r"], cot["v_a"]])
+        stats["n_reached"] = int((m["opacities"].grad != 0).sum())
     del r, a, m
 
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
+    # ---- the timed region: exactly `steps` steps between barrier + synchronize, one event per step ------------------
+    sampler = ClockSampler(torch.cuda.current_device()) if (clocks and rank == 0) else None
+    if sampler:
         sampler.start()
-    ops.TIMER = ops.StageTimer()
-    ms_total = timed(step, args.steps)
+    if stages:
+        ops.TIMER = ops.StageTimer()
+    barrier()
+    evs = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
+    evs[0].record()
+    for i in range(steps):
+        step()
+        evs[i + 1].record()
+    barrier()
     timer, ops.TIMER = ops.TIMER, None
-    clocks = sampler.stop() if rank == 0 else None
-    stage = timer.summary()
-    ms_per_step = ms_total / args.steps
+    ms_t = torch.tensor([evs[0].elapsed_time(evs[-1])], device=dev)
+    if world > 1:
+        dist.all_reduce(ms_t, op=dist.ReduceOp.MAX)
+    ms_total = float(ms_t.item())
+    per_step = [evs[i].elapsed_time(evs[i + 1]) for i in range(steps)]
+    clk = sampler.stop() if sampler else None
+    stage = timer.summary() if timer is not None else {}
+    ms_per_step = ms_total / steps
     pix_per_step = C_total * W * H
-    value = pix_per_step / (ms_per_step * 1e-3) / 1e6
+    out = {"workload": workload, "multi_gpu": multi_gpu if world > 1 else None, "n_gpus": world, "steps": steps, "warmup": warm,
+           "ms_per_step": ms_per_step, "ms_median": pctl(per_step, 0.5), "ms_p10": pctl(per_step, 0.1), "ms_p90": pctl(per_step, 0.9),
+           "value": pix_per_step / (ms_per_step * 1e-3) / 1e6, "iters_per_s": 1e3 / ms_per_step * C_total,
+           "stats": stats, "stage_ms": stage, "launches": timer.launches if timer is not None else None, "clocks": clk,
+           "stripe_rows": stripe_rows, "stripe_balance_rounds": balance_log, "packed": bool(packed or sharded),
+           "n_local": hi_n - lo_n, "C_total": C_total}
 
     # ---- e2e: host buffers in, host buffers out -----------------------------------------------------------
-    h2d = sum(v.numel() * 4 for v in leaves_host.values()) + sum(v.numel() * 4 for v in cam_host.values()) \
-        + v_r_host.numel() * 4 + v_a_host.numel() * 4
-    d2h = (v_r_host.numel() + v_a_host.numel()) * 4 + sum(v.numel() * 4 for v in leaves_host.values())
+    if e2e_steps:
+        v_r_host, v_a_host = cot["v_r_host"], cot["v_a_host"]
+        h2d = sum(v.numel() * 4 for v in leaves_host.values()) + sum(v.numel() * 4 for v in cam_host.values()) \
+            + (0 if fwd_only else (v_r_host.numel() + v_a_host.numel()) * 4)
+        d2h = (v_r_host.numel() + v_a_host.numel()) * 4 + (0 if fwd_only else sum(v.numel() * 4 for v in leaves_host.values()))
+        # Two slots, three streams: the H2D of step i+1 runs while step i computes and while its results go back (PCIe is
+        # full duplex), so a step costs max(H2D, D2H, compute) instead of their sum.  Every step still moves all of its
+        # inputs in and all of its results out.
+        s_in, s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+        main = torch.cuda.current_stream(dev)
+        slots = []
+        for _ in range(2):
+            slots.append({
+                "p": {k: torch.empty_like(v, device=dev).requires_grad_(not fwd_only) for k, v in leaves_host.items()},
+                "c": {k: torch.empty_like(v, device=dev) for k, v in cam_host.items()},
+                "vr": torch.empty_like(cot["v_r"]), "va": torch.empty_like(cot["v_a"]),
+                "out": {"render": torch.empty(v_r_host.shape).pin_memory(), "alpha": torch.empty(v_a_host.shape).pin_memory()},
+                "grads": {k: torch.empty_like(v).pin_memory() for k, v in leaves_host.items()} if not fwd_only else {},
+                "ev_in": torch.cuda.Event(), "ev_done": torch.cuda.Event(), "ev_out": None, "keep": None,
+            })
+        state = {"i": 0}
 
-    # Two slots, three streams: the H2D of step i+1 runs while step i computes and while its results go back (PCIe is
-    # full duplex), so a step costs max(H2D, D2H, compute) instead of their sum.  Every step still moves all of its
-    # inputs in and all of its results out.
-    s_in, s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
-    main = torch.cuda.current_stream(dev)
-    slots = []
-    for _ in range(2):
-        slots.append({
-            "p": {k: torch.empty_like(v, device=dev).requires_grad_() for k, v in leaves_host.items()},
-            "c": {k: torch.empty_like(v, device=dev) for k, v in cam_host.items()},
-            "vr": torch.empty_like(v_r), "va": torch.empty_like(v_a),
-            "out": {"render": torch.empty(v_r_host.shape).pin_memory(), "alpha": torch.empty(v_a_host.shape).pin_memory()},
-            "grads": {k: torch.empty_like(v).pin_memory() for k, v in leaves_host.items()},
-            "ev_in": torch.cuda.Event(), "ev_done": torch.cuda.Event(), "ev_out": None, "keep": None,
-        })
-    state = {"i": 0}
-
-    def e2e_step():
-        sl = slots[state["i"] % 2]
-        state["i"] += 1
-        if sl["ev_out"] is not None:
-            sl["ev_out"].synchronize()          # the caller has read this slot's host buffers; its device buffers are free
-        with torch.cuda.stream(s_in), torch.no_grad():
-            for k, v in leaves_host.items():
-                sl["p"][k].copy_(v, non_blocking=True)
-            for k, v in cam_host.items():
-                sl["c"][k].copy_(v, non_blocking=True)
-            sl["vr"].copy_(v_r_host, non_blocking=True)
-            sl["va"].copy_(v_a_host, non_blocking=True)
-            sl["ev_in"].record(s_in)
-        main.wait_event(sl["ev_in"])
-        r, a, _ = step(sl["p"], sl["c"], sl["vr"], sl["va"])
-        sl["ev_done"].record(main)
-        sl["keep"] = (r, a)                      # keep the results alive until their copy has run
-        with torch.cuda.stream(s_out), torch.no_grad():
-            s_out.wait_event(sl["ev_done"])
-            sl["out"]["render"].copy_(r.detach(), non_blocking=True)
-            sl["out"]["alpha"].copy_(a.detach(), non_blocking=True)
-            for k in sl["grads"]:
-                sl["grads"][k].copy_(sl["p"][k].grad, non_blocking=True)
-            ev = torch.cuda.Event()
-            ev.record(s_out)
-            sl["ev_out"] = ev
-
-    def e2e_run(steps):
-        for _ in range(steps):
-            e2e_step()
-        for sl in slots:                         # the last results are on the host when the timed region ends
+        def e2e_step():
+            sl = slots[state["i"] % 2]
+            state["i"] += 1
             if sl["ev_out"] is not None:
-                sl["ev_out"].synchronize()
+                sl["ev_out"].synchronize()          # the caller has read this slot's host buffers; its device buffers are free
+            with torch.cuda.stream(s_in), torch.no_grad():
+                for k, v in leaves_host.items():
+                    sl["p"][k].copy_(v, non_blocking=True)
+                for k, v in cam_host.items():
+                    sl["c"][k].copy_(v, non_blocking=True)
+                if not fwd_only:
+                    sl["vr"].copy_(v_r_host, non_blocking=True)
+                    sl["va"].copy_(v_a_host, non_blocking=True)
+                sl["ev_in"].record(s_in)
+            main.wait_event(sl["ev_in"])
+            r, a, _ = step(sl["p"], sl["c"], sl["vr"], sl["va"])
+            sl["ev_done"].record(main)
+            sl["keep"] = (r, a)                      # keep the results alive until their copy has run
+            with torch.cuda.stream(s_out), torch.no_grad():
+                s_out.wait_event(sl["ev_done"])
+                sl["out"]["render"].copy_(r.detach(), non_blocking=True)
+                sl["out"]["alpha"].copy_(a.detach(), non_blocking=True)
+                for k in sl["grads"]:
+                    sl["grads"][k].copy_(sl["p"][k].grad, non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(s_out)
+                sl["ev_out"] = ev
 
-    e2e_steps = args.e2e_steps or max(4, min(args.steps, 10))
-    if args.no_e2e:
-        e2e_ms, e2e_value = None, None
-    else:
+        def e2e_run(n):
+            for _ in range(n):
+                e2e_step()
+            for sl in slots:                         # the last results are on the host when the timed region ends
+                if sl["ev_out"] is not None:
+                    sl["ev_out"].synchronize()
+
         e2e_run(2)
         barrier()
         t0 = time.perf_counter()                 # three streams: wall clock between device-wide synchronisations
@@ -447,7 +511,131 @@ def main():
         if world > 1:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         e2e_ms = float(ms.item()) / e2e_steps
-        e2e_value = pix_per_step / (e2e_ms * 1e-3) / 1e6
+        out["e2e"] = {"value": pix_per_step / (e2e_ms * 1e-3) / 1e6, "unit": UNIT, "ms_per_step": e2e_ms, "h2d_bytes_per_step": h2d,
+                      "d2h_bytes_per_step": d2h, "steps": e2e_steps,
+                      "note": "rasterization() + backward driven from pinned host buffers: every step copies all inputs in and "
+                              "render, alpha and all gradients out; copies of neighbouring steps overlap (2 slots, 3 streams)"}
+    return out
+
+
+def release():
+    """Frees what a finished measurement held (its tensors die with run_gpu's frame)."""
+    import gc
+    gc.collect()
+    torch.cuda.empty_cache()
+
+
+def stage_table(res, peak):
+    """Per-stage times with algorithmic bytes and achieved GB/s of THIS rank's launches."""
+    N, deg, W, H, mode, fwd_only, init = WORKLOADS[res["workload"]]
+    st = res["stats"]
+    tiles = math.ceil(W / 16) * math.ceil(H / 16)
+    key_bits = 32 + tiles.bit_length() + 1
+    K = (deg + 1) ** 2
+    sparse = "bwd_classify" in res["stage_ms"]
+    ab = algorithmic_bytes(res["n_local"], st["n_cameras_projected"], st["n_visible_projected"], st["n_reached"] or 0, st["n_isects"],
+                           st["n_coarse_records"], K, tiles, key_bits, sparse)
+    per_stage = {}
+    for name, s_ in res["stage_ms"].items():
+        b = ab.get(name)
+        gbs = b / (s_["ms_avg"] * 1e-3) / 1e9 if (b and s_["ms_avg"] > 0) else None
+        per_stage[name] = {"ms": round(s_["ms_avg"], 4), "calls_per_step": s_["calls"] / res["steps"], "algorithmic_bytes": b,
+                           "GBps": round(gbs, 1) if gbs else None, "frac_of_peak": round(gbs / peak, 4) if gbs else None}
+    return per_stage
+
+
+def brief(res):
+    """What an `extras` entry keeps of a side measurement."""
+    keys = ("n_gpus", "steps", "warmup", "ms_per_step", "ms_median", "ms_p10", "ms_p90", "value", "iters_per_s", "packed",
+            "stripe_rows", "multi_gpu")
+    o = {k: res[k] for k in keys if res.get(k) is not None}
+    o["unit"] = UNIT
+    o["stats"] = res["stats"]
+    o["stage_ms"] = {k: round(v["ms_avg"], 4) for k, v in res["stage_ms"].items()}
+    return o
+
+
+# ----------------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="b2s", choices=["b2s", "reference"])
+    ap.add_argument("--workload", default=os.environ.get("B2S_BENCH_WORKLOAD", "config3"), choices=sorted(WORKLOADS))
+    ap.add_argument("--packed", action="store_true", help="packed=True layout (default: dense, as ns-train splatfacto)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--e2e-steps", type=int, default=None)
+    ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (profiling runs only)")
+    ap.add_argument("--no-extras", action="store_true", help="skip the side measurements (profiling runs only)")
+    ap.add_argument("--no-balance", action="store_true", help="stripes: keep the even split of the tile rows")
+    ap.add_argument("--multi-gpu", default="sharded", choices=["sharded", "allreduce", "stripes"],
+                    help="N>1: 'sharded' = Gaussians sharded over ranks + exchange of projected splats to the camera "
+                         "owners (rasterization(distributed=True), what the reference's multi-GPU branch runs); "
+                         "'allreduce' = replicated Gaussians + dense-gradient all-reduce (BASELINE config 4); "
+                         "'stripes' = ONE camera, Gaussians sharded over ranks, every rank composites a stripe of tile rows "
+                         "(rasterization(distributed=True, tile_stripes=True), BASELINE config 5; strong scaling)")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    N, deg, W, H, mode, fwd_only, init = WORKLOADS[args.workload]
+    config = workload_config(args.workload, args.packed, max(world, 1), args.multi_gpu)
+
+    # ------------------------------------------------------------------ reference arm: CPU oracle, rank 0 only
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        steps, warmup = max(1, min(args.steps, 30)), min(args.warmup, 5)
+        cb = run_cpu(args.workload, steps, warmup)
+        line = {
+            "impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus,
+            "steps": steps, "warmup": warmup, "ms_per_step": cb["s_per_step"] * 1e3, "higher_is_better": True,
+            "scaling": "strong" if args.multi_gpu == "stripes" else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": config,
+            "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample", "cpu_model")},
+            "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "iters_per_s": cb["iters_per_s_full_frame_equiv"],
+        }
+        print(json.dumps(line))
+        return 0
+
+    # ------------------------------------------------------------------ our arm
+    import torch.distributed as dist
+    assert torch.cuda.is_available(), "bench.py needs a GPU (there is no CPU path)"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    assert world == args.gpus or world == 1, "launch with torchrun --nproc-per-node == --gpus"
+
+    e2e_steps = 0 if args.no_e2e else (args.e2e_steps or max(4, min(args.steps, 10)))
+    res = run_gpu(args.workload, args.multi_gpu, args.steps, args.warmup, packed=args.packed, e2e_steps=e2e_steps,
+                  balance=not args.no_balance, clocks=True)
+    release()
+
+    # ---- side measurements kept in the same line (short; every rank takes part) -------------------------------------
+    extras = {}
+    if not args.no_extras and args.workload == "config3":
+        ex_steps, ex_warm = min(args.steps, 20), 5
+
+        def side(name, workload, multi_gpu, **kw):
+            try:
+                extras[name] = brief(run_gpu(workload, multi_gpu, ex_steps, ex_warm, stages=True, **kw))
+            except Exception as e:      # a side measurement never takes the headline down
+                extras[name] = {"error": f"{type(e).__name__}: {e}"[:300]}
+            release()
+
+        if world == 1:
+            side("config3_packed", "config3", "sharded", packed=True)
+            side("config3_gsplat_init", "config3_init", "sharded")
+            side("config2", "config2", "sharded")
+            side("config1_fwd", "config1", "sharded")
+            side("config5_1gpu", "config5", "stripes")
+        else:
+            side("config5_stripes", "config5", "stripes")
+            side("config4_allreduce", "config3", "allreduce")
 
     if rank != 0:
         if world > 1:
@@ -456,59 +644,45 @@ def main():
 
     # ---- roofline of the dominant HBM-bound kernel ----------------------------------------------------------
     peak, peak_src = peaks()
-    I = stats["n_isects"]
-    tiles = math.ceil(W / 16) * math.ceil(H / 16)
-    key_bits = 32 + (tiles).bit_length() + (1).bit_length()
-    K = (deg + 1) ** 2
-    n_cam_local = C_total if (world > 1 and sharded) else 1
-    if stripes:      # per-rank counters -> whole-job totals are not gathered; report rank 0's
-        pass
-    R = int(m_last.get("n_coarse_records") or 0) if m_last is not None else 0
-    ab = algorithmic_bytes(hi_n - lo_n, n_cam_local, n_visible, stats["n_reached"], I, R, W * H, K, tiles, key_bits)
-    per_stage = {}
-    for name, st_ in stage.items():
-        b = ab.get(name)
-        gbs = b / (st_["ms_avg"] * 1e-3) / 1e9 if (b and st_["ms_avg"] > 0) else None
-        per_stage[name] = {"ms": round(st_["ms_avg"], 4), "calls_per_step": st_["calls"] / args.steps, "algorithmic_bytes": b,
-                           "GBps": round(gbs, 1) if gbs else None, "frac_of_peak": round(gbs / peak, 4) if gbs else None}
-    hbm_stages = {k: v for k, v in per_stage.items() if v["GBps"] and k in ("project_fwd", "sh_bwd", "project_bwd")}
-    dom = max(hbm_stages, key=lambda k: hbm_stages[k]["ms"])
-    kernel_of = {"project_fwd": "project_fwd_kernel", "sh_bwd": "sh_bwd_fused_kernel", "project_bwd": "project_bwd_kernel"}
-    roofline = {"kernel": kernel_of[dom], "stage": dom, "bound": "hbm", "achieved": per_stage[dom]["GBps"], "peak": peak,
-                "unit": "GB/s", "frac": per_stage[dom]["frac_of_peak"], "traffic": NCU_TRAFFIC.get(dom) if args.workload == "config3" and world == 1 else None, "peak_source": peak_src,
-                "note": "largest HBM-bound kernel of the step (one launch per step; CUDA events around the launch, inside the "
-                        "timed region); the compositing kernels are instruction-issue bound (see profiles/), the sorts are "
-                        "L2-resident at this size; per-stage figures under 'stages'"}
+    per_stage = stage_table(res, peak)
+    hbm_stages = {k: v for k, v in per_stage.items() if v["GBps"] and k in ("project_fwd", "sh_bwd", "bwd_classify")}
+    dom = max(hbm_stages, key=lambda k: hbm_stages[k]["ms"]) if hbm_stages else None
+    kernel_of = {"project_fwd": "project_fwd_kernel", "sh_bwd": "sh_zero_kernel + sh_sparse_kernel (sparse) / sh_bwd_fused_kernel",
+                 "bwd_classify": "bwd_classify_kernel"}
+    roofline = None
+    if dom:
+        roofline = {"kernel": kernel_of[dom], "stage": dom, "bound": "hbm", "achieved": per_stage[dom]["GBps"], "peak": peak,
+                    "unit": "GB/s", "frac": per_stage[dom]["frac_of_peak"],
+                    "traffic": NCU_TRAFFIC.get(dom) if args.workload == "config3" and world == 1 else None, "peak_source": peak_src,
+                    "note": "largest HBM-bound kernel of the step (one launch per step; CUDA events around the launch, inside the "
+                            "timed region); algorithmic bytes are those of this rank's launch (its Gaussians into the cameras it "
+                            "projects); the compositing kernels are instruction-issue bound (see profiles/), the sorts are "
+                            "L2-resident at this size; per-stage figures under 'stages'"}
 
+    st = res["stats"]
     line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong" if args.multi_gpu == "stripes" else "weak",
-        "vs_baseline": None, "dtype": "f32",
-        "data": "synthetic",
-        "config": {"workload": f"{args.workload}: {N} random Gaussians, SH deg {deg}, {W}x{H}, {mode}, fwd+bwd, "
-                               f"packed={args.packed or sharded}, " + ("1 camera" if C_total == 1 else "1 camera per GPU") +
-                               ((", Gaussians sharded over ranks, every rank composites a stripe of tile rows of the one camera: "
-                                 "fused pack + NVLink peer-store exchange of projected splats to the stripe owners, gradients "
-                                 "returned by the reverse exchange and summed at the owner") if stripes else
-                                (", Gaussians sharded over ranks, NCCL all-to-all of projected splats to the camera owners, "
-                                 "reverse all-to-all of gradients") if sharded else
-                                (", replicated Gaussians, dense-gradient all-reduce" if world > 1 else "")),
-                   "n_isects": I, "n_visible": n_visible, "n_reached": stats["n_reached"], "n_coarse_records": R,
-                   "l2": "inputs (1.4 GB parameters + 0.3 GB keys) exceed the 126 MB L2",
-                   "parallelism": f"dp{world}", "stripe_rows": stripe_rows, "stripe_balance_rounds": balance_log},
-        "iters_per_s": 1e3 / ms_per_step * C_total,
-        "gpu_launches": timer.launches,
+        "metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": res["warmup"],
+        "warmup_requested": args.warmup, "ms_per_step": res["ms_per_step"], "ms_median": res["ms_median"], "ms_p10": res["ms_p10"],
+        "ms_p90": res["ms_p90"], "higher_is_better": True, "scaling": "strong" if args.multi_gpu == "stripes" else "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
+        "scene_stats": {"n_isects": st["n_isects"], "n_rows_composited": st["n_rows_composited"], "n_reached": st["n_reached"],
+                        "n_coarse_records": st["n_coarse_records"], "n_visible_projected_rank0": st["n_visible_projected"],
+                        "n_cameras_projected": st["n_cameras_projected"], "stripe_rows": res["stripe_rows"],
+                        "stripe_balance_rounds": res["stripe_balance_rounds"]},
+        "iters_per_s": res["iters_per_s"],
+        "gpu_launches": res["launches"],
         "gpu_launches_note": "kernels of libb2s.so launched inside the timed region (per step: project_fwd 1, depth sort 6, "
-                             "coarse binning 5, composite_fwd 1, composite_bwd 1, sh_bwd 4 (classify, dense [returns at once in "
-                             "sparse mode], zero fill, list-driven), project_bwd 2; all hand-written, no library kernels)",
-        "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "steps": e2e_steps, "note": "rasterization() + backward driven from pinned host buffers: every step copies all "
-                "inputs in and render, alpha and all gradients out; copies of neighbouring steps overlap (2 slots, 3 streams)"},
-        "roofline": roofline, "stages": per_stage, "clocks": clocks,
+                             "coarse binning 7, composite_fwd 1, composite_bwd 1, bwd_classify 1, sh_bwd 3 (dense [returns at once in "
+                             "sparse mode], zero fill, list-driven), project_bwd 1; all hand-written, no library kernels)",
+        "e2e": res.get("e2e"), "roofline": roofline, "stages": per_stage, "clocks": res["clocks"], "extras": extras,
     }
     if world == 1 and not args.no_cpu_baseline:
-        cb = run_cpu(args.workload, 1, 0)
+        cb = run_cpu(args.workload, 1, 0, keep_ref=True)
         line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample", "cpu_model")}
+        try:
+            line["parity_check"] = parity_against_oracle(args.workload, cb, dev, args.packed)
+        except Exception as e:
+            line["parity_check"] = {"error": f"{type(e).__name__}: {e}"[:300], "pass": False}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -115,7 +115,9 @@ typedef struct {
     float* v_opacities; /* [N] or NULL */
     float* v_sh_coeffs; /* [N, sh_stride_k, 3] or NULL; rows >= (deg+1)^2 are not touched */
     int32_t stages;         /* 0 = both; 1 = SH colour VJP only (v_sh_coeffs, v_means); 2 = projection VJP only (when
-                               sh_coeffs and v_sh_coeffs are set it ADDS to the v_means a stages == 1 call left) */
+                               sh_coeffs and v_sh_coeffs are set it ADDS to the v_means a stages == 1 call left);
+                               3 = the classify pass alone (needs the workspace), 4 = the SH part of a stages == 1 call after
+                               a stages == 3 call (1 == 3 then 4: lets a caller time the three parts separately) */
     /* optional scratch of b2s_project_bwd_workspace_bytes(N) bytes, 256-byte aligned (NULL: dense kernels only).
      * With it, rows whose cotangents are all zero (occluded: compositing never reached them) are filtered out once:
      * when at most a quarter of the rows is live the gradients are produced by a zero fill plus list-driven kernels.

@@ -466,12 +466,18 @@ def rasterization(
     backgrounds: Optional[Tensor] = None, render_mode: str = "RGB", sparse_grad: bool = False,
     absgrad: bool = False, rasterize_mode: str = "classic", channel_chunk: int = 32,
     distributed: bool = False, camera_model: str = "pinhole", return_fragile: bool = False,
+    tile_window: Optional[Tuple[int, int, int, int]] = None,
 ) -> Tuple[Tensor, Tensor, Dict]:
     """gsplat ``rasterization()`` restated.
 
     Inputs are post-activation.  ``colors`` is [N,D] / [C,N,D] when ``sh_degree`` is
     None, else SH coefficients [N,K,3] / [C,N,K,3].  ``packed`` changes only the
     layout of the intermediate tensors in ``meta``, never the image.
+
+    ``tile_window=(tx0, ty0, tx1, ty1)`` is a checker convenience, not reference semantics: projection and binning
+    run on the whole frame, then only the tiles [tx0,tx1) x [ty0,ty1) are composited (everything else renders as
+    empty) and ``meta`` carries the sorted lists filtered to those tiles -- a full-size scene can then be checked
+    against the CUDA path on a sub-frustum at a CPU cost proportional to the window.
     """
     assert camera_model == "pinhole" and not distributed
     assert render_mode in ("RGB", "D", "ED", "RGB+D", "RGB+ED")
@@ -519,6 +525,13 @@ def rasterization(
         tpg, isect_ids, flatten_ids = isect_tiles(means2d, radii, depths, tile_size, tw, th)
         r_in = (means2d, conics, cols, opac)
         m_radii, m_means2d, m_depths, m_conics, m_opac = radii, means2d, depths, conics, opac
+    if tile_window is not None:
+        tx0, ty0, tx1, ty1 = tile_window
+        tile_bits = (tw * th).bit_length()
+        tile = (isect_ids >> 32) & ((1 << tile_bits) - 1)
+        tyy, txx = torch.div(tile, tw, rounding_mode="floor"), tile % tw
+        keep = (txx >= tx0) & (txx < tx1) & (tyy >= ty0) & (tyy < ty1)
+        isect_ids, flatten_ids = isect_ids[keep], flatten_ids[keep]      # a subsequence of a sorted list stays sorted
     offsets = isect_offset_encode(isect_ids, C, tw, th)
     out = rasterize_to_pixels(*r_in, width, height, tile_size, offsets, flatten_ids, backgrounds,
                               return_fragile=return_fragile)

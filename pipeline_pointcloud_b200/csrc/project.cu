@@ -679,12 +679,14 @@ extern "C" int b2s_project_bwd(const b2s_project_bwd_args* a, b2s_stream_t strea
     B2S_REQUIRE(a->C <= B2S_MAX_CAMERAS_PER_CALL, "too many cameras in one call (loop over chunks)");
     if (a->N == 0) return 0;
     B2S_REQUIRE(a->means && a->quats && a->scales && a->viewmats && a->Ks && a->radii, "null input");
-    B2S_REQUIRE(a->v_means && (a->stages == 1 || (a->v_quats && a->v_scales)), "null gradient output");
-    B2S_REQUIRE(aligned16(a->quats) && (a->stages == 1 || aligned16(a->v_quats)), "quats misaligned");
-    B2S_REQUIRE(a->stages >= 0 && a->stages <= 2, "stages must be 0, 1 or 2");
-    const bool sh = a->sh_coeffs != nullptr && a->v_sh_coeffs != nullptr && a->stages != 2;
-    const bool geom = a->stages != 1;
+    B2S_REQUIRE(a->stages >= 0 && a->stages <= 4, "stages must be 0..4");
+    const bool sh_only = a->stages == 1 || a->stages == 4;
+    B2S_REQUIRE(a->v_means && (sh_only || (a->v_quats && a->v_scales)), "null gradient output");
+    B2S_REQUIRE(aligned16(a->quats) && (sh_only || aligned16(a->v_quats)), "quats misaligned");
+    // stages: 0 everything | 1 classify + SH | 2 projection VJP (after 1, or after 3 and 4) | 3 classify only | 4 SH only (after 3)
     const bool has_sh = a->sh_coeffs != nullptr && a->v_sh_coeffs != nullptr;
+    const bool sh = has_sh && (a->stages == 0 || a->stages == 1 || a->stages == 4);
+    const bool geom = a->stages == 0 || a->stages == 2;
     cudaStream_t st = (cudaStream_t)stream;
     const size_t cam_bytes = ((a->C * sizeof(Camera) + 15) / 16) * 16;
     // sparse mode: needs the caller's workspace, a single camera chunk, and (for the streaming zero fill) an aligned v_sh
@@ -702,7 +704,8 @@ extern "C" int b2s_project_bwd(const b2s_project_bwd_args* a, b2s_stream_t strea
             list_sh = list_geom + ((a->N + 63) / 64) * 64;
         }
     }
-    if (cnt && (a->stages != 2 || !has_sh)) {
+    if (a->stages == 3) B2S_REQUIRE(cnt != nullptr, "stages == 3 needs the sparse-backward workspace");
+    if (cnt && (a->stages == 0 || a->stages == 1 || a->stages == 3 || (a->stages == 2 && !has_sh))) {
         // first (or only) call of this backward: zero the small gradients, build the two lists
         B2S_CUDA(cudaMemsetAsync(cnt, 0, sizeof(BwdCounts), st));
         bwd_classify_kernel<<<(unsigned)cdiv(a->N, 256 * CLS_ROWS), 256, 0, st>>>(*a, has_sh, cnt, list_geom, list_sh);

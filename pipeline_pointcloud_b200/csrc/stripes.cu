@@ -402,7 +402,8 @@ extern "C" int64_t b2s_stripe_ctas(int64_t M) { return cdiv(M > 0 ? M : 1, ST_TH
 extern "C" int b2s_stripe_count(int64_t M, int64_t N, const float* means2d, const int32_t* radii, int32_t tile_size,
                                 int32_t tile_w, int32_t tile_h, const b2s_stripes* stripes, uint16_t* dest_mask, uint32_t* cta_counts,
                                 int64_t* totals, int64_t tag, b2s_stream_t stream) {
-    B2S_REQUIRE(M >= 0 && N > 0 && tile_size > 0 && tile_w > 0 && tile_h > 0 && totals && cta_counts, "bad args");
+    B2S_REQUIRE(M >= 0 && N >= 0 && (N > 0 || M == 0) && tile_size > 0 && tile_w > 0 && tile_h > 0 && totals && cta_counts, "bad args");
+    if (N == 0) N = 1;      // an empty shard (a rank that pruned all of its Gaussians): zero counts, no division by zero
     StripeTable sb;
     B2S_REQUIRE(fill_stripes(sb, stripes, tile_h), "stripes: 1..16 ranks, ascending tile rows from 0 to tile_h");
     B2S_REQUIRE(sb.cams_per_rank == 0 || M <= N * sb.cams_per_rank * sb.world, "more cameras than cams_per_rank * world");
@@ -441,8 +442,9 @@ extern "C" int b2s_stripe_pack(int64_t M, int64_t N, int32_t channels, int64_t g
                                const int32_t* radii, const uint16_t* dest_mask, const uint32_t* cta_prefix, int32_t world,
                                int32_t cams_per_rank, const int64_t* host_dest_base, void* const* host_peer_buffers,
                                b2s_stream_t stream) {
-    B2S_REQUIRE(M >= 0 && N > 0 && channels >= 0 && world >= 1 && world <= B2S_MAX_RANKS, "bad sizes");
+    B2S_REQUIRE(M >= 0 && N >= 0 && channels >= 0 && world >= 1 && world <= B2S_MAX_RANKS, "bad sizes");
     if (M == 0) return 0;
+    B2S_REQUIRE(N > 0, "rows without Gaussians");
     B2S_REQUIRE(means2d && depths && conics && opacities && colors && radii && dest_mask && cta_prefix, "null pointer");
     B2S_REQUIRE(host_dest_base && host_peer_buffers, "null routing table");
     PackArgs a;

@@ -163,8 +163,11 @@ def balanced_stripe_bounds(tiles_per_row: Tensor, world: int) -> List[int]:
     targets = torch.arange(1, world, dtype=torch.float64) * (total / world)
     inner = (torch.searchsorted(cum, targets) + 1).clamp(max=th).tolist()
     bounds = [0] + [int(b) for b in inner] + [th]
-    for i in range(1, len(bounds)):               # monotone
-        bounds[i] = max(bounds[i], bounds[i - 1])
+    min_rows = 1 if th >= world else 0            # no empty stripe unless there are fewer tile rows than ranks
+    for i in range(1, world):                     # ascending, at least min_rows per stripe
+        bounds[i] = max(bounds[i], bounds[i - 1] + min_rows)
+    for i in range(world - 1, 0, -1):
+        bounds[i] = min(bounds[i], bounds[i + 1] - min_rows)
     return bounds
 
 
@@ -318,19 +321,29 @@ class _SymmBuffers:
     """Persistent symmetric-memory exchange buffers (one per direction), mapped into every peer.  Growing them is
     a collective decision taken from the W x W count table, which every rank holds, so all ranks agree."""
     _cache = {}
+    _world = None          # the default process group the cached handles were made under
+
+    @classmethod
+    def clear(cls):
+        cls._cache.clear()
+        cls._world = None
 
     @classmethod
     def get(cls, group, key, n_floats, dev, dtype=torch.float32):
         import torch.distributed._symmetric_memory as symm
-        k = (id(group), key, dev.index)
+        if cls._world is not dist.group.WORLD:       # the job re-initialised torch.distributed: every handle is stale
+            cls.clear()
+            cls._world = dist.group.WORLD
+        pg = group if group is not None else dist.group.WORLD
+        k = (id(pg), key, dev.index)
         cur = cls._cache.get(k)
         if cur is None or cur[0].numel() < n_floats:
             cap = int(n_floats * 1.25) + 4096
             t = symm.empty(cap, dtype=dtype, device=dev)
-            h = symm.rendezvous(t, group if group is not None else dist.group.WORLD)
-            cur = (t, h)
+            h = symm.rendezvous(t, pg)
+            cur = (t, h, pg)                          # holding pg keeps id(pg) from being reused while the entry lives
             cls._cache[k] = cur
-        return cur
+        return cur[0], cur[1]
 
 
 def _i64(vals):
@@ -473,6 +486,56 @@ def _route_impl():
     return os.environ.get("B2S_ROUTE", "p2p")
 
 
+_P2P_OK = {}
+
+
+def peer_route_available(group, dev) -> bool:
+    """Whether the fused peer-store route can run for this group: every rank on the same host, peer access between all
+    the devices, ``torch.distributed._symmetric_memory`` importable and a trial rendezvous succeeding.  The reference's
+    one launch with WORLD_SIZE > 1 is multi-container SageMaker with one GPU per host (source/container/src/main.py:628-642):
+    there (and on PCIe-only boxes) the answer is no and ``rasterization(distributed=True)`` takes the NCCL route.
+    A collective decision (all ranks get the same answer), made once per process group."""
+    import socket
+    import warnings
+    pg = group if group is not None else dist.group.WORLD
+    hit = _P2P_OK.get(id(pg))
+    if hit is not None and hit[0] is pg:
+        return hit[1]
+    world = dist.get_world_size(group)
+    ok = world <= 16
+    why = "more than 16 ranks" if not ok else ""
+    if ok:
+        try:
+            import torch.distributed._symmetric_memory  # noqa: F401
+        except Exception as e:                      # pragma: no cover - depends on the torch build
+            ok, why = False, f"symmetric memory unavailable ({e})"
+    info = [None] * world
+    dist.all_gather_object(info, (socket.gethostname(), int(dev.index)), group=group)
+    if ok and len({h for h, _ in info}) != 1:
+        ok, why = False, "ranks on different hosts"
+    if ok:
+        for _, other in info:
+            if other != dev.index and not torch.cuda.can_device_access_peer(dev.index, other):
+                ok, why = False, f"no peer access {dev.index} -> {other}"
+                break
+    flag = torch.tensor([1 if ok else 0], device=dev)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+    ok = ok and bool(flag.item())
+    if bool(flag.item()):                            # everybody thinks it can: try it (rendezvous failures fall back too)
+        try:
+            _SymmBuffers.get(group, "s_tab", world * world * 4 + world, dev, dtype=torch.int64)
+        except Exception as e:
+            ok, why = False, f"symmetric-memory rendezvous failed ({e})"
+        flag = torch.tensor([1 if ok else 0], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+        ok = bool(flag.item())
+    if not ok and dist.get_rank(group) == 0:
+        warnings.warn("b200-splat: peer-store exchange unavailable (" + (why or "a peer declined") +
+                      "); rasterization(distributed=True) uses the NCCL all-to-all route")
+    _P2P_OK[id(pg)] = (pg, ok)
+    return ok
+
+
 # ----------------------------------------------------------------------------------------------------------
 # rasterization(distributed=True)
 # ----------------------------------------------------------------------------------------------------------
@@ -512,7 +575,8 @@ def rasterization_distributed(means, quats, scales, opacities, colors, viewmats,
 
     if tile_stripes:
         n_world = None
-        if not (_route_impl() == "p2p" and world <= 16):      # (the fused path carries the shard sizes in its count table)
+        fused_route = _route_impl() == "p2p" and peer_route_available(group, means.device)
+        if not fused_route:      # (the fused path carries the shard sizes in its count table)
             n = torch.tensor([N], dtype=torch.int64, device=means.device)
             ns = [torch.empty_like(n) for _ in range(world)]
             dist.all_gather(ns, n, group=group)
@@ -524,8 +588,8 @@ def rasterization_distributed(means, quats, scales, opacities, colors, viewmats,
         rows = (bounds[rank], bounds[rank + 1])
     else:
         # (the fused route carries the shard sizes in its count table)
-        viewmats_all, Ks_all, n_world = all_gather_cameras(viewmats.detach(), Ks.detach(), N, group,
-                                                           with_sizes=not (_route_impl() == "p2p" and world <= 16))
+        fused_route = _route_impl() == "p2p" and peer_route_available(group, means.device)
+        viewmats_all, Ks_all, n_world = all_gather_cameras(viewmats.detach(), Ks.detach(), N, group, with_sizes=not fused_route)
         C_all = viewmats_all.shape[0]
         if C_all != C_local * world:
             raise ValueError("every rank must hold the same number of cameras")
@@ -550,7 +614,6 @@ def rasterization_distributed(means, quats, scales, opacities, colors, viewmats,
     ch = cols.shape[-1]
 
     # ---- route the visible pairs to their owners: (fused) pack -> exchange -> split -------------------------------
-    fused_route = _route_impl() == "p2p" and world <= 16
     dkeys = rowids = counts = None
     if fused_route:
         (means2d_m, depths_m, conics_m, opac_m, cols_m, radii_m, tiles_m, dkeys, rowids, cam_local,
@@ -626,10 +689,15 @@ class _GatherStripes(torch.autograd.Function):
     def forward(ctx, x, pixel_bounds, group):
         rank, world = dist.get_rank(group), dist.get_world_size(group)
         C, _, W, ch = x.shape
-        parts = [x.new_empty(C, pixel_bounds[r + 1] - pixel_bounds[r], W, ch) for r in range(world)]
-        dist.all_gather(parts, x.contiguous(), group=group)
+        rows = [pixel_bounds[r + 1] - pixel_bounds[r] for r in range(world)]
+        mx = max(max(rows), 1)
+        # stripes differ in height (and may be empty): one equal-size collective over buffers padded to the tallest one
+        pad = x.new_zeros(C, mx, W, ch)
+        pad[:, :rows[rank]] = x
+        out = x.new_empty(world, C, mx, W, ch)
+        dist.all_gather_into_tensor(out, pad, group=group)
         ctx.rows = (pixel_bounds[rank], pixel_bounds[rank + 1])
-        return torch.cat(parts, dim=1)
+        return torch.cat([out[r, :, :rows[r]] for r in range(world)], dim=1)
 
     @staticmethod
     def backward(ctx, g):

@@ -190,9 +190,15 @@ class _ProjectFused(torch.autograd.Function):
                     v_sh_coeffs=ptr(v_sh), stages=stages, workspace=ptr(ws), workspace_bytes=ws.numel() if ws is not None else 0)
 
             sparse = ws is not None and c0 == 0      # kernels launched: + classify, zero fill and the two list-driven ones
-            if with_sh and TIMER is not None:     # time the two stages of the call separately (bench.py)
-                with _stage("sh_bwd", launches=4 if sparse else 1):
-                    check(lib.b2s_project_bwd(ctypes.byref(args(1)), st), "b2s_project_bwd")
+            if with_sh and TIMER is not None:     # time the stages of the call separately (bench.py)
+                if sparse:
+                    with _stage("bwd_classify", launches=1):
+                        check(lib.b2s_project_bwd(ctypes.byref(args(3)), st), "b2s_project_bwd")
+                    with _stage("sh_bwd", launches=3):
+                        check(lib.b2s_project_bwd(ctypes.byref(args(4)), st), "b2s_project_bwd")
+                else:
+                    with _stage("sh_bwd", launches=1):
+                        check(lib.b2s_project_bwd(ctypes.byref(args(1)), st), "b2s_project_bwd")
                 with _stage("project_bwd", launches=1):
                     check(lib.b2s_project_bwd(ctypes.byref(args(2)), st), "b2s_project_bwd")
             else:
@@ -654,10 +660,11 @@ class _RasterizeToPixels(torch.autograd.Function):
             render_colors=ptr(render), render_alphas=ptr(alphas), last_ids=ptr(last_ids), final_T=ptr(final_T),
             bin_offsets=ptr(isect_offsets) if bins is not None else None, bin_recs=ptr(recs),
             bin_ids=ptr(flatten_ids) if bins is not None else None, tile_row_lo=row_lo, tile_row_hi=row_hi)
-        if row_lo == row_hi == 0 and th > 0:        # an empty window at row 0 would read as "no window"
-            return render, alphas
-        with _stage("composite_fwd"):
-            check(L.lib().b2s_composite_fwd(ctypes.byref(a), L.stream_ptr(dev)), "b2s_composite_fwd")
+        # an empty window (a rank whose stripe holds no tile row) launches nothing, forward or backward; (0, 0) would
+        # read as "no window" in the C ABI, so it never gets there
+        if row_hi > row_lo:
+            with _stage("composite_fwd"):
+                check(L.lib().b2s_composite_fwd(ctypes.byref(a), L.stream_ptr(dev)), "b2s_composite_fwd")
         ctx.save_for_backward(means2d, conics, colors, opacities, backgrounds, isect_offsets, flatten_ids, alphas,
                               last_ids, final_T, recs)
         ctx.cfg = (width, height, tile_size, absgrad, C, tw, th, n_list, row_lo, row_hi)
@@ -693,8 +700,9 @@ class _RasterizeToPixels(torch.autograd.Function):
             v_means2d_abs=ptr(v_abs), v_conics=ptr(v_conics), v_colors=ptr(v_colors), v_opacities=ptr(v_opac),
             bin_offsets=ptr(isect_offsets) if use_bins else None, bin_recs=ptr(recs),
             bin_ids=ptr(flatten_ids) if use_bins else None, tile_row_lo=row_lo, tile_row_hi=row_hi)
-        with _stage("composite_bwd"):
-            check(L.lib().b2s_composite_bwd(ctypes.byref(a), L.stream_ptr(dev)), "b2s_composite_bwd")
+        if row_hi > row_lo:                         # empty window: the zero-filled slab is the gradient
+            with _stage("composite_bwd"):
+                check(L.lib().b2s_composite_bwd(ctypes.byref(a), L.stream_ptr(dev)), "b2s_composite_bwd")
         v_bg = None
         if backgrounds is not None and ctx.needs_input_grad[4]:
             v_bg = (v_render * final_T.abs()[..., None]).sum(dim=(1, 2))

@@ -102,35 +102,45 @@ def test_window_render_is_the_rows_of_the_whole_render(b2s, use_bins):
 # 2 GPUs: the whole stripe path
 # ----------------------------------------------------------------------------------------------------------
 N2, DEG, W2, H2, C2 = 8000, 3, 176, 150, 2
-WORLD = 2
+TH2 = (H2 + 15) // 16          # 10 tile rows
+# (world, stripe bounds): even-ish, uneven, and with EMPTY stripes (a rank that owns no tile row still projects its shard,
+# takes part in the exchange and gets the gradients of its Gaussians back)
+STRIPE_CASES = {
+    "w2": (2, [0, 4, TH2]),
+    "w2_empty_first": (2, [0, 0, TH2]),
+    "w4_uneven_one_empty": (4, [0, 3, 3, 7, TH2]),
+    "w8_uneven_one_empty": (8, [0, 1, 3, 3, 4, 6, 7, 9, TH2]),
+}
 
 
-def _worker(rank, port, out, route):
+def _worker(rank, world, bounds, port, out, route):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     os.environ["B2S_ROUTE"] = route
     torch.cuda.set_device(rank)
-    dist.init_process_group("nccl", rank=rank, world_size=WORLD, device_id=torch.device("cuda", rank))
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
     try:
         import pipeline_pointcloud_b200 as b2s
         from pipeline_pointcloud_b200.distributed import gather_stripes
         a = scene_args(N2, DEG, C2, W2, H2, seed=41)
-        a["scales"][:200] *= 5.0                      # splats that straddle the stripe boundary
+        a["scales"][:200] *= 5.0                      # splats that straddle the stripe boundaries
         dev = torch.device("cuda", rank)
-        lo, hi = rank * N2 // WORLD, (rank + 1) * N2 // WORLD
+        lo, hi = rank * N2 // world, (rank + 1) * N2 // world
         shard = {k: a[k][lo:hi].to(dev).requires_grad_() for k in LEAVES}
         g = torch.Generator().manual_seed(5)
         v_r = torch.rand(C2, H2, W2, 3, generator=g).to(dev)
         v_a = torch.rand(C2, H2, W2, 1, generator=g).to(dev)
-        bounds = [0, 4, (H2 + 15) // 16]
-        r, al, m = b2s.rasterization(shard["means"], shard["quats"], shard["scales"], shard["opacities"], shard["colors"],
-                                     a["viewmats"].to(dev), a["Ks"].to(dev), W2, H2, sh_degree=DEG, packed=True,
-                                     rasterize_mode="antialiased", distributed=True, tile_stripes=True, stripe_rows=bounds)
-        y0, y1 = m["stripe_pixel_rows"]
-        assert r.shape == (C2, y1 - y0, W2, 3)
-        full_r, full_a = gather_stripes(r, m), gather_stripes(al, m)
-        assert full_r.shape == (C2, H2, W2, 3)
-        torch.autograd.backward([full_r, full_a], [v_r, v_a])      # every rank evaluates the same "loss" on the full image
+        for it in range(2):                           # twice: the second pass reuses the exchange buffers and the table
+            for t in shard.values():
+                t.grad = None
+            r, al, m = b2s.rasterization(shard["means"], shard["quats"], shard["scales"], shard["opacities"], shard["colors"],
+                                         a["viewmats"].to(dev), a["Ks"].to(dev), W2, H2, sh_degree=DEG, packed=True,
+                                         rasterize_mode="antialiased", distributed=True, tile_stripes=True, stripe_rows=bounds)
+            y0, y1 = m["stripe_pixel_rows"]
+            assert r.shape == (C2, y1 - y0, W2, 3)
+            full_r, full_a = gather_stripes(r, m), gather_stripes(al, m)
+            assert full_r.shape == (C2, H2, W2, 3)
+            torch.autograd.backward([full_r, full_a], [v_r, v_a])      # every rank evaluates the same "loss" on the full image
         torch.save({"render": full_r.detach().cpu(), "alpha": full_a.detach().cpu(),
                     "grads": {k: shard[k].grad.cpu() for k in LEAVES}, "isect_ids": m["isect_ids"].cpu(),
                     "gids": m["gaussian_ids"][m["flatten_ids"].long()].cpu(), "cams": m["camera_ids"][m["flatten_ids"].long()].cpu()},
@@ -139,10 +149,15 @@ def _worker(rank, port, out, route):
         dist.destroy_process_group()
 
 
-@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
-@pytest.mark.parametrize("route", ["p2p", "nccl"])
-def test_tile_stripes_match_single_gpu(b2s, tmp_path, route):
-    mp.spawn(_worker, args=(29720 + (route == "nccl"), str(tmp_path), route), nprocs=WORLD, join=True)
+@pytest.mark.parametrize("case,route", [("w2", "p2p"), ("w2", "nccl"), ("w2_empty_first", "p2p"), ("w2_empty_first", "nccl"),
+                                        ("w4_uneven_one_empty", "p2p"), ("w4_uneven_one_empty", "nccl"),
+                                        ("w8_uneven_one_empty", "p2p")])
+def test_tile_stripes_match_single_gpu(b2s, tmp_path, case, route):
+    world, bounds = STRIPE_CASES[case]
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
+    port = 29720 + 7 * list(STRIPE_CASES).index(case) + (route == "nccl")
+    mp.spawn(_worker, args=(world, bounds, port, str(tmp_path), route), nprocs=world, join=True)
     a = scene_args(N2, DEG, C2, W2, H2, seed=41)
     a["scales"][:200] *= 5.0
     full = {k: (a[k].cuda().requires_grad_() if k in LEAVES else a[k].cuda()) for k in a}
@@ -152,12 +167,12 @@ def test_tile_stripes_match_single_gpu(b2s, tmp_path, route):
     v_r = torch.rand(C2, H2, W2, 3, generator=g)
     v_a = torch.rand(C2, H2, W2, 1, generator=g)
     torch.autograd.backward([r, al], [v_r.cuda(), v_a.cuda()])
-    tw, th = (W2 + 15) // 16, (H2 + 15) // 16
+    tw, th = (W2 + 15) // 16, TH2
     ids = m["isect_ids"].cpu()
     gids = m["gaussian_ids"][m["flatten_ids"].long()].cpu()
     trow = ((ids >> 32) & ((1 << (tw * th).bit_length()) - 1)) // tw
-    bounds = [0, 4, th]
-    for rank in range(WORLD):
+    total = 0
+    for rank in range(world):
         got = torch.load(os.path.join(str(tmp_path), f"rank{rank}.pt"))
         # same per-tile lists in the same order => the very same arithmetic per pixel
         assert torch.equal(got["render"], r.detach().cpu()) and torch.equal(got["alpha"], al.detach().cpu())
@@ -165,7 +180,9 @@ def test_tile_stripes_match_single_gpu(b2s, tmp_path, route):
         keep = (trow >= bounds[rank]) & (trow < bounds[rank + 1])
         assert torch.equal(got["isect_ids"], ids[keep])
         assert torch.equal(got["gids"], gids[keep])
-        lo, hi = rank * N2 // WORLD, (rank + 1) * N2 // WORLD
+        total += int(keep.sum())
+        lo, hi = rank * N2 // world, (rank + 1) * N2 // world
         for k in LEAVES:      # each rank holds the complete gradient of its own shard (summed over stripes and cameras)
             rel, bad = grad_report(got["grads"][k], full[k].grad[lo:hi])
             assert rel < 1e-4, (rank, k, rel)
+    assert total == ids.numel()                     # the stripes partition the single-GPU list
