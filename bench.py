@@ -139,15 +139,16 @@ class ClockSampler:
 # ----------------------------------------------------------------------------------------------------------
 # algorithmic bytes per stage (DESIGN.md "Measurement")
 # ----------------------------------------------------------------------------------------------------------
-def algorithmic_bytes(N, C, V, Vt, I, R, K, n_tiles, key_bits, sparse_bwd):
+def algorithmic_bytes(N, C, V, Vt, I, R, K, n_tiles, key_bits, sparse_bwd, V_any=None):
     """Compulsory HBM traffic per stage of ONE rank's launch (every input read once, every output written once; DESIGN.md
     section 4).  N = Gaussians the rank projects, C = cameras it projects them into, V = visible (camera, Gaussian)
     rows of THAT projection, Vt = rows compositing reached (non-zero cotangent), I = tile intersections, R = coarse-bin
     records.  The compositing stages are instruction-issue bound, not HBM bound: no figure."""
     M = C * N
     p = math.ceil(key_bits / 8)
+    V_any = V if V_any is None else V_any                           # Gaussians visible in at least one camera: SH rows read
     b = {
-        "project_fwd": N * 44 + V * 12 * K + M * 60,               # params + SH rows of visible + per-pair outputs (incl. keys)
+        "project_fwd": N * 44 + V_any * 12 * K + M * 60,           # params + SH rows of the visible Gaussians + per-pair outputs (incl. keys)
         # reference-shaped lists (B2S_BINNING=tiles)
         "isect_scan": M * 8,
         "isect_fill": M * 20 + I * 12,
@@ -400,6 +401,7 @@ def run_gpu(workload, multi_gpu, steps, warmup, packed=False, e2e_steps=0, stage
                                          all_v if sharded and not stripes else cams["viewmats"],
                                          all_k if sharded and not stripes else cams["Ks"], W, H)[0]
         stats["n_visible_projected"] = int((rad > 0).sum())
+        stats["n_visible_any_camera"] = int((rad > 0).any(dim=0).sum())
         stats["n_cameras_projected"] = int(rad.shape[0])
         del rad
     # rows compositing reached before saturation (outside the timed region): non-zero opacity cotangent
@@ -534,7 +536,7 @@ def stage_table(res, peak):
     K = (deg + 1) ** 2
     sparse = "bwd_classify" in res["stage_ms"]
     ab = algorithmic_bytes(res["n_local"], st["n_cameras_projected"], st["n_visible_projected"], st["n_reached"] or 0, st["n_isects"],
-                           st["n_coarse_records"], K, tiles, key_bits, sparse)
+                           st["n_coarse_records"], K, tiles, key_bits, sparse, V_any=st["n_visible_any_camera"])
     per_stage = {}
     for name, s_ in res["stage_ms"].items():
         b = ab.get(name)

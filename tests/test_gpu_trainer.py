@@ -33,9 +33,16 @@ def make_dataset(root, n_views=6, W=160, H=112, N=1500):
                        names, W, H, s["means"][sel].numpy().astype(np.float64), rgb)
 
 
+def main(argv):
+    """One in-process rank on cuda:0 (main() itself would spawn one worker per visible GPU, as upstream's cli() does: that
+    launch is covered by the _reference_launch tests below)."""
+    from pipeline_pointcloud_b200.simple_trainer import parse_args, train
+    print(f"checkpoint: {train(parse_args(argv), 0, 1, 0)}")
+    return 0
+
+
 def test_train_on_synthetic_colmap_dataset(tmp_path, capsys):
     from pipeline_pointcloud_b200 import export
-    from pipeline_pointcloud_b200.simple_trainer import main
     data, out = str(tmp_path / "data"), str(tmp_path / "out")
     make_dataset(data)
     rc = main(["default", "--max_steps", "700", "--result-dir", out, "--data_factor", "1", "--steps_scaler", "1.0", "--disable_viewer",
@@ -59,7 +66,6 @@ def test_train_on_synthetic_colmap_dataset(tmp_path, capsys):
 
 
 def test_mcmc_strategy_trains_and_grows(tmp_path, capsys):
-    from pipeline_pointcloud_b200.simple_trainer import main
     data, out = str(tmp_path / "data"), str(tmp_path / "out")
     make_dataset(data)
     rc = main(["mcmc", "--max_steps", "720", "--result-dir", out, "--data_factor", "1", "--steps_scaler", "1.0", "--disable_viewer",
