@@ -12,6 +12,9 @@
 //    the backward writes v_coeffs through the same tile so the 1.1 GB gradient goes out coalesced,
 //  * rows are only fetched when some lane of the warp sees its Gaussian in some camera,
 //  * the forward also emits tiles_per_gauss so binning needs no extra pass over means2d/radii.
+#include <cuda.h>      // CUtensorMap (types only: the encoder is fetched with cudaGetDriverEntryPoint, libcuda is not linked)
+#include <stdlib.h>
+
 #include "b2s_math.cuh"
 #include "common.cuh"
 
@@ -211,6 +214,164 @@ __global__ void __launch_bounds__(FWD_THREADS) project_fwd_kernel(const b2s_proj
             r = fmaxf(r + 0.5f, 0.f); g = fmaxf(g + 0.5f, 0.f); b = fmaxf(b + 0.5f, 0.f);
         }
         a.colors[3 * i] = r; a.colors[3 * i + 1] = g; a.colors[3 * i + 2] = b;
+    }
+}
+
+// =================================================================================================
+// forward, TMA variant (degree-3 coefficient tensors, [N,16,3] contiguous): the CTA's 256 coefficient rows (48 KB) are
+// fetched by the tensor-memory accelerator as two 2-D boxes -- floats [0,32) of every row with the 128-byte swizzle,
+// floats [32,48) with the 64-byte swizzle -- issued by ONE thread at kernel start, so the 1.1 GB coefficient stream is
+// in flight while all 256 threads do the projection arithmetic, and lands in shared memory without passing through
+// registers (the LDG.128 + STS.128 round trip of the kernel above).  The hardware XOR-swizzle (16-byte chunk index ^ row
+// bits) makes the per-thread row reads conflict free on dense, unpadded rows.  Completion is an mbarrier transaction count.
+// SASS: UTMALDG + SYNCS.  Rows beyond N are zero-filled by the accelerator (out-of-bounds fill), so the tail needs no mask.
+// =================================================================================================
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t mbar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mbar), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t mbar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t mbar, uint32_t parity) {
+    uint32_t ok, spins = 0;
+    do {
+        asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(ok) : "r"(mbar), "r"(parity) : "memory");
+        if (!ok && ++spins > (1u << 24)) __trap();      // a copy that never completes is a bug: fail, do not hang the GPU
+    } while (!ok);
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t mbar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                 ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(mbar) : "memory");
+}
+
+constexpr int TMA_A_BYTES = FWD_THREADS * 128, TMA_B_BYTES = FWD_THREADS * 64;   // 32 KB + 16 KB per CTA
+
+__global__ void __launch_bounds__(FWD_THREADS) project_fwd_tma_kernel(const b2s_project_fwd_args a,
+                                                                      const __grid_constant__ CUtensorMap map_a,
+                                                                      const __grid_constant__ CUtensorMap map_b) {
+    extern __shared__ unsigned char smem_raw[];
+    __shared__ __align__(8) unsigned long long s_mbar;
+    // 1024-byte aligned tile base (the 128-byte swizzle pattern repeats every 1 KB of shared-memory ADDRESS)
+    const uint32_t raw = smem_u32(smem_raw);
+    const uint32_t pad = ((raw + 1023u) & ~1023u) - raw;
+    unsigned char* tile_a = smem_raw + pad;
+    unsigned char* tile_b = tile_a + TMA_A_BYTES;
+    Camera* cams = reinterpret_cast<Camera*>(tile_b + TMA_B_BYTES);
+    const float W = (float)a.width, H = (float)a.height;
+    const uint32_t mbar = smem_u32(&s_mbar);
+    if (threadIdx.x == 0) mbar_init(mbar, 1);
+    load_cameras(cams, a.C, a.viewmats, a.Ks, a.campos, W, H);      // ends with __syncthreads: the barrier is initialised for all
+    const int64_t row0 = (int64_t)blockIdx.x * FWD_THREADS;
+    if (threadIdx.x == 0) {
+        mbar_expect_tx(mbar, TMA_A_BYTES + TMA_B_BYTES);
+        tma_load_2d(smem_u32(tile_a), &map_a, 0, (int)row0, mbar);
+        tma_load_2d(smem_u32(tile_b), &map_b, 32, (int)row0, mbar);
+    }
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t n = row0 + threadIdx.x;
+    const bool live = n < a.N;
+    const int64_t nc = live ? n : a.N - 1;  // clamp so every lane can run the same code
+
+    float mean[3], q[4], s[3];
+    mean[0] = __ldg(a.means + 3 * nc); mean[1] = __ldg(a.means + 3 * nc + 1); mean[2] = __ldg(a.means + 3 * nc + 2);
+    {
+        float4 qq = __ldg(reinterpret_cast<const float4*>(a.quats) + nc);
+        q[0] = qq.x; q[1] = qq.y; q[2] = qq.z; q[3] = qq.w;
+    }
+    s[0] = __ldg(a.scales + 3 * nc); s[1] = __ldg(a.scales + 3 * nc + 1); s[2] = __ldg(a.scales + 3 * nc + 2);
+    const float opac = a.opacities ? __ldg(a.opacities + nc) : 1.f;
+
+    Rot R; float qn[4], qnorm, M[9]; Sym3 S;
+    quat_to_rotmat(q, R, qn, qnorm);
+    covar_from_rot_scale(R, s, M, S);
+
+    unsigned long long vis = 0ull;
+    int my_tiles = 0, my_coarse = 0;
+    for (int c = 0; c < a.C; ++c) {
+        ProjOut o;
+        project_one(cams[c], mean, S, W, H, a.eps2d, a.near_plane, a.far_plane, a.radius_clip, o, nullptr);
+        if (!live) continue;
+        const int64_t i = (int64_t)c * a.N + n;
+        a.radii[i] = o.radius;
+        reinterpret_cast<float2*>(a.means2d)[i] = make_float2(o.x2d, o.y2d);
+        a.depths[i] = o.depth;
+        a.conics[3 * i] = o.conic_a; a.conics[3 * i + 1] = o.conic_b; a.conics[3 * i + 2] = o.conic_c;
+        if (a.compensations) a.compensations[i] = o.comp;
+        if (a.opacities_out) a.opacities_out[i] = a.antialiased ? opac * o.comp : opac;  // comp == 0 on culled rows
+        if (a.tiles_per_gauss) {
+            int cnt = 0;
+            if (o.radius > 0) {
+                int x0, y0, x1, y1;
+                tile_rect(o.x2d, o.y2d, o.radius, (float)a.tile_size, a.tile_w, a.tile_h, x0, y0, x1, y1);
+                cnt = (x1 - x0) * (y1 - y0);
+                if (cnt > 0)
+                    my_coarse += (((x1 + B2S_COARSE - 1) / B2S_COARSE) - x0 / B2S_COARSE) *
+                                 (((y1 + B2S_COARSE - 1) / B2S_COARSE) - y0 / B2S_COARSE);
+            }
+            a.tiles_per_gauss[i] = cnt;
+            my_tiles += cnt;
+        }
+        if (a.depth_keys) a.depth_keys[i] = o.radius > 0 ? __float_as_uint(o.depth) : 0xFFFFFFFFu;
+        if (a.row_ids) a.row_ids[i] = (int32_t)i;
+        if (o.radius > 0) vis |= 1ull << c;
+    }
+
+    if (a.total_isects) {      // (see project_fwd_kernel)
+        __shared__ int s_tot[3][FWD_THREADS / 32];
+        int wsum = my_tiles, vcount = __popcll(vis), csum = my_coarse;
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) {
+            wsum += __shfl_xor_sync(FULL, wsum, d);
+            vcount += __shfl_xor_sync(FULL, vcount, d);
+            csum += __shfl_xor_sync(FULL, csum, d);
+        }
+        if (lane == 0) { s_tot[0][warp] = wsum; s_tot[1][warp] = vcount; s_tot[2][warp] = csum; }
+        __syncthreads();
+        if (threadIdx.x < 3) {
+            int tsum = 0;
+#pragma unroll
+            for (int w = 0; w < FWD_THREADS / 32; ++w) tsum += s_tot[threadIdx.x][w];
+            if (tsum) atomicAdd(reinterpret_cast<unsigned long long*>(a.total_isects) + 4 * (blockIdx.x % B2S_TOTAL_SLOTS) + threadIdx.x,
+                                (unsigned long long)tsum);
+        }
+    }
+
+    mbar_wait(mbar, 0);            // the 48 KB of coefficient rows have landed (every thread observes the phase flip itself)
+    if (!live) return;
+    // row r = threadIdx.x; 16-byte chunk j of the row: j < 8 in box A at chunk (j ^ (r & 7)), j >= 8 in box B at ((j - 8) ^ ((r >> 1) & 3))
+    const unsigned r = threadIdx.x;
+    const float4* row_a = reinterpret_cast<const float4*>(tile_a + r * 128);
+    const float4* row_b = reinterpret_cast<const float4*>(tile_b + r * 64);
+    const unsigned xa = r & 7u, xb = (r >> 1) & 3u;
+    for (int c = 0; c < a.C; ++c) {
+        const int64_t i = (int64_t)c * a.N + n;
+        float cr = 0.f, cg = 0.f, cb = 0.f;
+        if ((vis >> c) & 1ull) {
+            float dx = mean[0] - cams[c].campos[0], dy = mean[1] - cams[c].campos[1], dz = mean[2] - cams[c].campos[2];
+            float inv = 1.f / fmaxf(sqrtf(dx * dx + dy * dy + dz * dz), 1e-12f);
+            float Y[16];
+            sh_basis(3, dx * inv, dy * inv, dz * inv, Y);
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {          // 4 bases = 12 floats = three 16-byte chunks
+                float4 ch[3];
+#pragma unroll
+                for (int t = 0; t < 3; ++t) {
+                    const int j = 3 * g + t;
+                    ch[t] = j < 8 ? row_a[(unsigned)j ^ xa] : row_b[(unsigned)(j - 8) ^ xb];
+                }
+                const float4 c0 = ch[0], c1 = ch[1], c2 = ch[2];
+                cr += Y[4 * g] * c0.x; cg += Y[4 * g] * c0.y; cb += Y[4 * g] * c0.z;
+                cr += Y[4 * g + 1] * c0.w; cg += Y[4 * g + 1] * c1.x; cb += Y[4 * g + 1] * c1.y;
+                cr += Y[4 * g + 2] * c1.z; cg += Y[4 * g + 2] * c1.w; cb += Y[4 * g + 2] * c2.x;
+                cr += Y[4 * g + 3] * c2.y; cg += Y[4 * g + 3] * c2.z; cb += Y[4 * g + 3] * c2.w;
+            }
+            cr = fmaxf(cr + 0.5f, 0.f); cg = fmaxf(cg + 0.5f, 0.f); cb = fmaxf(cb + 0.5f, 0.f);
+        }
+        a.colors[3 * i] = cr; a.colors[3 * i + 1] = cg; a.colors[3 * i + 2] = cb;
     }
 }
 
@@ -638,6 +799,38 @@ __global__ void __launch_bounds__(BWD_THREADS) project_bwd_sparse_kernel(const b
 
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
+// cuTensorMapEncodeTiled through the runtime (no link-time dependency on libcuda: the library must load on a box without a driver)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn tensor_map_encoder() {
+    const char* env = getenv("B2S_PROJECT_TMA");
+    if (env && env[0] == '0') return nullptr;                // A/B switch: the LDG/STS kernel
+    static EncodeTiledFn fn = []() -> EncodeTiledFn {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess)
+            return nullptr;
+        return reinterpret_cast<EncodeTiledFn>(p);
+    }();
+    return fn;
+}
+// the two boxes of the [N,48] fp32 coefficient tensor: floats [0,32) (128-byte swizzle) and [32,48) (64-byte swizzle) of 256 rows
+static bool sh_tensor_maps(const float* coeffs, int64_t N, CUtensorMap* map_a, CUtensorMap* map_b) {
+    EncodeTiledFn enc = tensor_map_encoder();
+    if (!enc || N <= 0 || N >= (1LL << 31)) return false;
+    const cuuint64_t gdim[2] = {48, (cuuint64_t)N};
+    const cuuint64_t gstride[1] = {192};
+    const cuuint32_t estr[2] = {1, 1};
+    const cuuint32_t box_a[2] = {32, (cuuint32_t)FWD_THREADS}, box_b[2] = {16, (cuuint32_t)FWD_THREADS};
+    void* g = const_cast<float*>(coeffs);
+    if (enc(map_a, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, g, gdim, gstride, box_a, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+        return false;
+    return enc(map_b, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, g, gdim, gstride, box_b, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 }  // namespace b2s
 
 using namespace b2s;
@@ -659,6 +852,16 @@ extern "C" int b2s_project_fwd(const b2s_project_fwd_args* a, b2s_stream_t strea
     }
     if (a->tiles_per_gauss) B2S_REQUIRE(a->tile_size > 0 && a->tile_w > 0 && a->tile_h > 0, "bad tile geometry");
     const bool vec = sh && K == 16 && a->sh_stride_k == 16 && aligned16(a->sh_coeffs);
+    if (vec) {      // Blackwell data path: the coefficient rows arrive through the tensor-memory accelerator
+        alignas(64) CUtensorMap map_a, map_b;
+        if (sh_tensor_maps(a->sh_coeffs, a->N, &map_a, &map_b)) {
+            const size_t smem_tma = 1024 + TMA_A_BYTES + TMA_B_BYTES + ((a->C * sizeof(Camera) + 15) / 16) * 16;
+            B2S_CUDA(cudaFuncSetAttribute(project_fwd_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tma));
+            project_fwd_tma_kernel<<<(unsigned)cdiv(a->N, FWD_THREADS), FWD_THREADS, smem_tma, (cudaStream_t)stream>>>(*a, map_a, map_b);
+            B2S_LAUNCH_CHECK();
+            return 0;
+        }
+    }
     size_t smem = ((a->C * sizeof(Camera) + 15) / 16) * 16;
     if (sh) smem += (size_t)(FWD_THREADS / 32) * 32 * sh_row_stride(K) * sizeof(float);
     dim3 grid((unsigned)cdiv(a->N, FWD_THREADS));

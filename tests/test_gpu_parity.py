@@ -357,3 +357,30 @@ def test_sparse_backward_equals_dense_backward(b2s, monkeypatch, C, deg):
         assert x.shape == y.shape
         assert ((x == 0) == (y == 0)).all(), name                 # the same rows are touched
         assert grad_report(x, y)[0] < 1e-5, name
+
+
+@pytest.mark.parametrize("N,C", [(70_001, 1), (5000, 3), (255, 1)])
+def test_tma_coefficient_path_equals_ldg_path(b2s, monkeypatch, N, C):
+    """Stage 1 with the degree-3 coefficient rows fetched by the tensor-memory accelerator (swizzled boxes, mbarrier) must
+    produce bit for bit what the LDG/STS kernel produces (same arithmetic order), tail CTA included."""
+    from pipeline_pointcloud_b200 import ops
+    W, H = 160, 96
+    a = scene_args(N, 3, C, W, H, seed=23, stress=True)
+    g = {k: v.cuda() for k, v in a.items()}
+    outs = {}
+    for mode in ("1", "0"):
+        monkeypatch.setenv("B2S_PROJECT_TMA", mode)
+        o = ops._ProjectFused.apply(g["means"], g["quats"], g["scales"], g["opacities"], g["colors"], g["viewmats"], g["Ks"], None,
+                                    W, H, 0.3, 0.01, 1e10, 0.0, True, False, 3, 16)
+        torch.cuda.synchronize()
+        outs[mode] = [t.clone() for t in o]
+    assert (outs["1"][0] > 0).sum() > N // 4
+    for x, y in zip(outs["1"], outs["0"]):
+        assert torch.equal(x, y)
+    # and against the fp64 oracle
+    radii = outs["1"][0].cpu()
+    campos = torch.linalg.inv(a["viewmats"])[:, :3, 3]
+    dirs = a["means"][None] - campos[:, None]
+    ref = torch.clamp_min(O.spherical_harmonics(3, dirs.double(), a["colors"][None].expand(C, N, 16, 3).double(), radii > 0) + 0.5, 0.0)
+    ref = ref * (radii > 0)[..., None]
+    assert (outs["1"][6].cpu().double() - ref).abs().max() < 2e-5
