@@ -149,6 +149,9 @@ def algorithmic_bytes(N, C, V, Vt, I, R, K, n_tiles, key_bits, sparse_bwd, V_any
     V_any = V if V_any is None else V_any                           # Gaussians visible in at least one camera: SH rows read
     b = {
         "project_fwd": N * 44 + V_any * 12 * K + M * 60,           # params + SH rows of the visible Gaussians + per-pair outputs (incl. keys)
+        # multi-GPU direct route: the same reads, dense radii out, and one 52-byte record per visible row over NVLink
+        # (a straddling row of a stripe job leaves once per stripe: counted once here)
+        "route_project": N * 44 + N * 12 * K + M * 4 + V * 52,
         # reference-shaped lists (B2S_BINNING=tiles)
         "isect_scan": M * 8,
         "isect_fill": M * 20 + I * 12,
@@ -373,7 +376,7 @@ def run_gpu(workload, multi_gpu, steps, warmup, packed=False, e2e_steps=0, stage
     if stripes and balance:
         # feedback load balancing of the stripes (untimed, part of the warm-up): every rank measures its stripe-dependent
         # stages, the bounds are cut again at equal-cost quantiles; three rounds
-        STRIPE_STAGES = ("stripe_unpack", "depth_order", "coarse_bin", "composite_fwd", "composite_bwd", "stripe_return")
+        STRIPE_STAGES = ("stripe_unpack", "route_gather", "depth_order", "coarse_bin", "composite_fwd", "composite_bwd", "stripe_return")
         step(); step()
         for _ in range(3):
             ops.TIMER = ops.StageTimer()
@@ -647,9 +650,10 @@ def main():
     # ---- roofline of the dominant HBM-bound kernel ----------------------------------------------------------
     peak, peak_src = peaks()
     per_stage = stage_table(res, peak)
-    hbm_stages = {k: v for k, v in per_stage.items() if v["GBps"] and k in ("project_fwd", "sh_bwd", "bwd_classify")}
+    hbm_stages = {k: v for k, v in per_stage.items() if v["GBps"] and k in ("project_fwd", "route_project", "sh_bwd", "bwd_classify")}
     dom = max(hbm_stages, key=lambda k: hbm_stages[k]["ms"]) if hbm_stages else None
-    kernel_of = {"project_fwd": "project_fwd_kernel", "sh_bwd": "sh_zero_kernel + sh_sparse_kernel (sparse) / sh_bwd_fused_kernel",
+    kernel_of = {"project_fwd": "project_fwd_tma_kernel", "route_project": "project_route_kernel (projection + SH colour + NVLink peer stores)",
+                 "sh_bwd": "sh_zero_kernel + sh_sparse_kernel (sparse) / sh_bwd_fused_kernel",
                  "bwd_classify": "bwd_classify_kernel"}
     roofline = None
     if dom:

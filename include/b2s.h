@@ -325,6 +325,59 @@ B2S_API int b2s_stripe_scatter_add(int32_t world, int32_t channels, const float*
                                    b2s_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Stage 1 FUSED with the multi-GPU exchange (the "direct" route; csrc/route.cu).  Replaces, for
+ * `rasterization(distributed=True)`, upstream's projection -> pack -> all_to_all(counts) -> all_to_all(payload) ->
+ * split (gsplat/rendering.py + gsplat/distributed.py behind source/container/src/main.py:1317-1347) and this library's
+ * own b2s_project_fwd + b2s_stripe_count/scan/pack/unpack: ONE kernel projects the rank's shard into every camera,
+ * evaluates the colour and stores each visible row, as a finished record, straight into the receive buffer of the rank
+ * that composites it (peer pointers of symmetric memory), plus per-CTA counts into that rank's count table.
+ *
+ * Receive buffer of a rank: world * region_cams REGIONS of cap_rows records of (10 + channels) words
+ *   [x, y, depth, conic(3), opacity, colour(ch), radius, local camera, LOCAL Gaussian index];
+ * region (source s, camera lc) = s * region_cams + lc; inside it source CTA b (Gaussians [256 b, 256 b + 256)) owns the
+ * slots [256 b, 256 b + 256) and fills them from the front in ascending Gaussian order.  Count table: int32[4] per
+ * (region, source CTA) = rows, tile intersections, coarse-bin records (inside the destination's window), tag
+ * (CTA 0 of a region: the source's Gaussian count).  cap_rows: a multiple of 256, >= every rank's Gaussian count;
+ * a source whose count exceeds it (or overflow != 0) publishes only its tag -- the receivers see it in info[3] and
+ * the caller grows the buffers collectively and repeats the call.  The caller provides ONE barrier between
+ * b2s_route_project and b2s_route_scan and alternates two buffer sets (parity) between consecutive exchanges.
+ *   b2s_route_scan   : row_base[region][source CTA] = exclusive prefix of the row counts in receive order (source rank,
+ *                      camera, Gaussian); info (int64 [4 + 2 world]) = rows, tile intersections, coarse-bin records,
+ *                      max source Gaussian count, rows per source, Gaussian count per source
+ *   b2s_route_gather : occupied slots -> compact tensors (camera_ids local, gaussian_ids GLOBAL = sum of the lower
+ *                      ranks' counts + local index) and the inputs of binning, as b2s_stripe_unpack
+ * The backward returns the gradients with b2s_stripe_return / b2s_stripe_scatter_add.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct {
+    b2s_project_fwd_args proj;   /* N, C (ALL cameras of the job), parameters, cameras, sh_coeffs / sh_degree / sh_stride_k,
+                                    tile geometry; of the outputs only `radii` (dense [C,N], read by the backward) is written */
+    int32_t world, rank;
+    int32_t cams_per_rank;       /* > 0: camera owners (camera c is composited by rank c / cams_per_rank); 0: tile stripes */
+    int32_t region_cams;         /* cameras per destination: cams_per_rank, or C for tile stripes */
+    int32_t channels;            /* colour channels of a record, 1..4 */
+    int32_t color_mode;          /* 0: SH colour (3 channels); 1: per-Gaussian colours_in [N, n_color_in] */
+    int32_t n_color_in;
+    int32_t depth_channel;       /* 1: the depth is appended as the last channel (render modes RGB+D, D) */
+    int32_t overflow;            /* != 0: publish the tag only */
+    int32_t bounds[B2S_MAX_RANKS + 1];   /* tile stripes: ascending tile rows from 0 to tile_h */
+    int64_t cap_rows;
+    const float* colors_in;
+    void* peer_rec[B2S_MAX_RANKS];       /* every rank's receive buffer (this parity), peer-mapped */
+    void* peer_cnt[B2S_MAX_RANKS];       /* every rank's count table (this parity), peer-mapped, 16-byte aligned */
+} b2s_route_args;
+B2S_API int64_t b2s_route_rec_floats(int32_t world, int32_t region_cams, int64_t cap_rows);   /* sized for 4 channels */
+B2S_API int64_t b2s_route_cnt_ints(int32_t world, int32_t region_cams, int64_t cap_rows);
+B2S_API int b2s_route_project(const b2s_route_args* a, b2s_stream_t stream);
+B2S_API int b2s_route_scan(int32_t world, int32_t region_cams, int64_t cap_rows, const int32_t* cnt, int32_t* row_base,
+                           int64_t* info, b2s_stream_t stream);
+B2S_API int b2s_route_gather(int32_t world, int32_t region_cams, int64_t cap_rows, int32_t channels, const float* rec,
+                             const int32_t* cnt, const int32_t* row_base, const int64_t* host_n_src, int64_t n_rows,
+                             int32_t tile_size, int32_t tile_w, int32_t tile_h, const b2s_tile_rows* rows, float* means2d,
+                             float* depths, float* conics, float* opacities, float* colors, int32_t* radii, int64_t* camera_ids,
+                             int64_t* gaussian_ids, int32_t* tiles_per_gauss, uint32_t* depth_keys, int32_t* row_ids,
+                             b2s_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Stage 3: per-16x16-tile front-to-back compositing.  Replaces gsplat `rasterize_to_pixels`
  * fwd / bwd.  Rows of means2d/conics/colors/opacities are addressed by
  * flatten_ids, so dense [C*N] and packed [nnz] layouts both work.  channels in {1,2,3,4,8,16,32}.

@@ -53,6 +53,18 @@ class ProjectFwdArgs(Structure):
     ]
 
 
+class RouteArgs(Structure):
+    """b2s_route_args: stage 1 fused with the multi-GPU exchange (csrc/route.cu)."""
+    _fields_ = [
+        ("proj", ProjectFwdArgs),
+        ("world", c_int32), ("rank", c_int32), ("cams_per_rank", c_int32), ("region_cams", c_int32),
+        ("channels", c_int32), ("color_mode", c_int32), ("n_color_in", c_int32), ("depth_channel", c_int32),
+        ("overflow", c_int32), ("bounds", c_int32 * 17),
+        ("cap_rows", c_int64), ("colors_in", c_void_p),
+        ("peer_rec", c_void_p * 16), ("peer_cnt", c_void_p * 16),
+    ]
+
+
 class ProjectBwdArgs(Structure):
     _fields_ = [
         ("N", c_int64), ("C", c_int32),
@@ -147,6 +159,12 @@ SYMBOLS = {
                           [c_void_p] * 11 + [c_void_p]),
     "b2s_stripe_return": (c_int32, [c_int64, c_int32] + [c_void_p] * 7 + [c_int64, c_int32] + [c_void_p] * 6 + [c_void_p]),
     "b2s_stripe_scatter_add": (c_int32, [c_int32, c_int32] + [c_void_p] * 9 + [c_void_p]),
+    "b2s_route_rec_floats": (c_int64, [c_int32, c_int32, c_int64]),
+    "b2s_route_cnt_ints": (c_int64, [c_int32, c_int32, c_int64]),
+    "b2s_route_project": (c_int32, [POINTER(RouteArgs), c_void_p]),
+    "b2s_route_scan": (c_int32, [c_int32, c_int32, c_int64, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "b2s_route_gather": (c_int32, [c_int32, c_int32, c_int64, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_int64,
+                                   c_int32, c_int32, c_int32, POINTER(TileRows)] + [c_void_p] * 11 + [c_void_p]),
     "b2s_l1_ssim_ctas": (c_int64, [c_int32, c_int32, c_int32]),
     "b2s_l1_ssim_fwd": (c_int32, [c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "b2s_l1_ssim_bwd": (c_int32, [c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_float, c_float, c_void_p,

@@ -479,11 +479,206 @@ class _RouteStripes(torch.autograd.Function):
         return tuple(outs) + (None,) * 5
 
 
+class _RouteBuffers:
+    """Symmetric-memory buffers of the direct route (csrc/route.cu): two receive buffers and two count tables (parity:
+    one barrier per exchange suffices because consecutive exchanges never touch the same set), one gradient-return
+    buffer and its counters.  ``cap`` -- the capacity of a (source, camera) region in rows -- must be the same on every
+    rank and at least every rank's Gaussian count: it is agreed with one all-gather when the buffers are first made and
+    grown collectively when a source reports (through the count table) that it no longer fits."""
+    _state = {}
+
+    @classmethod
+    def get(cls, group, dev, world, region_cams, n_local):
+        pg = group if group is not None else dist.group.WORLD
+        st = cls._state.get(id(pg))
+        if st is None or st["pg"] is not pg or st["world_pg"] is not dist.group.WORLD:
+            n = torch.tensor([n_local], dtype=torch.int64, device=dev)
+            ns = [torch.empty_like(n) for _ in range(world)]
+            dist.all_gather(ns, n, group=group)
+            st = {"pg": pg, "world_pg": dist.group.WORLD, "cap": cls.round_cap(max(int(t) for t in ns)), "parity": 0, "cams": 0}
+            cls._state[id(pg)] = st
+        st["cams"] = max(st["cams"], int(region_cams))       # allocation only: the layout of a call uses ITS camera count
+        return st
+
+    @staticmethod
+    def round_cap(n_max: int) -> int:
+        return ((int(n_max * 1.5) + 4096 + 255) // 256) * 256
+
+    @classmethod
+    def tensors(cls, st, group, dev, world):
+        from . import _lib as L
+        lib = L.lib()
+        cams, cap = st["cams"], st["cap"]
+        rec_f = int(lib.b2s_route_rec_floats(world, cams, cap))
+        cnt_i = int(lib.b2s_route_cnt_ints(world, cams, cap))
+        out = {}
+        for par in (0, 1):
+            out[f"rec{par}"] = _SymmBuffers.get(group, f"r_rec{par}", rec_f, dev)
+            out[f"cnt{par}"] = _SymmBuffers.get(group, f"r_cnt{par}", cnt_i, dev, dtype=torch.int32)
+        out["ret"] = _SymmBuffers.get(group, "r_ret", world * cams * cap * 12, dev)          # 8 + 4 words per returned record
+        out["ctr"] = _SymmBuffers.get(group, "r_ctr", 64, dev, dtype=torch.int64)
+        return out
+
+
+class _ProjectRoute(torch.autograd.Function):
+    """Stage 1 fused with the exchange (csrc/route.cu): the rank's Gaussians are projected into every camera and each visible
+    row is stored, as a finished record, straight into the receive buffer of the rank that composites it (camera owner or
+    tile-stripe owner) by the projection kernel itself; ONE barrier; then the receiver scans the count table (the forward's
+    one host sync) and gathers its rows.  Backward: sparse return of the gradients (csrc/stripes.cu), ONE barrier,
+    scatter-add into dense cotangents, projection / SH VJP."""
+
+    @staticmethod
+    def forward(ctx, means, quats, scales, opacities, colors, viewmats, Ks, group, cfg):
+        import ctypes
+        from . import _lib as L
+        from . import ops
+        (width, height, eps2d, near_plane, far_plane, radius_clip, antialiased, sh_degree, tile_size, bounds, cams_per_rank,
+         depth_mode) = cfg
+        dev = L.require_cuda(means, quats, scales, opacities, colors, viewmats, Ks)
+        rank, world = dist.get_rank(group), dist.get_world_size(group)
+        means, quats, scales, opacities = (L.f32c(t) for t in (means, quats, scales, opacities))
+        colors, viewmats, Ks = L.f32c(colors), L.f32c(viewmats), L.f32c(Ks)
+        N, C = means.shape[0], viewmats.shape[0]
+        tw, th = (width + tile_size - 1) // tile_size, (height + tile_size - 1) // tile_size
+        with_sh = sh_degree is not None
+        n_color_in = 0 if (with_sh or depth_mode == 2) else colors.shape[-1]
+        ch = (3 if with_sh else n_color_in) + (1 if depth_mode else 0)
+        region_cams = int(cams_per_rank) if cams_per_rank else C
+        lib, st = L.lib(), L.stream_ptr(dev)
+        state = _RouteBuffers.get(group, dev, world, region_cams, N)
+        radii = torch.empty(C, N, dtype=torch.int32, device=dev)
+        info = torch.empty(4 + 2 * world, dtype=torch.int64, device=dev)
+        for attempt in range(3):
+            cap = state["cap"]
+            bufs = _RouteBuffers.tensors(state, group, dev, world)
+            par = state["parity"]
+            state["parity"] ^= 1
+            (rec, h_rec), (cnt, h_cnt), (_ctr, h_ctr) = bufs[f"rec{par}"], bufs[f"cnt{par}"], bufs["ctr"]
+            a = L.RouteArgs()
+            a.proj = L.ProjectFwdArgs(
+                N=N, C=C, means=L.ptr(means), quats=L.ptr(quats), scales=L.ptr(scales), opacities=L.ptr(opacities),
+                viewmats=L.ptr(viewmats), Ks=L.ptr(Ks), width=width, height=height, eps2d=eps2d, near_plane=near_plane,
+                far_plane=far_plane, radius_clip=radius_clip, antialiased=int(antialiased),
+                sh_coeffs=L.ptr(colors) if with_sh else None, campos=None, sh_degree=int(sh_degree) if with_sh else 0,
+                sh_stride_k=colors.shape[1] if with_sh else 0, tile_size=tile_size, tile_w=tw, tile_h=th, radii=L.ptr(radii))
+            a.world, a.rank, a.cams_per_rank, a.region_cams = world, rank, int(cams_per_rank or 0), region_cams
+            a.channels, a.color_mode, a.n_color_in, a.depth_channel = ch, 0 if with_sh else 1, n_color_in, 1 if depth_mode else 0
+            a.overflow = int(N > cap)
+            for d, b in enumerate(bounds if not cams_per_rank else []):
+                a.bounds[d] = int(b)
+            a.cap_rows = cap
+            a.colors_in = None if (with_sh or n_color_in == 0) else L.ptr(colors)
+            for d in range(world):
+                a.peer_rec[d], a.peer_cnt[d] = int(h_rec.buffer_ptrs[d]), int(h_cnt.buffer_ptrs[d])
+            with ops._stage("route_project"):
+                L.check(lib.b2s_route_project(ctypes.byref(a), st), "b2s_route_project")
+            with ops._stage("route_barrier", launches=0):
+                h_ctr.barrier()                # every peer's projection kernel -- and with it its stores into this rank -- is done
+            row_base = torch.empty(max(cnt.numel() // 4, 1), dtype=torch.int32, device=dev)
+            with ops._stage("route_scan"):
+                L.check(lib.b2s_route_scan(world, region_cams, cap, L.ptr(cnt), L.ptr(row_base), L.ptr(info), st), "b2s_route_scan")
+            host = info.tolist()               # the one host sync of the forward: sizes of everything downstream
+            if host[3] <= cap:
+                break
+            # a source no longer fits its regions (densification grew it): every rank saw the same tags -> grow together
+            state["cap"] = _RouteBuffers.round_cap(host[3])
+        else:
+            raise RuntimeError("route buffers could not be grown")
+        n_recv, n_isects, n_records = int(host[0]), int(host[1]), int(host[2])
+        rows_from, n_world = [int(v) for v in host[4:4 + world]], [int(v) for v in host[4 + world:4 + 2 * world]]
+        o = dict(device=dev)
+        means2d_m, depths_m, conics_m = torch.empty(n_recv, 2, **o), torch.empty(n_recv, **o), torch.empty(n_recv, 3, **o)
+        opac_m, cols_m = torch.empty(n_recv, **o), torch.empty(n_recv, ch, **o)
+        radii_m, tiles_m = torch.empty(n_recv, dtype=torch.int32, **o), torch.empty(n_recv, dtype=torch.int32, **o)
+        dkeys, rowids = torch.empty(max(n_recv, 1), dtype=torch.int32, **o), torch.empty(max(n_recv, 1), dtype=torch.int32, **o)
+        cam_m, gid_m = torch.empty(n_recv, dtype=torch.int64, **o), torch.empty(n_recv, dtype=torch.int64, **o)
+        rows = L.TileRows(0, th) if cams_per_rank else L.TileRows(int(bounds[rank]), int(bounds[rank + 1]))
+        with ops._stage("route_gather"):
+            L.check(lib.b2s_route_gather(world, region_cams, cap, ch, L.ptr(rec), L.ptr(cnt), L.ptr(row_base), _i64(n_world), n_recv,
+                                         tile_size, tw, th, ctypes.byref(rows), L.ptr(means2d_m), L.ptr(depths_m), L.ptr(conics_m),
+                                         L.ptr(opac_m), L.ptr(cols_m), L.ptr(radii_m), L.ptr(cam_m), L.ptr(gid_m), L.ptr(tiles_m),
+                                         L.ptr(dkeys), L.ptr(rowids), st), "b2s_route_gather")
+        ctx.save_for_backward(means, quats, scales, opacities, colors if with_sh else None, viewmats, Ks, None, radii, cam_m, gid_m,
+                              None if with_sh else colors)
+        ctx.cfg = cfg
+        ctx.route = (rows_from, n_world, group, ch, n_color_in, state, cap)
+        ctx.set_materialize_grads(False)
+        ctx.mark_non_differentiable(radii_m, tiles_m, dkeys, rowids, cam_m, gid_m)
+        _ProjectRoute.last_counts = (n_isects, n_records)
+        return means2d_m, depths_m, conics_m, opac_m, cols_m, radii_m, tiles_m, dkeys, rowids, cam_m, gid_m
+
+    @staticmethod
+    def backward(ctx, g_means2d, g_depths, g_conics, g_opac, g_cols, *_):
+        from . import _lib as L
+        from . import ops
+        means, quats, scales, opacities, sh_coeffs, viewmats, Ks, _campos, radii, cam_m, gid_m, plain_colors = ctx.saved_tensors
+        (width, height, eps2d, near_plane, far_plane, radius_clip, antialiased, sh_degree, tile_size, bounds, cams_per_rank,
+         depth_mode) = ctx.cfg
+        rows_from, n_world, group, ch, n_color_in, state, cap = ctx.route
+        if ctx.needs_input_grad[5] or ctx.needs_input_grad[6]:
+            raise NotImplementedError("gradients w.r.t. viewmats / Ks are not implemented")
+        dev = means.device
+        rank, world = dist.get_rank(group), dist.get_world_size(group)
+        N, C = means.shape[0], viewmats.shape[0]
+        n_recv = int(sum(rows_from))
+        lib, st = L.lib(), L.stream_ptr(dev)
+        if state["cap"] != cap:
+            raise RuntimeError("the route buffers were re-made between this forward and its backward")
+        bufs = _RouteBuffers.tensors(state, group, dev, world)
+        (ret, h_ret), (ctr, h_ctr) = bufs["ret"], bufs["ctr"]
+        gs = [L.f32c(g) for g in (g_means2d, g_depths, g_conics, g_opac, g_cols)]
+        counters = torch.empty(world, dtype=torch.int64, device=dev)
+        recv_prefix = [0]
+        for c in rows_from:
+            recv_prefix.append(recv_prefix[-1] + int(c))
+        gid_offset = [int(sum(n_world[:s])) for s in range(world)]
+        region_rows = (int(cams_per_rank) if cams_per_rank else C) * cap      # capacity of one returning rank's region in a source's buffer
+        with ops._stage("stripe_return", launches=2):
+            L.check(lib.b2s_stripe_return(n_recv, ch, *[L.ptr(g) for g in gs], L.ptr(cam_m), L.ptr(gid_m),
+                                          rank * int(cams_per_rank or 0), world, _i64(recv_prefix), _i64(gid_offset), _i64(n_world),
+                                          _i64([rank * region_rows] * world), L.ptr(counters), _ptrs(h_ret.buffer_ptrs), st),
+                    "b2s_stripe_return")
+            L.check(lib.b2s_p2p_put(world, L.ptr(counters), 1, 1, _ptrs([p + rank * 8 for p in h_ctr.buffer_ptrs]), st), "b2s_p2p_put")
+        with ops._stage("route_return_barrier", launches=0):
+            h_ctr.barrier()
+        # one zero-filled slab for the dense cotangents of the projected rows
+        shapes = [(C, N, 2), (C, N), (C, N, 3), (C, N), (C, N, ch)]
+        sizes = [int(torch.Size(s).numel()) for s in shapes]
+        slab = torch.zeros(sum(sizes), dtype=torch.float32, device=dev)
+        outs, o = [], 0
+        for sz, shp in zip(sizes, shapes):
+            outs.append(slab[o:o + sz].view(shp))
+            o += sz
+        with ops._stage("stripe_scatter"):
+            L.check(lib.b2s_stripe_scatter_add(world, ch, L.ptr(ret), _i64([d * region_rows for d in range(world)]),
+                                               _i64([region_rows] * world), ctr.data_ptr(), *[L.ptr(t) for t in outs], st),
+                    "b2s_stripe_scatter_add")
+        v_means2d, v_depths, v_conics, v_opac_out, v_cols = outs
+        with_sh = sh_degree is not None
+        n_col = 3 if with_sh else n_color_in
+        v_colors_in = None
+        if depth_mode:
+            v_depths = v_depths + v_cols[..., n_col]
+        if with_sh:
+            v_sh_in = v_cols if ch == 3 else v_cols[..., :3].contiguous()
+        else:
+            v_sh_in = None
+            if n_col:
+                v_colors_in = v_cols[..., :n_col].sum(dim=0)
+        saved = (means, quats, scales, opacities, sh_coeffs, viewmats, Ks, None, radii)
+        pcfg = (width, height, eps2d, near_plane, far_plane, radius_clip, bool(antialiased), sh_degree if with_sh else 0)
+        v_means, v_quats, v_scales, v_opac, v_sh = ops.project_backward(saved, pcfg, v_means2d, v_depths, v_conics, None, v_opac_out,
+                                                                         v_sh_in)
+        return v_means, v_quats, v_scales, v_opac, (v_sh if with_sh else v_colors_in), None, None, None, None
+
+
 def _route_impl():
-    """'p2p' (default): the exchange fused into the count / pack / return kernels over NVLink peer stores (symmetric
-    memory, `_RouteStripes`); 'nccl': the unfused reference implementation (torch selection + pack + all_to_all_single)."""
+    """'direct' (default): stage 1 fused with the exchange -- the projection kernel stores finished records straight into
+    the owners' receive buffers over NVLink peer mappings (`_ProjectRoute`, csrc/route.cu); 'p2p': the earlier fused
+    count / pack / return kernels behind a dense projection (`_RouteStripes`); 'nccl': the unfused reference
+    implementation (torch selection + pack + all_to_all_single), also the fallback when peer access is unavailable."""
     import os
-    return os.environ.get("B2S_ROUTE", "p2p")
+    return os.environ.get("B2S_ROUTE", "direct")
 
 
 _P2P_OK = {}
@@ -575,7 +770,7 @@ def rasterization_distributed(means, quats, scales, opacities, colors, viewmats,
 
     if tile_stripes:
         n_world = None
-        fused_route = _route_impl() == "p2p" and peer_route_available(group, means.device)
+        fused_route = _route_impl() in ("p2p", "direct") and peer_route_available(group, means.device)
         if not fused_route:      # (the fused path carries the shard sizes in its count table)
             n = torch.tensor([N], dtype=torch.int64, device=means.device)
             ns = [torch.empty_like(n) for _ in range(world)]
@@ -588,16 +783,36 @@ def rasterization_distributed(means, quats, scales, opacities, colors, viewmats,
         rows = (bounds[rank], bounds[rank + 1])
     else:
         # (the fused route carries the shard sizes in its count table)
-        fused_route = _route_impl() == "p2p" and peer_route_available(group, means.device)
+        fused_route = _route_impl() in ("p2p", "direct") and peer_route_available(group, means.device)
         viewmats_all, Ks_all, n_world = all_gather_cameras(viewmats.detach(), Ks.detach(), N, group, with_sizes=not fused_route)
         C_all = viewmats_all.shape[0]
         if C_all != C_local * world:
             raise ValueError("every rank must hold the same number of cameras")
         rows = None
 
-    # ---- local shard projected into every camera (one kernel; SH coefficients read once) ----------------------
     antialiased = rasterize_mode == "antialiased"
     fused_sh = sh_degree is not None
+    depth_mode = 1 if render_mode in ("RGB+D", "RGB+ED") else (2 if render_mode in ("D", "ED") else 0)
+    ch_direct = (3 if fused_sh else (0 if depth_mode == 2 else colors.shape[-1])) + (1 if depth_mode else 0)
+    direct = fused_route and _route_impl() == "direct" and 1 <= ch_direct <= 4 and C_all <= ops.MAX_CAMS
+    dkeys = rowids = counts = None
+    if direct:
+        # ---- projection, colour and the exchange in ONE kernel (peer stores), then scan + gather on the receiver --------
+        if backgrounds is not None and depth_mode:
+            backgrounds = (torch.zeros_like(backgrounds[:, :1]) if depth_mode == 2
+                           else torch.cat([backgrounds, torch.zeros_like(backgrounds[:, :1])], dim=-1))
+        cfg = (width, height, float(eps2d), float(near_plane), float(far_plane), float(radius_clip), antialiased,
+               int(sh_degree) if fused_sh else None, tile_size, tuple(bounds) if tile_stripes else None,
+               0 if tile_stripes else C_local, depth_mode)
+        (means2d_m, depths_m, conics_m, opac_m, cols_m, radii_m, tiles_m, dkeys, rowids, cam_local,
+         gauss_global) = _ProjectRoute.apply(means, quats, scales, opacities, colors, viewmats_all, Ks_all, group, cfg)
+        counts = _ProjectRoute.last_counts
+        ch = ch_direct
+        return _composite_routed(means2d_m, depths_m, conics_m, opac_m, cols_m, radii_m, tiles_m, dkeys, rowids, counts, cam_local,
+                                 gauss_global, width, height, tile_size, tw, th, C_local, rows, bounds if tile_stripes else None,
+                                 backgrounds, render_mode, absgrad, ch)
+
+    # ---- local shard projected into every camera (one kernel; SH coefficients read once) ----------------------
     radii, means2d, depths, conics, _comps, opac, sh_cols, tiles, _dk, _ri, _tot = ops._ProjectFused.apply(
         means, quats, scales, opacities, colors if fused_sh else None, viewmats_all, Ks_all, None, width, height,
         float(eps2d), float(near_plane), float(far_plane), float(radius_clip), antialiased, False,
@@ -636,6 +851,16 @@ def rasterization_distributed(means, quats, scales, opacities, colors, viewmats,
             tiles_m = ops.isect_tiles(means2d_m.detach(), radii_m, depths_m.detach(), tile_size, tw, th, sort=False, packed=True,
                                       n_cameras=C_local, camera_ids=cam_local, tile_rows=rows, count_only=True)
 
+    return _composite_routed(means2d_m, depths_m, conics_m, opac_m, cols_m, radii_m, tiles_m, dkeys, rowids, counts, cam_local,
+                             gauss_global, width, height, tile_size, tw, th, C_local, rows, bounds if tile_stripes else None,
+                             backgrounds, render_mode, absgrad, ch)
+
+
+def _composite_routed(means2d_m, depths_m, conics_m, opac_m, cols_m, radii_m, tiles_m, dkeys, rowids, counts, cam_local,
+                      gauss_global, width, height, tile_size, tw, th, C_local, rows, bounds, backgrounds, render_mode, absgrad, ch):
+    """Own cameras / own stripe: binning + compositing of the rows the exchange delivered (packed layout)."""
+    from . import ops
+    tile_stripes = bounds is not None
     # ---- own cameras / own stripe: binning + compositing ---------------------------------------------------------
     from .rendering import _use_coarse_bins
     meta = ops.LazyMeta({

@@ -146,65 +146,74 @@ class _ProjectFused(torch.autograd.Function):
     @staticmethod
     def backward(ctx, _v_radii, v_means2d, v_depths, v_conics, v_comps, v_opac_out, v_colors, _v_tiles=None, _v_keys=None,
                  _v_rows=None, _v_total=None):
-        means, quats, scales, opacities, sh_coeffs, viewmats, Ks, campos, radii = ctx.saved_tensors
-        width, height, eps2d, near_plane, far_plane, radius_clip, antialiased, sh_degree = ctx.cfg
         if ctx.needs_input_grad[5] or ctx.needs_input_grad[6]:
             raise NotImplementedError("gradients w.r.t. viewmats / Ks are not implemented")
-        N, C = means.shape[0], viewmats.shape[0]
-        dev = means.device
-        v_means2d, v_depths, v_conics = f32c(v_means2d), f32c(v_depths), f32c(v_conics)
-        v_comps, v_opac_out, v_colors = f32c(v_comps), f32c(v_opac_out), f32c(v_colors)
-        with_sh = sh_coeffs is not None
-        v_means = torch.empty_like(means)
-        v_quats = torch.empty_like(quats)
-        v_scales = torch.empty_like(scales)
-        v_opac = torch.empty_like(opacities) if opacities is not None else None
-        v_sh = None
-        if with_sh:
-            K = (sh_degree + 1) ** 2
-            v_sh = torch.empty_like(sh_coeffs) if K == sh_coeffs.shape[1] else torch.zeros_like(sh_coeffs)
-        lib = L.lib()
-        st = L.stream_ptr(dev)
-        # scratch for the sparse backward (rows with all-zero cotangents are filtered once; include/b2s.h)
-        ws = None
-        if C <= MAX_CAMS and os.environ.get("B2S_SPARSE_BWD", "1") != "0":
-            ws = torch.empty(int(lib.b2s_project_bwd_workspace_bytes(N)), dtype=torch.uint8, device=dev)
+        grads = project_backward(ctx.saved_tensors, ctx.cfg, v_means2d, v_depths, v_conics, v_comps, v_opac_out, v_colors)
+        return tuple(grads) + (None,) * 13
 
-        def sl(t, c0, c1):
-            return ptr(t[c0:c1]) if t is not None else None
 
-        for c0 in range(0, max(C, 1), MAX_CAMS):
-            c1 = min(C, c0 + MAX_CAMS)
+def project_backward(saved, cfg, v_means2d, v_depths, v_conics, v_comps, v_opac_out, v_colors):
+    """VJP of stage 1 from dense ``[C,N,..]`` cotangents (any of them may be None): (v_means, v_quats, v_scales,
+    v_opacities, v_sh_coeffs).  Shared by ``_ProjectFused`` and the multi-GPU ``_ProjectRoute``."""
+    means, quats, scales, opacities, sh_coeffs, viewmats, Ks, campos, radii = saved
+    width, height, eps2d, near_plane, far_plane, radius_clip, antialiased, sh_degree = cfg
+    N, C = means.shape[0], viewmats.shape[0]
+    dev = means.device
+    v_means2d, v_depths, v_conics = f32c(v_means2d), f32c(v_depths), f32c(v_conics)
+    v_comps, v_opac_out, v_colors = f32c(v_comps), f32c(v_opac_out), f32c(v_colors)
+    with_sh = sh_coeffs is not None
+    v_means = torch.empty_like(means)
+    v_quats = torch.empty_like(quats)
+    v_scales = torch.empty_like(scales)
+    v_opac = torch.empty_like(opacities) if opacities is not None else None
+    v_sh = None
+    if with_sh:
+        K = (sh_degree + 1) ** 2
+        v_sh = torch.empty_like(sh_coeffs) if K == sh_coeffs.shape[1] else torch.zeros_like(sh_coeffs)
+    if N == 0:
+        return v_means, v_quats, v_scales, v_opac, v_sh
+    lib = L.lib()
+    st = L.stream_ptr(dev)
+    # scratch for the sparse backward (rows with all-zero cotangents are filtered once; include/b2s.h)
+    ws = None
+    if C <= MAX_CAMS and os.environ.get("B2S_SPARSE_BWD", "1") != "0":
+        ws = torch.empty(int(lib.b2s_project_bwd_workspace_bytes(N)), dtype=torch.uint8, device=dev)
 
-            def args(stages):
-                return L.ProjectBwdArgs(
-                    N=N, C=c1 - c0, means=ptr(means), quats=ptr(quats), scales=ptr(scales), opacities=ptr(opacities),
-                    viewmats=ptr(viewmats[c0:c1]), Ks=ptr(Ks[c0:c1]), width=width, height=height, eps2d=eps2d,
-                    near_plane=near_plane, far_plane=far_plane, radius_clip=radius_clip, antialiased=int(antialiased),
-                    sh_coeffs=ptr(sh_coeffs), campos=sl(campos, c0, c1), sh_degree=int(sh_degree) if with_sh else 0,
-                    sh_stride_k=sh_coeffs.shape[1] if with_sh else 0, radii=ptr(radii[c0:c1]),
-                    v_means2d=sl(v_means2d, c0, c1), v_depths=sl(v_depths, c0, c1), v_conics=sl(v_conics, c0, c1),
-                    v_compensations=sl(v_comps, c0, c1), v_opacities_out=sl(v_opac_out, c0, c1),
-                    v_colors=sl(v_colors, c0, c1), accumulate=int(c0 > 0),
-                    v_means=ptr(v_means), v_quats=ptr(v_quats), v_scales=ptr(v_scales), v_opacities=ptr(v_opac),
-                    v_sh_coeffs=ptr(v_sh), stages=stages, workspace=ptr(ws), workspace_bytes=ws.numel() if ws is not None else 0)
+    def sl(t, c0, c1):
+        return ptr(t[c0:c1]) if t is not None else None
 
-            sparse = ws is not None and c0 == 0      # kernels launched: + classify, zero fill and the two list-driven ones
-            if with_sh and TIMER is not None:     # time the stages of the call separately (bench.py)
-                if sparse:
-                    with _stage("bwd_classify", launches=1):
-                        check(lib.b2s_project_bwd(ctypes.byref(args(3)), st), "b2s_project_bwd")
-                    with _stage("sh_bwd", launches=3):
-                        check(lib.b2s_project_bwd(ctypes.byref(args(4)), st), "b2s_project_bwd")
-                else:
-                    with _stage("sh_bwd", launches=1):
-                        check(lib.b2s_project_bwd(ctypes.byref(args(1)), st), "b2s_project_bwd")
-                with _stage("project_bwd", launches=1):
-                    check(lib.b2s_project_bwd(ctypes.byref(args(2)), st), "b2s_project_bwd")
+    for c0 in range(0, max(C, 1), MAX_CAMS):
+        c1 = min(C, c0 + MAX_CAMS)
+
+        def args(stages):
+            return L.ProjectBwdArgs(
+                N=N, C=c1 - c0, means=ptr(means), quats=ptr(quats), scales=ptr(scales), opacities=ptr(opacities),
+                viewmats=ptr(viewmats[c0:c1]), Ks=ptr(Ks[c0:c1]), width=width, height=height, eps2d=eps2d,
+                near_plane=near_plane, far_plane=far_plane, radius_clip=radius_clip, antialiased=int(antialiased),
+                sh_coeffs=ptr(sh_coeffs), campos=sl(campos, c0, c1), sh_degree=int(sh_degree) if with_sh else 0,
+                sh_stride_k=sh_coeffs.shape[1] if with_sh else 0, radii=ptr(radii[c0:c1]),
+                v_means2d=sl(v_means2d, c0, c1), v_depths=sl(v_depths, c0, c1), v_conics=sl(v_conics, c0, c1),
+                v_compensations=sl(v_comps, c0, c1), v_opacities_out=sl(v_opac_out, c0, c1),
+                v_colors=sl(v_colors, c0, c1), accumulate=int(c0 > 0),
+                v_means=ptr(v_means), v_quats=ptr(v_quats), v_scales=ptr(v_scales), v_opacities=ptr(v_opac),
+                v_sh_coeffs=ptr(v_sh), stages=stages, workspace=ptr(ws), workspace_bytes=ws.numel() if ws is not None else 0)
+
+        sparse = ws is not None and c0 == 0      # kernels launched: + classify, zero fill and the two list-driven ones
+        if with_sh and TIMER is not None:     # time the stages of the call separately (bench.py)
+            if sparse:
+                with _stage("bwd_classify", launches=1):
+                    check(lib.b2s_project_bwd(ctypes.byref(args(3)), st), "b2s_project_bwd")
+                with _stage("sh_bwd", launches=3):
+                    check(lib.b2s_project_bwd(ctypes.byref(args(4)), st), "b2s_project_bwd")
             else:
-                with _stage("project_bwd", launches=(5 if with_sh else 2) if sparse else (2 if with_sh else 1)):
-                    check(lib.b2s_project_bwd(ctypes.byref(args(0)), st), "b2s_project_bwd")
-        return (v_means, v_quats, v_scales, v_opac, v_sh) + (None,) * 13
+                with _stage("sh_bwd", launches=1):
+                    check(lib.b2s_project_bwd(ctypes.byref(args(1)), st), "b2s_project_bwd")
+            with _stage("project_bwd", launches=1):
+                check(lib.b2s_project_bwd(ctypes.byref(args(2)), st), "b2s_project_bwd")
+        else:
+            with _stage("project_bwd", launches=(5 if with_sh else 2) if sparse else (2 if with_sh else 1)):
+                check(lib.b2s_project_bwd(ctypes.byref(args(0)), st), "b2s_project_bwd")
+    return v_means, v_quats, v_scales, v_opac, v_sh
 
 
 def fully_fused_projection(

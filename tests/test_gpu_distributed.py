@@ -13,9 +13,10 @@ N, DEG, W, H = 6000, 3, 160, 96
 WORLD = 2
 
 
-def _worker(rank, port, out):
+def _worker(rank, port, out, route, render_mode):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
+    os.environ["B2S_ROUTE"] = route
     torch.cuda.set_device(rank)
     dist.init_process_group("nccl", rank=rank, world_size=WORLD, device_id=torch.device("cuda", rank))
     try:
@@ -28,11 +29,16 @@ def _worker(rank, port, out):
         g = torch.Generator().manual_seed(5)
         v_r = torch.rand(WORLD, H, W, 3, generator=g)
         v_a = torch.rand(WORLD, H, W, 1, generator=g)
-        r, al, m = b2s.rasterization(shard["means"], shard["quats"], shard["scales"], shard["opacities"], shard["colors"],
-                                     a["viewmats"][rank:rank + 1].to(dev), a["Ks"][rank:rank + 1].to(dev), W, H, sh_degree=DEG,
-                                     packed=True, rasterize_mode="antialiased", distributed=True)
-        m["means2d"].retain_grad()
-        torch.autograd.backward([r, al], [v_r[rank:rank + 1].to(dev), v_a[rank:rank + 1].to(dev)])
+        nch = 4 if render_mode == "RGB+D" else 3
+        v_r = torch.rand(WORLD, H, W, nch, generator=g)
+        for it in range(2):                   # twice: the second pass alternates the exchange buffers
+            for t in shard.values():
+                t.grad = None
+            r, al, m = b2s.rasterization(shard["means"], shard["quats"], shard["scales"], shard["opacities"], shard["colors"],
+                                         a["viewmats"][rank:rank + 1].to(dev), a["Ks"][rank:rank + 1].to(dev), W, H, sh_degree=DEG,
+                                         packed=True, rasterize_mode="antialiased", distributed=True, render_mode=render_mode)
+            m["means2d"].retain_grad()
+            torch.autograd.backward([r, al], [v_r[rank:rank + 1].to(dev), v_a[rank:rank + 1].to(dev)])
         assert m["means2d"].grad is not None
         assert int(m["gaussian_ids"].max()) < N and int(m["camera_ids"].max()) == 0
         torch.save({"render": r.detach().cpu(), "alpha": al.detach().cpu(), "grads": {k: shard[k].grad.cpu() for k in LEAVES},
@@ -42,23 +48,29 @@ def _worker(rank, port, out):
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
-def test_sharded_all_to_all_matches_single_gpu(tmp_path):
+@pytest.mark.parametrize("route,render_mode", [("direct", "RGB"), ("direct", "RGB+D"), ("p2p", "RGB"), ("nccl", "RGB")])
+def test_sharded_all_to_all_matches_single_gpu(tmp_path, route, render_mode):
     import pipeline_pointcloud_b200 as b2s
     from tests.util import LEAVES, grad_report, scene_args
-    mp.spawn(_worker, args=(29700, str(tmp_path)), nprocs=WORLD, join=True)
+    mp.spawn(_worker, args=(29700 + ("direct", "p2p", "nccl").index(route) + 3 * (render_mode != "RGB"), str(tmp_path), route,
+                            render_mode), nprocs=WORLD, join=True)
     a = scene_args(N, DEG, WORLD, W, H, seed=21)
     full = {k: (a[k].cuda().requires_grad_() if k in LEAVES else a[k].cuda()) for k in a}
     r, al, m = b2s.rasterization(full["means"], full["quats"], full["scales"], full["opacities"], full["colors"],
-                                 full["viewmats"], full["Ks"], W, H, sh_degree=DEG, packed=True, rasterize_mode="antialiased")
+                                 full["viewmats"], full["Ks"], W, H, sh_degree=DEG, packed=True, rasterize_mode="antialiased",
+                                 render_mode=render_mode)
     g = torch.Generator().manual_seed(5)
     v_r = torch.rand(WORLD, H, W, 3, generator=g)
     v_a = torch.rand(WORLD, H, W, 1, generator=g)
+    v_r = torch.rand(WORLD, H, W, 4 if render_mode == "RGB+D" else 3, generator=g)
     torch.autograd.backward([r, al], [v_r.cuda(), v_a.cuda()])
     rows = 0
     for rank in range(WORLD):
         got = torch.load(os.path.join(str(tmp_path), f"rank{rank}.pt"))
         # same splats, same depth order: the composite differs only by the packed row numbering
-        assert (got["render"][0] - r[rank].detach().cpu()).abs().max() < 2e-5
+        assert (got["render"][0][..., :3] - r[rank].detach().cpu()[..., :3]).abs().max() < 2e-5
+        if render_mode == "RGB+D":
+            assert (got["render"][0][..., 3] - r[rank].detach().cpu()[..., 3]).abs().max() < 2e-4
         assert (got["alpha"][0] - al[rank].detach().cpu()).abs().max() < 2e-5
         lo, hi = rank * N // WORLD, (rank + 1) * N // WORLD
         for k in LEAVES:      # each rank holds the complete gradient of its own shard (sum over both cameras)

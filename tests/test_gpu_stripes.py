@@ -149,14 +149,15 @@ def _worker(rank, world, bounds, port, out, route):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("case,route", [("w2", "p2p"), ("w2", "nccl"), ("w2_empty_first", "p2p"), ("w2_empty_first", "nccl"),
+@pytest.mark.parametrize("case,route", [("w2", "direct"), ("w2", "p2p"), ("w2", "nccl"), ("w2_empty_first", "direct"),
+                                        ("w2_empty_first", "p2p"), ("w2_empty_first", "nccl"), ("w4_uneven_one_empty", "direct"),
                                         ("w4_uneven_one_empty", "p2p"), ("w4_uneven_one_empty", "nccl"),
-                                        ("w8_uneven_one_empty", "p2p")])
+                                        ("w8_uneven_one_empty", "direct")])
 def test_tile_stripes_match_single_gpu(b2s, tmp_path, case, route):
     world, bounds = STRIPE_CASES[case]
     if torch.cuda.device_count() < world:
         pytest.skip(f"needs {world} GPUs")
-    port = 29720 + 7 * list(STRIPE_CASES).index(case) + (route == "nccl")
+    port = 29720 + 7 * list(STRIPE_CASES).index(case) + ("direct", "p2p", "nccl").index(route)
     mp.spawn(_worker, args=(world, bounds, port, str(tmp_path), route), nprocs=world, join=True)
     a = scene_args(N2, DEG, C2, W2, H2, seed=41)
     a["scales"][:200] *= 5.0
