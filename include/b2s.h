@@ -127,6 +127,12 @@ typedef struct {
 } b2s_project_bwd_args;
 B2S_API int64_t b2s_project_bwd_workspace_bytes(int64_t N);
 B2S_API int b2s_project_bwd(const b2s_project_bwd_args* a, b2s_stream_t stream);
+/* Camera gradients of the same backward (gsplat's `v_viewmats`; only nerfstudio's optional camera optimizer asks for them):
+ * v_view [C,16], zero-filled by the caller, accumulated with one atomic per value, camera and CTA after a warp + CTA
+ * reduction: [0..8] d/dR (row-major world->camera rotation), [9..11] d/dt, [12..14] d/d(camera centre) from the SH view
+ * directions (the caller chains it through campos = -R^-1 t), [15] unused.  Takes the arguments of b2s_project_bwd
+ * (gradient outputs, stages and workspace are ignored). */
+B2S_API int b2s_viewmat_bwd(const b2s_project_bwd_args* a, float* v_view, b2s_stream_t stream);
 
 /* Stand-alone SH evaluation over M directions (gsplat `spherical_harmonics` fwd/bwd): the
  * stage-level op; the training path uses the fused kernels above.  masks may be NULL. */

@@ -119,6 +119,7 @@ SYMBOLS = {
     "b2s_project_fwd": (c_int32, [POINTER(ProjectFwdArgs), c_void_p]),
     "b2s_project_bwd_workspace_bytes": (c_int64, [c_int64]),
     "b2s_project_bwd": (c_int32, [POINTER(ProjectBwdArgs), c_void_p]),
+    "b2s_viewmat_bwd": (c_int32, [POINTER(ProjectBwdArgs), c_void_p, c_void_p]),
     "b2s_sh_fwd": (c_int32, [c_int64, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "b2s_sh_bwd": (c_int32, [c_int64, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "b2s_quat_scale_to_covar_preci": (c_int32, [c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),

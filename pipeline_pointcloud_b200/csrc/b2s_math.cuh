@@ -280,8 +280,10 @@ struct ProjGradIn {
     float v_comp;
 };
 
+// v_cam (optional, 12 floats, accumulated): gradient w.r.t. the camera's world->camera rotation (row-major 3x3) and
+// translation -- the `v_viewmats` of gsplat's projection backward (t = R mean + t_cam; Sigma_cam = R Sigma R^T).
 B2S_HD void project_one_bwd(const Camera& cam, const float mean[3], const Sym3& S, float eps2d, const ProjMid& m,
-                            const ProjGradIn& g, float v_mean[3], Sym3& v_S) {
+                            const ProjGradIn& g, float v_mean[3], Sym3& v_S, float* v_cam = nullptr) {
     const float* R = cam.R;
     // ---- conic = inverse([[a,b],[b,d]]) -> v_a, v_b (total for the off-diagonal), v_d
     float det = m.det;
@@ -352,7 +354,20 @@ B2S_HD void project_one_bwd(const Camera& cam, const float mean[3], const Sym3& 
     float f22 = T[6] * R[2] + T[7] * R[5] + T[8] * R[8];
     v_S.c00 += f00; v_S.c11 += f11; v_S.c22 += f22;
     v_S.c01 += 2.f * f01; v_S.c02 += 2.f * f02; v_S.c12 += 2.f * f12;
-    (void)mean; (void)S; (void)eps2d;
+    if (v_cam) {
+        // t = R mean + t_cam
+        v_cam[9] += v_tx; v_cam[10] += v_ty; v_cam[11] += v_tz;
+        for (int j = 0; j < 3; ++j) { v_cam[j] += v_tx * mean[j]; v_cam[3 + j] += v_ty * mean[j]; v_cam[6 + j] += v_tz * mean[j]; }
+        // Sigma_cam = R Sigma R^T  ->  v_R += (VS + VS^T) (R Sigma) = 2 VS (R Sigma)
+        const float Sg[9] = {S.c00, S.c01, S.c02, S.c01, S.c11, S.c12, S.c02, S.c12, S.c22};
+        float A[9];
+        for (int i = 0; i < 3; ++i)
+            for (int j = 0; j < 3; ++j) A[3 * i + j] = R[3 * i] * Sg[j] + R[3 * i + 1] * Sg[3 + j] + R[3 * i + 2] * Sg[6 + j];
+        for (int i = 0; i < 3; ++i)
+            for (int j = 0; j < 3; ++j)
+                v_cam[3 * i + j] += 2.f * (VS[3 * i] * A[j] + VS[3 * i + 1] * A[3 + j] + VS[3 * i + 2] * A[6 + j]);
+    }
+    (void)eps2d;
 }
 
 // Sigma = M M^T, M = R(q) diag(s):  v_Sigma (6 unique, off-diagonals already doubled) -> v_quat, v_scale

@@ -702,6 +702,94 @@ __global__ void __launch_bounds__(BWD_THREADS) project_bwd_sparse_kernel(const b
 }
 
 
+// =================================================================================================
+// camera gradients (gsplat's `v_viewmats`; nerfstudio's camera optimizer behind source/container/src/main.py:1270-1316 reads
+// them).  A separate pass, launched only when the caller asks for it, so the kernels above stay as they are: per
+// (camera, Gaussian) with a live cotangent it re-derives the projection VJP's camera terms (12 values: dR, dt) and the SH
+// colour's view-direction term (3 values: d campos), reduces them over the warp and the CTA (shuffles, then shared
+// memory) and issues ONE atomic per value, camera and CTA.  v_view: [C,16] = dR (9, row-major), dt (3), dcampos (3), pad.
+// =================================================================================================
+constexpr int VW_THREADS = 256, VW_VALS = 15;
+__global__ void __launch_bounds__(VW_THREADS) viewmat_bwd_kernel(const b2s_project_bwd_args a, float* __restrict__ v_view) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    Camera* cams = reinterpret_cast<Camera*>(smem_raw);
+    __shared__ float s_red[VW_THREADS / 32][VW_VALS];
+    load_cameras(cams, a.C, a.viewmats, a.Ks, a.campos, (float)a.width, (float)a.height);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t n = (int64_t)blockIdx.x * VW_THREADS + threadIdx.x;
+    const bool live = n < a.N;
+    const int64_t nc = live ? n : a.N - 1;
+    float mean[3], q[4], s[3];
+    mean[0] = __ldg(a.means + 3 * nc); mean[1] = __ldg(a.means + 3 * nc + 1); mean[2] = __ldg(a.means + 3 * nc + 2);
+    {
+        const float4 qq = __ldg(reinterpret_cast<const float4*>(a.quats) + nc);
+        q[0] = qq.x; q[1] = qq.y; q[2] = qq.z; q[3] = qq.w;
+    }
+    s[0] = __ldg(a.scales + 3 * nc); s[1] = __ldg(a.scales + 3 * nc + 1); s[2] = __ldg(a.scales + 3 * nc + 2);
+    const float opac = a.opacities ? __ldg(a.opacities + nc) : 1.f;
+    Rot R; float qn[4], qnorm, M[9]; Sym3 S;
+    quat_to_rotmat(q, R, qn, qnorm);
+    covar_from_rot_scale(R, s, M, S);
+    const bool with_sh = a.sh_coeffs != nullptr && a.v_colors != nullptr;
+    const int K = (a.sh_degree + 1) * (a.sh_degree + 1);
+    for (int c = 0; c < a.C; ++c) {
+        float acc[VW_VALS];
+#pragma unroll
+        for (int k = 0; k < VW_VALS; ++k) acc[k] = 0.f;
+        const int64_t i = (int64_t)c * a.N + nc;
+        if (live && __ldg(a.radii + i) > 0) {
+            ProjMid mid;
+            project_mid_fast(cams[c], mean, S, a.eps2d, mid);
+            if (mid.det > 0.f) {
+                ProjGradIn g;
+                if (a.v_means2d) { const float2 v = __ldg(reinterpret_cast<const float2*>(a.v_means2d) + i); g.v_x2d = v.x; g.v_y2d = v.y; }
+                else { g.v_x2d = g.v_y2d = 0.f; }
+                g.v_depth = a.v_depths ? __ldg(a.v_depths + i) : 0.f;
+                if (a.v_conics) { g.v_conic_a = __ldg(a.v_conics + 3 * i); g.v_conic_b = __ldg(a.v_conics + 3 * i + 1); g.v_conic_c = __ldg(a.v_conics + 3 * i + 2); }
+                else { g.v_conic_a = g.v_conic_b = g.v_conic_c = 0.f; }
+                g.v_comp = a.v_compensations ? __ldg(a.v_compensations + i) : 0.f;
+                if (a.v_opacities_out && a.antialiased) g.v_comp += __ldg(a.v_opacities_out + i) * opac;
+                float vm[3] = {0.f, 0.f, 0.f};
+                Sym3 vS = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+                project_one_bwd(cams[c], mean, S, a.eps2d, mid, g, vm, vS, acc);
+            }
+            if (with_sh) {
+                const float g0 = __ldg(a.v_colors + 3 * i), g1 = __ldg(a.v_colors + 3 * i + 1), g2 = __ldg(a.v_colors + 3 * i + 2);
+                if (g0 != 0.f || g1 != 0.f || g2 != 0.f) {
+                    const float* cf = a.sh_coeffs + nc * a.sh_stride_k * 3;
+                    const float dx = mean[0] - cams[c].campos[0], dy = mean[1] - cams[c].campos[1], dz = mean[2] - cams[c].campos[2];
+                    const float inv = 1.f / fmaxf(sqrtf(dx * dx + dy * dy + dz * dz), 1e-12f);
+                    const float ux = dx * inv, uy = dy * inv, uz = dz * inv;
+                    float Y[16], w[16];
+                    sh_basis(a.sh_degree, ux, uy, uz, Y);
+                    float cr = 0.5f, cg = 0.5f, cb = 0.5f;
+                    for (int k = 0; k < K; ++k) { cr += Y[k] * __ldg(cf + 3 * k); cg += Y[k] * __ldg(cf + 3 * k + 1); cb += Y[k] * __ldg(cf + 3 * k + 2); }
+                    const float vr = cr > 0.f ? g0 : 0.f, vg = cg > 0.f ? g1 : 0.f, vb = cb > 0.f ? g2 : 0.f;
+                    for (int k = 0; k < K; ++k) w[k] = __ldg(cf + 3 * k) * vr + __ldg(cf + 3 * k + 1) * vg + __ldg(cf + 3 * k + 2) * vb;
+                    float vx, vy, vz;
+                    sh_basis_vjp(a.sh_degree, ux, uy, uz, w, vx, vy, vz);
+                    const float dp = ux * vx + uy * vy + uz * vz;
+                    // dirs = mean - campos: d/d campos = -d/d dirs
+                    acc[12] -= (vx - ux * dp) * inv; acc[13] -= (vy - uy * dp) * inv; acc[14] -= (vz - uz * dp) * inv;
+                }
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < VW_VALS; ++k) {
+            const float r = warp_sum(acc[k]);
+            if (lane == 0) s_red[warp][k] = r;
+        }
+        __syncthreads();
+        if (threadIdx.x < VW_VALS) {
+            float t = 0.f;
+#pragma unroll
+            for (int w = 0; w < VW_THREADS / 32; ++w) t += s_red[w][threadIdx.x];
+            if (t != 0.f) atomicAdd(v_view + 16 * c + threadIdx.x, t);
+        }
+        __syncthreads();
+    }
+}
+
 }  // namespace b2s
 
 using namespace b2s;
@@ -818,5 +906,21 @@ extern "C" int b2s_project_bwd(const b2s_project_bwd_args* a, b2s_stream_t strea
         }
         B2S_LAUNCH_CHECK();
     }
+    return 0;
+}
+
+extern "C" int b2s_viewmat_bwd(const b2s_project_bwd_args* a, float* v_view, b2s_stream_t stream) {
+    B2S_REQUIRE(a != nullptr && v_view != nullptr, "null args");
+    B2S_REQUIRE(a->N >= 0 && a->C >= 0 && a->C <= B2S_MAX_CAMERAS_PER_CALL, "bad sizes");
+    if (a->N == 0 || a->C == 0) return 0;
+    B2S_REQUIRE(a->means && a->quats && a->scales && a->viewmats && a->Ks && a->radii, "null input");
+    B2S_REQUIRE(aligned16(a->quats), "quats misaligned");
+    if (a->sh_coeffs && a->v_colors) {
+        B2S_REQUIRE(a->sh_degree >= 0 && a->sh_degree <= 3, "sh_degree must be 0..3");
+        B2S_REQUIRE(a->sh_stride_k >= (a->sh_degree + 1) * (a->sh_degree + 1), "sh_stride_k < (deg+1)^2");
+    }
+    const size_t cam_bytes = ((a->C * sizeof(Camera) + 15) / 16) * 16;
+    viewmat_bwd_kernel<<<(unsigned)cdiv(a->N, VW_THREADS), VW_THREADS, cam_bytes, (cudaStream_t)stream>>>(*a, v_view);
+    B2S_LAUNCH_CHECK();
     return 0;
 }

@@ -615,8 +615,8 @@ class _ProjectRoute(torch.autograd.Function):
         (width, height, eps2d, near_plane, far_plane, radius_clip, antialiased, sh_degree, tile_size, bounds, cams_per_rank,
          depth_mode) = ctx.cfg
         rows_from, n_world, group, ch, n_color_in, state, cap = ctx.route
-        if ctx.needs_input_grad[5] or ctx.needs_input_grad[6]:
-            raise NotImplementedError("gradients w.r.t. viewmats / Ks are not implemented")
+        if ctx.needs_input_grad[5]:
+            raise NotImplementedError("distributed=True: gradients w.r.t. viewmats are not implemented (every rank holds a partial sum)")
         dev = means.device
         rank, world = dist.get_rank(group), dist.get_world_size(group)
         N, C = means.shape[0], viewmats.shape[0]

@@ -146,15 +146,16 @@ class _ProjectFused(torch.autograd.Function):
     @staticmethod
     def backward(ctx, _v_radii, v_means2d, v_depths, v_conics, v_comps, v_opac_out, v_colors, _v_tiles=None, _v_keys=None,
                  _v_rows=None, _v_total=None):
-        if ctx.needs_input_grad[5] or ctx.needs_input_grad[6]:
-            raise NotImplementedError("gradients w.r.t. viewmats / Ks are not implemented")
-        grads = project_backward(ctx.saved_tensors, ctx.cfg, v_means2d, v_depths, v_conics, v_comps, v_opac_out, v_colors)
-        return tuple(grads) + (None,) * 13
+        # viewmats: gsplat's `v_viewmats` (nerfstudio's camera optimizer); Ks: no gradient, as upstream
+        want_view = ctx.needs_input_grad[5]
+        grads = project_backward(ctx.saved_tensors, ctx.cfg, v_means2d, v_depths, v_conics, v_comps, v_opac_out, v_colors,
+                                 want_viewmats=want_view)
+        return tuple(grads[:5]) + ((grads[5] if want_view else None),) + (None,) * 12
 
 
-def project_backward(saved, cfg, v_means2d, v_depths, v_conics, v_comps, v_opac_out, v_colors):
+def project_backward(saved, cfg, v_means2d, v_depths, v_conics, v_comps, v_opac_out, v_colors, want_viewmats=False):
     """VJP of stage 1 from dense ``[C,N,..]`` cotangents (any of them may be None): (v_means, v_quats, v_scales,
-    v_opacities, v_sh_coeffs).  Shared by ``_ProjectFused`` and the multi-GPU ``_ProjectRoute``."""
+    v_opacities, v_sh_coeffs[, v_viewmats]).  Shared by ``_ProjectFused`` and the multi-GPU ``_ProjectRoute``."""
     means, quats, scales, opacities, sh_coeffs, viewmats, Ks, campos, radii = saved
     width, height, eps2d, near_plane, far_plane, radius_clip, antialiased, sh_degree = cfg
     N, C = means.shape[0], viewmats.shape[0]
@@ -171,9 +172,10 @@ def project_backward(saved, cfg, v_means2d, v_depths, v_conics, v_comps, v_opac_
         K = (sh_degree + 1) ** 2
         v_sh = torch.empty_like(sh_coeffs) if K == sh_coeffs.shape[1] else torch.zeros_like(sh_coeffs)
     if N == 0:
-        return v_means, v_quats, v_scales, v_opac, v_sh
+        return (v_means, v_quats, v_scales, v_opac, v_sh) + ((torch.zeros_like(viewmats),) if want_viewmats else ())
     lib = L.lib()
     st = L.stream_ptr(dev)
+    v_view = torch.zeros(C, 16, device=dev) if want_viewmats else None
     # scratch for the sparse backward (rows with all-zero cotangents are filtered once; include/b2s.h)
     ws = None
     if C <= MAX_CAMS and os.environ.get("B2S_SPARSE_BWD", "1") != "0":
@@ -213,7 +215,23 @@ def project_backward(saved, cfg, v_means2d, v_depths, v_conics, v_comps, v_opac_
         else:
             with _stage("project_bwd", launches=(5 if with_sh else 2) if sparse else (2 if with_sh else 1)):
                 check(lib.b2s_project_bwd(ctypes.byref(args(0)), st), "b2s_project_bwd")
-    return v_means, v_quats, v_scales, v_opac, v_sh
+        if want_viewmats:
+            with _stage("viewmat_bwd"):
+                check(lib.b2s_viewmat_bwd(ctypes.byref(args(0)), ptr(v_view[c0:c1]), st), "b2s_viewmat_bwd")
+    if not want_viewmats:
+        return v_means, v_quats, v_scales, v_opac, v_sh
+    # assemble [C,4,4]: rotation block and translation column; the SH view directions reach the camera through its
+    # centre campos = -A^-1 t (as torch.linalg.inv does upstream): d campos = -A^-1 dA campos - A^-1 dt
+    A, t = viewmats[:, :3, :3].double(), viewmats[:, :3, 3].double()
+    d_rot, d_t, d_cam = v_view[:, :9].reshape(C, 3, 3).double(), v_view[:, 9:12].double(), v_view[:, 12:15].double()
+    if campos is None:
+        cam_c = -torch.linalg.solve(A, t.unsqueeze(-1)).squeeze(-1)
+        w = torch.linalg.solve(A.transpose(1, 2), d_cam.unsqueeze(-1)).squeeze(-1)
+        d_rot = d_rot - w.unsqueeze(-1) * cam_c.unsqueeze(-2)
+        d_t = d_t - w
+    v_viewmats = torch.zeros(C, 4, 4, dtype=torch.float64, device=dev)
+    v_viewmats[:, :3, :3], v_viewmats[:, :3, 3] = d_rot, d_t
+    return v_means, v_quats, v_scales, v_opac, v_sh, v_viewmats.to(viewmats.dtype)
 
 
 def fully_fused_projection(

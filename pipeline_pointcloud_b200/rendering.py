@@ -118,7 +118,7 @@ def rasterization(
     elif fused_sh:
         cols = sh_cols
     else:  # per-camera coefficients [C,N,K,3]
-        campos = torch.linalg.inv(viewmats.detach().float())[:, :3, 3]
+        campos = torch.linalg.inv(viewmats.float())[:, :3, 3]
         dirs = means[None, :, :] - campos[:, None, :]
         cols = ops.spherical_harmonics(sh_degree, dirs, colors, masks=radii > 0)
         cols = torch.clamp_min(cols + 0.5, 0.0)

@@ -384,3 +384,34 @@ def test_tma_coefficient_path_equals_ldg_path(b2s, monkeypatch, N, C):
     ref = torch.clamp_min(O.spherical_harmonics(3, dirs.double(), a["colors"][None].expand(C, N, 16, 3).double(), radii > 0) + 0.5, 0.0)
     ref = ref * (radii > 0)[..., None]
     assert (outs["1"][6].cpu().double() - ref).abs().max() < 2e-5
+
+
+@pytest.mark.parametrize("mode,deg,C", [("antialiased", 3, 2), ("classic", 1, 1), ("classic", None, 3)])
+def test_viewmat_gradients(b2s, mode, deg, C):
+    """gsplat's `v_viewmats` (nerfstudio's camera optimizer reads it): gradients of the render w.r.t. the world->camera
+    matrices -- through the means, the covariances and the SH view directions -- against the oracle's autograd."""
+    N, W, H = 3000, 96, 64
+    a = scene_args(N, deg if deg is not None else 0, C, W, H, seed=14)
+    if deg is None:
+        a["colors"] = torch.rand(N, 3, generator=torch.Generator().manual_seed(2))
+    kw = dict(sh_degree=deg, packed=False, rasterize_mode=mode)
+    ref_in = {k: v.clone() for k, v in a.items()}
+    ref_in["viewmats"].requires_grad_()
+    ref_in["means"].requires_grad_()
+    ref_r, ref_a, ref_m = call(O.rasterization, ref_in, W, H, return_fragile=True, **kw)
+    keep = (~ref_m["fragile"])[..., None].float()
+    gen = torch.Generator().manual_seed(7)
+    v_r, v_a = torch.rand(ref_r.shape, generator=gen) * keep, torch.rand(ref_a.shape, generator=gen) * keep
+    ((ref_r * v_r).sum() + (ref_a * v_a).sum()).backward()
+    g = {k: v.cuda() for k, v in a.items()}
+    g["viewmats"].requires_grad_()
+    g["means"].requires_grad_()
+    r, al, m = call(b2s.rasterization, g, W, H, **kw)
+    ((r * v_r.cuda()).sum() + (al * v_a.cuda()).sum()).backward()
+    got, ref = g["viewmats"].grad.cpu().double(), ref_in["viewmats"].grad.double()
+    assert got.shape == (C, 4, 4) and torch.all(got[:, 3] == 0)
+    for c in range(C):
+        rel = ((got[c, :3] - ref[c, :3]).norm() / ref[c, :3].norm()).item()
+        assert rel < 1e-3, (c, rel, got[c], ref[c])
+    assert grad_report(g["means"].grad, ref_in["means"].grad)[0] < 1e-3
+    assert g["Ks"].grad is None
