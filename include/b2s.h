@@ -347,9 +347,9 @@ B2S_API int b2s_stripe_scatter_add(int32_t world, int32_t channels, const float*
  * a source whose count exceeds it (or overflow != 0) publishes only its tag -- the receivers see it in info[3] and
  * the caller grows the buffers collectively and repeats the call.  The caller provides ONE barrier between
  * b2s_route_project and b2s_route_scan and alternates two buffer sets (parity) between consecutive exchanges.
- *   b2s_route_scan   : row_base[region][source CTA] = exclusive prefix of the row counts in receive order (source rank,
- *                      camera, Gaussian); info (int64 [4 + 2 world]) = rows, tile intersections, coarse-bin records,
- *                      max source Gaussian count, rows per source, Gaussian count per source
+ *   b2s_route_scan   : row_base[region][source CTA] = exclusive prefix of the row counts inside the source (camera, then
+ *                      Gaussian order); info (int64 [4 + 4 world]): info[4 + 4 s ..] = (rows, Gaussian count, tile
+ *                      intersections, coarse-bin records) of source s (one CTA per source; the host adds them up)
  *   b2s_route_gather : occupied slots -> compact tensors (camera_ids local, gaussian_ids GLOBAL = sum of the lower
  *                      ranks' counts + local index) and the inputs of binning, as b2s_stripe_unpack
  * The backward returns the gradients with b2s_stripe_return / b2s_stripe_scatter_add.
@@ -377,7 +377,8 @@ B2S_API int b2s_route_project(const b2s_route_args* a, b2s_stream_t stream);
 B2S_API int b2s_route_scan(int32_t world, int32_t region_cams, int64_t cap_rows, const int32_t* cnt, int32_t* row_base,
                            int64_t* info, b2s_stream_t stream);
 B2S_API int b2s_route_gather(int32_t world, int32_t region_cams, int64_t cap_rows, int32_t channels, const float* rec,
-                             const int32_t* cnt, const int32_t* row_base, const int64_t* host_n_src, int64_t n_rows,
+                             const int32_t* cnt, const int32_t* row_base, const int64_t* host_n_src,
+                             const int64_t* host_rows_from /* [world]: rows per source, from info */, int64_t n_rows,
                              int32_t tile_size, int32_t tile_w, int32_t tile_h, const b2s_tile_rows* rows, float* means2d,
                              float* depths, float* conics, float* opacities, float* colors, int32_t* radii, int64_t* camera_ids,
                              int64_t* gaussian_ids, int32_t* tiles_per_gauss, uint32_t* depth_keys, int32_t* row_ids,

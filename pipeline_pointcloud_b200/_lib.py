@@ -164,7 +164,7 @@ SYMBOLS = {
     "b2s_route_cnt_ints": (c_int64, [c_int32, c_int32, c_int64]),
     "b2s_route_project": (c_int32, [POINTER(RouteArgs), c_void_p]),
     "b2s_route_scan": (c_int32, [c_int32, c_int32, c_int64, c_void_p, c_void_p, c_void_p, c_void_p]),
-    "b2s_route_gather": (c_int32, [c_int32, c_int32, c_int64, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_int64,
+    "b2s_route_gather": (c_int32, [c_int32, c_int32, c_int64, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64,
                                    c_int32, c_int32, c_int32, POINTER(TileRows)] + [c_void_p] * 11 + [c_void_p]),
     "b2s_l1_ssim_ctas": (c_int64, [c_int32, c_int32, c_int32]),
     "b2s_l1_ssim_fwd": (c_int32, [c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),

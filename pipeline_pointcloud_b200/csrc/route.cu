@@ -223,77 +223,97 @@ __global__ void __launch_bounds__(FWD_THREADS) project_route_kernel(const b2s_pr
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
-// receiver: scan of the count table.  One CTA walks the regions in order (source-rank major, camera, source CTA):
-// row_base = exclusive prefix of the row counts; info = [n_rows, n_isects, n_records, max N_src, rows per source (W),
-// N per source (W)].
+// receiver: scan of the count table, one CTA per source rank.  row_base[region][source CTA] = exclusive prefix of the row
+// counts INSIDE the source (camera-major, then source CTA); info[4 + 4 s ..] = (rows, Gaussian count, tile intersections,
+// coarse-bin records) of source s -- the host adds the sources up when it reads them (its one sync).
+// Every thread takes 8 consecutive entries per sweep (independent 128-bit loads), so a source of 8 K CTAs is one sweep.
 // ---------------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(1024) route_scan_kernel(int world, int region_cams, long long n_ctas_cap, const int32_t* __restrict__ cnt,
-                                                          int32_t* __restrict__ row_base, long long* __restrict__ info) {
+constexpr int SC_THREADS = 1024, SC_PER = 8;
+__global__ void __launch_bounds__(SC_THREADS) route_scan_kernel(int region_cams, long long n_ctas_cap, const int32_t* __restrict__ cnt,
+                                                                int32_t* __restrict__ row_base, long long* __restrict__ info) {
     __shared__ unsigned s_wsum[32];
-    __shared__ unsigned long long s_carry, s_tiles, s_coarse, s_src;
+    __shared__ unsigned long long s_tl[32], s_co[32];
+    __shared__ unsigned long long s_carry, s_tiles, s_coarse;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int src = blockIdx.x;
+    const long long n_src = cnt[((long long)src * region_cams * n_ctas_cap) * 4 + 3];     // tag of (src, camera 0, CTA 0)
+    const long long n_ctas = min((max(n_src, 0LL) + FWD_THREADS - 1) / FWD_THREADS, n_ctas_cap);
+    const long long items = n_ctas * region_cams;
     if (threadIdx.x == 0) { s_carry = 0ull; s_tiles = 0ull; s_coarse = 0ull; }
     __syncthreads();
-    long long max_n = 0;
-    for (int src = 0; src < world; ++src) {
-        const long long n_src = cnt[((long long)src * region_cams * n_ctas_cap) * 4 + 3];     // tag of (src, camera 0, CTA 0)
-        max_n = max(max_n, n_src);
-        const long long n_ctas = min((n_src + FWD_THREADS - 1) / FWD_THREADS, n_ctas_cap);
-        if (threadIdx.x == 0) s_src = 0ull;
-        __syncthreads();
-        for (int lc = 0; lc < region_cams; ++lc) {
-            const long long reg = (long long)src * region_cams + lc;
-            for (long long base = 0; base < n_ctas; base += 1024) {
-                const long long k = base + threadIdx.x;
-                int4 e = make_int4(0, 0, 0, 0);
-                if (k < n_ctas) e = *reinterpret_cast<const int4*>(cnt + (reg * n_ctas_cap + k) * 4);
-                unsigned incl = (unsigned)e.x;
-                unsigned long long tl = (unsigned long long)e.y, co = (unsigned long long)e.z;
+    for (long long base = 0; base < items; base += (long long)SC_THREADS * SC_PER) {
+        const long long k0 = base + (long long)threadIdx.x * SC_PER;
+        unsigned rows[SC_PER];
+        long long addr[SC_PER];
+        unsigned tsum = 0;
+        unsigned long long tl = 0, co = 0;
 #pragma unroll
-                for (int d = 1; d < 32; d <<= 1) {
-                    const unsigned t = __shfl_up_sync(FULL, incl, d);
-                    if (lane >= d) incl += t;
-                }
-#pragma unroll
-                for (int d = 16; d > 0; d >>= 1) { tl += __shfl_xor_sync(FULL, tl, d); co += __shfl_xor_sync(FULL, co, d); }
-                if (lane == 31) s_wsum[warp] = incl;
-                if (lane == 0 && (tl | co)) { atomicAdd(&s_tiles, tl); atomicAdd(&s_coarse, co); }
-                __syncthreads();
-                if (warp == 0) {
-                    const unsigned w = s_wsum[lane];
-                    unsigned wi = w;
-#pragma unroll
-                    for (int d = 1; d < 32; d <<= 1) {
-                        const unsigned t = __shfl_up_sync(FULL, wi, d);
-                        if (lane >= d) wi += t;
-                    }
-                    s_wsum[lane] = wi - w;
-                }
-                __syncthreads();
-                const unsigned long long carry = s_carry;
-                if (k < n_ctas) row_base[reg * n_ctas_cap + k] = (int32_t)(carry + s_wsum[warp] + incl - (unsigned)e.x);
-                __syncthreads();
-                if (threadIdx.x == 1023) {
-                    const unsigned long long sweep = (unsigned long long)s_wsum[31] + incl;
-                    s_carry = carry + sweep;
-                    s_src += sweep;
-                }
-                __syncthreads();
+        for (int i = 0; i < SC_PER; ++i) {
+            const long long k = k0 + i;
+            int4 e = make_int4(0, 0, 0, 0);
+            addr[i] = -1;
+            if (k < items) {
+                const long long lc = k / n_ctas, b = k - lc * n_ctas;
+                addr[i] = ((long long)src * region_cams + lc) * n_ctas_cap + b;
+                e = *reinterpret_cast<const int4*>(cnt + addr[i] * 4);
             }
+            rows[i] = (unsigned)e.x;
+            tsum += rows[i];
+            tl += (unsigned long long)e.y;
+            co += (unsigned long long)e.z;
         }
-        if (threadIdx.x == 0) { info[4 + src] = (long long)s_src; info[4 + world + src] = n_src; }
+        unsigned incl = tsum;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const unsigned t = __shfl_up_sync(FULL, incl, d);
+            if (lane >= d) incl += t;
+        }
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) { tl += __shfl_xor_sync(FULL, tl, d); co += __shfl_xor_sync(FULL, co, d); }
+        if (lane == 31) s_wsum[warp] = incl;
+        if (lane == 0) { s_tl[warp] = tl; s_co[warp] = co; }
+        __syncthreads();
+        if (warp == 0) {
+            const unsigned w = s_wsum[lane];
+            unsigned wi = w;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const unsigned t = __shfl_up_sync(FULL, wi, d);
+                if (lane >= d) wi += t;
+            }
+            s_wsum[lane] = wi - w;                     // exclusive prefix of the warp totals
+            unsigned long long a = s_tl[lane], c = s_co[lane];
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) { a += __shfl_xor_sync(FULL, a, d); c += __shfl_xor_sync(FULL, c, d); }
+            if (lane == 0) { s_tiles += a; s_coarse += c; }
+        }
+        __syncthreads();
+        const unsigned long long carry = s_carry;
+        unsigned run = (unsigned)carry + s_wsum[warp] + incl - tsum;
+#pragma unroll
+        for (int i = 0; i < SC_PER; ++i) {
+            if (addr[i] >= 0) row_base[addr[i]] = (int32_t)run;
+            run += rows[i];
+        }
+        __syncthreads();
+        if (threadIdx.x == SC_THREADS - 1) s_carry = carry + s_wsum[31] + incl;      // thread 1023 holds the sweep's last inclusive sum
         __syncthreads();
     }
-    if (threadIdx.x == 0) { info[0] = (long long)s_carry; info[1] = (long long)s_tiles; info[2] = (long long)s_coarse; info[3] = max_n; }
+    if (threadIdx.x == 0) {
+        info[4 + 4 * src] = (long long)s_carry; info[4 + 4 * src + 1] = n_src;
+        info[4 + 4 * src + 2] = (long long)s_tiles; info[4 + 4 * src + 3] = (long long)s_coarse;
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
-// receiver: occupied slots -> compact tensors (one warp per source CTA), plus what binning needs
+// receiver: occupied slots -> compact tensors (one warp per source CTA), plus what binning needs.  A source CTA's rows
+// are one contiguous run of records: the warp moves 32 records at a time through shared memory with coalesced 128-bit
+// loads, then every lane takes its row apart and the fields leave as coalesced stores.
 // ---------------------------------------------------------------------------------------------------------------------
 struct GatherArgs {
     int world, region_cams, ch;
     long long cap_rows, n_ctas_cap;
-    long long n_src[B2S_MAX_RANKS], gid_offset[B2S_MAX_RANKS], cta_base[B2S_MAX_RANKS + 1];   // cta_base: first work item of source s
+    long long n_src[B2S_MAX_RANKS], gid_offset[B2S_MAX_RANKS], row_offset[B2S_MAX_RANKS], cta_base[B2S_MAX_RANKS + 1];
     const float* rec; const int32_t* cnt; const int32_t* row_base;
     float tile_size; int tile_w, row_lo, row_hi;
     float2* means2d; float* depths; float* conics; float* opac; float* colors; int32_t* radii;
@@ -301,8 +321,9 @@ struct GatherArgs {
 };
 
 __global__ void __launch_bounds__(256) route_gather_kernel(const GatherArgs a) {
-    const int lane = threadIdx.x & 31;
-    const long long item = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);          // (source, camera, source CTA), flattened
+    __shared__ __align__(16) float s_rows[8][32 * RT_MAXF];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long long item = (long long)blockIdx.x * 8 + warp;          // (source, camera, source CTA), flattened
     if (item >= a.cta_base[a.world]) return;
     int src = 0;
     while (src + 1 < a.world && item >= a.cta_base[src + 1]) ++src;
@@ -312,28 +333,37 @@ __global__ void __launch_bounds__(256) route_gather_kernel(const GatherArgs a) {
     const long long b = local - (long long)lc * n_ctas;
     const long long reg = (long long)src * a.region_cams + lc;
     const int count = a.cnt[(reg * a.n_ctas_cap + b) * 4];
-    const long long base = a.row_base[reg * a.n_ctas_cap + b];
+    const long long base = a.row_offset[src] + a.row_base[reg * a.n_ctas_cap + b];
     const int F = 10 + a.ch;
-    const float* slot = a.rec + (reg * a.cap_rows + b * FWD_THREADS) * (long long)F;
-    for (int t = lane; t < count; t += 32) {
-        const float* p = slot + (long long)t * F;
-        const long long j = base + t;
-        const float2 m = make_float2(p[0], p[1]);
-        const float depth = p[2];
-        a.means2d[j] = m;
-        a.depths[j] = depth;
-        a.conics[3 * j] = p[3]; a.conics[3 * j + 1] = p[4]; a.conics[3 * j + 2] = p[5];
-        a.opac[j] = p[6];
-        for (int k = 0; k < a.ch; ++k) a.colors[j * a.ch + k] = p[7 + k];
-        const int radius = __float_as_int(p[7 + a.ch]);
-        a.radii[j] = radius;
-        a.camera_ids[j] = (int64_t)__float_as_int(p[8 + a.ch]);
-        a.gaussian_ids[j] = a.gid_offset[src] + (int64_t)__float_as_int(p[9 + a.ch]);
-        int x0, y0, x1, y1;
-        tile_rect(m.x, m.y, radius, a.tile_size, a.tile_w, a.row_lo, a.row_hi, x0, y0, x1, y1);
-        a.tiles[j] = max(0, x1 - x0) * max(0, y1 - y0);
-        a.depth_keys[j] = radius > 0 ? __float_as_uint(depth) : 0xFFFFFFFFu;
-        a.row_ids[j] = (int32_t)j;
+    const float* slot = a.rec + (reg * a.cap_rows + b * FWD_THREADS) * (long long)F;     // 16-byte aligned: 256 F floats per slot
+    float* sm = s_rows[warp];
+    for (int t0 = 0; t0 < count; t0 += 32) {
+        const int rows = min(32, count - t0);
+        const int n4 = (rows * F + 3) >> 2;                             // (reads at most 3 floats past the chunk, inside the slot's 256 rows or its successor)
+        const float4* g4 = reinterpret_cast<const float4*>(slot + (long long)t0 * F);
+        for (int q = lane; q < n4; q += 32) reinterpret_cast<float4*>(sm)[q] = ldg_stream4(g4 + q);
+        __syncwarp();
+        if (lane < rows) {
+            const float* p = sm + lane * F;
+            const long long j = base + t0 + lane;
+            const float2 m = make_float2(p[0], p[1]);
+            const float depth = p[2];
+            a.means2d[j] = m;
+            a.depths[j] = depth;
+            a.conics[3 * j] = p[3]; a.conics[3 * j + 1] = p[4]; a.conics[3 * j + 2] = p[5];
+            a.opac[j] = p[6];
+            for (int k = 0; k < a.ch; ++k) a.colors[j * a.ch + k] = p[7 + k];
+            const int radius = __float_as_int(p[7 + a.ch]);
+            a.radii[j] = radius;
+            a.camera_ids[j] = (int64_t)__float_as_int(p[8 + a.ch]);
+            a.gaussian_ids[j] = a.gid_offset[src] + (int64_t)__float_as_int(p[9 + a.ch]);
+            int x0, y0, x1, y1;
+            tile_rect(m.x, m.y, radius, a.tile_size, a.tile_w, a.row_lo, a.row_hi, x0, y0, x1, y1);
+            a.tiles[j] = max(0, x1 - x0) * max(0, y1 - y0);
+            a.depth_keys[j] = radius > 0 ? __float_as_uint(depth) : 0xFFFFFFFFu;
+            a.row_ids[j] = (int32_t)j;
+        }
+        __syncwarp();
     }
 }
 
@@ -418,33 +448,37 @@ extern "C" int b2s_route_scan(int32_t world, int32_t region_cams, int64_t cap_ro
                               int64_t* info, b2s_stream_t stream) {
     B2S_REQUIRE(world >= 1 && world <= B2S_MAX_RANKS && region_cams > 0 && cap_rows > 0 && cap_rows % FWD_THREADS == 0, "bad sizes");
     B2S_REQUIRE(cnt && row_base && info && aligned16(cnt), "null / misaligned pointer");
-    route_scan_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(world, region_cams, cap_rows / FWD_THREADS, cnt, row_base,
-                                                            reinterpret_cast<long long*>(info));
+    route_scan_kernel<<<world, SC_THREADS, 0, (cudaStream_t)stream>>>(region_cams, cap_rows / FWD_THREADS, cnt, row_base,
+                                                                     reinterpret_cast<long long*>(info));
     B2S_LAUNCH_CHECK();
     return 0;
 }
 
 extern "C" int b2s_route_gather(int32_t world, int32_t region_cams, int64_t cap_rows, int32_t channels, const float* rec,
-                                const int32_t* cnt, const int32_t* row_base, const int64_t* host_n_src, int64_t n_rows,
+                                const int32_t* cnt, const int32_t* row_base, const int64_t* host_n_src,
+                                const int64_t* host_rows_from, int64_t n_rows,
                                 int32_t tile_size, int32_t tile_w, int32_t tile_h, const b2s_tile_rows* rows, float* means2d,
                                 float* depths, float* conics, float* opacities, float* colors, int32_t* radii, int64_t* camera_ids,
                                 int64_t* gaussian_ids, int32_t* tiles_per_gauss, uint32_t* depth_keys, int32_t* row_ids,
                                 b2s_stream_t stream) {
     B2S_REQUIRE(world >= 1 && world <= B2S_MAX_RANKS && region_cams > 0 && cap_rows > 0 && cap_rows % FWD_THREADS == 0, "bad sizes");
-    B2S_REQUIRE(channels >= 1 && channels <= RT_MAXCH && host_n_src && tile_size > 0 && tile_w > 0 && tile_h > 0, "bad args");
+    B2S_REQUIRE(channels >= 1 && channels <= RT_MAXCH && host_n_src && host_rows_from && tile_size > 0 && tile_w > 0 && tile_h > 0,
+                "bad args");
     if (n_rows == 0) return 0;
     B2S_REQUIRE(rec && cnt && row_base && means2d && depths && conics && opacities && colors && radii && camera_ids && gaussian_ids &&
                 tiles_per_gauss && depth_keys && row_ids, "null pointer");
     GatherArgs g;
     g.world = world; g.region_cams = region_cams; g.ch = channels; g.cap_rows = cap_rows; g.n_ctas_cap = cap_rows / FWD_THREADS;
-    long long off = 0, items = 0;
+    long long off = 0, items = 0, rows_before = 0;
     for (int s = 0; s < B2S_MAX_RANKS; ++s) {
         const long long ns = s < world ? host_n_src[s] : 0;
         B2S_REQUIRE(ns >= 0 && ns <= cap_rows, "a source's Gaussian count exceeds the region capacity");
-        g.n_src[s] = ns; g.gid_offset[s] = off; g.cta_base[s] = items;
+        g.n_src[s] = ns; g.gid_offset[s] = off; g.cta_base[s] = items; g.row_offset[s] = rows_before;
         off += ns;
         items += cdiv(ns, FWD_THREADS) * region_cams;
+        rows_before += s < world ? host_rows_from[s] : 0;
     }
+    B2S_REQUIRE(rows_before == n_rows, "rows per source do not add up to n_rows");
     g.cta_base[B2S_MAX_RANKS] = items;
     for (int s = world; s <= B2S_MAX_RANKS; ++s) g.cta_base[s] = items;
     g.rec = rec; g.cnt = cnt; g.row_base = row_base;

@@ -547,7 +547,7 @@ class _ProjectRoute(torch.autograd.Function):
         lib, st = L.lib(), L.stream_ptr(dev)
         state = _RouteBuffers.get(group, dev, world, region_cams, N)
         radii = torch.empty(C, N, dtype=torch.int32, device=dev)
-        info = torch.empty(4 + 2 * world, dtype=torch.int64, device=dev)
+        info = torch.empty(4 + 4 * world, dtype=torch.int64, device=dev)
         for attempt in range(3):
             cap = state["cap"]
             bufs = _RouteBuffers.tensors(state, group, dev, world)
@@ -578,14 +578,15 @@ class _ProjectRoute(torch.autograd.Function):
             with ops._stage("route_scan"):
                 L.check(lib.b2s_route_scan(world, region_cams, cap, L.ptr(cnt), L.ptr(row_base), L.ptr(info), st), "b2s_route_scan")
             host = info.tolist()               # the one host sync of the forward: sizes of everything downstream
-            if host[3] <= cap:
+            rows_from, n_world = [int(host[4 + 4 * s]) for s in range(world)], [int(host[5 + 4 * s]) for s in range(world)]
+            if max(n_world) <= cap:
                 break
             # a source no longer fits its regions (densification grew it): every rank saw the same tags -> grow together
-            state["cap"] = _RouteBuffers.round_cap(host[3])
+            state["cap"] = _RouteBuffers.round_cap(max(n_world))
         else:
             raise RuntimeError("route buffers could not be grown")
-        n_recv, n_isects, n_records = int(host[0]), int(host[1]), int(host[2])
-        rows_from, n_world = [int(v) for v in host[4:4 + world]], [int(v) for v in host[4 + world:4 + 2 * world]]
+        n_recv = sum(rows_from)
+        n_isects, n_records = sum(int(host[6 + 4 * s]) for s in range(world)), sum(int(host[7 + 4 * s]) for s in range(world))
         o = dict(device=dev)
         means2d_m, depths_m, conics_m = torch.empty(n_recv, 2, **o), torch.empty(n_recv, **o), torch.empty(n_recv, 3, **o)
         opac_m, cols_m = torch.empty(n_recv, **o), torch.empty(n_recv, ch, **o)
@@ -594,7 +595,7 @@ class _ProjectRoute(torch.autograd.Function):
         cam_m, gid_m = torch.empty(n_recv, dtype=torch.int64, **o), torch.empty(n_recv, dtype=torch.int64, **o)
         rows = L.TileRows(0, th) if cams_per_rank else L.TileRows(int(bounds[rank]), int(bounds[rank + 1]))
         with ops._stage("route_gather"):
-            L.check(lib.b2s_route_gather(world, region_cams, cap, ch, L.ptr(rec), L.ptr(cnt), L.ptr(row_base), _i64(n_world), n_recv,
+            L.check(lib.b2s_route_gather(world, region_cams, cap, ch, L.ptr(rec), L.ptr(cnt), L.ptr(row_base), _i64(n_world), _i64(rows_from), n_recv,
                                          tile_size, tw, th, ctypes.byref(rows), L.ptr(means2d_m), L.ptr(depths_m), L.ptr(conics_m),
                                          L.ptr(opac_m), L.ptr(cols_m), L.ptr(radii_m), L.ptr(cam_m), L.ptr(gid_m), L.ptr(tiles_m),
                                          L.ptr(dkeys), L.ptr(rowids), st), "b2s_route_gather")
