@@ -212,8 +212,11 @@ __global__ void __launch_bounds__(FWD_THREADS) project_route_kernel(const b2s_pr
             }
             __syncthreads();
             // one contiguous, coalesced run of `total` records into the destination's slot of this CTA
-            float* dst = rp.rec[d] + ((reg * rp.cap_rows + row0) * (long long)F);
-            for (int t = threadIdx.x; t < total * F; t += FWD_THREADS) dst[t] = s_stage[t];
+            // (128-bit peer stores; the slot starts 16-byte aligned and the last store may run up to 3 floats past the
+            // CTA's records, still inside its own 256-row slot)
+            float4* dst = reinterpret_cast<float4*>(rp.rec[d] + ((reg * rp.cap_rows + row0) * (long long)F));
+            const float4* src4 = reinterpret_cast<const float4*>(s_stage);
+            for (int t = threadIdx.x; t < ((total * F + 3) >> 2); t += FWD_THREADS) dst[t] = src4[t];
             if (threadIdx.x == 0) {
                 int4 e = make_int4(total, t_tiles, t_coarse, blockIdx.x == 0 ? (int)a.N : 0);
                 *reinterpret_cast<int4*>(rp.cnt[d] + (reg * rp.n_ctas_cap + blockIdx.x) * 4) = e;
