@@ -81,7 +81,8 @@ def workload_config(workload, packed, world, multi_gpu):
         s += (", Gaussians sharded over ranks, fused pack + NVLink peer-store exchange of projected splats to the camera owners "
               "(NCCL all-to-all when peer access is unavailable), gradients returned by the reverse exchange")
     elif world > 1:
-        s += ", replicated Gaussians, dense-gradient all-reduce"
+        s += ", replicated Gaussians, gradient all-reduce" + (" (NCCL, dense)" if multi_gpu == "allreduce_dense"
+                                                              else " (sparse records when few rows are live, else NCCL dense)")
     return {"workload": s, "l2": "inputs (1.4 GB parameters + 0.3 GB keys at config 3) exceed the 126 MB L2",
             "parallelism": f"dp{world}"}
 
@@ -310,7 +311,7 @@ def run_gpu(workload, multi_gpu, steps, warmup, packed=False, e2e_steps=0, stage
     import torch.distributed as dist
     import pipeline_pointcloud_b200 as b2s
     from pipeline_pointcloud_b200 import ops
-    from pipeline_pointcloud_b200.distributed import allreduce_gradients
+    from pipeline_pointcloud_b200.distributed import allreduce_gradients, allreduce_splat_gradients
 
     rank = dist.get_rank() if dist.is_initialized() else 0
     world = dist.get_world_size() if dist.is_initialized() else 1
@@ -363,8 +364,11 @@ def run_gpu(workload, multi_gpu, steps, warmup, packed=False, e2e_steps=0, stage
                                     c["Ks"], W, H, **kw)
         torch.autograd.backward([r, a], [vr, va])
         if world > 1 and not sharded:
-            with ops._stage("grad_allreduce", launches=0):
-                allreduce_gradients(p.values())
+            if multi_gpu == "allreduce_dense":
+                with ops._stage("grad_allreduce", launches=0):
+                    allreduce_gradients(p.values())
+            else:
+                allreduce_splat_gradients(p["means"], p["quats"], p["scales"], p["opacities"], p["colors"])
         return r, a, m
 
     def barrier():
@@ -574,10 +578,11 @@ def main():
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (profiling runs only)")
     ap.add_argument("--no-extras", action="store_true", help="skip the side measurements (profiling runs only)")
     ap.add_argument("--no-balance", action="store_true", help="stripes: keep the even split of the tile rows")
-    ap.add_argument("--multi-gpu", default="sharded", choices=["sharded", "allreduce", "stripes"],
+    ap.add_argument("--multi-gpu", default="sharded", choices=["sharded", "allreduce", "allreduce_dense", "stripes"],
                     help="N>1: 'sharded' = Gaussians sharded over ranks + exchange of projected splats to the camera "
                          "owners (rasterization(distributed=True), what the reference's multi-GPU branch runs); "
-                         "'allreduce' = replicated Gaussians + dense-gradient all-reduce (BASELINE config 4); "
+                         "'allreduce' = replicated Gaussians + gradient all-reduce (BASELINE config 4), sparse when few rows are "
+                         "live ('allreduce_dense': always NCCL's dense all-reduce); "
                          "'stripes' = ONE camera, Gaussians sharded over ranks, every rank composites a stripe of tile rows "
                          "(rasterization(distributed=True, tile_stripes=True), BASELINE config 5; strong scaling)")
     args = ap.parse_args()
@@ -641,6 +646,7 @@ def main():
         else:
             side("config5_stripes", "config5", "stripes")
             side("config4_allreduce", "config3", "allreduce")
+            side("config4_allreduce_dense", "config3", "allreduce_dense")
 
     if rank != 0:
         if world > 1:

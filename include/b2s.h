@@ -331,6 +331,19 @@ B2S_API int b2s_stripe_scatter_add(int32_t world, int32_t channels, const float*
                                    b2s_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Sparse gradient synchronisation for camera data-parallel training (BASELINE config 4; csrc/gradsync.cu):
+ * instead of all-reducing 236 B per Gaussian, every rank compacts the rows that carry a gradient into records
+ * [row, v_means 3, v_quats 4, v_scales 3, v_opacity, v_sh sh_floats] (12 + sh_floats words), the records are
+ * all-gathered and added into every rank's dense gradients.  total[0] (device, zeroed by the call) = live rows; at most
+ * `cap` records are written -- when total exceeds cap the caller falls back to the dense all-reduce.
+ * ---------------------------------------------------------------------------------------------- */
+B2S_API int b2s_grad_compact(int64_t N, int32_t sh_floats, const float* v_means, const float* v_quats, const float* v_scales,
+                             const float* v_opacities /* or NULL */, const float* v_sh /* [N, sh_floats] or NULL */,
+                             int64_t* total, float* records, int64_t cap, b2s_stream_t stream);
+B2S_API int b2s_grad_scatter_add(int64_t n_records, int32_t sh_floats, const float* records, float* v_means, float* v_quats,
+                                 float* v_scales, float* v_opacities, float* v_sh, b2s_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Stage 1 FUSED with the multi-GPU exchange (the "direct" route; csrc/route.cu).  Replaces, for
  * `rasterization(distributed=True)`, upstream's projection -> pack -> all_to_all(counts) -> all_to_all(payload) ->
  * split (gsplat/rendering.py + gsplat/distributed.py behind source/container/src/main.py:1317-1347) and this library's

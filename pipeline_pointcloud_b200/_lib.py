@@ -160,6 +160,9 @@ SYMBOLS = {
                           [c_void_p] * 11 + [c_void_p]),
     "b2s_stripe_return": (c_int32, [c_int64, c_int32] + [c_void_p] * 7 + [c_int64, c_int32] + [c_void_p] * 6 + [c_void_p]),
     "b2s_stripe_scatter_add": (c_int32, [c_int32, c_int32] + [c_void_p] * 9 + [c_void_p]),
+    "b2s_grad_compact": (c_int32, [c_int64, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64,
+                                   c_void_p]),
+    "b2s_grad_scatter_add": (c_int32, [c_int64, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "b2s_route_rec_floats": (c_int64, [c_int32, c_int32, c_int64]),
     "b2s_route_cnt_ints": (c_int64, [c_int32, c_int32, c_int64]),
     "b2s_route_project": (c_int32, [POINTER(RouteArgs), c_void_p]),

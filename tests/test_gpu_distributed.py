@@ -78,3 +78,87 @@ def test_sharded_all_to_all_matches_single_gpu(tmp_path, route, render_mode):
             assert rel < 1e-4, (rank, k, rel)
         rows += got["n_rows"]
     assert rows == m["means2d"].shape[0]
+
+
+def test_grad_compact_and_scatter_add_single_gpu():
+    """The two kernels of the sparse gradient synchronisation (csrc/gradsync.cu) without a process group: the records of
+    rank A's live rows, added into rank B's dense gradients, give A + B."""
+    from pipeline_pointcloud_b200 import _lib as L
+    torch.manual_seed(0)
+    N, K = 20_000, 16
+    dev = torch.device("cuda", 0)
+    shapes = [(N, 3), (N, 4), (N, 3), (N,), (N, K, 3)]
+
+    def sparse_grads(seed, frac):
+        g = torch.Generator(device="cpu").manual_seed(seed)
+        live = torch.rand(N, generator=g) < frac
+        out = []
+        for s in shapes:
+            t = torch.randn(s, generator=g)
+            t[~live] = 0
+            out.append(t.to(dev))
+        # a row whose only gradient is its colour: still live (first SH row non-zero)
+        out[0][live.nonzero()[0, 0]] = 0; out[1][live.nonzero()[0, 0]] = 0; out[2][live.nonzero()[0, 0]] = 0; out[3][live.nonzero()[0, 0]] = 0
+        return out, int(live.sum())
+
+    a, na = sparse_grads(1, 0.03)
+    b, _ = sparse_grads(2, 0.05)
+    lib, st = L.lib(), L.stream_ptr(dev)
+    R = 12 + 3 * K
+    total = torch.empty(1, dtype=torch.int64, device=dev)
+    rec = torch.empty(N // 8, R, device=dev)
+    L.check(lib.b2s_grad_compact(N, 3 * K, *[L.ptr(t) for t in a], L.ptr(total), L.ptr(rec), N // 8, st), "compact")
+    assert int(total) == na
+    rows = rec[:na, 0].contiguous().view(torch.int32)
+    assert rows.unique().numel() == na
+    want = [x + y for x, y in zip(a, b)]
+    L.check(lib.b2s_grad_scatter_add(na, 3 * K, L.ptr(rec), *[L.ptr(t) for t in b], st), "scatter")
+    for x, y in zip(b, want):
+        assert torch.equal(x, y)                       # one add per element: exact
+    # capacity overflow is reported, not written past
+    L.check(lib.b2s_grad_compact(N, 3 * K, *[L.ptr(t) for t in a], L.ptr(total), L.ptr(rec), 10, st), "compact")
+    assert int(total) == na
+
+
+def _allreduce_worker(rank, port, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=WORLD, device_id=torch.device("cuda", rank))
+    try:
+        import pipeline_pointcloud_b200 as b2s
+        from pipeline_pointcloud_b200.distributed import allreduce_gradients, allreduce_splat_gradients
+        from tests.util import LEAVES, scene_args
+        Nn = 40_000
+        a = scene_args(Nn, DEG, WORLD, W, H, seed=33)
+        a["scales"] *= 3.0                       # saturating scene: few rows carry a gradient
+        a["opacities"] = a["opacities"].clamp_min(0.6)
+        dev = torch.device("cuda", rank)
+        p = {k: a[k].to(dev).requires_grad_() for k in LEAVES}
+        g = torch.Generator().manual_seed(5)
+        v_r, v_a = torch.rand(WORLD, H, W, 3, generator=g), torch.rand(WORLD, H, W, 1, generator=g)
+        r, al, m = b2s.rasterization(p["means"], p["quats"], p["scales"], p["opacities"], p["colors"],
+                                     a["viewmats"][rank:rank + 1].to(dev), a["Ks"][rank:rank + 1].to(dev), W, H, sh_degree=DEG,
+                                     packed=False, rasterize_mode="antialiased")
+        torch.autograd.backward([r, al], [v_r[rank:rank + 1].to(dev), v_a[rank:rank + 1].to(dev)])
+        dense = {k: p[k].grad.clone() for k in LEAVES}
+        for t in dense.values():
+            dist.all_reduce(t)
+        stats = {}
+        mode = allreduce_splat_gradients(p["means"], p["quats"], p["scales"], p["opacities"], p["colors"], stats=stats)
+        torch.save({"mode": mode, "live": stats.get("live_rows"), "sparse": {k: p[k].grad.cpu() for k in LEAVES},
+                    "dense": {k: v.cpu() for k, v in dense.items()}}, os.path.join(out, f"ar{rank}.pt"))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_sparse_gradient_allreduce_matches_dense(tmp_path):
+    from tests.util import LEAVES, grad_report
+    mp.spawn(_allreduce_worker, args=(29790, str(tmp_path)), nprocs=WORLD, join=True)
+    for rank in range(WORLD):
+        got = torch.load(os.path.join(str(tmp_path), f"ar{rank}.pt"))
+        assert got["mode"] == "sparse" and max(got["live"]) < 40_000 // 8, got["live"]
+        for k in LEAVES:
+            assert grad_report(got["sparse"][k], got["dense"][k])[0] < 1e-6, k
+            assert ((got["sparse"][k] == 0) == (got["dense"][k] == 0)).all(), k
