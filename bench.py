@@ -306,7 +306,7 @@ def pctl(xs, q):
     return xs[lo] + (xs[hi] - xs[lo]) * (i - lo)
 
 
-def run_gpu(workload, multi_gpu, steps, warmup, packed=False, e2e_steps=0, stages=True, balance=True, clocks=False):
+def run_gpu(workload, multi_gpu, steps, warmup, packed=False, e2e_steps=0, stages=True, balance=True, clocks=False, touch_meta=False):
     """Times `steps` steps of `workload` on the current process group.  Returns the result dict on every rank."""
     import torch.distributed as dist
     import pipeline_pointcloud_b200 as b2s
@@ -362,7 +362,11 @@ def run_gpu(workload, multi_gpu, steps, warmup, packed=False, e2e_steps=0, stage
             t.grad = None
         r, a, m = b2s.rasterization(p["means"], p["quats"], p["scales"], p["opacities"], p["colors"], c["viewmats"],
                                     c["Ks"], W, H, **kw)
+        if touch_meta:          # what the reference's trainer reads every iteration (densification statistics)
+            m["means2d"].retain_grad()
         torch.autograd.backward([r, a], [vr, va])
+        if touch_meta:
+            assert m["means2d"].grad is not None and m["radii"].shape[0] == m["gaussian_ids"].shape[0]
         if world > 1 and not sharded:
             if multi_gpu == "allreduce_dense":
                 with ops._stage("grad_allreduce", launches=0):
@@ -420,7 +424,8 @@ def run_gpu(workload, multi_gpu, steps, warmup, packed=False, e2e_steps=0, stage
                                     cams["viewmats"], cams["Ks"], W, H, **kw)
         m["opacities"].retain_grad()
         torch.autograd.backward([r, a], [cot["v_r"], cot["v_a"]])
-        stats["n_reached"] = int((m["opacities"].grad != 0).sum())
+        og = m["opacities"].grad          # (packed=True on one GPU: the packed tensors of meta are views off the autograd path)
+        stats["n_reached"] = int((og != 0).sum()) if og is not None else int((params["opacities"].grad != 0).sum())
     del r, a, m
 
     # ---- the timed region: exactly `steps` steps between barrier + synchronize, one event per step ------------------
@@ -639,6 +644,7 @@ def main():
 
         if world == 1:
             side("config3_packed", "config3", "sharded", packed=True)
+            side("config3_packed_meta_read", "config3", "sharded", packed=True, touch_meta=True)
             side("config3_gsplat_init", "config3_init", "sharded")
             side("config2", "config2", "sharded")
             side("config1_fwd", "config1", "sharded")

@@ -170,6 +170,10 @@ B2S_API int b2s_isect_count(int64_t M, const float* means2d, const int32_t* radi
 B2S_API int64_t b2s_isect_scan_workspace_bytes(int64_t M);
 B2S_API int b2s_isect_scan(int64_t M, const int32_t* tiles_per_gauss, int32_t* cum_tiles, int64_t* total,
                            void* workspace, int64_t workspace_bytes, b2s_stream_t stream);
+/* Packed layout (gsplat `packed=True`): sel = the indices of the rows with radius > 0, ascending (camera-major,
+ * Gaussian-ascending), at most cap of them; total[0] (device) = their number.  Workspace as b2s_isect_scan. */
+B2S_API int b2s_select_visible(int64_t M, const int32_t* radii, int64_t* sel, int64_t cap, int64_t* total, void* workspace,
+                               int64_t workspace_bytes, b2s_stream_t stream);
 B2S_API int b2s_isect_fill(int64_t M, int64_t N, const int64_t* camera_ids /* or NULL */, const float* means2d,
                            const int32_t* radii, const float* depths, const int32_t* cum_tiles, int32_t tile_size,
                            int32_t tile_w, int32_t tile_h, int64_t* isect_ids, int32_t* flatten_ids,

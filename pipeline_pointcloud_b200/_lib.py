@@ -126,6 +126,7 @@ SYMBOLS = {
     "b2s_isect_count": (c_int32, [c_int64, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p, POINTER(TileRows), c_void_p]),
     "b2s_isect_scan_workspace_bytes": (c_int64, [c_int64]),
     "b2s_isect_scan": (c_int32, [c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
+    "b2s_select_visible": (c_int32, [c_int64, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_void_p]),
     "b2s_isect_fill": (c_int32, [c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32,
                                  c_int32, c_void_p, c_void_p, POINTER(TileRows), c_void_p]),
     "b2s_isect_sort_workspace_bytes": (c_int64, [c_int64]),

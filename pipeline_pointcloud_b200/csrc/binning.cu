@@ -127,6 +127,58 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_kernel(int64_t M, const int
 }
 
 // -------------------------------------------------------------------------------------------------
+// packed layout: indices of the visible rows (radius > 0), ascending -- camera-major, Gaussian-ascending, the row order
+// of gsplat's packed mode -- by the same single-pass look-back scan (replaces torch.nonzero, a library kernel)
+// -------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(SCAN_THREADS) select_visible_kernel(int64_t M, const int32_t* __restrict__ radii,
+                                                                      int64_t* __restrict__ sel, int64_t cap, int64_t* __restrict__ total,
+                                                                      unsigned long long* status, unsigned int* tile_counter) {
+    __shared__ unsigned int s_tile;
+    __shared__ unsigned long long s_warp[SCAN_THREADS / 32];
+    __shared__ unsigned long long s_prefix;
+    if (threadIdx.x == 0) s_tile = atomicAdd(tile_counter, 1u);
+    __syncthreads();
+    const unsigned int tile = s_tile;
+    const int64_t base = (int64_t)tile * SCAN_TILE + (int64_t)threadIdx.x * SCAN_ITEMS;
+    unsigned flags = 0;
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; ++k)
+        if (base + k < M && radii[base + k] > 0) flags |= 1u << k;
+    const unsigned long long tsum = __popc(flags);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned long long inc = tsum;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        unsigned long long o = __shfl_up_sync(FULL, inc, d);
+        if (lane >= d) inc += o;
+    }
+    if (lane == 31) s_warp[warp] = inc;
+    __syncthreads();
+    unsigned long long warp_off = 0, block_sum = 0;
+#pragma unroll
+    for (int w = 0; w < SCAN_THREADS / 32; ++w) {
+        unsigned long long x = s_warp[w];
+        if (w < warp) warp_off += x;
+        block_sum += x;
+    }
+    if (warp == 0) {
+        const unsigned long long excl = lookback_warp(status, tile, block_sum, lane);
+        if (lane == 0) {
+            s_prefix = excl;
+            if ((int64_t)(tile + 1) * SCAN_TILE >= M) *total = (int64_t)(excl + block_sum);
+        }
+    }
+    __syncthreads();
+    int64_t run = (int64_t)(s_prefix + warp_off + (inc - tsum));
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; ++k)
+        if ((flags >> k) & 1u) {
+            if (run < cap) sel[run] = base + k;
+            ++run;
+        }
+}
+
+// -------------------------------------------------------------------------------------------------
 // fill: one key/value per covered tile, row-major inside the rectangle (y outer, x inner)
 // key = cam << (32 + tile_bits) | tile << 32 | bits(depth)
 // -------------------------------------------------------------------------------------------------
@@ -649,6 +701,29 @@ extern "C" int b2s_isect_scan(int64_t M, const int32_t* tiles_per_gauss, int32_t
     unsigned int* counter = reinterpret_cast<unsigned int*>(workspace);
     unsigned long long* status = reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(workspace) + 16);
     scan_kernel<false><<<(unsigned)tiles, SCAN_THREADS, 0, st>>>(M, tiles_per_gauss, nullptr, cum_tiles, total, status, counter);
+    B2S_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int b2s_select_visible(int64_t M, const int32_t* radii, int64_t* sel, int64_t cap, int64_t* total, void* workspace,
+                                  int64_t workspace_bytes, b2s_stream_t stream) {
+    B2S_REQUIRE(M >= 0 && cap >= 0 && total != nullptr, "bad args");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (M == 0) {
+        B2S_CUDA(cudaMemsetAsync(total, 0, sizeof(int64_t), st));
+        return 0;
+    }
+    B2S_REQUIRE(radii && (sel || cap == 0) && workspace, "null pointer");
+    if (workspace_bytes < b2s_isect_scan_workspace_bytes(M)) {
+        set_error("b2s_select_visible: workspace too small");
+        return B2S_E_WORKSPACE;
+    }
+    B2S_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 15u) == 0, "workspace must be 16-byte aligned");
+    const int64_t tiles = cdiv(M, SCAN_TILE);
+    B2S_CUDA(cudaMemsetAsync(workspace, 0, (size_t)(16 + tiles * 8), st));
+    unsigned int* counter = reinterpret_cast<unsigned int*>(workspace);
+    unsigned long long* status = reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(workspace) + 16);
+    select_visible_kernel<<<(unsigned)tiles, SCAN_THREADS, 0, st>>>(M, radii, sel, cap, total, status, counter);
     B2S_LAUNCH_CHECK();
     return 0;
 }

@@ -257,10 +257,28 @@ def fully_fused_projection(
     if not packed:
         return radii, means2d, depths, conics, comps
     N = means.shape[0]
-    sel = (radii.reshape(-1) > 0).nonzero(as_tuple=True)[0]
+    sel = select_visible(radii)
     camera_ids, gaussian_ids = sel // N, sel % N
     return (camera_ids, gaussian_ids, radii.reshape(-1)[sel], means2d.reshape(-1, 2)[sel], depths.reshape(-1)[sel],
             conics.reshape(-1, 3)[sel], comps.reshape(-1)[sel] if comps is not None else None)
+
+
+@torch.no_grad()
+def select_visible(radii: Tensor, nnz: Optional[int] = None) -> Tensor:
+    """Indices (int64, ascending: camera-major, Gaussian-ascending) of the rows of dense ``radii`` with radius > 0 -- the
+    row order of gsplat's packed mode.  One single-pass scan kernel; ``nnz`` (when the caller already knows it) saves the
+    host sync that sizes the result."""
+    dev = L.require_cuda(radii)
+    radii = radii.contiguous()
+    M = radii.numel()
+    lib, st = L.lib(), L.stream_ptr(dev)
+    cap = M if nnz is None else int(nnz)
+    sel = torch.empty(cap, dtype=torch.int64, device=dev)
+    total = torch.empty(1, dtype=torch.int64, device=dev)
+    ws = torch.empty(int(lib.b2s_isect_scan_workspace_bytes(M)) + 16, dtype=torch.uint8, device=dev)
+    with _stage("select_visible"):
+        check(lib.b2s_select_visible(M, ptr(radii), ptr(sel), cap, ptr(total), ptr(ws), ws.numel(), st), "b2s_select_visible")
+    return sel[:int(total.item())] if nnz is None else sel
 
 
 class _PackVisible(torch.autograd.Function):
@@ -309,14 +327,25 @@ class _PackVisible(torch.autograd.Function):
 
 
 def pack_visible(radii: Tensor, means2d: Tensor, depths: Tensor, conics: Tensor, opacities: Tensor, colors: Tensor,
-                 tiles: Optional[Tensor] = None):
+                 tiles: Optional[Tensor] = None, sel: Optional[Tensor] = None):
     """Packed layout of the visible (camera, Gaussian) pairs of dense ``[C,N,..]`` tensors.
     Returns (camera_ids, gaussian_ids, radii, means2d, depths, conics, opacities, colors, tiles)."""
     N = radii.shape[1]
-    sel = (radii.reshape(-1) > 0).nonzero(as_tuple=True)[0]
+    if sel is None:
+        sel = select_visible(radii)
     m2, d, c, o, col, r, t, cam, gid = _PackVisible.apply(sel, N, means2d, depths, conics, opacities, colors,
                                                           radii.contiguous(), tiles.contiguous() if tiles is not None else None)
     return cam, gid, r, m2, d, c, o, col, t
+
+
+@torch.no_grad()
+def gather_rows2(x: Tensor, sel: Tensor) -> Tensor:
+    """``x.reshape(-1, 2)[sel]`` with the gather kernel of the packed layout (the gradient of ``meta["means2d"]``)."""
+    x = f32c(x)
+    out = torch.empty(sel.numel(), 2, device=x.device)
+    check(L.lib().b2s_pack_rows(sel.numel(), 1, ptr(sel), 0, ptr(x), None, None, None, None, None, None, ptr(out), None, None, None,
+                                None, None, None, None, None, L.stream_ptr(x.device)), "b2s_pack_rows")
+    return out
 
 
 # ======================================================================================
@@ -578,11 +607,11 @@ def coarse_bins_supported(n_cameras: int, tile_width: int, tile_height: int, cha
 
 class CoarseBins:
     """Depth-ordered rows binned into 8x8-tile coarse bins; the compositing kernels expand per-tile lists from it."""
-    __slots__ = ("recs", "ids", "offsets", "sorted_ids", "n_records", "n_isects")
+    __slots__ = ("recs", "ids", "offsets", "sorted_ids", "n_records", "n_isects", "n_visible")
 
-    def __init__(self, recs, ids, offsets, sorted_ids, n_records, n_isects):
+    def __init__(self, recs, ids, offsets, sorted_ids, n_records, n_isects, n_visible=None):
         self.recs, self.ids, self.offsets, self.sorted_ids = recs, ids, offsets, sorted_ids
-        self.n_records, self.n_isects = n_records, n_isects
+        self.n_records, self.n_isects, self.n_visible = n_records, n_isects, n_visible
 
 
 @torch.no_grad()
@@ -619,11 +648,12 @@ def bin_coarse(means2d: Tensor, radii: Tensor, depths: Tensor, tile_size: int, t
         check(lib.b2s_depth_order(M, ptr(depth_keys), ptr(row_ids), ptr(sorted_ids), ptr(ws), ws.numel(), st), "b2s_depth_order")
     # The one host sync of a forward (sizes the record buffers).  The depth sort is already enqueued, so the GPU
     # keeps working while the host waits for the counts that stage 1 produced.
+    n_visible = None
     if counts is not None:             # (n_isects, n_records) already on the host (the multi-GPU stripe table)
         n_isects, n_records = int(counts[0]), int(counts[1])
     elif totals is not None:
         sums = totals.sum(dim=0).tolist()
-        n_isects, n_records = int(sums[0]), int(sums[2])
+        n_isects, n_records, n_visible = int(sums[0]), int(sums[2]), int(sums[1])
     else:
         n_isects, n_records = None, int(tot.item())
     if n_records >= 2 ** 31:
@@ -638,7 +668,7 @@ def bin_coarse(means2d: Tensor, radii: Tensor, depths: Tensor, tile_size: int, t
         check(lib.b2s_coarse_bin(M, N, ptr(cam), n_records, ptr(sorted_ids), ptr(means2d), ptr(radii), C, tile_size, tile_width,
                                  tile_height, ptr(recs), ptr(ids), ptr(offsets), ptr(ws2), ws2.numel(), L.tile_rows(tile_rows),
                                  st), "b2s_coarse_bin")
-    return CoarseBins(recs, ids, offsets, sorted_ids, n_records, n_isects)
+    return CoarseBins(recs, ids, offsets, sorted_ids, n_records, n_isects, n_visible)
 
 
 # ======================================================================================

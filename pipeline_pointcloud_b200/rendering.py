@@ -132,18 +132,18 @@ def rasterization(
         if backgrounds is not None:
             backgrounds = torch.zeros_like(backgrounds[:, :1])
 
-    # ---- packed layout: compact the visible pairs (camera-major, Gaussian-ascending) ----------------------
+    # ---- packed layout ----------------------------------------------------------------------------------------
+    # The pipeline always runs on the dense [C,N] rows (the kernels address rows by index, so nothing is gained by
+    # compacting 92 % of them first); with packed=True the packed tensors of `meta` (camera_ids, gaussian_ids, radii,
+    # means2d, ...: the nnz visible pairs, camera-major / Gaussian-ascending) are produced on first access by one
+    # selection kernel and one gather kernel, see _packed_meta.
     camera_ids = gaussian_ids = None
-    if packed:
-        (camera_ids, gaussian_ids, radii_m, means2d_m, depths_m, conics_m, opac_m, cols_m,
-         tiles_m) = ops.pack_visible(radii, means2d, depths, conics, opac, cols, tiles)
-    else:
-        radii_m, means2d_m, depths_m, conics_m, opac_m, cols_m, tiles_m = radii, means2d, depths, conics, opac, cols, tiles
+    radii_m, means2d_m, depths_m, conics_m, opac_m, cols_m, tiles_m = radii, means2d, depths, conics, opac, cols, tiles
 
     # ---- stage 2: binning --------------------------------------------------------------------------------
     tiles_per_gauss = tiles_m
     ch = cols_m.shape[-1]
-    fused_keys = (not packed) and C <= ops.MAX_CAMS
+    fused_keys = C <= ops.MAX_CAMS
     if _use_coarse_bins() and ops.coarse_bins_supported(C, tw, th, ch):
         # two-level binning: coarse bins now, per-tile lists expanded inside the compositing kernels; the reference's
         # per-intersection lists (flatten_ids, isect_offsets, isect_ids) are built only if somebody reads them
@@ -170,14 +170,14 @@ def rasterization(
         for c0 in range(0, ch, channel_chunk):
             bg = backgrounds[..., c0:c0 + channel_chunk] if backgrounds is not None else None
             rc, ra = ops.rasterize_to_pixels(means2d_m, conics_m, cols_m[..., c0:c0 + channel_chunk], opac_m, width, height,
-                                             tile_size, isect_offsets, flatten_ids, backgrounds=bg, packed=packed,
+                                             tile_size, isect_offsets, flatten_ids, backgrounds=bg, packed=False,
                                              absgrad=absgrad, bins=bins, n_cameras=C)
             outs.append(rc)
         render_colors, render_alphas = torch.cat(outs, dim=-1), ra
     else:
         render_colors, render_alphas = ops.rasterize_to_pixels(
             means2d_m, conics_m, cols_m, opac_m, width, height, tile_size, isect_offsets, flatten_ids,
-            backgrounds=backgrounds, packed=packed, absgrad=absgrad, bins=bins, n_cameras=C)
+            backgrounds=backgrounds, packed=False, absgrad=absgrad, bins=bins, n_cameras=C)
     if render_mode in ("ED", "RGB+ED"):
         render_colors = torch.cat(
             [render_colors[..., :-1], render_colors[..., -1:] / render_alphas.clamp(min=1e-10)], dim=-1)
@@ -195,4 +195,51 @@ def rasterization(
     else:
         meta["flatten_ids"], meta["isect_offsets"] = flatten_ids, isect_offsets
         meta.set_lazy("isect_ids", make_isect_ids)     # 64-bit sorted keys, rebuilt on first access
+    if packed:
+        meta = _packed_meta(meta, N, C, cols_m, bins.n_visible if bins is not None else None)
     return render_colors, render_alphas, meta
+
+
+def _packed_meta(dense: "ops.LazyMeta", N: int, C: int, cols: Tensor, nnz: Optional[int]) -> "ops.LazyMeta":
+    """``meta`` of ``rasterization(packed=True)``: the per-pair tensors restricted to the nnz visible (camera, Gaussian)
+    pairs, camera-major / Gaussian-ascending, ``camera_ids`` / ``gaussian_ids`` int64 and ``flatten_ids`` re-based on the
+    packed rows -- built on first access from the dense rows the pipeline ran on (one selection kernel, one gather kernel;
+    the gather is differentiable).  ``meta["means2d"]`` receives ``.grad`` (and ``.absgrad``) after the backward, as the
+    densification strategies of the reference's trainer expect (``retain_grad()`` on it is honoured): a hook on the dense
+    tensor gathers its gradient into the packed one."""
+    cache = {}
+
+    def pk():
+        if not cache:
+            radii = dense["radii"]
+            sel = ops.select_visible(radii, nnz)
+            d_m2 = dense["means2d"]
+            cam, gid, r_p, m2_p, d_p, c_p, o_p, col_p, t_p = ops.pack_visible(radii, d_m2, dense["depths"], dense["conics"],
+                                                                               dense["opacities"], cols, dense["tiles_per_gauss"], sel=sel)
+            if d_m2.requires_grad:
+                def hook(g):
+                    m2_p.grad = ops.gather_rows2(g, sel)
+                    ab = getattr(d_m2, "absgrad", None)
+                    if ab is not None:
+                        m2_p.absgrad = ops.gather_rows2(ab, sel)
+                d_m2.register_hook(hook)
+            cache.update(sel=sel, camera_ids=cam, gaussian_ids=gid, radii=r_p, means2d=m2_p, depths=d_p, conics=c_p,
+                         opacities=o_p, tiles_per_gauss=t_p)
+        return cache
+
+    def flat():
+        sel = pk()["sel"]
+        inv = torch.full((C * N,), -1, dtype=torch.int32, device=sel.device)
+        inv[sel] = torch.arange(sel.numel(), dtype=torch.int32, device=sel.device)
+        return inv[dense["flatten_ids"].long()]
+
+    meta = ops.LazyMeta({k: dense[k] for k in ("tile_width", "tile_height", "width", "height", "tile_size", "n_cameras")})
+    for k in ("n_isects", "n_coarse_records"):
+        if k in dense:
+            meta[k] = dense[k]
+    for k in ("camera_ids", "gaussian_ids", "radii", "means2d", "depths", "conics", "opacities", "tiles_per_gauss"):
+        meta.set_lazy(k, (lambda kk: (lambda: pk()[kk]))(k))
+    meta.set_lazy("flatten_ids", flat)
+    meta.set_lazy("isect_offsets", lambda: dense["isect_offsets"])
+    meta.set_lazy("isect_ids", lambda: dense["isect_ids"])
+    return meta
