@@ -73,7 +73,8 @@ def workload_config(workload, packed, world, multi_gpu):
     s = (f"{workload}: {N} random Gaussians" + (" in gsplat's initial state (opacity 0.1, isotropic NN-distance scales)"
                                                  if init == "gsplat_init" else "") +
          f", SH deg {deg}, {W}x{H}, {mode}, " + ("forward only" if fwd_only else "fwd+bwd") +
-         f", packed={bool(packed or sharded)}, " + ("1 camera" if (world == 1 or stripes) else "1 camera per GPU"))
+         f", packed={bool(packed or sharded)}, " + ("1 camera" if (world == 1 or stripes) else
+                                                    "1 camera per GPU (views related by the cube's symmetries: equal work per GPU)"))
     if world > 1 and stripes:
         s += (", Gaussians sharded over ranks, every rank composites a stripe of tile rows of the one camera: fused pack + NVLink "
               "peer-store exchange of projected splats to the stripe owners, gradients returned by the reverse exchange")
@@ -195,6 +196,20 @@ def build_scene(workload, C_total, lo=None, hi=None, seed=0):
         scene = make_scene(N, deg, C_total, W, H, seed=seed)            # identical on every rank (CPU generator)
         for k in LEAVES:
             scene[k] = scene[k][lo:hi].contiguous()
+    if C_total > 1:
+        # Weak scaling must keep the per-GPU work fixed: the scene is a cube, so the views related by its symmetries (quarter
+        # turns about the vertical axis and the mirror image) cost the same, while the evenly spaced circle of make_cameras
+        # mixes face-on and diagonal views of different depth complexity.  Camera 0 is the camera of the single-GPU run.
+        from pipeline_pointcloud_b200.scene import look_at_viewmat
+        vm = []
+        for c in range(C_total):
+            if c < 8:
+                ang = (c // 2) * (math.pi / 2.0) + (0.3 if c % 2 == 0 else -0.3)
+            else:
+                ang = 2.0 * math.pi * c / C_total + 0.3
+            eye = torch.tensor([2.3 * 3.0 * math.cos(ang), 2.3 * 3.0 * math.sin(ang), 0.5 * 3.0])
+            vm.append(look_at_viewmat(eye, torch.zeros(3), torch.tensor([0.0, 0.0, 1.0])))
+        scene["viewmats"] = torch.stack(vm)
     if init == "gsplat_init":
         # gsplat's simple_trainer initial state on these positions: opacity 0.1, isotropic scale = RMS distance to the 3
         # nearest neighbours (uniform points of density rho: ~0.75 rho^(-1/3); a log-normal jitter stands in for its spread)

@@ -323,10 +323,13 @@ struct GatherArgs {
     int64_t* camera_ids; int64_t* gaussian_ids; int32_t* tiles; uint32_t* depth_keys; int32_t* row_ids;
 };
 
+template <int WPS>      // warps per slot: 8 when the slots are nearly full (camera owners), fewer when they are sparse (tile stripes)
 __global__ void __launch_bounds__(256) route_gather_kernel(const GatherArgs a) {
     __shared__ __align__(16) float s_rows[8][32 * RT_MAXF];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const long long item = blockIdx.x;                                // (source, camera, source CTA), flattened; warp w: rows [32 w, 32 w + 32)
+    // item = (source, camera, source CTA), flattened; 8 / WPS items per CTA; warp w of an item's group: rows [32 w, ..) step 32 WPS
+    const long long item = (long long)blockIdx.x * (8 / WPS) + warp / WPS;
+    if (item >= a.cta_base[a.world]) return;
     int src = 0;
     while (src + 1 < a.world && item >= a.cta_base[src + 1]) ++src;
     const long long n_ctas = (a.n_src[src] + FWD_THREADS - 1) / FWD_THREADS;
@@ -335,36 +338,38 @@ __global__ void __launch_bounds__(256) route_gather_kernel(const GatherArgs a) {
     const long long b = local - (long long)lc * n_ctas;
     const long long reg = (long long)src * a.region_cams + lc;
     const int count = a.cnt[(reg * a.n_ctas_cap + b) * 4];
-    const int t0 = warp * 32;
-    if (t0 >= count) return;
     const long long base = a.row_offset[src] + a.row_base[reg * a.n_ctas_cap + b];
     const int F = 10 + a.ch;
     const float* slot = a.rec + (reg * a.cap_rows + b * FWD_THREADS) * (long long)F;     // 16-byte aligned: 256 F floats per slot
     float* sm = s_rows[warp];
-    const int rows = min(32, count - t0);
-    const int n4 = (rows * F + 3) >> 2;                                 // (reads at most 3 floats past the chunk, inside the slot)
-    const float4* g4 = reinterpret_cast<const float4*>(slot + (long long)t0 * F);
-    for (int q = lane; q < n4; q += 32) reinterpret_cast<float4*>(sm)[q] = ldg_stream4(g4 + q);
-    __syncwarp();
-    if (lane >= rows) return;
-    const float* p = sm + lane * F;
-    const long long j = base + t0 + lane;
-    const float2 m = make_float2(p[0], p[1]);
-    const float depth = p[2];
-    a.means2d[j] = m;
-    a.depths[j] = depth;
-    a.conics[3 * j] = p[3]; a.conics[3 * j + 1] = p[4]; a.conics[3 * j + 2] = p[5];
-    a.opac[j] = p[6];
-    for (int k = 0; k < a.ch; ++k) a.colors[j * a.ch + k] = p[7 + k];
-    const int radius = __float_as_int(p[7 + a.ch]);
-    a.radii[j] = radius;
-    a.camera_ids[j] = (int64_t)__float_as_int(p[8 + a.ch]);
-    a.gaussian_ids[j] = a.gid_offset[src] + (int64_t)__float_as_int(p[9 + a.ch]);
-    int x0, y0, x1, y1;
-    tile_rect(m.x, m.y, radius, a.tile_size, a.tile_w, a.row_lo, a.row_hi, x0, y0, x1, y1);
-    a.tiles[j] = max(0, x1 - x0) * max(0, y1 - y0);
-    a.depth_keys[j] = radius > 0 ? __float_as_uint(depth) : 0xFFFFFFFFu;
-    a.row_ids[j] = (int32_t)j;
+    for (int t0 = (warp % WPS) * 32; t0 < count; t0 += 32 * WPS) {
+        const int rows = min(32, count - t0);
+        const int n4 = (rows * F + 3) >> 2;                             // (reads at most 3 floats past the chunk, inside the slot)
+        const float4* g4 = reinterpret_cast<const float4*>(slot + (long long)t0 * F);
+        for (int q = lane; q < n4; q += 32) reinterpret_cast<float4*>(sm)[q] = ldg_stream4(g4 + q);
+        __syncwarp();
+        if (lane < rows) {
+            const float* p = sm + lane * F;
+            const long long j = base + t0 + lane;
+            const float2 m = make_float2(p[0], p[1]);
+            const float depth = p[2];
+            a.means2d[j] = m;
+            a.depths[j] = depth;
+            a.conics[3 * j] = p[3]; a.conics[3 * j + 1] = p[4]; a.conics[3 * j + 2] = p[5];
+            a.opac[j] = p[6];
+            for (int k = 0; k < a.ch; ++k) a.colors[j * a.ch + k] = p[7 + k];
+            const int radius = __float_as_int(p[7 + a.ch]);
+            a.radii[j] = radius;
+            a.camera_ids[j] = (int64_t)__float_as_int(p[8 + a.ch]);
+            a.gaussian_ids[j] = a.gid_offset[src] + (int64_t)__float_as_int(p[9 + a.ch]);
+            int x0, y0, x1, y1;
+            tile_rect(m.x, m.y, radius, a.tile_size, a.tile_w, a.row_lo, a.row_hi, x0, y0, x1, y1);
+            a.tiles[j] = max(0, x1 - x0) * max(0, y1 - y0);
+            a.depth_keys[j] = radius > 0 ? __float_as_uint(depth) : 0xFFFFFFFFu;
+            a.row_ids[j] = (int32_t)j;
+        }
+        __syncwarp();
+    }
 }
 
 }  // namespace b2s
@@ -490,7 +495,12 @@ extern "C" int b2s_route_gather(int32_t world, int32_t region_cams, int64_t cap_
     g.radii = radii; g.camera_ids = camera_ids; g.gaussian_ids = gaussian_ids; g.tiles = tiles_per_gauss; g.depth_keys = depth_keys;
     g.row_ids = row_ids;
     if (items == 0) return 0;
-    route_gather_kernel<<<(unsigned)items, 256, 0, (cudaStream_t)stream>>>(g);
+    const long long avg = n_rows / items;                       // rows per occupied slot, on average
+    cudaStream_t st = (cudaStream_t)stream;
+    if (avg > 128) route_gather_kernel<8><<<(unsigned)items, 256, 0, st>>>(g);
+    else if (avg > 64) route_gather_kernel<4><<<(unsigned)cdiv(items, 2), 256, 0, st>>>(g);
+    else if (avg > 32) route_gather_kernel<2><<<(unsigned)cdiv(items, 4), 256, 0, st>>>(g);
+    else route_gather_kernel<1><<<(unsigned)cdiv(items, 8), 256, 0, st>>>(g);
     B2S_LAUNCH_CHECK();
     return 0;
 }
