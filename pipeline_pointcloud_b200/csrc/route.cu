@@ -346,7 +346,12 @@ __global__ void __launch_bounds__(256) route_gather_kernel(const GatherArgs a) {
         const int rows = min(32, count - t0);
         const int n4 = (rows * F + 3) >> 2;                             // (reads at most 3 floats past the chunk, inside the slot)
         const float4* g4 = reinterpret_cast<const float4*>(slot + (long long)t0 * F);
-        for (int q = lane; q < n4; q += 32) reinterpret_cast<float4*>(sm)[q] = ldg_stream4(g4 + q);
+        float4 v[4];                                                    // 32 rows x at most 14 words = at most 112 float4: four per lane,
+#pragma unroll                                                          // all in flight before the first shared-memory store
+        for (int i = 0; i < 4; ++i) v[i] = (lane + 32 * i < n4) ? ldg_stream4(g4 + lane + 32 * i) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+            if (lane + 32 * i < n4) reinterpret_cast<float4*>(sm)[lane + 32 * i] = v[i];
         __syncwarp();
         if (lane < rows) {
             const float* p = sm + lane * F;
