@@ -315,13 +315,17 @@ __global__ void __launch_bounds__(ST_THREADS) stripe_return_kernel(const ReturnA
     float g[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     bool nz = false;
     if (j < a.n) {
+        // every load is issued before the first test (one memory round trip per row, not two)
+        float c0 = 0.f, c1 = 0.f, c2 = 0.f;
+        if (a.g_colors && a.ch == 3) { c0 = a.g_colors[3 * j]; c1 = a.g_colors[3 * j + 1]; c2 = a.g_colors[3 * j + 2]; }
         if (a.g_means2d) { const float2 v = a.g_means2d[j]; g[0] = v.x; g[1] = v.y; }
         if (a.g_depths) g[2] = a.g_depths[j];
         if (a.g_conics) { g[3] = a.g_conics[3 * j]; g[4] = a.g_conics[3 * j + 1]; g[5] = a.g_conics[3 * j + 2]; }
         if (a.g_opac) g[6] = a.g_opac[j];
 #pragma unroll
         for (int k = 0; k < 7; ++k) nz |= g[k] != 0.f;
-        if (a.g_colors && !nz)
+        nz |= (c0 != 0.f) | (c1 != 0.f) | (c2 != 0.f);
+        if (a.g_colors && a.ch != 3 && !nz)
             for (int k = 0; k < a.ch; ++k) nz |= a.g_colors[j * a.ch + k] != 0.f;
     }
     int src = 0;
