@@ -49,7 +49,7 @@ WORKLOADS = {
 METRIC = "3DGS rasterization fwd+bwd throughput"
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture (profiles/), config 3
 NCU_TRAFFIC = {
-    "project_fwd": 1_628_177_000,   # profiles/r01_ncu_full_v14_summary.md: 1.314 GB read + 0.314 GB written
+    "project_fwd": 1_701_901_000,   # profiles/r02_ncu_full_summary.md (project_fwd_tma_kernel): 1.369 GB read + 0.333 GB written
 }
 UNIT = "Mpix/s"
 LEAVES = ("means", "quats", "scales", "opacities", "colors")
