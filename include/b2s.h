@@ -124,7 +124,11 @@ typedef struct {
      * A stages == 2 call must be given the workspace its stages == 1 call used. */
     void* workspace;
     int64_t workspace_bytes;
+    int32_t v_sh_prezeroed;  /* != 0: the caller already zero-filled v_sh_coeffs (e.g. on a second stream, under the forward's
+                                compositing kernel, which leaves HBM idle): the sparse mode skips its own zero fill */
 } b2s_project_bwd_args;
+/* Streaming zero fill of a device buffer (any alignment), for gradient buffers that are accumulated into. */
+B2S_API int b2s_zero_fill(void* p, int64_t bytes, b2s_stream_t stream);
 B2S_API int64_t b2s_project_bwd_workspace_bytes(int64_t N);
 B2S_API int b2s_project_bwd(const b2s_project_bwd_args* a, b2s_stream_t stream);
 /* Camera gradients of the same backward (gsplat's `v_viewmats`; only nerfstudio's optional camera optimizer asks for them):

@@ -81,6 +81,7 @@ class ProjectBwdArgs(Structure):
         ("v_means", c_void_p), ("v_quats", c_void_p), ("v_scales", c_void_p), ("v_opacities", c_void_p),
         ("v_sh_coeffs", c_void_p), ("stages", c_int32),
         ("workspace", c_void_p), ("workspace_bytes", c_int64),
+        ("v_sh_prezeroed", c_int32),
     ]
 
 
@@ -117,6 +118,7 @@ SYMBOLS = {
     "b2s_version": (c_int32, []),
     "b2s_last_error": (c_char_p, []),
     "b2s_project_fwd": (c_int32, [POINTER(ProjectFwdArgs), c_void_p]),
+    "b2s_zero_fill": (c_int32, [c_void_p, c_int64, c_void_p]),
     "b2s_project_bwd_workspace_bytes": (c_int64, [c_int64]),
     "b2s_project_bwd": (c_int32, [POINTER(ProjectBwdArgs), c_void_p]),
     "b2s_viewmat_bwd": (c_int32, [POINTER(ProjectBwdArgs), c_void_p, c_void_p]),

@@ -886,8 +886,10 @@ extern "C" int b2s_project_bwd(const b2s_project_bwd_args* a, b2s_stream_t strea
         kern<<<(unsigned)min((int64_t)148 * 4, cdiv(a->N, SHB_THREADS)), SHB_THREADS, smem, st>>>(*a, cnt);
         B2S_LAUNCH_CHECK();
         if (cnt) {
-            sh_zero_kernel<<<148 * 32, 256, 0, st>>>(*a, cnt);
-            B2S_LAUNCH_CHECK();
+            if (!a->v_sh_prezeroed) {
+                sh_zero_kernel<<<148 * 32, 256, 0, st>>>(*a, cnt);
+                B2S_LAUNCH_CHECK();
+            }
             const unsigned grid = (unsigned)min((int64_t)148 * 16, cdiv(cdiv(a->N, 4), 128));
             if (vec) sh_sparse_kernel<true><<<grid, 128, cam_bytes, st>>>(*a, cnt, list_sh);
             else sh_sparse_kernel<false><<<grid, 128, cam_bytes, st>>>(*a, cnt, list_sh);

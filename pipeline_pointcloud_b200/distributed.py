@@ -655,6 +655,9 @@ class _ProjectRoute(torch.autograd.Function):
                               None if with_sh else colors)
         ctx.cfg = cfg
         ctx.route = (rows_from, n_world, group, ch, n_color_in, state, cap)
+        ctx.v_sh_pre = None
+        if with_sh and ctx.needs_input_grad[4] and N > 0 and ops._prefill_enabled():
+            ctx.v_sh_pre = ops.prefill_zeros(colors.numel(), dev)     # the dense SH gradient, zero-filled under binning / compositing
         ctx.set_materialize_grads(False)
         ctx.mark_non_differentiable(radii_m, tiles_m, dkeys, rowids, cam_m, gid_m)
         _ProjectRoute.last_counts = (n_isects, n_records)
@@ -720,8 +723,9 @@ class _ProjectRoute(torch.autograd.Function):
                 v_colors_in = v_cols[..., :n_col].sum(dim=0)
         saved = (means, quats, scales, opacities, sh_coeffs, viewmats, Ks, None, radii)
         pcfg = (width, height, eps2d, near_plane, far_plane, radius_clip, bool(antialiased), sh_degree if with_sh else 0)
+        pre, ctx.v_sh_pre = ctx.v_sh_pre, None
         v_means, v_quats, v_scales, v_opac, v_sh = ops.project_backward(saved, pcfg, v_means2d, v_depths, v_conics, None, v_opac_out,
-                                                                         v_sh_in)
+                                                                         v_sh_in, v_sh_pre=pre)
         return v_means, v_quats, v_scales, v_opac, (v_sh if with_sh else v_colors_in), None, None, None, None
 
 

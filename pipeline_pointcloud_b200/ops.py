@@ -77,6 +77,40 @@ def _bit_length(v: int) -> int:
     return int(v).bit_length()
 
 
+# --------------------------------------------------------------------------------------
+# zero fills under the compositing kernels.  The backward accumulates into two large zero-filled buffers: the dense SH
+# gradient (12 K bytes per Gaussian: 1.1 GB at 5.8 M, 0.165 ms of pure HBM writes) and the slab of per-row gradients
+# that compositing adds into atomically.  Neither depends on anything the forward computes, and the forward's
+# compositing kernel is instruction-issue bound with HBM 96 % idle -- so they are filled on a second stream while it
+# runs, and the backward finds them ready (B2S_PREFILL=0: filled in the backward, as in round 1).
+# --------------------------------------------------------------------------------------
+_SIDE_STREAMS = {}
+
+
+def _prefill_enabled() -> bool:
+    return os.environ.get("B2S_PREFILL", "1") != "0"
+
+
+def prefill_zeros(numel: int, dev):
+    """(fp32 zeros[numel] being filled on the side stream, the event that marks the fill done).  The consumer's stream
+    must wait for the event."""
+    main = torch.cuda.current_stream(dev)
+    t = torch.empty(max(int(numel), 1), dtype=torch.float32, device=dev)       # allocated on the caller's stream
+    side = _SIDE_STREAMS.get(dev.index)
+    if side is None:
+        side = _SIDE_STREAMS[dev.index] = torch.cuda.Stream(dev)
+    ev0 = torch.cuda.Event()
+    ev0.record(main)
+    side.wait_event(ev0)                       # earlier users of this block (the caching allocator reuses memory) are done
+    check(L.lib().b2s_zero_fill(ptr(t), t.numel() * 4, side.cuda_stream), "b2s_zero_fill")
+    if TIMER is not None:
+        TIMER.launches += 1
+    ev1 = torch.cuda.Event()
+    ev1.record(side)
+    t.record_stream(side)                      # the block is not handed out again before the fill has run
+    return t, ev1
+
+
 # ======================================================================================
 # stage 1: fused projection (+SH colour, + tile count)
 # ======================================================================================
@@ -137,6 +171,9 @@ class _ProjectFused(torch.autograd.Function):
                 check(lib.b2s_project_fwd(ctypes.byref(a), st), "b2s_project_fwd")
         ctx.save_for_backward(means, quats, scales, opacities, sh_coeffs, viewmats, Ks, campos, radii)
         ctx.cfg = (width, height, eps2d, near_plane, far_plane, radius_clip, bool(antialiased), sh_degree)
+        ctx.v_sh_pre = None
+        if with_sh and ctx.needs_input_grad[4] and C <= MAX_CAMS and N > 0 and _prefill_enabled():
+            ctx.v_sh_pre = prefill_zeros(sh_coeffs.numel(), dev)       # the dense SH gradient, zero-filled under compositing
         ctx.set_materialize_grads(False)
         ctx.mark_non_differentiable(radii)
         if tiles is not None:
@@ -148,12 +185,13 @@ class _ProjectFused(torch.autograd.Function):
                  _v_rows=None, _v_total=None):
         # viewmats: gsplat's `v_viewmats` (nerfstudio's camera optimizer); Ks: no gradient, as upstream
         want_view = ctx.needs_input_grad[5]
+        pre, ctx.v_sh_pre = ctx.v_sh_pre, None          # (a second backward of the same graph gets a fresh buffer)
         grads = project_backward(ctx.saved_tensors, ctx.cfg, v_means2d, v_depths, v_conics, v_comps, v_opac_out, v_colors,
-                                 want_viewmats=want_view)
+                                 want_viewmats=want_view, v_sh_pre=pre)
         return tuple(grads[:5]) + ((grads[5] if want_view else None),) + (None,) * 12
 
 
-def project_backward(saved, cfg, v_means2d, v_depths, v_conics, v_comps, v_opac_out, v_colors, want_viewmats=False):
+def project_backward(saved, cfg, v_means2d, v_depths, v_conics, v_comps, v_opac_out, v_colors, want_viewmats=False, v_sh_pre=None):
     """VJP of stage 1 from dense ``[C,N,..]`` cotangents (any of them may be None): (v_means, v_quats, v_scales,
     v_opacities, v_sh_coeffs[, v_viewmats]).  Shared by ``_ProjectFused`` and the multi-GPU ``_ProjectRoute``."""
     means, quats, scales, opacities, sh_coeffs, viewmats, Ks, campos, radii = saved
@@ -167,10 +205,15 @@ def project_backward(saved, cfg, v_means2d, v_depths, v_conics, v_comps, v_opac_
     v_quats = torch.empty_like(quats)
     v_scales = torch.empty_like(scales)
     v_opac = torch.empty_like(opacities) if opacities is not None else None
-    v_sh = None
+    v_sh, prezeroed = None, 0
     if with_sh:
         K = (sh_degree + 1) ** 2
-        v_sh = torch.empty_like(sh_coeffs) if K == sh_coeffs.shape[1] else torch.zeros_like(sh_coeffs)
+        if v_sh_pre is not None:              # zero-filled on the side stream during the forward (prefill_zeros)
+            buf, ev = v_sh_pre
+            torch.cuda.current_stream(dev).wait_event(ev)
+            v_sh, prezeroed = buf[:sh_coeffs.numel()].view(sh_coeffs.shape), 1
+        else:
+            v_sh = torch.empty_like(sh_coeffs) if K == sh_coeffs.shape[1] else torch.zeros_like(sh_coeffs)
     if N == 0:
         return (v_means, v_quats, v_scales, v_opac, v_sh) + ((torch.zeros_like(viewmats),) if want_viewmats else ())
     lib = L.lib()
@@ -198,7 +241,8 @@ def project_backward(saved, cfg, v_means2d, v_depths, v_conics, v_comps, v_opac_
                 v_compensations=sl(v_comps, c0, c1), v_opacities_out=sl(v_opac_out, c0, c1),
                 v_colors=sl(v_colors, c0, c1), accumulate=int(c0 > 0),
                 v_means=ptr(v_means), v_quats=ptr(v_quats), v_scales=ptr(v_scales), v_opacities=ptr(v_opac),
-                v_sh_coeffs=ptr(v_sh), stages=stages, workspace=ptr(ws), workspace_bytes=ws.numel() if ws is not None else 0)
+                v_sh_coeffs=ptr(v_sh), stages=stages, workspace=ptr(ws), workspace_bytes=ws.numel() if ws is not None else 0,
+                v_sh_prezeroed=prezeroed)
 
         sparse = ws is not None and c0 == 0      # kernels launched: + classify, zero fill and the two list-driven ones
         if with_sh and TIMER is not None:     # time the stages of the call separately (bench.py)
@@ -725,6 +769,10 @@ class _RasterizeToPixels(torch.autograd.Function):
         ctx.save_for_backward(means2d, conics, colors, opacities, backgrounds, isect_offsets, flatten_ids, alphas,
                               last_ids, final_T, recs)
         ctx.cfg = (width, height, tile_size, absgrad, C, tw, th, n_list, row_lo, row_hi)
+        ctx.slab_pre = None
+        if any(ctx.needs_input_grad[:4]) and _prefill_enabled():
+            # the slab of atomically accumulated gradients, zero-filled on the side stream under this forward
+            ctx.slab_pre = prefill_zeros(opacities.numel() * (6 + ch + (2 if absgrad else 0)), dev)
         return render, alphas
 
     @staticmethod
@@ -739,7 +787,13 @@ class _RasterizeToPixels(torch.autograd.Function):
         # one zero-filled slab for every atomically accumulated gradient (one fill instead of four)
         M = opacities.numel()
         widths = [2, 3, ch, 1] + ([2] if absgrad else [])
-        slab = torch.zeros(M * sum(widths), dtype=torch.float32, device=dev)
+        if ctx.slab_pre is not None:
+            slab, ev = ctx.slab_pre
+            ctx.slab_pre = None                # (a second backward of the same graph gets a fresh slab)
+            torch.cuda.current_stream(dev).wait_event(ev)
+            slab = slab[:M * sum(widths)]
+        else:
+            slab = torch.zeros(M * sum(widths), dtype=torch.float32, device=dev)
         parts, o = [], 0
         for wd in widths:
             parts.append(slab[o:o + M * wd])
