@@ -173,8 +173,11 @@ __device__ __forceinline__ void stage_splat(int g, const float* __restrict__ mea
 // =================================================================================================
 // forward
 // =================================================================================================
+#ifndef B2S_COMP_MINBLOCKS
+#define B2S_COMP_MINBLOCKS 1
+#endif
 template <int CH, bool BINS>
-__global__ void __launch_bounds__(CTA) composite_fwd_kernel(const b2s_composite_fwd_args a, float* __restrict__ final_T) {
+__global__ void __launch_bounds__(CTA, B2S_COMP_MINBLOCKS) composite_fwd_kernel(const b2s_composite_fwd_args a, float* __restrict__ final_T) {
     __shared__ float4 s_rec0[CTA];
     __shared__ float4 s_rec1[CTA];
     __shared__ float4 s_box[CTA];
@@ -350,7 +353,7 @@ __device__ __forceinline__ int halving_slot(int lane, bool& owner) {
 // backward: replay back-to-front from the last contributor, multi-value warp reduce, one RED per warp
 // =================================================================================================
 template <int CH, bool ABS, bool BINS>
-__global__ void __launch_bounds__(CTA) composite_bwd_kernel(const b2s_composite_bwd_args a, const float* __restrict__ final_T) {
+__global__ void __launch_bounds__(CTA, B2S_COMP_MINBLOCKS) composite_bwd_kernel(const b2s_composite_bwd_args a, const float* __restrict__ final_T) {
     constexpr int V = CH + 6 + (ABS ? 2 : 0);   // values reduced per (warp, Gaussian)
     __shared__ float4 s_rec0[CTA];
     __shared__ float4 s_rec1[CTA];

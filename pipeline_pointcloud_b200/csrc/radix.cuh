@@ -101,8 +101,11 @@ template <> struct St<unsigned long long> {
     static constexpr unsigned long long MASK = (1ull << 62) - 1ull;
 };
 
+#ifndef B2S_RADIX_MINBLOCKS
+#define B2S_RADIX_MINBLOCKS 3
+#endif
 template <typename KeyT, typename StatusT>
-__global__ void __launch_bounds__(THREADS, 3) onesweep_kernel(unsigned n, const KeyT* __restrict__ keys_in,
+__global__ void __launch_bounds__(THREADS, B2S_RADIX_MINBLOCKS) onesweep_kernel(unsigned n, const KeyT* __restrict__ keys_in,
                                                               const int32_t* __restrict__ vals_in, KeyT* __restrict__ keys_out,
                                                               int32_t* __restrict__ vals_out, int shift, unsigned mask,
                                                               const unsigned long long* __restrict__ digit_base /* [256] */,

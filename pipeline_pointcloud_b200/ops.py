@@ -604,7 +604,7 @@ def bin_depth_first(means2d: Tensor, radii: Tensor, depths: Tensor, tiles_per_ga
             check(lib.b2s_depth_order(M, ptr(depth_keys), ptr(row_ids), ptr(sorted_ids), ptr(ws), ws.numel(), st), "b2s_depth_order")
     # The one host sync of a forward (sizes the per-intersection buffers).  The depth sort is already
     # enqueued, so the GPU keeps working while the host waits for the count that stage 1 produced.
-    n_isects = int(total_isects.reshape(-1, 4)[:, 0].sum().item()) if total_isects.numel() > 1 else int(total_isects.item())
+    n_isects = int(sum(r[0] for r in total_isects.reshape(-1, 4).tolist())) if total_isects.numel() > 1 else int(total_isects.item())
     if n_isects >= 2 ** 31:
         raise B2SError(f"n_isects = {n_isects} does not fit the int32 offsets of the API")
     key_bytes = int(lib.b2s_tile_key_bytes(C, tile_width, tile_height))
@@ -696,8 +696,8 @@ def bin_coarse(means2d: Tensor, radii: Tensor, depths: Tensor, tile_size: int, t
     if counts is not None:             # (n_isects, n_records) already on the host (the multi-GPU stripe table)
         n_isects, n_records = int(counts[0]), int(counts[1])
     elif totals is not None:
-        sums = totals.sum(dim=0).tolist()
-        n_isects, n_records, n_visible = int(sums[0]), int(sums[2]), int(sums[1])
+        slots = totals.tolist()                    # 32 counter rows, added up on the host (no reduction kernel)
+        n_isects, n_visible, n_records = (int(sum(r[k] for r in slots)) for k in (0, 1, 2))
     else:
         n_isects, n_records = None, int(tot.item())
     if n_records >= 2 ** 31:
