@@ -173,8 +173,11 @@ __device__ __forceinline__ void stage_splat(int g, const float* __restrict__ mea
 // =================================================================================================
 // forward
 // =================================================================================================
+// 5 resident CTAs per SM: ptxas then fits the kernels in 47 registers and schedules them measurably better than the
+// unconstrained 48-register build (composite_fwd 0.372 -> 0.351 ms, composite_bwd 0.734 -> 0.663 ms on the same box;
+// 6 CTAs / 40 registers: 0.358 / 0.706), profiles/r02_variants_c9.txt
 #ifndef B2S_COMP_MINBLOCKS
-#define B2S_COMP_MINBLOCKS 1
+#define B2S_COMP_MINBLOCKS 5
 #endif
 template <int CH, bool BINS>
 __global__ void __launch_bounds__(CTA, B2S_COMP_MINBLOCKS) composite_fwd_kernel(const b2s_composite_fwd_args a, float* __restrict__ final_T) {

@@ -657,7 +657,7 @@ class _ProjectRoute(torch.autograd.Function):
         ctx.route = (rows_from, n_world, group, ch, n_color_in, state, cap)
         ctx.v_sh_pre = None
         if with_sh and ctx.needs_input_grad[4] and N > 0 and ops._prefill_enabled():
-            ctx.v_sh_pre = ops.prefill_zeros(colors.numel(), dev)     # the dense SH gradient, zero-filled under binning / compositing
+            ctx.v_sh_pre = ops.prefill_zeros(colors.numel(), dev, defer=True)     # the dense SH gradient, zero-filled under compositing
         ctx.set_materialize_grads(False)
         ctx.mark_non_differentiable(radii_m, tiles_m, dkeys, rowids, cam_m, gid_m)
         _ProjectRoute.last_counts = (n_isects, n_records)

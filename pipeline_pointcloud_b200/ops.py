@@ -85,17 +85,16 @@ def _bit_length(v: int) -> int:
 # runs, and the backward finds them ready (B2S_PREFILL=0: filled in the backward, as in round 1).
 # --------------------------------------------------------------------------------------
 _SIDE_STREAMS = {}
+_PENDING_FILLS = []        # deferred fills: (tensor, holder), launched when the compositing kernel is about to be enqueued
 
 
 def _prefill_enabled() -> bool:
     return os.environ.get("B2S_PREFILL", "1") != "0"
 
 
-def prefill_zeros(numel: int, dev):
-    """(fp32 zeros[numel] being filled on the side stream, the event that marks the fill done).  The consumer's stream
-    must wait for the event."""
+def _launch_fill(t: Tensor, holder: dict) -> None:
+    dev = t.device
     main = torch.cuda.current_stream(dev)
-    t = torch.empty(max(int(numel), 1), dtype=torch.float32, device=dev)       # allocated on the caller's stream
     side = _SIDE_STREAMS.get(dev.index)
     if side is None:
         side = _SIDE_STREAMS[dev.index] = torch.cuda.Stream(dev)
@@ -108,7 +107,44 @@ def prefill_zeros(numel: int, dev):
     ev1 = torch.cuda.Event()
     ev1.record(side)
     t.record_stream(side)                      # the block is not handed out again before the fill has run
-    return t, ev1
+    holder["ev"] = ev1
+
+
+def prefill_zeros(numel: int, dev, defer: bool = False):
+    """fp32 zeros[numel] filled on the side stream: returns (tensor, holder); ``holder["ev"]`` is the event that marks the
+    fill done once it has been launched.  ``defer``: launch it with ``flush_prefills`` -- stage 1 creates its buffer
+    early but the fill must not run beside the depth sort (L2 resident: 1.3 GB of streaming writes next to it cost the
+    sort 0.15 ms, measured), only beside compositing."""
+    t = torch.empty(max(int(numel), 1), dtype=torch.float32, device=dev)       # allocated on the caller's stream
+    holder = {"ev": None}
+    if defer:
+        if len(_PENDING_FILLS) >= 8:           # forwards that never composited: do not hold on to their buffers
+            flush_prefills(dev)
+        _PENDING_FILLS.append((t, holder))
+    else:
+        _launch_fill(t, holder)
+    return t, holder
+
+
+def flush_prefills(dev) -> None:
+    keep = []
+    for t, holder in _PENDING_FILLS:
+        if t.device == dev:
+            _launch_fill(t, holder)
+        else:
+            keep.append((t, holder))
+    _PENDING_FILLS[:] = keep
+
+
+def take_prefilled(pre, numel: int, dev) -> Tensor:
+    """The zeros of a ``prefill_zeros`` pair, ready on the current stream (a fill that was never launched runs now)."""
+    t, holder = pre
+    if holder["ev"] is None:
+        _PENDING_FILLS[:] = [(x, h) for x, h in _PENDING_FILLS if h is not holder]
+        check(L.lib().b2s_zero_fill(ptr(t), t.numel() * 4, L.stream_ptr(dev)), "b2s_zero_fill")
+    else:
+        torch.cuda.current_stream(dev).wait_event(holder["ev"])
+    return t[:numel]
 
 
 # ======================================================================================
@@ -173,7 +209,7 @@ class _ProjectFused(torch.autograd.Function):
         ctx.cfg = (width, height, eps2d, near_plane, far_plane, radius_clip, bool(antialiased), sh_degree)
         ctx.v_sh_pre = None
         if with_sh and ctx.needs_input_grad[4] and C <= MAX_CAMS and N > 0 and _prefill_enabled():
-            ctx.v_sh_pre = prefill_zeros(sh_coeffs.numel(), dev)       # the dense SH gradient, zero-filled under compositing
+            ctx.v_sh_pre = prefill_zeros(sh_coeffs.numel(), dev, defer=True)   # the dense SH gradient, zero-filled under compositing
         ctx.set_materialize_grads(False)
         ctx.mark_non_differentiable(radii)
         if tiles is not None:
@@ -209,9 +245,7 @@ def project_backward(saved, cfg, v_means2d, v_depths, v_conics, v_comps, v_opac_
     if with_sh:
         K = (sh_degree + 1) ** 2
         if v_sh_pre is not None:              # zero-filled on the side stream during the forward (prefill_zeros)
-            buf, ev = v_sh_pre
-            torch.cuda.current_stream(dev).wait_event(ev)
-            v_sh, prezeroed = buf[:sh_coeffs.numel()].view(sh_coeffs.shape), 1
+            v_sh, prezeroed = take_prefilled(v_sh_pre, sh_coeffs.numel(), dev).view(sh_coeffs.shape), 1
         else:
             v_sh = torch.empty_like(sh_coeffs) if K == sh_coeffs.shape[1] else torch.zeros_like(sh_coeffs)
     if N == 0:
@@ -761,6 +795,12 @@ class _RasterizeToPixels(torch.autograd.Function):
             render_colors=ptr(render), render_alphas=ptr(alphas), last_ids=ptr(last_ids), final_T=ptr(final_T),
             bin_offsets=ptr(isect_offsets) if bins is not None else None, bin_recs=ptr(recs),
             bin_ids=ptr(flatten_ids) if bins is not None else None, tile_row_lo=row_lo, tile_row_hi=row_hi)
+        ctx.slab_pre = None
+        if _prefill_enabled():
+            flush_prefills(dev)                 # stage 1's deferred fill starts now, beside the compositing kernel
+            if any(ctx.needs_input_grad[:4]):
+                # the slab of atomically accumulated gradients, zero-filled on the side stream under this forward
+                ctx.slab_pre = prefill_zeros(opacities.numel() * (6 + ch + (2 if absgrad else 0)), dev)
         # an empty window (a rank whose stripe holds no tile row) launches nothing, forward or backward; (0, 0) would
         # read as "no window" in the C ABI, so it never gets there
         if row_hi > row_lo:
@@ -769,10 +809,6 @@ class _RasterizeToPixels(torch.autograd.Function):
         ctx.save_for_backward(means2d, conics, colors, opacities, backgrounds, isect_offsets, flatten_ids, alphas,
                               last_ids, final_T, recs)
         ctx.cfg = (width, height, tile_size, absgrad, C, tw, th, n_list, row_lo, row_hi)
-        ctx.slab_pre = None
-        if any(ctx.needs_input_grad[:4]) and _prefill_enabled():
-            # the slab of atomically accumulated gradients, zero-filled on the side stream under this forward
-            ctx.slab_pre = prefill_zeros(opacities.numel() * (6 + ch + (2 if absgrad else 0)), dev)
         return render, alphas
 
     @staticmethod
@@ -788,10 +824,8 @@ class _RasterizeToPixels(torch.autograd.Function):
         M = opacities.numel()
         widths = [2, 3, ch, 1] + ([2] if absgrad else [])
         if ctx.slab_pre is not None:
-            slab, ev = ctx.slab_pre
-            ctx.slab_pre = None                # (a second backward of the same graph gets a fresh slab)
-            torch.cuda.current_stream(dev).wait_event(ev)
-            slab = slab[:M * sum(widths)]
+            pre, ctx.slab_pre = ctx.slab_pre, None       # (a second backward of the same graph gets a fresh slab)
+            slab = take_prefilled(pre, M * sum(widths), dev)
         else:
             slab = torch.zeros(M * sum(widths), dtype=torch.float32, device=dev)
         parts, o = [], 0
