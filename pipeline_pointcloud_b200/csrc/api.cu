@@ -14,10 +14,20 @@ void set_error(const char* fmt, ...) {
 }  // namespace b2s
 
 namespace b2s {
-// streaming zero fill (128-bit stores that bypass L1): what a gradient buffer needs before sparse or atomic accumulation
-__global__ void __launch_bounds__(256) zero_fill_kernel(float4* __restrict__ p, int64_t n4) {
+// streaming zero fill (128-bit stores that bypass L1): what a gradient buffer needs before sparse or atomic accumulation.
+// Deliberately THIN -- two 128-thread CTAs per SM, eight independent stores per thread and iteration: stores do not wait,
+// so four warps per SM keep HBM's write side busy, and when the fill runs on a second stream beside an issue-bound kernel
+// (the compositing forward) it takes almost none of that kernel's residency (a 256-thread, 4736-CTA fill took as long out
+// of compositing as it saved: profiles/r02_variants_c9.txt).
+__global__ void __launch_bounds__(128) zero_fill_kernel(float4* __restrict__ p, int64_t n4) {
     const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) stg_stream4(p + i, z);
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    for (; i + 7 * stride < n4; i += 8 * stride) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) stg_stream4(p + i + k * stride, z);
+    }
+    for (; i < n4; i += stride) stg_stream4(p + i, z);
 }
 }  // namespace b2s
 
@@ -31,7 +41,7 @@ extern "C" int b2s_zero_fill(void* p, int64_t bytes, b2s_stream_t stream) {
     if (head) B2S_CUDA(cudaMemsetAsync(c, 0, (size_t)head, st));
     const int64_t n4 = (bytes - head) / 16, tail = bytes - head - n4 * 16;
     if (n4) {
-        b2s::zero_fill_kernel<<<(unsigned)b2s::cdiv(n4 < 148 * 32 * 256 ? n4 : 148 * 32 * 256, 256), 256, 0, st>>>(
+        b2s::zero_fill_kernel<<<(unsigned)(n4 < 148 * 2 * 128 ? b2s::cdiv(n4, 128) : 148 * 2), 128, 0, st>>>(
             reinterpret_cast<float4*>(c + head), n4);
         B2S_LAUNCH_CHECK();
     }
