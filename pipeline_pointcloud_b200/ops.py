@@ -78,18 +78,21 @@ def _bit_length(v: int) -> int:
 
 
 # --------------------------------------------------------------------------------------
-# zero fills under the compositing kernels.  The backward accumulates into two large zero-filled buffers: the dense SH
-# gradient (12 K bytes per Gaussian: 1.1 GB at 5.8 M, 0.165 ms of pure HBM writes) and the slab of per-row gradients
-# that compositing adds into atomically.  Neither depends on anything the forward computes, and the forward's
-# compositing kernel is instruction-issue bound with HBM 96 % idle -- so they are filled on a second stream while it
-# runs, and the backward finds them ready (B2S_PREFILL=0: filled in the backward, as in round 1).
+# zero fills on a second stream (OFF by default: a measured negative result, kept switchable with B2S_PREFILL=1).
+# The backward accumulates into two large zero-filled buffers: the dense SH gradient (12 K bytes per Gaussian: 1.1 GB at
+# 5.8 M, 0.17 ms of pure HBM writes) and the slab of per-row gradients compositing adds into atomically.  Neither
+# depends on the forward, and the forward's compositing kernel is issue bound with HBM 96 % idle, so filling them on a
+# second stream while it runs looked free.  It is not (profiles/r02_variants_c9.txt, gpurun_out r2c10/r2c11): beside the
+# L2-resident depth sort the fill costs the sort 0.15 ms; beside compositing -- even as a thin 2-CTA-per-SM kernel that
+# reaches 6.2 TB/s alone -- compositing slows by 0.14 ms (its gathers queue behind 6 TB/s of writes in L2) and the step
+# gets 0.16 ms LONGER (2.50 vs 2.34 ms).  The fills therefore stay where round 1 had them, in the backward.
 # --------------------------------------------------------------------------------------
 _SIDE_STREAMS = {}
 _PENDING_FILLS = []        # deferred fills: (tensor, holder), launched when the compositing kernel is about to be enqueued
 
 
 def _prefill_enabled() -> bool:
-    return os.environ.get("B2S_PREFILL", "1") != "0"
+    return os.environ.get("B2S_PREFILL", "0") == "1"
 
 
 def _launch_fill(t: Tensor, holder: dict) -> None:
