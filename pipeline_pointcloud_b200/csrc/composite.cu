@@ -179,9 +179,6 @@ __device__ __forceinline__ void stage_splat(int g, const float* __restrict__ mea
 #ifndef B2S_COMP_MINBLOCKS
 #define B2S_COMP_MINBLOCKS 5
 #endif
-#ifndef B2S_BWD_DIRECT_MAX
-#define B2S_BWD_DIRECT_MAX 0
-#endif
 template <int CH, bool BINS>
 __global__ void __launch_bounds__(CTA, B2S_COMP_MINBLOCKS) composite_fwd_kernel(const b2s_composite_fwd_args a, float* __restrict__ final_T) {
     __shared__ float4 s_rec0[CTA];
@@ -480,24 +477,8 @@ __global__ void __launch_bounds__(CTA, B2S_COMP_MINBLOCKS) composite_bwd_kernel(
         const float v_y = v_s2 * fmaf(k1 * r1.y, dx, k2 * r1.z * dy);
 
         const unsigned g = (unsigned)__float_as_int(r1.w);
-#if B2S_BWD_DIRECT_MAX > 0
-        // few contributing pixels (a small splat clipping the warp's 8x4 block): their lanes add straight into the
-        // gradients -- 9 predicated REDs -- instead of paying the 32-lane reduction for mostly-zero values
-        if (V == 9) {
-            const unsigned act = __ballot_sync(FULL, alpha > 0.f);
-            if (__popc(act) <= B2S_BWD_DIRECT_MAX) {
-                if (alpha > 0.f) {
-                    const uint64_t gg = g;
-                    atomicAdd(a.v_means2d + 2 * gg, v_x); atomicAdd(a.v_means2d + 2 * gg + 1, v_y);
-                    atomicAdd(a.v_conics + 3 * gg, v_ca); atomicAdd(a.v_conics + 3 * gg + 1, v_cb); atomicAdd(a.v_conics + 3 * gg + 2, v_cc);
-#pragma unroll
-                    for (int k = 0; k < CH; ++k) atomicAdd(a.v_colors + gg * CH + k, v_col[k]);
-                    atomicAdd(a.v_opacities + gg, v_op);
-                }
-                return;
-            }
-        }
-#endif
+        // (tried, round 2: letting the lanes of a pair with <= 2 / 4 / 8 contributing pixels add straight into the gradients
+        // instead of paying the 32-lane reduction -- 0.661 -> 0.678 / 0.672 / 0.666 ms: no gain, profiles/r02_variants_c9.txt)
         if (V <= 9) {
             float r8[8];
 #pragma unroll
