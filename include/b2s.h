@@ -24,6 +24,7 @@
  */
 #ifndef B2S_H
 #define B2S_H
+#include <stdbool.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -491,6 +492,25 @@ B2S_API int b2s_spz_pack(int64_t N, int32_t sh_dim, const float* means, const fl
                          const float* opacity_logits, const float* sh0, const float* shN, int32_t shN_rows,
                          uint8_t* positions, uint8_t* alphas, uint8_t* colors, uint8_t* scales, uint8_t* rotations,
                          uint8_t* sh, b2s_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * SPZ decoding: unpackGaussians() (load-spz.cc:373-440) fused with the row interleave of saveSplatToPly()
+ * (load-spz.cc:752-790).  Inputs are the codec's byte arrays as b2s_spz_pack writes them (24-bit positions only: the
+ * float16 layout of SPZ version 1 is rejected by the file-level call); output is the PLY vertex table
+ * [N, 17 + 3*sh_dim] fp32 in the reference's column order x y z nx ny nz f_dc_0..2 f_rest_* (channel-major) opacity
+ * scale_0..2 rot_0..3 (w first).  Bit-exact against the reference's converter.
+ *
+ * b2s_convert_spz_to_ply / ConvertSpzToPly: the reference's exported C entry point
+ * (spz/src/spz_converter_api.cpp:7-30, same name and signature) and the `.spz` branch of `splat_converter`
+ * (spz/src/main.cpp:29-35): HOST paths in, file out.  Reads + inflates on the host, decodes on the current device (the
+ * only entry of this library that allocates device memory and synchronises), writes the PLY.  A missing or malformed
+ * file returns an error (the reference returns false for a missing file and divides by zero on an empty cloud).
+ * ---------------------------------------------------------------------------------------------- */
+B2S_API int b2s_spz_unpack(int64_t N, int32_t sh_dim, int32_t fractional_bits, const uint8_t* positions, const uint8_t* alphas,
+                           const uint8_t* colors, const uint8_t* scales, const uint8_t* rotations, const uint8_t* sh,
+                           float* ply_rows, b2s_stream_t stream);
+B2S_API int b2s_convert_spz_to_ply(const char* host_spz_path, const char* host_ply_path);
+B2S_API bool ConvertSpzToPly(const char* spzFilePath, const char* plyFilePath);
 
 #ifdef __cplusplus
 }

@@ -115,3 +115,78 @@ def spz_payload_from_ply_columns(cols) -> bytes:
     pos, scales, rot, alphas, colors, sh = cloud_from_ply_columns(cols)
     packed = pack_gaussians(pos, scales, rot, alphas, colors, sh)
     return serialize(packed, pos.shape[0], degree_for_dim(sh.shape[1]))
+
+
+# ----------------------------------------------------------------------------------------------------------
+# the decode direction: loadSpz + saveSplatToPly (`splat_converter splat.spz`, spz/src/main.cpp:29-35; the exported C
+# entry point ConvertSpzToPly, spz/src/spz_converter_api.cpp:7-30)
+# ----------------------------------------------------------------------------------------------------------
+def _logf(x32: np.ndarray) -> np.ndarray:
+    """std::log on floats (load-spz.cc:86).  glibc's logf through ctypes when it is there (the reference binary links
+    it), else the float64 logarithm rounded once (which is what a correctly rounded logf returns)."""
+    try:
+        import ctypes
+        libm = ctypes.CDLL("libm.so.6")
+        libm.logf.restype, libm.logf.argtypes = ctypes.c_float, [ctypes.c_float]
+        with np.errstate(all="ignore"):
+            return np.array([libm.logf(float(v)) for v in x32.reshape(-1)], dtype=F).reshape(x32.shape)
+    except OSError:
+        with np.errstate(all="ignore"):
+            return np.log(x32.astype(np.float64)).astype(F)
+
+
+def alpha_table() -> np.ndarray:
+    """invSigmoid(alpha / 255.0f) for the 256 byte values (load-spz.cc:86, :428)."""
+    with np.errstate(all="ignore"):
+        x = (np.arange(256, dtype=F) / F(255.0)).astype(F)
+        return _logf((x / (F(1.0) - x)).astype(F))
+
+
+def deserialize(data: bytes):
+    """load-spz.cc:458-490 deserializePackedGaussians: header (:131-139), then positions, alphas, colors, scales, rotations, sh."""
+    magic, version, n, sh_degree, frac_bits, flags, _ = struct.unpack_from("<IIIBBBB", data, 0)
+    if magic != 0x5053474E or version not in (1, 2):
+        raise ValueError("not an SPZ payload")
+    if version != 2:
+        raise NotImplementedError("float16 positions (version 1) were never released")
+    sh_dim = {0: 0, 1: 3, 2: 8, 3: 15}[sh_degree]
+    o, out = 16, {}
+    for k, size in (("positions", 9 * n), ("alphas", n), ("colors", 3 * n), ("scales", 3 * n), ("rotations", 3 * n), ("sh", 3 * sh_dim * n)):
+        out[k] = np.frombuffer(data, dtype=np.uint8, count=size, offset=o)
+        o += size
+    return out, n, sh_degree, frac_bits, bool(flags & 1)
+
+
+def unpack_gaussians(packed, n: int, sh_dim: int, frac_bits: int = 12):
+    """load-spz.cc:373-440 unpackGaussians: fp32 positions [N,3], log-scales [N,3], rotations [N,4] as (x, y, z, w),
+    alpha logits [N], DC colours [N,3], sh [N, shDim, 3]; every step one IEEE-754 single operation."""
+    p = packed["positions"].reshape(-1, 3).astype(np.int32)
+    fixed = p[:, 0] | (p[:, 1] << 8) | (p[:, 2] << 16)
+    fixed = np.where(fixed & 0x800000, fixed | np.int32(-16777216), fixed).astype(np.int32)
+    positions = (fixed.astype(F) * F(1.0 / (1 << frac_bits))).astype(F).reshape(n, 3)
+    scales = (packed["scales"].astype(F) / F(16.0) - F(10.0)).astype(F).reshape(n, 3)
+    xyz = ((packed["rotations"].astype(F) * F(1.0 / 127.5)).astype(F) + F(-1.0)).astype(F).reshape(n, 3)
+    sq = ((xyz[:, 0] * xyz[:, 0] + xyz[:, 1] * xyz[:, 1]).astype(F) + xyz[:, 2] * xyz[:, 2]).astype(F)
+    w = np.sqrt(np.maximum(F(0.0), (F(1.0) - sq).astype(F)).astype(np.float64)).astype(F)
+    rotations = np.concatenate([xyz, w[:, None]], axis=1).astype(F)
+    alphas = alpha_table()[packed["alphas"]]
+    colors = (((packed["colors"].astype(F) / F(255.0)).astype(F) - F(0.5)).astype(F) / COLOR_SCALE).astype(F).reshape(n, 3)
+    sh = ((packed["sh"].astype(F) - F(128.0)) / F(128.0)).astype(F).reshape(n, sh_dim, 3)
+    return positions, scales, rotations, alphas, colors, sh
+
+
+def ply_bytes_from_cloud(positions, scales, rotations_xyzw, alphas, colors, sh) -> bytes:
+    """load-spz.cc:752-838 saveSplatToPly: x y z nx ny nz f_dc_0..2 f_rest_* (channel-major) opacity scale_0..2 rot_0..3 (w first)."""
+    n, sh_dim = positions.shape[0], sh.shape[1]
+    cols = [positions, np.zeros((n, 3), F), colors] + [sh[:, :, c] for c in range(3)] + \
+           [alphas[:, None], scales, rotations_xyzw[:, 3:4], rotations_xyzw[:, :3]]
+    table = np.concatenate([c.reshape(n, -1) for c in cols], axis=1).astype("<f4")
+    names = ["x", "y", "z", "nx", "ny", "nz", "f_dc_0", "f_dc_1", "f_dc_2"] + [f"f_rest_{i}" for i in range(3 * sh_dim)] + \
+            ["opacity", "scale_0", "scale_1", "scale_2", "rot_0", "rot_1", "rot_2", "rot_3"]
+    head = "ply\nformat binary_little_endian 1.0\n" + f"element vertex {n}\n" + "".join(f"property float {k}\n" for k in names) + "end_header\n"
+    return head.encode("ascii") + table.tobytes()
+
+
+def ply_bytes_from_spz(blob: bytes) -> bytes:
+    packed, n, sh_degree, frac_bits, _aa = deserialize(gunzip_bytes(blob))
+    return ply_bytes_from_cloud(*unpack_gaussians(packed, n, {0: 0, 1: 3, 2: 8, 3: 15}[sh_degree], frac_bits))

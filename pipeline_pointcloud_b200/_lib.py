@@ -179,6 +179,8 @@ SYMBOLS = {
     "b2s_adam_step": (c_int32, [c_int64, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_float, c_float,
                                 c_float, c_int64, c_void_p]),
     "b2s_spz_pack": (c_int32, [c_int64, c_int32] + [c_void_p] * 6 + [c_int32] + [c_void_p] * 6 + [c_void_p]),
+    "b2s_spz_unpack": (c_int32, [c_int64, c_int32, c_int32] + [c_void_p] * 7 + [c_void_p]),
+    "b2s_convert_spz_to_ply": (c_int32, [ctypes.c_char_p, ctypes.c_char_p]),
     "b2s_composite_fwd": (c_int32, [POINTER(CompositeFwdArgs), c_void_p]),
     "b2s_composite_bwd": (c_int32, [POINTER(CompositeBwdArgs), c_void_p]),
 }

@@ -151,13 +151,52 @@ def convert_ply_to_spz(ply_path: str) -> str:
     return out
 
 
+def ply_table_from_spz_payload(data: bytes, device="cuda") -> torch.Tensor:
+    """Header + packed arrays (``spz_payload``'s bytes) -> the PLY vertex table [N, 17 + 3*shDim] fp32 on the GPU
+    (csrc/spz.cu ``spz_unpack_kernel`` = unpackGaussians + the row interleave of saveSplatToPly, load-spz.cc:373-440,
+    752-790)."""
+    import struct
+    from . import _lib as L
+    if len(data) < 16:
+        raise ValueError("not an SPZ payload")
+    magic, version, n, sh_degree, frac_bits, _flags, _ = struct.unpack_from("<IIIBBBB", data, 0)
+    if magic != 0x5053474E or version != 2 or sh_degree > 3 or n > 10_000_000:
+        raise ValueError("not an SPZ version-2 payload the reference's loader accepts (load-spz.cc:463-478)")
+    sh_dim = (0, 3, 8, 15)[sh_degree]
+    sizes = [9 * n, n, 3 * n, 3 * n, 3 * n, 3 * sh_dim * n]                              # positions alphas colors scales rotations sh
+    if len(data) - 16 < sum(sizes):
+        raise ValueError("SPZ payload shorter than its header says")
+    buf = torch.frombuffer(bytearray(data[16:16 + sum(sizes)]), dtype=torch.uint8).to(device)
+    dev = L.require_cuda(buf)
+    parts, o = [], 0
+    for m in sizes:
+        parts.append(buf[o:o + m])
+        o += m
+    rows = torch.empty(n, 17 + 3 * sh_dim, dtype=torch.float32, device=dev)
+    L.check(L.lib().b2s_spz_unpack(n, sh_dim, frac_bits, *[L.ptr(x) if x.numel() else None for x in parts], L.ptr(rows),
+                                   L.stream_ptr(dev)), "b2s_spz_unpack")
+    return rows
+
+
+def convert_spz_to_ply(spz_path: str, ply_path: str = None) -> str:
+    """`splat_converter splat.spz` / the exported ``ConvertSpzToPly`` (spz/src/main.cpp:29-35, spz_converter_api.cpp:7-30):
+    the library's native file-level entry point (host inflate + GPU decode + PLY write, csrc/spz_file.cu)."""
+    from . import _lib as L
+    out = ply_path or os.path.splitext(spz_path)[0] + ".ply"
+    L.check(L.lib().b2s_convert_spz_to_ply(os.fsencode(spz_path), os.fsencode(out)), "b2s_convert_spz_to_ply")
+    return out
+
+
 def main(argv=None) -> int:
     argv = list(sys.argv[1:] if argv is None else argv)
     if len(argv) == 1 and argv[0].endswith(".ply"):          # the Spz-Export component's command line
         print(f"Converted {argv[0]} to {convert_ply_to_spz(argv[0])}")
         return 0
+    if len(argv) == 1 and argv[0].endswith(".spz"):          # the converter's other direction (spz/src/main.cpp:29-35)
+        print(f"Converted {argv[0]} to {convert_spz_to_ply(argv[0])}")
+        return 0
     if len(argv) != 2:
-        print("usage: python -m pipeline_pointcloud_b200.export CKPT_DIR OUTPUT.ply | INPUT.ply", file=sys.stderr)
+        print("usage: python -m pipeline_pointcloud_b200.export CKPT_DIR OUTPUT.ply | INPUT.ply | INPUT.spz", file=sys.stderr)
         return 2
     n = export_ply(argv[0], argv[1])
     print(f"wrote {n} Gaussians to {argv[1]}")

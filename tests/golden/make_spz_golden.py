@@ -1,6 +1,6 @@
-"""Generates tests/golden/splat_small.ply and tests/golden/splat_small.spz: the .spz is written by the REFERENCE's own
+"""Generates tests/golden/splat_small.ply, tests/golden/splat_small.spz and tests/golden/splat_small_decoded.ply: the .spz is written by the REFERENCE's own
 converter (oracle/_ref/splat_converter, compiled by oracle/Makefile from
-/root/reference/source/container/src/pipeline/post_processing/spz/src) from the committed .ply.
+/root/reference/source/container/src/pipeline/post_processing/spz/src) from the committed .ply, and the decoded .ply by the same binary from that .spz.
 Run in the build container:  make -C oracle && python tests/golden/make_spz_golden.py"""
 import os
 import subprocess
@@ -39,3 +39,10 @@ if __name__ == "__main__":
     conv = os.path.join(ROOT, "oracle", "_ref", "splat_converter")
     subprocess.run([conv, ply], check=True)
     print(os.path.getsize(ply), os.path.getsize(os.path.join(HERE, "splat_small.spz")))
+    # the decode direction: the reference binary turns its own .spz back into a .ply (spz/src/main.cpp:29-35)
+    import shutil
+    import tempfile
+    with tempfile.TemporaryDirectory() as d:
+        shutil.copy(os.path.join(HERE, "splat_small.spz"), os.path.join(d, "a.spz"))
+        subprocess.run([conv, os.path.join(d, "a.spz")], check=True)
+        shutil.copy(os.path.join(d, "a.ply"), os.path.join(HERE, "splat_small_decoded.ply"))

@@ -50,3 +50,44 @@ def test_cuda_converter_matches_compiled_reference(tmp_path):
     subprocess.run([REF_BIN, ply], check=True, stdout=subprocess.DEVNULL)
     ref = open(str(tmp_path / "splat.spz"), "rb").read()
     assert mine == ref
+
+
+# ---- the decode direction (csrc/spz.cu spz_unpack_kernel, csrc/spz_file.cu ConvertSpzToPly) ----
+from tests.test_spz_cpu import oracle_ply_from_spz
+
+
+def test_cuda_decoder_matches_reference_golden_ply(tmp_path):
+    """The native file-level entry point on the golden pair the reference binary wrote (spz -> ply), whole file."""
+    out = str(tmp_path / "x.ply")
+    assert export.convert_spz_to_ply(os.path.join(HERE, "golden", "splat_small.spz"), out) == out
+    assert open(out, "rb").read() == open(os.path.join(HERE, "golden", "splat_small_decoded.ply"), "rb").read()
+
+
+@pytest.mark.parametrize("rows,n", [(0, 1000), (3, 70001), (8, 4097), (15, 300000)])
+def test_cuda_decoder_matches_oracle(rows, n):
+    sp = random_splats(n, rows, seed=20 + rows)
+    sp["opacities"][:256] = torch.linspace(-12, 12, 256)
+    sp["means"][:50] *= 100.0
+    payload = export.spz_payload({k: v.cuda() for k, v in sp.items()})
+    table = export.ply_table_from_spz_payload(payload).cpu().numpy()
+    ref = oracle_ply_from_spz(S.gzip_bytes(payload))
+    body = np.frombuffer(ref[ref.index(b"end_header\n") + 11:], dtype="<u4").reshape(n, -1)
+    assert table.shape == body.shape and int((table.view(np.uint32) != body).sum()) == 0     # bit patterns: +-inf logits too
+
+
+@pytest.mark.skipif(not os.path.exists(REF_BIN), reason="compiled reference (oracle/_ref/splat_converter) not built")
+def test_cuda_spz_to_ply_matches_compiled_reference(tmp_path):
+    import ctypes
+    from pipeline_pointcloud_b200 import _lib
+    sp = random_splats(200000, 15, seed=77)
+    spz = str(tmp_path / "splat.spz")
+    export.write_spz(spz, {k: v.cuda() for k, v in sp.items()})
+    assert export.main([spz]) == 0                                # `splat_converter splat.spz` -> splat.ply, on the GPU
+    mine = open(str(tmp_path / "splat.ply"), "rb").read()
+    subprocess.run([REF_BIN, spz], check=True, stdout=subprocess.DEVNULL)
+    assert mine == open(str(tmp_path / "splat.ply"), "rb").read()
+    fn = _lib.lib().ConvertSpzToPly                               # the reference's exported name (spz_converter_api.cpp:7)
+    fn.restype, fn.argtypes = ctypes.c_bool, [ctypes.c_char_p, ctypes.c_char_p]
+    assert fn(spz.encode(), str(tmp_path / "again.ply").encode()) is True
+    assert open(str(tmp_path / "again.ply"), "rb").read() == mine
+    assert fn(str(tmp_path / "missing.spz").encode(), str(tmp_path / "no.ply").encode()) is False

@@ -60,3 +60,62 @@ def test_oracle_matches_compiled_reference(tmp_path, rows):
     mine = S.spz_payload_from_ply_columns(export.read_ply(ply))
     assert mine == S.gunzip_bytes(ref)
     assert S.gzip_bytes(mine) == ref
+
+
+# ---- the decode direction: loadSpz + saveSplatToPly (spz/src/main.cpp:29-35, ConvertSpzToPly) ----
+def oracle_ply_from_spz(blob: bytes) -> bytes:
+    packed, n, deg, frac_bits, _ = S.deserialize(S.gunzip_bytes(blob))
+    return S.ply_bytes_from_cloud(*S.unpack_gaussians(packed, n, {0: 0, 1: 3, 2: 8, 3: 15}[deg], frac_bits))
+
+
+def test_alpha_logit_table_is_the_rounded_fp64_logarithm():
+    """std::log (glibc logf) on the 256 possible alpha bytes = log in fp64 rounded once: the CUDA decoder computes the latter."""
+    t = S.alpha_table()
+    x = (np.arange(256, dtype=np.float32) / np.float32(255.0)).astype(np.float32)
+    with np.errstate(all="ignore"):
+        t64 = np.log((x / (np.float32(1.0) - x)).astype(np.float32).astype(np.float64)).astype(np.float32)
+    assert np.array_equal(t.view(np.uint32), t64.view(np.uint32))
+    assert t[0] == -np.inf and t[255] == np.inf and t[128] > 0 > t[127]
+
+
+def test_decode_rules():
+    f = np.float32
+    packed = {"positions": np.array([0x00, 0x10, 0x00, 0x00, 0xF0, 0xFF, 0xFF, 0xFF, 0x7F], np.uint8), "alphas": np.array([128], np.uint8),
+              "colors": np.array([0, 128, 255], np.uint8), "scales": np.array([0, 160, 255], np.uint8),
+              "rotations": np.array([128, 128, 128], np.uint8), "sh": np.zeros(0, np.uint8)}
+    pos, sc, rot, al, col, sh = S.unpack_gaussians(packed, 1, 0)
+    assert pos.tolist() == [[1.0, -1.0, float(f(0x7FFFFF) / f(4096))]]
+    assert sc.tolist() == [[-10.0, 0.0, float(f(255) / f(16) - f(10))]]
+    assert col[0, 0] == f(f(-0.5) / f(0.15)) and col[0, 2] == f(f(0.5) / f(0.15))
+    assert abs(rot[0, 0] - 0.5 / 127.5) < 1e-6 and rot[0, 3] <= 1.0 and sh.shape == (1, 0, 3)
+    assert abs(float(al[0]) - float(np.log((128 / 255) / (127 / 255)))) < 1e-6
+
+
+@pytest.mark.skipif(not os.path.exists(REF_BIN), reason="compiled reference (oracle/_ref/splat_converter) not built")
+def test_decode_oracle_matches_reference_on_its_golden_file(tmp_path):
+    spz = str(tmp_path / "a.spz")
+    blob = open(os.path.join(HERE, "golden", "splat_small.spz"), "rb").read()
+    open(spz, "wb").write(blob)
+    subprocess.run([REF_BIN, spz], check=True, stdout=subprocess.DEVNULL)
+    assert oracle_ply_from_spz(blob) == open(str(tmp_path / "a.ply"), "rb").read()
+
+
+def test_decode_oracle_matches_committed_golden_ply():
+    """tests/golden/splat_small_decoded.ply was written by the reference binary from splat_small.spz (make_spz_golden.py)."""
+    blob = open(os.path.join(HERE, "golden", "splat_small.spz"), "rb").read()
+    assert oracle_ply_from_spz(blob) == open(os.path.join(HERE, "golden", "splat_small_decoded.ply"), "rb").read()
+
+
+@pytest.mark.skipif(not os.path.exists(REF_BIN), reason="compiled reference (oracle/_ref/splat_converter) not built")
+@pytest.mark.parametrize("rows", [0, 3, 8, 15])
+def test_decode_oracle_matches_compiled_reference(tmp_path, rows):
+    """Every byte value of every field occurs: 20 000 random Gaussians with wide ranges, through the reference both ways."""
+    sp = random_splats(20000, rows, seed=rows + 11)
+    sp["opacities"][:256] = torch.linspace(-12, 12, 256)             # alpha bytes 0 and 255 (infinite logits) included
+    ply = str(tmp_path / "splat.ply")
+    export.write_ply(ply, export.ply_channels(sp))
+    subprocess.run([REF_BIN, ply], check=True, stdout=subprocess.DEVNULL)
+    blob = open(str(tmp_path / "splat.spz"), "rb").read()
+    os.rename(ply, str(tmp_path / "orig.ply"))
+    subprocess.run([REF_BIN, str(tmp_path / "splat.spz")], check=True, stdout=subprocess.DEVNULL)
+    assert oracle_ply_from_spz(blob) == open(ply, "rb").read()
