@@ -245,6 +245,28 @@ B2S_API int b2s_coarse_bin(int64_t M, int64_t N, const int64_t* camera_ids /* or
                            int32_t* bin_offsets, void* workspace, int64_t workspace_bytes, const b2s_tile_rows* rows,
                            b2s_stream_t stream);
 
+/* The same binning with two fusions (what `rasterization()` runs; the pair above is kept as the unfused reference and for
+ * A/B, B2S_BINNING_FUSED=0):
+ *   b2s_depth_order_rects : b2s_depth_order whose LAST radix pass, knowing every row's final position, gathers the row's
+ *                           means2d / radius and stores its tile rectangle there, in depth order: rect_xs [M] =
+ *                           x0 | x1 << 16, rect_ys [M] = y0 | y1 << 16 (tile units, rows clipped to the window; 0 on
+ *                           culled rows).  Needs nothing the host has to wait for, so it too is enqueued before the
+ *                           host reads the record count.  tile_w, tile_h < 65536.
+ *   b2s_coarse_bin_rects  : one kernel streams the rectangles, scans the record counts (decoupled look-back), writes the
+ *                           records and counts the digits of the bin sort on the way; one radix pass (two above 256
+ *                           bins) sorts them; with one pass the scanned digit histogram is the offset table.
+ * Outputs are bit-identical to b2s_depth_order + b2s_coarse_bin. */
+B2S_API int64_t b2s_depth_order_rects_workspace_bytes(int64_t M);
+B2S_API int b2s_depth_order_rects(int64_t M, const uint32_t* depth_keys, const int32_t* row_ids, const float* means2d,
+                                  const int32_t* radii, int32_t tile_size, int32_t tile_w, int32_t tile_h,
+                                  const b2s_tile_rows* rows, int32_t* sorted_ids, uint32_t* rect_xs, uint32_t* rect_ys,
+                                  void* workspace, int64_t workspace_bytes, b2s_stream_t stream);
+B2S_API int64_t b2s_coarse_bin_rects_workspace_bytes(int64_t M, int64_t n_records);
+B2S_API int b2s_coarse_bin_rects(int64_t M, int64_t N, const int64_t* camera_ids /* or NULL */, int64_t n_records,
+                                 const int32_t* sorted_ids, const uint32_t* rect_xs, const uint32_t* rect_ys, int32_t C,
+                                 int32_t tile_w, int32_t tile_h, uint32_t* bin_recs, int32_t* bin_ids, int32_t* bin_offsets,
+                                 void* workspace, int64_t workspace_bytes, b2s_stream_t stream);
+
 /* Packed layout (gsplat `packed=True`): gather the visible rows `sel` (ascending dense indices c*N+n) of the
  * stage-1 outputs into nnz-row tensors (+ camera_ids / gaussian_ids), and scatter gradients back into
  * zero-filled dense tensors.  Any output pointer may be NULL (skipped). */

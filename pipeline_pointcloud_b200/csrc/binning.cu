@@ -607,6 +607,154 @@ __global__ void __launch_bounds__(EXP_THREADS) coarse_emit_kernel(int64_t M, int
     }
 }
 
+// ---- fused path (b2s_depth_order_rects + b2s_coarse_bin_rects) ------------------------------------------------------
+// The last pass of the depth sort knows every row's final position, so it gathers the row's geometry and stores the tile
+// rectangle there (RectEpilogue): coarse_rects_kernel -- a pass of dependent gathers at 30 % issue rate -- disappears, and
+// the sorted depth keys, which nobody reads, are never written.
+struct RectEpilogue {
+    const float2* means2d;
+    const int32_t* radii;
+    float tile_size;
+    int tile_w, row_lo, row_hi;
+    int32_t* sorted_ids;
+    uint32_t *xs, *ys;
+    __device__ __forceinline__ void operator()(bool active, unsigned pos, uint32_t /*key*/, int32_t id) const {
+        if (!active) return;
+        const int r = __ldg(radii + id);
+        const float2 m = __ldg(means2d + id);
+        int x0 = 0, y0 = 0, x1 = 0, y1 = 0;
+        if (r > 0) {
+            tile_rect(m.x, m.y, r, tile_size, tile_w, row_lo, row_hi, x0, y0, x1, y1);
+            if (!(x1 > x0 && y1 > y0)) x0 = x1 = y0 = y1 = 0;
+        }
+        sorted_ids[pos] = id;
+        xs[pos] = (uint32_t)x0 | ((uint32_t)x1 << 16);
+        ys[pos] = (uint32_t)y0 | ((uint32_t)y1 << 16);
+    }
+};
+
+// Expansion of the depth-ordered rectangles into coarse-bin records, one kernel: every CTA streams the rectangles of
+// EMIT_ROWS rows (coalesced -- no gather in front of the scan any more, so a CTA publishes its record count a few hundred
+// cycles after it starts and the decoupled look-back never waits for long), and counts the digits of the bin sort on the
+// way (shared-memory histogram, flushed once per CTA), which replaces the sort's own histogram pass over the records.
+constexpr int EMIT_GROUPS = 4;                               // 32-row groups per warp
+constexpr int EMIT_ROWS = EXP_THREADS * EMIT_GROUPS;         // rows per CTA
+
+__global__ void __launch_bounds__(EXP_THREADS) coarse_emit_lb_kernel(int64_t M, int64_t N, const int64_t* __restrict__ camera_ids,
+                                                                     const int32_t* __restrict__ sorted_ids,
+                                                                     const uint32_t* __restrict__ xs, const uint32_t* __restrict__ ys,
+                                                                     int bins_w, int bins_h, unsigned long long* status,
+                                                                     unsigned int* cta_counter, const radix::Plan pl,
+                                                                     unsigned long long* __restrict__ hist,
+                                                                     uint32_t* __restrict__ recs, int32_t* __restrict__ vals) {
+    __shared__ int s_start[EXP_THREADS];
+    __shared__ int s_id[EXP_THREADS];
+    __shared__ uint32_t s_xs[EXP_THREADS], s_ys[EXP_THREADS];
+    __shared__ uint32_t s_cam[EXP_THREADS];
+    __shared__ unsigned int s_cta;
+    __shared__ int s_warp_tot[EXP_THREADS / 32];
+    __shared__ unsigned long long s_prefix;
+    __shared__ unsigned s_hist[2 * radix::RADIX];
+    if (threadIdx.x == 0) s_cta = atomicAdd(cta_counter, 1u);
+    for (int i = threadIdx.x; i < 2 * radix::RADIX; i += EXP_THREADS) s_hist[i] = 0u;
+    __syncthreads();
+    const unsigned int cta = s_cta;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wbase = threadIdx.x & ~31;
+    const int64_t row0 = (int64_t)cta * EMIT_ROWS + (int64_t)warp * (32 * EMIT_GROUPS) + lane;
+    uint32_t px[EMIT_GROUPS], py[EMIT_GROUPS];
+    int id[EMIT_GROUPS], excl[EMIT_GROUPS], tot[EMIT_GROUPS];
+#pragma unroll
+    for (int g = 0; g < EMIT_GROUPS; ++g) {
+        const int64_t j = row0 + g * 32;
+        px[g] = 0u; py[g] = 0u; id[g] = 0;
+        if (j < M) {
+            px[g] = xs[j];
+            py[g] = ys[j];
+            id[g] = sorted_ids[j];
+        }
+    }
+    int warp_total = 0;
+#pragma unroll
+    for (int g = 0; g < EMIT_GROUPS; ++g) {
+        const int x0 = (int)(px[g] & 0xFFFFu), x1 = (int)(px[g] >> 16), y0 = (int)(py[g] & 0xFFFFu), y1 = (int)(py[g] >> 16);
+        const int cnt = (x1 > x0 && y1 > y0) ? coarse_span(x0, x1) * coarse_span(y0, y1) : 0;
+        int incl = cnt;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int o = __shfl_up_sync(FULL, incl, d);
+            if (lane >= d) incl += o;
+        }
+        excl[g] = incl - cnt;                                   // inside the group
+        tot[g] = __shfl_sync(FULL, incl, 31);
+        warp_total += tot[g];
+    }
+    if (lane == 0) s_warp_tot[warp] = warp_total;
+    __syncthreads();
+    int warp_off = 0, block_sum = 0;
+#pragma unroll
+    for (int w = 0; w < EXP_THREADS / 32; ++w) {
+        const int x = s_warp_tot[w];
+        if (w < warp) warp_off += x;
+        block_sum += x;
+    }
+    if (warp == 0) {
+        const unsigned long long e = lookback_warp(status, cta, (unsigned long long)block_sum, lane);
+        if (lane == 0) s_prefix = e;
+    }
+    __syncthreads();
+    int64_t out0 = (int64_t)s_prefix + warp_off;
+    const unsigned m0 = (1u << pl.bits[0]) - 1u, m1 = pl.passes > 1 ? (1u << pl.bits[1]) - 1u : 0u;
+    const int sh1 = pl.shift[1];
+    const uint32_t per_cam = (uint32_t)(bins_w * bins_h);
+#pragma unroll
+    for (int g = 0; g < EMIT_GROUPS; ++g) {
+        const int total = tot[g];
+        if (total == 0) continue;                               // warp-uniform
+        __syncwarp();
+        int64_t cam = 0;
+        if (px[g] >> 16) cam = camera_ids ? camera_ids[id[g]] : (id[g] / N);
+        s_start[threadIdx.x] = excl[g];
+        s_id[threadIdx.x] = id[g];
+        s_xs[threadIdx.x] = px[g];
+        s_ys[threadIdx.x] = py[g];
+        s_cam[threadIdx.x] = (uint32_t)cam * per_cam;
+        __syncwarp();
+        for (int e = lane; e < total; e += 32) {
+            int lo = 0;
+#pragma unroll
+            for (int step = 16; step > 0; step >>= 1)
+                if (s_start[wbase + lo + step] <= e) lo += step;
+            const int q = wbase + lo;
+            const int k = e - s_start[q];
+            const int gx0 = (int)(s_xs[q] & 0xFFFFu), gx1 = (int)(s_xs[q] >> 16);
+            const int gy0 = (int)(s_ys[q] & 0xFFFFu), gy1 = (int)(s_ys[q] >> 16);
+            const int bx0 = gx0 / CB, by0 = gy0 / CB;
+            const int w = coarse_span(gx0, gx1);
+            const int dy = k / w, dx = k - dy * w;
+            const int bx = bx0 + dx, by = by0 + dy;
+            const int lx0 = max(gx0 - bx * CB, 0), lx1 = min(gx1 - bx * CB, CB);
+            const int ly0 = max(gy0 - by * CB, 0), ly1 = min(gy1 - by * CB, CB);
+            const uint32_t mx = ((1u << lx1) - 1u) & ~((1u << lx0) - 1u);
+            const uint32_t my = ((1u << ly1) - 1u) & ~((1u << ly0) - 1u);
+            const uint32_t key = s_cam[q] + (uint32_t)(by * bins_w + bx);
+            recs[out0 + e] = (my << 24) | (mx << 16) | key;
+            vals[out0 + e] = s_id[q];
+            atomicAdd(&s_hist[key & m0], 1u);
+            if (m1) atomicAdd(&s_hist[radix::RADIX + ((key >> sh1) & m1)], 1u);
+        }
+        out0 += total;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < pl.passes * radix::RADIX; i += EXP_THREADS)
+        if (s_hist[i]) atomicAdd(&hist[i], (unsigned long long)s_hist[i]);
+}
+
+// one digit pass sorts the records: the scanned digit histogram of that pass IS the offset table
+__global__ void coarse_offsets_from_hist_kernel(const unsigned long long* __restrict__ scanned, int64_t n_bins, int64_t n_records,
+                                                int32_t* __restrict__ offsets) {
+    for (int64_t k = threadIdx.x; k <= n_bins; k += blockDim.x) offsets[k] = k < n_bins ? (int32_t)scanned[k] : (int32_t)n_records;
+}
+
 // bin_offsets[k] = lower bound of coarse key k in the sorted records, k = 0 .. n_bins (inclusive: the end)
 __global__ void coarse_offsets_kernel(int64_t n, const uint32_t* __restrict__ recs, int64_t n_bins, int32_t* __restrict__ offsets) {
     int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -1010,6 +1158,100 @@ extern "C" int b2s_coarse_bin(int64_t M, int64_t N, const int64_t* camera_ids, i
         B2S_CUDA(cudaMemsetAsync(bin_ids + n_records, 0, (pad4(n_records) - (size_t)n_records) * 4, st));
     }
     coarse_offsets_kernel<<<(unsigned)cdiv(n_bins + 1, 128), 128, 0, st>>>(n_records, bin_recs, n_bins, bin_offsets);
+    B2S_LAUNCH_CHECK();
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// fused two-level binning: depth sort whose last pass emits the rectangles, one-kernel expansion
+// ---------------------------------------------------------------------------------------------------
+extern "C" int64_t b2s_depth_order_rects_workspace_bytes(int64_t M) {
+    if (M <= 0) return 256;
+    return (int64_t)align256(radix::workspace_bytes<uint32_t>(M));
+}
+
+extern "C" int b2s_depth_order_rects(int64_t M, const uint32_t* depth_keys, const int32_t* row_ids, const float* means2d,
+                                     const int32_t* radii, int32_t tile_size, int32_t tile_w, int32_t tile_h,
+                                     const b2s_tile_rows* rows, int32_t* sorted_ids, uint32_t* rect_xs, uint32_t* rect_ys,
+                                     void* workspace, int64_t workspace_bytes, b2s_stream_t stream) {
+    B2S_REQUIRE(M >= 0 && tile_size > 0 && tile_w > 0 && tile_h > 0, "bad args");
+    B2S_REQUIRE(tile_w < 65536 && tile_h < 65536, "tile grid too large for 16-bit rectangle corners");
+    int row_lo, row_hi;
+    B2S_REQUIRE(row_window(rows, tile_h, row_lo, row_hi), "bad tile-row window");
+    if (M == 0) return 0;
+    B2S_REQUIRE(depth_keys && row_ids && means2d && radii && sorted_ids && rect_xs && rect_ys && workspace, "null pointer");
+    if (workspace_bytes < b2s_depth_order_rects_workspace_bytes(M)) {
+        set_error("b2s_depth_order_rects: workspace too small");
+        return B2S_E_WORKSPACE;
+    }
+    B2S_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255u) == 0, "workspace must be 256-byte aligned");
+    const RectEpilogue epi{reinterpret_cast<const float2*>(means2d), radii, (float)tile_size, tile_w, row_lo, row_hi, sorted_ids,
+                           rect_xs, rect_ys};
+    return radix::sort_pairs_ex<uint32_t, RectEpilogue>(M, 32, depth_keys, row_ids, epi, false, workspace, (cudaStream_t)stream);
+}
+
+extern "C" int64_t b2s_coarse_bin_rects_workspace_bytes(int64_t M, int64_t n_records) {
+    if (n_records <= 0 || M <= 0) return 256;
+    // unsorted records + unsorted ids + sort scratch + look-back status (counter + one word per CTA)
+    return (int64_t)(2 * align256(pad4(n_records) * 4) + align256(radix::workspace_bytes<uint32_t>(n_records)) +
+                     align256(16 + (size_t)cdiv(M, EMIT_ROWS) * 8));
+}
+
+extern "C" int b2s_coarse_bin_rects(int64_t M, int64_t N, const int64_t* camera_ids, int64_t n_records, const int32_t* sorted_ids,
+                                    const uint32_t* rect_xs, const uint32_t* rect_ys, int32_t C, int32_t tile_w, int32_t tile_h,
+                                    uint32_t* bin_recs, int32_t* bin_ids, int32_t* bin_offsets, void* workspace,
+                                    int64_t workspace_bytes, b2s_stream_t stream) {
+    B2S_REQUIRE(M >= 0 && n_records >= 0 && C >= 0 && tile_w > 0 && tile_h > 0 && bin_offsets, "bad args");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int bins_w = (tile_w + CB - 1) / CB, bins_h = (tile_h + CB - 1) / CB;
+    const int64_t n_bins = (int64_t)C * bins_w * bins_h;
+    if (n_bins > 65536) {
+        set_error("b2s_coarse_bin_rects: C * bins_w * bins_h = %lld exceeds 65536", (long long)n_bins);
+        return B2S_E_UNSUPPORTED;
+    }
+    if (n_records == 0 || M == 0) {
+        B2S_CUDA(cudaMemsetAsync(bin_offsets, 0, (size_t)(n_bins + 1) * 4, st));
+        return 0;
+    }
+    B2S_REQUIRE(camera_ids != nullptr || N > 0, "dense rows need N");
+    B2S_REQUIRE(sorted_ids && rect_xs && rect_ys && bin_recs && bin_ids && workspace, "null pointer");
+    B2S_REQUIRE(n_records < 2147483647LL, "n_records must fit int32");
+    if (workspace_bytes < b2s_coarse_bin_rects_workspace_bytes(M, n_records)) {
+        set_error("b2s_coarse_bin_rects: workspace too small");
+        return B2S_E_WORKSPACE;
+    }
+    B2S_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255u) == 0, "workspace must be 256-byte aligned");
+    B2S_REQUIRE(((reinterpret_cast<uintptr_t>(bin_recs) | reinterpret_cast<uintptr_t>(bin_ids)) & 15u) == 0,
+                "bin_recs / bin_ids must be 16-byte aligned");
+    char* w = reinterpret_cast<char*>(workspace);
+    uint32_t* recs_u = reinterpret_cast<uint32_t*>(w);
+    w += align256(pad4(n_records) * 4);
+    int32_t* vals_u = reinterpret_cast<int32_t*>(w);
+    w += align256(pad4(n_records) * 4);
+    void* sort_ws = w;
+    w += align256(radix::workspace_bytes<uint32_t>(n_records));
+    const int64_t ctas = cdiv(M, EMIT_ROWS);
+    unsigned int* counter = reinterpret_cast<unsigned int*>(w);
+    unsigned long long* status = reinterpret_cast<unsigned long long*>(w + 16);
+    const int key_bits = bit_length(n_bins > 1 ? n_bins - 1 : 1);
+    const radix::Plan pl = radix::make_plan(key_bits);                       // at most 2 passes (16 key bits)
+    unsigned long long* hist = radix::hist_ptr<uint32_t>(sort_ws, n_records);
+    B2S_CUDA(cudaMemsetAsync(counter, 0, (size_t)(16 + ctas * 8), st));
+    B2S_CUDA(cudaMemsetAsync(hist, 0, sizeof(uint32_t) * radix::RADIX * 8, st));
+    coarse_emit_lb_kernel<<<(unsigned)ctas, EXP_THREADS, 0, st>>>(M, N, camera_ids, sorted_ids, rect_xs, rect_ys, bins_w, bins_h, status,
+                                                                  counter, pl, hist, recs_u, vals_u);
+    B2S_LAUNCH_CHECK();
+    {
+        const radix::StorePairs<uint32_t> out{bin_recs, bin_ids};
+        int rc = radix::sort_pairs_ex<uint32_t, radix::StorePairs<uint32_t>>(n_records, key_bits, recs_u, vals_u, out, true, sort_ws, st);
+        if (rc != 0) return rc;
+    }
+    if (pad4(n_records) > (size_t)n_records) {       // the kernels read the lists 4 entries at a time: define the pad entries
+        B2S_CUDA(cudaMemsetAsync(bin_recs + n_records, 0, (pad4(n_records) - (size_t)n_records) * 4, st));
+        B2S_CUDA(cudaMemsetAsync(bin_ids + n_records, 0, (pad4(n_records) - (size_t)n_records) * 4, st));
+    }
+    if (pl.passes == 1) coarse_offsets_from_hist_kernel<<<1, 256, 0, st>>>(hist, n_bins, n_records, bin_offsets);
+    else coarse_offsets_kernel<<<(unsigned)cdiv(n_bins + 1, 128), 128, 0, st>>>(n_records, bin_recs, n_bins, bin_offsets);
     B2S_LAUNCH_CHECK();
     return 0;
 }

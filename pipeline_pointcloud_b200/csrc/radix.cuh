@@ -25,7 +25,10 @@ constexpr int THREADS = 256;
 constexpr int WARPS = THREADS / 32;
 constexpr unsigned long long R_FLAG_AGG = 1ull << 62, R_FLAG_INC = 2ull << 62, R_VAL_MASK = (1ull << 62) - 1;
 
-template <typename KeyT> struct Cfg { static constexpr int ITEMS = 16; };
+#ifndef B2S_RADIX_ITEMS32
+#define B2S_RADIX_ITEMS32 16
+#endif
+template <typename KeyT> struct Cfg { static constexpr int ITEMS = B2S_RADIX_ITEMS32; };
 template <> struct Cfg<uint64_t> { static constexpr int ITEMS = 8; };
 
 template <typename KeyT>
@@ -104,10 +107,33 @@ template <> struct St<unsigned long long> {
 #ifndef B2S_RADIX_MINBLOCKS
 #define B2S_RADIX_MINBLOCKS 3
 #endif
-template <typename KeyT, typename StatusT>
+// What the scatter of a pass does with an element whose final position is known.  The default stores the pair; the last
+// pass of the depth sort swaps in an epilogue that consumes the element on the spot (binning.cu: the row's tile rectangle
+// is gathered and written in depth order, the sorted keys -- which nobody reads -- are never stored).
+template <typename KeyT>
+struct StorePairs {
+    KeyT* keys_out;
+    int32_t* vals_out;
+    __device__ __forceinline__ void operator()(bool active, unsigned pos, KeyT key, int32_t val) const {
+        if (active) {
+            keys_out[pos] = key;
+            vals_out[pos] = val;
+        }
+    }
+};
+
+// Ranking inside a warp (A/B, profiles/r02_variants_c15.txt):
+//   0  `match.any` on the digit (the product default)
+//   1  peer masks built with shared-memory atomicOr (two alternating mask arrays that alias the reorder buffers)
+//   2  one ballot per digit bit
+#ifndef B2S_RADIX_RANK
+#define B2S_RADIX_RANK 0
+#endif
+
+template <typename KeyT, typename StatusT, typename Epi>
 __global__ void __launch_bounds__(THREADS, B2S_RADIX_MINBLOCKS) onesweep_kernel(unsigned n, const KeyT* __restrict__ keys_in,
-                                                              const int32_t* __restrict__ vals_in, KeyT* __restrict__ keys_out,
-                                                              int32_t* __restrict__ vals_out, int shift, unsigned mask,
+                                                              const int32_t* __restrict__ vals_in, const Epi epi, int shift,
+                                                              unsigned mask,
                                                               const unsigned long long* __restrict__ digit_base /* [256] */,
                                                               StatusT* status /* [tiles][256] */, unsigned int* tile_counter) {
     constexpr int ITEMS = Cfg<KeyT>::ITEMS;
@@ -120,9 +146,20 @@ __global__ void __launch_bounds__(THREADS, B2S_RADIX_MINBLOCKS) onesweep_kernel(
     __shared__ int32_t s_vals[TILE];
     __shared__ unsigned s_wsum[WARPS];
     __shared__ unsigned int s_tile;
+#if B2S_RADIX_RANK == 1
+    static_assert(4 * TILE >= (size_t)WARPS * RADIX * 4, "mask arrays alias the reorder buffers");
+    unsigned* s_mask0 = reinterpret_cast<unsigned*>(s_keys);     // [WARPS][RADIX], dead before the reorder starts
+    unsigned* s_mask1 = reinterpret_cast<unsigned*>(s_vals);
+#endif
 
     if (threadIdx.x == 0) s_tile = atomicAdd(tile_counter, 1u);
     for (int i = threadIdx.x; i < WARPS * HS; i += THREADS) s_warp_hist[i] = 0;
+#if B2S_RADIX_RANK == 1
+    for (int i = threadIdx.x; i < WARPS * RADIX; i += THREADS) {
+        s_mask0[i] = 0;
+        s_mask1[i] = 0;
+    }
+#endif
     __syncthreads();
     const unsigned tile = s_tile;
     const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -153,12 +190,51 @@ __global__ void __launch_bounds__(THREADS, B2S_RADIX_MINBLOCKS) onesweep_kernel(
     }
     // 2. rank inside the warp, in memory order.  All MATCH instructions are issued first (independent); then, item
     // by item, every lane reads its digit's counter (a broadcast within the group) and the group leader bumps it.
-    unsigned peers[ITEMS];
-#pragma unroll
-    for (int i = 0; i < ITEMS; ++i) peers[i] = __match_any_sync(FULL, dig[i]);
     unsigned* my_hist = s_warp_hist + warp * HS;
     const unsigned lt_mask = (1u << lane) - 1u;
     unsigned rank[ITEMS];
+#if B2S_RADIX_RANK == 1
+    // peers through shared memory: every lane ORs its bit into its digit's mask word; the group leader clears the word
+    // again.  Consecutive items use different mask arrays, so the clear of item i never races the ORs of item i + 1.
+    {
+        unsigned* mk0 = s_mask0 + warp * RADIX;
+        unsigned* mk1 = s_mask1 + warp * RADIX;
+#pragma unroll
+        for (int i = 0; i < ITEMS; ++i) {
+            unsigned* mk = (i & 1) ? mk1 : mk0;
+            const bool live = full || dig[i] < RADIX;            // the dump-bin lanes of the last tile are never stored
+            if (live) atomicOr(&mk[dig[i]], 1u << lane);
+            __syncwarp();
+            const unsigned peers = live ? mk[dig[i]] : (1u << lane);
+            const unsigned pre = my_hist[dig[i]];
+            __syncwarp();
+            if (live && lane == __ffs(peers) - 1) {
+                mk[dig[i]] = 0u;
+                my_hist[dig[i]] = pre + __popc(peers);
+            }
+            rank[i] = pre + __popc(peers & lt_mask);
+        }
+        __syncwarp();
+    }
+#else
+    unsigned peers[ITEMS];
+#if B2S_RADIX_RANK == 2
+#pragma unroll
+    for (int i = 0; i < ITEMS; ++i) {
+        unsigned m = FULL;
+#pragma unroll
+        for (int b = 0; b <= RADIX_BITS; ++b) {          // bit 8: the dump bin of the last tile
+            if (b == RADIX_BITS && full) break;
+            const bool bit = (dig[i] >> b) & 1u;
+            const unsigned bal = __ballot_sync(FULL, bit);
+            m &= bit ? bal : ~bal;
+        }
+        peers[i] = m;
+    }
+#else
+#pragma unroll
+    for (int i = 0; i < ITEMS; ++i) peers[i] = __match_any_sync(FULL, dig[i]);
+#endif
 #pragma unroll
     for (int i = 0; i < ITEMS; ++i) {
         const unsigned pre = my_hist[dig[i]];
@@ -167,6 +243,7 @@ __global__ void __launch_bounds__(THREADS, B2S_RADIX_MINBLOCKS) onesweep_kernel(
         rank[i] = pre + __popc(peers[i] & lt_mask);
         __syncwarp();
     }
+#endif
     __syncthreads();
     // 3. thread d <-> digit d: exclusive prefix across warps, tile total
     const unsigned d = threadIdx.x;
@@ -243,11 +320,10 @@ __global__ void __launch_bounds__(THREADS, B2S_RADIX_MINBLOCKS) onesweep_kernel(
     }
     __syncthreads();
 #pragma unroll 4
-    for (unsigned p = threadIdx.x; p < tile_count; p += THREADS) {
+    for (unsigned p = threadIdx.x; p - threadIdx.x < tile_count; p += THREADS) {     // whole warps: the epilogue may vote
         const KeyT k = s_keys[p];
         const unsigned pos = s_off[digit_of(k, shift, mask)] + p;
-        keys_out[pos] = k;
-        vals_out[pos] = s_vals[p];
+        epi(p < tile_count, pos, k, s_vals[p]);
     }
 }
 
@@ -268,10 +344,20 @@ static inline size_t workspace_bytes(int64_t n) {
            up256((size_t)tiles_of<KeyT>(n) * RADIX * 8) + up256((size_t)max_passes * 4);
 }
 
-// Sorts bits [0, key_bits) ascending, stable.  keys_in/vals_in are not modified; result in keys_out/vals_out.
+// where the [passes][256] digit histograms live inside the workspace (a caller that counts the digits itself -- the
+// coarse-bin expansion -- zeroes and fills them, then sorts with hist_ready = true)
 template <typename KeyT>
-static int sort_pairs(int64_t n, int key_bits, const KeyT* keys_in, const int32_t* vals_in, KeyT* keys_out, int32_t* vals_out,
-                      void* workspace, cudaStream_t st) {
+static inline unsigned long long* hist_ptr(void* workspace, int64_t n) {
+    return reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(workspace) + 2 * up256((size_t)n * sizeof(KeyT)) +
+                                                 2 * up256((size_t)n * 4));
+}
+
+// Sorts bits [0, key_bits) ascending, stable.  keys_in/vals_in are not modified.  Every pass but the last stores the
+// pairs into the workspace; the last pass hands each element with its final position to `last` (StorePairs = the plain
+// sort).  hist_ready: the workspace histograms already hold the digit counts of `make_plan(key_bits)`.
+template <typename KeyT, typename Epi>
+static int sort_pairs_ex(int64_t n, int key_bits, const KeyT* keys_in, const int32_t* vals_in, const Epi& last, bool hist_ready,
+                         void* workspace, cudaStream_t st) {
     if (n <= 0) return 0;
     if (n >= 2147483647LL) {
         set_error("radix::sort_pairs: n must be < 2^31");
@@ -297,35 +383,50 @@ static int sort_pairs(int64_t n, int key_bits, const KeyT* keys_in, const int32_
     w += up256((size_t)tiles * RADIX * 8);
     unsigned int* counters = reinterpret_cast<unsigned int*>(w);
 
-    B2S_CUDA(cudaMemsetAsync(hist, 0, (size_t)MAXP * RADIX * 8, st));
+    if (!hist_ready) {
+        B2S_CUDA(cudaMemsetAsync(hist, 0, (size_t)MAXP * RADIX * 8, st));
+        const int hist_grid = (int)min((int64_t)148 * 8, cdiv(n, THREADS));
+        hist_kernel<KeyT, MAXP><<<hist_grid, THREADS, 0, st>>>(n, keys_in, pl, hist);
+        B2S_LAUNCH_CHECK();
+    }
     B2S_CUDA(cudaMemsetAsync(counters, 0, (size_t)MAXP * 4, st));
-    const int hist_grid = (int)min((int64_t)148 * 8, cdiv(n, THREADS));
-    hist_kernel<KeyT, MAXP><<<hist_grid, THREADS, 0, st>>>(n, keys_in, pl, hist);
-    B2S_LAUNCH_CHECK();
     scan_hist_kernel<<<passes, RADIX, 0, st>>>(hist);
     B2S_LAUNCH_CHECK();
     const KeyT* src_k = keys_in;
     const int32_t* src_v = vals_in;
+    const bool small = n < (1LL << 30);
     for (int p = 0; p < passes; ++p) {
-        const bool last = (p == passes - 1);
-        KeyT* dst_k = last ? keys_out : tk[p & 1];
-        int32_t* dst_v = last ? vals_out : tv[p & 1];
-        if (n < (1LL << 30)) {
-            B2S_CUDA(cudaMemsetAsync(status, 0, (size_t)tiles * RADIX * 4, st));
-            onesweep_kernel<KeyT, unsigned><<<(unsigned)tiles, THREADS, 0, st>>>(
-                (unsigned)n, src_k, src_v, dst_k, dst_v, pl.shift[p], (1u << pl.bits[p]) - 1u, hist + (size_t)p * RADIX,
-                reinterpret_cast<unsigned*>(status), counters + p);
+        B2S_CUDA(cudaMemsetAsync(status, 0, (size_t)tiles * RADIX * (small ? 4 : 8), st));
+        const unsigned mask = (1u << pl.bits[p]) - 1u;
+        const unsigned long long* base = hist + (size_t)p * RADIX;
+        if (p == passes - 1) {
+            if (small)
+                onesweep_kernel<KeyT, unsigned, Epi><<<(unsigned)tiles, THREADS, 0, st>>>(
+                    (unsigned)n, src_k, src_v, last, pl.shift[p], mask, base, reinterpret_cast<unsigned*>(status), counters + p);
+            else
+                onesweep_kernel<KeyT, unsigned long long, Epi><<<(unsigned)tiles, THREADS, 0, st>>>(
+                    (unsigned)n, src_k, src_v, last, pl.shift[p], mask, base, status, counters + p);
         } else {
-            B2S_CUDA(cudaMemsetAsync(status, 0, (size_t)tiles * RADIX * 8, st));
-            onesweep_kernel<KeyT, unsigned long long><<<(unsigned)tiles, THREADS, 0, st>>>(
-                (unsigned)n, src_k, src_v, dst_k, dst_v, pl.shift[p], (1u << pl.bits[p]) - 1u, hist + (size_t)p * RADIX, status,
-                counters + p);
+            const StorePairs<KeyT> mid{tk[p & 1], tv[p & 1]};
+            if (small)
+                onesweep_kernel<KeyT, unsigned, StorePairs<KeyT>><<<(unsigned)tiles, THREADS, 0, st>>>(
+                    (unsigned)n, src_k, src_v, mid, pl.shift[p], mask, base, reinterpret_cast<unsigned*>(status), counters + p);
+            else
+                onesweep_kernel<KeyT, unsigned long long, StorePairs<KeyT>><<<(unsigned)tiles, THREADS, 0, st>>>(
+                    (unsigned)n, src_k, src_v, mid, pl.shift[p], mask, base, status, counters + p);
+            src_k = tk[p & 1];
+            src_v = tv[p & 1];
         }
         B2S_LAUNCH_CHECK();
-        src_k = dst_k;
-        src_v = dst_v;
     }
     return 0;
+}
+
+template <typename KeyT>
+static int sort_pairs(int64_t n, int key_bits, const KeyT* keys_in, const int32_t* vals_in, KeyT* keys_out, int32_t* vals_out,
+                      void* workspace, cudaStream_t st) {
+    return sort_pairs_ex<KeyT, StorePairs<KeyT>>(n, key_bits, keys_in, vals_in, StorePairs<KeyT>{keys_out, vals_out}, false,
+                                                 workspace, st);
 }
 
 }  // namespace radix

@@ -724,9 +724,21 @@ def bin_coarse(means2d: Tensor, radii: Tensor, depths: Tensor, tile_size: int, t
             check(lib.b2s_coarse_count(M, ptr(means2d), ptr(radii), tile_size, tile_width, tile_height, ptr(tot),
                                        L.tile_rows(tile_rows), st), "b2s_coarse_count")
     sorted_ids = torch.empty(max(M, 1), dtype=torch.int32, device=dev)
-    ws = _ws(lib.b2s_depth_order_workspace_bytes(M), dev)
-    with _stage("depth_order", launches=6):      # histogram, scan, 4 digit passes
-        check(lib.b2s_depth_order(M, ptr(depth_keys), ptr(row_ids), ptr(sorted_ids), ptr(ws), ws.numel(), st), "b2s_depth_order")
+    # fused path: the sort's last pass stores the tile rectangles in depth order, the expansion is one kernel
+    # (B2S_BINNING_FUSED=0: the unfused reference kernels, same outputs bit for bit)
+    fused = os.environ.get("B2S_BINNING_FUSED", "1") != "0" and tile_width < 65536 and tile_height < 65536
+    if fused:
+        rect_xs = torch.empty(max(M, 1), dtype=torch.int32, device=dev)
+        rect_ys = torch.empty(max(M, 1), dtype=torch.int32, device=dev)
+        ws = _ws(lib.b2s_depth_order_rects_workspace_bytes(M), dev)
+        with _stage("depth_order", launches=6):      # histogram, scan, 4 digit passes (the last one emits the rectangles)
+            check(lib.b2s_depth_order_rects(M, ptr(depth_keys), ptr(row_ids), ptr(means2d), ptr(radii), tile_size, tile_width,
+                                            tile_height, L.tile_rows(tile_rows), ptr(sorted_ids), ptr(rect_xs), ptr(rect_ys),
+                                            ptr(ws), ws.numel(), st), "b2s_depth_order_rects")
+    else:
+        ws = _ws(lib.b2s_depth_order_workspace_bytes(M), dev)
+        with _stage("depth_order", launches=6):      # histogram, scan, 4 digit passes
+            check(lib.b2s_depth_order(M, ptr(depth_keys), ptr(row_ids), ptr(sorted_ids), ptr(ws), ws.numel(), st), "b2s_depth_order")
     # The one host sync of a forward (sizes the record buffers).  The depth sort is already enqueued, so the GPU
     # keeps working while the host waits for the counts that stage 1 produced.
     n_visible = None
@@ -744,8 +756,16 @@ def bin_coarse(means2d: Tensor, radii: Tensor, depths: Tensor, tile_size: int, t
     recs = torch.empty(n_alloc, dtype=torch.int32, device=dev)
     ids = torch.empty(n_alloc, dtype=torch.int32, device=dev)
     offsets = torch.empty(C * bw * bh + 1, dtype=torch.int32, device=dev)
+    two_passes = (C * bw * bh - 1).bit_length() > 8
+    if fused:
+        ws2 = _ws(lib.b2s_coarse_bin_rects_workspace_bytes(M, n_records), dev)
+        with _stage("coarse_bin", launches=4 + two_passes):          # emit, scan, passes, offsets
+            check(lib.b2s_coarse_bin_rects(M, N, ptr(cam), n_records, ptr(sorted_ids), ptr(rect_xs), ptr(rect_ys), C, tile_width,
+                                           tile_height, ptr(recs), ptr(ids), ptr(offsets), ptr(ws2), ws2.numel(), st),
+                  "b2s_coarse_bin_rects")
+        return CoarseBins(recs, ids, offsets, sorted_ids, n_records, n_isects, n_visible)
     ws2 = _ws(lib.b2s_coarse_bin_workspace_bytes(M, n_records), dev)
-    with _stage("coarse_bin", launches=7 + ((C * bw * bh - 1).bit_length() > 8)):   # rects, scan, emit, histogram, scan, passes, offsets
+    with _stage("coarse_bin", launches=7 + two_passes):   # rects, scan, emit, histogram, scan, passes, offsets
         check(lib.b2s_coarse_bin(M, N, ptr(cam), n_records, ptr(sorted_ids), ptr(means2d), ptr(radii), C, tile_size, tile_width,
                                  tile_height, ptr(recs), ptr(ids), ptr(offsets), ptr(ws2), ws2.numel(), L.tile_rows(tile_rows),
                                  st), "b2s_coarse_bin")
