@@ -145,9 +145,9 @@ SYMBOLS = {
     "b2s_coarse_count": (c_int32, [c_int64, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p, POINTER(TileRows), c_void_p]),
     "b2s_depth_order_rects_workspace_bytes": (c_int64, [c_int64]),
     "b2s_depth_order_rects": (c_int32, [c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32,
-                                        POINTER(TileRows), c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
+                                        POINTER(TileRows), c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
     "b2s_coarse_bin_rects_workspace_bytes": (c_int64, [c_int64, c_int64]),
-    "b2s_coarse_bin_rects": (c_int32, [c_int64, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_int32, c_int32,
+    "b2s_coarse_bin_rects": (c_int32, [c_int64, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_int32, c_int32,
                                        c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
     "b2s_coarse_bin_workspace_bytes": (c_int64, [c_int64, c_int64]),
     "b2s_coarse_bin": (c_int32, [c_int64, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_int32, c_int32,

@@ -608,18 +608,18 @@ __global__ void __launch_bounds__(EXP_THREADS) coarse_emit_kernel(int64_t M, int
 }
 
 // ---- fused path (b2s_depth_order_rects + b2s_coarse_bin_rects) ------------------------------------------------------
-// The last pass of the depth sort knows every row's final position, so it gathers the row's geometry and stores the tile
-// rectangle there (RectEpilogue): coarse_rects_kernel -- a pass of dependent gathers at 30 % issue rate -- disappears, and
-// the sorted depth keys, which nobody reads, are never written.
-struct RectEpilogue {
+// coarse_rects_kernel above is a pass of dependent gathers (sorted id -> radius, mean: two 32-byte sectors per row, DRAM
+// bound at ~65 us for 5.8 M rows wherever it runs -- fused into the sort's last pass it cost the same).  The fused path has
+// no gather at all: the FIRST pass of the depth sort, whose elements are still in row order, computes every row's tile
+// rectangle from coalesced loads and the rectangle then rides through the passes as a second 32-bit payload
+// (x0 | x1 << 8 | y0 << 16 | y1 << 24 in tile units: grids up to 255 x 255 tiles, i.e. 4080 x 4080 pixels); the last pass
+// stores (id, rectangle) in depth order and never writes the sorted keys, which nobody reads.
+struct RectLoader {
     const float2* means2d;
     const int32_t* radii;
     float tile_size;
     int tile_w, row_lo, row_hi;
-    int32_t* sorted_ids;
-    uint32_t *xs, *ys;
-    __device__ __forceinline__ void operator()(bool active, unsigned pos, uint32_t /*key*/, int32_t id) const {
-        if (!active) return;
+    __device__ __forceinline__ uint32_t operator()(unsigned /*g*/, int32_t id) const {
         const int r = __ldg(radii + id);
         const float2 m = __ldg(means2d + id);
         int x0 = 0, y0 = 0, x1 = 0, y1 = 0;
@@ -627,30 +627,44 @@ struct RectEpilogue {
             tile_rect(m.x, m.y, r, tile_size, tile_w, row_lo, row_hi, x0, y0, x1, y1);
             if (!(x1 > x0 && y1 > y0)) x0 = x1 = y0 = y1 = 0;
         }
-        sorted_ids[pos] = id;
-        xs[pos] = (uint32_t)x0 | ((uint32_t)x1 << 16);
-        ys[pos] = (uint32_t)y0 | ((uint32_t)y1 << 16);
+        return (uint32_t)x0 | ((uint32_t)x1 << 8) | ((uint32_t)y0 << 16) | ((uint32_t)y1 << 24);
+    }
+};
+struct RectStore {
+    int32_t* sorted_ids;
+    uint32_t* rects;
+    __device__ __forceinline__ void operator()(bool active, unsigned pos, uint32_t /*key*/, int32_t id, uint32_t rect) const {
+        if (active) {
+            sorted_ids[pos] = id;
+            rects[pos] = rect;
+        }
     }
 };
 
-// Expansion of the depth-ordered rectangles into coarse-bin records, one kernel: every CTA streams the rectangles of
-// EMIT_ROWS rows (coalesced -- no gather in front of the scan any more, so a CTA publishes its record count a few hundred
-// cycles after it starts and the decoupled look-back never waits for long), and counts the digits of the bin sort on the
-// way (shared-memory histogram, flushed once per CTA), which replaces the sort's own histogram pass over the records.
+// Expansion of the depth-ordered rectangles into coarse-bin records, one kernel: every CTA streams (id, rectangle) of
+// EMIT_ROWS rows (coalesced -- no gather in front of the scan, so a CTA publishes its record count a few hundred cycles
+// after it starts and the decoupled look-back never waits for long).  A row overlaps 1.4 bins on average, so every lane
+// writes the (up to EMIT_DIRECT) records of its own row itself -- the slots of neighbouring lanes are neighbours, the
+// stores coalesce -- and only the rare larger rows are expanded by the whole warp.  The digits of the bin sort are counted
+// on the way (shared-memory histogram, flushed once per CTA), which replaces the sort's own histogram pass.
 constexpr int EMIT_GROUPS = 4;                               // 32-row groups per warp
 constexpr int EMIT_ROWS = EXP_THREADS * EMIT_GROUPS;         // rows per CTA
+constexpr int EMIT_DIRECT = 4;
+
+__device__ __forceinline__ uint32_t coarse_record(int gx0, int gx1, int gy0, int gy1, int bx, int by, uint32_t cam_base, int bins_w) {
+    const int lx0 = max(gx0 - bx * CB, 0), lx1 = min(gx1 - bx * CB, CB);
+    const int ly0 = max(gy0 - by * CB, 0), ly1 = min(gy1 - by * CB, CB);
+    const uint32_t mx = ((1u << lx1) - 1u) & ~((1u << lx0) - 1u);
+    const uint32_t my = ((1u << ly1) - 1u) & ~((1u << ly0) - 1u);
+    return (my << 24) | (mx << 16) | (cam_base + (uint32_t)(by * bins_w + bx));
+}
 
 __global__ void __launch_bounds__(EXP_THREADS) coarse_emit_lb_kernel(int64_t M, int64_t N, const int64_t* __restrict__ camera_ids,
                                                                      const int32_t* __restrict__ sorted_ids,
-                                                                     const uint32_t* __restrict__ xs, const uint32_t* __restrict__ ys,
-                                                                     int bins_w, int bins_h, unsigned long long* status,
-                                                                     unsigned int* cta_counter, const radix::Plan pl,
-                                                                     unsigned long long* __restrict__ hist,
+                                                                     const uint32_t* __restrict__ rects, int bins_w, int bins_h,
+                                                                     unsigned long long* status, unsigned int* cta_counter,
+                                                                     const radix::Plan pl, unsigned long long* __restrict__ hist,
                                                                      uint32_t* __restrict__ recs, int32_t* __restrict__ vals) {
-    __shared__ int s_start[EXP_THREADS];
-    __shared__ int s_id[EXP_THREADS];
-    __shared__ uint32_t s_xs[EXP_THREADS], s_ys[EXP_THREADS];
-    __shared__ uint32_t s_cam[EXP_THREADS];
     __shared__ unsigned int s_cta;
     __shared__ int s_warp_tot[EXP_THREADS / 32];
     __shared__ unsigned long long s_prefix;
@@ -659,36 +673,34 @@ __global__ void __launch_bounds__(EXP_THREADS) coarse_emit_lb_kernel(int64_t M, 
     for (int i = threadIdx.x; i < 2 * radix::RADIX; i += EXP_THREADS) s_hist[i] = 0u;
     __syncthreads();
     const unsigned int cta = s_cta;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wbase = threadIdx.x & ~31;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int64_t row0 = (int64_t)cta * EMIT_ROWS + (int64_t)warp * (32 * EMIT_GROUPS) + lane;
-    uint32_t px[EMIT_GROUPS], py[EMIT_GROUPS];
-    int id[EMIT_GROUPS], excl[EMIT_GROUPS], tot[EMIT_GROUPS];
+    uint32_t rc[EMIT_GROUPS];
+    int id[EMIT_GROUPS], cnt[EMIT_GROUPS], excl[EMIT_GROUPS];
 #pragma unroll
     for (int g = 0; g < EMIT_GROUPS; ++g) {
         const int64_t j = row0 + g * 32;
-        px[g] = 0u; py[g] = 0u; id[g] = 0;
+        rc[g] = 0u; id[g] = 0;
         if (j < M) {
-            px[g] = xs[j];
-            py[g] = ys[j];
+            rc[g] = rects[j];
             id[g] = sorted_ids[j];
         }
     }
-    int warp_total = 0;
+    int run = 0;                                               // records of the warp's earlier groups
 #pragma unroll
     for (int g = 0; g < EMIT_GROUPS; ++g) {
-        const int x0 = (int)(px[g] & 0xFFFFu), x1 = (int)(px[g] >> 16), y0 = (int)(py[g] & 0xFFFFu), y1 = (int)(py[g] >> 16);
-        const int cnt = (x1 > x0 && y1 > y0) ? coarse_span(x0, x1) * coarse_span(y0, y1) : 0;
-        int incl = cnt;
+        const int x0 = (int)(rc[g] & 0xFFu), x1 = (int)((rc[g] >> 8) & 0xFFu), y0 = (int)((rc[g] >> 16) & 0xFFu), y1 = (int)(rc[g] >> 24);
+        cnt[g] = (x1 > x0 && y1 > y0) ? coarse_span(x0, x1) * coarse_span(y0, y1) : 0;
+        int incl = cnt[g];
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
             const int o = __shfl_up_sync(FULL, incl, d);
             if (lane >= d) incl += o;
         }
-        excl[g] = incl - cnt;                                   // inside the group
-        tot[g] = __shfl_sync(FULL, incl, 31);
-        warp_total += tot[g];
+        excl[g] = run + incl - cnt[g];
+        run += __shfl_sync(FULL, incl, 31);
     }
-    if (lane == 0) s_warp_tot[warp] = warp_total;
+    if (lane == 0) s_warp_tot[warp] = run;
     __syncthreads();
     int warp_off = 0, block_sum = 0;
 #pragma unroll
@@ -702,47 +714,45 @@ __global__ void __launch_bounds__(EXP_THREADS) coarse_emit_lb_kernel(int64_t M, 
         if (lane == 0) s_prefix = e;
     }
     __syncthreads();
-    int64_t out0 = (int64_t)s_prefix + warp_off;
+    const int64_t out0 = (int64_t)s_prefix + warp_off;
     const unsigned m0 = (1u << pl.bits[0]) - 1u, m1 = pl.passes > 1 ? (1u << pl.bits[1]) - 1u : 0u;
     const int sh1 = pl.shift[1];
     const uint32_t per_cam = (uint32_t)(bins_w * bins_h);
+    auto put = [&](int64_t slot, uint32_t rec, int v) {
+        recs[slot] = rec;
+        vals[slot] = v;
+        atomicAdd(&s_hist[rec & m0], 1u);
+        if (m1) atomicAdd(&s_hist[radix::RADIX + ((rec >> sh1) & m1)], 1u);
+    };
 #pragma unroll
     for (int g = 0; g < EMIT_GROUPS; ++g) {
-        const int total = tot[g];
-        if (total == 0) continue;                               // warp-uniform
-        __syncwarp();
-        int64_t cam = 0;
-        if (px[g] >> 16) cam = camera_ids ? camera_ids[id[g]] : (id[g] / N);
-        s_start[threadIdx.x] = excl[g];
-        s_id[threadIdx.x] = id[g];
-        s_xs[threadIdx.x] = px[g];
-        s_ys[threadIdx.x] = py[g];
-        s_cam[threadIdx.x] = (uint32_t)cam * per_cam;
-        __syncwarp();
-        for (int e = lane; e < total; e += 32) {
-            int lo = 0;
-#pragma unroll
-            for (int step = 16; step > 0; step >>= 1)
-                if (s_start[wbase + lo + step] <= e) lo += step;
-            const int q = wbase + lo;
-            const int k = e - s_start[q];
-            const int gx0 = (int)(s_xs[q] & 0xFFFFu), gx1 = (int)(s_xs[q] >> 16);
-            const int gy0 = (int)(s_ys[q] & 0xFFFFu), gy1 = (int)(s_ys[q] >> 16);
-            const int bx0 = gx0 / CB, by0 = gy0 / CB;
-            const int w = coarse_span(gx0, gx1);
-            const int dy = k / w, dx = k - dy * w;
-            const int bx = bx0 + dx, by = by0 + dy;
-            const int lx0 = max(gx0 - bx * CB, 0), lx1 = min(gx1 - bx * CB, CB);
-            const int ly0 = max(gy0 - by * CB, 0), ly1 = min(gy1 - by * CB, CB);
-            const uint32_t mx = ((1u << lx1) - 1u) & ~((1u << lx0) - 1u);
-            const uint32_t my = ((1u << ly1) - 1u) & ~((1u << ly0) - 1u);
-            const uint32_t key = s_cam[q] + (uint32_t)(by * bins_w + bx);
-            recs[out0 + e] = (my << 24) | (mx << 16) | key;
-            vals[out0 + e] = s_id[q];
-            atomicAdd(&s_hist[key & m0], 1u);
-            if (m1) atomicAdd(&s_hist[radix::RADIX + ((key >> sh1) & m1)], 1u);
+        const int gx0 = (int)(rc[g] & 0xFFu), gx1 = (int)((rc[g] >> 8) & 0xFFu), gy0 = (int)((rc[g] >> 16) & 0xFFu), gy1 = (int)(rc[g] >> 24);
+        uint32_t cam_base = 0u;
+        if (cnt[g] > 0) cam_base = (uint32_t)(camera_ids ? camera_ids[id[g]] : (id[g] / N)) * per_cam;
+        const int bx0 = gx0 / CB, by0 = gy0 / CB, w = cnt[g] > 0 ? coarse_span(gx0, gx1) : 1;
+        // small rows: each lane writes its own records
+        if (cnt[g] <= EMIT_DIRECT) {
+            int dx = 0, dy = 0;
+            for (int k = 0; k < cnt[g]; ++k) {
+                put(out0 + excl[g] + k, coarse_record(gx0, gx1, gy0, gy1, bx0 + dx, by0 + dy, cam_base, bins_w), id[g]);
+                if (++dx == w) { dx = 0; ++dy; }
+            }
         }
-        out0 += total;
+        // large rows: one at a time, the warp strides over the row's bins
+        unsigned big = __ballot_sync(FULL, cnt[g] > EMIT_DIRECT);
+        while (big) {
+            const int src = __ffs(big) - 1;
+            big &= big - 1;
+            const uint32_t r = __shfl_sync(FULL, rc[g], src);
+            const int n = __shfl_sync(FULL, cnt[g], src), v = __shfl_sync(FULL, id[g], src);
+            const int ex = __shfl_sync(FULL, excl[g], src), ww = __shfl_sync(FULL, w, src);
+            const uint32_t cb = __shfl_sync(FULL, cam_base, src);
+            const int rx0 = (int)(r & 0xFFu), rx1 = (int)((r >> 8) & 0xFFu), ry0 = (int)((r >> 16) & 0xFFu), ry1 = (int)(r >> 24);
+            for (int k = lane; k < n; k += 32) {
+                const int dy = k / ww, dx = k - dy * ww;
+                put(out0 + ex + k, coarse_record(rx0, rx1, ry0, ry1, rx0 / CB + dx, ry0 / CB + dy, cb, bins_w), v);
+            }
+        }
     }
     __syncthreads();
     for (int i = threadIdx.x; i < pl.passes * radix::RADIX; i += EXP_THREADS)
@@ -1167,27 +1177,31 @@ extern "C" int b2s_coarse_bin(int64_t M, int64_t N, const int64_t* camera_ids, i
 // ---------------------------------------------------------------------------------------------------
 extern "C" int64_t b2s_depth_order_rects_workspace_bytes(int64_t M) {
     if (M <= 0) return 256;
-    return (int64_t)align256(radix::workspace_bytes<uint32_t>(M));
+    return (int64_t)align256(radix::workspace_bytes2<uint32_t>(M));
 }
 
 extern "C" int b2s_depth_order_rects(int64_t M, const uint32_t* depth_keys, const int32_t* row_ids, const float* means2d,
                                      const int32_t* radii, int32_t tile_size, int32_t tile_w, int32_t tile_h,
-                                     const b2s_tile_rows* rows, int32_t* sorted_ids, uint32_t* rect_xs, uint32_t* rect_ys,
-                                     void* workspace, int64_t workspace_bytes, b2s_stream_t stream) {
+                                     const b2s_tile_rows* rows, int32_t* sorted_ids, uint32_t* rects, void* workspace,
+                                     int64_t workspace_bytes, b2s_stream_t stream) {
     B2S_REQUIRE(M >= 0 && tile_size > 0 && tile_w > 0 && tile_h > 0, "bad args");
-    B2S_REQUIRE(tile_w < 65536 && tile_h < 65536, "tile grid too large for 16-bit rectangle corners");
+    if (tile_w > 255 || tile_h > 255) {
+        set_error("b2s_depth_order_rects: the packed rectangles need a tile grid of at most 255 x 255 (use b2s_depth_order + b2s_coarse_bin)");
+        return B2S_E_UNSUPPORTED;
+    }
     int row_lo, row_hi;
     B2S_REQUIRE(row_window(rows, tile_h, row_lo, row_hi), "bad tile-row window");
     if (M == 0) return 0;
-    B2S_REQUIRE(depth_keys && row_ids && means2d && radii && sorted_ids && rect_xs && rect_ys && workspace, "null pointer");
+    B2S_REQUIRE(depth_keys && row_ids && means2d && radii && sorted_ids && rects && workspace, "null pointer");
     if (workspace_bytes < b2s_depth_order_rects_workspace_bytes(M)) {
         set_error("b2s_depth_order_rects: workspace too small");
         return B2S_E_WORKSPACE;
     }
     B2S_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255u) == 0, "workspace must be 256-byte aligned");
-    const RectEpilogue epi{reinterpret_cast<const float2*>(means2d), radii, (float)tile_size, tile_w, row_lo, row_hi, sorted_ids,
-                           rect_xs, rect_ys};
-    return radix::sort_pairs_ex<uint32_t, RectEpilogue>(M, 32, depth_keys, row_ids, epi, false, workspace, (cudaStream_t)stream);
+    const RectLoader first{reinterpret_cast<const float2*>(means2d), radii, (float)tile_size, tile_w, row_lo, row_hi};
+    const RectStore last{sorted_ids, rects};
+    return radix::sort_ex<uint32_t, true, RectLoader, RectStore>(M, 32, depth_keys, row_ids, first, last, false, workspace,
+                                                                 (cudaStream_t)stream);
 }
 
 extern "C" int64_t b2s_coarse_bin_rects_workspace_bytes(int64_t M, int64_t n_records) {
@@ -1198,7 +1212,7 @@ extern "C" int64_t b2s_coarse_bin_rects_workspace_bytes(int64_t M, int64_t n_rec
 }
 
 extern "C" int b2s_coarse_bin_rects(int64_t M, int64_t N, const int64_t* camera_ids, int64_t n_records, const int32_t* sorted_ids,
-                                    const uint32_t* rect_xs, const uint32_t* rect_ys, int32_t C, int32_t tile_w, int32_t tile_h,
+                                    const uint32_t* rects, int32_t C, int32_t tile_w, int32_t tile_h,
                                     uint32_t* bin_recs, int32_t* bin_ids, int32_t* bin_offsets, void* workspace,
                                     int64_t workspace_bytes, b2s_stream_t stream) {
     B2S_REQUIRE(M >= 0 && n_records >= 0 && C >= 0 && tile_w > 0 && tile_h > 0 && bin_offsets, "bad args");
@@ -1214,7 +1228,7 @@ extern "C" int b2s_coarse_bin_rects(int64_t M, int64_t N, const int64_t* camera_
         return 0;
     }
     B2S_REQUIRE(camera_ids != nullptr || N > 0, "dense rows need N");
-    B2S_REQUIRE(sorted_ids && rect_xs && rect_ys && bin_recs && bin_ids && workspace, "null pointer");
+    B2S_REQUIRE(sorted_ids && rects && bin_recs && bin_ids && workspace, "null pointer");
     B2S_REQUIRE(n_records < 2147483647LL, "n_records must fit int32");
     if (workspace_bytes < b2s_coarse_bin_rects_workspace_bytes(M, n_records)) {
         set_error("b2s_coarse_bin_rects: workspace too small");
@@ -1238,8 +1252,8 @@ extern "C" int b2s_coarse_bin_rects(int64_t M, int64_t N, const int64_t* camera_
     unsigned long long* hist = radix::hist_ptr<uint32_t>(sort_ws, n_records);
     B2S_CUDA(cudaMemsetAsync(counter, 0, (size_t)(16 + ctas * 8), st));
     B2S_CUDA(cudaMemsetAsync(hist, 0, sizeof(uint32_t) * radix::RADIX * 8, st));
-    coarse_emit_lb_kernel<<<(unsigned)ctas, EXP_THREADS, 0, st>>>(M, N, camera_ids, sorted_ids, rect_xs, rect_ys, bins_w, bins_h, status,
-                                                                  counter, pl, hist, recs_u, vals_u);
+    coarse_emit_lb_kernel<<<(unsigned)ctas, EXP_THREADS, 0, st>>>(M, N, camera_ids, sorted_ids, rects, bins_w, bins_h, status, counter, pl,
+                                                                  hist, recs_u, vals_u);
     B2S_LAUNCH_CHECK();
     {
         const radix::StorePairs<uint32_t> out{bin_recs, bin_ids};

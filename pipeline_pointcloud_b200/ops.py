@@ -724,17 +724,17 @@ def bin_coarse(means2d: Tensor, radii: Tensor, depths: Tensor, tile_size: int, t
             check(lib.b2s_coarse_count(M, ptr(means2d), ptr(radii), tile_size, tile_width, tile_height, ptr(tot),
                                        L.tile_rows(tile_rows), st), "b2s_coarse_count")
     sorted_ids = torch.empty(max(M, 1), dtype=torch.int32, device=dev)
-    # fused path: the sort's last pass stores the tile rectangles in depth order, the expansion is one kernel
-    # (B2S_BINNING_FUSED=0: the unfused reference kernels, same outputs bit for bit)
-    fused = os.environ.get("B2S_BINNING_FUSED", "1") != "0" and tile_width < 65536 and tile_height < 65536
+    # fused path: the sort's first pass computes the tile rectangles (coalesced), they ride through the passes as a second
+    # payload and come out in depth order; the expansion is one kernel (B2S_BINNING_FUSED=0: the unfused reference kernels,
+    # same outputs bit for bit; they also serve tile grids beyond 255 x 255)
+    fused = os.environ.get("B2S_BINNING_FUSED", "1") != "0" and tile_width <= 255 and tile_height <= 255
     if fused:
-        rect_xs = torch.empty(max(M, 1), dtype=torch.int32, device=dev)
-        rect_ys = torch.empty(max(M, 1), dtype=torch.int32, device=dev)
+        rects = torch.empty(max(M, 1), dtype=torch.int32, device=dev)
         ws = _ws(lib.b2s_depth_order_rects_workspace_bytes(M), dev)
-        with _stage("depth_order", launches=6):      # histogram, scan, 4 digit passes (the last one emits the rectangles)
+        with _stage("depth_order", launches=6):      # histogram, scan, 4 digit passes
             check(lib.b2s_depth_order_rects(M, ptr(depth_keys), ptr(row_ids), ptr(means2d), ptr(radii), tile_size, tile_width,
-                                            tile_height, L.tile_rows(tile_rows), ptr(sorted_ids), ptr(rect_xs), ptr(rect_ys),
-                                            ptr(ws), ws.numel(), st), "b2s_depth_order_rects")
+                                            tile_height, L.tile_rows(tile_rows), ptr(sorted_ids), ptr(rects), ptr(ws), ws.numel(),
+                                            st), "b2s_depth_order_rects")
     else:
         ws = _ws(lib.b2s_depth_order_workspace_bytes(M), dev)
         with _stage("depth_order", launches=6):      # histogram, scan, 4 digit passes
@@ -760,7 +760,7 @@ def bin_coarse(means2d: Tensor, radii: Tensor, depths: Tensor, tile_size: int, t
     if fused:
         ws2 = _ws(lib.b2s_coarse_bin_rects_workspace_bytes(M, n_records), dev)
         with _stage("coarse_bin", launches=4 + two_passes):          # emit, scan, passes, offsets
-            check(lib.b2s_coarse_bin_rects(M, N, ptr(cam), n_records, ptr(sorted_ids), ptr(rect_xs), ptr(rect_ys), C, tile_width,
+            check(lib.b2s_coarse_bin_rects(M, N, ptr(cam), n_records, ptr(sorted_ids), ptr(rects), C, tile_width,
                                            tile_height, ptr(recs), ptr(ids), ptr(offsets), ptr(ws2), ws2.numel(), st),
                   "b2s_coarse_bin_rects")
         return CoarseBins(recs, ids, offsets, sorted_ids, n_records, n_isects, n_visible)
