@@ -245,17 +245,18 @@ B2S_API int b2s_coarse_bin(int64_t M, int64_t N, const int64_t* camera_ids /* or
                            int32_t* bin_offsets, void* workspace, int64_t workspace_bytes, const b2s_tile_rows* rows,
                            b2s_stream_t stream);
 
-/* The same binning without its gather and with four launches fewer (what `rasterization()` runs; the pair above is kept
+/* The same binning with half the gather and four launches fewer (what `rasterization()` runs; the pair above is kept
  * as the unfused reference and for A/B, B2S_BINNING_FUSED=0, and serves tile grids beyond 255 x 255):
  *   b2s_depth_order_rects : b2s_depth_order whose FIRST radix pass -- its elements are still in row order, so the loads
- *                           coalesce -- computes every row's tile rectangle; the rectangle rides through the passes as a
- *                           second 32-bit payload and the last pass stores, in depth order, sorted_ids [M] and
+ *                           coalesce -- also derives every row's tile rectangle and stores it BY ROW, packed into 32 bits:
  *                           rects [M] = x0 | x1 << 8 | y0 << 16 | y1 << 24 (tile units, rows clipped to the window, 0 on
- *                           culled rows); the sorted keys are never written.  Needs nothing the host has to wait for,
- *                           so it too is enqueued before the host reads the record count.  tile_w, tile_h <= 255.
- *   b2s_coarse_bin_rects  : one kernel streams the rectangles, scans the record counts (decoupled look-back), writes the
- *                           records and counts the digits of the bin sort on the way; one radix pass (two above 256
- *                           bins) sorts them; with one pass the scanned digit histogram is the offset table.
+ *                           culled rows; every row id in row_ids must be < M); the last pass stores sorted_ids [M] and
+ *                           never writes the sorted keys.  Needs nothing the host has to wait for, so it too is
+ *                           enqueued before the host reads the record count.  tile_w, tile_h <= 255.
+ *   b2s_coarse_bin_rects  : one kernel gathers the rectangles of the depth-ordered rows (one word per row), scans the
+ *                           record counts (decoupled look-back), writes the records and counts the digits of the bin
+ *                           sort on the way; one radix pass (two above 256 bins) sorts them; with one pass the scanned
+ *                           digit histogram is the offset table.
  * Outputs are bit-identical to b2s_depth_order + b2s_coarse_bin. */
 B2S_API int64_t b2s_depth_order_rects_workspace_bytes(int64_t M);
 B2S_API int b2s_depth_order_rects(int64_t M, const uint32_t* depth_keys, const int32_t* row_ids, const float* means2d,

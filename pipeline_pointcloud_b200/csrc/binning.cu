@@ -609,41 +609,44 @@ __global__ void __launch_bounds__(EXP_THREADS) coarse_emit_kernel(int64_t M, int
 
 // ---- fused path (b2s_depth_order_rects + b2s_coarse_bin_rects) ------------------------------------------------------
 // coarse_rects_kernel above is a pass of dependent gathers (sorted id -> radius, mean: two 32-byte sectors per row, DRAM
-// bound at ~65 us for 5.8 M rows wherever it runs -- fused into the sort's last pass it cost the same).  The fused path has
-// no gather at all: the FIRST pass of the depth sort, whose elements are still in row order, computes every row's tile
-// rectangle from coalesced loads and the rectangle then rides through the passes as a second 32-bit payload
-// (x0 | x1 << 8 | y0 << 16 | y1 << 24 in tile units: grids up to 255 x 255 tiles, i.e. 4080 x 4080 pixels); the last pass
-// stores (id, rectangle) in depth order and never writes the sorted keys, which nobody reads.
-struct RectLoader {
+// bound at ~65 us for 5.8 M rows wherever it runs -- fused into the sort's last pass it cost the same).  Here the FIRST pass
+// of the depth sort, whose elements are still in row order, derives every row's tile rectangle from coalesced loads and
+// stores it, packed into 32 bits, by row (x0 | x1 << 8 | y0 << 16 | y1 << 24 in tile units: grids up to 255 x 255 tiles,
+// i.e. 4080 x 4080 pixels); the expansion then gathers ONE 4-byte word per depth-ordered row.  The last pass does not
+// write the sorted keys, which nobody reads.
+struct RectSide {
     const float2* means2d;
     const int32_t* radii;
-    float tile_size;
+    float tile_size, inv_tile;       // inv_tile > 0: tile_size is a power of two and x / tile_size == x * inv_tile exactly
     int tile_w, row_lo, row_hi;
-    __device__ __forceinline__ uint32_t operator()(unsigned /*g*/, int32_t id) const {
+    uint32_t* rects;                 // [M], by row
+    __device__ __forceinline__ void operator()(unsigned /*g*/, int32_t id) const {
         const int r = __ldg(radii + id);
         const float2 m = __ldg(means2d + id);
         int x0 = 0, y0 = 0, x1 = 0, y1 = 0;
         if (r > 0) {
-            tile_rect(m.x, m.y, r, tile_size, tile_w, row_lo, row_hi, x0, y0, x1, y1);
+            if (inv_tile > 0.f) {    // the same values as tile_rect, without three IEEE divisions per row
+                const float mx = __fmul_rn(m.x, inv_tile), my = __fmul_rn(m.y, inv_tile), rr = __fmul_rn((float)r, inv_tile);
+                x0 = iclamp((int)floorf(__fsub_rn(mx, rr)), 0, tile_w); y0 = iclamp((int)floorf(__fsub_rn(my, rr)), row_lo, row_hi);
+                x1 = iclamp((int)ceilf(__fadd_rn(mx, rr)), 0, tile_w); y1 = iclamp((int)ceilf(__fadd_rn(my, rr)), row_lo, row_hi);
+            } else {
+                tile_rect(m.x, m.y, r, tile_size, tile_w, row_lo, row_hi, x0, y0, x1, y1);
+            }
             if (!(x1 > x0 && y1 > y0)) x0 = x1 = y0 = y1 = 0;
         }
-        return (uint32_t)x0 | ((uint32_t)x1 << 8) | ((uint32_t)y0 << 16) | ((uint32_t)y1 << 24);
+        rects[id] = (uint32_t)x0 | ((uint32_t)x1 << 8) | ((uint32_t)y0 << 16) | ((uint32_t)y1 << 24);
     }
 };
-struct RectStore {
+struct IdStore {
     int32_t* sorted_ids;
-    uint32_t* rects;
-    __device__ __forceinline__ void operator()(bool active, unsigned pos, uint32_t /*key*/, int32_t id, uint32_t rect) const {
-        if (active) {
-            sorted_ids[pos] = id;
-            rects[pos] = rect;
-        }
+    __device__ __forceinline__ void operator()(bool active, unsigned pos, uint32_t /*key*/, int32_t id) const {
+        if (active) sorted_ids[pos] = id;
     }
 };
 
-// Expansion of the depth-ordered rectangles into coarse-bin records, one kernel: every CTA streams (id, rectangle) of
-// EMIT_ROWS rows (coalesced -- no gather in front of the scan, so a CTA publishes its record count a few hundred cycles
-// after it starts and the decoupled look-back never waits for long).  A row overlaps 1.4 bins on average, so every lane
+// Expansion of the depth-ordered rows into coarse-bin records, one kernel: every CTA takes EMIT_ROWS rows, gathers their
+// packed rectangles (one word per row: four times the rows per CTA and half the sectors per row of the fused look-back
+// kernel that stalled behind its chained scan) and obtains its output base by decoupled look-back.  A row overlaps 1.4 bins on average, so every lane
 // writes the (up to EMIT_DIRECT) records of its own row itself -- the slots of neighbouring lanes are neighbours, the
 // stores coalesce -- and only the rare larger rows are expanded by the whole warp.  The digits of the bin sort are counted
 // on the way (shared-memory histogram, flushed once per CTA), which replaces the sort's own histogram pass.
@@ -682,8 +685,8 @@ __global__ void __launch_bounds__(EXP_THREADS) coarse_emit_lb_kernel(int64_t M, 
         const int64_t j = row0 + g * 32;
         rc[g] = 0u; id[g] = 0;
         if (j < M) {
-            rc[g] = rects[j];
             id[g] = sorted_ids[j];
+            rc[g] = __ldg(rects + id[g]);
         }
     }
     int run = 0;                                               // records of the warp's earlier groups
@@ -1177,7 +1180,7 @@ extern "C" int b2s_coarse_bin(int64_t M, int64_t N, const int64_t* camera_ids, i
 // ---------------------------------------------------------------------------------------------------
 extern "C" int64_t b2s_depth_order_rects_workspace_bytes(int64_t M) {
     if (M <= 0) return 256;
-    return (int64_t)align256(radix::workspace_bytes2<uint32_t>(M));
+    return (int64_t)align256(radix::workspace_bytes<uint32_t>(M));
 }
 
 extern "C" int b2s_depth_order_rects(int64_t M, const uint32_t* depth_keys, const int32_t* row_ids, const float* means2d,
@@ -1198,10 +1201,12 @@ extern "C" int b2s_depth_order_rects(int64_t M, const uint32_t* depth_keys, cons
         return B2S_E_WORKSPACE;
     }
     B2S_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255u) == 0, "workspace must be 256-byte aligned");
-    const RectLoader first{reinterpret_cast<const float2*>(means2d), radii, (float)tile_size, tile_w, row_lo, row_hi};
-    const RectStore last{sorted_ids, rects};
-    return radix::sort_ex<uint32_t, true, RectLoader, RectStore>(M, 32, depth_keys, row_ids, first, last, false, workspace,
-                                                                 (cudaStream_t)stream);
+    const bool pow2 = (tile_size & (tile_size - 1)) == 0;
+    const RectSide first{reinterpret_cast<const float2*>(means2d), radii, (float)tile_size, pow2 ? 1.0f / (float)tile_size : 0.f,
+                         tile_w, row_lo, row_hi, rects};
+    const IdStore last{sorted_ids};
+    return radix::sort_ex<uint32_t, RectSide, IdStore>(M, 32, depth_keys, row_ids, first, last, false, workspace,
+                                                       (cudaStream_t)stream);
 }
 
 extern "C" int64_t b2s_coarse_bin_rects_workspace_bytes(int64_t M, int64_t n_records) {

@@ -14,8 +14,6 @@
 // Replaces cub::DeviceRadixSort on the training path (depth sort of Gaussians, (camera,tile) split of the
 // intersections) and in the reference-algorithm path (64-bit isect keys).
 #pragma once
-#include <type_traits>
-
 #include "common.cuh"
 
 namespace b2s {
@@ -109,41 +107,25 @@ template <> struct St<unsigned long long> {
 #ifndef B2S_RADIX_MINBLOCKS
 #define B2S_RADIX_MINBLOCKS 3
 #endif
-// What the scatter of a pass does with an element whose final position is known.  The default stores the pair (or the
-// triple, when a second 32-bit payload rides along); the last pass of the depth sort swaps in an epilogue that stores only
-// what the next stage reads (binning.cu).
+// What the scatter of a pass does with an element whose final position is known.  The default stores the pair; the last
+// pass of the depth sort swaps in an epilogue that stores only what the next stage reads (binning.cu).
 template <typename KeyT>
 struct StorePairs {
     KeyT* keys_out;
     int32_t* vals_out;
-    __device__ __forceinline__ void operator()(bool active, unsigned pos, KeyT key, int32_t val, uint32_t /*val2*/) const {
+    __device__ __forceinline__ void operator()(bool active, unsigned pos, KeyT key, int32_t val) const {
         if (active) {
             keys_out[pos] = key;
             vals_out[pos] = val;
         }
     }
 };
-template <typename KeyT>
-struct StoreTriples {
-    KeyT* keys_out;
-    int32_t* vals_out;
-    uint32_t* vals2_out;
-    __device__ __forceinline__ void operator()(bool active, unsigned pos, KeyT key, int32_t val, uint32_t val2) const {
-        if (active) {
-            keys_out[pos] = key;
-            vals_out[pos] = val;
-            vals2_out[pos] = val2;
-        }
-    }
-};
-// Where the second payload of an element comes from: nowhere (pairs), the previous pass's array, or -- in the first pass,
-// where the elements are still in their original, coalesced order -- a functor of the caller that derives it from the value.
-struct NoVal2 {
-    __device__ __forceinline__ uint32_t operator()(unsigned /*g*/, int32_t /*val*/) const { return 0u; }
-};
-struct LoadVal2 {
-    const uint32_t* vals2_in;
-    __device__ __forceinline__ uint32_t operator()(unsigned g, int32_t /*val*/) const { return vals2_in[g]; }
+// A hook of the FIRST pass, whose elements are still in their original order (coalesced loads): the depth sort uses it to
+// derive each row's tile rectangle on the way (binning.cu).  (Tried, round 2: carrying the rectangle through the passes as
+// a second 32-bit payload instead of gathering it afterwards -- +19 us per pass for 5.8 M rows, register spills included:
+// as expensive as the gather it removes, profiles/r02_variants_c15.txt.)
+struct NoSide {
+    __device__ __forceinline__ void operator()(unsigned /*g*/, int32_t /*val*/) const {}
 };
 
 // Ranking inside a warp (A/B on config 3, profiles/r02_variants_c15.txt: depth sort 0.393 / 0.346 / 0.399 ms, bin pass alike):
@@ -156,9 +138,9 @@ struct LoadVal2 {
 #define B2S_RADIX_RANK 1
 #endif
 
-template <typename KeyT, typename StatusT, bool TWO, typename Ld2, typename Epi>
+template <typename KeyT, typename StatusT, typename Side, typename Epi>
 __global__ void __launch_bounds__(THREADS, B2S_RADIX_MINBLOCKS) onesweep_kernel(unsigned n, const KeyT* __restrict__ keys_in,
-                                                              const int32_t* __restrict__ vals_in, const Ld2 ld2, const Epi epi,
+                                                              const int32_t* __restrict__ vals_in, const Side side, const Epi epi,
                                                               int shift, unsigned mask,
                                                               const unsigned long long* __restrict__ digit_base /* [256] */,
                                                               StatusT* status /* [tiles][256] */, unsigned int* tile_counter) {
@@ -172,7 +154,6 @@ __global__ void __launch_bounds__(THREADS, B2S_RADIX_MINBLOCKS) onesweep_kernel(
     __shared__ int32_t s_vals[TILE];
     __shared__ unsigned s_wsum[WARPS];
     __shared__ unsigned int s_tile;
-    extern __shared__ uint32_t s_vals2[];                // TWO: [TILE], dynamic (static + dynamic exceed 48 KB)
 #if B2S_RADIX_RANK == 1
     static_assert(4 * TILE >= (size_t)WARPS * RADIX * 4, "mask arrays alias the reorder buffers");
     unsigned* s_mask0 = reinterpret_cast<unsigned*>(s_keys);     // [WARPS][RADIX], dead before the reorder starts
@@ -197,17 +178,14 @@ __global__ void __launch_bounds__(THREADS, B2S_RADIX_MINBLOCKS) onesweep_kernel(
 
     KeyT key[ITEMS];
     int32_t val[ITEMS];
-    uint32_t val2[TWO ? ITEMS : 1];
     unsigned dig[ITEMS];
     if (full) {
 #pragma unroll
         for (int i = 0; i < ITEMS; ++i) key[i] = keys_in[warp_base + i * 32];
 #pragma unroll
         for (int i = 0; i < ITEMS; ++i) val[i] = vals_in[warp_base + i * 32];
-        if (TWO) {
 #pragma unroll
-            for (int i = 0; i < ITEMS; ++i) val2[TWO ? i : 0] = ld2(warp_base + i * 32, val[i]);
-        }
+        for (int i = 0; i < ITEMS; ++i) side(warp_base + i * 32, val[i]);
 #pragma unroll
         for (int i = 0; i < ITEMS; ++i) dig[i] = digit_of(key[i], shift, mask);
     } else {
@@ -217,7 +195,7 @@ __global__ void __launch_bounds__(THREADS, B2S_RADIX_MINBLOCKS) onesweep_kernel(
             const bool ok = g < n;
             key[i] = ok ? keys_in[g] : (KeyT)0;
             val[i] = ok ? vals_in[g] : 0;
-            if (TWO) val2[TWO ? i : 0] = ok ? ld2(g, val[i]) : 0u;
+            if (ok) side(g, val[i]);
             dig[i] = ok ? digit_of(key[i], shift, mask) : (unsigned)RADIX;   // out-of-range lanes share the dump bin
         }
     }
@@ -349,7 +327,6 @@ __global__ void __launch_bounds__(THREADS, B2S_RADIX_MINBLOCKS) onesweep_kernel(
             const unsigned p = s_cta_start[dig[i]] + s_warp_hist[warp * HS + dig[i]] + rank[i];
             s_keys[p] = key[i];
             s_vals[p] = val[i];
-            if (TWO) s_vals2[p] = val2[TWO ? i : 0];
         }
     }
     __syncthreads();
@@ -357,7 +334,7 @@ __global__ void __launch_bounds__(THREADS, B2S_RADIX_MINBLOCKS) onesweep_kernel(
     for (unsigned p = threadIdx.x; p - threadIdx.x < tile_count; p += THREADS) {     // whole warps: the epilogue may vote
         const KeyT k = s_keys[p];
         const unsigned pos = s_off[digit_of(k, shift, mask)] + p;
-        epi(p < tile_count, pos, k, s_vals[p], TWO ? s_vals2[p] : 0u);
+        epi(p < tile_count, pos, k, s_vals[p]);
     }
 }
 
@@ -385,35 +362,21 @@ static inline unsigned long long* hist_ptr(void* workspace, int64_t n) {
     return reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(workspace) + 2 * up256((size_t)n * sizeof(KeyT)) +
                                                  2 * up256((size_t)n * 4));
 }
-// workspace of a sort that carries a second 32-bit payload: the plain one + two temp arrays for it
-template <typename KeyT>
-static inline size_t workspace_bytes2(int64_t n) { return up256(workspace_bytes<KeyT>(n)) + 2 * up256((size_t)n * 4); }
-
-template <typename KeyT, typename StatusT, bool TWO, typename Ld2, typename Epi>
-static inline cudaError_t launch_pass(int64_t tiles, unsigned n, const KeyT* k, const int32_t* v, const Ld2& ld2, const Epi& epi,
+template <typename KeyT, typename StatusT, typename Side, typename Epi>
+static inline cudaError_t launch_pass(int64_t tiles, unsigned n, const KeyT* k, const int32_t* v, const Side& side, const Epi& epi,
                                       int shift, unsigned mask, const unsigned long long* base, void* status, unsigned int* counter,
                                       cudaStream_t st) {
-    auto kern = onesweep_kernel<KeyT, StatusT, TWO, Ld2, Epi>;
-    constexpr size_t dyn = TWO ? (size_t)THREADS * Cfg<KeyT>::ITEMS * 4 : 0;
-    if (TWO) {
-        static bool configured = false;        // per instantiation; the attribute is idempotent, so a race only repeats it
-        if (!configured) {
-            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
-            if (e != cudaSuccess) return e;
-            configured = true;
-        }
-    }
-    kern<<<(unsigned)tiles, THREADS, dyn, st>>>(n, k, v, ld2, epi, shift, mask, base, reinterpret_cast<StatusT*>(status), counter);
+    onesweep_kernel<KeyT, StatusT, Side, Epi><<<(unsigned)tiles, THREADS, 0, st>>>(n, k, v, side, epi, shift, mask, base,
+                                                                                  reinterpret_cast<StatusT*>(status), counter);
     return cudaGetLastError();
 }
 
 // Sorts bits [0, key_bits) ascending, stable.  keys_in/vals_in are not modified.  Every pass but the last stores its
 // output into the workspace; the last pass hands each element with its final position to `last` (StorePairs = the plain
-// sort).  hist_ready: the workspace histograms already hold the digit counts of `make_plan(key_bits)`.
-// TWO: a second 32-bit payload rides along; `first` produces it in the first pass (elements still in input order), the
-// workspace is workspace_bytes2.
-template <typename KeyT, bool TWO, typename Ld2, typename Epi>
-static int sort_ex(int64_t n, int key_bits, const KeyT* keys_in, const int32_t* vals_in, const Ld2& first, const Epi& last,
+// sort); `first` sees every element of the first pass (NoSide = nothing).  hist_ready: the workspace histograms already
+// hold the digit counts of `make_plan(key_bits)`.
+template <typename KeyT, typename Side, typename Epi>
+static int sort_ex(int64_t n, int key_bits, const KeyT* keys_in, const int32_t* vals_in, const Side& first, const Epi& last,
                    bool hist_ready, void* workspace, cudaStream_t st) {
     if (n <= 0) return 0;
     if (n >= 2147483647LL) {
@@ -430,7 +393,6 @@ static int sort_ex(int64_t n, int key_bits, const KeyT* keys_in, const int32_t* 
     char* w = reinterpret_cast<char*>(workspace);
     KeyT* tk[2];
     int32_t* tv[2];
-    uint32_t* tv2[2] = {nullptr, nullptr};
     tk[0] = reinterpret_cast<KeyT*>(w); w += up256((size_t)n * sizeof(KeyT));
     tk[1] = reinterpret_cast<KeyT*>(w); w += up256((size_t)n * sizeof(KeyT));
     tv[0] = reinterpret_cast<int32_t*>(w); w += up256((size_t)n * 4);
@@ -440,11 +402,6 @@ static int sort_ex(int64_t n, int key_bits, const KeyT* keys_in, const int32_t* 
     const int64_t tiles = tiles_of<KeyT>(n);
     w += up256((size_t)tiles * RADIX * 8);
     unsigned int* counters = reinterpret_cast<unsigned int*>(w);
-    if (TWO) {
-        w = reinterpret_cast<char*>(workspace) + up256(workspace_bytes<KeyT>(n));
-        tv2[0] = reinterpret_cast<uint32_t*>(w); w += up256((size_t)n * 4);
-        tv2[1] = reinterpret_cast<uint32_t*>(w);
-    }
 
     if (!hist_ready) {
         B2S_CUDA(cudaMemsetAsync(hist, 0, (size_t)MAXP * RADIX * 8, st));
@@ -455,32 +412,27 @@ static int sort_ex(int64_t n, int key_bits, const KeyT* keys_in, const int32_t* 
     B2S_CUDA(cudaMemsetAsync(counters, 0, (size_t)MAXP * 4, st));
     scan_hist_kernel<<<passes, RADIX, 0, st>>>(hist);
     B2S_LAUNCH_CHECK();
-    using Mid = typename std::conditional<TWO, StoreTriples<KeyT>, StorePairs<KeyT>>::type;
-    using Ld = typename std::conditional<TWO, LoadVal2, NoVal2>::type;
+    using Mid = StorePairs<KeyT>;
     const KeyT* src_k = keys_in;
     const int32_t* src_v = vals_in;
-    const uint32_t* src_v2 = nullptr;
     const bool small = n < (1LL << 30);
     for (int p = 0; p < passes; ++p) {
         B2S_CUDA(cudaMemsetAsync(status, 0, (size_t)tiles * RADIX * (small ? 4 : 8), st));
         const unsigned mask = (1u << pl.bits[p]) - 1u;
         const unsigned long long* base = hist + (size_t)p * RADIX;
         const bool is_first = p == 0, is_last = p == passes - 1;
-        Mid mid;
-        if constexpr (TWO) mid = Mid{tk[p & 1], tv[p & 1], tv2[p & 1]};
-        else mid = Mid{tk[p & 1], tv[p & 1]};
-        Ld ld;
-        if constexpr (TWO) ld = Ld{src_v2};
+        const Mid mid{tk[p & 1], tv[p & 1]};
+        const NoSide none{};
         cudaError_t e;
-#define B2S_PASS(LD, EPI, ld_, epi_)                                                                                              \
-    (small ? launch_pass<KeyT, unsigned, TWO, LD, EPI>(tiles, (unsigned)n, src_k, src_v, ld_, epi_, pl.shift[p], mask, base, status, \
-                                                       counters + p, st)                                                          \
-           : launch_pass<KeyT, unsigned long long, TWO, LD, EPI>(tiles, (unsigned)n, src_k, src_v, ld_, epi_, pl.shift[p], mask,   \
-                                                                 base, status, counters + p, st))
-        if (is_first && is_last) e = B2S_PASS(Ld2, Epi, first, last);
-        else if (is_first) e = B2S_PASS(Ld2, Mid, first, mid);
-        else if (is_last) e = B2S_PASS(Ld, Epi, ld, last);
-        else e = B2S_PASS(Ld, Mid, ld, mid);
+#define B2S_PASS(SIDE, EPI, side_, epi_)                                                                                           \
+    (small ? launch_pass<KeyT, unsigned, SIDE, EPI>(tiles, (unsigned)n, src_k, src_v, side_, epi_, pl.shift[p], mask, base, status, \
+                                                    counters + p, st)                                                             \
+           : launch_pass<KeyT, unsigned long long, SIDE, EPI>(tiles, (unsigned)n, src_k, src_v, side_, epi_, pl.shift[p], mask,    \
+                                                              base, status, counters + p, st))
+        if (is_first && is_last) e = B2S_PASS(Side, Epi, first, last);
+        else if (is_first) e = B2S_PASS(Side, Mid, first, mid);
+        else if (is_last) e = B2S_PASS(NoSide, Epi, none, last);
+        else e = B2S_PASS(NoSide, Mid, none, mid);
 #undef B2S_PASS
         if (e != cudaSuccess) {
             set_error("radix::sort: digit pass %d -> %s", p, cudaGetErrorString(e));
@@ -488,7 +440,6 @@ static int sort_ex(int64_t n, int key_bits, const KeyT* keys_in, const int32_t* 
         }
         src_k = tk[p & 1];
         src_v = tv[p & 1];
-        src_v2 = tv2[p & 1];
     }
     return 0;
 }
@@ -496,7 +447,7 @@ static int sort_ex(int64_t n, int key_bits, const KeyT* keys_in, const int32_t* 
 template <typename KeyT, typename Epi>
 static int sort_pairs_ex(int64_t n, int key_bits, const KeyT* keys_in, const int32_t* vals_in, const Epi& last, bool hist_ready,
                          void* workspace, cudaStream_t st) {
-    return sort_ex<KeyT, false, NoVal2, Epi>(n, key_bits, keys_in, vals_in, NoVal2{}, last, hist_ready, workspace, st);
+    return sort_ex<KeyT, NoSide, Epi>(n, key_bits, keys_in, vals_in, NoSide{}, last, hist_ready, workspace, st);
 }
 
 template <typename KeyT>
