@@ -247,8 +247,8 @@ B2S_API int b2s_coarse_bin(int64_t M, int64_t N, const int64_t* camera_ids /* or
 
 /* The same binning with half the gather and four launches fewer (what `rasterization()` runs; the pair above is kept
  * as the unfused reference and for A/B, B2S_BINNING_FUSED=0, and serves tile grids beyond 255 x 255):
- *   b2s_depth_order_rects : b2s_depth_order whose FIRST radix pass -- its elements are still in row order, so the loads
- *                           coalesce -- also derives every row's tile rectangle and stores it BY ROW, packed into 32 bits:
+ *   b2s_depth_order_rects : b2s_depth_order whose histogram kernel -- a streaming pass over the rows in row order, so the
+ *                           loads coalesce -- also derives every row's tile rectangle and stores it BY ROW, packed into 32 bits:
  *                           rects [M] = x0 | x1 << 8 | y0 << 16 | y1 << 24 (tile units, rows clipped to the window, 0 on
  *                           culled rows; every row id in row_ids must be < M); the last pass stores sorted_ids [M] and
  *                           never writes the sorted keys.  Needs nothing the host has to wait for, so it too is

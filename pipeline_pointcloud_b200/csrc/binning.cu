@@ -609,18 +609,19 @@ __global__ void __launch_bounds__(EXP_THREADS) coarse_emit_kernel(int64_t M, int
 
 // ---- fused path (b2s_depth_order_rects + b2s_coarse_bin_rects) ------------------------------------------------------
 // coarse_rects_kernel above is a pass of dependent gathers (sorted id -> radius, mean: two 32-byte sectors per row, DRAM
-// bound at ~65 us for 5.8 M rows wherever it runs -- fused into the sort's last pass it cost the same).  Here the FIRST pass
-// of the depth sort, whose elements are still in row order, derives every row's tile rectangle from coalesced loads and
+// bound at ~65 us for 5.8 M rows wherever it runs -- fused into the sort's last pass it cost the same).  Here the histogram
+// kernel of the depth sort, which streams the rows in row order, derives every row's tile rectangle from coalesced loads and
 // stores it, packed into 32 bits, by row (x0 | x1 << 8 | y0 << 16 | y1 << 24 in tile units: grids up to 255 x 255 tiles,
 // i.e. 4080 x 4080 pixels); the expansion then gathers ONE 4-byte word per depth-ordered row.  The last pass does not
 // write the sorted keys, which nobody reads.
 struct RectSide {
+    static constexpr bool kActive = true;
     const float2* means2d;
     const int32_t* radii;
     float tile_size, inv_tile;       // inv_tile > 0: tile_size is a power of two and x / tile_size == x * inv_tile exactly
     int tile_w, row_lo, row_hi;
     uint32_t* rects;                 // [M], by row
-    __device__ __forceinline__ void operator()(unsigned /*g*/, int32_t id) const {
+    __device__ __forceinline__ void operator()(int64_t /*i*/, int32_t id) const {
         const int r = __ldg(radii + id);
         const float2 m = __ldg(means2d + id);
         int x0 = 0, y0 = 0, x1 = 0, y1 = 0;

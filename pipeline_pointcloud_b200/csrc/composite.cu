@@ -136,6 +136,30 @@ __device__ __forceinline__ bool box_hits(const float4& box, const WarpBlock& b) 
 // keeps a value in a register: without it ptxas rematerialises the pixel centre from %ctaid/%tid
 // inside the hot loop (14 extra instructions per Gaussian)
 __device__ __forceinline__ void pin(float& v) { asm volatile("" : "+f"(v)); }
+// The staged splats live in ONE shared-memory block addressed from a pinned 32-bit shared-window base: ptxas otherwise
+// rebuilds the window address of every array (S2R SR_CgaCtaId + MOV + LEA) inside the hot loop to stay under the register
+// cap -- 12 of the forward's 56 instructions per (warp, splat) pair (profiles/r02_ncu_full_summary.md).
+template <int CH>
+struct __align__(16) Staged {
+    float4 rec0[CTA];
+    float4 rec1[CTA];
+    float4 box[CTA];
+    float col[CTA * CH];
+};
+constexpr int ST_REC1 = CTA * 16, ST_BOX = 2 * CTA * 16, ST_COL = 3 * CTA * 16;   // byte offsets inside Staged
+__device__ __forceinline__ void pin_u32(uint32_t& v) { asm volatile("" : "+r"(v)); }
+template <int OFF>
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4+%5];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr), "n"(OFF));
+    return v;
+}
+template <int OFF>
+__device__ __forceinline__ float lds32(uint32_t addr) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1+%2];" : "=f"(v) : "r"(addr), "n"(OFF));
+    return v;
+}
 __device__ __forceinline__ float ex2_approx(float x) {
     float r;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
@@ -181,12 +205,15 @@ __device__ __forceinline__ void stage_splat(int g, const float* __restrict__ mea
 #endif
 template <int CH, bool BINS>
 __global__ void __launch_bounds__(CTA, B2S_COMP_MINBLOCKS) composite_fwd_kernel(const b2s_composite_fwd_args a, float* __restrict__ final_T) {
-    __shared__ float4 s_rec0[CTA];
-    __shared__ float4 s_rec1[CTA];
-    __shared__ float4 s_box[CTA];
-    __shared__ float s_col[CTA * CH];
+    __shared__ Staged<CH> s_st;
     __shared__ int2 s_q[BINS ? QRING : 1];
     __shared__ int s_wtot[2][CTA / 32];
+    float4* const s_rec0 = s_st.rec0;
+    float4* const s_rec1 = s_st.rec1;
+    float4* const s_box = s_st.box;
+    float* const s_col = s_st.col;
+    uint32_t sbase = (uint32_t)__cvta_generic_to_shared(&s_st);
+    pin_u32(sbase);
 
     // blockIdx.y counts from the first tile row of the launch's window (a tile stripe of a multi-GPU job, or the whole grid);
     // tile ids, bin keys and pixel centres are those of the whole image, the output tensors hold the window's rows only
@@ -210,12 +237,13 @@ __global__ void __launch_bounds__(CTA, B2S_COMP_MINBLOCKS) composite_fwd_kernel(
         hi = (tile_id == n_tiles_total - 1) ? (int)a.n_isects : a.isect_offsets[tile_id + 1];
     }
 
-    float T = 1.f;
+    // A pixel that is done (saturated: stopped at T_next <= 1e-4; or outside the image) carries its transmittance NEGATED:
+    // one sign test replaces a flag register in the hot loop, and -T is exactly what final_T stores for a saturated pixel.
+    float T = pm.inside ? 1.f : -1.f;
     float acc[CH];
 #pragma unroll
     for (int k = 0; k < CH; ++k) acc[k] = 0.f;
     int last = 0;
-    bool done = !pm.inside;
 
     // One batch of `bs` staged splats.  32 splats at a time, each lane tests one splat's box against the warp's pixel
     // block; only the survivors are evaluated per pixel.  `last` records s_rec1[j].w (BINS: the record position) or
@@ -227,23 +255,41 @@ __global__ void __launch_bounds__(CTA, B2S_COMP_MINBLOCKS) composite_fwd_kernel(
             while (m) {
                 const int j = j0 + __ffs(m) - 1;
                 m &= m - 1;
-                if (done) continue;
-                const float4 r0 = s_rec0[j];
-                const float4 r1 = s_rec1[j];
-                const float dx = r0.x - px, dy = r0.y - py;
-                const float s2 = fmaf(dx, fmaf(r1.x, dx, r1.y * dy), r1.z * dy * dy);
-                if (s2 < 0.f || s2 > r0.w) continue;
-                const float alpha = fminf(ALPHA_MAX, r0.z * ex2_approx(-s2));
-                if (alpha < ALPHA_MIN) continue;
-                const float nT = T * (1.f - alpha);
-                if (nT <= T_STOP) { done = true; continue; }
-                const float w = alpha * T;
+                if (T > 0.f) {
+                    const uint32_t sa = sbase + (uint32_t)j * 16u;
+                    const float4 r0 = lds128<0>(sa);
+                    const float4 r1 = lds128<ST_REC1>(sa);
+                    const float dx = r0.x - px, dy = r0.y - py;
+                    const float s2 = fmaf(dx, fmaf(r1.x, dx, r1.y * dy), r1.z * dy * dy);
+                    if (!(s2 < 0.f || s2 > r0.w)) {
+                        const float alpha = fminf(ALPHA_MAX, r0.z * ex2_approx(-s2));
+                        if (!(alpha < ALPHA_MIN)) {
+                            const float nT = T * (1.f - alpha);
+                            if (nT <= T_STOP) {
+                                T = -T;
+                            } else {
+                                const float w = alpha * T;
+                                const uint32_t sc = sbase + (uint32_t)j * (4u * CH);
+                                if constexpr (CH % 4 == 0) {
 #pragma unroll
-                for (int k = 0; k < CH; ++k) acc[k] = fmaf(w, s_col[j * CH + k], acc[k]);
-                T = nT;
-                last = BINS ? __float_as_int(r1.w) : start + j;
+                                    for (int k = 0; k < CH; k += 4) {
+                                        const float4 c4 = k == 0 ? lds128<ST_COL>(sc) : lds128<ST_COL>(sc + 4u * k);
+                                        acc[k] = fmaf(w, c4.x, acc[k]); acc[k + 1] = fmaf(w, c4.y, acc[k + 1]);
+                                        acc[k + 2] = fmaf(w, c4.z, acc[k + 2]); acc[k + 3] = fmaf(w, c4.w, acc[k + 3]);
+                                    }
+                                } else {
+#pragma unroll
+                                    for (int k = 0; k < CH; ++k)
+                                        acc[k] = fmaf(w, k == 0 ? lds32<ST_COL>(sc) : lds32<ST_COL>(sc + 4u * k), acc[k]);
+                                }
+                                T = nT;
+                                last = BINS ? __float_as_int(r1.w) : start + j;
+                            }
+                        }
+                    }
+                }
             }
-            if (__all_sync(FULL, done)) break;
+            if (__all_sync(FULL, !(T > 0.f))) break;
         }
     };
 
@@ -252,7 +298,7 @@ __global__ void __launch_bounds__(CTA, B2S_COMP_MINBLOCKS) composite_fwd_kernel(
         int pos = lo & ~3;                       // next window of the coarse bin's list (4-aligned)
         int qhead = 0, qcount = 0, round = 0;
         while (true) {
-            if (__syncthreads_count(done) == CTA) break;   // also fences the previous batch's smem reads
+            if (__syncthreads_count(!(T > 0.f)) == CTA) break;   // also fences the previous batch's smem reads
             bool scanned = false;
             while (qcount < CTA && pos < hi) {
                 qcount += scan_round<false>(a.bin_recs, a.bin_ids, pos, lo, hi, lx, ly, s_q, qhead + qcount, s_wtot[round & 1]);
@@ -277,13 +323,13 @@ __global__ void __launch_bounds__(CTA, B2S_COMP_MINBLOCKS) composite_fwd_kernel(
             __syncthreads();
             qhead += bs;
             qcount -= bs;
-            if (__all_sync(FULL, done)) continue;          // early termination by warp vote
+            if (__all_sync(FULL, !(T > 0.f))) continue;          // early termination by warp vote
             composite_batch(bs, 0);
         }
     } else {
         const int nb = (hi - lo + CTA - 1) / CTA;
         for (int b = 0; b < nb; ++b) {
-            if (__syncthreads_count(done) == CTA) break;  // also fences the previous batch's smem reads
+            if (__syncthreads_count(!(T > 0.f)) == CTA) break;  // also fences the previous batch's smem reads
             const int start = lo + b * CTA;
             const int idx = start + threadIdx.x;
             if (idx < hi) {
@@ -297,7 +343,7 @@ __global__ void __launch_bounds__(CTA, B2S_COMP_MINBLOCKS) composite_fwd_kernel(
                 for (int k = 0; k < CH; ++k) s_col[threadIdx.x * CH + k] = a.colors[(int64_t)g * CH + k];
             }
             __syncthreads();
-            if (__all_sync(FULL, done)) continue;  // early termination by warp vote
+            if (__all_sync(FULL, !(T > 0.f))) continue;  // early termination by warp vote
             composite_batch(min(CTA, hi - start), start);
         }
     }
@@ -305,10 +351,10 @@ __global__ void __launch_bounds__(CTA, B2S_COMP_MINBLOCKS) composite_fwd_kernel(
         const int64_t pix = ((int64_t)cam * out_h + (pm.py - out_y0)) * a.width + pm.px;
 #pragma unroll
         for (int k = 0; k < CH; ++k)
-            a.render_colors[pix * CH + k] = a.backgrounds ? acc[k] + T * a.backgrounds[cam * CH + k] : acc[k];
-        a.render_alphas[pix] = 1.f - T;
+            a.render_colors[pix * CH + k] = a.backgrounds ? acc[k] + fabsf(T) * a.backgrounds[cam * CH + k] : acc[k];
+        a.render_alphas[pix] = 1.f - fabsf(T);
         a.last_ids[pix] = last;
-        if (final_T) final_T[pix] = done ? -T : T;    // sign bit = the pixel saturated (stopped at T_next <= 1e-4)
+        if (final_T) final_T[pix] = T;               // sign bit = the pixel saturated (stopped at T_next <= 1e-4)
     }
 }
 
@@ -358,10 +404,13 @@ __device__ __forceinline__ int halving_slot(int lane, bool& owner) {
 template <int CH, bool ABS, bool BINS>
 __global__ void __launch_bounds__(CTA, B2S_COMP_MINBLOCKS) composite_bwd_kernel(const b2s_composite_bwd_args a, const float* __restrict__ final_T) {
     constexpr int V = CH + 6 + (ABS ? 2 : 0);   // values reduced per (warp, Gaussian)
-    __shared__ float4 s_rec0[CTA];
-    __shared__ float4 s_rec1[CTA];
-    __shared__ float4 s_box[CTA];
-    __shared__ float s_col[CTA * CH];
+    __shared__ Staged<CH> s_st;
+    float4* const s_rec0 = s_st.rec0;
+    float4* const s_rec1 = s_st.rec1;
+    float4* const s_box = s_st.box;
+    float* const s_col = s_st.col;
+    uint32_t sbase = (uint32_t)__cvta_generic_to_shared(&s_st);
+    pin_u32(sbase);
     __shared__ int s_pos[BINS ? CTA : 1];       // BINS: list position of each staged splat (descending)
     __shared__ int2 s_q[BINS ? QRING : 1];
     __shared__ int s_wtot[2][CTA / 32];
@@ -441,8 +490,9 @@ __global__ void __launch_bounds__(CTA, B2S_COMP_MINBLOCKS) composite_bwd_kernel(
 
     // One staged splat (smem slot t) against this thread's pixel; `mine` = the pixel takes part in it.
     auto splat_bwd = [&](int t, bool mine) {
-        const float4 r0 = s_rec0[t];
-        const float4 r1 = s_rec1[t];
+        const uint32_t sa = sbase + (uint32_t)t * 16u;
+        const float4 r0 = lds128<0>(sa);
+        const float4 r1 = lds128<ST_REC1>(sa);
         const float dx = r0.x - px, dy = r0.y - py;
         const float s2 = fmaf(dx, fmaf(r1.x, dx, r1.y * dy), r1.z * dy * dy);
         // invalid lanes run the same straight-line code with alpha = 0, vis = 0: every term vanishes
@@ -459,9 +509,10 @@ __global__ void __launch_bounds__(CTA, B2S_COMP_MINBLOCKS) composite_bwd_kernel(
         const float fac = alpha * T;
         float v_alpha = v_T_final * ra;
         float v_col[CH];
+        const uint32_t sc = sbase + (uint32_t)t * (4u * CH);
 #pragma unroll
         for (int k = 0; k < CH; ++k) {
-            const float c = s_col[t * CH + k];
+            const float c = k == 0 ? lds32<ST_COL>(sc) : lds32<ST_COL>(sc + 4u * k);
             v_col[k] = fac * v_out[k];
             v_alpha = fmaf(fmaf(c, T, -S[k] * ra), v_out[k], v_alpha);
             S[k] = fmaf(c, fac, S[k]);

@@ -57,8 +57,19 @@ static inline Plan make_plan(int key_bits) {
 }
 
 // ---- histogram of every digit position in one pass over the keys ------------------------------------------
-template <typename KeyT, int MAX_PASSES>
-__global__ void __launch_bounds__(THREADS) hist_kernel(int64_t n, const KeyT* __restrict__ keys, const Plan pl,
+// A hook that sees every (index, value) of the input once, in input order, from the histogram kernel -- a streaming pass at
+// full occupancy whose time goes to shared-memory atomics, so independent coalesced loads and stores ride along for free.
+// The depth sort uses it to derive each row's tile rectangle on the way (binning.cu).  (Tried, round 2: the same hook inside
+// the first digit pass -- +71 us there, the pass is latency bound at 35 % occupancy; and carrying the rectangle through the
+// passes as a second 32-bit payload -- +19 us per pass, register spills included: profiles/r02_variants_c15.txt.)
+struct NoSide {
+    static constexpr bool kActive = false;
+    __device__ __forceinline__ void operator()(int64_t /*i*/, int32_t /*val*/) const {}
+};
+
+template <typename KeyT, int MAX_PASSES, typename Side>
+__global__ void __launch_bounds__(THREADS) hist_kernel(int64_t n, const KeyT* __restrict__ keys, const int32_t* __restrict__ vals,
+                                                       const Side side, const Plan pl,
                                                        unsigned long long* __restrict__ hist /* [passes][256] */) {
     const int passes = pl.passes;
     __shared__ unsigned s_hist[MAX_PASSES * RADIX];
@@ -66,6 +77,7 @@ __global__ void __launch_bounds__(THREADS) hist_kernel(int64_t n, const KeyT* __
     __syncthreads();
     for (int64_t i = (int64_t)blockIdx.x * THREADS + threadIdx.x; i < n; i += (int64_t)gridDim.x * THREADS) {
         const KeyT k = keys[i];
+        if (Side::kActive) side(i, vals[i]);
 #pragma unroll
         for (int p = 0; p < MAX_PASSES; ++p)
             if (p < passes) atomicAdd(&s_hist[p * RADIX + digit_of(k, pl.shift[p], (1u << pl.bits[p]) - 1u)], 1u);
@@ -120,14 +132,6 @@ struct StorePairs {
         }
     }
 };
-// A hook of the FIRST pass, whose elements are still in their original order (coalesced loads): the depth sort uses it to
-// derive each row's tile rectangle on the way (binning.cu).  (Tried, round 2: carrying the rectangle through the passes as
-// a second 32-bit payload instead of gathering it afterwards -- +19 us per pass for 5.8 M rows, register spills included:
-// as expensive as the gather it removes, profiles/r02_variants_c15.txt.)
-struct NoSide {
-    __device__ __forceinline__ void operator()(unsigned /*g*/, int32_t /*val*/) const {}
-};
-
 // Ranking inside a warp (A/B on config 3, profiles/r02_variants_c15.txt: depth sort 0.393 / 0.346 / 0.399 ms, bin pass alike):
 //   0  `match.any` on the digit: its cost grows with the number of distinct digits in the warp (~28 of 32 on the uniform
 //      low digits; the concentrated top digit ran twice as fast, 41 vs 72-76 us)
@@ -138,9 +142,9 @@ struct NoSide {
 #define B2S_RADIX_RANK 1
 #endif
 
-template <typename KeyT, typename StatusT, typename Side, typename Epi>
+template <typename KeyT, typename StatusT, typename Epi>
 __global__ void __launch_bounds__(THREADS, B2S_RADIX_MINBLOCKS) onesweep_kernel(unsigned n, const KeyT* __restrict__ keys_in,
-                                                              const int32_t* __restrict__ vals_in, const Side side, const Epi epi,
+                                                              const int32_t* __restrict__ vals_in, const Epi epi,
                                                               int shift, unsigned mask,
                                                               const unsigned long long* __restrict__ digit_base /* [256] */,
                                                               StatusT* status /* [tiles][256] */, unsigned int* tile_counter) {
@@ -185,8 +189,6 @@ __global__ void __launch_bounds__(THREADS, B2S_RADIX_MINBLOCKS) onesweep_kernel(
 #pragma unroll
         for (int i = 0; i < ITEMS; ++i) val[i] = vals_in[warp_base + i * 32];
 #pragma unroll
-        for (int i = 0; i < ITEMS; ++i) side(warp_base + i * 32, val[i]);
-#pragma unroll
         for (int i = 0; i < ITEMS; ++i) dig[i] = digit_of(key[i], shift, mask);
     } else {
 #pragma unroll
@@ -195,7 +197,6 @@ __global__ void __launch_bounds__(THREADS, B2S_RADIX_MINBLOCKS) onesweep_kernel(
             const bool ok = g < n;
             key[i] = ok ? keys_in[g] : (KeyT)0;
             val[i] = ok ? vals_in[g] : 0;
-            if (ok) side(g, val[i]);
             dig[i] = ok ? digit_of(key[i], shift, mask) : (unsigned)RADIX;   // out-of-range lanes share the dump bin
         }
     }
@@ -362,21 +363,21 @@ static inline unsigned long long* hist_ptr(void* workspace, int64_t n) {
     return reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(workspace) + 2 * up256((size_t)n * sizeof(KeyT)) +
                                                  2 * up256((size_t)n * 4));
 }
-template <typename KeyT, typename StatusT, typename Side, typename Epi>
-static inline cudaError_t launch_pass(int64_t tiles, unsigned n, const KeyT* k, const int32_t* v, const Side& side, const Epi& epi,
-                                      int shift, unsigned mask, const unsigned long long* base, void* status, unsigned int* counter,
+template <typename KeyT, typename StatusT, typename Epi>
+static inline cudaError_t launch_pass(int64_t tiles, unsigned n, const KeyT* k, const int32_t* v, const Epi& epi, int shift,
+                                      unsigned mask, const unsigned long long* base, void* status, unsigned int* counter,
                                       cudaStream_t st) {
-    onesweep_kernel<KeyT, StatusT, Side, Epi><<<(unsigned)tiles, THREADS, 0, st>>>(n, k, v, side, epi, shift, mask, base,
-                                                                                  reinterpret_cast<StatusT*>(status), counter);
+    onesweep_kernel<KeyT, StatusT, Epi><<<(unsigned)tiles, THREADS, 0, st>>>(n, k, v, epi, shift, mask, base,
+                                                                            reinterpret_cast<StatusT*>(status), counter);
     return cudaGetLastError();
 }
 
 // Sorts bits [0, key_bits) ascending, stable.  keys_in/vals_in are not modified.  Every pass but the last stores its
 // output into the workspace; the last pass hands each element with its final position to `last` (StorePairs = the plain
-// sort); `first` sees every element of the first pass (NoSide = nothing).  hist_ready: the workspace histograms already
-// hold the digit counts of `make_plan(key_bits)`.
+// sort); `side` sees every input element once, from the histogram kernel (NoSide = nothing).  hist_ready: the workspace
+// histograms already hold the digit counts of `make_plan(key_bits)` (then `side` is not called).
 template <typename KeyT, typename Side, typename Epi>
-static int sort_ex(int64_t n, int key_bits, const KeyT* keys_in, const int32_t* vals_in, const Side& first, const Epi& last,
+static int sort_ex(int64_t n, int key_bits, const KeyT* keys_in, const int32_t* vals_in, const Side& side, const Epi& last,
                    bool hist_ready, void* workspace, cudaStream_t st) {
     if (n <= 0) return 0;
     if (n >= 2147483647LL) {
@@ -406,7 +407,7 @@ static int sort_ex(int64_t n, int key_bits, const KeyT* keys_in, const int32_t* 
     if (!hist_ready) {
         B2S_CUDA(cudaMemsetAsync(hist, 0, (size_t)MAXP * RADIX * 8, st));
         const int hist_grid = (int)min((int64_t)148 * 8, cdiv(n, THREADS));
-        hist_kernel<KeyT, MAXP><<<hist_grid, THREADS, 0, st>>>(n, keys_in, pl, hist);
+        hist_kernel<KeyT, MAXP, Side><<<hist_grid, THREADS, 0, st>>>(n, keys_in, vals_in, side, pl, hist);
         B2S_LAUNCH_CHECK();
     }
     B2S_CUDA(cudaMemsetAsync(counters, 0, (size_t)MAXP * 4, st));
@@ -420,19 +421,14 @@ static int sort_ex(int64_t n, int key_bits, const KeyT* keys_in, const int32_t* 
         B2S_CUDA(cudaMemsetAsync(status, 0, (size_t)tiles * RADIX * (small ? 4 : 8), st));
         const unsigned mask = (1u << pl.bits[p]) - 1u;
         const unsigned long long* base = hist + (size_t)p * RADIX;
-        const bool is_first = p == 0, is_last = p == passes - 1;
         const Mid mid{tk[p & 1], tv[p & 1]};
-        const NoSide none{};
         cudaError_t e;
-#define B2S_PASS(SIDE, EPI, side_, epi_)                                                                                           \
-    (small ? launch_pass<KeyT, unsigned, SIDE, EPI>(tiles, (unsigned)n, src_k, src_v, side_, epi_, pl.shift[p], mask, base, status, \
-                                                    counters + p, st)                                                             \
-           : launch_pass<KeyT, unsigned long long, SIDE, EPI>(tiles, (unsigned)n, src_k, src_v, side_, epi_, pl.shift[p], mask,    \
-                                                              base, status, counters + p, st))
-        if (is_first && is_last) e = B2S_PASS(Side, Epi, first, last);
-        else if (is_first) e = B2S_PASS(Side, Mid, first, mid);
-        else if (is_last) e = B2S_PASS(NoSide, Epi, none, last);
-        else e = B2S_PASS(NoSide, Mid, none, mid);
+#define B2S_PASS(EPI, epi_)                                                                                                      \
+    (small ? launch_pass<KeyT, unsigned, EPI>(tiles, (unsigned)n, src_k, src_v, epi_, pl.shift[p], mask, base, status, counters + p, st) \
+           : launch_pass<KeyT, unsigned long long, EPI>(tiles, (unsigned)n, src_k, src_v, epi_, pl.shift[p], mask, base, status,   \
+                                                        counters + p, st))
+        if (p == passes - 1) e = B2S_PASS(Epi, last);
+        else e = B2S_PASS(Mid, mid);
 #undef B2S_PASS
         if (e != cudaSuccess) {
             set_error("radix::sort: digit pass %d -> %s", p, cudaGetErrorString(e));

@@ -1,0 +1,21 @@
+#!/bin/bash
+# round 2, call 18 (1 GPU): rectangles from the depth sort's histogram kernel; compositing hot loops on a pinned shared-window
+# base, the forward's done flag folded into the sign of T -- full GPU suite, A/B, per-launch times
+mkdir -p gpurun_out/r2c18 && cd $GRAFT_REPO_ROOT
+O=gpurun_out/r2c18
+timeout 900 python -m pytest tests -m gpu -q -rs -x > $O/pytest_gpu.log 2>&1; echo "pytest rc=$?"; tail -4 $O/pytest_gpu.log
+B="python bench.py --gpus 1 --steps 50 --warmup 10 --no-extras --no-e2e --no-cpu-baseline"
+run() { name=$1; shift; env "$@" timeout 300 $B > $O/$name.json 2> $O/$name.err; echo "$name rc=$?"; }
+run fused
+run unfused B2S_BINNING_FUSED=0
+run fused2
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/launches.csv python bench.py --gpus 1 --steps 2 --warmup 3 --no-extras --no-e2e --no-cpu-baseline > $O/ncu.log 2>&1; echo "ncu rc=$?"
+python - <<'PY'
+import json
+for f in ("fused","unfused","fused2"):
+    try:
+        d=json.loads(open(f"gpurun_out/r2c18/{f}.json").read().strip().splitlines()[-1])
+        print(f, round(d["ms_per_step"],4), round(d["ms_median"],4), {k:v["ms"] for k,v in d["stages"].items()})
+    except Exception as e:
+        print(f, "ERR", e)
+PY
