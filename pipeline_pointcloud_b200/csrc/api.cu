@@ -15,11 +15,11 @@ void set_error(const char* fmt, ...) {
 
 namespace b2s {
 // streaming zero fill (128-bit stores that bypass L1): what a gradient buffer needs before sparse or atomic accumulation.
-// Deliberately THIN -- two 128-thread CTAs per SM, eight independent stores per thread and iteration: stores do not wait,
-// so four warps per SM keep HBM's write side busy, and when the fill runs on a second stream beside an issue-bound kernel
-// (the compositing forward) it takes almost none of that kernel's residency (a 256-thread, 4736-CTA fill took as long out
-// of compositing as it saved: profiles/r02_variants_c9.txt).
-__global__ void __launch_bounds__(128) zero_fill_kernel(float4* __restrict__ p, int64_t n4) {
+// Eight independent stores per thread and iteration; 32 CTAs of 256 threads per SM's worth of grid, the shape that writes
+// 6.4 TB/s in sh_zero_kernel.  (A deliberately thin variant -- two 128-thread CTAs per SM -- was built for running the
+// fill on a second stream beside compositing; every placement of that overlap measured as a net loss,
+// profiles/r02_variants_c9.txt, so the fill runs on the caller's stream.)
+__global__ void __launch_bounds__(256) zero_fill_kernel(float4* __restrict__ p, int64_t n4) {
     const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -41,8 +41,8 @@ extern "C" int b2s_zero_fill(void* p, int64_t bytes, b2s_stream_t stream) {
     if (head) B2S_CUDA(cudaMemsetAsync(c, 0, (size_t)head, st));
     const int64_t n4 = (bytes - head) / 16, tail = bytes - head - n4 * 16;
     if (n4) {
-        b2s::zero_fill_kernel<<<(unsigned)(n4 < 148 * 2 * 128 ? b2s::cdiv(n4, 128) : 148 * 2), 128, 0, st>>>(
-            reinterpret_cast<float4*>(c + head), n4);
+        const int64_t grid = b2s::cdiv(n4, 256 * 8);
+        b2s::zero_fill_kernel<<<(unsigned)(grid < 148 * 32 ? grid : 148 * 32), 256, 0, st>>>(reinterpret_cast<float4*>(c + head), n4);
         B2S_LAUNCH_CHECK();
     }
     if (tail) B2S_CUDA(cudaMemsetAsync(c + head + n4 * 16, 0, (size_t)tail, st));

@@ -663,7 +663,7 @@ __device__ __forceinline__ uint32_t coarse_record(int gx0, int gx1, int gy0, int
     return (my << 24) | (mx << 16) | (cam_base + (uint32_t)(by * bins_w + bx));
 }
 
-__global__ void __launch_bounds__(EXP_THREADS) coarse_emit_lb_kernel(int64_t M, int64_t N, const int64_t* __restrict__ camera_ids,
+__global__ void __launch_bounds__(EXP_THREADS, 5) coarse_emit_lb_kernel(int64_t M, int64_t N, const int64_t* __restrict__ camera_ids,
                                                                      const int32_t* __restrict__ sorted_ids,
                                                                      const uint32_t* __restrict__ rects, int bins_w, int bins_h,
                                                                      unsigned long long* status, unsigned int* cta_counter,
@@ -731,8 +731,8 @@ __global__ void __launch_bounds__(EXP_THREADS) coarse_emit_lb_kernel(int64_t M, 
 #pragma unroll
     for (int g = 0; g < EMIT_GROUPS; ++g) {
         const int gx0 = (int)(rc[g] & 0xFFu), gx1 = (int)((rc[g] >> 8) & 0xFFu), gy0 = (int)((rc[g] >> 16) & 0xFFu), gy1 = (int)(rc[g] >> 24);
-        uint32_t cam_base = 0u;
-        if (cnt[g] > 0) cam_base = (uint32_t)(camera_ids ? camera_ids[id[g]] : (id[g] / N)) * per_cam;
+        uint32_t cam_base = 0u;                                 // (32-bit division, and none at all with one camera)
+        if (cnt[g] > 0 && (camera_ids || M > N)) cam_base = (camera_ids ? (uint32_t)camera_ids[id[g]] : (uint32_t)id[g] / (uint32_t)N) * per_cam;
         const int bx0 = gx0 / CB, by0 = gy0 / CB, w = cnt[g] > 0 ? coarse_span(gx0, gx1) : 1;
         // small rows: each lane writes its own records
         if (cnt[g] <= EMIT_DIRECT) {

@@ -75,12 +75,28 @@ __global__ void __launch_bounds__(THREADS) hist_kernel(int64_t n, const KeyT* __
     __shared__ unsigned s_hist[MAX_PASSES * RADIX];
     for (int i = threadIdx.x; i < passes * RADIX; i += THREADS) s_hist[i] = 0;
     __syncthreads();
-    for (int64_t i = (int64_t)blockIdx.x * THREADS + threadIdx.x; i < n; i += (int64_t)gridDim.x * THREADS) {
-        const KeyT k = keys[i];
-        if (Side::kActive) side(i, vals[i]);
+    // four elements per thread and iteration: their loads (and the dependent loads of the hook) are in flight together
+    constexpr int U = 4;
+    const int64_t stride = (int64_t)gridDim.x * THREADS;
+    for (int64_t i0 = (int64_t)blockIdx.x * THREADS + threadIdx.x; i0 < n; i0 += U * stride) {
+        KeyT k[U];
+        int32_t v[U];
 #pragma unroll
-        for (int p = 0; p < MAX_PASSES; ++p)
-            if (p < passes) atomicAdd(&s_hist[p * RADIX + digit_of(k, pl.shift[p], (1u << pl.bits[p]) - 1u)], 1u);
+        for (int u = 0; u < U; ++u) {
+            const int64_t i = i0 + u * stride;
+            k[u] = i < n ? keys[i] : (KeyT)0;
+            v[u] = (Side::kActive && i < n) ? vals[i] : 0;
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+            if (Side::kActive && i0 + u * stride < n) side(i0 + u * stride, v[u]);
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            if (i0 + u * stride >= n) break;
+#pragma unroll
+            for (int p = 0; p < MAX_PASSES; ++p)
+                if (p < passes) atomicAdd(&s_hist[p * RADIX + digit_of(k[u], pl.shift[p], (1u << pl.bits[p]) - 1u)], 1u);
+        }
     }
     __syncthreads();
     for (int i = threadIdx.x; i < passes * RADIX; i += THREADS)

@@ -113,6 +113,15 @@ def _launch_fill(t: Tensor, holder: dict) -> None:
     holder["ev"] = ev1
 
 
+def zeros_f32(numel: int, dev) -> Tensor:
+    """fp32 zeros[numel] on the current stream, filled by the library's own streaming kernel (b2s_zero_fill)."""
+    t = torch.empty(max(int(numel), 1), dtype=torch.float32, device=dev)
+    check(L.lib().b2s_zero_fill(ptr(t), t.numel() * 4, L.stream_ptr(dev)), "b2s_zero_fill")
+    if TIMER is not None:
+        TIMER.launches += 1
+    return t[:numel]
+
+
 def prefill_zeros(numel: int, dev, defer: bool = False):
     """fp32 zeros[numel] filled on the side stream: returns (tensor, holder); ``holder["ev"]`` is the event that marks the
     fill done once it has been launched.  ``defer``: launch it with ``flush_prefills`` -- stage 1 creates its buffer
@@ -183,7 +192,7 @@ class _ProjectFused(torch.autograd.Function):
         tiles = torch.empty(C, N, dtype=torch.int32, **o) if tile_size else None
         dkeys = torch.empty(C, N, dtype=torch.int32, **o) if tile_size else None     # uint32 bit patterns
         rowids = torch.empty(C, N, dtype=torch.int32, **o) if tile_size else None
-        total = torch.zeros(32, 4, dtype=torch.int64, **o) if tile_size else None   # B2S_TOTAL_SLOTS x [tiles, visible rows, coarse records, -]
+        total = zeros_f32(32 * 4 * 2, dev).view(torch.int64).view(32, 4) if tile_size else None   # B2S_TOTAL_SLOTS x [tiles, visible rows, coarse records, -]
         tw = (width + tile_size - 1) // tile_size if tile_size else 0
         th = (height + tile_size - 1) // tile_size if tile_size else 0
         lib = L.lib()
@@ -604,6 +613,26 @@ class LazyMeta(dict):
         return super().__len__() + len(self._lazy)
 
 
+def _async_to_host(t: Tensor):
+    """Copies a small device tensor to pinned host memory on the side stream, behind everything enqueued on the current
+    stream so far; returns (host tensor, event to ``synchronize()`` before reading it)."""
+    dev = t.device
+    main = torch.cuda.current_stream(dev)
+    side = _SIDE_STREAMS.get(dev.index)
+    if side is None:
+        side = _SIDE_STREAMS[dev.index] = torch.cuda.Stream(dev)
+    produced = torch.cuda.Event()
+    produced.record(main)
+    host = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)     # the pinned caching allocator: no cudaHostAlloc per call
+    with torch.cuda.stream(side):
+        side.wait_event(produced)
+        host.copy_(t, non_blocking=True)
+        done = torch.cuda.Event()
+        done.record(side)
+    t.record_stream(side)
+    return host, done
+
+
 def _ws(nbytes: int, dev) -> Tensor:
     return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=dev)   # torch allocations are 512-B aligned
 
@@ -723,6 +752,14 @@ def bin_coarse(means2d: Tensor, radii: Tensor, depths: Tensor, tile_size: int, t
         with _stage("coarse_count"):
             check(lib.b2s_coarse_count(M, ptr(means2d), ptr(radii), tile_size, tile_width, tile_height, ptr(tot),
                                        L.tile_rows(tile_rows), st), "b2s_coarse_count")
+    # The one host sync of a forward (the counts size the record buffers).  The counts are complete as soon as stage 1 is:
+    # they are copied to pinned host memory on a second stream NOW, the depth sort is enqueued behind them on the main
+    # stream, and the host waits for the copy only -- so it sizes, allocates and enqueues the rest of the forward while the
+    # sort runs.  (A plain `totals.tolist()` after the sort's launch is ordered behind the sort and leaves the GPU idle for
+    # as long as the host then needs to enqueue the next kernels.)
+    totals_host = totals_ready = None
+    if totals is not None and counts is None:
+        totals_host, totals_ready = _async_to_host(totals)
     sorted_ids = torch.empty(max(M, 1), dtype=torch.int32, device=dev)
     # fused path: the sort's first pass computes the tile rectangles (coalesced), they ride through the passes as a second
     # payload and come out in depth order; the expansion is one kernel (B2S_BINNING_FUSED=0: the unfused reference kernels,
@@ -739,13 +776,12 @@ def bin_coarse(means2d: Tensor, radii: Tensor, depths: Tensor, tile_size: int, t
         ws = _ws(lib.b2s_depth_order_workspace_bytes(M), dev)
         with _stage("depth_order", launches=6):      # histogram, scan, 4 digit passes
             check(lib.b2s_depth_order(M, ptr(depth_keys), ptr(row_ids), ptr(sorted_ids), ptr(ws), ws.numel(), st), "b2s_depth_order")
-    # The one host sync of a forward (sizes the record buffers).  The depth sort is already enqueued, so the GPU
-    # keeps working while the host waits for the counts that stage 1 produced.
     n_visible = None
     if counts is not None:             # (n_isects, n_records) already on the host (the multi-GPU stripe table)
         n_isects, n_records = int(counts[0]), int(counts[1])
     elif totals is not None:
-        slots = totals.tolist()                    # 32 counter rows, added up on the host (no reduction kernel)
+        totals_ready.synchronize()
+        slots = totals_host.tolist()               # 32 counter rows, added up on the host (no reduction kernel)
         n_isects, n_visible, n_records = (int(sum(r[k] for r in slots)) for k in (0, 1, 2))
     else:
         n_isects, n_records = None, int(tot.item())
@@ -850,7 +886,7 @@ class _RasterizeToPixels(torch.autograd.Function):
             pre, ctx.slab_pre = ctx.slab_pre, None       # (a second backward of the same graph gets a fresh slab)
             slab = take_prefilled(pre, M * sum(widths), dev)
         else:
-            slab = torch.zeros(M * sum(widths), dtype=torch.float32, device=dev)
+            slab = zeros_f32(M * sum(widths), dev)
         parts, o = [], 0
         for wd in widths:
             parts.append(slab[o:o + M * wd])
