@@ -759,6 +759,7 @@ __global__ void __launch_bounds__(EXP_THREADS, 5) coarse_emit_lb_kernel(int64_t 
         }
     }
     __syncthreads();
+    hist += (size_t)(cta % radix::HIST_COPIES) * sizeof(uint32_t) * radix::RADIX;      // [copies][4 passes][256]
     for (int i = threadIdx.x; i < pl.passes * radix::RADIX; i += EXP_THREADS)
         if (s_hist[i]) atomicAdd(&hist[i], (unsigned long long)s_hist[i]);
 }
@@ -1257,7 +1258,7 @@ extern "C" int b2s_coarse_bin_rects(int64_t M, int64_t N, const int64_t* camera_
     const radix::Plan pl = radix::make_plan(key_bits);                       // at most 2 passes (16 key bits)
     unsigned long long* hist = radix::hist_ptr<uint32_t>(sort_ws, n_records);
     B2S_CUDA(cudaMemsetAsync(counter, 0, (size_t)(16 + ctas * 8), st));
-    B2S_CUDA(cudaMemsetAsync(hist, 0, sizeof(uint32_t) * radix::RADIX * 8, st));
+    B2S_CUDA(cudaMemsetAsync(hist, 0, radix::hist_bytes<uint32_t>(), st));
     coarse_emit_lb_kernel<<<(unsigned)ctas, EXP_THREADS, 0, st>>>(M, N, camera_ids, sorted_ids, rects, bins_w, bins_h, status, counter, pl,
                                                                   hist, recs_u, vals_u);
     B2S_LAUNCH_CHECK();

@@ -23,6 +23,11 @@ constexpr int RADIX_BITS = 8;
 constexpr int RADIX = 1 << RADIX_BITS;
 constexpr int THREADS = 256;
 constexpr int WARPS = THREADS / 32;
+// The CTAs flush their shared-memory digit counts into HIST_COPIES copies of the global histogram (copy = CTA % copies), which
+// the scan kernel adds up: same-address atomics serialise in L2 (~27 cycles each), and with a few hot digits (a depth
+// key's top byte, 77 coarse bins) one copy made the flush the whole cost of the kernel -- 18 us for 1 184 CTAs, 80 us for the
+// 5 665 CTAs of the coarse-bin expansion.
+constexpr int HIST_COPIES = 16;
 constexpr unsigned long long R_FLAG_AGG = 1ull << 62, R_FLAG_INC = 2ull << 62, R_VAL_MASK = (1ull << 62) - 1;
 
 #ifndef B2S_RADIX_ITEMS32
@@ -70,29 +75,35 @@ struct NoSide {
 template <typename KeyT, int MAX_PASSES, typename Side>
 __global__ void __launch_bounds__(THREADS) hist_kernel(int64_t n, const KeyT* __restrict__ keys, const int32_t* __restrict__ vals,
                                                        const Side side, const Plan pl,
-                                                       unsigned long long* __restrict__ hist /* [passes][256] */) {
+                                                       unsigned long long* __restrict__ hist /* [copies][MAX_PASSES][256] */) {
     const int passes = pl.passes;
+    hist += (size_t)(blockIdx.x % HIST_COPIES) * MAX_PASSES * RADIX;
     __shared__ unsigned s_hist[MAX_PASSES * RADIX];
     for (int i = threadIdx.x; i < passes * RADIX; i += THREADS) s_hist[i] = 0;
     __syncthreads();
-    // four elements per thread and iteration: their loads (and the dependent loads of the hook) are in flight together
-    constexpr int U = 4;
-    const int64_t stride = (int64_t)gridDim.x * THREADS;
-    for (int64_t i0 = (int64_t)blockIdx.x * THREADS + threadIdx.x; i0 < n; i0 += U * stride) {
+    // U consecutive elements per thread and iteration: their loads (and the dependent loads of the hook) are in flight
+    // together and a warp still touches one contiguous run.  (U elements a grid stride apart measured SLOWER than one at a
+    // time: 62 vs 45 us with the rectangle hook at 5.8 M rows, profiles/r02_variants_c15.txt.)
+#ifndef B2S_HIST_U
+#define B2S_HIST_U 4
+#endif
+    constexpr int U = B2S_HIST_U;
+    const int64_t stride = (int64_t)gridDim.x * THREADS * U;
+    for (int64_t i0 = ((int64_t)blockIdx.x * THREADS + threadIdx.x) * U; i0 < n; i0 += stride) {
         KeyT k[U];
         int32_t v[U];
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-            const int64_t i = i0 + u * stride;
+            const int64_t i = i0 + u;
             k[u] = i < n ? keys[i] : (KeyT)0;
             v[u] = (Side::kActive && i < n) ? vals[i] : 0;
         }
 #pragma unroll
         for (int u = 0; u < U; ++u)
-            if (Side::kActive && i0 + u * stride < n) side(i0 + u * stride, v[u]);
+            if (Side::kActive && i0 + u < n) side(i0 + u, v[u]);
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-            if (i0 + u * stride >= n) break;
+            if (i0 + u >= n) break;
 #pragma unroll
             for (int p = 0; p < MAX_PASSES; ++p)
                 if (p < passes) atomicAdd(&s_hist[p * RADIX + digit_of(k[u], pl.shift[p], (1u << pl.bits[p]) - 1u)], 1u);
@@ -103,11 +114,13 @@ __global__ void __launch_bounds__(THREADS) hist_kernel(int64_t n, const KeyT* __
         if (s_hist[i]) atomicAdd(&hist[i], (unsigned long long)s_hist[i]);
 }
 
-// exclusive scan of each 256-bin histogram (one CTA per pass)
-static __global__ void __launch_bounds__(RADIX) scan_hist_kernel(unsigned long long* __restrict__ hist) {
+// sum of the copies, then exclusive scan of each 256-bin histogram (one CTA per pass); the result replaces copy 0
+static __global__ void __launch_bounds__(RADIX) scan_hist_kernel(unsigned long long* __restrict__ hist, int max_passes) {
     __shared__ unsigned long long s[RADIX];
     unsigned long long* h = hist + (size_t)blockIdx.x * RADIX;
-    const unsigned long long v = h[threadIdx.x];
+    unsigned long long v = 0ull;
+#pragma unroll 4
+    for (int c = 0; c < HIST_COPIES; ++c) v += h[(size_t)c * max_passes * RADIX + threadIdx.x];
     s[threadIdx.x] = v;
     __syncthreads();
     for (int d = 1; d < RADIX; d <<= 1) {
@@ -368,12 +381,15 @@ static inline int passes_of(int key_bits) { return (key_bits + RADIX_BITS - 1) /
 template <typename KeyT>
 static inline size_t workspace_bytes(int64_t n) {
     const int max_passes = (int)sizeof(KeyT);
-    return 2 * up256((size_t)n * sizeof(KeyT)) + 2 * up256((size_t)n * 4) + up256((size_t)max_passes * RADIX * 8) +
+    return 2 * up256((size_t)n * sizeof(KeyT)) + 2 * up256((size_t)n * 4) + up256((size_t)HIST_COPIES * max_passes * RADIX * 8) +
            up256((size_t)tiles_of<KeyT>(n) * RADIX * 8) + up256((size_t)max_passes * 4);
 }
 
-// where the [passes][256] digit histograms live inside the workspace (a caller that counts the digits itself -- the
-// coarse-bin expansion -- zeroes and fills them, then sorts with hist_ready = true)
+// where the [HIST_COPIES][sizeof(KeyT)][256] digit histograms live inside the workspace (a caller that counts the digits
+// itself -- the coarse-bin expansion -- zeroes all copies (hist_bytes), adds into any of them, then sorts with
+// hist_ready = true)
+template <typename KeyT>
+static inline size_t hist_bytes() { return (size_t)HIST_COPIES * sizeof(KeyT) * RADIX * 8; }
 template <typename KeyT>
 static inline unsigned long long* hist_ptr(void* workspace, int64_t n) {
     return reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(workspace) + 2 * up256((size_t)n * sizeof(KeyT)) +
@@ -414,20 +430,20 @@ static int sort_ex(int64_t n, int key_bits, const KeyT* keys_in, const int32_t* 
     tk[1] = reinterpret_cast<KeyT*>(w); w += up256((size_t)n * sizeof(KeyT));
     tv[0] = reinterpret_cast<int32_t*>(w); w += up256((size_t)n * 4);
     tv[1] = reinterpret_cast<int32_t*>(w); w += up256((size_t)n * 4);
-    unsigned long long* hist = reinterpret_cast<unsigned long long*>(w); w += up256((size_t)MAXP * RADIX * 8);
+    unsigned long long* hist = reinterpret_cast<unsigned long long*>(w); w += up256(hist_bytes<KeyT>());
     unsigned long long* status = reinterpret_cast<unsigned long long*>(w);
     const int64_t tiles = tiles_of<KeyT>(n);
     w += up256((size_t)tiles * RADIX * 8);
     unsigned int* counters = reinterpret_cast<unsigned int*>(w);
 
     if (!hist_ready) {
-        B2S_CUDA(cudaMemsetAsync(hist, 0, (size_t)MAXP * RADIX * 8, st));
+        B2S_CUDA(cudaMemsetAsync(hist, 0, hist_bytes<KeyT>(), st));
         const int hist_grid = (int)min((int64_t)148 * 8, cdiv(n, THREADS));
         hist_kernel<KeyT, MAXP, Side><<<hist_grid, THREADS, 0, st>>>(n, keys_in, vals_in, side, pl, hist);
         B2S_LAUNCH_CHECK();
     }
     B2S_CUDA(cudaMemsetAsync(counters, 0, (size_t)MAXP * 4, st));
-    scan_hist_kernel<<<passes, RADIX, 0, st>>>(hist);
+    scan_hist_kernel<<<passes, RADIX, 0, st>>>(hist, MAXP);
     B2S_LAUNCH_CHECK();
     using Mid = StorePairs<KeyT>;
     const KeyT* src_k = keys_in;

@@ -50,6 +50,12 @@ e1.record(); torch.cuda.synchronize()
 print(f"forward only: {e0.elapsed_time(e1)/20:.3f} ms")
 import cProfile, pstats
 pr = cProfile.Profile(); pr.enable()
+with torch.no_grad():
+    for _ in range(10): fwd()
+pr.disable(); torch.cuda.synchronize()
+print("---- forward only ----")
+pstats.Stats(pr).sort_stats("cumulative").print_stats(18)
+pr = cProfile.Profile(); pr.enable()
 for _ in range(10): step()
 pr.disable(); torch.cuda.synchronize()
 pstats.Stats(pr).sort_stats("cumulative").print_stats(25)
