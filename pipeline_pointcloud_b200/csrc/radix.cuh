@@ -295,43 +295,13 @@ __global__ void __launch_bounds__(THREADS, B2S_RADIX_MINBLOCKS) onesweep_kernel(
         s_warp_hist[w * HS + d] = cnt;
         cnt += t;
     }
-    // 4. look-back for digit d (the status word carries flag and value together: no fence needed)
-    unsigned long long excl = 0;
-    {
-        constexpr int SH = St<StatusT>::SHIFT;
-        volatile StatusT* st = status;
-        if (tile == 0) {
-            st[d] = ((StatusT)2 << SH) | (StatusT)cnt;
-        } else {
-            st[tile * RADIX + d] = ((StatusT)1 << SH) | (StatusT)cnt;
-            // Walk back LB tiles at a time: the LB status loads are independent, so a window of LB tiles costs
-            // one L2 round trip instead of LB.
-            constexpr int LB = 8;
-            int k = (int)tile - 1;
-            while (true) {
-                StatusT sv[LB];
-#pragma unroll
-                for (int u = 0; u < LB; ++u) sv[u] = (k - u >= 0) ? st[(unsigned)(k - u) * RADIX + d] : ((StatusT)2 << SH);
-                unsigned ready = 0, inc = 0;
-#pragma unroll
-                for (int u = 0; u < LB; ++u) {
-                    const unsigned f = (unsigned)(sv[u] >> SH);
-                    ready |= (f != 0u) << u;
-                    inc |= (f == 2u) << u;
-                }
-                const int first_wait = __ffs(~ready) - 1;                       // LB.. when all are published
-                const int first_inc = inc ? __ffs(inc) - 1 : LB;
-                const int usable = min(first_wait, first_inc + 1);              // tiles [k, k-usable) can be consumed
-#pragma unroll
-                for (int u = 0; u < LB; ++u)
-                    if (u < usable) excl += (unsigned long long)(sv[u] & St<StatusT>::MASK);
-                if (first_inc < usable) break;
-                k -= usable;
-            }
-            st[tile * RADIX + d] = ((StatusT)2 << SH) | (StatusT)(excl + cnt);
-        }
-    }
+    // 4a. publish the tile's aggregate for digit d at once (the status word carries flag and value together: no fence
+    // needed) -- the sooner it is visible, the less the tiles behind this one wait
+    constexpr int SH = St<StatusT>::SHIFT;
+    volatile StatusT* st = status;
+    st[tile * RADIX + d] = ((StatusT)(tile == 0 ? 2 : 1) << SH) | (StatusT)cnt;
     // exclusive scan of the tile's digit counts (256 values, one per thread)
+    unsigned start;
     {
         unsigned incl = cnt;
 #pragma unroll
@@ -345,12 +315,11 @@ __global__ void __launch_bounds__(THREADS, B2S_RADIX_MINBLOCKS) onesweep_kernel(
 #pragma unroll
         for (int w = 0; w < WARPS; ++w)
             if (w < (int)warp) woff += s_wsum[w];
-        const unsigned start = woff + incl - cnt;
+        start = woff + incl - cnt;
         s_cta_start[d] = start;
-        s_off[d] = (unsigned)(digit_base[d] + excl) - start;
     }
     __syncthreads();
-    // 5. local reorder, then coalesced scatter
+    // 5a. local reorder: needs nothing from other tiles, and it ends the life of the 4 x ITEMS item registers
 #pragma unroll
     for (int i = 0; i < ITEMS; ++i) {
         if (full || dig[i] < RADIX) {
@@ -359,7 +328,43 @@ __global__ void __launch_bounds__(THREADS, B2S_RADIX_MINBLOCKS) onesweep_kernel(
             s_vals[p] = val[i];
         }
     }
+    // 4b. look-back for digit d, LB tiles per round trip (independent loads).  With ~450 tiles in flight the nearest
+    // inclusive prefix is hundreds of tiles back (the whole first wave starts together): at 8 tiles per round the walk was
+    // the longest phase of a tile; the item registers being dead, the window can be 32 wide.
+    {
+        unsigned long long excl = 0;
+        if (tile != 0) {
+#ifndef B2S_RADIX_LB
+#define B2S_RADIX_LB 32
+#endif
+            constexpr int LB = B2S_RADIX_LB;
+            int k = (int)tile - 1;
+            while (true) {
+                StatusT sv[LB];
+#pragma unroll
+                for (int u = 0; u < LB; ++u) sv[u] = (k - u >= 0) ? st[(unsigned)(k - u) * RADIX + d] : ((StatusT)2 << SH);
+                unsigned ready = 0, inc = 0;
+#pragma unroll
+                for (int u = 0; u < LB; ++u) {
+                    const unsigned f = (unsigned)(sv[u] >> SH);
+                    ready |= (unsigned)(f != 0u) << u;
+                    inc |= (unsigned)(f == 2u) << u;
+                }
+                const int first_wait = (LB == 32 && ready == FULL) ? 32 : __ffs(~ready) - 1;   // LB when all are published
+                const int first_inc = inc ? __ffs(inc) - 1 : LB;
+                const int usable = min(first_wait, first_inc + 1);              // tiles [k, k-usable) can be consumed
+#pragma unroll
+                for (int u = 0; u < LB; ++u)
+                    if (u < usable) excl += (unsigned long long)(sv[u] & St<StatusT>::MASK);
+                if (first_inc < usable) break;
+                k -= usable;
+            }
+            st[tile * RADIX + d] = ((StatusT)2 << SH) | (StatusT)(excl + cnt);
+        }
+        s_off[d] = (unsigned)(digit_base[d] + excl) - start;
+    }
     __syncthreads();
+    // 5b. coalesced scatter
 #pragma unroll 4
     for (unsigned p = threadIdx.x; p - threadIdx.x < tile_count; p += THREADS) {     // whole warps: the epilogue may vote
         const KeyT k = s_keys[p];
