@@ -74,55 +74,6 @@ __device__ __forceinline__ unsigned long long lookback_warp(volatile unsigned lo
     return excl;
 }
 
-constexpr int LB_WARPS = 8;
-// The same look-back by a whole 256-thread CTA: a window of 256 predecessors per memory round trip.  When hundreds of CTAs
-// are in flight (the coarse-bin expansion keeps ~740 resident, each busy with a gather before it can finish), the nearest
-// inclusive prefix lies hundreds of tiles back and the 32-wide walk needs ~20 dependent round trips -- it WAS the kernel's
-// critical path (98 us for 5 665 CTAs; profiles/r02_variants_c15.txt).  Called by all threads; returns the exclusive prefix
-// to all of them.  s_sum / s_state: 8 words each.
-__device__ __forceinline__ unsigned long long lookback_cta(volatile unsigned long long* st, unsigned tile,
-                                                           unsigned long long block_sum, unsigned long long* s_sum, int* s_state) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if (tile == 0) {
-        if (threadIdx.x == 0) st[0] = FLAG_INC | block_sum;
-        return 0ull;
-    }
-    if (threadIdx.x == 0) st[tile] = FLAG_AGG | block_sum;     // flag and value travel in one word: no fence needed
-    unsigned long long excl = 0ull;
-    long long base = (long long)tile - 1;
-    while (true) {
-        const long long k = base - (long long)threadIdx.x;
-        unsigned long long sv = FLAG_INC;                       // before tile 0: inclusive prefix 0
-        if (k >= 0) sv = st[k];
-        const unsigned long long flag = sv & ~VAL_MASK;
-        const unsigned ready = __ballot_sync(FULL, flag != 0ull);
-        const unsigned inc = __ballot_sync(FULL, flag == FLAG_INC);
-        const int p = inc ? (__ffs(inc) - 1) : 31;              // nearest predecessor of this warp's window with an inclusive prefix
-        const unsigned need = (p == 31) ? FULL : ((1u << (p + 1)) - 1u);
-        unsigned long long v = (lane <= p) ? (sv & VAL_MASK) : 0ull;
-#pragma unroll
-        for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(FULL, v, d);
-        if (lane == 0) {
-            s_sum[warp] = v;
-            s_state[warp] = ((ready & need) != need) ? 2 : (inc ? 1 : 0);   // 2: somebody has not published yet
-        }
-        __syncthreads();
-        bool done = false;
-        int used = 0;                                           // warps' windows consumed this round (nearest first)
-        for (; used < LB_WARPS; ++used) {
-            const int state = s_state[used];
-            if (state == 2) break;
-            excl += s_sum[used];
-            if (state == 1) { done = true; break; }
-        }
-        __syncthreads();
-        if (done) break;
-        base -= 32 * used;
-    }
-    if (threadIdx.x == 0) st[tile] = FLAG_INC | (excl + block_sum);
-    return excl;
-}
-
 template <bool GATHER>  // GATHER: scan in[idx[i]] (values taken in a permuted order)
 __global__ void __launch_bounds__(SCAN_THREADS) scan_kernel(int64_t M, const int32_t* __restrict__ in,
                                                             const int32_t* __restrict__ idx,
@@ -720,8 +671,7 @@ __global__ void __launch_bounds__(EXP_THREADS, 5) coarse_emit_lb_kernel(int64_t 
                                                                      uint32_t* __restrict__ recs, int32_t* __restrict__ vals) {
     __shared__ unsigned int s_cta;
     __shared__ int s_warp_tot[EXP_THREADS / 32];
-    __shared__ unsigned long long s_lb_sum[EXP_THREADS / 32];
-    __shared__ int s_lb_state[EXP_THREADS / 32];
+    __shared__ unsigned long long s_prefix;
     __shared__ unsigned s_hist[2 * radix::RADIX];
     if (threadIdx.x == 0) s_cta = atomicAdd(cta_counter, 1u);
     for (int i = threadIdx.x; i < 2 * radix::RADIX; i += EXP_THREADS) s_hist[i] = 0u;
@@ -763,7 +713,14 @@ __global__ void __launch_bounds__(EXP_THREADS, 5) coarse_emit_lb_kernel(int64_t 
         if (w < warp) warp_off += x;
         block_sum += x;
     }
-    const int64_t out0 = (int64_t)lookback_cta(status, cta, (unsigned long long)block_sum, s_lb_sum, s_lb_state) + warp_off;
+    // (a look-back by the whole CTA -- 256 predecessors per round trip -- measured slower: 119 vs 98 us; the walk is short
+    // in practice and the wider poll only adds traffic, profiles/r02_variants_c15.txt)
+    if (warp == 0) {
+        const unsigned long long e = lookback_warp(status, cta, (unsigned long long)block_sum, lane);
+        if (lane == 0) s_prefix = e;
+    }
+    __syncthreads();
+    const int64_t out0 = (int64_t)s_prefix + warp_off;
     const unsigned m0 = (1u << pl.bits[0]) - 1u, m1 = pl.passes > 1 ? (1u << pl.bits[1]) - 1u : 0u;
     const int sh1 = pl.shift[1];
     const uint32_t per_cam = (uint32_t)(bins_w * bins_h);

@@ -328,14 +328,14 @@ __global__ void __launch_bounds__(THREADS, B2S_RADIX_MINBLOCKS) onesweep_kernel(
             s_vals[p] = val[i];
         }
     }
-    // 4b. look-back for digit d, LB tiles per round trip (independent loads).  With ~450 tiles in flight the nearest
-    // inclusive prefix is hundreds of tiles back (the whole first wave starts together): at 8 tiles per round the walk was
-    // the longest phase of a tile; the item registers being dead, the window can be 32 wide.
+    // 4b. look-back for digit d, LB tiles per round trip (independent loads).  (Windows of 16 and 32 tiles measured no
+    // better / worse than 8: 0.272 / 0.295 vs 0.272 ms for the depth sort -- the walk is short in practice and a wider poll
+    // only adds traffic; publishing early and reordering first is what gained, 0.285 -> 0.272 ms.)
     {
         unsigned long long excl = 0;
         if (tile != 0) {
 #ifndef B2S_RADIX_LB
-#define B2S_RADIX_LB 32
+#define B2S_RADIX_LB 8
 #endif
             constexpr int LB = B2S_RADIX_LB;
             int k = (int)tile - 1;
