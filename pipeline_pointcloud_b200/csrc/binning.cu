@@ -713,65 +713,53 @@ __global__ void __launch_bounds__(EXP_THREADS, 5) coarse_emit_lb_kernel(int64_t 
         if (w < warp) warp_off += x;
         block_sum += x;
     }
-    const unsigned m0 = (1u << pl.bits[0]) - 1u, m1 = pl.passes > 1 ? (1u << pl.bits[1]) - 1u : 0u;
-    const int sh1 = pl.shift[1];
-    const uint32_t per_cam = (uint32_t)(bins_w * bins_h);
-    // every record of the warp's rows, in order: fn(slot inside the warp's output range, record, row id)
-    auto each_record = [&](auto&& fn) {
-#pragma unroll
-        for (int g = 0; g < EMIT_GROUPS; ++g) {
-            const int gx0 = (int)(rc[g] & 0xFFu), gx1 = (int)((rc[g] >> 8) & 0xFFu), gy0 = (int)((rc[g] >> 16) & 0xFFu), gy1 = (int)(rc[g] >> 24);
-            uint32_t cam_base = 0u;                             // (32-bit division, and none at all with one camera)
-            if (cnt[g] > 0 && (camera_ids || M > N)) cam_base = (camera_ids ? (uint32_t)camera_ids[id[g]] : (uint32_t)id[g] / (uint32_t)N) * per_cam;
-            const int bx0 = gx0 / CB, by0 = gy0 / CB, w = cnt[g] > 0 ? coarse_span(gx0, gx1) : 1;
-            // small rows: each lane handles its own records
-            if (cnt[g] <= EMIT_DIRECT) {
-                int dx = 0, dy = 0;
-                for (int k = 0; k < cnt[g]; ++k) {
-                    fn(excl[g] + k, coarse_record(gx0, gx1, gy0, gy1, bx0 + dx, by0 + dy, cam_base, bins_w), id[g]);
-                    if (++dx == w) { dx = 0; ++dy; }
-                }
-            }
-            // large rows: one at a time, the warp strides over the row's bins
-            unsigned big = __ballot_sync(FULL, cnt[g] > EMIT_DIRECT);
-            while (big) {
-                const int src = __ffs(big) - 1;
-                big &= big - 1;
-                const uint32_t r = __shfl_sync(FULL, rc[g], src);
-                const int n = __shfl_sync(FULL, cnt[g], src), v = __shfl_sync(FULL, id[g], src);
-                const int ex = __shfl_sync(FULL, excl[g], src), ww = __shfl_sync(FULL, w, src);
-                const uint32_t cb = __shfl_sync(FULL, cam_base, src);
-                const int rx0 = (int)(r & 0xFFu), rx1 = (int)((r >> 8) & 0xFFu), ry0 = (int)((r >> 16) & 0xFFu), ry1 = (int)(r >> 24);
-                for (int k = lane; k < n; k += 32) {
-                    const int dy = k / ww, dx = k - dy * ww;
-                    fn(ex + k, coarse_record(rx0, rx1, ry0, ry1, rx0 / CB + dx, ry0 / CB + dy, cb, bins_w), v);
-                }
-            }
-        }
-    };
-    // (a look-back by the whole CTA -- 256 predecessors per round trip -- measured slower: 119 vs 98 us; the walk is short,
-    // what a CTA waits for is its predecessors' gathers, and the wider poll only adds traffic: profiles/r02_variants_c15.txt)
+    // (a look-back by the whole CTA -- 256 predecessors per round trip -- measured slower: 119 vs 98 us; the walk is short
+    // in practice and the wider poll only adds traffic, profiles/r02_variants_c15.txt)
     if (warp == 0) {
         const unsigned long long e = lookback_warp(status, cta, (unsigned long long)block_sum, lane);
         if (lane == 0) s_prefix = e;
-    } else {
-        // the other warps wait for the look-back anyway (37 % of the kernel's stall samples sat at this barrier): they count
-        // their digits now; warp 0 counts its own after the barrier
-        each_record([&](int, uint32_t rec, int) {
-            atomicAdd(&s_hist[rec & m0], 1u);
-            if (m1) atomicAdd(&s_hist[radix::RADIX + ((rec >> sh1) & m1)], 1u);
-        });
     }
     __syncthreads();
     const int64_t out0 = (int64_t)s_prefix + warp_off;
-    each_record([&](int slot, uint32_t rec, int v) {
-        recs[out0 + slot] = rec;
-        vals[out0 + slot] = v;
-        if (warp == 0) {
-            atomicAdd(&s_hist[rec & m0], 1u);
-            if (m1) atomicAdd(&s_hist[radix::RADIX + ((rec >> sh1) & m1)], 1u);
+    const unsigned m0 = (1u << pl.bits[0]) - 1u, m1 = pl.passes > 1 ? (1u << pl.bits[1]) - 1u : 0u;
+    const int sh1 = pl.shift[1];
+    const uint32_t per_cam = (uint32_t)(bins_w * bins_h);
+    auto put = [&](int64_t slot, uint32_t rec, int v) {
+        recs[slot] = rec;
+        vals[slot] = v;
+        atomicAdd(&s_hist[rec & m0], 1u);
+        if (m1) atomicAdd(&s_hist[radix::RADIX + ((rec >> sh1) & m1)], 1u);
+    };
+#pragma unroll
+    for (int g = 0; g < EMIT_GROUPS; ++g) {
+        const int gx0 = (int)(rc[g] & 0xFFu), gx1 = (int)((rc[g] >> 8) & 0xFFu), gy0 = (int)((rc[g] >> 16) & 0xFFu), gy1 = (int)(rc[g] >> 24);
+        uint32_t cam_base = 0u;                                 // (32-bit division, and none at all with one camera)
+        if (cnt[g] > 0 && (camera_ids || M > N)) cam_base = (camera_ids ? (uint32_t)camera_ids[id[g]] : (uint32_t)id[g] / (uint32_t)N) * per_cam;
+        const int bx0 = gx0 / CB, by0 = gy0 / CB, w = cnt[g] > 0 ? coarse_span(gx0, gx1) : 1;
+        // small rows: each lane writes its own records
+        if (cnt[g] <= EMIT_DIRECT) {
+            int dx = 0, dy = 0;
+            for (int k = 0; k < cnt[g]; ++k) {
+                put(out0 + excl[g] + k, coarse_record(gx0, gx1, gy0, gy1, bx0 + dx, by0 + dy, cam_base, bins_w), id[g]);
+                if (++dx == w) { dx = 0; ++dy; }
+            }
         }
-    });
+        // large rows: one at a time, the warp strides over the row's bins
+        unsigned big = __ballot_sync(FULL, cnt[g] > EMIT_DIRECT);
+        while (big) {
+            const int src = __ffs(big) - 1;
+            big &= big - 1;
+            const uint32_t r = __shfl_sync(FULL, rc[g], src);
+            const int n = __shfl_sync(FULL, cnt[g], src), v = __shfl_sync(FULL, id[g], src);
+            const int ex = __shfl_sync(FULL, excl[g], src), ww = __shfl_sync(FULL, w, src);
+            const uint32_t cb = __shfl_sync(FULL, cam_base, src);
+            const int rx0 = (int)(r & 0xFFu), rx1 = (int)((r >> 8) & 0xFFu), ry0 = (int)((r >> 16) & 0xFFu), ry1 = (int)(r >> 24);
+            for (int k = lane; k < n; k += 32) {
+                const int dy = k / ww, dx = k - dy * ww;
+                put(out0 + ex + k, coarse_record(rx0, rx1, ry0, ry1, rx0 / CB + dx, ry0 / CB + dy, cb, bins_w), v);
+            }
+        }
+    }
     __syncthreads();
     hist += (size_t)(cta % radix::HIST_COPIES) * sizeof(uint32_t) * radix::RADIX;      // [copies][4 passes][256]
     for (int i = threadIdx.x; i < pl.passes * radix::RADIX; i += EXP_THREADS)

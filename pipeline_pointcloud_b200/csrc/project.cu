@@ -332,7 +332,7 @@ __global__ void __launch_bounds__(SHB_THREADS, 4) sh_bwd_fused_kernel(const b2s_
     const unsigned row_mask = a.v_colors ? __ballot_sync(FULL, live && vis != 0ull) : 0u;
     if (row_mask == 0u && !a.accumulate) {
         // nothing in this warp's 32 rows can have a gradient (culled / occluded): stream zeros straight out
-        if (live && !cnt) { a.v_means[3 * n] = 0.f; a.v_means[3 * n + 1] = 0.f; a.v_means[3 * n + 2] = 0.f; }   // cnt: classify zero-filled it
+        if (live) { a.v_means[3 * n] = 0.f; a.v_means[3 * n + 1] = 0.f; a.v_means[3 * n + 2] = 0.f; }
         if (rows > 0) {
             float* g = a.v_sh_coeffs + (size_t)row0 * a.sh_stride_k * 3;
             if (KVEC == 16) {
@@ -425,10 +425,7 @@ __global__ void __launch_bounds__(SHB_THREADS, 4) sh_bwd_fused_kernel(const b2s_
         }
     }
     if (live) {
-        if (cnt) {      // zero-filled by classify; the list-driven projection VJP may be adding to the same rows on a second stream
-            if (vis != 0ull) { atomicAdd(a.v_means + 3 * n, v_mean[0]); atomicAdd(a.v_means + 3 * n + 1, v_mean[1]); atomicAdd(a.v_means + 3 * n + 2, v_mean[2]); }
-        }
-        else if (a.accumulate) { a.v_means[3 * n] += v_mean[0]; a.v_means[3 * n + 1] += v_mean[1]; a.v_means[3 * n + 2] += v_mean[2]; }
+        if (a.accumulate) { a.v_means[3 * n] += v_mean[0]; a.v_means[3 * n + 1] += v_mean[1]; a.v_means[3 * n + 2] += v_mean[2]; }
         else { a.v_means[3 * n] = v_mean[0]; a.v_means[3 * n + 1] = v_mean[1]; a.v_means[3 * n + 2] = v_mean[2]; }
     }
     __syncwarp();
@@ -579,9 +576,7 @@ __global__ void __launch_bounds__(128) sh_sparse_kernel(const b2s_project_bwd_ar
             for (int q = 0; q < 12; ++q)
                 stg_stream4(reinterpret_cast<float4*>(out) + q, make_float4(acc[4 * q], acc[4 * q + 1], acc[4 * q + 2], acc[4 * q + 3]));
         }
-        // zero-filled by classify; atomics because the list-driven projection VJP may run beside this kernel on a second
-        // stream and adds to the same rows (two addends per element: the sum does not depend on their order)
-        atomicAdd(a.v_means + 3 * n, v_mean[0]); atomicAdd(a.v_means + 3 * n + 1, v_mean[1]); atomicAdd(a.v_means + 3 * n + 2, v_mean[2]);
+        a.v_means[3 * n] += v_mean[0]; a.v_means[3 * n + 1] += v_mean[1]; a.v_means[3 * n + 2] += v_mean[2];   // zero-filled by classify
     }
 }
 
@@ -699,7 +694,7 @@ __global__ void __launch_bounds__(BWD_THREADS) project_bwd_sparse_kernel(const b
         const int64_t n = list_geom[idx];
         float v_mean[3], v_quat[4], v_scale[3], v_opac;
         const bool any = project_bwd_row(a, cams, n, v_mean, v_quat, v_scale, v_opac);
-        if (any) { atomicAdd(a.v_means + 3 * n, v_mean[0]); atomicAdd(a.v_means + 3 * n + 1, v_mean[1]); atomicAdd(a.v_means + 3 * n + 2, v_mean[2]); }
+        if (any) { a.v_means[3 * n] += v_mean[0]; a.v_means[3 * n + 1] += v_mean[1]; a.v_means[3 * n + 2] += v_mean[2]; }
         a.v_scales[3 * n] = v_scale[0]; a.v_scales[3 * n + 1] = v_scale[1]; a.v_scales[3 * n + 2] = v_scale[2];
         reinterpret_cast<float4*>(a.v_quats)[n] = make_float4(v_quat[0], v_quat[1], v_quat[2], v_quat[3]);
         if (a.v_opacities) a.v_opacities[n] = v_opac;

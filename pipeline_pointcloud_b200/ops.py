@@ -303,27 +303,6 @@ def project_backward(saved, cfg, v_means2d, v_depths, v_conics, v_comps, v_opac_
                     check(lib.b2s_project_bwd(ctypes.byref(args(1)), st), "b2s_project_bwd")
             with _stage("project_bwd", launches=1):
                 check(lib.b2s_project_bwd(ctypes.byref(args(2)), st), "b2s_project_bwd")
-        elif sparse and with_sh and prezeroed == 0 and os.environ.get("B2S_BWD_OVERLAP", "1") != "0":
-            # classify, then the list-driven projection VJP (a latency-bound kernel over the few live rows) on a second
-            # stream beside the 1.1 GB streaming zero fill of v_sh + the list-driven SH kernel on this one
-            main = torch.cuda.current_stream(dev)
-            side = _SIDE_STREAMS.get(dev.index)
-            if side is None:
-                side = _SIDE_STREAMS[dev.index] = torch.cuda.Stream(dev)
-            with _stage("project_bwd", launches=5):
-                check(lib.b2s_project_bwd(ctypes.byref(args(3)), st), "b2s_project_bwd")
-                fork = torch.cuda.Event()
-                fork.record(main)
-                side.wait_event(fork)
-                check(lib.b2s_project_bwd(ctypes.byref(args(2)), side.cuda_stream), "b2s_project_bwd")
-                join = torch.cuda.Event()
-                join.record(side)
-                check(lib.b2s_project_bwd(ctypes.byref(args(4)), st), "b2s_project_bwd")
-                main.wait_event(join)
-            for t in (means, quats, scales, opacities, viewmats, Ks, campos, radii, v_means2d, v_depths, v_conics, v_comps,
-                      v_opac_out, v_means, v_quats, v_scales, v_opac, ws):
-                if t is not None:
-                    t.record_stream(side)
         else:
             with _stage("project_bwd", launches=(5 if with_sh else 2) if sparse else (2 if with_sh else 1)):
                 check(lib.b2s_project_bwd(ctypes.byref(args(0)), st), "b2s_project_bwd")
