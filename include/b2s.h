@@ -269,76 +269,6 @@ B2S_API int b2s_coarse_bin_rects(int64_t M, int64_t N, const int64_t* camera_ids
                                  uint32_t* bin_recs, int32_t* bin_ids, int32_t* bin_offsets, void* workspace,
                                  int64_t workspace_bytes, b2s_stream_t stream);
 
-/* Packed layout (gsplat `packed=True`): sel = the indices of the rows with radius > 0, ascending (camera-major,
- * Gaussian-ascending), at most cap of them; total[0] (device) = their number.  Workspace as b2s_isect_scan. */
-B2S_API int b2s_select_visible(int64_t M, const int32_t* radii, int64_t* sel, int64_t cap, int64_t* total, void* workspace,
-                               int64_t workspace_bytes, b2s_stream_t stream);
-B2S_API int b2s_isect_fill(int64_t M, int64_t N, const int64_t* camera_ids /* or NULL */, const float* means2d,
-                           const int32_t* radii, const float* depths, const int32_t* cum_tiles, int32_t tile_size,
-                           int32_t tile_w, int32_t tile_h, int64_t* isect_ids, int32_t* flatten_ids,
-                           const b2s_tile_rows* rows, b2s_stream_t stream);
-B2S_API int64_t b2s_isect_sort_workspace_bytes(int64_t n_isects);
-B2S_API int b2s_isect_sort(int64_t n_isects, int32_t key_bits, const int64_t* isect_ids_in, const int32_t* flatten_ids_in,
-                           int64_t* isect_ids_out, int32_t* flatten_ids_out, void* workspace, int64_t workspace_bytes,
-                           b2s_stream_t stream);
-B2S_API int b2s_isect_offsets(int64_t n_isects, const int64_t* isect_ids_sorted, int32_t C, int32_t tile_w,
-                              int32_t tile_h, int32_t* offsets, b2s_stream_t stream);
-
-/* Depth-first binning -- the training path's replacement for fill + 64-bit sort + offset_encode.
- * Same sorted order as the reference (ascending (camera, tile, depth bits), ties by ascending flat
- * index) with ~3x less HBM traffic: Gaussians are depth-sorted once (M 32-bit keys), expanded to tile
- * intersections in that order, then stable-split by (camera, tile) with an LSD radix over
- * tile_bits+cam_bits bits of 8-byte records.  The 64-bit isect_ids are rebuilt on demand.
- *   b2s_isect_depth_keys : depth bits (0xFFFFFFFF on culled rows) + row ids   (stage 1 can emit both,
- *                          together with *total_isects, the data-dependent size the host must read)
- *   b2s_depth_order      : sorted_ids [M]  (32-bit LSD radix sort of the depth keys; enqueue it BEFORE
- *                          reading total_isects so the sort overlaps the host's wait)
- *   b2s_tile_bin         : fused scan + expansion in depth order, (camera,tile) radix sort, offsets:
- *                          tile_keys_sorted [I] (cam << tile_bits | tile; 16-bit when they fit, see
- *                          b2s_tile_key_bytes), flatten_ids [I], offsets [C*tile_h*tile_w]
- *   b2s_isect_ids_from_bins : isect_ids [I] = tile_key << 32 | bits(depths[flatten_ids])
- * Workspaces must be 256-byte aligned. */
-B2S_API int b2s_isect_depth_keys(int64_t M, const float* depths, const int32_t* radii, uint32_t* keys, int32_t* vals,
-                                 b2s_stream_t stream);
-B2S_API int64_t b2s_depth_order_workspace_bytes(int64_t M);
-B2S_API int b2s_depth_order(int64_t M, const uint32_t* depth_keys, const int32_t* row_ids, int32_t* sorted_ids,
-                            void* workspace, int64_t workspace_bytes, b2s_stream_t stream);
-B2S_API int32_t b2s_tile_key_bytes(int32_t C, int32_t tile_w, int32_t tile_h);
-B2S_API int64_t b2s_tile_bin_workspace_bytes(int64_t M, int64_t n_isects);
-B2S_API int b2s_tile_bin(int64_t M, int64_t N, const int64_t* camera_ids /* or NULL */, int64_t n_isects,
-                         const int32_t* sorted_ids, const float* means2d, const int32_t* radii, int32_t C,
-                         int32_t tile_size, int32_t tile_w, int32_t tile_h, void* tile_keys_sorted /* [I] x 4 bytes */,
-                         int32_t* flatten_ids, int32_t* offsets, void* workspace, int64_t workspace_bytes,
-                         const b2s_tile_rows* rows, b2s_stream_t stream);
-B2S_API int b2s_isect_ids_from_bins(int64_t n_isects, int32_t key_bytes, const void* tile_keys_sorted,
-                                    const int32_t* flatten_ids, const float* depths, int64_t* isect_ids,
-                                    b2s_stream_t stream);
-
-/* Two-level binning -- what `rasterization()` runs.  Compositing stops at the first few percent of a tile's
- * depth-sorted list once its pixels saturate, so materialising every (tile, Gaussian) intersection is mostly
- * wasted work.  Instead the depth-ordered rows are binned into COARSE bins of B2S_COARSE x B2S_COARSE tiles
- * (one record per (row, coarse bin) it overlaps, ~4x fewer records than tile intersections), and the compositing
- * kernels expand a tile's list on the fly: they walk the coarse bin's list in order and keep the records whose
- * tile mask covers the tile.  The kept records are exactly the tile's slice of the reference's sorted list
- * (same order: depth bits, ties by flat index), so renders and gradients are unchanged.
- *   record = mask_y(8) << 24 | mask_x(8) << 16 | coarse key(16), coarse key = (cam*bins_h + by)*bins_w + bx;
- *   mask_x bit i set <=> the row's tile rectangle covers tile column 8*bx + i (same for y).
- *   b2s_coarse_count : *total += number of (row, coarse bin) records        (stage 1 can emit this itself)
- *   b2s_coarse_bin   : bin_recs [n] / bin_ids [n] sorted by coarse key (stable: depth order inside a bin),
- *                      bin_offsets [C*bins_h*bins_w + 1].  bin_recs / bin_ids must be allocated with n rounded
- *                      up to a multiple of 4 entries and 16-byte aligned (the kernels read them 128 bits at a time).
- * Needs C * ceil(tile_w/8) * ceil(tile_h/8) <= 65536 (B2S_E_UNSUPPORTED otherwise). */
-#define B2S_COARSE 8
-B2S_API int b2s_coarse_count(int64_t M, const float* means2d, const int32_t* radii, int32_t tile_size, int32_t tile_w,
-                             int32_t tile_h, int64_t* total /* device, accumulated */, const b2s_tile_rows* rows,
-                             b2s_stream_t stream);
-B2S_API int64_t b2s_coarse_bin_workspace_bytes(int64_t M, int64_t n_records);
-B2S_API int b2s_coarse_bin(int64_t M, int64_t N, const int64_t* camera_ids /* or NULL */, int64_t n_records,
-                           const int32_t* sorted_ids, const float* means2d, const int32_t* radii, int32_t C,
-                           int32_t tile_size, int32_t tile_w, int32_t tile_h, uint32_t* bin_recs, int32_t* bin_ids,
-                           int32_t* bin_offsets, void* workspace, int64_t workspace_bytes, const b2s_tile_rows* rows,
-                           b2s_stream_t stream);
-
 /* Packed layout (gsplat `packed=True`): gather the visible rows `sel` (ascending dense indices c*N+n) of the
  * stage-1 outputs into nnz-row tensors (+ camera_ids / gaussian_ids), and scatter gradients back into
  * zero-filled dense tensors.  Any output pointer may be NULL (skipped). */
@@ -531,6 +461,9 @@ typedef struct {
     int32_t tile_row_lo, tile_row_hi;
 } b2s_composite_fwd_args;
 B2S_API int b2s_composite_fwd(const b2s_composite_fwd_args* a, b2s_stream_t stream);
+
+/* Backward.  The gradient tensors are accumulated into with atomics: zero them first (b2s_zero_fill).  The element offset
+ * of a gradient, row * width, is formed in 32 bits: rows * max(channels, 3) must be below 2^32 (the Python host checks it). */
 
 typedef struct {
     int32_t C, width, height, tile_size, tile_w, tile_h, channels;

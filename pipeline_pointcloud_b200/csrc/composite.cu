@@ -543,7 +543,7 @@ __global__ void __launch_bounds__(CTA, B2S_COMP_MINBLOCKS) composite_bwd_kernel(
                 const float ninth = warp_sum(v_op);
                 if (lane == 1) mine_v = ninth;
             }
-            if (slot_ptr) atomicAdd(slot_ptr + (uint64_t)g * slot_stride, mine_v);
+            if (slot_ptr) atomicAdd(slot_ptr + g * slot_stride, mine_v);    // 32-bit element offset: rows x width < 2^32 (include/b2s.h)
         } else if (V <= 16) {
             float r16[16];
 #pragma unroll
@@ -554,7 +554,7 @@ __global__ void __launch_bounds__(CTA, B2S_COMP_MINBLOCKS) composite_bwd_kernel(
             if (5 + CH < 16) r16[5 + CH] = v_op;
             if (ABS && 7 + CH < 16) { r16[6 + CH] = fabsf(v_x); r16[7 + CH] = fabsf(v_y); }
             const float mine_v = halving_reduce<16>(r16, lane);
-            if (slot_ptr) atomicAdd(slot_ptr + (uint64_t)g * slot_stride, mine_v);
+            if (slot_ptr) atomicAdd(slot_ptr + g * slot_stride, mine_v);    // 32-bit element offset: rows x width < 2^32 (include/b2s.h)
         } else {                               // wide feature vectors: one butterfly per value
             float v_ax = 0.f, v_ay = 0.f;
             if (ABS) { v_ax = warp_sum(fabsf(v_x)); v_ay = warp_sum(fabsf(v_y)); }

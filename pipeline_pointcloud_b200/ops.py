@@ -890,6 +890,8 @@ class _RasterizeToPixels(torch.autograd.Function):
         # one zero-filled slab for every atomically accumulated gradient (one fill instead of four)
         M = opacities.numel()
         widths = [2, 3, ch, 1] + ([2] if absgrad else [])
+        if M * max(widths) >= 2 ** 32:
+            raise B2SError(f"{M} rows x {max(widths)} gradient columns exceed the 32-bit element offsets of b2s_composite_bwd")
         if ctx.slab_pre is not None:
             pre, ctx.slab_pre = ctx.slab_pre, None       # (a second backward of the same graph gets a fresh slab)
             slab = take_prefilled(pre, M * sum(widths), dev)
