@@ -766,7 +766,7 @@ def bin_coarse(means2d: Tensor, radii: Tensor, depths: Tensor, tile_size: int, t
     # sort runs.  (A plain `totals.tolist()` after the sort's launch is ordered behind the sort and leaves the GPU idle for
     # as long as the host then needs to enqueue the next kernels.)
     totals_host = totals_ready = None
-    if totals is not None and counts is None:
+    if totals is not None and counts is None and os.environ.get("B2S_ASYNC_COUNTS", "1") != "0":
         totals_host, totals_ready = _async_to_host(totals)
     sorted_ids = torch.empty(max(M, 1), dtype=torch.int32, device=dev)
     # fused path: the sort's first pass computes the tile rectangles (coalesced), they ride through the passes as a second
@@ -788,8 +788,11 @@ def bin_coarse(means2d: Tensor, radii: Tensor, depths: Tensor, tile_size: int, t
     if counts is not None:             # (n_isects, n_records) already on the host (the multi-GPU stripe table)
         n_isects, n_records = int(counts[0]), int(counts[1])
     elif totals is not None:
-        totals_ready.synchronize()
-        slots = totals_host.tolist()               # 32 counter rows, added up on the host (no reduction kernel)
+        if totals_ready is not None:
+            totals_ready.synchronize()
+            slots = totals_host.tolist()           # 32 counter rows, added up on the host (no reduction kernel)
+        else:
+            slots = totals.tolist()                # B2S_ASYNC_COUNTS=0: ordered behind the depth sort (A/B)
         n_isects, n_visible, n_records = (int(sum(r[k] for r in slots)) for k in (0, 1, 2))
     else:
         n_isects, n_records = None, int(tot.item())
