@@ -11,6 +11,8 @@ options that are not implemented raise ``NotImplementedError`` instead of fallin
 """
 from __future__ import annotations
 
+import weakref
+
 import math
 from typing import Dict, Optional, Tuple
 
@@ -217,11 +219,20 @@ def _packed_meta(dense: "ops.LazyMeta", N: int, C: int, cols: Tensor, nnz: Optio
             cam, gid, r_p, m2_p, d_p, c_p, o_p, col_p, t_p = ops.pack_visible(radii, d_m2, dense["depths"], dense["conics"],
                                                                                dense["opacities"], cols, dense["tiles_per_gauss"], sel=sel)
             if d_m2.requires_grad:
+                # weak references: the hook lives on the autograd node of the dense tensor, which the packed tensor's own
+                # graph points to -- a closure holding either tensor strongly closes a cycle through the C++ graph, and
+                # every step's 340 MB of packed rows then stays alive until the cyclic collector runs (measured: reserved
+                # memory 3.5 -> 17 GB in 60 steps and a cudaMalloc stall of up to 200 ms every few steps)
+                packed_ref, dense_ref = weakref.ref(m2_p), weakref.ref(d_m2)
+
                 def hook(g):
-                    m2_p.grad = ops.gather_rows2(g, sel)
-                    ab = getattr(d_m2, "absgrad", None)
+                    m_p, d = packed_ref(), dense_ref()
+                    if m_p is None:
+                        return
+                    m_p.grad = ops.gather_rows2(g, sel)
+                    ab = getattr(d, "absgrad", None) if d is not None else None
                     if ab is not None:
-                        m2_p.absgrad = ops.gather_rows2(ab, sel)
+                        m_p.absgrad = ops.gather_rows2(ab, sel)
                 d_m2.register_hook(hook)
             cache.update(sel=sel, camera_ids=cam, gaussian_ids=gid, radii=r_p, means2d=m2_p, depths=d_p, conics=c_p,
                          opacities=o_p, tiles_per_gauss=t_p)
