@@ -160,10 +160,12 @@ def algorithmic_bytes(N, C, V, Vt, I, R, K, n_tiles, key_bits, sparse_bwd, V_any
         "isect_sort": I * 12 * 2 * p + I * 8,                        # LSD radix model; single-pass ideal = I*24
         "isect_offsets": I * 8 + 4 * n_tiles,
         "tile_bin": M * 20 + I * 8 + I * 4 + math.ceil((key_bits - 32) / 8) * I * 16 + I * 4 + 4 * n_tiles,
-        # depth sort of the rows: histogram read + 4 digit passes over (key, id) pairs, read + write each
-        "depth_order": M * 4 + 4 * M * 16,
-        # coarse binning: sorted ids + gathered (means2d, radius) in, records out; histogram; one digit pass; offsets
-        "coarse_bin": M * 4 + V * 12 + R * 8 + R * 4 + R * 16 + 4 * (n_tiles // 64 + 1),
+        # depth sort of the rows: the histogram kernel reads (key, id, radius, mean) and writes the packed rectangle by row;
+        # 3 digit passes over (key, id) pairs, read + write each; the last pass reads the pair and writes the id only
+        "depth_order": M * (4 + 4 + 4 + 8 + 4) + 3 * M * 16 + M * 12,
+        # coarse binning: sorted ids + one gathered rectangle word per row in, records out (digits counted on the way);
+        # one digit pass over the records; offsets from the scanned histogram
+        "coarse_bin": M * 8 + R * 8 + R * 16 + 4 * (n_tiles // 64 + 1),
         "composite_fwd": None,
         "composite_bwd": None,
     }
@@ -704,8 +706,8 @@ def main():
                         "stripe_balance_rounds": res["stripe_balance_rounds"]},
         "iters_per_s": res["iters_per_s"],
         "gpu_launches": res["launches"],
-        "gpu_launches_note": "kernels of libb2s.so launched inside the timed region (per step: project_fwd 1, depth sort 6, "
-                             "coarse binning 7, composite_fwd 1, composite_bwd 1, bwd_classify 1, sh_bwd 3 (dense [returns at once in "
+        "gpu_launches_note": "kernels of libb2s.so launched inside the timed region (per step: counter fill 1, project_fwd 1, depth sort 6, "
+                             "coarse binning 4, composite_fwd 1, gradient slab fill 1, composite_bwd 1, bwd_classify 1, sh_bwd 3 (dense [returns at once in "
                              "sparse mode], zero fill, list-driven), project_bwd 1; all hand-written, no library kernels)",
         "e2e": res.get("e2e"), "roofline": roofline, "stages": per_stage, "clocks": res["clocks"], "extras": extras,
     }
