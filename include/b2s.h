@@ -14,7 +14,8 @@
  *  - the caller owns every buffer, including scratch: query `*_workspace_bytes` first.
  *    The library never allocates device memory, never creates streams, never calls
  *    cudaSetDevice, and holds no global mutable state (re-entrant; forward is called on the
- *    Python thread, backward on torch's autograd thread).
+ *    Python thread, backward on torch's autograd thread).  The one exception is the file-level
+ *    converter at the end (b2s_convert_spz_to_ply / ConvertSpzToPly: host paths in, file out).
  *  - every call takes the CUDA stream explicitly (`cudaStream_t` passed as void*) and only
  *    enqueues work; nothing synchronises.
  *  - return value: 0 = ok, negative = B2S_E_* argument error, positive = cudaError_t.
