@@ -496,96 +496,6 @@ __global__ void __launch_bounds__(256) bwd_classify_kernel(const b2s_project_bwd
     }
 }
 
-// The same pass with 128-bit accesses: every thread takes FOUR CONSECUTIVE rows, so each per-row array is read (and each
-// small gradient zero-filled) with whole float4 / int4 words -- the stride-3 scalar accesses of the kernel above cost it
-// 30 % of the copy bandwidth (4.5 TB/s).  Needs N % 4 == 0 and 16-byte aligned tensors (the host entry checks; the scalar
-// kernel is the fallback).  The lists keep ascending row order: rank = rows before the thread's first live row.
-__device__ __forceinline__ unsigned nz4(const float4& v) {
-    return (unsigned)(v.x != 0.f) | ((unsigned)(v.y != 0.f) << 1) | ((unsigned)(v.z != 0.f) << 2) | ((unsigned)(v.w != 0.f) << 3);
-}
-// rows whose 3-vector (three consecutive floats of 12 = 3 float4) is non-zero, as a 4-bit mask
-__device__ __forceinline__ unsigned nz3x4(const float4& a, const float4& b, const float4& c) {
-    const unsigned r0 = (a.x != 0.f) | (a.y != 0.f) | (a.z != 0.f), r1 = (a.w != 0.f) | (b.x != 0.f) | (b.y != 0.f);
-    const unsigned r2 = (b.z != 0.f) | (b.w != 0.f) | (c.x != 0.f), r3 = (c.y != 0.f) | (c.z != 0.f) | (c.w != 0.f);
-    return r0 | (r1 << 1) | (r2 << 2) | (r3 << 3);
-}
-constexpr int CLSV_GROUPS = 4;   // 4 x (256 threads x 4 rows) = 4096 rows per CTA: the two list counters are hit once per CTA, and
-                                 // same-address atomics with a return value serialise in L2 (~14 ns each): at 1024 rows per CTA
-                                 // the 5 665 atomics per counter, not the 0.44 GB of traffic, set the kernel's time
-__global__ void __launch_bounds__(256) bwd_classify_vec_kernel(const b2s_project_bwd_args a, bool with_sh, BwdCounts* cnt,
-                                                               int32_t* __restrict__ list_geom, int32_t* __restrict__ list_sh) {
-    __shared__ unsigned s_g[CLSV_GROUPS * 8 + 1], s_s[CLSV_GROUPS * 8 + 1];
-    __shared__ unsigned s_base[2];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    unsigned mg[CLSV_GROUPS], ms[CLSV_GROUPS];                                    // 4-bit masks: live for geometry / SH colour
-    int ig[CLSV_GROUPS], is[CLSV_GROUPS];                                         // inclusive warp scans of the per-thread counts
-#pragma unroll
-    for (int k = 0; k < CLSV_GROUPS; ++k) {
-        const int64_t n0 = (((int64_t)blockIdx.x * CLSV_GROUPS + k) * 256 + threadIdx.x) * 4;   // first of four consecutive rows
-        mg[k] = 0u; ms[k] = 0u;
-        if (n0 < a.N) {
-            for (int c = 0; c < a.C; ++c) {
-                const int64_t i = (int64_t)c * a.N + n0;                          // multiple of 4
-                const int4 r = __ldg(reinterpret_cast<const int4*>(a.radii + i));
-                const unsigned vis = (unsigned)(r.x > 0) | ((unsigned)(r.y > 0) << 1) | ((unsigned)(r.z > 0) << 2) | ((unsigned)(r.w > 0) << 3);
-                if (vis == 0u) continue;
-                unsigned g = 0u;
-                if (a.v_means2d) {
-                    const float4 p = ldg_stream4(reinterpret_cast<const float4*>(a.v_means2d + 2 * i));
-                    const float4 q = ldg_stream4(reinterpret_cast<const float4*>(a.v_means2d + 2 * i) + 1);
-                    g |= (unsigned)((p.x != 0.f) | (p.y != 0.f)) | ((unsigned)((p.z != 0.f) | (p.w != 0.f)) << 1) |
-                         ((unsigned)((q.x != 0.f) | (q.y != 0.f)) << 2) | ((unsigned)((q.z != 0.f) | (q.w != 0.f)) << 3);
-                }
-                if (a.v_conics) {
-                    const float4* p = reinterpret_cast<const float4*>(a.v_conics + 3 * i);
-                    g |= nz3x4(ldg_stream4(p), ldg_stream4(p + 1), ldg_stream4(p + 2));
-                }
-                if (a.v_opacities_out) g |= nz4(ldg_stream4(reinterpret_cast<const float4*>(a.v_opacities_out + i)));
-                if (a.v_depths) g |= nz4(ldg_stream4(reinterpret_cast<const float4*>(a.v_depths + i)));
-                if (a.v_compensations) g |= nz4(ldg_stream4(reinterpret_cast<const float4*>(a.v_compensations + i)));
-                mg[k] |= g & vis;
-                if (with_sh && a.v_colors) {
-                    const float4* p = reinterpret_cast<const float4*>(a.v_colors + 3 * i);
-                    ms[k] |= nz3x4(ldg_stream4(p), ldg_stream4(p + 1), ldg_stream4(p + 2)) & vis;
-                }
-            }
-            const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-            float4* vm = reinterpret_cast<float4*>(a.v_means + 3 * n0);
-            stg_stream4(vm, z); stg_stream4(vm + 1, z); stg_stream4(vm + 2, z);
-            if (a.v_scales) { float4* vs = reinterpret_cast<float4*>(a.v_scales + 3 * n0); stg_stream4(vs, z); stg_stream4(vs + 1, z); stg_stream4(vs + 2, z); }
-            if (a.v_quats) { float4* vq = reinterpret_cast<float4*>(a.v_quats) + n0; stg_stream4(vq, z); stg_stream4(vq + 1, z); stg_stream4(vq + 2, z); stg_stream4(vq + 3, z); }
-            if (a.v_opacities) stg_stream4(reinterpret_cast<float4*>(a.v_opacities + n0), z);
-        }
-        // ascending row order inside the CTA = (group, thread, row of the thread)
-        ig[k] = __popc(mg[k]); is[k] = __popc(ms[k]);
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const int tg = __shfl_up_sync(FULL, ig[k], d), ts = __shfl_up_sync(FULL, is[k], d);
-            if (lane >= d) { ig[k] += tg; is[k] += ts; }
-        }
-        if (lane == 31) { s_g[k * 8 + warp] = (unsigned)ig[k]; s_s[k * 8 + warp] = (unsigned)is[k]; }
-    }
-    __syncthreads();
-    if (threadIdx.x < 2) {
-        unsigned* c = threadIdx.x == 0 ? s_g : s_s;
-        unsigned run = 0;
-        for (int j = 0; j < CLSV_GROUPS * 8; ++j) { const unsigned v = c[j]; c[j] = run; run += v; }
-        s_base[threadIdx.x] = run ? atomicAdd(threadIdx.x == 0 ? &cnt->n_geom : &cnt->n_sh, run) : 0u;
-    }
-    __syncthreads();
-#pragma unroll
-    for (int k = 0; k < CLSV_GROUPS; ++k) {
-        const int64_t n0 = (((int64_t)blockIdx.x * CLSV_GROUPS + k) * 256 + threadIdx.x) * 4;
-        unsigned og = s_base[0] + s_g[k * 8 + warp] + (unsigned)(ig[k] - __popc(mg[k]));
-        unsigned os = s_base[1] + s_s[k * 8 + warp] + (unsigned)(is[k] - __popc(ms[k]));
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            if ((mg[k] >> j) & 1u) list_geom[og++] = (int32_t)(n0 + j);
-            if ((ms[k] >> j) & 1u) list_sh[os++] = (int32_t)(n0 + j);
-        }
-    }
-}
-
 __global__ void __launch_bounds__(256) sh_zero_kernel(const b2s_project_bwd_args a, const BwdCounts* cnt) {
     if (!bwd_sparse(cnt->n_sh, a.N)) return;
     const int64_t total = a.N * a.sh_stride_k * 3;            // floats; the tensor is 16-byte aligned and a multiple of 4 here
@@ -960,12 +870,7 @@ extern "C" int b2s_project_bwd(const b2s_project_bwd_args* a, b2s_stream_t strea
     if (cnt && (a->stages == 0 || a->stages == 1 || a->stages == 3 || (a->stages == 2 && !has_sh))) {
         // first (or only) call of this backward: zero the small gradients, build the two lists
         B2S_CUDA(cudaMemsetAsync(cnt, 0, sizeof(BwdCounts), st));
-        const bool cls_vec = a->N % 4 == 0 && aligned16(a->radii) && aligned16(a->v_means2d) && aligned16(a->v_conics) &&
-                             aligned16(a->v_opacities_out) && aligned16(a->v_depths) && aligned16(a->v_compensations) &&
-                             aligned16(a->v_colors) && aligned16(a->v_means) && aligned16(a->v_scales) && aligned16(a->v_quats) &&
-                             aligned16(a->v_opacities) && getenv("B2S_CLASSIFY_SCALAR") == nullptr;
-        if (cls_vec) bwd_classify_vec_kernel<<<(unsigned)cdiv(a->N, 256 * 4 * CLSV_GROUPS), 256, 0, st>>>(*a, has_sh, cnt, list_geom, list_sh);
-        else bwd_classify_kernel<<<(unsigned)cdiv(a->N, 256 * CLS_ROWS), 256, 0, st>>>(*a, has_sh, cnt, list_geom, list_sh);
+        bwd_classify_kernel<<<(unsigned)cdiv(a->N, 256 * CLS_ROWS), 256, 0, st>>>(*a, has_sh, cnt, list_geom, list_sh);
         B2S_LAUNCH_CHECK();
     }
     if (sh) {
