@@ -73,8 +73,8 @@ def parse_args(argv: Optional[List[str]] = None) -> argparse.Namespace:
     a.init_scale = (0.1 if mcmc else 1.0) if a.init_scale is None else a.init_scale
     a.opacity_reg = (0.01 if mcmc else 0.0) if a.opacity_reg is None else a.opacity_reg
     a.scale_reg = (0.01 if mcmc else 0.0) if a.scale_reg is None else a.scale_reg
-    if a.batch_size != 1:
-        raise NotImplementedError("--batch-size 1 is what the reference passes; larger batches are not implemented")
+    if a.batch_size < 1:
+        raise ValueError("--batch-size must be >= 1")
     # gsplat scales every step-count option by steps_scaler (the reference passes 1 / n_gpus)
     s = a.steps_scaler
     a.max_steps = int(a.max_steps * s)
@@ -408,10 +408,10 @@ def optimizer_hparams(world: int, batch_size: int = 1):
     return {"lr_scale": math.sqrt(BS), "eps": 1e-15 / math.sqrt(BS), "betas": (1.0 - BS * (1.0 - 0.9), 1.0 - BS * (1.0 - 0.999))}
 
 
-def view_of_step(order: np.ndarray, step: int, rank: int, world: int) -> int:
+def view_of_step(order: np.ndarray, step: int, rank: int, world: int, batch_size: int = 1, slot: int = 0) -> int:
     """One permutation shared by every rank (same seed), strided by rank as ``DistributedSampler`` does: in one step
-    the ranks render ``world`` different views."""
-    return int(order[(step * world + rank) % len(order)])
+    the ranks render ``world * batch_size`` different views (``slot`` = position inside this rank's batch)."""
+    return int(order[((step * batch_size + slot) * world + rank) % len(order)])
 
 
 def train(a: argparse.Namespace, rank: int = 0, world: int = 1, local_rank: int = 0) -> str:
@@ -446,19 +446,23 @@ def train(a: argparse.Namespace, rank: int = 0, world: int = 1, local_rank: int 
     last_ckpt, t0, stats = "", time.time(), {}
     strategy.gid_offset = 0
     for step in range(a.max_steps):
-        e = (step * world) // len(order)                     # every rank crosses the epoch boundary at the same step
+        B = a.batch_size
+        e = (step * B * world) // len(order)                 # every rank crosses the epoch boundary at the same step
         if e != epoch:
             epoch, order = e, order_rng.permutation(len(data))
-        i = view_of_step(order, step, rank, world)
-        item = data.items[i]
-        W, H = item["size"]
-        target = data.image(i, dev)[None]
+        views = [view_of_step(order, step, rank, world, B, b) for b in range(B)]      # --batch-size views per rank and step
+        items = [data.items[i] for i in views]
+        W, H = items[0]["size"]
+        if any(tuple(it["size"]) != (W, H) for it in items):
+            raise ValueError("--batch-size > 1 needs images of one size (as upstream's dataloader does)")
+        target = torch.stack([data.image(i, dev) for i in views])
         deg = min(step // a.sh_degree_interval, a.sh_degree)
         colors = torch.cat([splats["sh0"], splats["shN"]], dim=1)
         render, alpha, meta = b2s.rasterization(
             splats["means"], splats["quats"], torch.exp(splats["scales"]), torch.sigmoid(splats["opacities"]), colors,
-            torch.from_numpy(item["viewmat"])[None].to(dev), torch.from_numpy(item["K"])[None].to(dev), W, H, sh_degree=deg,
-            packed=a.packed or world > 1, rasterize_mode="antialiased" if a.antialiased else "classic", distributed=world > 1)
+            torch.from_numpy(np.stack([it["viewmat"] for it in items])).to(dev), torch.from_numpy(np.stack([it["K"] for it in items])).to(dev),
+            W, H, sh_degree=deg, packed=a.packed or world > 1, rasterize_mode="antialiased" if a.antialiased else "classic",
+            distributed=world > 1)
         meta["means2d"].retain_grad()
         loss = l1_ssim_loss(render, target, a.ssim_lambda)
         if a.opacity_reg > 0.0:                         # mcmc preset: sparsity pressure on opacities and scales

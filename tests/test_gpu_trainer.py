@@ -65,6 +65,21 @@ def test_train_on_synthetic_colmap_dataset(tmp_path, capsys):
     assert export.export_ply(ck, ply) == N and len(export.read_ply(ply)) == 62
 
 
+def test_batch_size_two_trains(tmp_path, capsys):
+    """--batch-size 2: two views per step through one rasterization() call (C = 2), packed meta with camera ids feeding the
+    densification statistics; half the steps see the same number of views."""
+    data, out = str(tmp_path / "data"), str(tmp_path / "out")
+    make_dataset(data)
+    rc = main(["default", "--max_steps", "350", "--result-dir", out, "--data_factor", "1", "--steps_scaler", "1.0", "--disable_viewer",
+               "--packed", "--batch-size", "2", "--data-dir", data, "--log-every", "50", "--save-steps", "350"])
+    assert rc == 0
+    log = capsys.readouterr().out
+    losses = [float(l.split("loss")[1].split()[0]) for l in log.splitlines() if l.startswith("step")]
+    assert len(losses) > 4 and np.mean(losses[-2:]) < 0.7 * np.mean(losses[:2]), losses
+    ckpt = torch.load(os.path.join(out, "ckpts", "ckpt_349_rank0.pt"), map_location="cpu", weights_only=True)
+    assert all(torch.isfinite(v).all() for v in ckpt["splats"].values())
+
+
 def test_mcmc_strategy_trains_and_grows(tmp_path, capsys):
     data, out = str(tmp_path / "data"), str(tmp_path / "out")
     make_dataset(data)

@@ -22,8 +22,9 @@ def test_reference_command_line_is_accepted():
     m = parse_args(["mcmc", "--data-dir", "x"])              # gsplat's mcmc preset
     assert (m.init_opa, m.init_scale, m.opacity_reg, m.scale_reg, m.cap_max) == (0.5, 0.1, 0.01, 0.01, 1_000_000)
     assert (a.init_opa, a.init_scale, a.opacity_reg, a.scale_reg) == (0.1, 1.0, 0.0, 0.0)
-    with pytest.raises(NotImplementedError):
-        parse_args(["default", "--data-dir", "x", "--batch-size", "2"])
+    assert parse_args(["default", "--data-dir", "x", "--batch-size", "2"]).batch_size == 2
+    with pytest.raises(ValueError):
+        parse_args(["default", "--data-dir", "x", "--batch-size", "0"])
     with pytest.raises(SystemExit):
         parse_args(["default"])                      # --data-dir is required
 
@@ -208,6 +209,11 @@ def test_optimizer_scaling_and_view_order():
         views = [view_of_step(order, step, r, 4) for r in range(4)]
         assert len(set(views)) == 4
     assert sorted(view_of_step(order, s, r, 2) for s in range(5) for r in range(2)) == list(range(10))
+    # --batch-size 2 on 2 ranks: four different views per step; an epoch of 12 views takes three steps
+    order = np.random.default_rng(0).permutation(12)
+    per_step = [[view_of_step(order, s, r, 2, 2, b) for r in range(2) for b in range(2)] for s in range(3)]
+    assert all(len(set(v)) == 4 for v in per_step) and sorted(x for v in per_step for x in v) == list(range(12))
+    assert optimizer_hparams(2, 2) == optimizer_hparams(4)          # BS = batch size x world
 
 
 def _small_colmap(root):
