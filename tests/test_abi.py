@@ -55,3 +55,31 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 txt = open(os.path.join(dirpath, f)).read()
                 assert "import oracle" not in txt and "from oracle" not in txt, f
+
+
+def test_reference_codec_entry_point_is_exported(tmp_path):
+    """``ConvertSpzToPly`` -- the C symbol the reference's codec library exports (spz/src/spz_converter_api.cpp:7) -- is
+    exported under the same name and signature; its file and header checks run on the host (no GPU needed to fail)."""
+    import ctypes
+    from pipeline_pointcloud_b200 import _lib
+    h = _lib.lib()
+    fn = h.ConvertSpzToPly
+    fn.restype, fn.argtypes = ctypes.c_bool, [ctypes.c_char_p, ctypes.c_char_p]
+    out = str(tmp_path / "o.ply").encode()
+    assert fn(str(tmp_path / "missing.spz").encode(), out) is False
+    assert b"does not exist" in h.b2s_last_error()
+    bad = tmp_path / "bad.spz"
+    bad.write_bytes(b"this is not a gzip container")
+    assert h.b2s_convert_spz_to_ply(str(bad).encode(), out) == -1 and b"gzip" in h.b2s_last_error()
+    import gzip
+    import struct
+    wrong = tmp_path / "wrong.spz"                      # a gzip container whose payload is not an SPZ header
+    wrong.write_bytes(gzip.compress(struct.pack("<IIIBBBB", 0x12345678, 2, 1, 0, 12, 0, 0) + bytes(64)))
+    assert h.b2s_convert_spz_to_ply(str(wrong).encode(), out) == -1 and b"magic" in h.b2s_last_error()
+    short = tmp_path / "short.spz"                      # a valid header that promises more points than the payload holds
+    short.write_bytes(gzip.compress(struct.pack("<IIIBBBB", 0x5053474E, 2, 1000, 3, 12, 0, 0) + bytes(64)))
+    assert h.b2s_convert_spz_to_ply(str(short).encode(), out) == -1 and b"shorter" in h.b2s_last_error()
+    assert not os.path.exists(out.decode())
+    if not torch.cuda.is_available():                   # a well-formed file without a device: a CUDA error code, no crash
+        golden = os.path.join(ROOT, "tests", "golden", "splat_small.spz").encode()
+        assert h.b2s_convert_spz_to_ply(golden, out) > 0
