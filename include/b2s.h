@@ -538,6 +538,12 @@ B2S_API int b2s_spz_unpack(int64_t N, int32_t sh_dim, int32_t fractional_bits, c
                            const uint8_t* colors, const uint8_t* scales, const uint8_t* rotations, const uint8_t* sh,
                            float* ply_rows, b2s_stream_t stream);
 B2S_API int b2s_convert_spz_to_ply(const char* host_spz_path, const char* host_ply_path);
+/* The other branch of `splat_converter` (spz/src/main.cpp:22-28): loadSplatFromPly (load-spz.cc:568-750: the same header
+ * rules -- two fixed lines, `comment` lines skipped, float properties only, fields found by name, 1 .. 10 Mi vertices) +
+ * saveSpz.  The interleaved vertex table is uploaded as it lies in the file; a gather kernel splits it into the codec's
+ * arrays and b2s_spz_pack quantises them; gzip with the reference's parameters: the file is byte-identical to the
+ * reference binary's.  `pipeline_pointcloud_b200/splat_converter` is the reference's command line on top of both calls. */
+B2S_API int b2s_convert_ply_to_spz(const char* host_ply_path, const char* host_spz_path);
 B2S_API bool ConvertSpzToPly(const char* spzFilePath, const char* plyFilePath);
 
 #ifdef __cplusplus

@@ -187,6 +187,7 @@ SYMBOLS = {
     "b2s_spz_pack": (c_int32, [c_int64, c_int32] + [c_void_p] * 6 + [c_int32] + [c_void_p] * 6 + [c_void_p]),
     "b2s_spz_unpack": (c_int32, [c_int64, c_int32, c_int32] + [c_void_p] * 7 + [c_void_p]),
     "b2s_convert_spz_to_ply": (c_int32, [ctypes.c_char_p, ctypes.c_char_p]),
+    "b2s_convert_ply_to_spz": (c_int32, [ctypes.c_char_p, ctypes.c_char_p]),
     "b2s_composite_fwd": (c_int32, [POINTER(CompositeFwdArgs), c_void_p]),
     "b2s_composite_bwd": (c_int32, [POINTER(CompositeBwdArgs), c_void_p]),
 }

@@ -122,6 +122,169 @@ extern "C" int b2s_convert_spz_to_ply(const char* spz_path, const char* ply_path
     return 0;
 }
 
+// ----------------------------------------------------------------------------------------------------------
+// PLY -> SPZ: the `.ply` branch of the reference's converter (spz/src/main.cpp:22-28) = loadSplatFromPly
+// (load-spz.cc:568-750) + saveSpz (:492-500, :546-558: packGaussians, serialise, gzip).  The host parses the header exactly
+// as the reference does (the same two fixed lines, `comment` lines skipped, float properties only, fields found by name),
+// uploads the vertex table as it lies in the file, and the GPU does the rest: a gather kernel splits the interleaved rows
+// into the codec's arrays (the [N,C,S] -> [N,S,C] turn of the SH coefficients included, :742-747) and spz_pack_kernel
+// quantises them.  The gzip container is written with the reference's parameters (:189-191), so the file is byte-identical.
+// ----------------------------------------------------------------------------------------------------------
+namespace b2s {
+// one thread per (row, slot): slots = x y z | scale_0..2 | rot_0..3 (w first) | opacity | f_dc_0..2 | sh[j][c]
+__global__ void __launch_bounds__(256) ply_gather_kernel(int64_t N, int F, int sh_dim, const float* __restrict__ table,
+                                                         const int* __restrict__ cols, float* __restrict__ means,
+                                                         float* __restrict__ scales, float* __restrict__ quats,
+                                                         float* __restrict__ opac, float* __restrict__ sh0, float* __restrict__ shN) {
+    const int S = 14 + 3 * sh_dim;
+    const int64_t total = N * S;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t i = e / S;
+        const int s = (int)(e - i * S);
+        const float v = table[i * F + cols[s]];
+        if (s < 3) means[3 * i + s] = v;
+        else if (s < 6) scales[3 * i + (s - 3)] = v;
+        else if (s < 10) quats[4 * i + (s - 6)] = v;
+        else if (s == 10) opac[i] = v;
+        else if (s < 14) sh0[3 * i + (s - 11)] = v;
+        else shN[i * (3 * sh_dim) + (s - 14)] = v;
+    }
+}
+}  // namespace b2s
+
+namespace {
+
+bool next_line(const std::vector<uint8_t>& buf, size_t* pos, std::string* line) {      // std::getline on the header
+    if (*pos >= buf.size()) return false;
+    size_t e = *pos;
+    while (e < buf.size() && buf[e] != '\n') ++e;
+    line->assign(reinterpret_cast<const char*>(buf.data()) + *pos, e - *pos);
+    *pos = e < buf.size() ? e + 1 : e;
+    return true;
+}
+
+bool gzip_to(const std::vector<uint8_t>& in, std::vector<uint8_t>* out) {               // load-spz.cc:182-211
+    z_stream s = {};
+    if (deflateInit2(&s, Z_DEFAULT_COMPRESSION, Z_DEFLATED, 16 + MAX_WBITS, 9, Z_DEFAULT_STRATEGY) != Z_OK) return false;
+    out->resize(deflateBound(&s, (uLong)in.size()) + 64);
+    s.next_in = const_cast<Bytef*>(in.data());
+    s.avail_in = (uInt)in.size();
+    s.next_out = out->data();
+    s.avail_out = (uInt)out->size();
+    const int r = deflate(&s, Z_FINISH);
+    out->resize(s.total_out);
+    deflateEnd(&s);
+    return r == Z_STREAM_END;
+}
+
+}  // namespace
+
+extern "C" int b2s_convert_ply_to_spz(const char* ply_path, const char* spz_path) {
+    B2S_REQUIRE(ply_path && spz_path, "null path");
+    std::vector<uint8_t> file;
+    if (!read_file(ply_path, &file)) {
+        b2s::set_error("%s: unable to open: %s", __func__, ply_path);
+        return B2S_E_BADARG;
+    }
+    size_t pos = 0;
+    std::string line;
+    B2S_REQUIRE(next_line(file, &pos, &line) && line == "ply", "not a .ply file");                                   // :582
+    B2S_REQUIRE(next_line(file, &pos, &line) && line == "format binary_little_endian 1.0", "unsupported .ply format");  // :589
+    long long n = -1;
+    while (next_line(file, &pos, &line)) {                                                                           // :597-615
+        if (line.compare(0, 7, "comment") == 0) continue;
+        if (line.compare(0, 15, "element vertex ") == 0) {
+            char* end = nullptr;
+            n = strtoll(line.c_str() + 14, &end, 10);
+            if (end == line.c_str() + 14) n = -1;
+            break;
+        }
+    }
+    B2S_REQUIRE(n > 0 && n <= 10ll * 1024 * 1024, "invalid vertex count");                                            // :617
+    std::vector<std::string> names;
+    for (;;) {                                                                                                       // :627-645
+        B2S_REQUIRE(next_line(file, &pos, &line), "header without end_header");
+        if (line.compare(0, 7, "comment") == 0) continue;
+        if (line == "end_header") break;
+        B2S_REQUIRE(line.compare(0, 15, "property float ") == 0, "unsupported property data type");
+        names.push_back(line.substr(15));
+    }
+    const int F = (int)names.size();
+    auto index = [&](const std::string& name) {
+        for (int i = F - 1; i >= 0; --i)          // a repeated name keeps its last index, as the reference's map does
+            if (names[i] == name) return i;
+        return -1;
+    };
+    std::vector<int> cols;
+    for (const char* k : {"x", "y", "z", "scale_0", "scale_1", "scale_2", "rot_0", "rot_1", "rot_2", "rot_3", "opacity", "f_dc_0",
+                          "f_dc_1", "f_dc_2"}) {
+        const int c = index(k);
+        if (c < 0) {
+            b2s::set_error("%s: missing field: %s", __func__, k);                                                    // :651
+            return B2S_E_BADARG;
+        }
+        cols.push_back(c);
+    }
+    std::vector<int> sh_idx;                                                                                         // :692-699
+    for (int i = 0; i < 45; ++i) {
+        const int c = index("f_rest_" + std::to_string(i));
+        if (c < 0) break;
+        sh_idx.push_back(c);
+    }
+    const int sh_dim = (int)sh_idx.size() / 3;
+    // the reference goes on with degreeForDim(shDim) and then fails its size check in saveSpz unless shDim is 0, 3, 8 or 15
+    B2S_REQUIRE((sh_dim == 0 || sh_dim == 3 || sh_dim == 8 || sh_dim == 15) && (int)sh_idx.size() == 3 * sh_dim,
+                "f_rest_* must hold 0, 9, 24 or 45 coefficients");
+    for (int j = 0; j < sh_dim; ++j)
+        for (int c = 0; c < 3; ++c) cols.push_back(sh_idx[c * sh_dim + j]);                                          // [N,C,S] -> [N,S,C]
+    const size_t table_bytes = (size_t)n * F * sizeof(float);
+    B2S_REQUIRE(file.size() - pos >= table_bytes, "unable to load data (file shorter than its header says)");        // :703
+    static const int kDegree[16] = {0, 0, 0, 1, 0, 0, 0, 0, 2, 0, 0, 0, 0, 0, 0, 3};
+
+    const int S = 14 + 3 * sh_dim;
+    const size_t packed_bytes = (size_t)n * (9 + 1 + 3 + 3 + 3 + 3 * sh_dim);
+    std::vector<uint8_t> payload(sizeof(SpzHeader) + packed_bytes);
+    {
+        DeviceBuffer d_table, d_cols, d_arrays, d_packed;
+        B2S_CUDA(cudaMalloc(&d_table.p, table_bytes));
+        B2S_CUDA(cudaMalloc(&d_cols.p, cols.size() * sizeof(int)));
+        B2S_CUDA(cudaMalloc(&d_arrays.p, (size_t)n * S * sizeof(float)));
+        B2S_CUDA(cudaMalloc(&d_packed.p, packed_bytes));
+        B2S_CUDA(cudaMemcpy(d_table.p, file.data() + pos, table_bytes, cudaMemcpyHostToDevice));
+        B2S_CUDA(cudaMemcpy(d_cols.p, cols.data(), cols.size() * sizeof(int), cudaMemcpyHostToDevice));
+        float* a = static_cast<float*>(d_arrays.p);
+        float *means = a, *scales = means + 3 * n, *quats = scales + 3 * n, *opac = quats + 4 * n, *sh0 = opac + n, *shN = sh0 + 3 * n;
+        const int64_t total = n * S;
+        b2s::ply_gather_kernel<<<(unsigned)std::min<int64_t>(b2s::cdiv(total, 256), 148 * 64), 256>>>(
+            n, F, sh_dim, static_cast<const float*>(d_table.p), static_cast<const int*>(d_cols.p), means, scales, quats, opac, sh0, shN);
+        B2S_LAUNCH_CHECK();
+        uint8_t* b = static_cast<uint8_t*>(d_packed.p);                                    // serialised order, :448-453
+        uint8_t *o_pos = b, *o_alp = o_pos + 9 * n, *o_col = o_alp + n, *o_sca = o_col + 3 * n, *o_rot = o_sca + 3 * n, *o_sh = o_rot + 3 * n;
+        const int rc = b2s_spz_pack(n, sh_dim, means, scales, quats, opac, sh0, sh_dim ? shN : nullptr, sh_dim, o_pos, o_alp, o_col,
+                                    o_sca, o_rot, sh_dim ? o_sh : nullptr, nullptr);
+        if (rc != 0) return rc;
+        B2S_CUDA(cudaMemcpy(payload.data() + sizeof(SpzHeader), d_packed.p, packed_bytes, cudaMemcpyDeviceToHost));
+    }
+    SpzHeader h = {0x5053474eu, 2u, (uint32_t)n, (uint8_t)kDegree[sh_dim], 12, 0, 0};                                 // :131-139, :443-447
+    memcpy(payload.data(), &h, sizeof(h));
+    std::vector<uint8_t> gz;
+    if (!gzip_to(payload, &gz)) {
+        b2s::set_error("%s: gzip failed", __func__);
+        return B2S_E_BADARG;
+    }
+    FILE* f = fopen(spz_path, "wb");
+    if (!f) {
+        b2s::set_error("%s: unable to open for writing: %s", __func__, spz_path);
+        return B2S_E_BADARG;
+    }
+    const bool ok = fwrite(gz.data(), 1, gz.size(), f) == gz.size();
+    if (fclose(f) != 0 || !ok) {
+        b2s::set_error("%s: failed to write to: %s", __func__, spz_path);
+        return B2S_E_BADARG;
+    }
+    return 0;
+}
+
 // The reference's own exported name and signature (spz_converter_api.cpp:7): true on success, message on stderr otherwise.
 extern "C" B2S_API bool ConvertSpzToPly(const char* spzFilePath, const char* plyFilePath) {
     if (b2s_convert_spz_to_ply(spzFilePath, plyFilePath) == 0) return true;

@@ -187,6 +187,15 @@ def convert_spz_to_ply(spz_path: str, ply_path: str = None) -> str:
     return out
 
 
+def convert_ply_to_spz_native(ply_path: str, spz_path: str = None) -> str:
+    """`splat_converter splat.ply` through the library's native file-level entry point (host header parse + gzip in C++,
+    gather + quantisation on the GPU, csrc/spz_file.cu); ``convert_ply_to_spz`` is the same conversion driven from Python."""
+    from . import _lib as L
+    out = spz_path or os.path.splitext(ply_path)[0] + ".spz"
+    L.check(L.lib().b2s_convert_ply_to_spz(os.fsencode(ply_path), os.fsencode(out)), "b2s_convert_ply_to_spz")
+    return out
+
+
 def main(argv=None) -> int:
     argv = list(sys.argv[1:] if argv is None else argv)
     if len(argv) == 1 and argv[0].endswith(".ply"):          # the Spz-Export component's command line

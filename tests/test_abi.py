@@ -83,3 +83,40 @@ def test_reference_codec_entry_point_is_exported(tmp_path):
     if not torch.cuda.is_available():                   # a well-formed file without a device: a CUDA error code, no crash
         golden = os.path.join(ROOT, "tests", "golden", "splat_small.spz").encode()
         assert h.b2s_convert_spz_to_ply(golden, out) > 0
+
+
+def test_native_ply_reader_follows_the_reference_header_rules(tmp_path):
+    """b2s_convert_ply_to_spz parses the header as loadSplatFromPly does (load-spz.cc:581-645): every rejection happens on the
+    host, before any CUDA call."""
+    from pipeline_pointcloud_b200 import _lib
+    h = _lib.lib()
+    out = str(tmp_path / "o.spz").encode()
+    fields = ["x", "y", "z", "nx", "ny", "nz", "f_dc_0", "f_dc_1", "f_dc_2", "opacity", "scale_0", "scale_1", "scale_2",
+              "rot_0", "rot_1", "rot_2", "rot_3"]
+
+    def ply(first="ply", fmt="format binary_little_endian 1.0", n=2, props=None, body=None, extra=()):
+        props = fields if props is None else props
+        head = [first, fmt, *extra, f"element vertex {n}", *[f"property float {k}" for k in props], "end_header"]
+        data = bytes(4 * max(n, 0) * len(props)) if body is None else body
+        path = tmp_path / "t.ply"
+        path.write_bytes(("\n".join(head) + "\n").encode() + data)
+        return str(path).encode()
+
+    def rejected(path, needle):
+        assert h.b2s_convert_ply_to_spz(path, out) == -1, needle
+        assert needle in h.b2s_last_error(), h.b2s_last_error()
+
+    rejected(str(tmp_path / "missing.ply").encode(), b"unable to open")
+    rejected(ply(first="plx"), b"not a .ply file")
+    rejected(ply(fmt="format ascii 1.0"), b"unsupported .ply format")
+    rejected(ply(n=0), b"invalid vertex count")
+    rejected(ply(n=10 * 1024 * 1024 + 1, body=b""), b"invalid vertex count")
+    rejected(ply(props=[k for k in fields if k != "rot_3"]), b"missing field: rot_3")
+    rejected(ply(props=fields + ["f_rest_0", "f_rest_1"]), b"f_rest_*")
+    rejected(ply(body=bytes(8)), b"shorter")
+    bad = tmp_path / "u.ply"
+    bad.write_bytes(b"ply\nformat binary_little_endian 1.0\nelement vertex 1\nproperty uchar red\nend_header\n\x00")
+    rejected(str(bad).encode(), b"unsupported property data type")
+    assert not os.path.exists(out.decode())
+    if not torch.cuda.is_available():       # a well-formed file (with a comment line, as the reference tolerates): CUDA error, no crash
+        assert h.b2s_convert_ply_to_spz(ply(extra=("comment made by a test",)), out) > 0

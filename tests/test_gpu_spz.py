@@ -91,3 +91,54 @@ def test_cuda_spz_to_ply_matches_compiled_reference(tmp_path):
     assert fn(spz.encode(), str(tmp_path / "again.ply").encode()) is True
     assert open(str(tmp_path / "again.ply"), "rb").read() == mine
     assert fn(str(tmp_path / "missing.spz").encode(), str(tmp_path / "no.ply").encode()) is False
+
+
+# ---- the native file-level PLY -> SPZ entry point and the converter command line (csrc/spz_file.cu, splat_converter_main.cpp) ----
+CONVERTER = os.path.join(os.path.dirname(HERE), "pipeline_pointcloud_b200", "splat_converter")
+
+
+def test_native_ply_to_spz_matches_reference_golden_file(tmp_path):
+    out = str(tmp_path / "x.spz")
+    assert export.convert_ply_to_spz_native(os.path.join(HERE, "golden", "splat_small.ply"), out) == out
+    assert open(out, "rb").read() == open(os.path.join(HERE, "golden", "splat_small.spz"), "rb").read()
+
+
+@pytest.mark.parametrize("rows,n", [(0, 1000), (3, 70001), (8, 4097), (15, 120000)])
+def test_native_ply_to_spz_equals_python_path(tmp_path, rows, n):
+    sp = random_splats(n, rows, seed=40 + rows)
+    ply = str(tmp_path / "splat.ply")
+    export.write_ply(ply, export.ply_channels(sp))
+    export.convert_ply_to_spz(ply)                                # Python-driven: read_ply + b2s_spz_pack + zlib
+    via_python = open(str(tmp_path / "splat.spz"), "rb").read()
+    export.convert_ply_to_spz_native(ply, str(tmp_path / "native.spz"))
+    assert open(str(tmp_path / "native.spz"), "rb").read() == via_python
+
+
+@pytest.mark.skipif(not os.path.exists(CONVERTER), reason="pipeline_pointcloud_b200/splat_converter not built")
+def test_converter_command_line_both_directions(tmp_path):
+    """`splat_converter splat.ply` (what the Spz-Export component runs, main.py:1532-1545) and `splat_converter splat.spz`:
+    same files, same message, same exit codes as the reference binary."""
+    sp = random_splats(50000, 15, seed=61)
+    ply = str(tmp_path / "splat.ply")
+    export.write_ply(ply, export.ply_channels(sp))
+    r = subprocess.run([CONVERTER, ply], capture_output=True, text=True)
+    assert r.returncode == 0 and r.stdout.strip() == f'Converted {ply} to "{tmp_path / "splat.spz"}"', (r.stdout, r.stderr)
+    mine_spz = open(str(tmp_path / "splat.spz"), "rb").read()
+    os.rename(ply, str(tmp_path / "orig.ply"))
+    r = subprocess.run([CONVERTER, str(tmp_path / "splat.spz")], capture_output=True, text=True)
+    assert r.returncode == 0 and os.path.exists(ply)
+    mine_ply = open(ply, "rb").read()
+    assert subprocess.run([CONVERTER, str(tmp_path / "nothing.ply")], capture_output=True).returncode == 1
+    assert subprocess.run([CONVERTER, str(tmp_path / "orig.ply"), "extra"], capture_output=True).returncode == 1
+    other = tmp_path / "scene.obj"
+    other.write_text("x")
+    assert subprocess.run([CONVERTER, str(other)], capture_output=True).returncode == 1
+    if os.path.exists(REF_BIN):                                   # the reference binary on the same inputs
+        ref_dir = tmp_path / "ref"
+        ref_dir.mkdir()
+        os.link(str(tmp_path / "orig.ply"), str(ref_dir / "splat.ply"))
+        r = subprocess.run([REF_BIN, str(ref_dir / "splat.ply")], capture_output=True, text=True)
+        assert r.returncode == 0 and open(str(ref_dir / "splat.spz"), "rb").read() == mine_spz
+        os.remove(str(ref_dir / "splat.ply"))
+        subprocess.run([REF_BIN, str(ref_dir / "splat.spz")], check=True, capture_output=True)
+        assert open(str(ref_dir / "splat.ply"), "rb").read() == mine_ply
