@@ -769,9 +769,9 @@ def bin_coarse(means2d: Tensor, radii: Tensor, depths: Tensor, tile_size: int, t
     if totals is not None and counts is None and os.environ.get("B2S_ASYNC_COUNTS", "1") != "0":
         totals_host, totals_ready = _async_to_host(totals)
     sorted_ids = torch.empty(max(M, 1), dtype=torch.int32, device=dev)
-    # fused path: the sort's first pass computes the tile rectangles (coalesced), they ride through the passes as a second
-    # payload and come out in depth order; the expansion is one kernel (B2S_BINNING_FUSED=0: the unfused reference kernels,
-    # same outputs bit for bit; they also serve tile grids beyond 255 x 255)
+    # fused path: the sort's histogram kernel (a streaming pass over the rows in row order) also stores every row's packed tile
+    # rectangle by row; the one-kernel expansion gathers one word per depth-ordered row (B2S_BINNING_FUSED=0: the unfused
+    # reference kernels, same outputs bit for bit; they also serve tile grids beyond 255 x 255)
     fused = os.environ.get("B2S_BINNING_FUSED", "1") != "0" and tile_width <= 255 and tile_height <= 255
     if fused:
         rects = torch.empty(max(M, 1), dtype=torch.int32, device=dev)
