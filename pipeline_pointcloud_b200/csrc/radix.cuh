@@ -5,12 +5,16 @@
 // Per digit pass, a CTA owns a tile of 256 threads x ITEMS consecutive elements:
 //   1. warp-striped coalesced load; each warp owns a contiguous slice, so (warp, item, lane) order is
 //      memory order and ranking in that order keeps the sort stable;
-//   2. per-warp ranking with `__match_any_sync`: lanes holding the same digit find each other, the group
-//      leader bumps the warp's digit counter in shared memory, rank = counter + popc(lower peers);
-//   3. per-digit exclusive scan across the 8 warps (thread d <-> digit d);
-//   4. decoupled look-back across tiles, one thread per digit (256 chains in parallel, coalesced status rows),
-//      tile ids handed out dynamically so predecessors are always resident;
-//   5. local reorder through shared memory so the global scatter writes runs of equal digits contiguously.
+//   2. per-warp ranking: lanes holding the same digit find each other through a shared-memory mask word they all
+//      `atomicOr` their lane bit into (B2S_RADIX_RANK: `match.any` and per-bit ballots are the measured alternatives),
+//      the group leader bumps the warp's digit counter, rank = counter + popc(lower peers);
+//   3. per-digit exclusive scan across the 8 warps (thread d <-> digit d); the tile's aggregate is published at once;
+//   4. local reorder through shared memory (it needs nothing from other tiles and frees the item registers), then the
+//      decoupled look-back across tiles, one thread per digit (256 chains in parallel, coalesced status rows), tile ids
+//      handed out dynamically so predecessors are always resident;
+//   5. coalesced scatter: runs of equal digits leave contiguously.  The last pass may hand each element to an epilogue
+//      instead (the depth sort stores only the ids); the histogram kernel may carry a hook that sees every input element
+//      (the depth sort derives the rows' tile rectangles there).
 // Replaces cub::DeviceRadixSort on the training path (depth sort of Gaussians, (camera,tile) split of the
 // intersections) and in the reference-algorithm path (64-bit isect keys).
 #pragma once
